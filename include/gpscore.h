@@ -1,0 +1,122 @@
+/*
+ * gpscore.h — C-ABI of libgpscore.so: the GP scoring-rule objective+gradient hot path on B200.
+ *
+ * The reference (polarlightman/Scoring-rules-for-Gaussian-process-regression-…) exposes no
+ * FFI or plugin interface: the path is loop-body code inside four Python scripts
+ * (SURVEY.md §8b).  This header is the boundary a maintainer binds with ctypes
+ * (INTEGRATION.md shows the stub); every entry point cites the reference statements it
+ * replaces.  Abbreviations: KF = kin40k-FULL-compare.py, K20 = KIN40K-COMPARE-ALL-FITC-20.py,
+ * SF/SC = the SIMPLE scripts, CP = contour-plot.R.
+ *
+ * Conventions
+ *  - plain C types only; no torch types cross this boundary.
+ *  - hyper-parameters are passed as theta = [a, b_1..b_D, c] with a = log sf^2 (KF:9),
+ *    b_d = log l_d (KF:10-12, NOT log l^2) and c = log sn^2 (KF:239).  theta, inducing inputs,
+ *    objective values and gradients are HOST pointers (they are a few doubles).
+ *  - large arrays (X, y, test inputs, predictions, matrices of the element-wise entry points)
+ *    are "UVA pointers": device memory or host memory, copied with cudaMemcpyDefault.
+ *    All matrices are row-major float64.
+ *  - every function returns 0 on success or a GPS_E* code; gps_last_error() gives the text.
+ *    GPS_ENOTPD reports "matrix not positive definite" so that a host wrapper can raise
+ *    RuntimeError the way torch.potrf did (the convention KF:726 / K20:784 rely on).
+ *  - one host thread drives a context; work is enqueued on the context's stream and the
+ *    call synchronises before returning host scalars.
+ *  - there is no CPU fallback: gps_create fails with GPS_ENODEVICE without a CUDA device.
+ */
+#ifndef GPSCORE_H
+#define GPSCORE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct gps_ctx gps_ctx;
+
+enum { GPS_OK = 0, GPS_EINVAL = 1, GPS_ECUDA = 2, GPS_ENOTPD = 3, GPS_ENODEVICE = 4, GPS_ENOMEM = 5,
+       GPS_ESTATE = 6 };
+
+/* score selector: LOO-CRPS (KF:245), LOO log score (KF:424), negative log marginal
+ * likelihood (KF:331-334) */
+enum { GPS_CRPS = 0, GPS_LOGS = 1, GPS_NLML = 2 };
+
+/* ---- context ------------------------------------------------------------------------------- */
+int gps_create(int device, gps_ctx** out);
+void gps_destroy(gps_ctx* ctx);
+const char* gps_last_error(gps_ctx* ctx);
+/* version string of the library ("gpscore-b200 <n>") */
+const char* gps_version(void);
+/* number of kernels this context has launched since creation (bench.py's gpu_launches) */
+int64_t gps_launch_count(gps_ctx* ctx);
+/* device milliseconds the dominant dense kernels (DMMA tile GEMM) spent inside the last
+ * gps_full_eval, measured with CUDA events on the context's stream, and their launch count */
+int gps_last_gemm_ms(gps_ctx* ctx, double* ms, int64_t* launches);
+
+/* ---- training data (replaces train_x / train_y of KF:208-209, K20:198-199) ----------------- */
+/* X[N,D], y[N] row-major UVA pointers; copied into context-owned, tile-padded buffers and all
+ * N x N workspaces for the full GP are (re)allocated lazily on the first full-GP call. */
+int gps_set_data(gps_ctx* ctx, const double* X, const double* y, int64_t N, int D);
+
+/* ---- full GP: objective + gradient (replaces KF:239-252, KF:329-339, KF:416-428) ----------- */
+/* theta[D+2] host; obj[1] host; grad[D+2] host (may be NULL: objective only). */
+int gps_full_eval(gps_ctx* ctx, const double* theta, int score, double* obj, double* grad);
+/* LOO predictive mean / variance of the last CRPS or LOGS evaluation (mean_term, cov_term of
+ * KF:243-244); UVA pointers of length N. */
+int gps_full_loo(gps_ctx* ctx, double* loo_mean, double* loo_var);
+/* predictive mean and the diagonal of the predictive covariance at T test inputs
+ * (replaces KF:267-273 → cal_mean_and_cov KF:121-126; only the diagonal is formed). */
+int gps_full_predict(gps_ctx* ctx, const double* theta, const double* Xs, int64_t T, double* mean,
+                     double* var);
+
+/* ---- FITC: objective + gradient (replaces K20:222-236, K20:329-344, K20:434-452) ----------- */
+/* Woodbury O(N M^2) evaluation of the dense big_Q path, in three row passes.  U[M,D] host.
+ * grad_theta[D+2], grad_U[M*D] host.  For row-sharded multi-GPU runs the three passes are also
+ * exposed separately so the host can all-reduce the packed accumulators between them
+ * (acc buffers are DEVICE pointers owned by the caller; their lengths come from
+ * gps_fitc_acc_len).  world_n is the global number of rows (the mean in KF:67 divides by it). */
+int gps_fitc_eval(gps_ctx* ctx, const double* theta, const double* U, int M, double jitter, int score,
+                  double* obj, double* grad_theta, double* grad_U);
+int gps_fitc_acc_len(int M, int D, int64_t* len1, int64_t* len2, int64_t* len3);
+int gps_fitc_begin(gps_ctx* ctx, const double* theta, const double* U, int M, double jitter, int score,
+                   int64_t world_n);
+int gps_fitc_pass1(gps_ctx* ctx, double* acc1);           /* acc1 = [C - I (M*M) | v_y (M)]          */
+int gps_fitc_pass2(gps_ctx* ctx, const double* acc1, double* acc2); /* acc2 = [R (M*M) | beta_bar (M) | obj] */
+int gps_fitc_pass3(gps_ctx* ctx, const double* acc2, double* acc3); /* acc3 = [S (M*M) | sum lam_bar | g_a | g_b (D) | g_U (M*D)] */
+int gps_fitc_finish(gps_ctx* ctx, const double* acc2, const double* acc3, double* obj, double* grad_theta,
+                    double* grad_U);
+int gps_fitc_loo(gps_ctx* ctx, double* loo_mean, double* loo_var);
+/* replaces K20:270-277 → spgp_cal_mean_and_cov K20:76-83 (diagonal only). Needs a finished
+ * gps_fitc_eval / pass1+pass2 at the same theta, U (uses its L_A, L_C, beta). */
+int gps_fitc_predict(gps_ctx* ctx, const double* Xs, int64_t T, double* mean, double* var);
+
+/* ---- scoring of predictions (replaces KF:276-292: mse, SMSE KF:128-134, logs KF:52-57,
+ *      crps KF:60-68, trivial_loss KF:110-119, coverage KF:288-292) ---------------------------- */
+/* mean, var, y: UVA length n.  ytrain_mean / ytrain_var: mean and UNBIASED variance of the
+ * training targets (KF:113-114).  out[6] host = {mse, smse, logs, crps, msll, coverage}. */
+int gps_test_metrics(gps_ctx* ctx, const double* mean, const double* var, const double* y, int64_t n,
+                     double ytrain_mean, double ytrain_var, double* out);
+
+/* ---- element-wise twins of the reference helpers (same argument meaning) -------------------- */
+/* ARD(x, xp, a, b) KF:7-23: out[n,m] = e^a exp(-0.5 sum_d ((x_d - xp_d)/e^{b_d})^2).
+ * b host, nb = 1 (broadcast, KF:8) or D. */
+int gps_ard(gps_ctx* ctx, const double* x, int64_t n, const double* xp, int64_t m, int D, double a,
+            const double* b, int nb, double* out);
+/* chol_solve(B, A) KF:25-29: out[n,nrhs] = A^-1 B for SPD A[n,n]. */
+int gps_chol_solve(gps_ctx* ctx, const double* B, const double* A, int64_t n, int64_t nrhs, double* out);
+/* crps(m, c, y) KF:60-68 / logs(m, c, y) KF:52-57: c is the VARIANCE. which = GPS_CRPS | GPS_LOGS. */
+int gps_score(gps_ctx* ctx, const double* m, const double* c, const double* y, int64_t n, int which,
+              double* out);
+
+/* ---- hyper-parameter grid sweep (replaces CP:109-144: cal_NLML CP:68-73, cal_m_crps CP:43-53,
+ *      wrong_cal_m_crps CP:55-64, cal_m_logs CP:75-85 over a (length scale, noise s.d.) grid) -- */
+enum { GPS_GRID_NLML = 0, GPS_GRID_CRPS = 1, GPS_GRID_WRONG_CRPS = 2, GPS_GRID_LOGS = 3 };
+/* 1-D inputs x[n], targets y[n] (UVA); ls[G], noise_sd[G] host: the G grid points in natural
+ * parameters (k = 1 as in CP:44); out[G] host. */
+int gps_grid_eval(gps_ctx* ctx, const double* x, const double* y, int n, const double* ls,
+                  const double* noise_sd, int64_t G, int which, double* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GPSCORE_H */

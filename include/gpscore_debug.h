@@ -1,0 +1,34 @@
+/*
+ * gpscore_debug.h — stage-level entry points of libgpscore.so used by the GPU unit tests and by
+ * the micro-benchmarks that measure the FP64 roofline denominators.  Not part of the drop-in
+ * boundary (see gpscore.h); kept exported so each dense stage can be checked on its own.
+ */
+#ifndef GPSCORE_DEBUG_H
+#define GPSCORE_DEBUG_H
+#include "gpscore.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* C[Mp,Np'] = alpha * op(A) op(B) + beta * C over all 128x128 tiles with the full k range.
+ * kind 0: A[Mp,Kp] . B[Np',Kp]'   kind 1: A[Mp,Kp] . B[Kp,Np']   kind 2: A[Kp,Mp]' . B[Kp,Np'].
+ * All dimensions multiples of 128, DEVICE pointers, dense row-major (ld = row length).
+ * dvec (may be NULL, kind 0 only) scales the contraction index.  mirror (kind 2, square): also
+ * write the transposed tile, lower tiles only. */
+int gps_dbg_gemm(gps_ctx* ctx, int kind, const double* A, const double* B, double* C, int64_t Mp,
+                 int64_t Npp, int64_t Kp, double alpha, double beta, const double* dvec, int mirror);
+
+/* Factor the SPD matrix A[n,n] (UVA) with the blocked path; any of the outputs may be NULL:
+ * L[n,n] (lower Cholesky factor), Linv[n,n] = L^-1, Ainv[n,n] = A^-1 (full symmetric). */
+int gps_dbg_factor(gps_ctx* ctx, const double* A, int64_t n, double* L, double* Linv, double* Ainv);
+
+/* Issue-rate micro-benchmarks on all SMs: DMMA m8n8k4 and DFMA, TFLOP/s each. */
+int gps_dbg_fp64_peak(gps_ctx* ctx, int iters, double* dmma_tflops, double* dfma_tflops);
+
+/* Training Gram K = ARD(X,X) + sn2 I of the current data set at theta, N x N (UVA out). */
+int gps_dbg_gram(gps_ctx* ctx, const double* theta, double* K);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

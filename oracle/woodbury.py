@@ -1,0 +1,165 @@
+"""TEST INFRASTRUCTURE — algorithm-matched CPU baseline for the FITC path.
+
+O(N M^2) Woodbury restatement of the dense FITC objectives (K20:222-236,
+K20:329-344, K20:434-452) with the three-pass analytic adjoint of SURVEY.md
+App. A.2, staged exactly like the CUDA path (row pass -> reduce -> M x M
+algebra, three times) so that it (a) prototypes the kernels' arithmetic and
+(b) gives bench.py an honest like-for-like CPU number: the reference's own
+FITC is dense O(N^3), so timing only that would credit the
+GPU with the reference's algorithmic waste.
+
+`row_slices` splits the rows the way ranks do; the per-slice accumulators are
+summed where the NCCL all-reduce sits in the product.  tests/test_oracle.py
+checks this module against the reference-generated goldens.
+"""
+import math
+
+import numpy as np
+from scipy.linalg import cholesky, solve_triangular
+
+from . import gp_oracle as O
+
+
+def _kern(U, X, a, ell):
+    """ARD-SE by direct differences (KF:7-23 up to rounding)."""
+    diff = (U[:, None, :] - X[None, :, :]) / ell[None, None, :]
+    return math.exp(a) * np.exp(-0.5 * np.sum(diff * diff, axis=2))
+
+
+def _phi_adj(L, Lbar):
+    """Adjoint of a Cholesky factorisation: Abar from Lbar (A = L L')."""
+    P = np.tril(L.T @ Lbar)
+    P[np.diag_indices_from(P)] *= 0.5
+    T = solve_triangular(L, solve_triangular(L, (P + P.T).T, lower=True, trans="T").T, lower=True, trans="T")
+    return 0.5 * T
+
+
+def fitc_obj_grad(X, y, U, theta, score, jitter=O.JITTER, row_slices=None):
+    a, b, c = O._split(theta)
+    n, D = X.shape
+    m = U.shape[0]
+    ell = np.exp(np.asarray(b, dtype=np.float64).ravel())
+    if ell.size == 1:
+        ell = np.full(D, ell[0])
+    ea, sn2 = math.exp(a), math.exp(c)
+    y = y.reshape(-1)
+    if row_slices is None:
+        row_slices = [slice(0, n)]
+
+    # replicated: A = K_uu + jitter I = L_A L_A'
+    Kuu = _kern(U, U, a, ell)
+    LA = cholesky(Kuu + jitter * np.eye(m), lower=True)
+
+    # ---- pass 1 (rows): V, lambda; reduce C, v_y ------------------------------------------
+    st = []
+    C = np.eye(m)
+    vy = np.zeros(m)
+    for sl in row_slices:
+        Kuf = _kern(U, X[sl], a, ell)                       # M x n_r
+        V = solve_triangular(LA, Kuf, lower=True)
+        lam = ea - np.sum(V * V, axis=0) + sn2
+        C += (V / lam) @ V.T
+        vy += V @ (y[sl] / lam)
+        st.append(dict(Kuf=Kuf, V=V, lam=lam, y=y[sl], X=X[sl]))
+    LC = cholesky(C, lower=True)
+    beta = solve_triangular(LC, vy, lower=True)
+
+    # ---- pass 2 (rows): W, d, alpha, score + seeds; reduce beta_bar, R ---------------------
+    obj = 0.0
+    beta_bar = np.zeros(m)
+    R = np.zeros((m, m))
+    for s in st:
+        W = solve_triangular(LC, s["V"], lower=True)
+        r = np.sum(W * W, axis=0)
+        lam = s["lam"]
+        d = 1.0 / lam - r / lam ** 2
+        alpha = (s["y"] - W.T @ beta) / lam
+        if score == O.SCORE_NLML:
+            obj += 0.5 * np.sum(np.log(lam)) + 0.5 * float(s["y"] @ alpha)
+            abar, dbar = 0.5 * s["y"], np.zeros_like(d)
+            lam_bar = 0.5 / lam
+        else:
+            v, abar, dbar = O._score_and_seeds(alpha.reshape(-1, 1) , d.reshape(-1, 1), score)
+            # _score_and_seeds normalises by its own length; renormalise to the global N
+            k = alpha.shape[0] / n
+            obj += v * k
+            abar, dbar = abar.ravel() * k, dbar.ravel() * k
+            lam_bar = np.zeros_like(lam)
+        lam_bar = lam_bar + dbar * (-1.0 / lam ** 2 + 2.0 * r / lam ** 3) - abar * alpha / lam
+        rbar = -dbar / lam ** 2
+        tbar = -abar / lam
+        beta_bar += W @ tbar
+        R += (W * rbar) @ W.T
+        s.update(W=W, r=r, d=d, alpha=alpha, lam_bar=lam_bar, rbar=rbar, tbar=tbar)
+    if score == O.SCORE_NLML:
+        obj += 0.5 * n * math.log(2 * math.pi) + np.sum(np.log(np.diag(LC)))
+        LC_bar0 = np.diag(1.0 / np.diag(LC))
+    else:
+        LC_bar0 = np.zeros((m, m))
+    SW = np.outer(beta, beta_bar) + 2.0 * R + np.outer(beta_bar, beta)
+    LC_bar = -np.tril(solve_triangular(LC, SW, lower=True, trans="T")) + LC_bar0
+    C_bar = _phi_adj(LC, LC_bar)
+    vy_bar = solve_triangular(LC, beta_bar, lower=True, trans="T")
+
+    # ---- pass 3 (rows): lambda_bar, V_bar, Kuf_bar; reduce S, sums, kernel-gradient partials
+    S = np.zeros((m, m))
+    sum_lam_bar = 0.0
+    g_a = 0.0
+    g_b = np.zeros(D)
+    g_U = np.zeros((m, D))
+    for s in st:
+        V, W, lam, ys = s["V"], s["W"], s["lam"], s["y"]
+        CV = C_bar @ V
+        lam_bar = s["lam_bar"] - (beta_bar @ W) * ys / lam ** 2 - np.sum(V * CV, axis=0) / lam ** 2
+        Wbar = np.outer(beta, s["tbar"]) + 2.0 * W * s["rbar"]
+        Vbar = solve_triangular(LC, Wbar, lower=True, trans="T") + np.outer(vy_bar, ys / lam) \
+            + 2.0 * CV / lam - 2.0 * V * lam_bar
+        Kuf_bar = solve_triangular(LA, Vbar, lower=True, trans="T")
+        S += Vbar @ V.T
+        sum_lam_bar += lam_bar.sum()
+        G = Kuf_bar * s["Kuf"]
+        g_a += G.sum()
+        for dd in range(D):
+            diff = U[:, dd][:, None] - s["X"][:, dd][None, :]
+            g_b[dd] += np.sum(G * diff * diff) / ell[dd] ** 2
+            g_U[:, dd] += -np.sum(G * diff, axis=1) / ell[dd] ** 2
+    LA_bar = -np.tril(solve_triangular(LA, S, lower=True, trans="T"))
+    A_bar = _phi_adj(LA, LA_bar)
+    G2 = A_bar * Kuu
+    g_a += ea * sum_lam_bar + G2.sum()
+    g_c = sn2 * sum_lam_bar
+    for dd in range(D):
+        diff = U[:, dd][:, None] - U[:, dd][None, :]
+        g_b[dd] += np.sum(G2 * diff * diff) / ell[dd] ** 2
+        g_U[:, dd] += -2.0 * np.sum(G2 * diff, axis=1) / ell[dd] ** 2
+    loo_mean = np.concatenate([s["y"] - s["alpha"] / s["d"] for s in st])
+    loo_var = np.concatenate([1.0 / s["d"] for s in st])
+    return float(obj), np.concatenate([[g_a], g_b, [g_c]]), g_U, loo_mean, loo_var
+
+
+def fitc_predict(X, y, U, Xs, theta, jitter=O.JITTER):
+    """K20:76-83 in Woodbury variables: m* = K*u L_A^-T L_C^-T beta,
+    var* = sn2 + e^a - |L_A^-1 k_u*|^2 + |L_C^-1 L_A^-1 k_u*|^2."""
+    a, b, c = O._split(theta)
+    D = X.shape[1]
+    m = U.shape[0]
+    ell = np.exp(np.asarray(b, dtype=np.float64).ravel())
+    if ell.size == 1:
+        ell = np.full(D, ell[0])
+    ea, sn2 = math.exp(a), math.exp(c)
+    LA = cholesky(_kern(U, U, a, ell) + jitter * np.eye(m), lower=True)
+    V = solve_triangular(LA, _kern(U, X, a, ell), lower=True)
+    lam = ea - np.sum(V * V, axis=0) + sn2
+    LC = cholesky(np.eye(m) + (V / lam) @ V.T, lower=True)
+    beta = solve_triangular(LC, V @ (y.reshape(-1) / lam), lower=True)
+    Vs = solve_triangular(LA, _kern(U, Xs, a, ell), lower=True)
+    Ws = solve_triangular(LC, Vs, lower=True)
+    mean = Ws.T @ beta
+    var = sn2 + ea - np.sum(Vs * Vs, axis=0) + np.sum(Ws * Ws, axis=0)
+    return mean.reshape(-1, 1), var.reshape(-1, 1)
+
+
+def full_obj_grad(X, y, theta, score):
+    """Closed-form full GP — identical algorithm to the oracle's dense path;
+    re-exported so the CPU baseline has one entry point per model."""
+    return O.full_obj_grad(X, y, theta, score)

@@ -1,0 +1,439 @@
+"""Host-side mirror of the reference's function names over the CUDA library.
+
+The reference has no importable module: its hot path is loop-body code in four scripts
+(SURVEY.md §0).  This module keeps the *names and positional signatures* those loop bodies use —
+`ARD`, `chol_solve`, `Q`, `crps`, `logs`, `cal_mean_and_cov`, `spgp_cal_mean_and_cov`, `SMSE`,
+`trivial_loss` — and adds the fused entry points the loops are rewritten onto:
+
+    CRPS_ave = full_loo_objective(train_x, train_y, para_k, para_l, para_noise, "crps")   # KF:239-245
+    CRPS_ave.backward()                                                                    # KF:252
+    with torch.no_grad(): para_l -= lr * para_l.grad ...                                   # KF:254-260 unchanged
+
+torch tensors are buffers only: every number is produced by libgpscore.so through ctypes
+(lib.py).  Hyper-parameterisation as in the reference: para_k = log sf^2, para_l = log l
+(one element or [1, D]), para_noise = log sn^2 (KF:7-12, KF:239).
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import lib as _L
+
+JITTER = 1e-3  # K20:36
+
+# Module globals the reference's helpers read (KF:33-36, KF:44, KF:122).  Set them like the
+# scripts do (`gp.sigma_noise_sq = torch.exp(para_noise)`) or pass the keyword overrides.
+para_k = None
+para_l = None
+sigma_noise_sq = None
+
+
+def _as_f64(a, device=None):
+    if isinstance(a, torch.Tensor):
+        t = a.detach()
+        if t.dtype != torch.float64:
+            t = t.double()
+        if device is not None and t.device != device:
+            t = t.to(device)
+        return t.contiguous()
+    return torch.as_tensor(np.ascontiguousarray(a, dtype=np.float64), device=device)
+
+
+def _host_vec(a):
+    if isinstance(a, torch.Tensor):
+        a = a.detach().cpu().double().numpy()
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float64).ravel())
+
+
+def _dp(arr):
+    return arr.ctypes.data_as(C.POINTER(C.c_double))
+
+
+def _scalar(v):
+    if isinstance(v, torch.Tensor):
+        return float(v.detach().reshape(-1)[0])
+    return float(np.asarray(v).reshape(-1)[0])
+
+
+class Context:
+    """One gps_ctx on one GPU.  Owns the padded copy of the training set and all workspaces."""
+
+    def __init__(self, device=None):
+        self._lib = _L.load()
+        if device is None:
+            device = torch.cuda.current_device() if torch.cuda.is_available() else 0
+        if isinstance(device, torch.device):
+            device = device.index or 0
+        h = C.c_void_p()
+        code = self._lib.gps_create(int(device), C.byref(h))
+        if code != _L.GPS_OK:
+            _L.check(None, code)
+        self._h = h
+        self.device = torch.device("cuda", int(device))
+        self.N = 0
+        self.D = 0
+        self._data_key = None
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.gps_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, code):
+        _L.check(self._h, code)
+
+    # ---- data --------------------------------------------------------------------------------
+    def set_data(self, X, y):
+        """train_x [N, D], train_y [N] or [N, 1] (KF:208-209); host or device."""
+        X = _as_f64(X)
+        y = _as_f64(y).reshape(-1)
+        if X.dim() != 2 or y.numel() != X.shape[0]:
+            raise ValueError("set_data: X must be [N, D] and y must have N elements")
+        self._check(self._lib.gps_set_data(self._h, X.data_ptr(), y.data_ptr(), X.shape[0], X.shape[1]))
+        self.N, self.D = int(X.shape[0]), int(X.shape[1])
+        self._y_stats = (float(y.mean()), float(y.var(unbiased=True)) if y.numel() > 1 else 0.0)
+
+    def _theta(self, theta):
+        th = _host_vec(theta)
+        if th.size == 3 and self.D > 1:  # isotropic 1-element para_l (K20:422): broadcast (KF:8)
+            th = np.concatenate([[th[0]], np.full(self.D, th[1]), [th[2]]])
+        if th.size != self.D + 2:
+            raise ValueError("theta must have D + 2 = %d elements" % (self.D + 2))
+        return th
+
+    # ---- full GP -----------------------------------------------------------------------------
+    def full_eval(self, theta, score, grad=True):
+        """Objective and gradient wrt theta = [a, b_1..b_D, c] (KF:239-252 / 329-339 / 416-428)."""
+        th = self._theta(theta)
+        obj = np.zeros(1)
+        g = np.zeros(self.D + 2)
+        sc = _L.SCORES[score] if isinstance(score, str) else int(score)
+        self._check(self._lib.gps_full_eval(self._h, _dp(th), sc, _dp(obj), _dp(g) if grad else None))
+        return float(obj[0]), (g if grad else None)
+
+    def full_loo(self):
+        """mean_term, cov_term of KF:243-244 for the last crps/logs evaluation, as [N, 1] tensors."""
+        m = torch.empty(self.N, dtype=torch.float64, device=self.device)
+        v = torch.empty(self.N, dtype=torch.float64, device=self.device)
+        self._check(self._lib.gps_full_loo(self._h, m.data_ptr(), v.data_ptr()))
+        return m.view(-1, 1), v.view(-1, 1)
+
+    def full_predict(self, theta, Xs):
+        """Predictive mean and variance (diagonal of KF:121-126's covariance) at Xs [T, D]."""
+        th = self._theta(theta)
+        Xs = _as_f64(Xs)
+        T = int(Xs.shape[0])
+        m = torch.empty(T, dtype=torch.float64, device=self.device)
+        v = torch.empty(T, dtype=torch.float64, device=self.device)
+        self._check(self._lib.gps_full_predict(self._h, _dp(th), Xs.data_ptr(), T, m.data_ptr(), v.data_ptr()))
+        return m.view(-1, 1), v.view(-1, 1)
+
+    # ---- FITC --------------------------------------------------------------------------------
+    def fitc_eval(self, theta, U, score, jitter=JITTER):
+        """Objective and gradients (theta, inducing inputs) of K20:222-236 / 329-344 / 434-452."""
+        th = self._theta(theta)
+        Uh = _host_vec(U)
+        M = Uh.size // self.D
+        obj = np.zeros(1)
+        g = np.zeros(self.D + 2)
+        gU = np.zeros(M * self.D)
+        sc = _L.SCORES[score] if isinstance(score, str) else int(score)
+        self._check(self._lib.gps_fitc_eval(self._h, _dp(th), _dp(Uh), M, float(jitter), sc, _dp(obj), _dp(g), _dp(gU)))
+        return float(obj[0]), g, gU.reshape(M, self.D)
+
+    def fitc_acc_len(self, M):
+        a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
+        code = self._lib.gps_fitc_acc_len(int(M), self.D, C.byref(a), C.byref(b), C.byref(c))
+        if code != _L.GPS_OK:
+            raise _L.GpsError(code, "fitc_acc_len")
+        return a.value, b.value, c.value
+
+    def fitc_eval_sharded(self, theta, U, score, world_n, allreduce, jitter=JITTER):
+        """Row-sharded FITC evaluation: this context holds a contiguous block of rows; `allreduce`
+        sums a 1-D float64 device tensor in place across ranks (torch.distributed over NCCL in
+        production, gloo or a python stand-in in the CPU tests).  Three all-reduces per
+        evaluation."""
+        th = self._theta(theta)
+        Uh = _host_vec(U)
+        M = Uh.size // self.D
+        sc = _L.SCORES[score] if isinstance(score, str) else int(score)
+        l1, l2, l3 = self.fitc_acc_len(M)
+        key = (M, self.D)
+        if getattr(self, "_acc_key", None) != key:
+            self._acc = [torch.zeros(n, dtype=torch.float64, device=self.device) for n in (l1, l2, l3)]
+            self._acc_key = key
+        a1, a2, a3 = self._acc
+        self._check(self._lib.gps_fitc_begin(self._h, _dp(th), _dp(Uh), M, float(jitter), sc, int(world_n)))
+        self._check(self._lib.gps_fitc_pass1(self._h, a1.data_ptr()))
+        allreduce(a1)
+        self._check(self._lib.gps_fitc_pass2(self._h, a1.data_ptr(), a2.data_ptr()))
+        allreduce(a2)
+        self._check(self._lib.gps_fitc_pass3(self._h, a2.data_ptr(), a3.data_ptr()))
+        allreduce(a3)
+        obj = np.zeros(1)
+        g = np.zeros(self.D + 2)
+        gU = np.zeros(M * self.D)
+        self._check(self._lib.gps_fitc_finish(self._h, a2.data_ptr(), a3.data_ptr(), _dp(obj), _dp(g), _dp(gU)))
+        return float(obj[0]), g, gU.reshape(M, self.D)
+
+    def fitc_loo(self):
+        m = torch.empty(self.N, dtype=torch.float64, device=self.device)
+        v = torch.empty(self.N, dtype=torch.float64, device=self.device)
+        self._check(self._lib.gps_fitc_loo(self._h, m.data_ptr(), v.data_ptr()))
+        return m.view(-1, 1), v.view(-1, 1)
+
+    def fitc_predict(self, theta, U, Xs, jitter=JITTER, score="nlml"):
+        """Predictive mean / variance of K20:270-277 (diagonal only) at Xs."""
+        l1, l2, _ = self.fitc_acc_len(_host_vec(U).size // self.D)
+        th = self._theta(theta)
+        Uh = _host_vec(U)
+        M = Uh.size // self.D
+        a1 = torch.zeros(l1, dtype=torch.float64, device=self.device)
+        a2 = torch.zeros(l2, dtype=torch.float64, device=self.device)
+        self._check(self._lib.gps_fitc_begin(self._h, _dp(th), _dp(Uh), M, float(jitter), _L.SCORES[score], self.N))
+        self._check(self._lib.gps_fitc_pass1(self._h, a1.data_ptr()))
+        self._check(self._lib.gps_fitc_pass2(self._h, a1.data_ptr(), a2.data_ptr()))
+        Xs = _as_f64(Xs)
+        T = int(Xs.shape[0])
+        m = torch.empty(T, dtype=torch.float64, device=self.device)
+        v = torch.empty(T, dtype=torch.float64, device=self.device)
+        self._check(self._lib.gps_fitc_predict(self._h, Xs.data_ptr(), T, m.data_ptr(), v.data_ptr()))
+        return m.view(-1, 1), v.view(-1, 1)
+
+    # ---- metrics / element-wise twins ---------------------------------------------------------
+    def test_metrics(self, mean, var, y, y_train=None, return_sums=False):
+        """mse, SMSE (KF:128-134), logs, crps, MSLL (KF:110-119), +-2 sd coverage (KF:288-292)."""
+        mean, var, y = _as_f64(mean).reshape(-1), _as_f64(var).reshape(-1), _as_f64(y).reshape(-1)
+        if y_train is not None:
+            yt = _as_f64(y_train).reshape(-1)
+            ytm, ytv = float(yt.mean()), float(yt.var(unbiased=True))
+        else:
+            ytm, ytv = self._y_stats
+        out = np.zeros(12)
+        self._check(self._lib.gps_test_metrics(self._h, mean.data_ptr(), var.data_ptr(), y.data_ptr(), mean.numel(),
+                                               ytm, ytv, _dp(out)))
+        res = dict(zip(("mse", "smse", "logs", "crps", "msll", "coverage"), out[:6].tolist()))
+        if return_sums:
+            return res, out[6:].copy()
+        return res
+
+    def ard(self, x, xp, a, b):
+        x, xp = _as_f64(x), _as_f64(xp)
+        bh = _host_vec(b)
+        out = torch.empty(x.shape[0], xp.shape[0], dtype=torch.float64, device=x.device)
+        self._check(self._lib.gps_ard(self._h, x.data_ptr(), x.shape[0], xp.data_ptr(), xp.shape[0], x.shape[1],
+                                      _scalar(a), _dp(bh), bh.size, out.data_ptr()))
+        return out
+
+    def chol_solve(self, B, A):
+        B2, A2 = _as_f64(B), _as_f64(A)
+        n = A2.shape[0]
+        B2 = B2.reshape(n, -1)
+        out = torch.empty_like(B2)
+        self._check(self._lib.gps_chol_solve(self._h, B2.data_ptr(), A2.data_ptr(), n, B2.shape[1], out.data_ptr()))
+        return out
+
+    def score(self, m, c, y, which):
+        m, c, y = _as_f64(m).reshape(-1), _as_f64(c).reshape(-1), _as_f64(y).reshape(-1)
+        out = np.zeros(1)
+        self._check(self._lib.gps_score(self._h, m.data_ptr(), c.data_ptr(), y.data_ptr(), m.numel(),
+                                        _L.SCORES[which], _dp(out)))
+        return float(out[0])
+
+    def grid_eval(self, x, y, ls, noise_sd, which):
+        """CP:109-144: objective `which` at every (length scale, noise s.d.) pair."""
+        x, y = _as_f64(x).reshape(-1), _as_f64(y).reshape(-1)
+        ls, sd = _host_vec(ls), _host_vec(noise_sd)
+        out = np.zeros(ls.size)
+        self._check(self._lib.gps_grid_eval(self._h, x.data_ptr(), y.data_ptr(), x.numel(), _dp(ls), _dp(sd), ls.size,
+                                            _L.GRID_KINDS[which], _dp(out)))
+        return out
+
+    # ---- accounting --------------------------------------------------------------------------
+    def launch_count(self):
+        return int(self._lib.gps_launch_count(self._h))
+
+    def last_gemm_ms(self):
+        ms, n = C.c_double(), C.c_int64()
+        self._lib.gps_last_gemm_ms(self._h, C.byref(ms), C.byref(n))
+        return ms.value, n.value
+
+
+_default = {}
+
+
+def default_context(device=None):
+    """Process-wide context per GPU, created on first use."""
+    if device is None:
+        device = torch.cuda.current_device() if torch.cuda.is_available() else 0
+    if isinstance(device, torch.device):
+        device = device.index or 0
+    if device not in _default:
+        _default[device] = Context(device)
+    return _default[device]
+
+
+def _bind_data(ctx, X, y):
+    key = (X.data_ptr(), tuple(X.shape), X._version, y.data_ptr(), y._version) if isinstance(X, torch.Tensor) else None
+    if key is None or ctx._data_key != key:
+        ctx.set_data(X, y)
+        ctx._data_key = key
+
+
+def _theta_from_leaves(pk, pl, pn, D):
+    b = _host_vec(pl)
+    if b.size == 1:
+        b = np.full(D, b[0])
+    return np.concatenate([[_scalar(pk)], b, [_scalar(pn)]])
+
+
+class _FusedObjective(torch.autograd.Function):
+    """forward = one C-ABI call returning value AND gradient; backward scales the cached gradient.
+    Makes `obj.backward()` populate `.grad` of para_k / para_l / para_noise / inducing_x exactly as
+    the scripts' loops expect (KF:252-260, K20:236-251)."""
+
+    @staticmethod
+    def forward(fctx, pk, pl, pn, U, X, y, score, jitter, ctx):
+        D = X.shape[1]
+        theta = _theta_from_leaves(pk, pl, pn, D)
+        _bind_data(ctx, X, y)
+        if U is None:
+            val, g = ctx.full_eval(theta, score)
+            gU = None
+        else:
+            val, g, gU = ctx.fitc_eval(theta, U, score, jitter)
+        fctx.grads = (g, gU)
+        fctx.meta = (pk, pl, pn, U)
+        out = torch.tensor(val, dtype=pk.dtype, device=pk.device)
+        if score == "nlml":
+            out = out.reshape(1, 1)  # Neg_logL is a [1, 1] tensor in the scripts (KF:334)
+        return out
+
+    @staticmethod
+    def backward(fctx, gout):
+        g, gU = fctx.grads
+        pk, pl, pn, U = fctx.meta
+        s = float(gout.reshape(-1)[0])
+        gk = torch.tensor([g[0] * s], dtype=pk.dtype, device=pk.device).reshape(pk.shape)
+        gb = g[1:-1]
+        if pl.numel() == 1:
+            gl = torch.tensor([gb.sum() * s], dtype=pl.dtype, device=pl.device).reshape(pl.shape)
+        else:
+            gl = torch.tensor(gb * s, dtype=pl.dtype, device=pl.device).reshape(pl.shape)
+        gn = torch.tensor([g[-1] * s], dtype=pn.dtype, device=pn.device).reshape(pn.shape)
+        gu = None
+        if U is not None:
+            gu = torch.tensor(gU * s, dtype=U.dtype, device=U.device).reshape(U.shape)
+        return gk, gl, gn, gu, None, None, None, None, None
+
+
+def full_loo_objective(train_x, train_y, para_k, para_l, para_noise, score="crps", ctx=None):
+    """The six statements KF:239-245 (crps), KF:416-424 (logs) or KF:329-334 (nlml) as one fused,
+    differentiable call.  Returns the scalar the scripts call CRPS_ave / logs_ave / Neg_logL."""
+    ctx = ctx or default_context()
+    return _FusedObjective.apply(para_k, para_l, para_noise, None, train_x, train_y, score, JITTER, ctx)
+
+
+def fitc_loo_objective(train_x, train_y, inducing_x, para_k, para_l, para_noise, score="crps", jitter=JITTER,
+                       ctx=None):
+    """K20:222-234 (crps), K20:434-447 (logs) or K20:329-340 (nlml) as one fused, differentiable call;
+    gradients flow to inducing_x as well (K20:247)."""
+    ctx = ctx or default_context()
+    return _FusedObjective.apply(para_k, para_l, para_noise, inducing_x, train_x, train_y, score, jitter, ctx)
+
+
+def predict_diag(train_x, train_y, test_x, para_k, para_l, para_noise, inducing_x=None, jitter=JITTER, ctx=None):
+    """KF:267-273 / K20:270-277 with only the diagonal of the covariance formed: (mean, var) [T, 1]."""
+    ctx = ctx or default_context()
+    _bind_data(ctx, train_x, train_y)
+    theta = _theta_from_leaves(para_k, para_l, para_noise, train_x.shape[1])
+    if inducing_x is None:
+        return ctx.full_predict(theta, test_x)
+    return ctx.fitc_predict(theta, inducing_x, test_x, jitter)
+
+
+# ---- same-signature twins of the reference's helpers ----------------------------------------------
+def ARD(x, xp, a, b):
+    """KF:7-23."""
+    return default_context().ard(x, xp, a, b)
+
+
+def chol_solve(B, A):
+    """KF:25-29: A^-1 B."""
+    out = default_context().chol_solve(B, A)
+    return out.reshape(B.shape) if isinstance(B, torch.Tensor) else out
+
+
+def Q(a, u, b, para_k=None, para_l=None, jitter=JITTER):
+    """KF:32-39: K_au (K_uu + 1e-3 I)^-1 K_ub; para_k / para_l default to the module globals."""
+    g = globals()
+    pk = g["para_k"] if para_k is None else para_k
+    pl = g["para_l"] if para_l is None else para_l
+    K_au = ARD(a, u, pk, pl)
+    K_uu = ARD(u, u, pk, pl)
+    K_uu = K_uu + jitter * torch.eye(K_uu.shape[0], dtype=K_uu.dtype, device=K_uu.device)
+    K_ub = ARD(u, b, pk, pl)
+    return K_au.mm(chol_solve(K_ub, K_uu))
+
+
+def crps(m, c, data_y):
+    """KF:60-68; c is the variance."""
+    return torch.tensor(default_context().score(m, c, data_y, "crps"), dtype=torch.float64)
+
+
+def logs(m, c, data_y):
+    """KF:52-57."""
+    return torch.tensor(default_context().score(m, c, data_y, "logs"), dtype=torch.float64)
+
+
+def _noise(sn2):
+    v = globals()["sigma_noise_sq"] if sn2 is None else sn2
+    if v is None:
+        raise ValueError("sigma_noise_sq is not set (module global, KF:122) and no override was given")
+    return _scalar(v)
+
+
+def cal_mean_and_cov(k1, k2, k3, num, eye_num, data_y, sigma_noise_sq=None):
+    """KF:121-126 (full T x T covariance, as the reference returns it)."""
+    sn2 = _noise(sigma_noise_sq)
+    eye = torch.eye(eye_num, dtype=k2.dtype, device=k2.device)
+    Kn = k2 + sn2 * eye
+    sol = chol_solve(torch.cat([data_y.reshape(eye_num, -1), k1.t()], dim=1), Kn)
+    res_mean = k1.mm(sol[:, :1])
+    res_cov = sn2 * torch.eye(num, dtype=k2.dtype, device=k2.device) + k3 - k1.mm(sol[:, 1:])
+    return res_mean, res_cov
+
+
+def spgp_cal_mean_and_cov(k1, Q1, Q2, k2, num_test, num_jitter, data_y, sigma_noise_sq=None):
+    """K20:76-83."""
+    sn2 = _noise(sigma_noise_sq)
+    G = torch.diag(torch.diag(k1 - Q1) + sn2)
+    sol = chol_solve(torch.cat([data_y.reshape(num_jitter, -1), Q2.t()], dim=1), Q1 + G)
+    mean_term = Q2.mm(sol[:, :1])
+    cov_term = sn2 * torch.eye(num_test, dtype=k2.dtype, device=k2.device) + k2 - Q2.mm(sol[:, 1:])
+    return mean_term, cov_term
+
+
+def SMSE(m, data_y, data_yp):
+    """KF:128-134."""
+    r = default_context().test_metrics(m, torch.ones_like(_as_f64(m)), data_y, data_yp)
+    return torch.tensor(r["smse"], dtype=torch.float64)
+
+
+def trivial_loss(m, c, data_y, data_yp):
+    """KF:110-119 (MSLL)."""
+    r = default_context().test_metrics(m, c, data_y, data_yp)
+    return torch.tensor(r["msll"], dtype=torch.float64)
+
+
+def test_metrics(m, c, data_y, data_yp):
+    """KF:276-292 in one call."""
+    return default_context().test_metrics(m, c, data_y, data_yp)

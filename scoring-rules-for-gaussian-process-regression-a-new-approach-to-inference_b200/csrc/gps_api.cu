@@ -1,0 +1,341 @@
+// extern "C" boundary of libgpscore.so (see include/gpscore.h) — context, data staging and the
+// full-GP evaluation / prediction drivers.
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include "gps_common.cuh"
+
+int gps_fail(gps_ctx* c, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (c) c->err = buf;
+  return code;
+}
+
+int gps_ensure(gps_ctx* ctx, DevBuf& b, size_t n) {
+  if (b.n >= n && b.p) return GPS_OK;
+  if (b.p) cudaFree(b.p);
+  b.p = nullptr;
+  b.n = 0;
+  cudaError_t e = cudaMalloc(&b.p, n * sizeof(double));
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return gps_fail(ctx, GPS_ENOMEM, "cudaMalloc of %zu bytes failed: %s", n * sizeof(double),
+                    cudaGetErrorString(e));
+  }
+  b.n = n;
+  return GPS_OK;
+}
+
+bool gps_is_device_ptr(const void* p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return at.type == cudaMemoryTypeDevice || at.type == cudaMemoryTypeManaged;
+}
+
+
+// Input staging: returns a device pointer holding `n` doubles of `p` (p itself if already on the
+// device, else a copy in `tmp`).
+int gps_stage_in(gps_ctx* ctx, const double* p, size_t n, DevBuf& tmp, const double** out) {
+  if (n == 0) { *out = p; return GPS_OK; }
+  if (gps_is_device_ptr(p)) { *out = p; return GPS_OK; }
+  GPS_CHECK(gps_ensure(ctx, tmp, n));
+  GPS_CUDA(cudaMemcpyAsync(tmp.p, p, n * sizeof(double), cudaMemcpyDefault, ctx->stream));
+  *out = tmp.p;
+  return GPS_OK;
+}
+
+int gps_ensure_ws(gps_ctx* ctx, int64_t Np) {
+  GPS_CHECK(gps_ensure(ctx, ctx->params, PAR_LEN));
+  if (!ctx->d_info) GPS_CUDA(cudaMalloc(&ctx->d_info, sizeof(int)));
+  if (ctx->ws_Np != Np) {
+    GPS_CHECK(gps_ensure(ctx, ctx->Kb, (size_t)Np * Np));
+    GPS_CHECK(gps_ensure(ctx, ctx->Xb, (size_t)Np * Np));
+    GPS_CHECK(gps_ensure(ctx, ctx->Sb, (size_t)Np * Np));
+    GPS_CHECK(gps_ensure(ctx, ctx->vecs, (size_t)V_COUNT * Np));
+    GPS_CHECK(gps_build_tasks(ctx, Np));
+    ctx->ws_Np = Np;
+    ctx->loo_valid = false;
+  }
+  return GPS_OK;
+}
+
+int gps_upload_tasks2(gps_ctx* ctx, const std::vector<GemmTask>& h) {
+  if (h.size() > ctx->tasks2_cap) {
+    if (ctx->d_tasks2) cudaFree(ctx->d_tasks2);
+    ctx->d_tasks2 = nullptr;
+    GPS_CUDA(cudaMalloc(&ctx->d_tasks2, h.size() * sizeof(GemmTask)));
+    ctx->tasks2_cap = h.size();
+  }
+  GPS_CUDA(cudaMemcpyAsync(ctx->d_tasks2, h.data(), h.size() * sizeof(GemmTask), cudaMemcpyHostToDevice,
+                           ctx->stream));
+  GPS_CUDA(cudaStreamSynchronize(ctx->stream));  // h may be a temporary
+  return GPS_OK;
+}
+
+int gps_upload_params(gps_ctx* ctx, const double* theta, int D, double* ea_out, double* sn2_out) {
+  double h[2 + 64];
+  if (D > 64) return gps_fail(ctx, GPS_EINVAL, "D=%d exceeds 64", D);
+  h[0] = exp(theta[0]);
+  h[1] = exp(theta[D + 1]);
+  for (int d = 0; d < D; ++d) h[2 + d] = exp(-theta[1 + d]);
+  GPS_CUDA(cudaMemcpyAsync(ctx->params.p, h, (2 + D) * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  // h is on the stack: the copy from pageable memory is staged before the call returns
+  if (ea_out) *ea_out = h[0];
+  if (sn2_out) *sn2_out = h[1];
+  return GPS_OK;
+}
+
+namespace {
+
+void gemm_timing_begin(gps_ctx* ctx) { ctx->gemm_events_used = 0; }
+
+int gemm_timing_end(gps_ctx* ctx) {
+  double ms = 0;
+  for (size_t i = 0; i < ctx->gemm_events_used; ++i) {
+    float t = 0;
+    GPS_CUDA(cudaEventElapsedTime(&t, ctx->gemm_events[i].first, ctx->gemm_events[i].second));
+    ms += t;
+  }
+  ctx->last_gemm_ms = ms;
+  ctx->last_gemm_launches = (int64_t)ctx->gemm_events_used;
+  return GPS_OK;
+}
+
+}  // namespace
+
+// K = ARD(X, X) + sn2 I  ->  L, L^-1, K^-1 (in Kb), alpha.  logdiag optionally.
+int gps_factor_and_invert(gps_ctx* ctx, bool want_logdet) {
+  const int64_t N = ctx->N, Np = ctx->Np;
+  double* v = ctx->vecs.p;
+  GPS_CHECK(gps_gram_sym(ctx, ctx->X.p, N, Np, ctx->D, ctx->params.p, ctx->Kb.p));
+  GPS_CHECK(gps_potrf(ctx, ctx->Kb.p, ctx->Xb.p, Np));
+  if (want_logdet) GPS_CHECK(gps_diag_extract(ctx, ctx->Kb.p, Np, v + V_LOGD * Np, 1));
+  GPS_CHECK(gps_trtri(ctx, ctx->Kb.p, ctx->Xb.p, ctx->Sb.p, Np));
+  GPS_CHECK(gps_lauum(ctx, ctx->Xb.p, ctx->Kb.p, Np));
+  GPS_CHECK(gps_symv(ctx, ctx->Kb.p, Np, ctx->y.p, v + V_ALPHA * Np));
+  return GPS_OK;
+}
+
+extern "C" {
+
+const char* gps_version(void) { return "gpscore-b200 0.1 (sm_100a)"; }
+
+int gps_create(int device, gps_ctx** out) {
+  if (!out) return GPS_EINVAL;
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n == 0) {
+    cudaGetLastError();
+    return GPS_ENODEVICE;  // there is no CPU fallback
+  }
+  if (device < 0 || device >= n) return GPS_EINVAL;
+  if (cudaSetDevice(device) != cudaSuccess) return GPS_ECUDA;
+  gps_ctx* ctx = new gps_ctx();
+  ctx->device = device;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {
+    delete ctx;
+    return GPS_ECUDA;
+  }
+  *out = ctx;
+  return GPS_OK;
+}
+
+void gps_destroy(gps_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  DevBuf* bufs[] = {&ctx->X, &ctx->y, &ctx->Kb, &ctx->Xb, &ctx->Sb, &ctx->vecs, &ctx->red, &ctx->params,
+                    &ctx->fitc.V, &ctx->fitc.W, &ctx->fitc.rowv, &ctx->fitc.small, &ctx->fitc.part,
+                    &ctx->fitc.acc1, &ctx->fitc.acc2, &ctx->fitc.acc3, &ctx->stage[0], &ctx->stage[1],
+                    &ctx->stage[2], &ctx->stage[3]};
+  for (DevBuf* b : bufs)
+    if (b->p) cudaFree(b->p);
+  if (ctx->d_info) cudaFree(ctx->d_info);
+  if (ctx->d_tasks) cudaFree(ctx->d_tasks);
+  if (ctx->d_tasks2) cudaFree(ctx->d_tasks2);
+  for (auto& pr : ctx->gemm_events) {
+    cudaEventDestroy(pr.first);
+    cudaEventDestroy(pr.second);
+  }
+  cudaEventDestroy(ctx->ev0);
+  cudaEventDestroy(ctx->ev1);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char* gps_last_error(gps_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int64_t gps_launch_count(gps_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int gps_last_gemm_ms(gps_ctx* ctx, double* ms, int64_t* launches) {
+  if (!ctx) return GPS_EINVAL;
+  if (ms) *ms = ctx->last_gemm_ms;
+  if (launches) *launches = ctx->last_gemm_launches;
+  return GPS_OK;
+}
+
+int gps_set_data(gps_ctx* ctx, const double* X, const double* y, int64_t N, int D) {
+  if (!ctx) return GPS_EINVAL;
+  if (!X || !y || N <= 0 || D <= 0 || D > 64) return gps_fail(ctx, GPS_EINVAL, "set_data: bad N=%lld D=%d", (long long)N, D);
+  GPS_CUDA(cudaSetDevice(ctx->device));
+  const int64_t Np = gps_pad(N);
+  GPS_CHECK(gps_ensure(ctx, ctx->X, (size_t)Np * D));
+  GPS_CHECK(gps_ensure(ctx, ctx->y, (size_t)Np));
+  GPS_CUDA(cudaMemsetAsync(ctx->X.p, 0, (size_t)Np * D * sizeof(double), ctx->stream));
+  GPS_CUDA(cudaMemsetAsync(ctx->y.p, 0, (size_t)Np * sizeof(double), ctx->stream));
+  GPS_CUDA(cudaMemcpyAsync(ctx->X.p, X, (size_t)N * D * sizeof(double), cudaMemcpyDefault, ctx->stream));
+  GPS_CUDA(cudaMemcpyAsync(ctx->y.p, y, (size_t)N * sizeof(double), cudaMemcpyDefault, ctx->stream));
+  GPS_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->N = N;
+  ctx->Np = Np;
+  ctx->D = D;
+  ctx->loo_valid = false;
+  ctx->fitc.begun = false;
+  ctx->fitc.pass2_done = false;
+  return GPS_OK;
+}
+
+int gps_full_eval(gps_ctx* ctx, const double* theta, int score, double* obj, double* grad) {
+  if (!ctx) return GPS_EINVAL;
+  if (ctx->N == 0) return gps_fail(ctx, GPS_ESTATE, "full_eval: call gps_set_data first");
+  if (!theta || !obj || score < GPS_CRPS || score > GPS_NLML) return gps_fail(ctx, GPS_EINVAL, "full_eval: bad arguments");
+  GPS_CUDA(cudaSetDevice(ctx->device));
+  const int64_t N = ctx->N, Np = ctx->Np;
+  const int D = ctx->D;
+  GPS_CHECK(gps_ensure_ws(ctx, Np));
+  double ea, sn2;
+  GPS_CHECK(gps_upload_params(ctx, theta, D, &ea, &sn2));
+  gemm_timing_begin(ctx);
+  GPS_CHECK(gps_factor_and_invert(ctx, score == GPS_NLML));
+  double* v = ctx->vecs.p;
+  double* par = ctx->params.p;
+  if (score != GPS_NLML) {
+    GPS_CHECK(gps_diag_extract(ctx, ctx->Kb.p, Np, v + V_D * Np, 0));
+    GPS_CHECK(gps_loo_score(ctx, score, N, Np, v + V_ALPHA * Np, v + V_D * Np, ctx->y.p, v + V_ABAR * Np,
+                            v + V_DBAR * Np, v + V_LOOM * Np, v + V_LOOV * Np, par + PAR_OBJ));
+    ctx->loo_valid = true;
+    if (grad) {
+      GPS_CHECK(gps_symv(ctx, ctx->Kb.p, Np, v + V_ABAR * Np, v + V_U * Np));
+      GPS_CHECK(gps_symprod(ctx, ctx->Kb.p, v + V_DBAR * Np, ctx->Sb.p, Np));
+      GPS_CHECK(gps_grad_contract(ctx, 0, ctx->Sb.p, N, Np, ctx->X.p, D, par, v + V_ALPHA * Np, v + V_U * Np,
+                                  par + PAR_GSUM));
+    }
+  } else {
+    ctx->loo_valid = false;
+    GPS_CHECK(gps_nlml_value(ctx, N, Np, v + V_LOGD * Np, v + V_ALPHA * Np, ctx->y.p, par + PAR_OBJ));
+    if (grad)
+      GPS_CHECK(gps_grad_contract(ctx, 1, ctx->Kb.p, N, Np, ctx->X.p, D, par, v + V_ALPHA * Np, nullptr,
+                                  par + PAR_GSUM));
+  }
+  double h[8 + 66];
+  GPS_CUDA(cudaMemcpyAsync(h, par + PAR_OBJ, (size_t)(PAR_GSUM - PAR_OBJ + D + 2) * sizeof(double),
+                           cudaMemcpyDeviceToHost, ctx->stream));
+  GPS_CHECK(gps_check_info(ctx));  // synchronises the stream
+  GPS_CHECK(gemm_timing_end(ctx));
+  *obj = h[0];
+  if (grad) {
+    const double* gs = h + (PAR_GSUM - PAR_OBJ);
+    grad[0] = gs[0];
+    for (int d = 0; d < D; ++d) grad[1 + d] = gs[1 + d];
+    grad[D + 1] = sn2 * gs[1 + D];
+  }
+  return GPS_OK;
+}
+
+int gps_full_loo(gps_ctx* ctx, double* loo_mean, double* loo_var) {
+  if (!ctx) return GPS_EINVAL;
+  if (!ctx->loo_valid) return gps_fail(ctx, GPS_ESTATE, "full_loo: no CRPS/LOGS evaluation to report");
+  GPS_CUDA(cudaSetDevice(ctx->device));
+  const int64_t N = ctx->N, Np = ctx->Np;
+  if (loo_mean)
+    GPS_CUDA(cudaMemcpyAsync(loo_mean, ctx->vecs.p + V_LOOM * Np, N * sizeof(double), cudaMemcpyDefault, ctx->stream));
+  if (loo_var)
+    GPS_CUDA(cudaMemcpyAsync(loo_var, ctx->vecs.p + V_LOOV * Np, N * sizeof(double), cudaMemcpyDefault, ctx->stream));
+  GPS_CUDA(cudaStreamSynchronize(ctx->stream));
+  return GPS_OK;
+}
+
+int gps_test_metrics(gps_ctx* ctx, const double* mean, const double* var, const double* y, int64_t n,
+                     double ytm, double ytv, double* out) {
+  if (!ctx) return GPS_EINVAL;
+  if (!mean || !var || !y || !out || n <= 0) return gps_fail(ctx, GPS_EINVAL, "test_metrics: bad arguments");
+  GPS_CUDA(cudaSetDevice(ctx->device));
+  GPS_CHECK(gps_ensure(ctx, ctx->params, PAR_LEN));
+  const double *dm, *dv, *dy;
+  GPS_CHECK(gps_stage_in(ctx, mean, n, ctx->stage[0], &dm));
+  GPS_CHECK(gps_stage_in(ctx, var, n, ctx->stage[1], &dv));
+  GPS_CHECK(gps_stage_in(ctx, y, n, ctx->stage[2], &dy));
+  GPS_CHECK(gps_metrics_kernel(ctx, dm, dv, dy, n, ytm, ytv, ctx->params.p + PAR_OBJ));
+  double s[6];
+  GPS_CUDA(cudaMemcpyAsync(s, ctx->params.p + PAR_OBJ, sizeof s, cudaMemcpyDeviceToHost, ctx->stream));
+  GPS_CUDA(cudaStreamSynchronize(ctx->stream));
+  // out = {mse, smse, logs, crps, msll, coverage} followed by the six raw sums (for row-sharded callers)
+  out[0] = s[0] / n;
+  out[1] = s[0] / s[1];
+  out[2] = s[2] / n;
+  out[3] = s[3] / n;
+  out[4] = (s[2] - s[4]) / n;
+  out[5] = s[5] / n;
+  for (int k = 0; k < 6; ++k) out[6 + k] = s[k];
+  return GPS_OK;
+}
+
+int gps_score(gps_ctx* ctx, const double* m, const double* c, const double* y, int64_t n, int which,
+              double* out) {
+  if (!ctx) return GPS_EINVAL;
+  if (!m || !c || !y || !out || n <= 0 || (which != GPS_CRPS && which != GPS_LOGS))
+    return gps_fail(ctx, GPS_EINVAL, "score: bad arguments");
+  GPS_CUDA(cudaSetDevice(ctx->device));
+  GPS_CHECK(gps_ensure(ctx, ctx->params, PAR_LEN));
+  const double *dm, *dv, *dy;
+  GPS_CHECK(gps_stage_in(ctx, m, n, ctx->stage[0], &dm));
+  GPS_CHECK(gps_stage_in(ctx, c, n, ctx->stage[1], &dv));
+  GPS_CHECK(gps_stage_in(ctx, y, n, ctx->stage[2], &dy));
+  GPS_CHECK(gps_score_kernel(ctx, dm, dv, dy, n, which, ctx->params.p + PAR_OBJ));
+  GPS_CUDA(cudaMemcpyAsync(out, ctx->params.p + PAR_OBJ, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  GPS_CUDA(cudaStreamSynchronize(ctx->stream));
+  return GPS_OK;
+}
+
+int gps_ard(gps_ctx* ctx, const double* x, int64_t n, const double* xp, int64_t m, int D, double a,
+            const double* b, int nb, double* out) {
+  if (!ctx) return GPS_EINVAL;
+  if (!x || !xp || !b || !out || n < 0 || m < 0 || D <= 0 || D > 64 || (nb != 1 && nb != D))
+    return gps_fail(ctx, GPS_EINVAL, "ard: bad arguments");
+  if (n == 0 || m == 0) return GPS_OK;
+  GPS_CUDA(cudaSetDevice(ctx->device));
+  GPS_CHECK(gps_ensure(ctx, ctx->params, PAR_LEN));
+  double th[66];
+  th[0] = a;
+  for (int d = 0; d < D; ++d) th[1 + d] = b[nb == 1 ? 0 : d];
+  th[D + 1] = 0.0;
+  GPS_CHECK(gps_upload_params(ctx, th, D, nullptr, nullptr));
+  const double *dx, *dxp;
+  GPS_CHECK(gps_stage_in(ctx, x, (size_t)n * D, ctx->stage[0], &dx));
+  GPS_CHECK(gps_stage_in(ctx, xp, (size_t)m * D, ctx->stage[1], &dxp));
+  double* dout = out;
+  const bool dev_out = gps_is_device_ptr(out);
+  if (!dev_out) {
+    GPS_CHECK(gps_ensure(ctx, ctx->stage[2], (size_t)n * m));
+    dout = ctx->stage[2].p;
+  }
+  GPS_CHECK(gps_gram_rect(ctx, dx, n, dxp, m, D, ctx->params.p, dout, m));
+  if (!dev_out)
+    GPS_CUDA(cudaMemcpyAsync(out, dout, (size_t)n * m * sizeof(double), cudaMemcpyDefault, ctx->stream));
+  GPS_CUDA(cudaStreamSynchronize(ctx->stream));
+  return GPS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,279 @@
+// Blocked fp64 Cholesky / triangular inverse / Cholesky-inverse drivers for the full-GP path.
+//
+// Replaces chol_solve's potrf + two gesv on an N-column identity (KF:25-29, KF:242) by
+//   POTRF   K = L L'            right-looking, 128-wide block columns
+//   TRTRI   X = L^-1            recursive halving over block ranges, batched per level
+//   LAUUM   K^-1 = X' X         one batched launch, lower tiles + mirror
+//   SYMPROD S = K^-1 diag(dbar) K^-1   (the N^3 term of the analytic gradient, App. A.1)
+// All N^3 work runs in the DMMA tile-GEMM (gps_gemm.cu); only the 128 x 128 diagonal blocks are
+// factored and inverted by a dedicated one-CTA kernel below.
+#include <algorithm>
+
+#include "gps_common.cuh"
+
+namespace {
+
+constexpr int T = GPS_TILE;
+constexpr int LSLD = T + 1;
+constexpr size_t POTF2_SMEM = (size_t)T * LSLD * sizeof(double) + 2 * T * sizeof(double);
+
+// One CTA (16 x 16 threads).  Thread (ty, tx) owns the 8 x 8 cyclic sub-block
+// A[ty + 16 r][tx + 16 c].  Phase 1: right-looking Cholesky of the 128 x 128 diagonal block with
+// the matrix in registers and the current column broadcast through shared memory.  Phase 2:
+// forward substitution on the identity (all 128 right-hand sides at once) gives L^-1.
+// Writes L (strict upper part zeroed) back to Kd and L^-1 (strict upper part zero) to Xd.
+__global__ void __launch_bounds__(256, 1)
+potf2_inv_kernel(double* __restrict__ K, double* __restrict__ Xinv, int64_t ld, int blk, int* __restrict__ info) {
+  extern __shared__ __align__(16) double sm[];
+  double* Ls = sm;                       // [128][129]
+  double* buf = sm + (size_t)T * LSLD;   // [2][128]
+  const int tid = threadIdx.x;
+  const int ty = tid >> 4, tx = tid & 15;
+  double* Kd = K + (int64_t)blk * T * ld + (int64_t)blk * T;
+  double* Xd = Xinv + (int64_t)blk * T * ld + (int64_t)blk * T;
+
+  double a[8][8];
+#pragma unroll
+  for (int r = 0; r < 8; ++r)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) a[r][c] = Kd[(int64_t)(ty + 16 * r) * ld + tx + 16 * c];
+
+  // ---- phase 1: Cholesky -----------------------------------------------------------------
+#pragma unroll
+  for (int kq = 0; kq < 8; ++kq) {
+    for (int kc = 0; kc < 16; ++kc) {
+      const int k = 16 * kq + kc;
+      double* cb = buf + (k & 1) * T;
+      if (tx == kc) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) cb[ty + 16 * r] = a[r][kq];
+      }
+      __syncthreads();
+      double piv = cb[k];
+      if (!(piv > 0.0)) {
+        if (tid == 0) atomicCAS(info, 0, blk * T + k + 1);
+        piv = 1.0;
+      }
+      const double sq = sqrt(piv);
+      const double rs = 1.0 / sq;
+      double li[8], lc[8];
+#pragma unroll
+      for (int r = kq; r < 8; ++r) {
+        const int i = ty + 16 * r;
+        li[r] = (i > k) ? cb[i] * rs : 0.0;
+      }
+#pragma unroll
+      for (int c = kq; c < 8; ++c) {
+        const int j = tx + 16 * c;
+        lc[c] = (j > k) ? cb[j] * rs : 0.0;
+      }
+#pragma unroll
+      for (int r = kq; r < 8; ++r)
+#pragma unroll
+        for (int c = kq; c < 8; ++c) a[r][c] -= li[r] * lc[c];
+      if (tx == kc) {
+#pragma unroll
+        for (int r = kq; r < 8; ++r) {
+          const int i = ty + 16 * r;
+          if (i > k) a[r][kq] = li[r];
+          else if (i == k) a[r][kq] = sq;
+        }
+      }
+    }
+  }
+  // L -> shared + global (zero the strict upper triangle)
+#pragma unroll
+  for (int r = 0; r < 8; ++r)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const int i = ty + 16 * r, j = tx + 16 * c;
+      const double v = (j <= i) ? a[r][c] : 0.0;
+      Ls[i * LSLD + j] = v;
+      Kd[(int64_t)i * ld + j] = v;
+    }
+  __syncthreads();
+
+  // ---- phase 2: X = L^-1 by forward substitution on I ------------------------------------
+#pragma unroll
+  for (int r = 0; r < 8; ++r)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) a[r][c] = (ty + 16 * r == tx + 16 * c) ? 1.0 : 0.0;
+
+#pragma unroll
+  for (int kq = 0; kq < 8; ++kq) {
+    for (int kc = 0; kc < 16; ++kc) {
+      const int k = 16 * kq + kc;
+      double* rb = buf + (k & 1) * T;
+      if (ty == kc) {
+        const double inv = 1.0 / Ls[k * LSLD + k];
+#pragma unroll
+        for (int c = 0; c <= kq; ++c) {
+          const double x = a[kq][c] * inv;
+          a[kq][c] = x;
+          rb[tx + 16 * c] = x;
+        }
+      }
+      __syncthreads();
+      double li[8], xr[8];
+#pragma unroll
+      for (int r = kq; r < 8; ++r) {
+        const int i = ty + 16 * r;
+        li[r] = (i > k) ? Ls[i * LSLD + k] : 0.0;
+      }
+#pragma unroll
+      for (int c = 0; c <= kq; ++c) {
+        const int j = tx + 16 * c;
+        xr[c] = (j <= k) ? rb[j] : 0.0;
+      }
+#pragma unroll
+      for (int r = kq; r < 8; ++r)
+#pragma unroll
+        for (int c = 0; c <= kq; ++c) a[r][c] -= li[r] * xr[c];
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 8; ++r)
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const int i = ty + 16 * r, j = tx + 16 * c;
+      Xd[(int64_t)i * ld + j] = (j <= i) ? a[r][c] : 0.0;
+    }
+}
+
+struct Node { int lo, mid, hi, depth; };
+
+void collect(int lo, int hi, int depth, std::vector<Node>& out) {
+  if (hi - lo <= 1) return;
+  const int mid = lo + (hi - lo) / 2;
+  out.push_back({lo, mid, hi, depth});
+  collect(lo, mid, depth + 1, out);
+  collect(mid, hi, depth + 1, out);
+}
+
+}  // namespace
+
+int gps_build_tasks(gps_ctx* ctx, int64_t Np) {
+  if (ctx->ws_Np == Np && ctx->d_tasks) return GPS_OK;
+  const int nb = (int)(Np / T);
+  std::vector<GemmTask>& h = ctx->h_tasks;
+  h.clear();
+  auto push = [&](int a_row, int b_row, int k0, int k1, int ci, int cj) {
+    GemmTask t;
+    t.a_row = a_row; t.b_row = b_row; t.k0 = k0; t.k1 = k1; t.c_row = ci * T; t.c_col = cj * T;
+    t.flags = 0; t.pad = 0;
+    h.push_back(t);
+  };
+  ctx->potrf_panel.assign(nb, {});
+  ctx->potrf_trail.assign(nb, {});
+  for (int k = 0; k < nb; ++k) {
+    ctx->potrf_panel[k].off = h.size();
+    for (int i = k + 1; i < nb; ++i) push(i * T, k * T, k * T, (k + 1) * T, i, k);
+    ctx->potrf_panel[k].cnt = h.size() - ctx->potrf_panel[k].off;
+    ctx->potrf_trail[k].off = h.size();
+    // the block column the next panel needs goes first
+    for (int j = k + 1; j < nb; ++j)
+      for (int i = j; i < nb; ++i) push(i * T, j * T, k * T, (k + 1) * T, i, j);
+    ctx->potrf_trail[k].cnt = h.size() - ctx->potrf_trail[k].off;
+  }
+  // TRTRI: nodes by depth, deepest first
+  std::vector<Node> nodes;
+  collect(0, nb, 0, nodes);
+  int maxd = -1;
+  for (auto& n : nodes) maxd = std::max(maxd, n.depth);
+  ctx->trtri_p.clear();
+  ctx->trtri_x.clear();
+  for (int d = maxd; d >= 0; --d) {
+    gps_ctx::Range rp, rx;
+    rp.off = h.size();
+    for (auto& n : nodes)
+      if (n.depth == d)
+        for (int j = n.lo; j < n.mid; ++j)          // longest k-range first within a node
+          for (int i = n.mid; i < n.hi; ++i) push(i * T, j * T, j * T, n.mid * T, i, j);
+    rp.cnt = h.size() - rp.off;
+    rx.off = h.size();
+    for (auto& n : nodes)
+      if (n.depth == d)
+        for (int i = n.hi - 1; i >= n.mid; --i)
+          for (int j = n.lo; j < n.mid; ++j) push(i * T, j * T, n.mid * T, (i + 1) * T, i, j);
+    rx.cnt = h.size() - rx.off;
+    ctx->trtri_p.push_back(rp);
+    ctx->trtri_x.push_back(rx);
+  }
+  // LAUUM: lower tiles, k in [i, nb); longest first
+  ctx->lauum.off = h.size();
+  for (int i = 0; i < nb; ++i)
+    for (int j = 0; j <= i; ++j) push(i * T, j * T, i * T, nb * T, i, j);
+  ctx->lauum.cnt = h.size() - ctx->lauum.off;
+  // SYMPROD: lower tiles, full k
+  ctx->symprod.off = h.size();
+  for (int i = 0; i < nb; ++i)
+    for (int j = 0; j <= i; ++j) push(i * T, j * T, 0, nb * T, i, j);
+  ctx->symprod.cnt = h.size() - ctx->symprod.off;
+
+  if (h.size() > ctx->tasks_cap) {
+    if (ctx->d_tasks) cudaFree(ctx->d_tasks);
+    ctx->d_tasks = nullptr;
+    GPS_CUDA(cudaMalloc(&ctx->d_tasks, h.size() * sizeof(GemmTask)));
+    ctx->tasks_cap = h.size();
+  }
+  GPS_CUDA(cudaMemcpyAsync(ctx->d_tasks, h.data(), h.size() * sizeof(GemmTask), cudaMemcpyHostToDevice,
+                           ctx->stream));
+  GPS_CUDA(cudaStreamSynchronize(ctx->stream));
+  return GPS_OK;
+}
+
+int gps_potrf(gps_ctx* ctx, double* K, double* Xinv, int64_t Np) {
+  const int nb = (int)(Np / T);
+  static bool configured = false;
+  if (!configured) {
+    GPS_CUDA(cudaFuncSetAttribute(potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)POTF2_SMEM));
+    configured = true;
+  }
+  GPS_CUDA(cudaMemsetAsync(ctx->d_info, 0, sizeof(int), ctx->stream));
+  for (int k = 0; k < nb; ++k) {
+    potf2_inv_kernel<<<1, 256, POTF2_SMEM, ctx->stream>>>(K, Xinv, Np, k, ctx->d_info);
+    GPS_LAUNCH_CHECK();
+    ctx->launches++;
+    if (k + 1 < nb) {
+      // panel: L_ik = A_ik * inv(L_kk)'
+      GPS_CHECK(gps_gemm_tasks(ctx, GEMM_KC_KC, K, Np, Xinv, Np, K, Np, 1.0, 0.0, nullptr, false,
+                               ctx->d_tasks + ctx->potrf_panel[k].off, ctx->potrf_panel[k].cnt));
+      // trailing update: A_ij -= L_ik L_jk'
+      GPS_CHECK(gps_gemm_tasks(ctx, GEMM_KC_KC, K, Np, K, Np, K, Np, -1.0, 1.0, nullptr, false,
+                               ctx->d_tasks + ctx->potrf_trail[k].off, ctx->potrf_trail[k].cnt));
+    }
+  }
+  return GPS_OK;
+}
+
+int gps_check_info(gps_ctx* ctx) {
+  int info = 0;
+  GPS_CUDA(cudaMemcpyAsync(&info, ctx->d_info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  GPS_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (info != 0)
+    return gps_fail(ctx, GPS_ENOTPD, "matrix not positive definite: leading minor of order %d", info);
+  return GPS_OK;
+}
+
+int gps_trtri(gps_ctx* ctx, const double* L, double* Xinv, double* scratch, int64_t Np) {
+  for (size_t lv = 0; lv < ctx->trtri_p.size(); ++lv) {
+    // P = L21 * X11
+    GPS_CHECK(gps_gemm_tasks(ctx, GEMM_KC_MC, L, Np, Xinv, Np, scratch, Np, 1.0, 0.0, nullptr, false,
+                             ctx->d_tasks + ctx->trtri_p[lv].off, ctx->trtri_p[lv].cnt));
+    // X21 = -X22 * P
+    GPS_CHECK(gps_gemm_tasks(ctx, GEMM_KC_MC, Xinv, Np, scratch, Np, Xinv, Np, -1.0, 0.0, nullptr, false,
+                             ctx->d_tasks + ctx->trtri_x[lv].off, ctx->trtri_x[lv].cnt));
+  }
+  return GPS_OK;
+}
+
+int gps_lauum(gps_ctx* ctx, const double* Xinv, double* Kinv, int64_t Np) {
+  return gps_gemm_tasks(ctx, GEMM_MC_MC, Xinv, Np, Xinv, Np, Kinv, Np, 1.0, 0.0, nullptr, true,
+                        ctx->d_tasks + ctx->lauum.off, ctx->lauum.cnt);
+}
+
+int gps_symprod(gps_ctx* ctx, const double* Kinv, const double* dvec, double* S, int64_t Np) {
+  return gps_gemm_tasks(ctx, GEMM_KC_KC, Kinv, Np, Kinv, Np, S, Np, 1.0, 0.0, dvec, false,
+                        ctx->d_tasks + ctx->symprod.off, ctx->symprod.cnt);
+}

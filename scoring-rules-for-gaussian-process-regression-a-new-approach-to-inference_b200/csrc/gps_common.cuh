@@ -1,0 +1,170 @@
+// Shared declarations for libgpscore (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/gpscore.h"
+
+#define GPS_TILE 128  // matrix tile edge: every N x N buffer is padded to a multiple of it
+
+struct GemmTask {  // one 128 x 128 output tile of a tile-GEMM launch
+  int32_t a_row;   // first row (KC operand) / first column (MC operand) of the A panel
+  int32_t b_row;   // same for B
+  int32_t k0, k1;  // contraction range in elements, multiples of 16
+  int32_t c_row, c_col;
+  int32_t flags;
+  int32_t pad;
+};
+
+struct DevBuf {
+  double* p = nullptr;
+  size_t n = 0;  // doubles
+};
+
+struct gps_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::string err;
+  int64_t launches = 0;
+  int sm_count = 148;
+  // GEMM timing of the last full eval
+  bool time_gemm = true;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> gemm_events;
+  size_t gemm_events_used = 0;
+  double last_gemm_ms = 0;
+  int64_t last_gemm_launches = 0;
+
+  // ---- training data -------------------------------------------------------------------------
+  int64_t N = 0;   // rows
+  int64_t Np = 0;  // N padded to GPS_TILE
+  int D = 0;
+  DevBuf X;        // [Np, D] row-major, pad rows zero
+  DevBuf y;        // [Np], pad zero
+
+  // ---- full-GP workspaces (allocated lazily) -------------------------------------------------
+  int64_t ws_Np = 0;
+  DevBuf Kb;       // K -> L (lower, in place) -> K^-1 (full symmetric)
+  DevBuf Xb;       // L^-1 (lower block triangle; diagonal blocks fully defined)
+  DevBuf Sb;       // scratch for TRTRI, then S = K^-1 diag(dbar) K^-1 (lower tiles)
+  DevBuf vecs;     // alpha, d, abar, dbar, u, loo_mean, loo_var, logdiag : 8 x Np
+  DevBuf red;      // reduction scratch
+  DevBuf params;   // device copy of theta-derived parameters
+  int* d_info = nullptr;       // device: first failing pivot (0 = ok)
+  GemmTask* d_tasks = nullptr; // device task lists (cached per ws_Np)
+  size_t tasks_cap = 0;
+  GemmTask* d_tasks2 = nullptr; // per-call task lists (prediction, chol_solve)
+  size_t tasks2_cap = 0;
+  DevBuf stage[4];             // staging for host-resident arguments of the element-wise entry points
+  std::vector<GemmTask> h_tasks;
+  bool loo_valid = false;
+  // cached task-list layout for ws_Np (offsets into d_tasks)
+  struct Range { size_t off = 0, cnt = 0; };
+  std::vector<Range> potrf_panel, potrf_trail;
+  std::vector<Range> trtri_p, trtri_x;
+  Range lauum, symprod;
+
+  // ---- FITC state ----------------------------------------------------------------------------
+  struct Fitc {
+    int M = 0, MP = 0, score = 0;
+    double jitter = 0, ea = 0, sn2 = 0;
+    int64_t world_n = 0;
+    int grid = 0;
+    DevBuf V, W;          // [N, MP] row-major
+    DevBuf rowv;          // per-row scalars: lam, lam_bar0, rbar, tbar, alpha, d : 6 x N
+    DevBuf small;         // replicated small matrices (layout in gps_fitc.cu)
+    DevBuf part;          // per-block partial accumulators
+    DevBuf acc1, acc2, acc3;  // single-GPU accumulators
+    bool begun = false, pass2_done = false;
+  } fitc;
+};
+
+int gps_fail(gps_ctx* c, int code, const char* fmt, ...);
+
+#define GPS_CUDA(call)                                                                         \
+  do {                                                                                         \
+    cudaError_t e__ = (call);                                                                  \
+    if (e__ != cudaSuccess)                                                                    \
+      return gps_fail(ctx, GPS_ECUDA, "%s:%d %s -> %s", __FILE__, __LINE__, #call,             \
+                      cudaGetErrorString(e__));                                                \
+  } while (0)
+
+#define GPS_CHECK(call)          \
+  do {                           \
+    int r__ = (call);            \
+    if (r__ != GPS_OK) return r__; \
+  } while (0)
+
+#define GPS_LAUNCH_CHECK() GPS_CUDA(cudaGetLastError())
+
+int gps_ensure(gps_ctx* ctx, DevBuf& b, size_t n);
+bool gps_is_device_ptr(const void* p);
+int gps_stage_in(gps_ctx* ctx, const double* p, size_t n, DevBuf& tmp, const double** out);
+int gps_ensure_ws(gps_ctx* ctx, int64_t Np);
+int gps_upload_params(gps_ctx* ctx, const double* theta, int D, double* ea_out, double* sn2_out);
+int gps_upload_tasks2(gps_ctx* ctx, const std::vector<GemmTask>& h);
+int gps_factor_and_invert(gps_ctx* ctx, bool want_logdet);
+// offsets (doubles) into ctx->params and rows of ctx->vecs
+constexpr int PAR_OBJ = 128;
+constexpr int PAR_GSUM = 136;
+constexpr int PAR_LEN = 512;
+enum { V_ALPHA = 0, V_D, V_ABAR, V_DBAR, V_U, V_LOOM, V_LOOV, V_LOGD, V_COUNT };
+
+static inline int64_t gps_pad(int64_t n) { return (n + GPS_TILE - 1) / GPS_TILE * GPS_TILE; }
+
+// ---- device helpers ----------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// block-wide sum; result valid in thread 0. `sh` must hold >= 32 doubles.
+__device__ __forceinline__ double block_sum(double v, double* sh) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  const int nw = (blockDim.x + 31) >> 5;
+  if (w == 0) {
+    v = lane < nw ? sh[lane] : 0.0;
+    v = warp_sum(v);
+  }
+  return v;
+}
+
+// ---- modules -------------------------------------------------------------------------------------
+// gps_gram.cu
+int gps_gram_sym(gps_ctx* ctx, const double* X, int64_t N, int64_t Np, int D, const double* d_par, double* K);
+int gps_gram_rect(gps_ctx* ctx, const double* x, int64_t n, const double* xp, int64_t m, int D,
+                  const double* d_par, double* out, int64_t ldo);
+// gps_gemm.cu
+enum { GEMM_KC_KC = 0, GEMM_KC_MC = 1, GEMM_MC_MC = 2 };
+int gps_gemm_tasks(gps_ctx* ctx, int kind, const double* A, int64_t lda, const double* B, int64_t ldb,
+                   double* C, int64_t ldc, double alpha, double beta, const double* dvec, bool mirror,
+                   const GemmTask* d_tasks, size_t ntasks);
+// gps_chol.cu
+int gps_build_tasks(gps_ctx* ctx, int64_t Np);
+int gps_potrf(gps_ctx* ctx, double* K, double* Xinv, int64_t Np);       // K -> L in place; diag-block inverses -> Xinv
+int gps_trtri(gps_ctx* ctx, const double* L, double* Xinv, double* scratch, int64_t Np);
+int gps_lauum(gps_ctx* ctx, const double* Xinv, double* Kinv, int64_t Np);
+int gps_symprod(gps_ctx* ctx, const double* Kinv, const double* dvec, double* S, int64_t Np);
+int gps_check_info(gps_ctx* ctx);
+// gps_score.cu
+int gps_symv(gps_ctx* ctx, const double* A, int64_t Np, const double* x, double* y);
+int gps_diag_extract(gps_ctx* ctx, const double* A, int64_t Np, double* d, int do_log);
+int gps_loo_score(gps_ctx* ctx, int score, int64_t N, int64_t Np, const double* alpha, const double* d,
+                  const double* y, double* abar, double* dbar, double* loo_mean, double* loo_var,
+                  double* obj_dev);
+int gps_nlml_value(gps_ctx* ctx, int64_t N, int64_t Np, const double* logdiag, const double* alpha,
+                   const double* y, double* obj_dev);
+int gps_grad_contract(gps_ctx* ctx, int mode, const double* Mx, int64_t N, int64_t Np, const double* X, int D,
+                      const double* d_par, const double* alpha, const double* u, double* out_dev);
+int gps_metrics_kernel(gps_ctx* ctx, const double* mean, const double* var, const double* y, int64_t n,
+                       double ytm, double ytv, double* out_dev);
+int gps_score_kernel(gps_ctx* ctx, const double* m, const double* c, const double* y, int64_t n, int which,
+                     double* out_dev);

@@ -1,0 +1,156 @@
+// Stage-level test hooks and FP64 issue-rate micro-benchmarks (include/gpscore_debug.h).
+#include "../../include/gpscore_debug.h"
+#include "gps_common.cuh"
+
+namespace {
+
+__global__ void __launch_bounds__(256)
+dmma_peak_kernel(int iters, double* out) {
+  double acc[16][2];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i][0] = acc[i][1] = 0.0;
+  double a = 1.0 + threadIdx.x * 1e-9, b = 1.0 - threadIdx.x * 1e-9;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                   : "+d"(acc[i][0]), "+d"(acc[i][1])
+                   : "d"(a), "d"(b));
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += acc[i][0] + acc[i][1];
+  if (s == 123.456) out[0] = s;
+}
+
+__global__ void __launch_bounds__(256)
+dfma_peak_kernel(int iters, double* out) {
+  double acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = i;
+  const double a = 1.0 + threadIdx.x * 1e-12, b = 1e-9;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = fma(acc[i], a, b);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += acc[i];
+  if (s == 123.456) out[0] = s;
+}
+
+}  // namespace
+
+extern "C" {
+
+int gps_dbg_gemm(gps_ctx* ctx, int kind, const double* A, const double* B, double* C, int64_t Mp,
+                 int64_t Npp, int64_t Kp, double alpha, double beta, const double* dvec, int mirror) {
+  if (!ctx) return GPS_EINVAL;
+  if (Mp % GPS_TILE || Npp % GPS_TILE || Kp % GPS_TILE) return gps_fail(ctx, GPS_EINVAL, "dbg_gemm: dims must be multiples of 128");
+  GPS_CUDA(cudaSetDevice(ctx->device));
+  std::vector<GemmTask> tasks;
+  for (int ti = 0; ti < Mp / GPS_TILE; ++ti)
+    for (int tj = 0; tj < Npp / GPS_TILE; ++tj) {
+      if (mirror && tj > ti) continue;
+      GemmTask t;
+      t.a_row = ti * GPS_TILE; t.b_row = tj * GPS_TILE; t.k0 = 0; t.k1 = (int)Kp;
+      t.c_row = ti * GPS_TILE; t.c_col = tj * GPS_TILE; t.flags = 0; t.pad = 0;
+      tasks.push_back(t);
+    }
+  GPS_CHECK(gps_upload_tasks2(ctx, tasks));
+  ctx->gemm_events_used = 0;
+  const int64_t lda = (kind == 2) ? Mp : Kp;
+  const int64_t ldb = (kind == 0) ? Kp : Npp;
+  GPS_CHECK(gps_gemm_tasks(ctx, kind, A, lda, B, ldb, C, Npp, alpha, beta, dvec, mirror != 0, ctx->d_tasks2,
+                           tasks.size()));
+  GPS_CUDA(cudaStreamSynchronize(ctx->stream));
+  float ms = 0;
+  GPS_CUDA(cudaEventElapsedTime(&ms, ctx->gemm_events[0].first, ctx->gemm_events[0].second));
+  ctx->last_gemm_ms = ms;
+  ctx->last_gemm_launches = 1;
+  return GPS_OK;
+}
+
+int gps_dbg_factor(gps_ctx* ctx, const double* A, int64_t n, double* L, double* Linv, double* Ainv) {
+  if (!ctx) return GPS_EINVAL;
+  if (!A || n <= 0) return gps_fail(ctx, GPS_EINVAL, "dbg_factor: bad arguments");
+  GPS_CUDA(cudaSetDevice(ctx->device));
+  const int64_t Np = gps_pad(n);
+  GPS_CHECK(gps_ensure_ws(ctx, Np));
+  ctx->loo_valid = false;
+  ctx->gemm_events_used = 0;
+  GPS_CUDA(cudaMemsetAsync(ctx->Kb.p, 0, (size_t)Np * Np * sizeof(double), ctx->stream));
+  GPS_CUDA(cudaMemsetAsync(ctx->Xb.p, 0, (size_t)Np * Np * sizeof(double), ctx->stream));
+  GPS_CUDA(cudaMemcpy2DAsync(ctx->Kb.p, Np * sizeof(double), A, n * sizeof(double), n * sizeof(double), n,
+                             cudaMemcpyDefault, ctx->stream));
+  std::vector<double> ones((size_t)(Np - n), 1.0);
+  if (Np > n)
+    GPS_CUDA(cudaMemcpy2DAsync(ctx->Kb.p + n * Np + n, (Np + 1) * sizeof(double), ones.data(), sizeof(double),
+                               sizeof(double), Np - n, cudaMemcpyDefault, ctx->stream));
+  GPS_CHECK(gps_potrf(ctx, ctx->Kb.p, ctx->Xb.p, Np));
+  GPS_CHECK(gps_check_info(ctx));
+  if (L)
+    GPS_CUDA(cudaMemcpy2DAsync(L, n * sizeof(double), ctx->Kb.p, Np * sizeof(double), n * sizeof(double), n,
+                               cudaMemcpyDefault, ctx->stream));
+  GPS_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (Linv || Ainv) {
+    GPS_CHECK(gps_trtri(ctx, ctx->Kb.p, ctx->Xb.p, ctx->Sb.p, Np));
+    if (Linv)
+      GPS_CUDA(cudaMemcpy2DAsync(Linv, n * sizeof(double), ctx->Xb.p, Np * sizeof(double), n * sizeof(double), n,
+                                 cudaMemcpyDefault, ctx->stream));
+    GPS_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  if (Ainv) {
+    GPS_CHECK(gps_lauum(ctx, ctx->Xb.p, ctx->Kb.p, Np));
+    GPS_CUDA(cudaMemcpy2DAsync(Ainv, n * sizeof(double), ctx->Kb.p, Np * sizeof(double), n * sizeof(double), n,
+                               cudaMemcpyDefault, ctx->stream));
+    GPS_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  return GPS_OK;
+}
+
+int gps_dbg_fp64_peak(gps_ctx* ctx, int iters, double* dmma_tflops, double* dfma_tflops) {
+  if (!ctx) return GPS_EINVAL;
+  GPS_CUDA(cudaSetDevice(ctx->device));
+  GPS_CHECK(gps_ensure(ctx, ctx->params, PAR_LEN));
+  const int blocks = ctx->sm_count * 4;
+  float ms = 0;
+  for (int rep = 0; rep < 2; ++rep) {
+    GPS_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+    dmma_peak_kernel<<<blocks, 256, 0, ctx->stream>>>(iters, ctx->params.p + 256);
+    GPS_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+    GPS_CUDA(cudaStreamSynchronize(ctx->stream));
+    GPS_LAUNCH_CHECK();
+    GPS_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+  }
+  // per warp instruction: 8*8*4 FMA = 512 flop
+  if (dmma_tflops) *dmma_tflops = (double)blocks * 8 /*warps*/ * 16.0 * iters * 512.0 / (ms * 1e-3) / 1e12;
+  for (int rep = 0; rep < 2; ++rep) {
+    GPS_CUDA(cudaEventRecord(ctx->ev0, ctx->stream));
+    dfma_peak_kernel<<<blocks, 256, 0, ctx->stream>>>(iters, ctx->params.p + 256);
+    GPS_CUDA(cudaEventRecord(ctx->ev1, ctx->stream));
+    GPS_CUDA(cudaStreamSynchronize(ctx->stream));
+    GPS_LAUNCH_CHECK();
+    GPS_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+  }
+  if (dfma_tflops) *dfma_tflops = (double)blocks * 256 * 16.0 * iters * 2.0 / (ms * 1e-3) / 1e12;
+  ctx->launches += 4;
+  return GPS_OK;
+}
+
+int gps_dbg_gram(gps_ctx* ctx, const double* theta, double* K) {
+  if (!ctx) return GPS_EINVAL;
+  if (ctx->N == 0) return gps_fail(ctx, GPS_ESTATE, "dbg_gram: no data");
+  GPS_CUDA(cudaSetDevice(ctx->device));
+  GPS_CHECK(gps_ensure_ws(ctx, ctx->Np));
+  GPS_CHECK(gps_upload_params(ctx, theta, ctx->D, nullptr, nullptr));
+  GPS_CHECK(gps_gram_sym(ctx, ctx->X.p, ctx->N, ctx->Np, ctx->D, ctx->params.p, ctx->Kb.p));
+  // lower tiles only were written: copy the lower triangle, caller mirrors
+  GPS_CUDA(cudaMemcpy2DAsync(K, ctx->N * sizeof(double), ctx->Kb.p, ctx->Np * sizeof(double),
+                             ctx->N * sizeof(double), ctx->N, cudaMemcpyDefault, ctx->stream));
+  GPS_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->loo_valid = false;
+  return GPS_OK;
+}
+
+}  // extern "C"

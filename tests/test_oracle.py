@@ -87,3 +87,35 @@ def test_grid_twins_match_python_forms():
         assert abs(v - O.cal_NLML(x, y, l, j)) < 1e-9 * abs(v)
         _, mu, s2 = O.full_objective(x.reshape(-1, 1), y, theta, O.SCORE_LOGS)
         assert abs(O.logs(mu, s2 + j * j, y) - O.cal_m_logs(x, y, l, j)) < 1e-12
+
+
+# ---- the O(N M^2) Woodbury restatement (algorithm-matched CPU baseline, prototype of the CUDA passes)
+from oracle import woodbury as WB
+
+
+@pytest.mark.parametrize("name", golden_names(("c2", "c4")))
+@pytest.mark.parametrize("score", ["crps", "logs", "nlml"])
+@pytest.mark.parametrize("nslices", [1, 3])
+def test_woodbury_matches_reference(name, score, nslices):
+    g = load_golden(name)
+    n = g["X"].shape[0]
+    cuts = np.linspace(0, n, nslices + 1).astype(int)
+    slices = [slice(cuts[i], cuts[i + 1]) for i in range(nslices)]
+    val, grad, gU, mu, s2 = WB.fitc_obj_grad(g["X"], g["y"], g["U"], g["theta"], O.SCORES[score], row_slices=slices)
+    assert abs(val - g["obj_" + score]) <= OBJ_TOL * abs(g["obj_" + score])
+    ref = grad_vector(g, score)
+    if int(g["d_b"]) == 1 and g["X"].shape[1] > 1:
+        grad = np.concatenate([[grad[0]], [grad[1:-1].sum()], [grad[-1]]])
+    assert relerr(grad, ref) <= GRAD_TOL
+    assert relerr(gU, g["grad_u_" + score]) <= GRAD_TOL
+    if score != "nlml":
+        assert relerr(mu, g["loo_mean_" + score].ravel()) <= 1e-8
+        assert relerr(s2, g["loo_var_" + score].ravel()) <= 1e-8
+
+
+@pytest.mark.parametrize("name", golden_names(("c2", "c4")))
+def test_woodbury_predict(name):
+    g = load_golden(name)
+    mean, var = WB.fitc_predict(g["X"], g["y"], g["U"], g["Xs"], g["theta"])
+    assert relerr(mean, g["pred_mean"]) <= 1e-8
+    assert relerr(var, g["pred_var"]) <= 1e-7
