@@ -1,0 +1,1058 @@
+// FITC objective + gradient in O(N M^2): Woodbury restatement of the dense big_Q path
+// (K20:222-236, K20:329-344, K20:434-452) with the three-pass analytic adjoint of SURVEY.md
+// App. A.2, including the gradient wrt the inducing inputs (K20:247).
+//
+//   begin   replicated: Us = U / l, K_uu, L_A = chol(K_uu + jitter I)
+//   pass 1  rows: k_i -> V_i = L_A^-1 k_i, lambda_i          reduce  C - I = sum V V'/lambda, v_y
+//   pass 2  replicated: L_C, beta;  rows: W_i, d_i, alpha_i, score + seeds
+//                                                             reduce  R = sum rbar W W', beta_bar, obj
+//   pass 3  replicated: C_bar, vy_bar;  rows: lambda_bar, V_bar, Kuf_bar
+//                                                             reduce  S = sum V_bar V', S0, P, g_b, sum lambda_bar
+//   finish  replicated: L_A_bar -> A_bar, kernel-parameter and inducing-input gradients
+//
+// Rows are independent: a rank owns a contiguous block of rows and the three packed
+// accumulators are what gets all-reduced.  One thread owns one row (its M-vectors
+// live in registers, the M x M factors are broadcast from shared memory); the M x M outer-product
+// reductions over the block's 128 rows run on the DMMA tensor path from transposed shared tiles.
+// M is padded to MP = 8, 16, 24 or 32 (pad inducing points have k = 0 and an identity factor).
+#include "gps_common.cuh"
+
+namespace {
+
+constexpr int RB = 128;        // rows per block iteration = threads per block
+constexpr int LDT = RB + 4;    // transposed tile stride: conflict-free for row-owner writes and DMMA loads
+constexpr double INV_SQRT_PI = 0.56418958354775628695;
+constexpr double INV_SQRT_2PI = 0.39894228040143267794;
+constexpr double INV_SQRT2 = 0.70710678118654752440;
+constexpr double HALF_LOG_2PI = 0.91893853320467274178;
+
+__device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+// layout of the replicated small-matrix buffer (doubles), MP-strided
+struct SmallLayout {
+  int us, la, lai, kuu, lc, lci, beta, bbar, cbar, vyb, total;
+  __host__ __device__ SmallLayout(int MP, int D) {
+    int o = 0;
+    us = o;   o += MP * D;
+    la = o;   o += MP * MP;
+    lai = o;  o += MP;
+    kuu = o;  o += MP * MP;
+    lc = o;   o += MP * MP;
+    lci = o;  o += MP;
+    beta = o; o += MP;
+    bbar = o; o += MP;
+    cbar = o; o += MP * MP;
+    vyb = o;  o += MP;
+    total = o;
+  }
+};
+
+// ---- small dense helpers, executed by ONE WARP on matrices in shared memory ---------------------
+// In-place lower Cholesky of A[n][ld]; returns first bad pivot (1-based) or 0.  Strict upper part zeroed.
+__device__ int warp_chol(double* A, int n, int ld, int lane) {
+  int bad = 0;
+  for (int j = 0; j < n; ++j) {
+    double s = 0.0;
+    if (lane >= j && lane < n) {
+      s = A[lane * ld + j];
+      for (int k = 0; k < j; ++k) s -= A[lane * ld + k] * A[j * ld + k];
+    }
+    double piv = __shfl_sync(0xffffffffu, s, j);
+    if (!(piv > 0.0)) {
+      if (!bad) bad = j + 1;
+      piv = 1.0;
+    }
+    const double sq = sqrt(piv);
+    __syncwarp();
+    if (lane == j) A[j * ld + j] = sq;
+    else if (lane > j && lane < n) A[lane * ld + j] = s / sq;
+    else if (lane < j) A[lane * ld + j] = 0.0;
+    __syncwarp();
+  }
+  return bad;
+}
+
+// Solve L' X = B in place for the n columns of B[n][ld] (lane = column), L lower [n][ld].
+__device__ void warp_solve_LT(const double* L, double* B, int n, int ld, int lane) {
+  if (lane < n) {
+    for (int i = n - 1; i >= 0; --i) {
+      double s = B[i * ld + lane];
+      for (int k = i + 1; k < n; ++k) s -= L[k * ld + i] * B[k * ld + lane];
+      B[i * ld + lane] = s / L[i * ld + i];
+    }
+  }
+  __syncwarp();
+}
+
+// Abar = 0.5 L^-T (P + P') L^-1 with P = Phi(L' Lbar); Lbar [n][ld] is overwritten with Abar.
+// tmp [n][ld] scratch.
+__device__ void warp_chol_adjoint(const double* L, double* Lbar, double* tmp, int n, int ld, int lane) {
+  // P = tril(L' Lbar), diagonal halved -> tmp (lane = column c)
+  if (lane < n) {
+    for (int r = 0; r < n; ++r) {
+      double s = 0.0;
+      if (r >= lane) {
+        for (int k = r; k < n; ++k) s += L[k * ld + r] * Lbar[k * ld + lane];  // L'[r][k] = L[k][r], k >= r
+        if (r == lane) s *= 0.5;
+      }
+      tmp[r * ld + lane] = s;
+    }
+  }
+  __syncwarp();
+  // Z = P + P' -> Lbar
+  if (lane < n)
+    for (int r = 0; r < n; ++r) Lbar[r * ld + lane] = tmp[r * ld + lane] + tmp[lane * ld + r];
+  __syncwarp();
+  warp_solve_LT(L, Lbar, n, ld, lane);          // Y = L^-T Z
+  if (lane < n)
+    for (int r = 0; r < n; ++r) tmp[r * ld + lane] = Lbar[lane * ld + r];  // Y'
+  __syncwarp();
+  warp_solve_LT(L, tmp, n, ld, lane);           // L^-T Y' = (Y L^-1)'
+  if (lane < n)
+    for (int r = 0; r < n; ++r) Lbar[r * ld + lane] = 0.5 * tmp[lane * ld + r];
+  __syncwarp();
+}
+
+// ---- begin: replicated K_uu and its factor --------------------------------------------------------
+__global__ void __launch_bounds__(32)
+fitc_small0_kernel(const double* __restrict__ U, const double* __restrict__ par, double* __restrict__ small,
+                   int M, int MP, int D, double jitter, int* __restrict__ info) {
+  extern __shared__ double sh[];
+  const SmallLayout lo(MP, D);
+  double* A = sh;  // [MP][MP]
+  const int lane = threadIdx.x;
+  const double ea = par[0];
+  for (int e = lane; e < MP * D; e += 32) {
+    const int m = e / D, d = e - m * D;
+    small[lo.us + e] = (m < M) ? U[m * D + d] * par[2 + d] : 0.0;
+  }
+  __syncwarp();
+  for (int e = lane; e < MP * MP; e += 32) {
+    const int i = e / MP, j = e - i * MP;
+    double v = 0.0;
+    if (i < M && j < M) {
+      double r2 = 0.0;
+      for (int d = 0; d < D; ++d) {
+        const double df = small[lo.us + i * D + d] - small[lo.us + j * D + d];
+        r2 = fma(df, df, r2);
+      }
+      v = ea * exp(-0.5 * r2);
+    }
+    small[lo.kuu + e] = v;
+    A[e] = v + ((i == j) ? ((i < M) ? jitter : 1.0) : 0.0);
+  }
+  __syncwarp();
+  const int bad = warp_chol(A, MP, MP, lane);
+  if (bad && lane == 0) atomicCAS(info, 0, bad);
+  for (int e = lane; e < MP * MP; e += 32) small[lo.la + e] = A[e];
+  if (lane < MP) small[lo.lai + lane] = 1.0 / A[lane * MP + lane];
+}
+
+// per-row kernel vector k_m = ea exp(-0.5 |us_m - xs|^2); xs read from the transposed tile column `tid`
+template <int MP>
+__device__ __forceinline__ void kernel_vec(const double* __restrict__ Us, const double* __restrict__ XsT, int tid,
+                                           int M, int D, double ea, double* k) {
+#pragma unroll
+  for (int m = 0; m < MP; ++m) {
+    double r2 = 0.0;
+    for (int d = 0; d < D; ++d) {
+      const double df = Us[m * D + d] - XsT[d * LDT + tid];
+      r2 = fma(df, df, r2);
+    }
+    k[m] = (m < M) ? ea * exp(-0.5 * r2) : 0.0;
+  }
+}
+
+template <int MP>
+__device__ __forceinline__ void fwd_subst(const double* __restrict__ L, const double* __restrict__ Li, double* v) {
+#pragma unroll
+  for (int m = 0; m < MP; ++m) {
+    double s = v[m];
+#pragma unroll
+    for (int j = 0; j < m; ++j) s = fma(-L[m * MP + j], v[j], s);
+    v[m] = s * Li[m];
+  }
+}
+
+template <int MP>
+__device__ __forceinline__ void bwd_subst_T(const double* __restrict__ L, const double* __restrict__ Li, double* v) {
+#pragma unroll
+  for (int m = MP - 1; m >= 0; --m) {
+    double s = v[m];
+#pragma unroll
+    for (int j = m + 1; j < MP; ++j) s = fma(-L[j * MP + m], v[j], s);
+    v[m] = s * Li[m];
+  }
+}
+
+// warp-level accumulation over this warp's 32 rows of the transposed tiles:
+//   C[mf][nf] += sum_r A_T[m][r] * (B_T[n][r] * bscale[r])
+template <int MFR, int NFR, bool SCALE>
+__device__ __forceinline__ void tile_outer(const double* __restrict__ AT, const double* __restrict__ BT,
+                                           const double* __restrict__ bscale, int warp, int lane,
+                                           double (&acc)[MFR][NFR][2]) {
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int kk = 0; kk < 8; ++kk) {
+    const int r = warp * 32 + kk * 4 + t;
+    double a[MFR], b[NFR];
+#pragma unroll
+    for (int i = 0; i < MFR; ++i) a[i] = AT[(i * 8 + g) * LDT + r];
+    const double sc = SCALE ? bscale[r] : 1.0;
+#pragma unroll
+    for (int j = 0; j < NFR; ++j) b[j] = BT[(j * 8 + g) * LDT + r] * sc;
+#pragma unroll
+    for (int i = 0; i < MFR; ++i)
+#pragma unroll
+      for (int j = 0; j < NFR; ++j) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+  }
+}
+
+// column accumulation: c[mf] += sum_r A_T[m][r] * col[r]   (result sits in fragment column 0)
+template <int MFR>
+__device__ __forceinline__ void tile_col(const double* __restrict__ AT, const double* __restrict__ col, int warp,
+                                         int lane, double (&acc)[MFR][2]) {
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int kk = 0; kk < 8; ++kk) {
+    const int r = warp * 32 + kk * 4 + t;
+    const double b = (g == 0) ? col[r] : 0.0;
+#pragma unroll
+    for (int i = 0; i < MFR; ++i) dmma(acc[i][0], acc[i][1], AT[(i * 8 + g) * LDT + r], b);
+  }
+}
+
+// sum the four warps' fragments into shared Cs[MROWS][ncols] (zeroed by the caller), serially per warp
+template <int MFR, int NFR>
+__device__ __forceinline__ void frags_to_smem(double (&acc)[MFR][NFR][2], double* Cs, int ncols, int warp, int lane) {
+  const int g = lane >> 2, t = lane & 3;
+  for (int w = 0; w < 4; ++w) {
+    if (warp == w) {
+#pragma unroll
+      for (int i = 0; i < MFR; ++i)
+#pragma unroll
+        for (int j = 0; j < NFR; ++j) {
+          Cs[(i * 8 + g) * ncols + j * 8 + 2 * t] += acc[i][j][0];
+          Cs[(i * 8 + g) * ncols + j * 8 + 2 * t + 1] += acc[i][j][1];
+        }
+    }
+    __syncthreads();
+  }
+}
+
+template <int MFR>
+__device__ __forceinline__ void colfrag_to_smem(double (&acc)[MFR][2], double* vs, int warp, int lane) {
+  const int g = lane >> 2, t = lane & 3;
+  for (int w = 0; w < 4; ++w) {
+    if (warp == w && t == 0) {
+#pragma unroll
+      for (int i = 0; i < MFR; ++i) vs[i * 8 + g] += acc[i][0];
+    }
+    __syncthreads();
+  }
+}
+
+// ---- pass 1 ---------------------------------------------------------------------------------------
+// part1[block] = [ sum V V'/lambda (MP*MP) | sum V y/lambda (MP) ]
+template <int MP>
+__global__ void __launch_bounds__(RB)
+fitc_row1_kernel(const double* __restrict__ X, const double* __restrict__ y, int64_t N, int D, int M,
+                 const double* __restrict__ par, const double* __restrict__ small, double* __restrict__ Vg,
+                 double* __restrict__ lamg, double* __restrict__ part) {
+  extern __shared__ double sh[];
+  constexpr int MF = MP / 8;
+  const SmallLayout lo(MP, D);
+  double* Us = sh;                       // [MP][D]
+  double* LA = Us + MP * D;              // [MP][MP]
+  double* LAi = LA + MP * MP;            // [MP]
+  double* XsT = LAi + MP;                // [D][LDT]
+  double* WT = XsT + (size_t)D * LDT;    // [MP][LDT]   v / sqrt(lambda)
+  double* Ys = WT + (size_t)MP * LDT;    // [RB]        y / sqrt(lambda)
+  double* Cs = Ys + RB;                  // [MP][MP] + [MP]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int e = tid; e < MP * D; e += RB) Us[e] = small[lo.us + e];
+  for (int e = tid; e < MP * MP; e += RB) LA[e] = small[lo.la + e];
+  if (tid < MP) LAi[tid] = small[lo.lai + tid];
+  for (int e = tid; e < MP * MP + MP; e += RB) Cs[e] = 0.0;
+  const double ea = par[0], sn2 = par[1];
+  double cacc[MF][MF][2], vacc[MF][2];
+#pragma unroll
+  for (int i = 0; i < MF; ++i) {
+    vacc[i][0] = vacc[i][1] = 0.0;
+#pragma unroll
+    for (int j = 0; j < MF; ++j) cacc[i][j][0] = cacc[i][j][1] = 0.0;
+  }
+  __syncthreads();
+  for (int64_t base = (int64_t)blockIdx.x * RB; base < N; base += (int64_t)gridDim.x * RB) {
+    const int64_t i = base + tid;
+    const bool live = i < N;
+    for (int d = 0; d < D; ++d) XsT[d * LDT + tid] = live ? X[i * D + d] * par[2 + d] : 0.0;
+    double v[MP];
+    kernel_vec<MP>(Us, XsT, tid, M, D, ea, v);
+    fwd_subst<MP>(LA, LAi, v);
+    double q = 0.0;
+#pragma unroll
+    for (int m = 0; m < MP; ++m) q = fma(v[m], v[m], q);
+    const double lam = ea - q + sn2;
+    const double rs = live ? rsqrt(lam) : 0.0;
+    if (live) {
+      lamg[i] = lam;
+#pragma unroll
+      for (int m = 0; m < MP; ++m) Vg[i * MP + m] = v[m];
+    }
+    // rsqrt() is approximate in fp64: refine once (Newton) so that rs^2 = 1/lambda to rounding
+    const double rs2 = live ? rs * (1.5 - 0.5 * lam * rs * rs) : 0.0;
+#pragma unroll
+    for (int m = 0; m < MP; ++m) WT[m * LDT + tid] = v[m] * rs2;
+    Ys[tid] = live ? y[i] * rs2 : 0.0;
+    __syncwarp();
+    tile_outer<MF, MF, false>(WT, WT, nullptr, warp, lane, cacc);
+    tile_col<MF>(WT, Ys, warp, lane, vacc);
+    __syncwarp();
+  }
+  frags_to_smem<MF, MF>(cacc, Cs, MP, warp, lane);
+  colfrag_to_smem<MF>(vacc, Cs + MP * MP, warp, lane);
+  for (int e = tid; e < MP * MP + MP; e += RB) part[(int64_t)blockIdx.x * (MP * MP + MP) + e] = Cs[e];
+}
+
+// acc[e] = sum_b part[b][e]
+__global__ void __launch_bounds__(256)
+fitc_reduce_kernel(const double* __restrict__ part, int nblocks, int len, double* __restrict__ acc) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= len) return;
+  double s = 0.0;
+  for (int b = 0; b < nblocks; ++b) s += part[(int64_t)b * len + e];
+  acc[e] = s;
+}
+
+// ---- replicated step before pass 2: C = I + acc1, L_C, beta -----------------------------------------
+__global__ void __launch_bounds__(32)
+fitc_small1_kernel(const double* __restrict__ acc1, double* __restrict__ small, int MP, int D,
+                   int* __restrict__ info) {
+  extern __shared__ double sh[];
+  const SmallLayout lo(MP, D);
+  double* C = sh;
+  const int lane = threadIdx.x;
+  for (int e = lane; e < MP * MP; e += 32) {
+    const int i = e / MP, j = e - i * MP;
+    C[e] = acc1[e] + (i == j ? 1.0 : 0.0);
+  }
+  __syncwarp();
+  const int bad = warp_chol(C, MP, MP, lane);
+  if (bad && lane == 0) atomicCAS(info, 0, 1000000 + bad);
+  for (int e = lane; e < MP * MP; e += 32) small[lo.lc + e] = C[e];
+  if (lane < MP) small[lo.lci + lane] = 1.0 / C[lane * MP + lane];
+  __syncwarp();
+  if (lane == 0) {  // beta = L_C^-1 v_y
+    for (int m = 0; m < MP; ++m) {
+      double s = acc1[MP * MP + m];
+      for (int j = 0; j < m; ++j) s -= C[m * MP + j] * small[lo.beta + j];
+      small[lo.beta + m] = s / C[m * MP + m];
+    }
+  }
+}
+
+// ---- pass 2 ---------------------------------------------------------------------------------------
+// part2[block] = [ sum rbar W W' (MP*MP) | sum tbar W (MP) | obj partial ]
+template <int MP>
+__global__ void __launch_bounds__(RB)
+fitc_row2_kernel(const double* __restrict__ y, int64_t N, int D, int score, double invN,
+                 const double* __restrict__ small, const double* __restrict__ Vg, double* __restrict__ Wg,
+                 double* __restrict__ rowv, double* __restrict__ part) {
+  extern __shared__ double sh[];
+  constexpr int MF = MP / 8;
+  const SmallLayout lo(MP, D);
+  double* LC = sh;                  // [MP][MP]
+  double* LCi = LC + MP * MP;       // [MP]
+  double* beta = LCi + MP;          // [MP]
+  double* WT = beta + MP;           // [MP][LDT]
+  double* rbs = WT + (size_t)MP * LDT;  // [RB]
+  double* tbs = rbs + RB;           // [RB]
+  double* Cs = tbs + RB;            // [MP][MP] + [MP]
+  double* red = Cs + MP * MP + MP;  // [32]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int e = tid; e < MP * MP; e += RB) LC[e] = small[lo.lc + e];
+  if (tid < MP) {
+    LCi[tid] = small[lo.lci + tid];
+    beta[tid] = small[lo.beta + tid];
+  }
+  for (int e = tid; e < MP * MP + MP; e += RB) Cs[e] = 0.0;
+  double racc[MF][MF][2], bacc[MF][2];
+#pragma unroll
+  for (int i = 0; i < MF; ++i) {
+    bacc[i][0] = bacc[i][1] = 0.0;
+#pragma unroll
+    for (int j = 0; j < MF; ++j) racc[i][j][0] = racc[i][j][1] = 0.0;
+  }
+  double obj = 0.0;
+  __syncthreads();
+  double* lamg = rowv;
+  double* lb0g = rowv + N;
+  double* rbg = rowv + 2 * N;
+  double* tbg = rowv + 3 * N;
+  double* alg = rowv + 4 * N;
+  double* dg = rowv + 5 * N;
+  for (int64_t base = (int64_t)blockIdx.x * RB; base < N; base += (int64_t)gridDim.x * RB) {
+    const int64_t i = base + tid;
+    const bool live = i < N;
+    double w[MP];
+#pragma unroll
+    for (int m = 0; m < MP; ++m) w[m] = live ? Vg[i * MP + m] : 0.0;
+    fwd_subst<MP>(LC, LCi, w);
+    double rbar = 0.0, tbar = 0.0;
+    if (live) {
+      double r = 0.0, wb = 0.0;
+#pragma unroll
+      for (int m = 0; m < MP; ++m) {
+        r = fma(w[m], w[m], r);
+        wb = fma(w[m], beta[m], wb);
+      }
+      const double lam = lamg[i], yi = y[i];
+      const double il = 1.0 / lam;
+      const double d = il - r * il * il;
+      const double alpha = (yi - wb) * il;
+      double abar, dbar, lb0 = 0.0;
+      if (score == GPS_CRPS) {
+        const double s2 = 1.0 / d, s = sqrt(s2), z = alpha * s;
+        const double tpm1 = erf(z * INV_SQRT2);
+        const double g = z * tpm1 + 2.0 * INV_SQRT_2PI * exp(-0.5 * z * z) - INV_SQRT_PI;
+        obj += s * g * invN;
+        abar = tpm1 * s2 * invN;
+        dbar = -(0.5 * s2 * s * g + 0.5 * tpm1 * alpha * s2 * s2) * invN;
+      } else if (score == GPS_LOGS) {
+        const double s2 = 1.0 / d;
+        obj += (0.5 * alpha * alpha * s2 - 0.5 * log(d) + HALF_LOG_2PI) * invN;
+        abar = alpha * s2 * invN;
+        dbar = -(0.5 * alpha * alpha * s2 * s2 + 0.5 * s2) * invN;
+      } else {  // NLML: 0.5 log lambda + 0.5 y alpha per row (K20:337-340 through Woodbury)
+        obj += 0.5 * log(lam) + 0.5 * yi * alpha;
+        abar = 0.5 * yi;
+        dbar = 0.0;
+        lb0 = 0.5 * il;
+      }
+      lb0 += dbar * (-il * il + 2.0 * r * il * il * il) - abar * alpha * il;
+      rbar = -dbar * il * il;
+      tbar = -abar * il;
+      lb0g[i] = lb0;
+      rbg[i] = rbar;
+      tbg[i] = tbar;
+      alg[i] = alpha;
+      dg[i] = d;
+#pragma unroll
+      for (int m = 0; m < MP; ++m) Wg[i * MP + m] = w[m];
+    }
+#pragma unroll
+    for (int m = 0; m < MP; ++m) WT[m * LDT + tid] = w[m];
+    rbs[tid] = rbar;
+    tbs[tid] = tbar;
+    __syncwarp();
+    tile_outer<MF, MF, true>(WT, WT, rbs, warp, lane, racc);
+    tile_col<MF>(WT, tbs, warp, lane, bacc);
+    __syncwarp();
+  }
+  frags_to_smem<MF, MF>(racc, Cs, MP, warp, lane);
+  colfrag_to_smem<MF>(bacc, Cs + MP * MP, warp, lane);
+  const double o = block_sum(obj, red);
+  const int len = MP * MP + MP + 1;
+  for (int e = tid; e < MP * MP + MP; e += RB) part[(int64_t)blockIdx.x * len + e] = Cs[e];
+  if (tid == 0) part[(int64_t)blockIdx.x * len + MP * MP + MP] = o;
+}
+
+// ---- replicated step before pass 3: C_bar, vy_bar ----------------------------------------------------
+__global__ void __launch_bounds__(32)
+fitc_small2_kernel(const double* __restrict__ acc2, double* __restrict__ small, int M, int MP, int D, int score) {
+  extern __shared__ double sh[];
+  const SmallLayout lo(MP, D);
+  double* LC = sh;               // [MP][MP]
+  double* Lb = LC + MP * MP;     // [MP][MP]  S_W -> L_C_bar -> C_bar
+  double* tmp = Lb + MP * MP;    // [MP][MP]
+  double* vb = tmp + MP * MP;    // [MP]
+  const int lane = threadIdx.x;
+  for (int e = lane; e < MP * MP; e += 32) LC[e] = small[lo.lc + e];
+  __syncwarp();
+  for (int e = lane; e < MP * MP; e += 32) {
+    const int i = e / MP, j = e - i * MP;
+    const double bi = small[lo.beta + i], bj = small[lo.beta + j];
+    const double bbi = acc2[MP * MP + i], bbj = acc2[MP * MP + j];
+    Lb[e] = bi * bbj + 2.0 * acc2[e] + bbi * bj;   // S_W
+  }
+  if (lane < MP) {
+    small[lo.bbar + lane] = acc2[MP * MP + lane];
+    vb[lane] = acc2[MP * MP + lane];
+  }
+  __syncwarp();
+  warp_solve_LT(LC, Lb, MP, MP, lane);             // L_C^-T S_W
+  for (int e = lane; e < MP * MP; e += 32) {
+    const int i = e / MP, j = e - i * MP;
+    double v = (j <= i) ? -Lb[e] : 0.0;
+    if (score == GPS_NLML && i == j && i < M) v += 1.0 / LC[e];   // d/dL_C of sum log diag(L_C)
+    Lb[e] = v;
+  }
+  __syncwarp();
+  warp_chol_adjoint(LC, Lb, tmp, MP, MP, lane);
+  for (int e = lane; e < MP * MP; e += 32) small[lo.cbar + e] = Lb[e];
+  // vy_bar = L_C^-T beta_bar  (treat as one column: lane 0)
+  if (lane == 0) {
+    for (int i = MP - 1; i >= 0; --i) {
+      double s = vb[i];
+      for (int k = i + 1; k < MP; ++k) s -= LC[k * MP + i] * vb[k];
+      vb[i] = s / LC[i * MP + i];
+    }
+  }
+  __syncwarp();
+  if (lane < MP) small[lo.vyb + lane] = vb[lane];
+}
+
+// ---- pass 3 ---------------------------------------------------------------------------------------
+// part3[block] = [ S = sum Vbar V' (MP*MP) | P = sum G [xs | 1] (MP * 8*NF) | g_b rows (D) | sum lambda_bar ]
+template <int MP, int NF>
+__global__ void __launch_bounds__(RB)
+fitc_row3_kernel(const double* __restrict__ X, const double* __restrict__ y, int64_t N, int D, int M,
+                 const double* __restrict__ par, const double* __restrict__ small,
+                 const double* __restrict__ Vg, const double* __restrict__ Wg, const double* __restrict__ rowv,
+                 double* __restrict__ part) {
+  extern __shared__ double sh[];
+  constexpr int MF = MP / 8;
+  constexpr int PC = 8 * NF;         // columns of P: xs_0..xs_{D-1}, 1, zero padding
+  const SmallLayout lo(MP, D);
+  double* Us = sh;                          // [MP][D]
+  double* LA = Us + MP * D;                 // [MP][MP]
+  double* LAi = LA + MP * MP;               // [MP]
+  double* LC = LAi + MP;                    // [MP][MP]
+  double* LCi = LC + MP * MP;               // [MP]
+  double* Cb = LCi + MP;                    // [MP][MP]
+  double* beta = Cb + MP * MP;              // [MP]
+  double* bbar = beta + MP;                 // [MP]
+  double* vyb = bbar + MP;                  // [MP]
+  double* XsT = vyb + MP;                   // [PC][LDT]
+  double* VT = XsT + (size_t)PC * LDT;      // [MP][LDT]   V
+  double* VbT = VT + (size_t)MP * LDT;      // [MP][LDT]   V_bar
+  double* GT = VbT + (size_t)MP * LDT;      // [MP][LDT]   G = Kuf_bar o Kuf
+  double* gbs = GT + (size_t)MP * LDT;      // [D][RB]     per-thread g_b partials
+  double* Cs = gbs + (size_t)D * RB;        // [MP][MP] + [MP][PC]
+  double* red = Cs + MP * MP + MP * PC;     // [32]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int e = tid; e < MP * D; e += RB) Us[e] = small[lo.us + e];
+  for (int e = tid; e < MP * MP; e += RB) {
+    LA[e] = small[lo.la + e];
+    LC[e] = small[lo.lc + e];
+    Cb[e] = small[lo.cbar + e];
+  }
+  if (tid < MP) {
+    LAi[tid] = small[lo.lai + tid];
+    LCi[tid] = small[lo.lci + tid];
+    beta[tid] = small[lo.beta + tid];
+    bbar[tid] = small[lo.bbar + tid];
+    vyb[tid] = small[lo.vyb + tid];
+  }
+  for (int e = tid; e < MP * MP + MP * PC; e += RB) Cs[e] = 0.0;
+  for (int d = 0; d < D; ++d) gbs[d * RB + tid] = 0.0;
+  for (int c = D + 1; c < PC; ++c) XsT[c * LDT + tid] = 0.0;
+  double sacc[MF][MF][2], pacc[MF][NF][2];
+#pragma unroll
+  for (int i = 0; i < MF; ++i) {
+#pragma unroll
+    for (int j = 0; j < MF; ++j) sacc[i][j][0] = sacc[i][j][1] = 0.0;
+#pragma unroll
+    for (int j = 0; j < NF; ++j) pacc[i][j][0] = pacc[i][j][1] = 0.0;
+  }
+  double sum_lb = 0.0;
+  const double ea = par[0];
+  const double* lamg = rowv;
+  const double* lb0g = rowv + N;
+  const double* rbg = rowv + 2 * N;
+  const double* tbg = rowv + 3 * N;
+  __syncthreads();
+  for (int64_t base = (int64_t)blockIdx.x * RB; base < N; base += (int64_t)gridDim.x * RB) {
+    const int64_t i = base + tid;
+    const bool live = i < N;
+    for (int d = 0; d < D; ++d) XsT[d * LDT + tid] = live ? X[i * D + d] * par[2 + d] : 0.0;
+    XsT[D * LDT + tid] = live ? 1.0 : 0.0;
+    double v[MP], cv[MP], w[MP];
+#pragma unroll
+    for (int m = 0; m < MP; ++m) {
+      v[m] = live ? Vg[i * MP + m] : 0.0;
+      w[m] = live ? Wg[i * MP + m] : 0.0;
+      VT[m * LDT + tid] = v[m];
+    }
+    const double lam = live ? lamg[i] : 1.0, yi = live ? y[i] : 0.0;
+    const double il = 1.0 / lam;
+    const double rbar = live ? rbg[i] : 0.0, tbar = live ? tbg[i] : 0.0;
+    // cv = C_bar v ; s1 = v' C_bar v ; bw = beta_bar' w
+    double s1 = 0.0, bw = 0.0;
+#pragma unroll
+    for (int m = 0; m < MP; ++m) {
+      double s = 0.0;
+#pragma unroll
+      for (int j = 0; j < MP; ++j) s = fma(Cb[m * MP + j], v[j], s);
+      cv[m] = s;
+      s1 = fma(v[m], s, s1);
+      bw = fma(bbar[m], w[m], bw);
+    }
+    const double lb = live ? (lb0g[i] - bw * yi * il * il - s1 * il * il) : 0.0;
+    sum_lb += lb;
+    // W_bar = tbar beta + 2 rbar w  (in place), then V_bar = L_C^-T W_bar + vy_bar y/lam + 2 cv/lam - 2 lb v
+#pragma unroll
+    for (int m = 0; m < MP; ++m) w[m] = fma(tbar, beta[m], 2.0 * rbar * w[m]);
+    bwd_subst_T<MP>(LC, LCi, w);
+#pragma unroll
+    for (int m = 0; m < MP; ++m) {
+      w[m] += vyb[m] * yi * il + 2.0 * cv[m] * il - 2.0 * lb * v[m];
+      VbT[m * LDT + tid] = w[m];
+    }
+    // Kuf_bar = L_A^-T V_bar (in place), G = Kuf_bar o Kuf, g_b rows
+    bwd_subst_T<MP>(LA, LAi, w);
+#pragma unroll
+    for (int m = 0; m < MP; ++m) {
+      double r2 = 0.0;
+      for (int d = 0; d < D; ++d) {
+        const double df = Us[m * D + d] - XsT[d * LDT + tid];
+        r2 = fma(df, df, r2);
+      }
+      const double gm = (m < M && live) ? w[m] * ea * exp(-0.5 * r2) : 0.0;
+      GT[m * LDT + tid] = gm;
+      for (int d = 0; d < D; ++d) {
+        const double df = Us[m * D + d] - XsT[d * LDT + tid];
+        gbs[d * RB + tid] = fma(gm, df * df, gbs[d * RB + tid]);
+      }
+    }
+    __syncwarp();
+    tile_outer<MF, MF, false>(VbT, VT, nullptr, warp, lane, sacc);
+    tile_outer<MF, NF, false>(GT, XsT, nullptr, warp, lane, pacc);
+    __syncwarp();
+  }
+  frags_to_smem<MF, MF>(sacc, Cs, MP, warp, lane);
+  frags_to_smem<MF, NF>(pacc, Cs + MP * MP, PC, warp, lane);
+  const int len = MP * MP + MP * PC + D + 1;
+  double* out = part + (int64_t)blockIdx.x * len;
+  for (int e = tid; e < MP * MP + MP * PC; e += RB) out[e] = Cs[e];
+  for (int d = 0; d < D; ++d) {
+    const double s = block_sum(gbs[d * RB + tid], red);
+    if (tid == 0) out[MP * MP + MP * PC + d] = s;
+  }
+  const double s = block_sum(sum_lb, red);
+  if (tid == 0) out[MP * MP + MP * PC + D] = s;
+}
+
+// ---- finish: L_A_bar -> A_bar, all gradients --------------------------------------------------------
+// out = [obj | g_theta (D+2) | g_U (M*D)]
+__global__ void __launch_bounds__(32)
+fitc_small3_kernel(const double* __restrict__ acc2, const double* __restrict__ acc3,
+                   const double* __restrict__ small, const double* __restrict__ par, int M, int MP, int D,
+                   int PC, int score, double world_n, double* __restrict__ out) {
+  extern __shared__ double sh[];
+  const SmallLayout lo(MP, D);
+  double* LA = sh;               // [MP][MP]
+  double* Lb = LA + MP * MP;     // S -> L_A_bar -> A_bar -> G2
+  double* tmp = Lb + MP * MP;
+  double* red = tmp + MP * MP;   // [32]
+  const int lane = threadIdx.x;
+  for (int e = lane; e < MP * MP; e += 32) {
+    LA[e] = small[lo.la + e];
+    Lb[e] = acc3[e];
+  }
+  __syncwarp();
+  warp_solve_LT(LA, Lb, MP, MP, lane);     // L_A^-T S
+  for (int e = lane; e < MP * MP; e += 32) {
+    const int i = e / MP, j = e - i * MP;
+    Lb[e] = (j <= i) ? -Lb[e] : 0.0;
+  }
+  __syncwarp();
+  warp_chol_adjoint(LA, Lb, tmp, MP, MP, lane);
+  for (int e = lane; e < MP * MP; e += 32) Lb[e] *= small[lo.kuu + e];   // G2 = A_bar o K_uu
+  __syncwarp();
+  const double* P = acc3 + MP * MP;          // [MP][PC]
+  const double* gbrow = P + MP * PC;         // [D]
+  const double sum_lb = gbrow[D];
+  const double ea = par[0], sn2 = par[1];
+  // g_a = ea * sum_lb + sum_m S0_m + sum G2
+  double s = 0.0;
+  for (int e = lane; e < MP * MP; e += 32) s += Lb[e];
+  for (int m = lane; m < MP; m += 32) s += P[m * PC + D];
+  s = warp_sum(s);
+  if (lane == 0) {
+    double obj = acc2[MP * MP + MP];
+    if (score == GPS_NLML) {
+      obj += 0.5 * world_n * 1.83787706640934548356;  // N/2 log 2 pi
+      for (int m = 0; m < M; ++m) obj -= log(small[lo.lci + m]);   // + sum log diag(L_C)
+    }
+    out[0] = obj;
+    out[1] = ea * sum_lb + s;
+    out[1 + D + 1] = sn2 * sum_lb;
+  }
+  const double* Us = small + lo.us;
+  for (int d = 0; d < D; ++d) {
+    double sb = 0.0;
+    for (int e = lane; e < MP * MP; e += 32) {
+      const int i = e / MP, j = e - i * MP;
+      const double df = Us[i * D + d] - Us[j * D + d];
+      sb = fma(Lb[e], df * df, sb);
+    }
+    sb = warp_sum(sb);
+    if (lane == 0) out[2 + d] = gbrow[d] + sb;
+  }
+  // g_U[m][d] = -invl_d ( us_md S0_m - P_md ) - 2 invl_d sum_m' G2_mm' (us_md - us_m'd)
+  for (int e = lane; e < M * D; e += 32) {
+    const int m = e / D, d = e - m * D;
+    double t = 0.0;
+    for (int j = 0; j < MP; ++j) t = fma(Lb[m * MP + j], Us[m * D + d] - Us[j * D + d], t);
+    out[1 + D + 2 + e] = -par[2 + d] * (Us[m * D + d] * P[m * PC + D] - P[m * PC + d]) - 2.0 * par[2 + d] * t;
+  }
+}
+
+// ---- LOO outputs and prediction ----------------------------------------------------------------------
+__global__ void fitc_loo_kernel(const double* __restrict__ y, const double* __restrict__ rowv, int64_t N,
+                                double* __restrict__ mean, double* __restrict__ var) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const double alpha = rowv[4 * N + i], d = rowv[5 * N + i];
+  mean[i] = y[i] - alpha / d;   // K20:231
+  var[i] = 1.0 / d;             // K20:232
+}
+
+template <int MP>
+__global__ void __launch_bounds__(RB)
+fitc_predict_kernel(const double* __restrict__ Xs, int64_t T, int D, int M, const double* __restrict__ par,
+                    const double* __restrict__ small, double* __restrict__ mean, double* __restrict__ var) {
+  extern __shared__ double sh[];
+  const SmallLayout lo(MP, D);
+  double* Us = sh;
+  double* LA = Us + MP * D;
+  double* LAi = LA + MP * MP;
+  double* LC = LAi + MP;
+  double* LCi = LC + MP * MP;
+  double* beta = LCi + MP;
+  double* XsT = beta + MP;   // [D][LDT]
+  const int tid = threadIdx.x;
+  for (int e = tid; e < MP * D; e += RB) Us[e] = small[lo.us + e];
+  for (int e = tid; e < MP * MP; e += RB) {
+    LA[e] = small[lo.la + e];
+    LC[e] = small[lo.lc + e];
+  }
+  if (tid < MP) {
+    LAi[tid] = small[lo.lai + tid];
+    LCi[tid] = small[lo.lci + tid];
+    beta[tid] = small[lo.beta + tid];
+  }
+  __syncthreads();
+  const int64_t i = (int64_t)blockIdx.x * RB + tid;
+  const bool live = i < T;
+  for (int d = 0; d < D; ++d) XsT[d * LDT + tid] = live ? Xs[i * D + d] * par[2 + d] : 0.0;
+  double v[MP];
+  kernel_vec<MP>(Us, XsT, tid, M, D, par[0], v);
+  fwd_subst<MP>(LA, LAi, v);
+  double q = 0.0;
+#pragma unroll
+  for (int m = 0; m < MP; ++m) q = fma(v[m], v[m], q);
+  fwd_subst<MP>(LC, LCi, v);
+  double r = 0.0, mb = 0.0;
+#pragma unroll
+  for (int m = 0; m < MP; ++m) {
+    r = fma(v[m], v[m], r);
+    mb = fma(v[m], beta[m], mb);
+  }
+  if (live) {
+    mean[i] = mb;
+    var[i] = par[1] + par[0] - q + r;
+  }
+}
+
+// ---- host-side dispatch -------------------------------------------------------------------------------
+size_t smem_row1(int MP, int D) { return ((size_t)MP * D + MP * MP + MP + (size_t)D * LDT + (size_t)MP * LDT + RB + MP * MP + MP) * 8; }
+size_t smem_row2(int MP) { return ((size_t)MP * MP + 2 * MP + (size_t)MP * LDT + 2 * RB + MP * MP + MP + 32) * 8; }
+size_t smem_row3(int MP, int D, int PC) {
+  return ((size_t)MP * D + 3 * MP * MP + 5 * MP + (size_t)PC * LDT + 3 * (size_t)MP * LDT + (size_t)D * RB + MP * MP +
+          MP * PC + 32) * 8;
+}
+size_t smem_pred(int MP, int D) { return ((size_t)MP * D + 2 * MP * MP + 3 * MP + (size_t)D * LDT) * 8; }
+
+template <typename K>
+int set_smem(gps_ctx* ctx, K kern, size_t bytes) {
+  GPS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return GPS_OK;
+}
+
+template <int MP>
+int run_row1(gps_ctx* ctx, double* part) {
+  auto& f = ctx->fitc;
+  const size_t sm = smem_row1(MP, ctx->D);
+  GPS_CHECK(set_smem(ctx, fitc_row1_kernel<MP>, sm));
+  fitc_row1_kernel<MP><<<f.grid, RB, sm, ctx->stream>>>(ctx->X.p, ctx->y.p, ctx->N, ctx->D, f.M, ctx->params.p,
+                                                        f.small.p, f.V.p, f.rowv.p, part);
+  GPS_LAUNCH_CHECK();
+  return GPS_OK;
+}
+
+template <int MP>
+int run_row2(gps_ctx* ctx, double* part) {
+  auto& f = ctx->fitc;
+  const size_t sm = smem_row2(MP);
+  GPS_CHECK(set_smem(ctx, fitc_row2_kernel<MP>, sm));
+  fitc_row2_kernel<MP><<<f.grid, RB, sm, ctx->stream>>>(ctx->y.p, ctx->N, ctx->D, f.score, 1.0 / (double)f.world_n,
+                                                        f.small.p, f.V.p, f.W.p, f.rowv.p, part);
+  GPS_LAUNCH_CHECK();
+  return GPS_OK;
+}
+
+template <int MP, int NF>
+int run_row3(gps_ctx* ctx, double* part) {
+  auto& f = ctx->fitc;
+  const size_t sm = smem_row3(MP, ctx->D, 8 * NF);
+  GPS_CHECK(set_smem(ctx, (fitc_row3_kernel<MP, NF>), sm));
+  fitc_row3_kernel<MP, NF><<<f.grid, RB, sm, ctx->stream>>>(ctx->X.p, ctx->y.p, ctx->N, ctx->D, f.M, ctx->params.p,
+                                                            f.small.p, f.V.p, f.W.p, f.rowv.p, part);
+  GPS_LAUNCH_CHECK();
+  return GPS_OK;
+}
+
+template <int MP>
+int run_pred(gps_ctx* ctx, const double* Xs, int64_t T, double* mean, double* var) {
+  auto& f = ctx->fitc;
+  const size_t sm = smem_pred(MP, ctx->D);
+  GPS_CHECK(set_smem(ctx, fitc_predict_kernel<MP>, sm));
+  fitc_predict_kernel<MP><<<(unsigned)((T + RB - 1) / RB), RB, sm, ctx->stream>>>(Xs, T, ctx->D, f.M, ctx->params.p,
+                                                                                f.small.p, mean, var);
+  GPS_LAUNCH_CHECK();
+  return GPS_OK;
+}
+
+#define MP_DISPATCH(MPV, CALL)                    \
+  switch (MPV) {                                  \
+    case 8:  { constexpr int MPC = 8;  CALL; } break;  \
+    case 16: { constexpr int MPC = 16; CALL; } break;  \
+    case 24: { constexpr int MPC = 24; CALL; } break;  \
+    case 32: { constexpr int MPC = 32; CALL; } break;  \
+    default: return gps_fail(ctx, GPS_EINVAL, "FITC: M padded to %d is not supported", MPV); \
+  }
+
+int pc_of(int D) { return (D + 1 <= 8) ? 8 : 16; }
+int len1_of(int MP) { return MP * MP + MP; }
+int len2_of(int MP) { return MP * MP + MP + 1; }
+int len3_of(int MP, int D) { return MP * MP + MP * pc_of(D) + D + 1; }
+
+int reduce_to(gps_ctx* ctx, const double* part, int nblocks, int len, double* acc) {
+  fitc_reduce_kernel<<<(len + 255) / 256, 256, 0, ctx->stream>>>(part, nblocks, len, acc);
+  GPS_LAUNCH_CHECK();
+  ctx->launches++;
+  return GPS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int gps_fitc_acc_len(int M, int D, int64_t* len1, int64_t* len2, int64_t* len3) {
+  if (M <= 0 || M > 32 || D <= 0 || D > 15) return GPS_EINVAL;
+  const int MP = (M + 7) / 8 * 8;
+  if (len1) *len1 = len1_of(MP);
+  if (len2) *len2 = len2_of(MP);
+  if (len3) *len3 = len3_of(MP, D);
+  return GPS_OK;
+}
+
+int gps_fitc_begin(gps_ctx* ctx, const double* theta, const double* U, int M, double jitter, int score,
+                   int64_t world_n) {
+  if (!ctx) return GPS_EINVAL;
+  if (ctx->N == 0) return gps_fail(ctx, GPS_ESTATE, "fitc: call gps_set_data first");
+  if (!theta || !U || score < GPS_CRPS || score > GPS_NLML) return gps_fail(ctx, GPS_EINVAL, "fitc: bad arguments");
+  if (M <= 0 || M > 32)
+    return gps_fail(ctx, GPS_EINVAL, "fitc: M=%d outside the fused row-kernel range 1..32", M);
+  if (ctx->D > 15) return gps_fail(ctx, GPS_EINVAL, "fitc: D=%d > 15 not supported by the row kernels", ctx->D);
+  GPS_CUDA(cudaSetDevice(ctx->device));
+  auto& f = ctx->fitc;
+  const int D = ctx->D;
+  const int MP = (M + 7) / 8 * 8;
+  const int64_t N = ctx->N;
+  f.M = M; f.MP = MP; f.score = score; f.jitter = jitter; f.world_n = world_n > 0 ? world_n : N;
+  f.begun = false; f.pass2_done = false;
+  GPS_CHECK(gps_ensure(ctx, ctx->params, PAR_LEN));
+  if (!ctx->d_info) GPS_CUDA(cudaMalloc(&ctx->d_info, sizeof(int)));
+  GPS_CUDA(cudaMemsetAsync(ctx->d_info, 0, sizeof(int), ctx->stream));
+  const SmallLayout lo(MP, D);
+  int64_t blocks = (N + RB - 1) / RB;
+  const int64_t cap = (int64_t)ctx->sm_count * 4;
+  f.grid = (int)(blocks < cap ? blocks : cap);
+  GPS_CHECK(gps_ensure(ctx, f.V, (size_t)N * MP));
+  GPS_CHECK(gps_ensure(ctx, f.W, (size_t)N * MP));
+  GPS_CHECK(gps_ensure(ctx, f.rowv, (size_t)6 * N));
+  GPS_CHECK(gps_ensure(ctx, f.small, (size_t)lo.total + M * D + 8 + D + 2 + M * D));
+  GPS_CHECK(gps_ensure(ctx, f.part, (size_t)f.grid * len3_of(MP, D)));
+  GPS_CHECK(gps_ensure(ctx, f.acc1, len1_of(MP)));
+  GPS_CHECK(gps_ensure(ctx, f.acc2, len2_of(MP)));
+  GPS_CHECK(gps_ensure(ctx, f.acc3, len3_of(MP, D)));
+  GPS_CHECK(gps_upload_params(ctx, theta, D, &f.ea, &f.sn2));
+  double* dU = f.small.p + lo.total;   // raw inducing inputs
+  GPS_CUDA(cudaMemcpyAsync(dU, U, (size_t)M * D * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  fitc_small0_kernel<<<1, 32, (size_t)MP * MP * 8, ctx->stream>>>(dU, ctx->params.p, f.small.p, M, MP, D, jitter,
+                                                                 ctx->d_info);
+  GPS_LAUNCH_CHECK();
+  ctx->launches++;
+  f.begun = true;
+  return GPS_OK;
+}
+
+int gps_fitc_pass1(gps_ctx* ctx, double* acc1) {
+  if (!ctx) return GPS_EINVAL;
+  auto& f = ctx->fitc;
+  if (!f.begun) return gps_fail(ctx, GPS_ESTATE, "fitc_pass1: call gps_fitc_begin first");
+  GPS_CUDA(cudaSetDevice(ctx->device));
+  MP_DISPATCH(f.MP, GPS_CHECK(run_row1<MPC>(ctx, f.part.p)));
+  ctx->launches++;
+  GPS_CHECK(reduce_to(ctx, f.part.p, f.grid, len1_of(f.MP), acc1));
+  GPS_CUDA(cudaStreamSynchronize(ctx->stream));   // acc1 is handed to the caller's collective
+  return GPS_OK;
+}
+
+int gps_fitc_pass2(gps_ctx* ctx, const double* acc1, double* acc2) {
+  if (!ctx) return GPS_EINVAL;
+  auto& f = ctx->fitc;
+  if (!f.begun) return gps_fail(ctx, GPS_ESTATE, "fitc_pass2: call gps_fitc_begin first");
+  GPS_CUDA(cudaSetDevice(ctx->device));
+  fitc_small1_kernel<<<1, 32, (size_t)f.MP * f.MP * 8, ctx->stream>>>(acc1, f.small.p, f.MP, ctx->D, ctx->d_info);
+  GPS_LAUNCH_CHECK();
+  MP_DISPATCH(f.MP, GPS_CHECK(run_row2<MPC>(ctx, f.part.p)));
+  ctx->launches += 2;
+  GPS_CHECK(reduce_to(ctx, f.part.p, f.grid, len2_of(f.MP), acc2));
+  GPS_CUDA(cudaStreamSynchronize(ctx->stream));
+  f.pass2_done = true;
+  return GPS_OK;
+}
+
+int gps_fitc_pass3(gps_ctx* ctx, const double* acc2, double* acc3) {
+  if (!ctx) return GPS_EINVAL;
+  auto& f = ctx->fitc;
+  if (!f.pass2_done) return gps_fail(ctx, GPS_ESTATE, "fitc_pass3: pass 2 has not run");
+  GPS_CUDA(cudaSetDevice(ctx->device));
+  fitc_small2_kernel<<<1, 32, (size_t)(3 * f.MP * f.MP + f.MP) * 8, ctx->stream>>>(acc2, f.small.p, f.M, f.MP, ctx->D,
+                                                                                 f.score);
+  GPS_LAUNCH_CHECK();
+  if (pc_of(ctx->D) == 8) {
+    MP_DISPATCH(f.MP, GPS_CHECK((run_row3<MPC, 1>(ctx, f.part.p))));
+  } else {
+    MP_DISPATCH(f.MP, GPS_CHECK((run_row3<MPC, 2>(ctx, f.part.p))));
+  }
+  ctx->launches += 2;
+  GPS_CHECK(reduce_to(ctx, f.part.p, f.grid, len3_of(f.MP, ctx->D), acc3));
+  GPS_CUDA(cudaStreamSynchronize(ctx->stream));
+  return GPS_OK;
+}
+
+int gps_fitc_finish(gps_ctx* ctx, const double* acc2, const double* acc3, double* obj, double* grad_theta,
+                    double* grad_U) {
+  if (!ctx) return GPS_EINVAL;
+  auto& f = ctx->fitc;
+  if (!f.pass2_done) return gps_fail(ctx, GPS_ESTATE, "fitc_finish: passes have not run");
+  GPS_CUDA(cudaSetDevice(ctx->device));
+  const int D = ctx->D, M = f.M, MP = f.MP;
+  const SmallLayout lo(MP, D);
+  double* out = f.small.p + lo.total + M * D;   // [obj | g_theta | g_U]
+  const int nout = 1 + D + 2 + M * D;
+  fitc_small3_kernel<<<1, 32, (size_t)(3 * MP * MP + 32) * 8, ctx->stream>>>(
+      acc2, acc3, f.small.p, ctx->params.p, M, MP, D, pc_of(D), f.score, (double)f.world_n, out);
+  GPS_LAUNCH_CHECK();
+  ctx->launches++;
+  std::vector<double> h(nout);
+  GPS_CUDA(cudaMemcpyAsync(h.data(), out, nout * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  int info = 0;
+  GPS_CUDA(cudaMemcpyAsync(&info, ctx->d_info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  GPS_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (info != 0)
+    return gps_fail(ctx, GPS_ENOTPD, "fitc: %s not positive definite at pivot %d",
+                    info >= 1000000 ? "I + V V'/lambda" : "K_uu + jitter I", info % 1000000);
+  if (obj) *obj = h[0];
+  if (grad_theta)
+    for (int k = 0; k < D + 2; ++k) grad_theta[k] = h[1 + k];
+  if (grad_U)
+    for (int k = 0; k < M * D; ++k) grad_U[k] = h[1 + D + 2 + k];
+  return GPS_OK;
+}
+
+int gps_fitc_eval(gps_ctx* ctx, const double* theta, const double* U, int M, double jitter, int score,
+                  double* obj, double* grad_theta, double* grad_U) {
+  if (!ctx) return GPS_EINVAL;
+  GPS_CHECK(gps_fitc_begin(ctx, theta, U, M, jitter, score, ctx->N));
+  auto& f = ctx->fitc;
+  // single GPU: same kernels, no host synchronisation between the passes
+  MP_DISPATCH(f.MP, GPS_CHECK(run_row1<MPC>(ctx, f.part.p)));
+  GPS_CHECK(reduce_to(ctx, f.part.p, f.grid, len1_of(f.MP), f.acc1.p));
+  fitc_small1_kernel<<<1, 32, (size_t)f.MP * f.MP * 8, ctx->stream>>>(f.acc1.p, f.small.p, f.MP, ctx->D, ctx->d_info);
+  GPS_LAUNCH_CHECK();
+  MP_DISPATCH(f.MP, GPS_CHECK(run_row2<MPC>(ctx, f.part.p)));
+  GPS_CHECK(reduce_to(ctx, f.part.p, f.grid, len2_of(f.MP), f.acc2.p));
+  f.pass2_done = true;
+  ctx->launches += 3;
+  if (grad_theta || grad_U) {
+    fitc_small2_kernel<<<1, 32, (size_t)(3 * f.MP * f.MP + f.MP) * 8, ctx->stream>>>(f.acc2.p, f.small.p, f.M, f.MP,
+                                                                                   ctx->D, f.score);
+    GPS_LAUNCH_CHECK();
+    if (pc_of(ctx->D) == 8) {
+      MP_DISPATCH(f.MP, GPS_CHECK((run_row3<MPC, 1>(ctx, f.part.p))));
+    } else {
+      MP_DISPATCH(f.MP, GPS_CHECK((run_row3<MPC, 2>(ctx, f.part.p))));
+    }
+    ctx->launches += 2;
+    GPS_CHECK(reduce_to(ctx, f.part.p, f.grid, len3_of(f.MP, ctx->D), f.acc3.p));
+  } else {
+    GPS_CUDA(cudaMemsetAsync(f.acc3.p, 0, len3_of(f.MP, ctx->D) * sizeof(double), ctx->stream));
+  }
+  return gps_fitc_finish(ctx, f.acc2.p, f.acc3.p, obj, grad_theta, grad_U);
+}
+
+int gps_fitc_loo(gps_ctx* ctx, double* loo_mean, double* loo_var) {
+  if (!ctx) return GPS_EINVAL;
+  auto& f = ctx->fitc;
+  if (!f.pass2_done) return gps_fail(ctx, GPS_ESTATE, "fitc_loo: no evaluation to report");
+  if (!loo_mean || !loo_var) return gps_fail(ctx, GPS_EINVAL, "fitc_loo: null output");
+  GPS_CUDA(cudaSetDevice(ctx->device));
+  const int64_t N = ctx->N;
+  const bool dev = gps_is_device_ptr(loo_mean) && gps_is_device_ptr(loo_var);
+  double *dm = loo_mean, *dv = loo_var;
+  if (!dev) {
+    GPS_CHECK(gps_ensure(ctx, ctx->stage[1], (size_t)N));
+    GPS_CHECK(gps_ensure(ctx, ctx->stage[2], (size_t)N));
+    dm = ctx->stage[1].p;
+    dv = ctx->stage[2].p;
+  }
+  fitc_loo_kernel<<<(unsigned)((N + 255) / 256), 256, 0, ctx->stream>>>(ctx->y.p, f.rowv.p, N, dm, dv);
+  GPS_LAUNCH_CHECK();
+  ctx->launches++;
+  if (!dev) {
+    GPS_CUDA(cudaMemcpyAsync(loo_mean, dm, N * sizeof(double), cudaMemcpyDefault, ctx->stream));
+    GPS_CUDA(cudaMemcpyAsync(loo_var, dv, N * sizeof(double), cudaMemcpyDefault, ctx->stream));
+  }
+  GPS_CUDA(cudaStreamSynchronize(ctx->stream));
+  return GPS_OK;
+}
+
+int gps_fitc_predict(gps_ctx* ctx, const double* Xs, int64_t T, double* mean, double* var) {
+  if (!ctx) return GPS_EINVAL;
+  auto& f = ctx->fitc;
+  if (!f.pass2_done) return gps_fail(ctx, GPS_ESTATE, "fitc_predict: run passes 1 and 2 at this theta, U first");
+  if (!Xs || !mean || !var || T < 0) return gps_fail(ctx, GPS_EINVAL, "fitc_predict: bad arguments");
+  if (T == 0) return GPS_OK;
+  GPS_CUDA(cudaSetDevice(ctx->device));
+  const double* dXs;
+  GPS_CHECK(gps_stage_in(ctx, Xs, (size_t)T * ctx->D, ctx->stage[0], &dXs));
+  const bool dev = gps_is_device_ptr(mean) && gps_is_device_ptr(var);
+  double *dm = mean, *dv = var;
+  if (!dev) {
+    GPS_CHECK(gps_ensure(ctx, ctx->stage[1], (size_t)T));
+    GPS_CHECK(gps_ensure(ctx, ctx->stage[2], (size_t)T));
+    dm = ctx->stage[1].p;
+    dv = ctx->stage[2].p;
+  }
+  MP_DISPATCH(f.MP, GPS_CHECK(run_pred<MPC>(ctx, dXs, T, dm, dv)));
+  ctx->launches++;
+  if (!dev) {
+    GPS_CUDA(cudaMemcpyAsync(mean, dm, T * sizeof(double), cudaMemcpyDefault, ctx->stream));
+    GPS_CUDA(cudaMemcpyAsync(var, dv, T * sizeof(double), cudaMemcpyDefault, ctx->stream));
+  }
+  GPS_CUDA(cudaStreamSynchronize(ctx->stream));
+  return GPS_OK;
+}
+
+}  // extern "C"
