@@ -49,6 +49,12 @@ const char* gps_last_error(gps_ctx* ctx);
 const char* gps_version(void);
 /* number of kernels this context has launched since creation (bench.py's gpu_launches) */
 int64_t gps_launch_count(gps_ctx* ctx);
+/* run on the caller's CUDA stream (a cudaStream_t, e.g. torch.cuda.current_stream().cuda_stream)
+ * instead of the context's own; NULL restores the context's stream.  Lets the caller bracket calls
+ * with its own CUDA events. */
+int gps_set_stream(gps_ctx* ctx, void* cuda_stream);
+/* switch the per-launch CUDA-event timing of the tile GEMMs on (1) or off (0, default) */
+int gps_set_gemm_timing(gps_ctx* ctx, int on);
 /* device milliseconds the dominant dense kernels (DMMA tile GEMM) spent inside the last
  * gps_full_eval, measured with CUDA events on the context's stream, and their launch count */
 int gps_last_gemm_ms(gps_ctx* ctx, double* ms, int64_t* launches);
@@ -82,7 +88,7 @@ int gps_fitc_begin(gps_ctx* ctx, const double* theta, const double* U, int M, do
                    int64_t world_n);
 int gps_fitc_pass1(gps_ctx* ctx, double* acc1);           /* acc1 = [C - I (M*M) | v_y (M)]          */
 int gps_fitc_pass2(gps_ctx* ctx, const double* acc1, double* acc2); /* acc2 = [R (M*M) | beta_bar (M) | obj] */
-int gps_fitc_pass3(gps_ctx* ctx, const double* acc2, double* acc3); /* acc3 = [S (M*M) | sum lam_bar | g_a | g_b (D) | g_U (M*D)] */
+int gps_fitc_pass3(gps_ctx* ctx, const double* acc2, double* acc3); /* acc3 = [S | P = G [xs|1] | g_b rows (D) | sum lam_bar] */
 int gps_fitc_finish(gps_ctx* ctx, const double* acc2, const double* acc3, double* obj, double* grad_theta,
                     double* grad_U);
 int gps_fitc_loo(gps_ctx* ctx, double* loo_mean, double* loo_var);
@@ -93,7 +99,8 @@ int gps_fitc_predict(gps_ctx* ctx, const double* Xs, int64_t T, double* mean, do
 /* ---- scoring of predictions (replaces KF:276-292: mse, SMSE KF:128-134, logs KF:52-57,
  *      crps KF:60-68, trivial_loss KF:110-119, coverage KF:288-292) ---------------------------- */
 /* mean, var, y: UVA length n.  ytrain_mean / ytrain_var: mean and UNBIASED variance of the
- * training targets (KF:113-114).  out[6] host = {mse, smse, logs, crps, msll, coverage}. */
+ * training targets (KF:113-114).  out[12] host = {mse, smse, logs, crps, msll, coverage} followed by
+ * the six raw sums they are formed from (what row-sharded callers all-reduce). */
 int gps_test_metrics(gps_ctx* ctx, const double* mean, const double* var, const double* y, int64_t n,
                      double ytrain_mean, double ytrain_var, double* out);
 

@@ -258,6 +258,13 @@ class Context:
         return out
 
     # ---- accounting --------------------------------------------------------------------------
+    def set_stream(self, stream=None):
+        """Enqueue on a torch stream (so torch.cuda.Event brackets the work); None = own stream."""
+        self._check(self._lib.gps_set_stream(self._h, None if stream is None else stream.cuda_stream))
+
+    def set_gemm_timing(self, on):
+        self._check(self._lib.gps_set_gemm_timing(self._h, 1 if on else 0))
+
     def launch_count(self):
         return int(self._lib.gps_launch_count(self._h))
 

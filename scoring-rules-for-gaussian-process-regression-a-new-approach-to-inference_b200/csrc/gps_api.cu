@@ -143,12 +143,27 @@ int gps_create(int device, gps_ctx** out) {
   ctx->device = device;
   cudaDeviceProp prop;
   if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) ctx->sm_count = prop.multiProcessorCount;
-  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+  if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {
     delete ctx;
     return GPS_ECUDA;
   }
+  ctx->stream = ctx->own_stream;
   *out = ctx;
+  return GPS_OK;
+}
+
+int gps_set_stream(gps_ctx* ctx, void* cuda_stream) {
+  if (!ctx) return GPS_EINVAL;
+  cudaStreamSynchronize(ctx->stream);
+  ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+  return GPS_OK;
+}
+
+int gps_set_gemm_timing(gps_ctx* ctx, int on) {
+  if (!ctx) return GPS_EINVAL;
+  ctx->time_gemm = on != 0;
+  ctx->gemm_events_used = 0;
   return GPS_OK;
 }
 
@@ -171,7 +186,7 @@ void gps_destroy(gps_ctx* ctx) {
   }
   cudaEventDestroy(ctx->ev0);
   cudaEventDestroy(ctx->ev1);
-  cudaStreamDestroy(ctx->stream);
+  cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }
 

@@ -26,13 +26,14 @@ struct DevBuf {
 
 struct gps_ctx {
   int device = 0;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr;      // stream all work is enqueued on
+  cudaStream_t own_stream = nullptr;  // the context's own stream
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::string err;
   int64_t launches = 0;
   int sm_count = 148;
   // GEMM timing of the last full eval
-  bool time_gemm = true;
+  bool time_gemm = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> gemm_events;
   size_t gemm_events_used = 0;
   double last_gemm_ms = 0;

@@ -59,10 +59,14 @@ int gps_dbg_gemm(gps_ctx* ctx, int kind, const double* A, const double* B, doubl
     }
   GPS_CHECK(gps_upload_tasks2(ctx, tasks));
   ctx->gemm_events_used = 0;
+  const bool prev_timing = ctx->time_gemm;
+  ctx->time_gemm = true;
   const int64_t lda = (kind == 2) ? Mp : Kp;
   const int64_t ldb = (kind == 0) ? Kp : Npp;
-  GPS_CHECK(gps_gemm_tasks(ctx, kind, A, lda, B, ldb, C, Npp, alpha, beta, dvec, mirror != 0, ctx->d_tasks2,
-                           tasks.size()));
+  const int rc = gps_gemm_tasks(ctx, kind, A, lda, B, ldb, C, Npp, alpha, beta, dvec, mirror != 0, ctx->d_tasks2,
+                                tasks.size());
+  ctx->time_gemm = prev_timing;
+  GPS_CHECK(rc);
   GPS_CUDA(cudaStreamSynchronize(ctx->stream));
   float ms = 0;
   GPS_CUDA(cudaEventElapsedTime(&ms, ctx->gemm_events[0].first, ctx->gemm_events[0].second));

@@ -25,6 +25,8 @@ SIGNATURES = {
     "gps_last_error": (C.c_char_p, [_vp]),
     "gps_version": (C.c_char_p, []),
     "gps_launch_count": (_i64, [_vp]),
+    "gps_set_stream": (C.c_int, [_vp, _vp]),
+    "gps_set_gemm_timing": (C.c_int, [_vp, C.c_int]),
     "gps_last_gemm_ms": (C.c_int, [_vp, _dp, C.POINTER(_i64)]),
     "gps_set_data": (C.c_int, [_vp, _vp, _vp, _i64, C.c_int]),
     "gps_full_eval": (C.c_int, [_vp, _dp, C.c_int, _dp, _dp]),
