@@ -184,6 +184,8 @@ void gps_destroy(gps_ctx* ctx) {
     cudaEventDestroy(pr.first);
     cudaEventDestroy(pr.second);
   }
+  for (auto e : ctx->potrf_events) cudaEventDestroy(e);
+  if (ctx->panel_stream) cudaStreamDestroy(ctx->panel_stream);
   cudaEventDestroy(ctx->ev0);
   cudaEventDestroy(ctx->ev1);
   cudaStreamDestroy(ctx->own_stream);

@@ -15,7 +15,7 @@ namespace {
 
 constexpr int T = GPS_TILE;
 constexpr int LSLD = T + 1;
-constexpr size_t POTF2_SMEM = (size_t)T * LSLD * sizeof(double) + 2 * T * sizeof(double);
+constexpr size_t POTF2_SMEM = (size_t)T * LSLD * sizeof(double) + 3 * T * sizeof(double);
 
 // One CTA (16 x 16 threads).  Thread (ty, tx) owns the 8 x 8 cyclic sub-block
 // A[ty + 16 r][tx + 16 c].  Phase 1: right-looking Cholesky of the 128 x 128 diagonal block with
@@ -54,8 +54,9 @@ potf2_inv_kernel(double* __restrict__ K, double* __restrict__ Xinv, int64_t ld, 
         if (tid == 0) atomicCAS(info, 0, blk * T + k + 1);
         piv = 1.0;
       }
-      const double sq = sqrt(piv);
-      const double rs = 1.0 / sq;
+      // one reciprocal square root per step keeps the serial chain short: L_kk = piv * rs
+      const double rs = rsqrt(piv);
+      const double sq = piv * rs;
       double li[8], lc[8];
 #pragma unroll
       for (int r = kq; r < 8; ++r) {
@@ -92,6 +93,9 @@ potf2_inv_kernel(double* __restrict__ K, double* __restrict__ Xinv, int64_t ld, 
       Kd[(int64_t)i * ld + j] = v;
     }
   __syncthreads();
+  double* dinv = buf + 2 * T;            // [128] 1 / L_kk, all computed up front (off the serial chain)
+  if (tid < T) dinv[tid] = 1.0 / Ls[tid * LSLD + tid];
+  __syncthreads();
 
   // ---- phase 2: X = L^-1 by forward substitution on I ------------------------------------
 #pragma unroll
@@ -105,7 +109,7 @@ potf2_inv_kernel(double* __restrict__ K, double* __restrict__ Xinv, int64_t ld, 
       const int k = 16 * kq + kc;
       double* rb = buf + (k & 1) * T;
       if (ty == kc) {
-        const double inv = 1.0 / Ls[k * LSLD + k];
+        const double inv = dinv[k];
 #pragma unroll
         for (int c = 0; c <= kq; ++c) {
           const double x = a[kq][c] * inv;
@@ -163,17 +167,37 @@ int gps_build_tasks(gps_ctx* ctx, int64_t Np) {
     t.flags = 0; t.pad = 0;
     h.push_back(t);
   };
+  // POTRF, two-level: outer block columns of OB tiles.  Inside a block column the 128-wide
+  // steps (diagonal kernel, panel solve, update of the remaining inner columns) only touch that
+  // block column; the rest of the matrix receives ONE update per outer step with k = OB*128,
+  // split into the part the next block column needs (A) and the remainder (B) so that the next
+  // block column can be factored on a second stream while B runs (look-ahead).
+  const int OB = GPS_POTRF_OB;
+  const int no = (nb + OB - 1) / OB;
   ctx->potrf_panel.assign(nb, {});
-  ctx->potrf_trail.assign(nb, {});
-  for (int k = 0; k < nb; ++k) {
-    ctx->potrf_panel[k].off = h.size();
-    for (int i = k + 1; i < nb; ++i) push(i * T, k * T, k * T, (k + 1) * T, i, k);
-    ctx->potrf_panel[k].cnt = h.size() - ctx->potrf_panel[k].off;
-    ctx->potrf_trail[k].off = h.size();
-    // the block column the next panel needs goes first
-    for (int j = k + 1; j < nb; ++j)
-      for (int i = j; i < nb; ++i) push(i * T, j * T, k * T, (k + 1) * T, i, j);
-    ctx->potrf_trail[k].cnt = h.size() - ctx->potrf_trail[k].off;
+  ctx->potrf_inner.assign(nb, {});
+  ctx->potrf_trailA.assign(no, {});
+  ctx->potrf_trailB.assign(no, {});
+  for (int o = 0; o < no; ++o) {
+    const int c0 = o * OB, c1 = std::min(nb, c0 + OB);
+    for (int k = c0; k < c1; ++k) {
+      ctx->potrf_panel[k].off = h.size();
+      for (int i = k + 1; i < nb; ++i) push(i * T, k * T, k * T, (k + 1) * T, i, k);
+      ctx->potrf_panel[k].cnt = h.size() - ctx->potrf_panel[k].off;
+      ctx->potrf_inner[k].off = h.size();
+      for (int j = k + 1; j < c1; ++j)
+        for (int i = j; i < nb; ++i) push(i * T, j * T, k * T, (k + 1) * T, i, j);
+      ctx->potrf_inner[k].cnt = h.size() - ctx->potrf_inner[k].off;
+    }
+    const int n1 = std::min(nb, c1 + OB);
+    ctx->potrf_trailA[o].off = h.size();
+    for (int j = c1; j < n1; ++j)
+      for (int i = j; i < nb; ++i) push(i * T, j * T, c0 * T, c1 * T, i, j);
+    ctx->potrf_trailA[o].cnt = h.size() - ctx->potrf_trailA[o].off;
+    ctx->potrf_trailB[o].off = h.size();
+    for (int j = n1; j < nb; ++j)
+      for (int i = j; i < nb; ++i) push(i * T, j * T, c0 * T, c1 * T, i, j);
+    ctx->potrf_trailB[o].cnt = h.size() - ctx->potrf_trailB[o].off;
   }
   // TRTRI: nodes by depth, deepest first
   std::vector<Node> nodes;
@@ -224,27 +248,62 @@ int gps_build_tasks(gps_ctx* ctx, int64_t Np) {
 
 int gps_potrf(gps_ctx* ctx, double* K, double* Xinv, int64_t Np) {
   const int nb = (int)(Np / T);
+  const int OB = GPS_POTRF_OB;
+  const int no = (nb + OB - 1) / OB;
   static bool configured = false;
   if (!configured) {
     GPS_CUDA(cudaFuncSetAttribute(potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)POTF2_SMEM));
     configured = true;
   }
-  GPS_CUDA(cudaMemsetAsync(ctx->d_info, 0, sizeof(int), ctx->stream));
-  for (int k = 0; k < nb; ++k) {
-    potf2_inv_kernel<<<1, 256, POTF2_SMEM, ctx->stream>>>(K, Xinv, Np, k, ctx->d_info);
-    GPS_LAUNCH_CHECK();
-    ctx->launches++;
-    if (k + 1 < nb) {
-      // panel: L_ik = A_ik * inv(L_kk)'
-      GPS_CHECK(gps_gemm_tasks(ctx, GEMM_KC_KC, K, Np, Xinv, Np, K, Np, 1.0, 0.0, nullptr, false,
-                               ctx->d_tasks + ctx->potrf_panel[k].off, ctx->potrf_panel[k].cnt));
-      // trailing update: A_ij -= L_ik L_jk'
-      GPS_CHECK(gps_gemm_tasks(ctx, GEMM_KC_KC, K, Np, K, Np, K, Np, -1.0, 1.0, nullptr, false,
-                               ctx->d_tasks + ctx->potrf_trail[k].off, ctx->potrf_trail[k].cnt));
-    }
+  if (!ctx->panel_stream) {
+    int lo = 0, hi = 0;
+    GPS_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    GPS_CUDA(cudaStreamCreateWithPriority(&ctx->panel_stream, cudaStreamNonBlocking, hi));
   }
-  return GPS_OK;
+  while ((int)ctx->potrf_events.size() < 2 * no + 2) {
+    cudaEvent_t e;
+    GPS_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ctx->potrf_events.push_back(e);
+  }
+  cudaStream_t s_main = ctx->stream, s_pan = ctx->panel_stream;
+  GPS_CUDA(cudaMemsetAsync(ctx->d_info, 0, sizeof(int), s_main));
+  // event 2*o: block column o has received every update (recorded on s_main);
+  // event 2*o + 1: block column o is factored (recorded on s_pan)
+  GPS_CUDA(cudaEventRecord(ctx->potrf_events[0], s_main));
+  int rc = GPS_OK;
+  for (int o = 0; o < no && rc == GPS_OK; ++o) {
+    const int c0 = o * OB, c1 = std::min(nb, c0 + OB);
+    // ---- factor block column o on the panel stream ------------------------------------------
+    GPS_CUDA(cudaStreamWaitEvent(s_pan, ctx->potrf_events[2 * o], 0));
+    ctx->stream = s_pan;
+    for (int k = c0; k < c1 && rc == GPS_OK; ++k) {
+      potf2_inv_kernel<<<1, 256, POTF2_SMEM, s_pan>>>(K, Xinv, Np, k, ctx->d_info);
+      if (cudaGetLastError() != cudaSuccess) rc = gps_fail(ctx, GPS_ECUDA, "potf2 launch failed");
+      ctx->launches++;
+      // panel: L_ik = A_ik * inv(L_kk)'
+      if (rc == GPS_OK)
+        rc = gps_gemm_tasks(ctx, GEMM_KC_KC, K, Np, Xinv, Np, K, Np, 1.0, 0.0, nullptr, false,
+                            ctx->d_tasks + ctx->potrf_panel[k].off, ctx->potrf_panel[k].cnt);
+      // remaining columns of this block column: A_ij -= L_ik L_jk'
+      if (rc == GPS_OK)
+        rc = gps_gemm_tasks(ctx, GEMM_KC_KC, K, Np, K, Np, K, Np, -1.0, 1.0, nullptr, false,
+                            ctx->d_tasks + ctx->potrf_inner[k].off, ctx->potrf_inner[k].cnt);
+    }
+    ctx->stream = s_main;
+    if (rc != GPS_OK) break;
+    GPS_CUDA(cudaEventRecord(ctx->potrf_events[2 * o + 1], s_pan));
+    // ---- trailing update from block column o on the main stream ------------------------------
+    GPS_CUDA(cudaStreamWaitEvent(s_main, ctx->potrf_events[2 * o + 1], 0));
+    rc = gps_gemm_tasks(ctx, GEMM_KC_KC, K, Np, K, Np, K, Np, -1.0, 1.0, nullptr, false,
+                        ctx->d_tasks + ctx->potrf_trailA[o].off, ctx->potrf_trailA[o].cnt);
+    if (rc != GPS_OK) break;
+    GPS_CUDA(cudaEventRecord(ctx->potrf_events[2 * o + 2], s_main));
+    rc = gps_gemm_tasks(ctx, GEMM_KC_KC, K, Np, K, Np, K, Np, -1.0, 1.0, nullptr, false,
+                        ctx->d_tasks + ctx->potrf_trailB[o].off, ctx->potrf_trailB[o].cnt);
+  }
+  ctx->stream = s_main;
+  return rc;
 }
 
 int gps_check_info(gps_ctx* ctx) {

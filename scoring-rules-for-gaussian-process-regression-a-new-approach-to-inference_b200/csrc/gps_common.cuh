@@ -9,6 +9,7 @@
 #include "../../include/gpscore.h"
 
 #define GPS_TILE 128  // matrix tile edge: every N x N buffer is padded to a multiple of it
+#define GPS_POTRF_OB 4  // POTRF outer block column = 4 tiles (k = 512 trailing updates)
 
 struct GemmTask {  // one 128 x 128 output tile of a tile-GEMM launch
   int32_t a_row;   // first row (KC operand) / first column (MC operand) of the A panel
@@ -64,7 +65,9 @@ struct gps_ctx {
   bool loo_valid = false;
   // cached task-list layout for ws_Np (offsets into d_tasks)
   struct Range { size_t off = 0, cnt = 0; };
-  std::vector<Range> potrf_panel, potrf_trail;
+  std::vector<Range> potrf_panel, potrf_inner, potrf_trailA, potrf_trailB;
+  cudaStream_t panel_stream = nullptr;          // high-priority stream for the POTRF look-ahead
+  std::vector<cudaEvent_t> potrf_events;
   std::vector<Range> trtri_p, trtri_x;
   Range lauum, symprod;
 
