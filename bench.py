@@ -27,6 +27,7 @@ import sys
 import threading
 import time
 
+os.environ["OMP_NUM_THREADS"] = os.environ["MKL_NUM_THREADS"] = os.environ["OPENBLAS_NUM_THREADS"] = str(os.cpu_count() or 1)  # torchrun forces 1; the CPU legs use every host core
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))

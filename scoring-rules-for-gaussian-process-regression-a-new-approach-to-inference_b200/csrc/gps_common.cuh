@@ -83,6 +83,7 @@ struct gps_ctx {
     DevBuf part;          // per-block partial accumulators
     DevBuf acc1, acc2, acc3;  // single-GPU accumulators
     bool begun = false, pass2_done = false;
+    std::vector<double> host_out;
   } fitc;
 };
 

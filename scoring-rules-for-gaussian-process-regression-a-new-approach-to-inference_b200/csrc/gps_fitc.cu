@@ -51,93 +51,157 @@ struct SmallLayout {
   }
 };
 
-// ---- small dense helpers, executed by ONE WARP on matrices in shared memory ---------------------
-// In-place lower Cholesky of A[n][ld]; returns first bad pivot (1-based) or 0.  Strict upper part zeroed.
-__device__ int warp_chol(double* A, int n, int ld, int lane) {
+// ---- small dense helpers: ONE WARP, rows/columns of the M x M matrices live in registers ---------
+// (MP is a compile-time constant, so every register array is statically indexed; lanes >= MP idle
+// but take part in the shuffles).  All serial chains are one shuffle / multiply / fma long per step.
+
+// In-place lower Cholesky of A[MP][MP] (shared, row-major).  Lane i owns row i.  Right-looking:
+// pivot and column broadcast by shuffle.  Returns the first bad pivot (1-based) or 0.
+template <int MP>
+__device__ int warp_chol(double* A, int lane) {
+  double r[MP];
+#pragma unroll
+  for (int j = 0; j < MP; ++j) r[j] = (lane < MP) ? A[lane * MP + j] : 0.0;
   int bad = 0;
-  for (int j = 0; j < n; ++j) {
-    double s = 0.0;
-    if (lane >= j && lane < n) {
-      s = A[lane * ld + j];
-      for (int k = 0; k < j; ++k) s -= A[lane * ld + k] * A[j * ld + k];
-    }
-    double piv = __shfl_sync(0xffffffffu, s, j);
+#pragma unroll
+  for (int j = 0; j < MP; ++j) {
+    double piv = __shfl_sync(0xffffffffu, r[j], j);
     if (!(piv > 0.0)) {
       if (!bad) bad = j + 1;
       piv = 1.0;
     }
-    const double sq = sqrt(piv);
-    __syncwarp();
-    if (lane == j) A[j * ld + j] = sq;
-    else if (lane > j && lane < n) A[lane * ld + j] = s / sq;
-    else if (lane < j) A[lane * ld + j] = 0.0;
-    __syncwarp();
+    const double lj = r[j] * rsqrt(piv);          // lanes >= j: L[i][j]; lane j: sqrt(piv)
+#pragma unroll
+    for (int c = j + 1; c < MP; ++c) {
+      const double lc = __shfl_sync(0xffffffffu, lj, c);
+      r[c] = fma(-lj, lc, r[c]);                  // meaningful for lanes >= c (lower triangle)
+    }
+    r[j] = lj;
   }
+  if (lane < MP) {
+#pragma unroll
+    for (int j = 0; j < MP; ++j) A[lane * MP + j] = (j <= lane) ? r[j] : 0.0;
+  }
+  __syncwarp();
   return bad;
 }
 
-// Solve L' X = B in place for the n columns of B[n][ld] (lane = column), L lower [n][ld].
-__device__ void warp_solve_LT(const double* L, double* B, int n, int ld, int lane) {
-  if (lane < n) {
-    for (int i = n - 1; i >= 0; --i) {
-      double s = B[i * ld + lane];
-      for (int k = i + 1; k < n; ++k) s -= L[k * ld + i] * B[k * ld + lane];
-      B[i * ld + lane] = s / L[i * ld + i];
-    }
+// Solve L' x = b for the column held by this lane (b[] in registers); L lower in shared memory
+// (warp-uniform addresses: broadcast reads), Li = 1 / diag(L).
+template <int MP>
+__device__ __forceinline__ void col_solve_LT(const double* __restrict__ L, const double* __restrict__ Li,
+                                             double (&b)[MP]) {
+  // volatile: keep the broadcast loads next to their fma instead of hoisting the whole triangle
+  // into registers (the fully unrolled body otherwise spills for MP >= 24)
+  const volatile double* Lv = L;
+#pragma unroll
+  for (int i = MP - 1; i >= 0; --i) {
+    b[i] *= Li[i];
+#pragma unroll
+    for (int k = 0; k < i; ++k) b[k] = fma(-Lv[i * MP + k], b[i], b[k]);
   }
-  __syncwarp();
 }
 
-// Abar = 0.5 L^-T (P + P') L^-1 with P = Phi(L' Lbar); Lbar [n][ld] is overwritten with Abar.
-// tmp [n][ld] scratch.
-__device__ void warp_chol_adjoint(const double* L, double* Lbar, double* tmp, int n, int ld, int lane) {
-  // P = tril(L' Lbar), diagonal halved -> tmp (lane = column c)
-  if (lane < n) {
-    for (int r = 0; r < n; ++r) {
-      double s = 0.0;
-      if (r >= lane) {
-        for (int k = r; k < n; ++k) s += L[k * ld + r] * Lbar[k * ld + lane];  // L'[r][k] = L[k][r], k >= r
-        if (r == lane) s *= 0.5;
-      }
-      tmp[r * ld + lane] = s;
-    }
+// Solve L x = v (forward) or L' x = v (backward) for ONE vector spread over the lanes (lane m holds
+// v_m); returns x_m.
+template <int MP>
+__device__ __forceinline__ double warp_fwd_vec(const double* __restrict__ L, const double* __restrict__ Li,
+                                               double v, int lane) {
+#pragma unroll
+  for (int j = 0; j < MP; ++j) {
+    const double xj = __shfl_sync(0xffffffffu, v, j) * Li[j];
+    if (lane == j) v = xj;
+    else if (lane > j && lane < MP) v = fma(-L[lane * MP + j], xj, v);
+  }
+  return v;
+}
+template <int MP>
+__device__ __forceinline__ double warp_bwd_vecT(const double* __restrict__ L, const double* __restrict__ Li,
+                                                double v, int lane) {
+#pragma unroll
+  for (int j = MP - 1; j >= 0; --j) {
+    const double xj = __shfl_sync(0xffffffffu, v, j) * Li[j];
+    if (lane == j) v = xj;
+    else if (lane < j) v = fma(-L[j * MP + lane], xj, v);
+  }
+  return v;
+}
+
+// Adjoint of a Cholesky factorisation: lb[] = column `lane` of Lbar (lower triangular) in, column
+// `lane` of Abar = 0.5 L^-T (P + P') L^-1, P = Phi(L' Lbar), out.  T[MP][MP] shared scratch.
+template <int MP>
+__device__ __forceinline__ void warp_chol_adjoint(const double* __restrict__ L, const double* __restrict__ Li,
+                                                  double* __restrict__ T, double (&lb)[MP], int lane) {
+  double p[MP];
+  const volatile double* Lv = L;
+#pragma unroll
+  for (int r = 0; r < MP; ++r) {
+    double s = 0.0;
+#pragma unroll
+    for (int k = r; k < MP; ++k) s = fma(Lv[k * MP + r], lb[k], s);   // (L' Lbar)[r][lane]
+    p[r] = (r > lane) ? s : ((r == lane) ? 0.5 * s : 0.0);
+  }
+  if (lane < MP) {
+#pragma unroll
+    for (int r = 0; r < MP; ++r) T[r * MP + lane] = p[r];
   }
   __syncwarp();
-  // Z = P + P' -> Lbar
-  if (lane < n)
-    for (int r = 0; r < n; ++r) Lbar[r * ld + lane] = tmp[r * ld + lane] + tmp[lane * ld + r];
+#pragma unroll
+  for (int r = 0; r < MP; ++r) p[r] += (lane < MP) ? T[lane * MP + r] : 0.0;   // Z = P + P'
   __syncwarp();
-  warp_solve_LT(L, Lbar, n, ld, lane);          // Y = L^-T Z
-  if (lane < n)
-    for (int r = 0; r < n; ++r) tmp[r * ld + lane] = Lbar[lane * ld + r];  // Y'
+  col_solve_LT<MP>(L, Li, p);                                                    // Y = L^-T Z
+  if (lane < MP) {
+#pragma unroll
+    for (int r = 0; r < MP; ++r) T[r * MP + lane] = p[r];
+  }
   __syncwarp();
-  warp_solve_LT(L, tmp, n, ld, lane);           // L^-T Y' = (Y L^-1)'
-  if (lane < n)
-    for (int r = 0; r < n; ++r) Lbar[r * ld + lane] = 0.5 * tmp[lane * ld + r];
+#pragma unroll
+  for (int r = 0; r < MP; ++r) p[r] = (lane < MP) ? T[lane * MP + r] : 0.0;     // column of Y'
   __syncwarp();
+  col_solve_LT<MP>(L, Li, p);                                                    // (Y L^-1)' = symmetric
+#pragma unroll
+  for (int r = 0; r < MP; ++r) lb[r] = 0.5 * p[r];
+}
+
+// acc[e] = sum_b part[b][e], by the whole block; result also left in shared `sacc` if non-null
+__device__ __forceinline__ void block_reduce_partials(const double* __restrict__ part, int nblocks, int len,
+                                                      double* __restrict__ acc_out) {
+  for (int e = threadIdx.x; e < len; e += blockDim.x) {
+    double s0 = 0.0, s1 = 0.0;
+    int bI = 0;
+    for (; bI + 1 < nblocks; bI += 2) {
+      s0 += part[(int64_t)bI * len + e];
+      s1 += part[(int64_t)(bI + 1) * len + e];
+    }
+    if (bI < nblocks) s0 += part[(int64_t)bI * len + e];
+    acc_out[e] = s0 + s1;
+  }
 }
 
 // ---- begin: replicated K_uu and its factor --------------------------------------------------------
-__global__ void __launch_bounds__(32)
+template <int MP>
+__global__ void __launch_bounds__(128)
 fitc_small0_kernel(const double* __restrict__ U, const double* __restrict__ par, double* __restrict__ small,
-                   int M, int MP, int D, double jitter, int* __restrict__ info) {
-  extern __shared__ double sh[];
+                   int M, int D, double jitter, int* __restrict__ info) {
+  __shared__ double A[MP * MP];
+  __shared__ double us[MP * 16];
   const SmallLayout lo(MP, D);
-  double* A = sh;  // [MP][MP]
-  const int lane = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31;
   const double ea = par[0];
-  for (int e = lane; e < MP * D; e += 32) {
+  for (int e = tid; e < MP * D; e += 128) {
     const int m = e / D, d = e - m * D;
-    small[lo.us + e] = (m < M) ? U[m * D + d] * par[2 + d] : 0.0;
+    const double v = (m < M) ? U[m * D + d] * par[2 + d] : 0.0;
+    us[e] = v;
+    small[lo.us + e] = v;
   }
-  __syncwarp();
-  for (int e = lane; e < MP * MP; e += 32) {
+  __syncthreads();
+  for (int e = tid; e < MP * MP; e += 128) {
     const int i = e / MP, j = e - i * MP;
     double v = 0.0;
     if (i < M && j < M) {
       double r2 = 0.0;
       for (int d = 0; d < D; ++d) {
-        const double df = small[lo.us + i * D + d] - small[lo.us + j * D + d];
+        const double df = us[i * D + d] - us[j * D + d];
         r2 = fma(df, df, r2);
       }
       v = ea * exp(-0.5 * r2);
@@ -145,11 +209,14 @@ fitc_small0_kernel(const double* __restrict__ U, const double* __restrict__ par,
     small[lo.kuu + e] = v;
     A[e] = v + ((i == j) ? ((i < M) ? jitter : 1.0) : 0.0);
   }
-  __syncwarp();
-  const int bad = warp_chol(A, MP, MP, lane);
-  if (bad && lane == 0) atomicCAS(info, 0, bad);
-  for (int e = lane; e < MP * MP; e += 32) small[lo.la + e] = A[e];
-  if (lane < MP) small[lo.lai + lane] = 1.0 / A[lane * MP + lane];
+  __syncthreads();
+  if (tid < 32) {
+    const int bad = warp_chol<MP>(A, lane);
+    if (bad && lane == 0) atomicCAS(info, 0, bad);
+  }
+  __syncthreads();
+  for (int e = tid; e < MP * MP; e += 128) small[lo.la + e] = A[e];
+  if (tid < MP) small[lo.lai + tid] = 1.0 / A[tid * MP + tid];
 }
 
 // per-row kernel vector k_m = ea exp(-0.5 |us_m - xs|^2); xs read from the transposed tile column `tid`
@@ -167,14 +234,15 @@ __device__ __forceinline__ void kernel_vec(const double* __restrict__ Us, const 
   }
 }
 
+// per-thread triangular solves, column oriented: after x_m is final it is eliminated from all later
+// entries with independent fmas, so the serial chain is one multiply + one fma per step.
 template <int MP>
 __device__ __forceinline__ void fwd_subst(const double* __restrict__ L, const double* __restrict__ Li, double* v) {
 #pragma unroll
   for (int m = 0; m < MP; ++m) {
-    double s = v[m];
+    v[m] *= Li[m];
 #pragma unroll
-    for (int j = 0; j < m; ++j) s = fma(-L[m * MP + j], v[j], s);
-    v[m] = s * Li[m];
+    for (int j = m + 1; j < MP; ++j) v[j] = fma(-L[j * MP + m], v[m], v[j]);
   }
 }
 
@@ -182,10 +250,9 @@ template <int MP>
 __device__ __forceinline__ void bwd_subst_T(const double* __restrict__ L, const double* __restrict__ Li, double* v) {
 #pragma unroll
   for (int m = MP - 1; m >= 0; --m) {
-    double s = v[m];
+    v[m] *= Li[m];
 #pragma unroll
-    for (int j = m + 1; j < MP; ++j) s = fma(-L[j * MP + m], v[j], s);
-    v[m] = s * Li[m];
+    for (int j = 0; j < m; ++j) v[j] = fma(-L[m * MP + j], v[m], v[j]);
   }
 }
 
@@ -319,41 +386,45 @@ fitc_row1_kernel(const double* __restrict__ X, const double* __restrict__ y, int
   for (int e = tid; e < MP * MP + MP; e += RB) part[(int64_t)blockIdx.x * (MP * MP + MP) + e] = Cs[e];
 }
 
-// acc[e] = sum_b part[b][e]
+// acc = sum of the per-block partials (multi-GPU path: the result is handed to the all-reduce)
 __global__ void __launch_bounds__(256)
 fitc_reduce_kernel(const double* __restrict__ part, int nblocks, int len, double* __restrict__ acc) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= len) return;
-  double s = 0.0;
-  for (int b = 0; b < nblocks; ++b) s += part[(int64_t)b * len + e];
-  acc[e] = s;
+  block_reduce_partials(part, nblocks, len, acc);
 }
 
 // ---- replicated step before pass 2: C = I + acc1, L_C, beta -----------------------------------------
-__global__ void __launch_bounds__(32)
-fitc_small1_kernel(const double* __restrict__ acc1, double* __restrict__ small, int MP, int D,
-                   int* __restrict__ info) {
-  extern __shared__ double sh[];
+// If `part` is non-null the per-block partials of pass 1 are summed into acc1 first (single GPU:
+// no separate reduce launch).
+template <int MP>
+__global__ void __launch_bounds__(128)
+fitc_small1_kernel(const double* __restrict__ part, int nblocks, double* __restrict__ acc1,
+                   double* __restrict__ small, int D, int* __restrict__ info) {
+  __shared__ double C[MP * MP];
+  __shared__ double Li[MP];
   const SmallLayout lo(MP, D);
-  double* C = sh;
-  const int lane = threadIdx.x;
-  for (int e = lane; e < MP * MP; e += 32) {
+  const int tid = threadIdx.x, lane = tid & 31;
+  if (part) {
+    block_reduce_partials(part, nblocks, MP * MP + MP, acc1);
+    __syncthreads();
+  }
+  for (int e = tid; e < MP * MP; e += 128) {
     const int i = e / MP, j = e - i * MP;
     C[e] = acc1[e] + (i == j ? 1.0 : 0.0);
   }
-  __syncwarp();
-  const int bad = warp_chol(C, MP, MP, lane);
-  if (bad && lane == 0) atomicCAS(info, 0, 1000000 + bad);
-  for (int e = lane; e < MP * MP; e += 32) small[lo.lc + e] = C[e];
-  if (lane < MP) small[lo.lci + lane] = 1.0 / C[lane * MP + lane];
-  __syncwarp();
-  if (lane == 0) {  // beta = L_C^-1 v_y
-    for (int m = 0; m < MP; ++m) {
-      double s = acc1[MP * MP + m];
-      for (int j = 0; j < m; ++j) s -= C[m * MP + j] * small[lo.beta + j];
-      small[lo.beta + m] = s / C[m * MP + m];
+  __syncthreads();
+  if (tid < 32) {
+    const int bad = warp_chol<MP>(C, lane);
+    if (bad && lane == 0) atomicCAS(info, 0, 1000000 + bad);
+    if (lane < MP) Li[lane] = 1.0 / C[lane * MP + lane];
+    __syncwarp();
+    const double x = warp_fwd_vec<MP>(C, Li, lane < MP ? acc1[MP * MP + lane] : 0.0, lane);   // beta = L_C^-1 v_y
+    if (lane < MP) {
+      small[lo.beta + lane] = x;
+      small[lo.lci + lane] = Li[lane];
     }
   }
+  __syncthreads();
+  for (int e = tid; e < MP * MP; e += 128) small[lo.lc + e] = C[e];
 }
 
 // ---- pass 2 ---------------------------------------------------------------------------------------
@@ -463,48 +534,50 @@ fitc_row2_kernel(const double* __restrict__ y, int64_t N, int D, int score, doub
 }
 
 // ---- replicated step before pass 3: C_bar, vy_bar ----------------------------------------------------
-__global__ void __launch_bounds__(32)
-fitc_small2_kernel(const double* __restrict__ acc2, double* __restrict__ small, int M, int MP, int D, int score) {
-  extern __shared__ double sh[];
+template <int MP>
+__global__ void __launch_bounds__(128)
+fitc_small2_kernel(const double* __restrict__ part, int nblocks, double* __restrict__ acc2,
+                   double* __restrict__ small, int M, int D, int score) {
+  __shared__ double LC[MP * MP];
+  __shared__ double T[MP * MP];
+  __shared__ double Li[MP], beta[MP], bb[MP];
   const SmallLayout lo(MP, D);
-  double* LC = sh;               // [MP][MP]
-  double* Lb = LC + MP * MP;     // [MP][MP]  S_W -> L_C_bar -> C_bar
-  double* tmp = Lb + MP * MP;    // [MP][MP]
-  double* vb = tmp + MP * MP;    // [MP]
-  const int lane = threadIdx.x;
-  for (int e = lane; e < MP * MP; e += 32) LC[e] = small[lo.lc + e];
-  __syncwarp();
-  for (int e = lane; e < MP * MP; e += 32) {
-    const int i = e / MP, j = e - i * MP;
-    const double bi = small[lo.beta + i], bj = small[lo.beta + j];
-    const double bbi = acc2[MP * MP + i], bbj = acc2[MP * MP + j];
-    Lb[e] = bi * bbj + 2.0 * acc2[e] + bbi * bj;   // S_W
+  const int tid = threadIdx.x, lane = tid & 31;
+  if (part) {
+    block_reduce_partials(part, nblocks, MP * MP + MP + 1, acc2);
+    __syncthreads();
   }
-  if (lane < MP) {
-    small[lo.bbar + lane] = acc2[MP * MP + lane];
-    vb[lane] = acc2[MP * MP + lane];
+  for (int e = tid; e < MP * MP; e += 128) LC[e] = small[lo.lc + e];
+  if (tid < MP) {
+    Li[tid] = small[lo.lci + tid];
+    beta[tid] = small[lo.beta + tid];
+    bb[tid] = acc2[MP * MP + tid];
   }
-  __syncwarp();
-  warp_solve_LT(LC, Lb, MP, MP, lane);             // L_C^-T S_W
-  for (int e = lane; e < MP * MP; e += 32) {
-    const int i = e / MP, j = e - i * MP;
-    double v = (j <= i) ? -Lb[e] : 0.0;
-    if (score == GPS_NLML && i == j && i < M) v += 1.0 / LC[e];   // d/dL_C of sum log diag(L_C)
-    Lb[e] = v;
-  }
-  __syncwarp();
-  warp_chol_adjoint(LC, Lb, tmp, MP, MP, lane);
-  for (int e = lane; e < MP * MP; e += 32) small[lo.cbar + e] = Lb[e];
-  // vy_bar = L_C^-T beta_bar  (treat as one column: lane 0)
-  if (lane == 0) {
-    for (int i = MP - 1; i >= 0; --i) {
-      double s = vb[i];
-      for (int k = i + 1; k < MP; ++k) s -= LC[k * MP + i] * vb[k];
-      vb[i] = s / LC[i * MP + i];
+  __syncthreads();
+  if (tid < 32) {
+    const int c = lane < MP ? lane : 0;
+    double sw[MP];
+#pragma unroll
+    for (int r = 0; r < MP; ++r)   // column c of S_W = beta beta_bar' + 2 R + beta_bar beta'
+      sw[r] = (lane < MP) ? beta[r] * bb[c] + 2.0 * acc2[r * MP + c] + bb[r] * beta[c] : 0.0;
+    col_solve_LT<MP>(LC, Li, sw);                                     // L_C^-T S_W
+#pragma unroll
+    for (int r = 0; r < MP; ++r) {
+      double v = (r >= lane && lane < MP) ? -sw[r] : 0.0;
+      if (score == GPS_NLML && r == lane && lane < M) v += Li[r];    // d/dL_C of sum log diag(L_C)
+      sw[r] = v;
+    }
+    warp_chol_adjoint<MP>(LC, Li, T, sw, lane);
+    if (lane < MP) {
+#pragma unroll
+      for (int r = 0; r < MP; ++r) small[lo.cbar + r * MP + lane] = sw[r];
+    }
+    const double vb = warp_bwd_vecT<MP>(LC, Li, lane < MP ? bb[lane] : 0.0, lane);   // vy_bar = L_C^-T beta_bar
+    if (lane < MP) {
+      small[lo.vyb + lane] = vb;
+      small[lo.bbar + lane] = bb[lane];
     }
   }
-  __syncwarp();
-  if (lane < MP) small[lo.vyb + lane] = vb[lane];
 }
 
 // ---- pass 3 ---------------------------------------------------------------------------------------
@@ -604,7 +677,7 @@ fitc_row3_kernel(const double* __restrict__ X, const double* __restrict__ y, int
       w[m] += vyb[m] * yi * il + 2.0 * cv[m] * il - 2.0 * lb * v[m];
       VbT[m * LDT + tid] = w[m];
     }
-    // Kuf_bar = L_A^-T V_bar (in place), G = Kuf_bar o Kuf, g_b rows
+    // Kuf_bar = L_A^-T V_bar (in place), G = Kuf_bar o Kuf (kept in w[]), g_b rows
     bwd_subst_T<MP>(LA, LAi, w);
 #pragma unroll
     for (int m = 0; m < MP; ++m) {
@@ -613,12 +686,18 @@ fitc_row3_kernel(const double* __restrict__ X, const double* __restrict__ y, int
         const double df = Us[m * D + d] - XsT[d * LDT + tid];
         r2 = fma(df, df, r2);
       }
-      const double gm = (m < M && live) ? w[m] * ea * exp(-0.5 * r2) : 0.0;
-      GT[m * LDT + tid] = gm;
-      for (int d = 0; d < D; ++d) {
-        const double df = Us[m * D + d] - XsT[d * LDT + tid];
-        gbs[d * RB + tid] = fma(gm, df * df, gbs[d * RB + tid]);
+      w[m] = (m < M && live) ? w[m] * ea * exp(-0.5 * r2) : 0.0;
+      GT[m * LDT + tid] = w[m];
+    }
+    for (int d = 0; d < D; ++d) {
+      const double xd = XsT[d * LDT + tid];
+      double sgb = 0.0;
+#pragma unroll
+      for (int m = 0; m < MP; ++m) {
+        const double df = Us[m * D + d] - xd;
+        sgb = fma(w[m], df * df, sgb);
       }
+      gbs[d * RB + tid] += sgb;
     }
     __syncwarp();
     tile_outer<MF, MF, false>(VbT, VT, nullptr, warp, lane, sacc);
@@ -640,67 +719,76 @@ fitc_row3_kernel(const double* __restrict__ X, const double* __restrict__ y, int
 
 // ---- finish: L_A_bar -> A_bar, all gradients --------------------------------------------------------
 // out = [obj | g_theta (D+2) | g_U (M*D)]
-__global__ void __launch_bounds__(32)
-fitc_small3_kernel(const double* __restrict__ acc2, const double* __restrict__ acc3,
-                   const double* __restrict__ small, const double* __restrict__ par, int M, int MP, int D,
-                   int PC, int score, double world_n, double* __restrict__ out) {
-  extern __shared__ double sh[];
+template <int MP>
+__global__ void __launch_bounds__(128)
+fitc_small3_kernel(const double* __restrict__ part, int nblocks, const double* __restrict__ acc2,
+                   double* __restrict__ acc3, const double* __restrict__ small, const double* __restrict__ par,
+                   int M, int D, int PC, int score, double world_n, double* __restrict__ out) {
+  __shared__ double LA[MP * MP];
+  __shared__ double T[MP * MP];
+  __shared__ double G2[MP * MP];
+  __shared__ double Li[MP];
+  __shared__ double us[MP * 16];
+  __shared__ double red[32];
   const SmallLayout lo(MP, D);
-  double* LA = sh;               // [MP][MP]
-  double* Lb = LA + MP * MP;     // S -> L_A_bar -> A_bar -> G2
-  double* tmp = Lb + MP * MP;
-  double* red = tmp + MP * MP;   // [32]
-  const int lane = threadIdx.x;
-  for (int e = lane; e < MP * MP; e += 32) {
-    LA[e] = small[lo.la + e];
-    Lb[e] = acc3[e];
+  const int tid = threadIdx.x, lane = tid & 31;
+  if (part) {
+    block_reduce_partials(part, nblocks, MP * MP + MP * PC + D + 1, acc3);
+    __syncthreads();
   }
-  __syncwarp();
-  warp_solve_LT(LA, Lb, MP, MP, lane);     // L_A^-T S
-  for (int e = lane; e < MP * MP; e += 32) {
-    const int i = e / MP, j = e - i * MP;
-    Lb[e] = (j <= i) ? -Lb[e] : 0.0;
+  for (int e = tid; e < MP * MP; e += 128) LA[e] = small[lo.la + e];
+  for (int e = tid; e < MP * D; e += 128) us[e] = small[lo.us + e];
+  if (tid < MP) Li[tid] = small[lo.lai + tid];
+  __syncthreads();
+  if (tid < 32) {
+    const int c = lane < MP ? lane : 0;
+    double sc[MP];
+#pragma unroll
+    for (int r = 0; r < MP; ++r) sc[r] = (lane < MP) ? acc3[r * MP + c] : 0.0;   // column c of S
+    col_solve_LT<MP>(LA, Li, sc);                                                  // L_A^-T S
+#pragma unroll
+    for (int r = 0; r < MP; ++r) sc[r] = (r >= lane && lane < MP) ? -sc[r] : 0.0;  // L_A_bar
+    warp_chol_adjoint<MP>(LA, Li, T, sc, lane);                                    // A_bar
+    if (lane < MP) {
+#pragma unroll
+      for (int r = 0; r < MP; ++r) G2[r * MP + lane] = sc[r] * small[lo.kuu + r * MP + lane];   // A_bar o K_uu
+    }
   }
-  __syncwarp();
-  warp_chol_adjoint(LA, Lb, tmp, MP, MP, lane);
-  for (int e = lane; e < MP * MP; e += 32) Lb[e] *= small[lo.kuu + e];   // G2 = A_bar o K_uu
-  __syncwarp();
-  const double* P = acc3 + MP * MP;          // [MP][PC]
+  __syncthreads();
+  const double* P = acc3 + MP * MP;          // [MP][PC]: columns 0..D-1 = sum G xs_d, column D = sum G
   const double* gbrow = P + MP * PC;         // [D]
   const double sum_lb = gbrow[D];
   const double ea = par[0], sn2 = par[1];
-  // g_a = ea * sum_lb + sum_m S0_m + sum G2
-  double s = 0.0;
-  for (int e = lane; e < MP * MP; e += 32) s += Lb[e];
-  for (int m = lane; m < MP; m += 32) s += P[m * PC + D];
-  s = warp_sum(s);
-  if (lane == 0) {
+  double sa = 0.0;
+  for (int e = tid; e < MP * MP; e += 128) sa += G2[e];
+  for (int m = tid; m < MP; m += 128) sa += P[m * PC + D];
+  sa = block_sum(sa, red);
+  if (tid == 0) {
     double obj = acc2[MP * MP + MP];
     if (score == GPS_NLML) {
-      obj += 0.5 * world_n * 1.83787706640934548356;  // N/2 log 2 pi
+      obj += 0.5 * world_n * 1.83787706640934548356;               // N/2 log 2 pi
       for (int m = 0; m < M; ++m) obj -= log(small[lo.lci + m]);   // + sum log diag(L_C)
     }
     out[0] = obj;
-    out[1] = ea * sum_lb + s;
+    out[1] = ea * sum_lb + sa;
     out[1 + D + 1] = sn2 * sum_lb;
   }
-  const double* Us = small + lo.us;
   for (int d = 0; d < D; ++d) {
     double sb = 0.0;
-    for (int e = lane; e < MP * MP; e += 32) {
+    for (int e = tid; e < MP * MP; e += 128) {
       const int i = e / MP, j = e - i * MP;
-      const double df = Us[i * D + d] - Us[j * D + d];
-      sb = fma(Lb[e], df * df, sb);
+      const double df = us[i * D + d] - us[j * D + d];
+      sb = fma(G2[e], df * df, sb);
     }
-    sb = warp_sum(sb);
-    if (lane == 0) out[2 + d] = gbrow[d] + sb;
+    sb = block_sum(sb, red);
+    if (tid == 0) out[2 + d] = gbrow[d] + sb;
   }
   // g_U[m][d] = -invl_d ( us_md S0_m - P_md ) - 2 invl_d sum_m' G2_mm' (us_md - us_m'd)
-  for (int e = lane; e < M * D; e += 32) {
+  for (int e = tid; e < M * D; e += 128) {
     const int m = e / D, d = e - m * D;
     double t = 0.0;
-    for (int j = 0; j < MP; ++j) t = fma(Lb[m * MP + j], Us[m * D + d] - Us[j * D + d], t);
-    out[1 + D + 2 + e] = -par[2 + d] * (Us[m * D + d] * P[m * PC + D] - P[m * PC + d]) - 2.0 * par[2 + d] * t;
+    for (int j = 0; j < MP; ++j) t = fma(G2[m * MP + j], us[m * D + d] - us[j * D + d], t);
+    out[1 + D + 2 + e] = -par[2 + d] * (us[m * D + d] * P[m * PC + D] - P[m * PC + d]) - 2.0 * par[2 + d] * t;
   }
 }
 
@@ -770,9 +858,15 @@ size_t smem_row3(int MP, int D, int PC) {
 }
 size_t smem_pred(int MP, int D) { return ((size_t)MP * D + 2 * MP * MP + 3 * MP + (size_t)D * LDT) * 8; }
 
+// raise the dynamic shared-memory limit of a kernel once per (kernel, size)
 template <typename K>
 int set_smem(gps_ctx* ctx, K kern, size_t bytes) {
+  static size_t configured = 0;   // one instance per kernel type K... per template instantiation of set_smem
+  static K last = nullptr;
+  if (last == kern && configured >= bytes) return GPS_OK;
   GPS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  last = kern;
+  configured = bytes;
   return GPS_OK;
 }
 
@@ -820,6 +914,30 @@ int run_pred(gps_ctx* ctx, const double* Xs, int64_t T, double* mean, double* va
   return GPS_OK;
 }
 
+template <int MP>
+int run_small0(gps_ctx* ctx, const double* dU) {
+  auto& f = ctx->fitc;
+  fitc_small0_kernel<MP><<<1, 128, 0, ctx->stream>>>(dU, ctx->params.p, f.small.p, f.M, ctx->D, f.jitter, ctx->d_info);
+  GPS_LAUNCH_CHECK();
+  return GPS_OK;
+}
+template <int MP>
+int run_small1(gps_ctx* ctx, const double* part, double* acc1) {
+  auto& f = ctx->fitc;
+  fitc_small1_kernel<MP><<<1, 128, 0, ctx->stream>>>(part, f.grid, acc1, f.small.p, ctx->D, ctx->d_info);
+  GPS_LAUNCH_CHECK();
+  return GPS_OK;
+}
+template <int MP>
+int run_small2(gps_ctx* ctx, const double* part, double* acc2) {
+  auto& f = ctx->fitc;
+  fitc_small2_kernel<MP><<<1, 128, 0, ctx->stream>>>(part, f.grid, acc2, f.small.p, f.M, ctx->D, f.score);
+  GPS_LAUNCH_CHECK();
+  return GPS_OK;
+}
+template <int MP>
+int run_small3(gps_ctx* ctx, const double* part, const double* acc2, double* acc3, double* out);
+
 #define MP_DISPATCH(MPV, CALL)                    \
   switch (MPV) {                                  \
     case 8:  { constexpr int MPC = 8;  CALL; } break;  \
@@ -833,6 +951,15 @@ int pc_of(int D) { return (D + 1 <= 8) ? 8 : 16; }
 int len1_of(int MP) { return MP * MP + MP; }
 int len2_of(int MP) { return MP * MP + MP + 1; }
 int len3_of(int MP, int D) { return MP * MP + MP * pc_of(D) + D + 1; }
+
+template <int MP>
+int run_small3(gps_ctx* ctx, const double* part, const double* acc2, double* acc3, double* out) {
+  auto& f = ctx->fitc;
+  fitc_small3_kernel<MP><<<1, 128, 0, ctx->stream>>>(part, f.grid, acc2, acc3, f.small.p, ctx->params.p, f.M, ctx->D,
+                                                     pc_of(ctx->D), f.score, (double)f.world_n, out);
+  GPS_LAUNCH_CHECK();
+  return GPS_OK;
+}
 
 int reduce_to(gps_ctx* ctx, const double* part, int nblocks, int len, double* acc) {
   fitc_reduce_kernel<<<(len + 255) / 256, 256, 0, ctx->stream>>>(part, nblocks, len, acc);
@@ -887,9 +1014,7 @@ int gps_fitc_begin(gps_ctx* ctx, const double* theta, const double* U, int M, do
   GPS_CHECK(gps_upload_params(ctx, theta, D, &f.ea, &f.sn2));
   double* dU = f.small.p + lo.total;   // raw inducing inputs
   GPS_CUDA(cudaMemcpyAsync(dU, U, (size_t)M * D * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-  fitc_small0_kernel<<<1, 32, (size_t)MP * MP * 8, ctx->stream>>>(dU, ctx->params.p, f.small.p, M, MP, D, jitter,
-                                                                 ctx->d_info);
-  GPS_LAUNCH_CHECK();
+  MP_DISPATCH(MP, GPS_CHECK(run_small0<MPC>(ctx, dU)));
   ctx->launches++;
   f.begun = true;
   return GPS_OK;
@@ -912,8 +1037,7 @@ int gps_fitc_pass2(gps_ctx* ctx, const double* acc1, double* acc2) {
   auto& f = ctx->fitc;
   if (!f.begun) return gps_fail(ctx, GPS_ESTATE, "fitc_pass2: call gps_fitc_begin first");
   GPS_CUDA(cudaSetDevice(ctx->device));
-  fitc_small1_kernel<<<1, 32, (size_t)f.MP * f.MP * 8, ctx->stream>>>(acc1, f.small.p, f.MP, ctx->D, ctx->d_info);
-  GPS_LAUNCH_CHECK();
+  MP_DISPATCH(f.MP, GPS_CHECK(run_small1<MPC>(ctx, nullptr, const_cast<double*>(acc1))));
   MP_DISPATCH(f.MP, GPS_CHECK(run_row2<MPC>(ctx, f.part.p)));
   ctx->launches += 2;
   GPS_CHECK(reduce_to(ctx, f.part.p, f.grid, len2_of(f.MP), acc2));
@@ -927,9 +1051,7 @@ int gps_fitc_pass3(gps_ctx* ctx, const double* acc2, double* acc3) {
   auto& f = ctx->fitc;
   if (!f.pass2_done) return gps_fail(ctx, GPS_ESTATE, "fitc_pass3: pass 2 has not run");
   GPS_CUDA(cudaSetDevice(ctx->device));
-  fitc_small2_kernel<<<1, 32, (size_t)(3 * f.MP * f.MP + f.MP) * 8, ctx->stream>>>(acc2, f.small.p, f.M, f.MP, ctx->D,
-                                                                                 f.score);
-  GPS_LAUNCH_CHECK();
+  MP_DISPATCH(f.MP, GPS_CHECK(run_small2<MPC>(ctx, nullptr, const_cast<double*>(acc2))));
   if (pc_of(ctx->D) == 8) {
     MP_DISPATCH(f.MP, GPS_CHECK((run_row3<MPC, 1>(ctx, f.part.p))));
   } else {
@@ -941,21 +1063,17 @@ int gps_fitc_pass3(gps_ctx* ctx, const double* acc2, double* acc3) {
   return GPS_OK;
 }
 
-int gps_fitc_finish(gps_ctx* ctx, const double* acc2, const double* acc3, double* obj, double* grad_theta,
-                    double* grad_U) {
-  if (!ctx) return GPS_EINVAL;
+static int fitc_finish_impl(gps_ctx* ctx, const double* part, const double* acc2, double* acc3, double* obj,
+                           double* grad_theta, double* grad_U) {
   auto& f = ctx->fitc;
-  if (!f.pass2_done) return gps_fail(ctx, GPS_ESTATE, "fitc_finish: passes have not run");
-  GPS_CUDA(cudaSetDevice(ctx->device));
   const int D = ctx->D, M = f.M, MP = f.MP;
   const SmallLayout lo(MP, D);
   double* out = f.small.p + lo.total + M * D;   // [obj | g_theta | g_U]
   const int nout = 1 + D + 2 + M * D;
-  fitc_small3_kernel<<<1, 32, (size_t)(3 * MP * MP + 32) * 8, ctx->stream>>>(
-      acc2, acc3, f.small.p, ctx->params.p, M, MP, D, pc_of(D), f.score, (double)f.world_n, out);
-  GPS_LAUNCH_CHECK();
+  MP_DISPATCH(MP, GPS_CHECK(run_small3<MPC>(ctx, part, acc2, acc3, out)));
   ctx->launches++;
-  std::vector<double> h(nout);
+  std::vector<double>& h = f.host_out;
+  h.resize(nout + 1);
   GPS_CUDA(cudaMemcpyAsync(h.data(), out, nout * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   int info = 0;
   GPS_CUDA(cudaMemcpyAsync(&info, ctx->d_info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
@@ -971,35 +1089,42 @@ int gps_fitc_finish(gps_ctx* ctx, const double* acc2, const double* acc3, double
   return GPS_OK;
 }
 
+int gps_fitc_finish(gps_ctx* ctx, const double* acc2, const double* acc3, double* obj, double* grad_theta,
+                    double* grad_U) {
+  if (!ctx) return GPS_EINVAL;
+  auto& f = ctx->fitc;
+  if (!f.pass2_done) return gps_fail(ctx, GPS_ESTATE, "fitc_finish: passes have not run");
+  GPS_CUDA(cudaSetDevice(ctx->device));
+  return fitc_finish_impl(ctx, nullptr, acc2, const_cast<double*>(acc3), obj, grad_theta, grad_U);
+}
+
 int gps_fitc_eval(gps_ctx* ctx, const double* theta, const double* U, int M, double jitter, int score,
                   double* obj, double* grad_theta, double* grad_U) {
   if (!ctx) return GPS_EINVAL;
   GPS_CHECK(gps_fitc_begin(ctx, theta, U, M, jitter, score, ctx->N));
   auto& f = ctx->fitc;
-  // single GPU: same kernels, no host synchronisation between the passes
+  // single GPU: the same row kernels; the per-block partials are summed inside the replicated
+  // kernels (no separate reduce launches, no host synchronisation between the passes):
+  // 7 launches per evaluation.
   MP_DISPATCH(f.MP, GPS_CHECK(run_row1<MPC>(ctx, f.part.p)));
-  GPS_CHECK(reduce_to(ctx, f.part.p, f.grid, len1_of(f.MP), f.acc1.p));
-  fitc_small1_kernel<<<1, 32, (size_t)f.MP * f.MP * 8, ctx->stream>>>(f.acc1.p, f.small.p, f.MP, ctx->D, ctx->d_info);
-  GPS_LAUNCH_CHECK();
+  MP_DISPATCH(f.MP, GPS_CHECK(run_small1<MPC>(ctx, f.part.p, f.acc1.p)));
   MP_DISPATCH(f.MP, GPS_CHECK(run_row2<MPC>(ctx, f.part.p)));
-  GPS_CHECK(reduce_to(ctx, f.part.p, f.grid, len2_of(f.MP), f.acc2.p));
   f.pass2_done = true;
   ctx->launches += 3;
   if (grad_theta || grad_U) {
-    fitc_small2_kernel<<<1, 32, (size_t)(3 * f.MP * f.MP + f.MP) * 8, ctx->stream>>>(f.acc2.p, f.small.p, f.M, f.MP,
-                                                                                   ctx->D, f.score);
-    GPS_LAUNCH_CHECK();
+    MP_DISPATCH(f.MP, GPS_CHECK(run_small2<MPC>(ctx, f.part.p, f.acc2.p)));
     if (pc_of(ctx->D) == 8) {
       MP_DISPATCH(f.MP, GPS_CHECK((run_row3<MPC, 1>(ctx, f.part.p))));
     } else {
       MP_DISPATCH(f.MP, GPS_CHECK((run_row3<MPC, 2>(ctx, f.part.p))));
     }
     ctx->launches += 2;
-    GPS_CHECK(reduce_to(ctx, f.part.p, f.grid, len3_of(f.MP, ctx->D), f.acc3.p));
-  } else {
-    GPS_CUDA(cudaMemsetAsync(f.acc3.p, 0, len3_of(f.MP, ctx->D) * sizeof(double), ctx->stream));
+    return fitc_finish_impl(ctx, f.part.p, f.acc2.p, f.acc3.p, obj, grad_theta, grad_U);
   }
-  return gps_fitc_finish(ctx, f.acc2.p, f.acc3.p, obj, grad_theta, grad_U);
+  // objective only: reduce pass 2 and finish with a zero pass-3 accumulator
+  GPS_CHECK(reduce_to(ctx, f.part.p, f.grid, len2_of(f.MP), f.acc2.p));
+  GPS_CUDA(cudaMemsetAsync(f.acc3.p, 0, len3_of(f.MP, ctx->D) * sizeof(double), ctx->stream));
+  return fitc_finish_impl(ctx, nullptr, f.acc2.p, f.acc3.p, obj, nullptr, nullptr);
 }
 
 int gps_fitc_loo(gps_ctx* ctx, double* loo_mean, double* loo_var) {
