@@ -25,6 +25,10 @@ int gps_dbg_factor(gps_ctx* ctx, const double* A, int64_t n, double* L, double* 
 /* Issue-rate micro-benchmarks on all SMs: DMMA m8n8k4 and DFMA, TFLOP/s each. */
 int gps_dbg_fp64_peak(gps_ctx* ctx, int iters, double* dmma_tflops, double* dfma_tflops);
 
+/* Tuning knobs for A/B measurements: what = 0 selects the tile-GEMM policy
+ * (0: BK16 x 4 stages, 1: + fragment double-buffering, 2: BK32 x 3 stages, 3: BK32 + double-buffering). */
+int gps_dbg_set_variant(gps_ctx* ctx, int what, int value);
+
 /* Training Gram K = ARD(X,X) + sn2 I of the current data set at theta, N x N (UVA out). */
 int gps_dbg_gram(gps_ctx* ctx, const double* theta, double* K);
 

@@ -33,6 +33,7 @@ struct gps_ctx {
   std::string err;
   int64_t launches = 0;
   int sm_count = 148;
+  int gemm_variant = 5;               // tile-GEMM policy (see gps_gemm.cu); switched by gps_dbg_set_variant
   // GEMM timing of the last full eval
   bool time_gemm = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> gemm_events;

@@ -142,6 +142,13 @@ int gps_dbg_fp64_peak(gps_ctx* ctx, int iters, double* dmma_tflops, double* dfma
   return GPS_OK;
 }
 
+int gps_dbg_set_variant(gps_ctx* ctx, int what, int value) {
+  if (!ctx) return GPS_EINVAL;
+  if (what == 0) ctx->gemm_variant = value;
+  else return gps_fail(ctx, GPS_EINVAL, "dbg_set_variant: unknown knob %d", what);
+  return GPS_OK;
+}
+
 int gps_dbg_gram(gps_ctx* ctx, const double* theta, double* K) {
   if (!ctx) return GPS_EINVAL;
   if (ctx->N == 0) return gps_fail(ctx, GPS_ESTATE, "dbg_gram: no data");

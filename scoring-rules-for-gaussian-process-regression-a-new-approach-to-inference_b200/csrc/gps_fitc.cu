@@ -163,18 +163,15 @@ __device__ __forceinline__ void warp_chol_adjoint(const double* __restrict__ L, 
   for (int r = 0; r < MP; ++r) lb[r] = 0.5 * p[r];
 }
 
-// acc[e] = sum_b part[b][e], by the whole block; result also left in shared `sacc` if non-null
+// acc[e] = sum_b part[b][e] by the whole block, in block order (deterministic).  The loop is
+// unrolled so that 16 independent loads are in flight per thread: the sum is latency-bound.
 __device__ __forceinline__ void block_reduce_partials(const double* __restrict__ part, int nblocks, int len,
                                                       double* __restrict__ acc_out) {
   for (int e = threadIdx.x; e < len; e += blockDim.x) {
-    double s0 = 0.0, s1 = 0.0;
-    int bI = 0;
-    for (; bI + 1 < nblocks; bI += 2) {
-      s0 += part[(int64_t)bI * len + e];
-      s1 += part[(int64_t)(bI + 1) * len + e];
-    }
-    if (bI < nblocks) s0 += part[(int64_t)bI * len + e];
-    acc_out[e] = s0 + s1;
+    double s = 0.0;
+#pragma unroll 16
+    for (int b = 0; b < nblocks; ++b) s += part[(int64_t)b * len + e];
+    acc_out[e] = s;
   }
 }
 

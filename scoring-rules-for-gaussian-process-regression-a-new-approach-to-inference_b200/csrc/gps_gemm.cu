@@ -19,13 +19,22 @@
 
 namespace {
 
-constexpr int BK = 16;
-constexpr int STAGES = 4;
-constexpr int LD_KC = 20;     // [128][20]
-constexpr int LD_MC = 132;    // [16][132]
-constexpr int OPER = 128 * LD_KC;  // 2560 doubles >= 16*132
-constexpr int GEMM_THREADS = 256;
-constexpr size_t GEMM_SMEM = (size_t)STAGES * 2 * OPER * sizeof(double);  // 163840 B
+constexpr int LD_MC = 132;    // [BK][132]
+
+// Tile-shape policy: BK = k-depth of one pipeline stage, STAGES = ring depth, PIPE = explicit
+// register double-buffering of the m8n8k4 fragments across k4-steps.
+template <int BK_, int STAGES_, bool PIPE_, int WM_ = 2>
+struct GemmCfg {
+  static constexpr int BK = BK_;
+  static constexpr int STAGES = STAGES_;
+  static constexpr bool PIPE = PIPE_;
+  static constexpr int WM = WM_, WN = 4;                   // warp grid: WM x 4 warps
+  static constexpr int THREADS = 32 * WM_ * 4;
+  static constexpr int MF = 128 / WM_ / 8, NF = 4;         // m8n8k4 fragments per warp tile
+  static constexpr int LD_KC = BK_ + 4;                    // [128][BK+4]: (BK+4) % 16 == 4
+  static constexpr int OPER = 128 * LD_KC;                 // doubles per operand per stage (>= BK*132)
+  static constexpr size_t SMEM = (size_t)STAGES_ * 2 * OPER * sizeof(double);
+};
 
 __device__ __forceinline__ void cp_async16(double* smem, const double* gmem) {
   unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -43,17 +52,19 @@ __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, do
                : "d"(a), "d"(b));
 }
 
-// stage one 128 x 16 operand panel. KC: rows are matrix rows, k contiguous in memory.
+// stage one 128 x BK operand panel. KC: rows are matrix rows, k contiguous in memory.
 // MC: the panel is read from a [k][m] matrix (m contiguous in memory).
-template <bool MC>
+template <class Cfg, bool MC>
 __device__ __forceinline__ void load_panel(double* s, const double* __restrict__ g, int64_t ld, int row0,
                                            int k, int tid) {
+  constexpr int CHUNKS = 128 * Cfg::BK / 2;     // 16-byte chunks per panel
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int c = tid + i * GEMM_THREADS;
+  for (int i = 0; i < CHUNKS / Cfg::THREADS; ++i) {
+    const int c = tid + i * Cfg::THREADS;
     if (!MC) {
-      const int r = c >> 3, kc = c & 7;
-      cp_async16(s + r * LD_KC + kc * 2, g + (int64_t)(row0 + r) * ld + k + kc * 2);
+      constexpr int CPR = Cfg::BK / 2;          // chunks per row
+      const int r = c / CPR, kc = c % CPR;
+      cp_async16(s + r * Cfg::LD_KC + kc * 2, g + (int64_t)(row0 + r) * ld + k + kc * 2);
     } else {
       const int kr = c >> 6, mc = c & 63;
       cp_async16(s + kr * LD_MC + mc * 2, g + (int64_t)(k + kr) * ld + row0 + mc * 2);
@@ -61,35 +72,37 @@ __device__ __forceinline__ void load_panel(double* s, const double* __restrict__
   }
 }
 
-template <bool MC>
+template <class Cfg, bool MC>
 __device__ __forceinline__ double frag(const double* s, int row, int k) {
-  return MC ? s[k * LD_MC + row] : s[row * LD_KC + k];
+  return MC ? s[k * LD_MC + row] : s[row * Cfg::LD_KC + k];
 }
 
-template <bool A_MC, bool B_MC, bool DVEC, bool MIRROR>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
+template <class Cfg, bool A_MC, bool B_MC, bool DVEC, bool MIRROR>
+__global__ void __launch_bounds__(Cfg::THREADS, 1)
 gemm_tile_kernel(const double* __restrict__ A, int64_t lda, const double* __restrict__ B, int64_t ldb,
                  double* __restrict__ C, int64_t ldc, double alpha, double beta,
                  const double* __restrict__ dvec, const GemmTask* __restrict__ tasks) {
   extern __shared__ __align__(16) double smem[];
+  constexpr int BK = Cfg::BK, STAGES = Cfg::STAGES, OPER = Cfg::OPER, KSTEPS = Cfg::BK / 4;
+  constexpr int MF = Cfg::MF, NF = Cfg::NF, WROWS = 8 * Cfg::MF;
   const GemmTask t = tasks[blockIdx.x];
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
-  const int wm = warp >> 2, wn = warp & 3;
+  const int wm = warp >> 2, wn = warp & 3;   // WM x 4 warps
   const int g = lane >> 2, tq = lane & 3;
   const int nk = (t.k1 - t.k0) / BK;
 
-  double acc[8][4][2];
+  double acc[MF][NF][2];
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < MF; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int j = 0; j < NF; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
 #pragma unroll
   for (int s = 0; s < STAGES - 1; ++s) {
     if (s < nk) {
-      load_panel<A_MC>(smem + (size_t)s * 2 * OPER, A, lda, t.a_row, t.k0 + s * BK, tid);
-      load_panel<B_MC>(smem + (size_t)s * 2 * OPER + OPER, B, ldb, t.b_row, t.k0 + s * BK, tid);
+      load_panel<Cfg, A_MC>(smem + (size_t)s * 2 * OPER, A, lda, t.a_row, t.k0 + s * BK, tid);
+      load_panel<Cfg, B_MC>(smem + (size_t)s * 2 * OPER + OPER, B, ldb, t.b_row, t.k0 + s * BK, tid);
     }
     cp_async_commit();
   }
@@ -101,40 +114,68 @@ gemm_tile_kernel(const double* __restrict__ A, int64_t lda, const double* __rest
       const int nx = kb + STAGES - 1;
       if (nx < nk) {
         double* sl = smem + (size_t)(nx % STAGES) * 2 * OPER;
-        load_panel<A_MC>(sl, A, lda, t.a_row, t.k0 + nx * BK, tid);
-        load_panel<B_MC>(sl + OPER, B, ldb, t.b_row, t.k0 + nx * BK, tid);
+        load_panel<Cfg, A_MC>(sl, A, lda, t.a_row, t.k0 + nx * BK, tid);
+        load_panel<Cfg, B_MC>(sl + OPER, B, ldb, t.b_row, t.k0 + nx * BK, tid);
       }
       cp_async_commit();
     }
     const double* As = smem + (size_t)(kb % STAGES) * 2 * OPER;
     const double* Bs = As + OPER;
+    if (Cfg::PIPE) {
+      double a[2][MF], b[2][NF];
 #pragma unroll
-    for (int kk = 0; kk < BK / 4; ++kk) {
-      const int k = kk * 4 + tq;
-      double a[8], b[4];
+      for (int i = 0; i < MF; ++i) a[0][i] = frag<Cfg, A_MC>(As, wm * WROWS + i * 8 + g, tq);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) a[i] = frag<A_MC>(As, wm * 64 + i * 8 + g, k);
+      for (int j = 0; j < 4; ++j) b[0][j] = frag<Cfg, B_MC>(Bs, wn * 32 + j * 8 + g, tq);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = frag<B_MC>(Bs, wn * 32 + j * 8 + g, k);
-      if (DVEC) {
-        const double dv = __ldg(dvec + t.k0 + kb * BK + k);
+      for (int kk = 0; kk < KSTEPS; ++kk) {
+        const int cur = kk & 1, nxt = cur ^ 1;
+        if (kk + 1 < KSTEPS) {
+          const int k = (kk + 1) * 4 + tq;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) b[j] *= dv;
+          for (int j = 0; j < 4; ++j) b[nxt][j] = frag<Cfg, B_MC>(Bs, wn * 32 + j * 8 + g, k);
+#pragma unroll
+          for (int i = 0; i < MF; ++i) a[nxt][i] = frag<Cfg, A_MC>(As, wm * WROWS + i * 8 + g, k);
+        }
+        if (DVEC) {
+          const double dv = __ldg(dvec + t.k0 + kb * BK + kk * 4 + tq);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) b[cur][j] *= dv;
+        }
+#pragma unroll
+        for (int i = 0; i < MF; ++i)
+#pragma unroll
+          for (int j = 0; j < NF; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[cur][i], b[cur][j]);
       }
+    } else {
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
+      for (int kk = 0; kk < KSTEPS; ++kk) {
+        const int k = kk * 4 + tq;
+        double a[MF], b[NF];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        for (int i = 0; i < MF; ++i) a[i] = frag<Cfg, A_MC>(As, wm * WROWS + i * 8 + g, k);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) b[j] = frag<Cfg, B_MC>(Bs, wn * 32 + j * 8 + g, k);
+        if (DVEC) {
+          const double dv = __ldg(dvec + t.k0 + kb * BK + k);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) b[j] *= dv;
+        }
+#pragma unroll
+        for (int i = 0; i < MF; ++i)
+#pragma unroll
+          for (int j = 0; j < NF; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+      }
     }
   }
   cp_async_wait<0>();
 
   // epilogue: thread holds C[row][col..col+1] of each fragment
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int row = t.c_row + wm * 64 + i * 8 + g;
+  for (int i = 0; i < MF; ++i) {
+    const int row = t.c_row + wm * WROWS + i * 8 + g;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < NF; ++j) {
       const int col = t.c_col + wn * 32 + j * 8 + 2 * tq;
       double2* p = reinterpret_cast<double2*>(C + (int64_t)row * ldc + col);
       double2 v;
@@ -154,19 +195,36 @@ gemm_tile_kernel(const double* __restrict__ A, int64_t lda, const double* __rest
   }
 }
 
-template <bool A_MC, bool B_MC, bool DVEC, bool MIRROR>
+template <class Cfg, bool A_MC, bool B_MC, bool DVEC, bool MIRROR>
 int launch(gps_ctx* ctx, const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc,
            double alpha, double beta, const double* dvec, const GemmTask* tasks, size_t ntasks) {
-  auto kern = gemm_tile_kernel<A_MC, B_MC, DVEC, MIRROR>;
+  auto kern = gemm_tile_kernel<Cfg, A_MC, B_MC, DVEC, MIRROR>;
   static bool configured = false;
   if (!configured) {
-    GPS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GEMM_SMEM));
+    GPS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
     configured = true;
   }
-  kern<<<(unsigned)ntasks, GEMM_THREADS, GEMM_SMEM, ctx->stream>>>(A, lda, B, ldb, C, ldc, alpha, beta, dvec,
-                                                                    tasks);
+  kern<<<(unsigned)ntasks, Cfg::THREADS, Cfg::SMEM, ctx->stream>>>(A, lda, B, ldb, C, ldc, alpha, beta, dvec,
+                                                                  tasks);
   GPS_LAUNCH_CHECK();
   return GPS_OK;
+}
+
+template <class Cfg>
+int dispatch(gps_ctx* ctx, int kind, const double* A, int64_t lda, const double* B, int64_t ldb, double* C,
+             int64_t ldc, double alpha, double beta, const double* dvec, bool mirror, const GemmTask* d_tasks,
+             size_t ntasks) {
+  if (kind == GEMM_KC_KC) {
+    if (dvec) return launch<Cfg, false, false, true, false>(ctx, A, lda, B, ldb, C, ldc, alpha, beta, dvec, d_tasks, ntasks);
+    return launch<Cfg, false, false, false, false>(ctx, A, lda, B, ldb, C, ldc, alpha, beta, dvec, d_tasks, ntasks);
+  }
+  if (kind == GEMM_KC_MC)
+    return launch<Cfg, false, true, false, false>(ctx, A, lda, B, ldb, C, ldc, alpha, beta, dvec, d_tasks, ntasks);
+  if (kind == GEMM_MC_MC) {
+    if (mirror) return launch<Cfg, true, true, false, true>(ctx, A, lda, B, ldb, C, ldc, alpha, beta, dvec, d_tasks, ntasks);
+    return launch<Cfg, true, true, false, false>(ctx, A, lda, B, ldb, C, ldc, alpha, beta, dvec, d_tasks, ntasks);
+  }
+  return gps_fail(ctx, GPS_EINVAL, "gemm kind %d", kind);
 }
 
 }  // namespace
@@ -189,20 +247,13 @@ int gps_gemm_tasks(gps_ctx* ctx, int kind, const double* A, int64_t lda, const d
     GPS_CUDA(cudaEventRecord(e0, ctx->stream));
   }
   int r;
-  if (kind == GEMM_KC_KC) {
-    if (dvec)
-      r = launch<false, false, true, false>(ctx, A, lda, B, ldb, C, ldc, alpha, beta, dvec, d_tasks, ntasks);
-    else
-      r = launch<false, false, false, false>(ctx, A, lda, B, ldb, C, ldc, alpha, beta, dvec, d_tasks, ntasks);
-  } else if (kind == GEMM_KC_MC) {
-    r = launch<false, true, false, false>(ctx, A, lda, B, ldb, C, ldc, alpha, beta, dvec, d_tasks, ntasks);
-  } else if (kind == GEMM_MC_MC) {
-    if (mirror)
-      r = launch<true, true, false, true>(ctx, A, lda, B, ldb, C, ldc, alpha, beta, dvec, d_tasks, ntasks);
-    else
-      r = launch<true, true, false, false>(ctx, A, lda, B, ldb, C, ldc, alpha, beta, dvec, d_tasks, ntasks);
-  } else {
-    return gps_fail(ctx, GPS_EINVAL, "gemm kind %d", kind);
+  switch (ctx->gemm_variant) {
+    case 1: r = dispatch<GemmCfg<16, 4, true>>(ctx, kind, A, lda, B, ldb, C, ldc, alpha, beta, dvec, mirror, d_tasks, ntasks); break;
+    case 2: r = dispatch<GemmCfg<32, 3, false>>(ctx, kind, A, lda, B, ldb, C, ldc, alpha, beta, dvec, mirror, d_tasks, ntasks); break;
+    case 4: r = dispatch<GemmCfg<16, 4, false, 4>>(ctx, kind, A, lda, B, ldb, C, ldc, alpha, beta, dvec, mirror, d_tasks, ntasks); break;
+    case 5: r = dispatch<GemmCfg<32, 3, false, 4>>(ctx, kind, A, lda, B, ldb, C, ldc, alpha, beta, dvec, mirror, d_tasks, ntasks); break;
+    case 3: r = dispatch<GemmCfg<32, 3, true>>(ctx, kind, A, lda, B, ldb, C, ldc, alpha, beta, dvec, mirror, d_tasks, ntasks); break;
+    default: r = dispatch<GemmCfg<16, 4, false>>(ctx, kind, A, lda, B, ldb, C, ldc, alpha, beta, dvec, mirror, d_tasks, ntasks); break;
   }
   if (r != GPS_OK) return r;
   ctx->launches++;

@@ -53,6 +53,7 @@ DEBUG_SIGNATURES = {
     "gps_dbg_gemm": (C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _i64, _i64, _i64, C.c_double, C.c_double, _vp, C.c_int]),
     "gps_dbg_factor": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _vp]),
     "gps_dbg_fp64_peak": (C.c_int, [_vp, C.c_int, _dp, _dp]),
+    "gps_dbg_set_variant": (C.c_int, [_vp, C.c_int, C.c_int]),
     "gps_dbg_gram": (C.c_int, [_vp, _dp, _vp]),
 }
 
