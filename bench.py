@@ -183,6 +183,16 @@ def measure_fp64_peak(torch):
     return 2.0 * n ** 3 / (best * 1e-3) / 1e12
 
 
+def measured_hbm_peak():
+    """HBM copy bandwidth of this pool's B200s as measured by the driver (MEASURED_PEAKS.json),
+    else the profiling recipe's fallback."""
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    except Exception:
+        return 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -333,6 +343,48 @@ def run_ours(args):
         fitc["row_sharded_note"] = ("one evaluation split by rows over %d GPUs with 3 NCCL all-reduces; at N=10^4, "
                                     "M=20 it is launch/collective-latency bound, sharding pays at N=10^6" % world)
         cs.close()
+
+    # ---- FITC scaling-sweep point: N = 1e6 rows, M = 20 (BASELINE configs[4]) -----------------------------
+    N_BIG = 1000000
+    Xb, yb = synth.kin40k_like(N_BIG, seed=7)
+    hbm_peak, hbm_how = measured_hbm_peak()
+    cb = api.Context(local)
+    cb.set_stream(stream)
+    lo, hi = (N_BIG * rank) // world, (N_BIG * (rank + 1)) // world
+    if world == 1:
+        cb.set_data(torch.from_numpy(Xb).cuda(), torch.from_numpy(yb).cuda())
+        run_big = lambda: cb.fitc_eval(theta, U, "crps")
+    else:
+        cb.set_data(torch.from_numpy(Xb[lo:hi]).cuda(), torch.from_numpy(yb[lo:hi]).cuda())
+
+        def allreduce_b(t):
+            with torch.cuda.stream(stream):
+                dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            stream.synchronize()
+
+        th0 = synth.hyper_point("P1")
+        run_big = lambda: cb.fitc_eval_sharded(th0, U, "crps", N_BIG, allreduce_b)
+    for _ in range(3):
+        run_big()
+    barrier()
+    steps_b = max(args.steps * 4, 20)
+    e0.record(stream)
+    for _ in range(steps_b):
+        run_big()
+    e1.record(stream)
+    barrier()
+    ms_b = max_over_ranks(e0.elapsed_time(e1)) / steps_b
+    bytes_b = 3 * 8 * N_BIG * (D + 1)
+    fitc["sweep_N1e6_M20"] = {
+        "workload": "synthetic 8-D FITC N=1e6 M=20 LOO-CRPS obj+grad; rows sharded over %d GPU(s)%s" % (
+            world, "" if world == 1 else " with 3 NCCL all-reduces per evaluation"),
+        "evals_per_s": 1e3 / ms_b, "ms_per_eval": ms_b, "algorithmic_bytes_per_eval": bytes_b,
+        "roofline": {"bound": "hbm", "achieved": bytes_b / (ms_b * 1e-3) / 1e9 / world, "peak": hbm_peak, "unit": "GB/s",
+                     "frac": bytes_b / (ms_b * 1e-3) / 1e9 / world / hbm_peak, "peak_how": hbm_how,
+                     "note": "per-GPU algorithmic bytes (3 passes x 8 N (D+1)) over the whole-evaluation time; the row "
+                             "passes also do ~5.6 kflop/row of fp64 work, so this path sits on the HBM/ALU ridge"}}
+    cb.close()
+    del Xb, yb
 
     if rank == 0:
         # ---- CPU baseline (oracle port) on a bounded sample ------------------------------------------------

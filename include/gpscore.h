@@ -96,6 +96,15 @@ int gps_fitc_loo(gps_ctx* ctx, double* loo_mean, double* loo_var);
  * gps_fitc_eval / pass1+pass2 at the same theta, U (uses its L_A, L_C, beta). */
 int gps_fitc_predict(gps_ctx* ctx, const double* Xs, int64_t T, double* mean, double* var);
 
+/* ---- the scripts' optimiser loop in one call (replaces KF:237-260 / K20:219-251) ------------- */
+/* `iters` steps of fixed-step gradient descent, theta -= lr_theta * grad (and U -= lr_u * grad_U for
+ * FITC: the two learning rates of K20:326-327), without returning to the caller between steps.
+ * theta[D+2] and U[M*D] are host arrays updated in place; obj_trace (host, may be NULL) receives
+ * the objective before each step.  Stops early with GPS_ENOTPD if a factorisation fails. */
+int gps_full_descend(gps_ctx* ctx, double* theta, int score, double lr_theta, int iters, double* obj_trace);
+int gps_fitc_descend(gps_ctx* ctx, double* theta, double* U, int M, double jitter, int score, double lr_theta,
+                     double lr_u, int iters, double* obj_trace);
+
 /* ---- scoring of predictions (replaces KF:276-292: mse, SMSE KF:128-134, logs KF:52-57,
  *      crps KF:60-68, trivial_loss KF:110-119, coverage KF:288-292) ---------------------------- */
 /* mean, var, y: UVA length n.  ytrain_mean / ytrain_var: mean and UNBIASED variance of the

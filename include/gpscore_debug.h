@@ -26,7 +26,10 @@ int gps_dbg_factor(gps_ctx* ctx, const double* A, int64_t n, double* L, double* 
 int gps_dbg_fp64_peak(gps_ctx* ctx, int iters, double* dmma_tflops, double* dfma_tflops);
 
 /* Tuning knobs for A/B measurements: what = 0 selects the tile-GEMM policy
- * (0: BK16 x 4 stages, 1: + fragment double-buffering, 2: BK32 x 3 stages, 3: BK32 + double-buffering). */
+ * (0: BK16 x 4 stages, 1: + fragment double-buffering, 2: BK32 x 3 stages, 3: BK32 + double-buffering,
+ * 4: BK16 with 16 warps, 5: BK32 with 16 warps, 6: 64 x 128 CTA tile, 4 warps, two CTAs per SM = default,
+ * 7: 6 + double-buffering, 8: 6 with 64 x 32 warp tiles); what = 1 selects the diagonal-block kernel of
+ * POTRF (0: register-cyclic, 1: 32-blocked DMMA = default). */
 int gps_dbg_set_variant(gps_ctx* ctx, int what, int value);
 
 /* Training Gram K = ARD(X,X) + sn2 I of the current data set at theta, N x N (UVA out). */

@@ -119,6 +119,26 @@ class Context:
         self._check(self._lib.gps_full_eval(self._h, _dp(th), sc, _dp(obj), _dp(g) if grad else None))
         return float(obj[0]), (g if grad else None)
 
+    def full_descend(self, theta, score, lr, iters):
+        """`iters` steps of the scripts' fixed-step gradient descent (KF:237-260) in one call.
+        Returns (theta after the last step, objective before each step)."""
+        th = self._theta(theta).copy()
+        trace = np.zeros(int(iters))
+        sc = _L.SCORES[score] if isinstance(score, str) else int(score)
+        self._check(self._lib.gps_full_descend(self._h, _dp(th), sc, float(lr), int(iters), _dp(trace)))
+        return th, trace
+
+    def fitc_descend(self, theta, U, score, lr, lr_u, iters, jitter=JITTER):
+        """K20:219-251 in one call: theta -= lr * grad, inducing_x -= lr_u * grad (K20:326-327)."""
+        th = self._theta(theta).copy()
+        Uh = _host_vec(U).copy()
+        M = Uh.size // self.D
+        trace = np.zeros(int(iters))
+        sc = _L.SCORES[score] if isinstance(score, str) else int(score)
+        self._check(self._lib.gps_fitc_descend(self._h, _dp(th), _dp(Uh), M, float(jitter), sc, float(lr), float(lr_u),
+                                               int(iters), _dp(trace)))
+        return th, Uh.reshape(M, self.D), trace
+
     def full_loo(self):
         """mean_term, cov_term of KF:243-244 for the last crps/logs evaluation, as [N, 1] tensors."""
         m = torch.empty(self.N, dtype=torch.float64, device=self.device)

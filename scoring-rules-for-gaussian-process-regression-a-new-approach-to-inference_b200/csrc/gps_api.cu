@@ -271,6 +271,36 @@ int gps_full_eval(gps_ctx* ctx, const double* theta, int score, double* obj, dou
   return GPS_OK;
 }
 
+int gps_full_descend(gps_ctx* ctx, double* theta, int score, double lr_theta, int iters, double* obj_trace) {
+  if (!ctx) return GPS_EINVAL;
+  if (!theta || iters < 0) return gps_fail(ctx, GPS_EINVAL, "full_descend: bad arguments");
+  const int P = ctx->D + 2;
+  std::vector<double> g(P);
+  for (int it = 0; it < iters; ++it) {
+    double obj = 0.0;
+    GPS_CHECK(gps_full_eval(ctx, theta, score, &obj, g.data()));
+    if (obj_trace) obj_trace[it] = obj;
+    for (int k = 0; k < P; ++k) theta[k] -= lr_theta * g[k];   // KF:254-257
+  }
+  return GPS_OK;
+}
+
+int gps_fitc_descend(gps_ctx* ctx, double* theta, double* U, int M, double jitter, int score, double lr_theta,
+                     double lr_u, int iters, double* obj_trace) {
+  if (!ctx) return GPS_EINVAL;
+  if (!theta || !U || M <= 0 || iters < 0) return gps_fail(ctx, GPS_EINVAL, "fitc_descend: bad arguments");
+  const int P = ctx->D + 2, Q = M * ctx->D;
+  std::vector<double> g(P), gU(Q);
+  for (int it = 0; it < iters; ++it) {
+    double obj = 0.0;
+    GPS_CHECK(gps_fitc_eval(ctx, theta, U, M, jitter, score, &obj, g.data(), gU.data()));
+    if (obj_trace) obj_trace[it] = obj;
+    for (int k = 0; k < P; ++k) theta[k] -= lr_theta * g[k];   // K20:244-246
+    for (int k = 0; k < Q; ++k) U[k] -= lr_u * gU[k];          // K20:247 / K20:350
+  }
+  return GPS_OK;
+}
+
 int gps_full_loo(gps_ctx* ctx, double* loo_mean, double* loo_var) {
   if (!ctx) return GPS_EINVAL;
   if (!ctx->loo_valid) return gps_fail(ctx, GPS_ESTATE, "full_loo: no CRPS/LOGS evaluation to report");

@@ -144,6 +144,186 @@ potf2_inv_kernel(double* __restrict__ K, double* __restrict__ Xinv, int64_t ld, 
     }
 }
 
+// ---- diagonal-block kernel, second generation ------------------------------------------------------
+// Same contract as potf2_inv_kernel (L and L^-1 of one 128 x 128 diagonal block, one CTA), but
+// blocked by 32: the 32 x 32 diagonal sub-blocks are factored and inverted by ONE WARP with the
+// matrix rows in registers (pivot broadcast by shuffle: no block barrier on the serial chain), and
+// every 32 x 32 x 32 product — panel solve, trailing update, off-diagonal blocks of the inverse —
+// runs on DMMA from shared memory.  The lower 4 x 4 block triangle lives in shared memory as ten
+// [32][36] blocks (leading dimension 36: conflict-free m8n8k4 fragment loads).
+constexpr int SB = 32, SLD = 36, SBLK = SB * SLD;
+constexpr size_t POTF2V2_SMEM = (size_t)(10 + 10 + 3) * SBLK * sizeof(double) + 64 * sizeof(double);
+
+__device__ __forceinline__ void dmma4(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+__device__ __forceinline__ int blk_idx(int i, int j) { return i * (i + 1) / 2 + j; }
+
+// c[nf] += sgn * A[strip mf] * B'   (A, B blocks with k contiguous)
+__device__ __forceinline__ void strip_nt(const double* __restrict__ A, const double* __restrict__ B, int mf, int lane,
+                                         double sgn, double (&c)[4][2]) {
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int kk = 0; kk < 8; ++kk) {
+    const double a = sgn * A[(mf * 8 + g) * SLD + kk * 4 + t];
+#pragma unroll
+    for (int nf = 0; nf < 4; ++nf) dmma4(c[nf][0], c[nf][1], a, B[(nf * 8 + g) * SLD + kk * 4 + t]);
+  }
+}
+// c[nf] += sgn * A[strip mf] * B    (B block with rows = k, n contiguous)
+__device__ __forceinline__ void strip_nn(const double* __restrict__ A, const double* __restrict__ B, int mf, int lane,
+                                         double sgn, double (&c)[4][2]) {
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int kk = 0; kk < 8; ++kk) {
+    const double a = sgn * A[(mf * 8 + g) * SLD + kk * 4 + t];
+#pragma unroll
+    for (int nf = 0; nf < 4; ++nf) dmma4(c[nf][0], c[nf][1], a, B[(kk * 4 + t) * SLD + nf * 8 + g]);
+  }
+}
+__device__ __forceinline__ void strip_store(double* __restrict__ C, int mf, int lane, const double (&c)[4][2]) {
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int nf = 0; nf < 4; ++nf) {
+    C[(mf * 8 + g) * SLD + nf * 8 + 2 * t] = c[nf][0];
+    C[(mf * 8 + g) * SLD + nf * 8 + 2 * t + 1] = c[nf][1];
+  }
+}
+__device__ __forceinline__ void strip_load(const double* __restrict__ C, int mf, int lane, double (&c)[4][2]) {
+  const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int nf = 0; nf < 4; ++nf) {
+    c[nf][0] = C[(mf * 8 + g) * SLD + nf * 8 + 2 * t];
+    c[nf][1] = C[(mf * 8 + g) * SLD + nf * 8 + 2 * t + 1];
+  }
+}
+
+__global__ void __launch_bounds__(256, 1)
+potf2_inv_dmma_kernel(double* __restrict__ K, double* __restrict__ Xinv, int64_t ld, int blk, int* __restrict__ info) {
+  extern __shared__ __align__(16) double sm[];
+  double* Lb = sm;                    // 10 lower blocks of A -> L
+  double* Xb = Lb + 10 * SBLK;        // 10 lower blocks of L^-1
+  double* Tb = Xb + 10 * SBLK;        // 3 scratch blocks
+  double* Li = Tb + 3 * SBLK;         // [32] reciprocal diagonal of the current sub-block
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  double* Kd = K + (int64_t)blk * T * ld + (int64_t)blk * T;
+  double* Xd = Xinv + (int64_t)blk * T * ld + (int64_t)blk * T;
+
+  // load the lower block triangle (rows of 32 doubles, coalesced)
+  for (int e = tid; e < 10 * SB * SB; e += 256) {
+    const int b = e >> 10, r = (e >> 5) & 31, c = e & 31;
+    int bi = 0;
+    while ((bi + 1) * (bi + 2) / 2 <= b) ++bi;
+    const int bj = b - bi * (bi + 1) / 2;
+    Lb[b * SBLK + r * SLD + c] = Kd[(int64_t)(bi * SB + r) * ld + bj * SB + c];
+  }
+  __syncthreads();
+
+  for (int kb = 0; kb < 4; ++kb) {
+    double* D = Lb + blk_idx(kb, kb) * SBLK;
+    double* XD = Xb + blk_idx(kb, kb) * SBLK;
+    // (1) one warp: Cholesky of the 32 x 32 diagonal sub-block, rows in registers
+    if (warp == 0) {
+      double r[SB];
+#pragma unroll
+      for (int j = 0; j < SB; ++j) r[j] = D[lane * SLD + j];
+#pragma unroll
+      for (int j = 0; j < SB; ++j) {
+        double piv = __shfl_sync(0xffffffffu, r[j], j);
+        if (!(piv > 0.0)) {
+          if (lane == 0) atomicCAS(info, 0, blk * T + kb * SB + j + 1);
+          piv = 1.0;
+        }
+        const double lj = r[j] * rsqrt(piv);
+#pragma unroll
+        for (int c = j + 1; c < SB; ++c) {
+          const double lc = __shfl_sync(0xffffffffu, lj, c);
+          r[c] = fma(-lj, lc, r[c]);
+        }
+        r[j] = lj;
+      }
+#pragma unroll
+      for (int j = 0; j < SB; ++j) D[lane * SLD + j] = (j <= lane) ? r[j] : 0.0;
+      __syncwarp();
+      Li[lane] = 1.0 / D[lane * SLD + lane];
+      __syncwarp();
+      // inverse of the sub-block: lane c solves L x = e_c (column-oriented forward substitution)
+      double x[SB];
+#pragma unroll
+      for (int i = 0; i < SB; ++i) x[i] = (i == lane) ? 1.0 : 0.0;
+      const volatile double* Dv = D;
+#pragma unroll
+      for (int i = 0; i < SB; ++i) {
+        x[i] *= Li[i];
+#pragma unroll
+        for (int k2 = i + 1; k2 < SB; ++k2) x[k2] = fma(-Dv[k2 * SLD + i], x[i], x[k2]);
+      }
+#pragma unroll
+      for (int i = 0; i < SB; ++i) XD[i * SLD + lane] = (i >= lane) ? x[i] : 0.0;
+    }
+    __syncthreads();
+    // (2) panel: L(i,kb) = A(i,kb) * inv(L_D)'   — strips of 8 rows, in place
+    const int nbelow = 3 - kb;
+    for (int item = warp; item < nbelow * 4; item += 8) {
+      const int i = kb + 1 + item / 4, mf = item & 3;
+      double* P = Lb + blk_idx(i, kb) * SBLK;
+      double c[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
+      strip_nt(P, XD, mf, lane, 1.0, c);
+      __syncwarp();
+      strip_store(P, mf, lane, c);
+    }
+    __syncthreads();
+    // (3) trailing update inside the 128 block: A(i,j) -= L(i,kb) L(j,kb)'
+    const int ntr = nbelow * (nbelow + 1) / 2;
+    for (int item = warp; item < ntr * 4; item += 8) {
+      const int bidx = item / 4, mf = item & 3;
+      int ii = 0;
+      while ((ii + 1) * (ii + 2) / 2 <= bidx) ++ii;
+      const int jj = bidx - ii * (ii + 1) / 2;
+      const int i = kb + 1 + ii, j = kb + 1 + jj;
+      double* Cb = Lb + blk_idx(i, j) * SBLK;
+      double c[4][2];
+      strip_load(Cb, mf, lane, c);
+      strip_nt(Lb + blk_idx(i, kb) * SBLK, Lb + blk_idx(j, kb) * SBLK, mf, lane, -1.0, c);
+      strip_store(Cb, mf, lane, c);
+    }
+    __syncthreads();
+  }
+  // (4) off-diagonal blocks of X = L^-1 by block diagonals: X(i,j) = -X(i,i) sum_k L(i,k) X(k,j)
+  for (int d = 1; d < 4; ++d) {
+    const int nblk = 4 - d;
+    for (int item = warp; item < nblk * 4; item += 8) {
+      const int i = d + item / 4, j = i - d, mf = item & 3;
+      double c[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
+      for (int k2 = j; k2 < i; ++k2) strip_nn(Lb + blk_idx(i, k2) * SBLK, Xb + blk_idx(k2, j) * SBLK, mf, lane, 1.0, c);
+      strip_store(Tb + (i - d) * SBLK, mf, lane, c);
+    }
+    __syncthreads();
+    for (int item = warp; item < nblk * 4; item += 8) {
+      const int i = d + item / 4, j = i - d, mf = item & 3;
+      double c[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
+      strip_nn(Xb + blk_idx(i, i) * SBLK, Tb + (i - d) * SBLK, mf, lane, -1.0, c);
+      strip_store(Xb + blk_idx(i, j) * SBLK, mf, lane, c);
+    }
+    __syncthreads();
+  }
+  // write back: full 128 x 128 tiles of L and L^-1 with explicit zeros above the diagonal
+  for (int e = tid; e < T * T; e += 256) {
+    const int r = e >> 7, c = e & 127;
+    const int bi = r >> 5, bj = c >> 5;
+    double lv = 0.0, xv = 0.0;
+    if (bj <= bi) {
+      const int o = blk_idx(bi, bj) * SBLK + (r & 31) * SLD + (c & 31);
+      lv = Lb[o];
+      xv = Xb[o];
+    }
+    Kd[(int64_t)r * ld + c] = lv;
+    Xd[(int64_t)r * ld + c] = xv;
+  }
+}
+
 struct Node { int lo, mid, hi, depth; };
 
 void collect(int lo, int hi, int depth, std::vector<Node>& out) {
@@ -254,6 +434,8 @@ int gps_potrf(gps_ctx* ctx, double* K, double* Xinv, int64_t Np) {
   if (!configured) {
     GPS_CUDA(cudaFuncSetAttribute(potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)POTF2_SMEM));
+    GPS_CUDA(cudaFuncSetAttribute(potf2_inv_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)POTF2V2_SMEM));
     configured = true;
   }
   if (!ctx->panel_stream) {
@@ -278,7 +460,10 @@ int gps_potrf(gps_ctx* ctx, double* K, double* Xinv, int64_t Np) {
     GPS_CUDA(cudaStreamWaitEvent(s_pan, ctx->potrf_events[2 * o], 0));
     ctx->stream = s_pan;
     for (int k = c0; k < c1 && rc == GPS_OK; ++k) {
-      potf2_inv_kernel<<<1, 256, POTF2_SMEM, s_pan>>>(K, Xinv, Np, k, ctx->d_info);
+      if (ctx->potf2_variant == 0)
+        potf2_inv_kernel<<<1, 256, POTF2_SMEM, s_pan>>>(K, Xinv, Np, k, ctx->d_info);
+      else
+        potf2_inv_dmma_kernel<<<1, 256, POTF2V2_SMEM, s_pan>>>(K, Xinv, Np, k, ctx->d_info);
       if (cudaGetLastError() != cudaSuccess) rc = gps_fail(ctx, GPS_ECUDA, "potf2 launch failed");
       ctx->launches++;
       // panel: L_ik = A_ik * inv(L_kk)'

@@ -33,7 +33,8 @@ struct gps_ctx {
   std::string err;
   int64_t launches = 0;
   int sm_count = 148;
-  int gemm_variant = 5;               // tile-GEMM policy (see gps_gemm.cu); switched by gps_dbg_set_variant
+  int potf2_variant = 1;              // 0: register-cyclic diagonal kernel, 1: 32-blocked DMMA diagonal kernel
+  int gemm_variant = 6;               // tile-GEMM policy (see gps_gemm.cu); switched by gps_dbg_set_variant
   // GEMM timing of the last full eval
   bool time_gemm = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> gemm_events;

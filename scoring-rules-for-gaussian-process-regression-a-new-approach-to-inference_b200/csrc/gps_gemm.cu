@@ -9,31 +9,38 @@
 // Block-level triangular structure lives in the task's k-range; diagonal blocks of triangular
 // operands hold explicit zeros, so the kernel itself is a plain dense tile GEMM.
 //
-// Tile: 128 x 128 x 16, 256 threads = 8 warps as 2 (m) x 4 (n), warp tile 64 x 32 =
-// 8 x 4 m8n8k4 fragments (64 fp64 accumulators per thread).  Operands are staged with
-// 16-byte cp.async into a 4-deep ring of padded shared-memory tiles whose leading dimensions
-// (20 / 132 doubles) make every half-warp fragment load hit 16 distinct 8-byte bank pairs.
+// A CTA computes a TM x 128 slice of a task (TM = 128 or 64) with WM x WN warps; each warp owns
+// MF x NF m8n8k4 fragments.  Operands are staged with 16-byte cp.async into a ring of padded
+// shared-memory tiles whose leading dimensions (BK + 4, rows + 4 doubles) make every half-warp
+// fragment load hit 16 distinct 8-byte bank pairs.  The tile policy is a template parameter
+// (GemmCfg); the policies that were measured against each other are kept selectable
+// (gps_dbg_set_variant) and the numbers are in profiles/.
 //
 // tcgen05 has no f64 kind, so on B200 the FP64 tensor path IS mma.sync DMMA.
 #include "gps_common.cuh"
 
 namespace {
 
-constexpr int LD_MC = 132;    // [BK][132]
-
-// Tile-shape policy: BK = k-depth of one pipeline stage, STAGES = ring depth, PIPE = explicit
-// register double-buffering of the m8n8k4 fragments across k4-steps.
-template <int BK_, int STAGES_, bool PIPE_, int WM_ = 2>
+// Tile policy.  A task is always a 128 x 128 output tile; a CTA computes a TM x 128 slice of it
+// (TM = 128: one CTA per task, TM = 64: two).  BK = k-depth of a pipeline stage, STAGES = ring
+// depth, WM x WN = warp grid, PIPE = explicit register double-buffering of the fragments,
+// MINB = CTAs per SM the register budget is sized for.
+template <int TM_, int BK_, int STAGES_, int WM_, int WN_, bool PIPE_, int MINB_>
 struct GemmCfg {
+  static constexpr int TM = TM_, TN = 128;
   static constexpr int BK = BK_;
   static constexpr int STAGES = STAGES_;
   static constexpr bool PIPE = PIPE_;
-  static constexpr int WM = WM_, WN = 4;                   // warp grid: WM x 4 warps
-  static constexpr int THREADS = 32 * WM_ * 4;
-  static constexpr int MF = 128 / WM_ / 8, NF = 4;         // m8n8k4 fragments per warp tile
-  static constexpr int LD_KC = BK_ + 4;                    // [128][BK+4]: (BK+4) % 16 == 4
-  static constexpr int OPER = 128 * LD_KC;                 // doubles per operand per stage (>= BK*132)
-  static constexpr size_t SMEM = (size_t)STAGES_ * 2 * OPER * sizeof(double);
+  static constexpr int WM = WM_, WN = WN_, MINB = MINB_;
+  static constexpr int THREADS = 32 * WM_ * WN_;
+  static constexpr int MF = TM_ / WM_ / 8, NF = 128 / WN_ / 8;   // m8n8k4 fragments per warp tile
+  static constexpr int SPLIT = 128 / TM_;
+  static constexpr int LD_KC = BK_ + 4;                          // [rows][BK+4]: (BK+4) % 16 == 4
+  static constexpr int LD_MC_A = TM_ + 4, LD_MC_B = 128 + 4;     // [BK][rows+4]: (rows+4) % 16 == 4
+  static constexpr int OPER_A = (TM_ * LD_KC > BK_ * LD_MC_A) ? TM_ * LD_KC : BK_ * LD_MC_A;
+  static constexpr int OPER_B = (128 * LD_KC > BK_ * LD_MC_B) ? 128 * LD_KC : BK_ * LD_MC_B;
+  static constexpr int STAGE = OPER_A + OPER_B;                  // doubles per stage
+  static constexpr size_t SMEM = (size_t)STAGES_ * STAGE * sizeof(double);
 };
 
 __device__ __forceinline__ void cp_async16(double* smem, const double* gmem) {
@@ -52,12 +59,13 @@ __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, do
                : "d"(a), "d"(b));
 }
 
-// stage one 128 x BK operand panel. KC: rows are matrix rows, k contiguous in memory.
-// MC: the panel is read from a [k][m] matrix (m contiguous in memory).
-template <class Cfg, bool MC>
+// stage one ROWS x BK operand panel.  KC: rows are matrix rows, k contiguous in memory.
+// MC: the panel is read from a [k][rows] matrix (rows contiguous in memory).
+template <class Cfg, int ROWS, bool MC>
 __device__ __forceinline__ void load_panel(double* s, const double* __restrict__ g, int64_t ld, int row0,
                                            int k, int tid) {
-  constexpr int CHUNKS = 128 * Cfg::BK / 2;     // 16-byte chunks per panel
+  constexpr int CHUNKS = ROWS * Cfg::BK / 2;     // 16-byte chunks per panel
+  constexpr int LDM = ROWS + 4;
 #pragma unroll
   for (int i = 0; i < CHUNKS / Cfg::THREADS; ++i) {
     const int c = tid + i * Cfg::THREADS;
@@ -66,29 +74,35 @@ __device__ __forceinline__ void load_panel(double* s, const double* __restrict__
       const int r = c / CPR, kc = c % CPR;
       cp_async16(s + r * Cfg::LD_KC + kc * 2, g + (int64_t)(row0 + r) * ld + k + kc * 2);
     } else {
-      const int kr = c >> 6, mc = c & 63;
-      cp_async16(s + kr * LD_MC + mc * 2, g + (int64_t)(k + kr) * ld + row0 + mc * 2);
+      constexpr int CPK = ROWS / 2;             // chunks per k-row
+      const int kr = c / CPK, mc = c % CPK;
+      cp_async16(s + kr * LDM + mc * 2, g + (int64_t)(k + kr) * ld + row0 + mc * 2);
     }
   }
 }
 
-template <class Cfg, bool MC>
+template <class Cfg, int ROWS, bool MC>
 __device__ __forceinline__ double frag(const double* s, int row, int k) {
-  return MC ? s[k * LD_MC + row] : s[row * Cfg::LD_KC + k];
+  return MC ? s[k * (ROWS + 4) + row] : s[row * Cfg::LD_KC + k];
 }
 
 template <class Cfg, bool A_MC, bool B_MC, bool DVEC, bool MIRROR>
-__global__ void __launch_bounds__(Cfg::THREADS, 1)
+__global__ void __launch_bounds__(Cfg::THREADS, Cfg::MINB)
 gemm_tile_kernel(const double* __restrict__ A, int64_t lda, const double* __restrict__ B, int64_t ldb,
                  double* __restrict__ C, int64_t ldc, double alpha, double beta,
                  const double* __restrict__ dvec, const GemmTask* __restrict__ tasks) {
   extern __shared__ __align__(16) double smem[];
-  constexpr int BK = Cfg::BK, STAGES = Cfg::STAGES, OPER = Cfg::OPER, KSTEPS = Cfg::BK / 4;
-  constexpr int MF = Cfg::MF, NF = Cfg::NF, WROWS = 8 * Cfg::MF;
-  const GemmTask t = tasks[blockIdx.x];
+  constexpr int BK = Cfg::BK, STAGES = Cfg::STAGES, KSTEPS = Cfg::BK / 4, TM = Cfg::TM;
+  constexpr int MF = Cfg::MF, NF = Cfg::NF, WROWS = 8 * Cfg::MF, WCOLS = 8 * Cfg::NF;
+  constexpr int STAGE = Cfg::STAGE, OPER_A = Cfg::OPER_A;
+  GemmTask t = tasks[blockIdx.x / Cfg::SPLIT];
+  const bool diag_tile = t.c_row == t.c_col;
+  const int half = (int)(blockIdx.x % Cfg::SPLIT) * TM;
+  t.a_row += half;
+  t.c_row += half;
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
-  const int wm = warp >> 2, wn = warp & 3;   // WM x 4 warps
+  const int wm = warp / Cfg::WN, wn = warp % Cfg::WN;
   const int g = lane >> 2, tq = lane & 3;
   const int nk = (t.k1 - t.k0) / BK;
 
@@ -101,8 +115,8 @@ gemm_tile_kernel(const double* __restrict__ A, int64_t lda, const double* __rest
 #pragma unroll
   for (int s = 0; s < STAGES - 1; ++s) {
     if (s < nk) {
-      load_panel<Cfg, A_MC>(smem + (size_t)s * 2 * OPER, A, lda, t.a_row, t.k0 + s * BK, tid);
-      load_panel<Cfg, B_MC>(smem + (size_t)s * 2 * OPER + OPER, B, ldb, t.b_row, t.k0 + s * BK, tid);
+      load_panel<Cfg, TM, A_MC>(smem + (size_t)s * STAGE, A, lda, t.a_row, t.k0 + s * BK, tid);
+      load_panel<Cfg, 128, B_MC>(smem + (size_t)s * STAGE + OPER_A, B, ldb, t.b_row, t.k0 + s * BK, tid);
     }
     cp_async_commit();
   }
@@ -113,34 +127,34 @@ gemm_tile_kernel(const double* __restrict__ A, int64_t lda, const double* __rest
     {
       const int nx = kb + STAGES - 1;
       if (nx < nk) {
-        double* sl = smem + (size_t)(nx % STAGES) * 2 * OPER;
-        load_panel<Cfg, A_MC>(sl, A, lda, t.a_row, t.k0 + nx * BK, tid);
-        load_panel<Cfg, B_MC>(sl + OPER, B, ldb, t.b_row, t.k0 + nx * BK, tid);
+        double* sl = smem + (size_t)(nx % STAGES) * STAGE;
+        load_panel<Cfg, TM, A_MC>(sl, A, lda, t.a_row, t.k0 + nx * BK, tid);
+        load_panel<Cfg, 128, B_MC>(sl + OPER_A, B, ldb, t.b_row, t.k0 + nx * BK, tid);
       }
       cp_async_commit();
     }
-    const double* As = smem + (size_t)(kb % STAGES) * 2 * OPER;
-    const double* Bs = As + OPER;
+    const double* As = smem + (size_t)(kb % STAGES) * STAGE;
+    const double* Bs = As + OPER_A;
     if (Cfg::PIPE) {
       double a[2][MF], b[2][NF];
 #pragma unroll
-      for (int i = 0; i < MF; ++i) a[0][i] = frag<Cfg, A_MC>(As, wm * WROWS + i * 8 + g, tq);
+      for (int i = 0; i < MF; ++i) a[0][i] = frag<Cfg, TM, A_MC>(As, wm * WROWS + i * 8 + g, tq);
 #pragma unroll
-      for (int j = 0; j < 4; ++j) b[0][j] = frag<Cfg, B_MC>(Bs, wn * 32 + j * 8 + g, tq);
+      for (int j = 0; j < NF; ++j) b[0][j] = frag<Cfg, 128, B_MC>(Bs, wn * WCOLS + j * 8 + g, tq);
 #pragma unroll
       for (int kk = 0; kk < KSTEPS; ++kk) {
         const int cur = kk & 1, nxt = cur ^ 1;
         if (kk + 1 < KSTEPS) {
           const int k = (kk + 1) * 4 + tq;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) b[nxt][j] = frag<Cfg, B_MC>(Bs, wn * 32 + j * 8 + g, k);
+          for (int j = 0; j < NF; ++j) b[nxt][j] = frag<Cfg, 128, B_MC>(Bs, wn * WCOLS + j * 8 + g, k);
 #pragma unroll
-          for (int i = 0; i < MF; ++i) a[nxt][i] = frag<Cfg, A_MC>(As, wm * WROWS + i * 8 + g, k);
+          for (int i = 0; i < MF; ++i) a[nxt][i] = frag<Cfg, TM, A_MC>(As, wm * WROWS + i * 8 + g, k);
         }
         if (DVEC) {
           const double dv = __ldg(dvec + t.k0 + kb * BK + kk * 4 + tq);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) b[cur][j] *= dv;
+          for (int i = 0; i < MF; ++i) a[cur][i] *= dv;
         }
 #pragma unroll
         for (int i = 0; i < MF; ++i)
@@ -153,13 +167,18 @@ gemm_tile_kernel(const double* __restrict__ A, int64_t lda, const double* __rest
         const int k = kk * 4 + tq;
         double a[MF], b[NF];
 #pragma unroll
-        for (int i = 0; i < MF; ++i) a[i] = frag<Cfg, A_MC>(As, wm * WROWS + i * 8 + g, k);
+        for (int i = 0; i < MF; ++i) a[i] = frag<Cfg, TM, A_MC>(As, wm * WROWS + i * 8 + g, k);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) b[j] = frag<Cfg, B_MC>(Bs, wn * 32 + j * 8 + g, k);
+        for (int j = 0; j < NF; ++j) b[j] = frag<Cfg, 128, B_MC>(Bs, wn * WCOLS + j * 8 + g, k);
         if (DVEC) {
           const double dv = __ldg(dvec + t.k0 + kb * BK + k);
+          if (MF <= NF) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) b[j] *= dv;
+            for (int i = 0; i < MF; ++i) a[i] *= dv;
+          } else {
+#pragma unroll
+            for (int j = 0; j < NF; ++j) b[j] *= dv;
+          }
         }
 #pragma unroll
         for (int i = 0; i < MF; ++i)
@@ -176,7 +195,7 @@ gemm_tile_kernel(const double* __restrict__ A, int64_t lda, const double* __rest
     const int row = t.c_row + wm * WROWS + i * 8 + g;
 #pragma unroll
     for (int j = 0; j < NF; ++j) {
-      const int col = t.c_col + wn * 32 + j * 8 + 2 * tq;
+      const int col = t.c_col + wn * WCOLS + j * 8 + 2 * tq;
       double2* p = reinterpret_cast<double2*>(C + (int64_t)row * ldc + col);
       double2 v;
       v.x = alpha * acc[i][j][0];
@@ -187,7 +206,7 @@ gemm_tile_kernel(const double* __restrict__ A, int64_t lda, const double* __rest
         v.y += beta * o.y;
       }
       *p = v;
-      if (MIRROR && t.c_row != t.c_col) {
+      if (MIRROR && !diag_tile) {
         C[(int64_t)col * ldc + row] = v.x;
         C[(int64_t)(col + 1) * ldc + row] = v.y;
       }
@@ -204,7 +223,7 @@ int launch(gps_ctx* ctx, const double* A, int64_t lda, const double* B, int64_t 
     GPS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
     configured = true;
   }
-  kern<<<(unsigned)ntasks, Cfg::THREADS, Cfg::SMEM, ctx->stream>>>(A, lda, B, ldb, C, ldc, alpha, beta, dvec,
+  kern<<<(unsigned)(ntasks * Cfg::SPLIT), Cfg::THREADS, Cfg::SMEM, ctx->stream>>>(A, lda, B, ldb, C, ldc, alpha, beta, dvec,
                                                                   tasks);
   GPS_LAUNCH_CHECK();
   return GPS_OK;
@@ -247,14 +266,17 @@ int gps_gemm_tasks(gps_ctx* ctx, int kind, const double* A, int64_t lda, const d
     GPS_CUDA(cudaEventRecord(e0, ctx->stream));
   }
   int r;
-  switch (ctx->gemm_variant) {
-    case 1: r = dispatch<GemmCfg<16, 4, true>>(ctx, kind, A, lda, B, ldb, C, ldc, alpha, beta, dvec, mirror, d_tasks, ntasks); break;
-    case 2: r = dispatch<GemmCfg<32, 3, false>>(ctx, kind, A, lda, B, ldb, C, ldc, alpha, beta, dvec, mirror, d_tasks, ntasks); break;
-    case 4: r = dispatch<GemmCfg<16, 4, false, 4>>(ctx, kind, A, lda, B, ldb, C, ldc, alpha, beta, dvec, mirror, d_tasks, ntasks); break;
-    case 5: r = dispatch<GemmCfg<32, 3, false, 4>>(ctx, kind, A, lda, B, ldb, C, ldc, alpha, beta, dvec, mirror, d_tasks, ntasks); break;
-    case 3: r = dispatch<GemmCfg<32, 3, true>>(ctx, kind, A, lda, B, ldb, C, ldc, alpha, beta, dvec, mirror, d_tasks, ntasks); break;
-    default: r = dispatch<GemmCfg<16, 4, false>>(ctx, kind, A, lda, B, ldb, C, ldc, alpha, beta, dvec, mirror, d_tasks, ntasks); break;
+#define GPS_GEMM_ARGS ctx, kind, A, lda, B, ldb, C, ldc, alpha, beta, dvec, mirror, d_tasks, ntasks
+  switch (ctx->gemm_variant) {            //            TM  BK  ST WM WN PIPE  MINB
+    case 0: r = dispatch<GemmCfg<128, 16, 4, 2, 4, false, 1>>(GPS_GEMM_ARGS); break;
+    case 2: r = dispatch<GemmCfg<128, 32, 3, 2, 4, false, 1>>(GPS_GEMM_ARGS); break;
+    case 4: r = dispatch<GemmCfg<128, 16, 4, 4, 4, false, 1>>(GPS_GEMM_ARGS); break;
+    case 7: r = dispatch<GemmCfg<64, 16, 3, 2, 2, true, 2>>(GPS_GEMM_ARGS); break;
+    case 8: r = dispatch<GemmCfg<64, 16, 3, 1, 4, false, 2>>(GPS_GEMM_ARGS); break;   // 64 x 32 warp tiles
+    case 5: r = dispatch<GemmCfg<128, 32, 3, 4, 4, false, 1>>(GPS_GEMM_ARGS); break;
+    default: r = dispatch<GemmCfg<64, 16, 3, 2, 2, false, 2>>(GPS_GEMM_ARGS); break;   // 6: two 4-warp CTAs per SM
   }
+#undef GPS_GEMM_ARGS
   if (r != GPS_OK) return r;
   ctx->launches++;
   if (ctx->time_gemm) GPS_CUDA(cudaEventRecord(e1, ctx->stream));

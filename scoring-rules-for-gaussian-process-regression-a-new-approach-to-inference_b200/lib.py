@@ -41,6 +41,8 @@ SIGNATURES = {
     "gps_fitc_finish": (C.c_int, [_vp, _vp, _vp, _dp, _dp, _dp]),
     "gps_fitc_loo": (C.c_int, [_vp, _vp, _vp]),
     "gps_fitc_predict": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
+    "gps_full_descend": (C.c_int, [_vp, _dp, C.c_int, C.c_double, C.c_int, _dp]),
+    "gps_fitc_descend": (C.c_int, [_vp, _dp, _dp, C.c_int, C.c_double, C.c_int, C.c_double, C.c_double, C.c_int, _dp]),
     "gps_test_metrics": (C.c_int, [_vp, _vp, _vp, _vp, _i64, C.c_double, C.c_double, _dp]),
     "gps_ard": (C.c_int, [_vp, _vp, _i64, _vp, _i64, C.c_int, C.c_double, _dp, C.c_int, _vp]),
     "gps_chol_solve": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _vp]),

@@ -147,3 +147,27 @@ def test_reference_named_helpers(ctx):
     assert abs(float(api.logs(_dev(m), _dev(v), _dev(yy))) - O.logs(m, v, yy)) <= 1e-13
     assert abs(float(api.SMSE(_dev(m), _dev(yy), _dev(y))) - O.SMSE(m, yy, y)) <= 1e-13
     assert abs(float(api.trivial_loss(_dev(m), _dev(v), _dev(yy), _dev(y))) - O.trivial_loss(m, v, yy, y)) <= 1e-12
+
+
+def test_descend_equals_python_loop(ctx):
+    """gps_full_descend / gps_fitc_descend (the scripts' optimiser loop in one C-ABI call) give the
+    same trajectory as stepping from Python."""
+    from gpscore_b200 import synth
+    X, y = synth.kin40k_like(400, seed=8)
+    ctx.set_data(_dev(X), _dev(y))
+    theta = synth.hyper_point("P1")
+    th, trace = ctx.full_descend(theta, "crps", 1.0, 6)
+    ref = theta.copy()
+    for i in range(6):
+        v, g = ctx.full_eval(ref, "crps")
+        assert abs(v - trace[i]) <= 1e-12 * abs(v)
+        ref = ref - 1.0 * g
+    assert relerr(th, ref) <= 1e-12
+    U = synth.inducing_init(20)
+    th, Uo, trace = ctx.fitc_descend(theta, U, "logs", 0.2, 0.1, 5)
+    ref, Ur = theta.copy(), U.copy()
+    for i in range(5):
+        v, g, gU = ctx.fitc_eval(ref, Ur, "logs")
+        assert abs(v - trace[i]) <= 1e-12 * abs(v)
+        ref, Ur = ref - 0.2 * g, Ur - 0.1 * gU
+    assert relerr(th, ref) <= 1e-12 and relerr(Uo, Ur) <= 1e-12

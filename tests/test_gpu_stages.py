@@ -23,9 +23,19 @@ def _dev(a):
     return torch.from_numpy(np.ascontiguousarray(a)).cuda()
 
 
+@pytest.fixture
+def restore_variants(ctx):
+    yield
+    ctx._check(ctx._lib.gps_dbg_set_variant(ctx._h, 0, 6))
+    ctx._check(ctx._lib.gps_dbg_set_variant(ctx._h, 1, 1))
+
+
+@pytest.mark.parametrize("variant", [0, 2, 4, 5, 6, 7, 8])
 @pytest.mark.parametrize("kind", [0, 1, 2])
 @pytest.mark.parametrize("shape", [(128, 128, 128), (256, 384, 512)])
-def test_tile_gemm(ctx, kind, shape):
+def test_tile_gemm(ctx, restore_variants, kind, shape, variant):
+    """every tile policy (CTA tile, stage depth, warp grid) gives the same product"""
+    ctx._check(ctx._lib.gps_dbg_set_variant(ctx._h, 0, variant))
     Mp, Np, Kp = shape
     rng = np.random.default_rng(kind * 10 + Mp)
     A = rng.standard_normal((Mp, Kp))
@@ -40,7 +50,9 @@ def test_tile_gemm(ctx, kind, shape):
     assert relerr(Cd.cpu().numpy(), ref) < 1e-13
 
 
-def test_tile_gemm_dvec_and_mirror(ctx):
+@pytest.mark.parametrize("variant", [0, 5, 6, 8])
+def test_tile_gemm_dvec_and_mirror(ctx, restore_variants, variant):
+    ctx._check(ctx._lib.gps_dbg_set_variant(ctx._h, 0, variant))
     n = 384
     rng = np.random.default_rng(3)
     A = rng.standard_normal((n, n))
@@ -55,8 +67,11 @@ def test_tile_gemm_dvec_and_mirror(ctx):
     assert relerr(Cd.cpu().numpy(), A.T @ A) < 1e-13   # lower tiles computed, upper tiles mirrored
 
 
+@pytest.mark.parametrize("diag_kernel", [0, 1])
 @pytest.mark.parametrize("n", [1, 50, 128, 129, 300, 640, 1000])
-def test_factor_inverse(ctx, n):
+def test_factor_inverse(ctx, restore_variants, n, diag_kernel):
+    """both diagonal-block kernels (register-cyclic, 32-blocked DMMA) through POTRF/TRTRI/LAUUM"""
+    ctx._check(ctx._lib.gps_dbg_set_variant(ctx._h, 1, diag_kernel))
     rng = np.random.default_rng(n)
     G = rng.standard_normal((n, n + 5))
     A = G @ G.T / n + 0.5 * np.eye(n)

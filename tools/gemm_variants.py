@@ -19,7 +19,7 @@ Cd = torch.zeros(n, n, dtype=torch.float64, device="cuda")
 ref = None
 X, y = synth.kin40k_like(10000)
 theta = synth.hyper_point("P1")
-variants = [int(v) for v in sys.argv[1:]] or [0, 1, 2, 3]
+variants = [int(v) for v in sys.argv[1:]] or [5, 6, 7, 8]
 for v in variants:
     ctx._check(ctx._lib.gps_dbg_set_variant(ctx._h, 0, v))
     for kind in (0, 1, 2):
@@ -49,5 +49,17 @@ for v in variants:
         ctx.full_eval(theta, "nlml")
         ts.append(time.perf_counter() - t0)
     out["v%d_nlml_eval_ms" % v] = min(ts) * 1e3
+# diagonal-block kernel A/B at the default GEMM policy
+for pv in (0, 1):
+    ctx._check(ctx._lib.gps_dbg_set_variant(ctx._h, 0, variants[0]))
+    ctx._check(ctx._lib.gps_dbg_set_variant(ctx._h, 1, pv))
+    ctx.full_eval(theta, "crps")
+    ts = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        val, g = ctx.full_eval(theta, "crps")
+        ts.append(time.perf_counter() - t0)
+    out["potf2v%d_full_eval_ms" % pv] = min(ts) * 1e3
+    out["potf2v%d_obj" % pv] = val
 print(json.dumps(out, indent=1))
 json.dump(out, open(os.path.join(ROOT, "gpurun_out", "gemm_variants.json"), "w"), indent=1)
