@@ -283,18 +283,37 @@ def run_ours(args):
         g, gl = ctx.last_gemm_ms()
         gms.append(g)
     ctx.set_gemm_timing(False)
+    ctx.full_eval(theta, "crps")
+    stages = ctx.last_stage_ms()
     gemm_ms = min(gms)
     flops = 2.0 * float(N_FULL) ** 3
     roofline = None
     fitc = None
     cpu_baseline = None
     if rank == 0:
+        traffic, traffic_how = None, None
+        try:   # DRAM bytes of the tile-GEMM launches of one evaluation, from the committed ncu launch list
+            with open(os.path.join(ROOT, "profiles", "r01_launch_summary_N10000_v6.json")) as fh:
+                traffic = float(json.load(fh)["gemm_dram_bytes_per_eval"])
+                traffic_how = ("dram__bytes_read.sum + dram__bytes_write.sum summed over the tile-GEMM launches of one "
+                               "evaluation, ncu launch list profiles/r01_launches_N10000_v6.csv (bytes per step, like "
+                               "achieved); the kernel is tensor-bound: DRAM runs at ~6% of peak")
+        except Exception:
+            pass
         peak = measure_fp64_peak(torch)
         ach = flops / (gemm_ms * 1e-3) / 1e12
         roofline = {"bound": "tensor", "kernel": "gemm_tile_kernel (FP64 DMMA m8n8k4, sm_100a)", "achieved": ach,
-                    "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                    "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic, "traffic_how": traffic_how,
                     "launches_per_step": gl, "avg_launch_ms": gemm_ms / max(gl, 1),
-                    "algorithmic_flops_per_step": flops, "kernel_share_of_step": gemm_ms / ms_per_step,
+                    "algorithmic_flops_per_step": flops, "kernel_share_of_step": min(1.0, gemm_ms / ms_per_step),
+                    "share_note": "sum of per-launch CUDA-event durations / step time; launches on the POTRF look-ahead "
+                                  "stream overlap the main stream, so the raw sum can exceed the step (raw %.3f)" % (
+                                      gemm_ms / ms_per_step),
+                    "stages_ms": stages,
+                    "stage_tflops": {"potrf": N_FULL ** 3 / 3.0 / (stages["potrf"] * 1e-3) / 1e12,
+                                     "trtri": N_FULL ** 3 / 3.0 / (stages["trtri"] * 1e-3) / 1e12,
+                                     "lauum": N_FULL ** 3 / 3.0 / (stages["lauum"] * 1e-3) / 1e12,
+                                     "symprod": float(N_FULL) ** 3 / (stages["symprod"] * 1e-3) / 1e12},
                     "peak_how": "cuBLAS DGEMM 6144^3 (torch.matmul fp64), best of 5, CUDA events, measured in "
                                 "this run — MEASURED_PEAKS.json has no fp64 figure"}
     barrier()

@@ -58,6 +58,10 @@ int gps_set_gemm_timing(gps_ctx* ctx, int on);
 /* device milliseconds the dominant dense kernels (DMMA tile GEMM) spent inside the last
  * gps_full_eval, measured with CUDA events on the context's stream, and their launch count */
 int gps_last_gemm_ms(gps_ctx* ctx, double* ms, int64_t* launches);
+/* device milliseconds of the seven stages of the last CRPS / LOGS objective+gradient evaluation,
+ * from CUDA events on the context's stream: ms7 = {Gram, POTRF, TRTRI, LAUUM, alpha+scores+u,
+ * K^-1 diag(dbar) K^-1, gradient contraction} */
+int gps_last_stage_ms(gps_ctx* ctx, double* ms7);
 
 /* ---- training data (replaces train_x / train_y of KF:208-209, K20:198-199) ----------------- */
 /* X[N,D], y[N] row-major UVA pointers; copied into context-owned, tile-padded buffers and all

@@ -288,6 +288,12 @@ class Context:
     def launch_count(self):
         return int(self._lib.gps_launch_count(self._h))
 
+    def last_stage_ms(self):
+        """Device time per stage of the last CRPS/LOGS obj+grad evaluation (CUDA events)."""
+        ms = np.zeros(7)
+        self._check(self._lib.gps_last_stage_ms(self._h, _dp(ms)))
+        return dict(zip(("gram", "potrf", "trtri", "lauum", "score", "symprod", "contract"), ms.tolist()))
+
     def last_gemm_ms(self):
         ms, n = C.c_double(), C.c_int64()
         self._lib.gps_last_gemm_ms(self._h, C.byref(ms), C.byref(n))

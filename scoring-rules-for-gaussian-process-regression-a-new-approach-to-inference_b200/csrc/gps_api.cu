@@ -111,15 +111,26 @@ int gemm_timing_end(gps_ctx* ctx) {
 
 }  // namespace
 
+static int stage_mark(gps_ctx* ctx, int which) {
+  if (!ctx->stage_ev[which]) GPS_CUDA(cudaEventCreate(&ctx->stage_ev[which]));
+  GPS_CUDA(cudaEventRecord(ctx->stage_ev[which], ctx->stream));
+  return GPS_OK;
+}
+
 // K = ARD(X, X) + sn2 I  ->  L, L^-1, K^-1 (in Kb), alpha.  logdiag optionally.
 int gps_factor_and_invert(gps_ctx* ctx, bool want_logdet) {
   const int64_t N = ctx->N, Np = ctx->Np;
   double* v = ctx->vecs.p;
+  GPS_CHECK(stage_mark(ctx, gps_ctx::ST_BEGIN));
   GPS_CHECK(gps_gram_sym(ctx, ctx->X.p, N, Np, ctx->D, ctx->params.p, ctx->Kb.p));
+  GPS_CHECK(stage_mark(ctx, gps_ctx::ST_GRAM));
   GPS_CHECK(gps_potrf(ctx, ctx->Kb.p, ctx->Xb.p, Np));
   if (want_logdet) GPS_CHECK(gps_diag_extract(ctx, ctx->Kb.p, Np, v + V_LOGD * Np, 1));
+  GPS_CHECK(stage_mark(ctx, gps_ctx::ST_POTRF));
   GPS_CHECK(gps_trtri(ctx, ctx->Kb.p, ctx->Xb.p, ctx->Sb.p, Np));
+  GPS_CHECK(stage_mark(ctx, gps_ctx::ST_TRTRI));
   GPS_CHECK(gps_lauum(ctx, ctx->Xb.p, ctx->Kb.p, Np));
+  GPS_CHECK(stage_mark(ctx, gps_ctx::ST_LAUUM));
   GPS_CHECK(gps_symv(ctx, ctx->Kb.p, Np, ctx->y.p, v + V_ALPHA * Np));
   return GPS_OK;
 }
@@ -185,6 +196,7 @@ void gps_destroy(gps_ctx* ctx) {
     cudaEventDestroy(pr.second);
   }
   for (auto e : ctx->potrf_events) cudaEventDestroy(e);
+  for (auto e : ctx->stage_ev) if (e) cudaEventDestroy(e);
   if (ctx->panel_stream) cudaStreamDestroy(ctx->panel_stream);
   cudaEventDestroy(ctx->ev0);
   cudaEventDestroy(ctx->ev1);
@@ -200,6 +212,13 @@ int gps_last_gemm_ms(gps_ctx* ctx, double* ms, int64_t* launches) {
   if (!ctx) return GPS_EINVAL;
   if (ms) *ms = ctx->last_gemm_ms;
   if (launches) *launches = ctx->last_gemm_launches;
+  return GPS_OK;
+}
+
+int gps_last_stage_ms(gps_ctx* ctx, double* ms7) {
+  if (!ctx || !ms7) return GPS_EINVAL;
+  if (!ctx->stage_valid) return gps_fail(ctx, GPS_ESTATE, "last_stage_ms: no CRPS/LOGS obj+grad evaluation to report");
+  for (int k = 1; k < gps_ctx::ST_COUNT; ++k) ms7[k - 1] = ctx->last_stage_ms[k];
   return GPS_OK;
 }
 
@@ -238,6 +257,8 @@ int gps_full_eval(gps_ctx* ctx, const double* theta, int score, double* obj, dou
   GPS_CHECK(gps_factor_and_invert(ctx, score == GPS_NLML));
   double* v = ctx->vecs.p;
   double* par = ctx->params.p;
+  bool stages_full = false;
+  ctx->stage_valid = false;
   if (score != GPS_NLML) {
     GPS_CHECK(gps_diag_extract(ctx, ctx->Kb.p, Np, v + V_D * Np, 0));
     GPS_CHECK(gps_loo_score(ctx, score, N, Np, v + V_ALPHA * Np, v + V_D * Np, ctx->y.p, v + V_ABAR * Np,
@@ -245,9 +266,13 @@ int gps_full_eval(gps_ctx* ctx, const double* theta, int score, double* obj, dou
     ctx->loo_valid = true;
     if (grad) {
       GPS_CHECK(gps_symv(ctx, ctx->Kb.p, Np, v + V_ABAR * Np, v + V_U * Np));
+      GPS_CHECK(stage_mark(ctx, gps_ctx::ST_SCORE));
       GPS_CHECK(gps_symprod(ctx, ctx->Kb.p, v + V_DBAR * Np, ctx->Sb.p, Np));
+      GPS_CHECK(stage_mark(ctx, gps_ctx::ST_SYMPROD));
       GPS_CHECK(gps_grad_contract(ctx, 0, ctx->Sb.p, N, Np, ctx->X.p, D, par, v + V_ALPHA * Np, v + V_U * Np,
                                   par + PAR_GSUM));
+      GPS_CHECK(stage_mark(ctx, gps_ctx::ST_CONTRACT));
+      stages_full = true;
     }
   } else {
     ctx->loo_valid = false;
@@ -261,6 +286,14 @@ int gps_full_eval(gps_ctx* ctx, const double* theta, int score, double* obj, dou
                            cudaMemcpyDeviceToHost, ctx->stream));
   GPS_CHECK(gps_check_info(ctx));  // synchronises the stream
   GPS_CHECK(gemm_timing_end(ctx));
+  if (stages_full) {
+    for (int k = 1; k < gps_ctx::ST_COUNT; ++k) {
+      float ms = 0;
+      GPS_CUDA(cudaEventElapsedTime(&ms, ctx->stage_ev[k - 1], ctx->stage_ev[k]));
+      ctx->last_stage_ms[k] = ms;
+    }
+    ctx->stage_valid = true;
+  }
   *obj = h[0];
   if (grad) {
     const double* gs = h + (PAR_GSUM - PAR_OBJ);

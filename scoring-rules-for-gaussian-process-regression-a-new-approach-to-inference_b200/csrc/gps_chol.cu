@@ -152,7 +152,7 @@ potf2_inv_kernel(double* __restrict__ K, double* __restrict__ Xinv, int64_t ld, 
 // runs on DMMA from shared memory.  The lower 4 x 4 block triangle lives in shared memory as ten
 // [32][36] blocks (leading dimension 36: conflict-free m8n8k4 fragment loads).
 constexpr int SB = 32, SLD = 36, SBLK = SB * SLD;
-constexpr size_t POTF2V2_SMEM = (size_t)(10 + 10 + 3) * SBLK * sizeof(double) + 64 * sizeof(double);
+constexpr size_t POTF2V2_SMEM = (size_t)(10 + 10 + 3) * SBLK * sizeof(double) + 128 * sizeof(double);
 
 __device__ __forceinline__ void dmma4(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
@@ -160,6 +160,13 @@ __device__ __forceinline__ void dmma4(double& c0, double& c1, double a, double b
                : "d"(a), "d"(b));
 }
 __device__ __forceinline__ int blk_idx(int i, int j) { return i * (i + 1) / 2 + j; }
+// r[lane] without dynamic register indexing
+__device__ __forceinline__ double r_diag(const double (&r)[32], int lane) {
+  double v = r[0];
+#pragma unroll
+  for (int j = 1; j < 32; ++j) v = (lane == j) ? r[j] : v;
+  return v;
+}
 
 // c[nf] += sgn * A[strip mf] * B'   (A, B blocks with k contiguous)
 __device__ __forceinline__ void strip_nt(const double* __restrict__ A, const double* __restrict__ B, int mf, int lane,
@@ -206,24 +213,26 @@ potf2_inv_dmma_kernel(double* __restrict__ K, double* __restrict__ Xinv, int64_t
   double* Lb = sm;                    // 10 lower blocks of A -> L
   double* Xb = Lb + 10 * SBLK;        // 10 lower blocks of L^-1
   double* Tb = Xb + 10 * SBLK;        // 3 scratch blocks
-  double* Li = Tb + 3 * SBLK;         // [32] reciprocal diagonal of the current sub-block
+  double* Li = Tb + 3 * SBLK;         // [128] reciprocal diagonal of L
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   double* Kd = K + (int64_t)blk * T * ld + (int64_t)blk * T;
   double* Xd = Xinv + (int64_t)blk * T * ld + (int64_t)blk * T;
 
-  // load the lower block triangle (rows of 32 doubles, coalesced)
-  for (int e = tid; e < 10 * SB * SB; e += 256) {
-    const int b = e >> 10, r = (e >> 5) & 31, c = e & 31;
-    int bi = 0;
-    while ((bi + 1) * (bi + 2) / 2 <= b) ++bi;
+  // load the lower block triangle: 40 independent coalesced loads per thread (rows of 32 doubles)
+#pragma unroll
+  for (int b = 0; b < 10; ++b) {
+    const int bi = (b >= 6) ? 3 : (b >= 3) ? 2 : (b >= 1) ? 1 : 0;
     const int bj = b - bi * (bi + 1) / 2;
-    Lb[b * SBLK + r * SLD + c] = Kd[(int64_t)(bi * SB + r) * ld + bj * SB + c];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int e = tid + q * 256, r = e >> 5, c = e & 31;
+      Lb[b * SBLK + r * SLD + c] = Kd[(int64_t)(bi * SB + r) * ld + bj * SB + c];
+    }
   }
   __syncthreads();
 
   for (int kb = 0; kb < 4; ++kb) {
     double* D = Lb + blk_idx(kb, kb) * SBLK;
-    double* XD = Xb + blk_idx(kb, kb) * SBLK;
     // (1) one warp: Cholesky of the 32 x 32 diagonal sub-block, rows in registers
     if (warp == 0) {
       double r[SB];
@@ -246,41 +255,34 @@ potf2_inv_dmma_kernel(double* __restrict__ K, double* __restrict__ Xinv, int64_t
       }
 #pragma unroll
       for (int j = 0; j < SB; ++j) D[lane * SLD + j] = (j <= lane) ? r[j] : 0.0;
-      __syncwarp();
-      Li[lane] = 1.0 / D[lane * SLD + lane];
-      __syncwarp();
-      // inverse of the sub-block: lane c solves L x = e_c (column-oriented forward substitution)
-      double x[SB];
-#pragma unroll
-      for (int i = 0; i < SB; ++i) x[i] = (i == lane) ? 1.0 : 0.0;
-      const volatile double* Dv = D;
-#pragma unroll
-      for (int i = 0; i < SB; ++i) {
-        x[i] *= Li[i];
-#pragma unroll
-        for (int k2 = i + 1; k2 < SB; ++k2) x[k2] = fma(-Dv[k2 * SLD + i], x[i], x[k2]);
-      }
-#pragma unroll
-      for (int i = 0; i < SB; ++i) XD[i * SLD + lane] = (i >= lane) ? x[i] : 0.0;
+      Li[kb * SB + lane] = 1.0 / r_diag(r, lane);
     }
     __syncthreads();
-    // (2) panel: L(i,kb) = A(i,kb) * inv(L_D)'   — strips of 8 rows, in place
+    // (2) panel: solve X L_D' = A(i,kb) row by row (one thread per row, column-oriented
+    //     substitution with the row in registers; L_D broadcast from shared memory)
     const int nbelow = 3 - kb;
-    for (int item = warp; item < nbelow * 4; item += 8) {
-      const int i = kb + 1 + item / 4, mf = item & 3;
-      double* P = Lb + blk_idx(i, kb) * SBLK;
-      double c[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
-      strip_nt(P, XD, mf, lane, 1.0, c);
-      __syncwarp();
-      strip_store(P, mf, lane, c);
+    if (tid < nbelow * SB) {
+      double* P = Lb + blk_idx(kb + 1 + tid / SB, kb) * SBLK + (tid & 31) * SLD;
+      double x[SB];
+#pragma unroll
+      for (int j = 0; j < SB; ++j) x[j] = P[j];
+      const volatile double* Dv = D;
+      const double* Lik = Li + kb * SB;
+#pragma unroll
+      for (int j = 0; j < SB; ++j) {
+        x[j] *= Lik[j];
+#pragma unroll
+        for (int c = j + 1; c < SB; ++c) x[c] = fma(-Dv[c * SLD + j], x[j], x[c]);
+      }
+#pragma unroll
+      for (int j = 0; j < SB; ++j) P[j] = x[j];
     }
     __syncthreads();
     // (3) trailing update inside the 128 block: A(i,j) -= L(i,kb) L(j,kb)'
     const int ntr = nbelow * (nbelow + 1) / 2;
     for (int item = warp; item < ntr * 4; item += 8) {
       const int bidx = item / 4, mf = item & 3;
-      int ii = 0;
-      while ((ii + 1) * (ii + 2) / 2 <= bidx) ++ii;
+      const int ii = (bidx >= 3) ? 2 : (bidx >= 1) ? 1 : 0;
       const int jj = bidx - ii * (ii + 1) / 2;
       const int i = kb + 1 + ii, j = kb + 1 + jj;
       double* Cb = Lb + blk_idx(i, j) * SBLK;
@@ -291,6 +293,25 @@ potf2_inv_dmma_kernel(double* __restrict__ K, double* __restrict__ Xinv, int64_t
     }
     __syncthreads();
   }
+  // inverses of the four diagonal sub-blocks, one warp each: lane c solves L x = e_c
+  if (warp < 4) {
+    const double* D = Lb + blk_idx(warp, warp) * SBLK;
+    double* XD = Xb + blk_idx(warp, warp) * SBLK;
+    const double* Lik = Li + warp * SB;
+    double x[SB];
+#pragma unroll
+    for (int i = 0; i < SB; ++i) x[i] = (i == lane) ? 1.0 : 0.0;
+    const volatile double* Dv = D;
+#pragma unroll
+    for (int i = 0; i < SB; ++i) {
+      x[i] *= Lik[i];
+#pragma unroll
+      for (int k2 = i + 1; k2 < SB; ++k2) x[k2] = fma(-Dv[k2 * SLD + i], x[i], x[k2]);
+    }
+#pragma unroll
+    for (int i = 0; i < SB; ++i) XD[i * SLD + lane] = (i >= lane) ? x[i] : 0.0;
+  }
+  __syncthreads();
   // (4) off-diagonal blocks of X = L^-1 by block diagonals: X(i,j) = -X(i,i) sum_k L(i,k) X(k,j)
   for (int d = 1; d < 4; ++d) {
     const int nblk = 4 - d;
@@ -408,10 +429,17 @@ int gps_build_tasks(gps_ctx* ctx, int64_t Np) {
   for (int i = 0; i < nb; ++i)
     for (int j = 0; j <= i; ++j) push(i * T, j * T, i * T, nb * T, i, j);
   ctx->lauum.cnt = h.size() - ctx->lauum.off;
-  // SYMPROD: lower tiles, full k
+  // SYMPROD: lower tiles, full k.  Tiles are issued super-tile by super-tile (SUPER x SUPER tiles
+  // ~ one wave of CTAs), so that the CTAs resident at the same time share 2 * SUPER operand
+  // panels through L2 instead of streaming ~150 different ones from HBM.
   ctx->symprod.off = h.size();
-  for (int i = 0; i < nb; ++i)
-    for (int j = 0; j <= i; ++j) push(i * T, j * T, 0, nb * T, i, j);
+  {
+    const int SUPER = 12;
+    for (int I = 0; I < nb; I += SUPER)
+      for (int J = 0; J <= I; J += SUPER)
+        for (int i = I; i < std::min(nb, I + SUPER); ++i)
+          for (int j = J; j < std::min(nb, J + SUPER) && j <= i; ++j) push(i * T, j * T, 0, nb * T, i, j);
+  }
   ctx->symprod.cnt = h.size() - ctx->symprod.off;
 
   if (h.size() > ctx->tasks_cap) {

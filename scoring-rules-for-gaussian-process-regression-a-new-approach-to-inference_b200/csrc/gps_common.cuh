@@ -39,6 +39,11 @@ struct gps_ctx {
   bool time_gemm = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> gemm_events;
   size_t gemm_events_used = 0;
+  // stage boundaries of the last full-GP evaluation (events on the main stream)
+  enum { ST_BEGIN = 0, ST_GRAM, ST_POTRF, ST_TRTRI, ST_LAUUM, ST_SCORE, ST_SYMPROD, ST_CONTRACT, ST_COUNT };
+  cudaEvent_t stage_ev[ST_COUNT] = {};
+  double last_stage_ms[ST_COUNT] = {};
+  bool stage_valid = false;
   double last_gemm_ms = 0;
   int64_t last_gemm_launches = 0;
 

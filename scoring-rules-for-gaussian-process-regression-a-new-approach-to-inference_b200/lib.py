@@ -28,6 +28,7 @@ SIGNATURES = {
     "gps_set_stream": (C.c_int, [_vp, _vp]),
     "gps_set_gemm_timing": (C.c_int, [_vp, C.c_int]),
     "gps_last_gemm_ms": (C.c_int, [_vp, _dp, C.POINTER(_i64)]),
+    "gps_last_stage_ms": (C.c_int, [_vp, _dp]),
     "gps_set_data": (C.c_int, [_vp, _vp, _vp, _i64, C.c_int]),
     "gps_full_eval": (C.c_int, [_vp, _dp, C.c_int, _dp, _dp]),
     "gps_full_loo": (C.c_int, [_vp, _vp, _vp]),
