@@ -32,6 +32,11 @@ int gps_dbg_fp64_peak(gps_ctx* ctx, int iters, double* dmma_tflops, double* dfma
  * POTRF (0: register-cyclic, 1: 32-blocked DMMA = default). */
 int gps_dbg_set_variant(gps_ctx* ctx, int what, int value);
 
+/* clock64 phase stamps of the last diagonal-block kernel launch (first call arms the recording):
+ * cycles17[k] = cycles since kernel start at phase boundary k (load, 4 x {factor, panel, update},
+ * sub-block inverses, off-diagonal inverse, write-back). */
+int gps_dbg_potf2_phases(gps_ctx* ctx, int64_t* cycles17);
+
 /* Training Gram K = ARD(X,X) + sn2 I of the current data set at theta, N x N (UVA out). */
 int gps_dbg_gram(gps_ctx* ctx, const double* theta, double* K);
 

@@ -208,8 +208,12 @@ __device__ __forceinline__ void strip_load(const double* __restrict__ C, int mf,
 }
 
 __global__ void __launch_bounds__(256, 1)
-potf2_inv_dmma_kernel(double* __restrict__ K, double* __restrict__ Xinv, int64_t ld, int blk, int* __restrict__ info) {
+potf2_inv_dmma_kernel(double* __restrict__ K, double* __restrict__ Xinv, int64_t ld, int blk, int* __restrict__ info,
+                      long long* __restrict__ prof) {
   extern __shared__ __align__(16) double sm[];
+  int pslot = 0;
+#define GPS_PROF() do { if (prof && threadIdx.x == 0) prof[pslot] = clock64(); ++pslot; } while (0)
+  GPS_PROF();
   double* Lb = sm;                    // 10 lower blocks of A -> L
   double* Xb = Lb + 10 * SBLK;        // 10 lower blocks of L^-1
   double* Tb = Xb + 10 * SBLK;        // 3 scratch blocks
@@ -230,6 +234,7 @@ potf2_inv_dmma_kernel(double* __restrict__ K, double* __restrict__ Xinv, int64_t
     }
   }
   __syncthreads();
+  GPS_PROF();   // 1: loaded
 
   for (int kb = 0; kb < 4; ++kb) {
     double* D = Lb + blk_idx(kb, kb) * SBLK;
@@ -245,7 +250,7 @@ potf2_inv_dmma_kernel(double* __restrict__ K, double* __restrict__ Xinv, int64_t
           if (lane == 0) atomicCAS(info, 0, blk * T + kb * SB + j + 1);
           piv = 1.0;
         }
-        const double lj = r[j] * rsqrt(piv);
+        const double lj = r[j] * rsqrt(piv);   // (an fp32-seeded Newton rsqrt measured slower: 16.2k vs 11.2k cycles per sub-block)
 #pragma unroll
         for (int c = j + 1; c < SB; ++c) {
           const double lc = __shfl_sync(0xffffffffu, lj, c);
@@ -258,6 +263,7 @@ potf2_inv_dmma_kernel(double* __restrict__ K, double* __restrict__ Xinv, int64_t
       Li[kb * SB + lane] = 1.0 / r_diag(r, lane);
     }
     __syncthreads();
+    GPS_PROF();   // 2 + 3 kb: sub-block factored
     // (2) panel: solve X L_D' = A(i,kb) row by row (one thread per row, column-oriented
     //     substitution with the row in registers; L_D broadcast from shared memory)
     const int nbelow = 3 - kb;
@@ -278,6 +284,7 @@ potf2_inv_dmma_kernel(double* __restrict__ K, double* __restrict__ Xinv, int64_t
       for (int j = 0; j < SB; ++j) P[j] = x[j];
     }
     __syncthreads();
+    GPS_PROF();   // 3 + 3 kb: panel solved
     // (3) trailing update inside the 128 block: A(i,j) -= L(i,kb) L(j,kb)'
     const int ntr = nbelow * (nbelow + 1) / 2;
     for (int item = warp; item < ntr * 4; item += 8) {
@@ -292,6 +299,7 @@ potf2_inv_dmma_kernel(double* __restrict__ K, double* __restrict__ Xinv, int64_t
       strip_store(Cb, mf, lane, c);
     }
     __syncthreads();
+    GPS_PROF();   // 4 + 3 kb: trailing blocks updated
   }
   // inverses of the four diagonal sub-blocks, one warp each: lane c solves L x = e_c
   if (warp < 4) {
@@ -312,6 +320,7 @@ potf2_inv_dmma_kernel(double* __restrict__ K, double* __restrict__ Xinv, int64_t
     for (int i = 0; i < SB; ++i) XD[i * SLD + lane] = (i >= lane) ? x[i] : 0.0;
   }
   __syncthreads();
+  GPS_PROF();   // 14: sub-block inverses
   // (4) off-diagonal blocks of X = L^-1 by block diagonals: X(i,j) = -X(i,i) sum_k L(i,k) X(k,j)
   for (int d = 1; d < 4; ++d) {
     const int nblk = 4 - d;
@@ -330,8 +339,11 @@ potf2_inv_dmma_kernel(double* __restrict__ K, double* __restrict__ Xinv, int64_t
     }
     __syncthreads();
   }
+  GPS_PROF();   // 15: off-diagonal blocks of the inverse
   // write back: full 128 x 128 tiles of L and L^-1 with explicit zeros above the diagonal
-  for (int e = tid; e < T * T; e += 256) {
+#pragma unroll 8
+  for (int q = 0; q < T * T / 256; ++q) {
+    const int e = tid + q * 256;
     const int r = e >> 7, c = e & 127;
     const int bi = r >> 5, bj = c >> 5;
     double lv = 0.0, xv = 0.0;
@@ -343,6 +355,9 @@ potf2_inv_dmma_kernel(double* __restrict__ K, double* __restrict__ Xinv, int64_t
     Kd[(int64_t)r * ld + c] = lv;
     Xd[(int64_t)r * ld + c] = xv;
   }
+  __syncthreads();
+  GPS_PROF();   // 16: written back
+#undef GPS_PROF
 }
 
 struct Node { int lo, mid, hi, depth; };
@@ -491,7 +506,7 @@ int gps_potrf(gps_ctx* ctx, double* K, double* Xinv, int64_t Np) {
       if (ctx->potf2_variant == 0)
         potf2_inv_kernel<<<1, 256, POTF2_SMEM, s_pan>>>(K, Xinv, Np, k, ctx->d_info);
       else
-        potf2_inv_dmma_kernel<<<1, 256, POTF2V2_SMEM, s_pan>>>(K, Xinv, Np, k, ctx->d_info);
+        potf2_inv_dmma_kernel<<<1, 256, POTF2V2_SMEM, s_pan>>>(K, Xinv, Np, k, ctx->d_info, ctx->potf2_prof);
       if (cudaGetLastError() != cudaSuccess) rc = gps_fail(ctx, GPS_ECUDA, "potf2 launch failed");
       ctx->launches++;
       // panel: L_ik = A_ik * inv(L_kk)'

@@ -33,6 +33,7 @@ struct gps_ctx {
   std::string err;
   int64_t launches = 0;
   int sm_count = 148;
+  long long* potf2_prof = nullptr;    // device buffer for clock64 phase stamps of the diagonal kernel (debug)
   int potf2_variant = 1;              // 0: register-cyclic diagonal kernel, 1: 32-blocked DMMA diagonal kernel
   int gemm_variant = 6;               // tile-GEMM policy (see gps_gemm.cu); switched by gps_dbg_set_variant
   // GEMM timing of the last full eval

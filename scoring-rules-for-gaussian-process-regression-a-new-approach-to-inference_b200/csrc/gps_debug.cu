@@ -150,6 +150,22 @@ int gps_dbg_set_variant(gps_ctx* ctx, int what, int value) {
   return GPS_OK;
 }
 
+int gps_dbg_potf2_phases(gps_ctx* ctx, int64_t* cycles17) {
+  if (!ctx || !cycles17) return GPS_EINVAL;
+  GPS_CUDA(cudaSetDevice(ctx->device));
+  if (!ctx->potf2_prof) {
+    GPS_CUDA(cudaMalloc(&ctx->potf2_prof, 32 * sizeof(long long)));
+    GPS_CUDA(cudaMemset(ctx->potf2_prof, 0, 32 * sizeof(long long)));
+    for (int k = 0; k < 17; ++k) cycles17[k] = 0;
+    return GPS_OK;   // armed: the next factorisations record their phase stamps
+  }
+  GPS_CUDA(cudaStreamSynchronize(ctx->stream));
+  long long h[17];
+  GPS_CUDA(cudaMemcpy(h, ctx->potf2_prof, sizeof h, cudaMemcpyDeviceToHost));
+  for (int k = 0; k < 17; ++k) cycles17[k] = h[k] - h[0];
+  return GPS_OK;
+}
+
 int gps_dbg_gram(gps_ctx* ctx, const double* theta, double* K) {
   if (!ctx) return GPS_EINVAL;
   if (ctx->N == 0) return gps_fail(ctx, GPS_ESTATE, "dbg_gram: no data");
