@@ -29,7 +29,8 @@ int gps_dbg_fp64_peak(gps_ctx* ctx, int iters, double* dmma_tflops, double* dfma
  * (0: BK16 x 4 stages, 1: + fragment double-buffering, 2: BK32 x 3 stages, 3: BK32 + double-buffering,
  * 4: BK16 with 16 warps, 5: BK32 with 16 warps, 6: 64 x 128 CTA tile, 4 warps, two CTAs per SM = default,
  * 7: 6 + double-buffering, 8: 6 with 64 x 32 warp tiles); what = 1 selects the diagonal-block kernel of
- * POTRF (0: register-cyclic, 1: 32-blocked DMMA = default). */
+ * POTRF (0: register-cyclic, 1: 32-blocked DMMA = default); what = 2 selects the FITC row passes
+ * (0: thread-per-row, 1: tile/DMMA formulation = default). */
 int gps_dbg_set_variant(gps_ctx* ctx, int what, int value);
 
 /* clock64 phase stamps of the last diagonal-block kernel launch (first call arms the recording):

@@ -33,6 +33,7 @@ struct gps_ctx {
   std::string err;
   int64_t launches = 0;
   int sm_count = 148;
+  int fitc_variant = 1;               // 0: thread-per-row FITC passes, 1: tile (DMMA) formulation
   long long* potf2_prof = nullptr;    // device buffer for clock64 phase stamps of the diagonal kernel (debug)
   int potf2_variant = 1;              // 0: register-cyclic diagonal kernel, 1: 32-blocked DMMA diagonal kernel
   int gemm_variant = 6;               // tile-GEMM policy (see gps_gemm.cu); switched by gps_dbg_set_variant
@@ -85,12 +86,13 @@ struct gps_ctx {
     double jitter = 0, ea = 0, sn2 = 0;
     int64_t world_n = 0;
     int grid = 0;
-    DevBuf V, W;          // [N, MP] row-major
+    DevBuf V, W;          // [MP, N] (tile kernels) or [N, MP] (thread-per-row kernels)
     DevBuf rowv;          // per-row scalars: lam, lam_bar0, rbar, tbar, alpha, d : 6 x N
     DevBuf small;         // replicated small matrices (layout in gps_fitc.cu)
     DevBuf part;          // per-block partial accumulators
+    DevBuf part2;         // first-stage sums of the partials (large grids)
     DevBuf acc1, acc2, acc3;  // single-GPU accumulators
-    bool begun = false, pass2_done = false;
+    bool begun = false, pass2_done = false, tile = true;
     std::vector<double> host_out;
   } fitc;
 };

@@ -34,7 +34,7 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
 
 // layout of the replicated small-matrix buffer (doubles), MP-strided
 struct SmallLayout {
-  int us, la, lai, kuu, lc, lci, beta, bbar, cbar, vyb, total;
+  int us, la, lai, kuu, lc, lci, beta, bbar, cbar, vyb, lainv, lcinv, total;
   __host__ __device__ SmallLayout(int MP, int D) {
     int o = 0;
     us = o;   o += MP * D;
@@ -47,6 +47,8 @@ struct SmallLayout {
     bbar = o; o += MP;
     cbar = o; o += MP * MP;
     vyb = o;  o += MP;
+    lainv = o; o += MP * MP;
+    lcinv = o; o += MP * MP;
     total = o;
   }
 };
@@ -99,6 +101,27 @@ __device__ __forceinline__ void col_solve_LT(const double* __restrict__ L, const
     b[i] *= Li[i];
 #pragma unroll
     for (int k = 0; k < i; ++k) b[k] = fma(-Lv[i * MP + k], b[i], b[k]);
+  }
+}
+
+// X = L^-1 for lower-triangular L[MP][MP] in shared memory: lane c solves L x = e_c by
+// column-oriented forward substitution and writes column c of X (row-major, zeros above the diagonal).
+template <int MP>
+__device__ __forceinline__ void warp_tri_inverse(const double* __restrict__ L, const double* __restrict__ Li,
+                                                 double* __restrict__ Xout, int lane) {
+  double x[MP];
+#pragma unroll
+  for (int i = 0; i < MP; ++i) x[i] = (i == lane) ? 1.0 : 0.0;
+  const volatile double* Lv = L;
+#pragma unroll
+  for (int i = 0; i < MP; ++i) {
+    x[i] *= Li[i];
+#pragma unroll
+    for (int k = i + 1; k < MP; ++k) x[k] = fma(-Lv[k * MP + i], x[i], x[k]);
+  }
+  if (lane < MP) {
+#pragma unroll
+    for (int i = 0; i < MP; ++i) Xout[i * MP + lane] = (i >= lane) ? x[i] : 0.0;
   }
 }
 
@@ -212,8 +235,14 @@ fitc_small0_kernel(const double* __restrict__ U, const double* __restrict__ par,
     if (bad && lane == 0) atomicCAS(info, 0, bad);
   }
   __syncthreads();
+  __shared__ double Ai[MP];
   for (int e = tid; e < MP * MP; e += 128) small[lo.la + e] = A[e];
-  if (tid < MP) small[lo.lai + tid] = 1.0 / A[tid * MP + tid];
+  if (tid < MP) {
+    Ai[tid] = 1.0 / A[tid * MP + tid];
+    small[lo.lai + tid] = Ai[tid];
+  }
+  __syncthreads();
+  if (tid < 32) warp_tri_inverse<MP>(A, Ai, small + lo.lainv, lane);   // L_A^-1 for the tile kernels
 }
 
 // per-row kernel vector k_m = ea exp(-0.5 |us_m - xs|^2); xs read from the transposed tile column `tid`
@@ -389,6 +418,21 @@ fitc_reduce_kernel(const double* __restrict__ part, int nblocks, int len, double
   block_reduce_partials(part, nblocks, len, acc);
 }
 
+// first stage of the reduction for large grids: blockIdx.y sums its slice of the partial blocks,
+// blockIdx.x its slice of the entries; out[g][e].  Fixed slices: deterministic.
+__global__ void __launch_bounds__(128)
+fitc_reduce_stage_kernel(const double* __restrict__ part, int nblocks, int len, int per_group,
+                         double* __restrict__ out) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= len) return;
+  const int b0 = blockIdx.y * per_group;
+  const int b1 = min(nblocks, b0 + per_group);
+  double s = 0.0;
+#pragma unroll 16
+  for (int b = b0; b < b1; ++b) s += part[(int64_t)b * len + e];
+  out[(int64_t)blockIdx.y * len + e] = s;
+}
+
 // ---- replicated step before pass 2: C = I + acc1, L_C, beta -----------------------------------------
 // If `part` is non-null the per-block partials of pass 1 are summed into acc1 first (single GPU:
 // no separate reduce launch).
@@ -419,6 +463,7 @@ fitc_small1_kernel(const double* __restrict__ part, int nblocks, double* __restr
       small[lo.beta + lane] = x;
       small[lo.lci + lane] = Li[lane];
     }
+    warp_tri_inverse<MP>(C, Li, small + lo.lcinv, lane);   // L_C^-1 for the tile kernels
   }
   __syncthreads();
   for (int e = tid; e < MP * MP; e += 128) small[lo.lc + e] = C[e];
@@ -789,6 +834,357 @@ fitc_small3_kernel(const double* __restrict__ part, int nblocks, const double* _
   }
 }
 
+// =====================================================================================================
+// Tile formulation of the three row passes (default).  Same math, same accumulators, but every
+// M x M operation on a block of 128 rows is a small GEMM on the DMMA tensor path:
+//     V = K L_A^-T,   W = V L_C^-T,   CV = V C_bar,   V_bar = W_bar L_C^-1 + ...,   Kuf_bar = V_bar L_A^-1
+// Row tiles live transposed in shared memory ([MP][132]: a row owner walks a column conflict-free,
+// the m8n8k4 A-fragment loads are conflict-free); the M x M factors are staged once per CTA as
+// B operands ([MP][MP + 4]).  Per-row scalars (lambda, d, alpha, seeds) stay thread-per-row.  V and W
+// are kept in HBM transposed ([MP][N]) so tile loads and stores are coalesced.  Registers per thread
+// drop from 255 to well under 128 and nothing serial is longer than one fragment product.
+// =====================================================================================================
+template <int MP>
+struct TileCfg {
+  static constexpr int MF = 4;            // 32 rows per warp
+  static constexpr int NF = MP / 8;
+  static constexpr int KS = MP / 4;
+  static constexpr int LDM = MP + 4;      // B-operand stride: conflict-free fragment loads
+};
+
+// out[r][n] = sum_k in[r][k] * Mat[k][n] for this warp's 32 rows; tiles transposed ([MP][LDT]).
+// in == out is allowed (all reads complete before the first write).
+template <int MP>
+__device__ __forceinline__ void warp_tile_mm(const double* inT, const double* __restrict__ Mat, double* outT,
+                                             int warp, int lane) {
+  using C = TileCfg<MP>;
+  const int g = lane >> 2, t = lane & 3, r0 = warp * 32;
+  double acc[C::MF][C::NF][2];
+#pragma unroll
+  for (int i = 0; i < C::MF; ++i)
+#pragma unroll
+    for (int j = 0; j < C::NF; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+#pragma unroll
+  for (int kk = 0; kk < C::KS; ++kk) {
+    double a[C::MF], b[C::NF];
+#pragma unroll
+    for (int i = 0; i < C::MF; ++i) a[i] = inT[(kk * 4 + t) * LDT + r0 + i * 8 + g];
+#pragma unroll
+    for (int j = 0; j < C::NF; ++j) b[j] = Mat[(kk * 4 + t) * C::LDM + j * 8 + g];
+#pragma unroll
+    for (int i = 0; i < C::MF; ++i)
+#pragma unroll
+      for (int j = 0; j < C::NF; ++j) dmma(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+  }
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < C::MF; ++i)
+#pragma unroll
+    for (int j = 0; j < C::NF; ++j) {
+      outT[(j * 8 + 2 * t) * LDT + r0 + i * 8 + g] = acc[i][j][0];
+      outT[(j * 8 + 2 * t + 1) * LDT + r0 + i * 8 + g] = acc[i][j][1];
+    }
+  __syncwarp();
+}
+
+// stage an M x M matrix from the replicated buffer as a B operand: Mat[k][n] = src[k][n] or src[n][k]
+template <int MP, bool TRANSPOSE>
+__device__ __forceinline__ void stage_mat(double* Mat, const double* __restrict__ src, int tid) {
+  constexpr int LDM = TileCfg<MP>::LDM;
+  for (int e = tid; e < MP * MP; e += RB) {
+    const int k = e / MP, n = e - k * MP;
+    Mat[k * LDM + n] = TRANSPOSE ? src[n * MP + k] : src[k * MP + n];
+  }
+}
+
+template <int MP>
+__global__ void __launch_bounds__(RB)
+fitc_row1_tile_kernel(const double* __restrict__ X, const double* __restrict__ y, int64_t N, int D, int M,
+                      const double* __restrict__ par, const double* __restrict__ small, double* __restrict__ VgT,
+                      double* __restrict__ lamg, double* __restrict__ part) {
+  extern __shared__ double sh[];
+  constexpr int MF = MP / 8, LDM = TileCfg<MP>::LDM;
+  const SmallLayout lo(MP, D);
+  double* Us = sh;                        // [MP][D]
+  double* MatA = Us + MP * D;             // [MP][LDM]  B[k][n] = L_A^-1[n][k]
+  double* XsT = MatA + MP * LDM;          // [D][LDT]
+  double* KT = XsT + (size_t)D * LDT;     // [MP][LDT]   k -> V -> V / sqrt(lambda)
+  double* Ys = KT + (size_t)MP * LDT;     // [RB]
+  double* Cs = Ys + RB;                   // [MP][MP] + [MP]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int e = tid; e < MP * D; e += RB) Us[e] = small[lo.us + e];
+  stage_mat<MP, true>(MatA, small + lo.lainv, tid);
+  for (int e = tid; e < MP * MP + MP; e += RB) Cs[e] = 0.0;
+  const double ea = par[0], sn2 = par[1];
+  double cacc[MF][MF][2], vacc[MF][2];
+#pragma unroll
+  for (int i = 0; i < MF; ++i) {
+    vacc[i][0] = vacc[i][1] = 0.0;
+#pragma unroll
+    for (int j = 0; j < MF; ++j) cacc[i][j][0] = cacc[i][j][1] = 0.0;
+  }
+  __syncthreads();
+  for (int64_t base = (int64_t)blockIdx.x * RB; base < N; base += (int64_t)gridDim.x * RB) {
+    const int64_t i = base + tid;
+    const bool live = i < N;
+    for (int d = 0; d < D; ++d) XsT[d * LDT + tid] = live ? X[i * D + d] * par[2 + d] : 0.0;
+#pragma unroll 4
+    for (int m = 0; m < MP; ++m) {
+      double r2 = 0.0;
+      for (int d = 0; d < D; ++d) {
+        const double df = Us[m * D + d] - XsT[d * LDT + tid];
+        r2 = fma(df, df, r2);
+      }
+      KT[m * LDT + tid] = (m < M && live) ? ea * exp(-0.5 * r2) : 0.0;
+    }
+    __syncwarp();
+    warp_tile_mm<MP>(KT, MatA, KT, warp, lane);                 // V = K L_A^-T
+    double q = 0.0;
+#pragma unroll 8
+    for (int m = 0; m < MP; ++m) {
+      const double v = KT[m * LDT + tid];
+      q = fma(v, v, q);
+      if (live) VgT[(int64_t)m * N + i] = v;
+    }
+    const double lam = ea - q + sn2;
+    if (live) lamg[i] = lam;
+    const double rs = live ? 1.0 / sqrt(lam) : 0.0;
+#pragma unroll 8
+    for (int m = 0; m < MP; ++m) KT[m * LDT + tid] *= rs;
+    Ys[tid] = live ? y[i] * rs : 0.0;
+    __syncwarp();
+    tile_outer<MF, MF, false>(KT, KT, nullptr, warp, lane, cacc);
+    tile_col<MF>(KT, Ys, warp, lane, vacc);
+    __syncwarp();
+  }
+  frags_to_smem<MF, MF>(cacc, Cs, MP, warp, lane);
+  colfrag_to_smem<MF>(vacc, Cs + MP * MP, warp, lane);
+  for (int e = tid; e < MP * MP + MP; e += RB) part[(int64_t)blockIdx.x * (MP * MP + MP) + e] = Cs[e];
+}
+
+template <int MP>
+__global__ void __launch_bounds__(RB)
+fitc_row2_tile_kernel(const double* __restrict__ y, int64_t N, int D, int score, double invN,
+                      const double* __restrict__ small, const double* __restrict__ VgT, double* __restrict__ WgT,
+                      double* __restrict__ rowv, double* __restrict__ part) {
+  extern __shared__ double sh[];
+  constexpr int MF = MP / 8, LDM = TileCfg<MP>::LDM;
+  const SmallLayout lo(MP, D);
+  double* MatC = sh;                      // [MP][LDM]  B[k][n] = L_C^-1[n][k]
+  double* beta = MatC + MP * LDM;         // [MP]
+  double* WT = beta + MP;                 // [MP][LDT]
+  double* rbs = WT + (size_t)MP * LDT;    // [RB]
+  double* tbs = rbs + RB;                 // [RB]
+  double* Cs = tbs + RB;                  // [MP][MP] + [MP]
+  double* red = Cs + MP * MP + MP;        // [32]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  stage_mat<MP, true>(MatC, small + lo.lcinv, tid);
+  if (tid < MP) beta[tid] = small[lo.beta + tid];
+  for (int e = tid; e < MP * MP + MP; e += RB) Cs[e] = 0.0;
+  double racc[MF][MF][2], bacc[MF][2];
+#pragma unroll
+  for (int i = 0; i < MF; ++i) {
+    bacc[i][0] = bacc[i][1] = 0.0;
+#pragma unroll
+    for (int j = 0; j < MF; ++j) racc[i][j][0] = racc[i][j][1] = 0.0;
+  }
+  double obj = 0.0;
+  __syncthreads();
+  double* lamg = rowv;
+  double* lb0g = rowv + N;
+  double* rbg = rowv + 2 * N;
+  double* tbg = rowv + 3 * N;
+  double* alg = rowv + 4 * N;
+  double* dg = rowv + 5 * N;
+  for (int64_t base = (int64_t)blockIdx.x * RB; base < N; base += (int64_t)gridDim.x * RB) {
+    const int64_t i = base + tid;
+    const bool live = i < N;
+#pragma unroll 8
+    for (int m = 0; m < MP; ++m) WT[m * LDT + tid] = live ? VgT[(int64_t)m * N + i] : 0.0;
+    __syncwarp();
+    warp_tile_mm<MP>(WT, MatC, WT, warp, lane);                 // W = V L_C^-T
+    double rbar = 0.0, tbar = 0.0;
+    if (live) {
+      double r = 0.0, wb = 0.0;
+#pragma unroll 8
+      for (int m = 0; m < MP; ++m) {
+        const double w = WT[m * LDT + tid];
+        r = fma(w, w, r);
+        wb = fma(w, beta[m], wb);
+        WgT[(int64_t)m * N + i] = w;
+      }
+      const double lam = lamg[i], yi = y[i];
+      const double il = 1.0 / lam;
+      const double d = il - r * il * il;
+      const double alpha = (yi - wb) * il;
+      double abar, dbar, lb0 = 0.0;
+      if (score == GPS_CRPS) {
+        const double s2 = 1.0 / d, s = sqrt(s2), z = alpha * s;
+        const double tpm1 = erf(z * INV_SQRT2);
+        const double g = z * tpm1 + 2.0 * INV_SQRT_2PI * exp(-0.5 * z * z) - INV_SQRT_PI;
+        obj += s * g * invN;
+        abar = tpm1 * s2 * invN;
+        dbar = -(0.5 * s2 * s * g + 0.5 * tpm1 * alpha * s2 * s2) * invN;
+      } else if (score == GPS_LOGS) {
+        const double s2 = 1.0 / d;
+        obj += (0.5 * alpha * alpha * s2 - 0.5 * log(d) + HALF_LOG_2PI) * invN;
+        abar = alpha * s2 * invN;
+        dbar = -(0.5 * alpha * alpha * s2 * s2 + 0.5 * s2) * invN;
+      } else {
+        obj += 0.5 * log(lam) + 0.5 * yi * alpha;
+        abar = 0.5 * yi;
+        dbar = 0.0;
+        lb0 = 0.5 * il;
+      }
+      lb0 += dbar * (-il * il + 2.0 * r * il * il * il) - abar * alpha * il;
+      rbar = -dbar * il * il;
+      tbar = -abar * il;
+      lb0g[i] = lb0;
+      rbg[i] = rbar;
+      tbg[i] = tbar;
+      alg[i] = alpha;
+      dg[i] = d;
+    }
+    rbs[tid] = rbar;
+    tbs[tid] = tbar;
+    __syncwarp();
+    tile_outer<MF, MF, true>(WT, WT, rbs, warp, lane, racc);
+    tile_col<MF>(WT, tbs, warp, lane, bacc);
+    __syncwarp();
+  }
+  frags_to_smem<MF, MF>(racc, Cs, MP, warp, lane);
+  colfrag_to_smem<MF>(bacc, Cs + MP * MP, warp, lane);
+  const double o = block_sum(obj, red);
+  const int len = MP * MP + MP + 1;
+  for (int e = tid; e < MP * MP + MP; e += RB) part[(int64_t)blockIdx.x * len + e] = Cs[e];
+  if (tid == 0) part[(int64_t)blockIdx.x * len + MP * MP + MP] = o;
+}
+
+template <int MP, int NF>
+__global__ void __launch_bounds__(RB)
+fitc_row3_tile_kernel(const double* __restrict__ X, const double* __restrict__ y, int64_t N, int D, int M,
+                      const double* __restrict__ par, const double* __restrict__ small,
+                      const double* __restrict__ VgT, const double* __restrict__ WgT,
+                      const double* __restrict__ rowv, double* __restrict__ part) {
+  extern __shared__ double sh[];
+  constexpr int MF = MP / 8, LDM = TileCfg<MP>::LDM;
+  constexpr int PC = 8 * NF;
+  const SmallLayout lo(MP, D);
+  double* Us = sh;                          // [MP][D]
+  double* MatCb = Us + MP * D;              // [MP][LDM]  C_bar
+  double* MatLC = MatCb + MP * LDM;         // [MP][LDM]  B[k][n] = L_C^-1[k][n]
+  double* MatLA = MatLC + MP * LDM;         // [MP][LDM]  B[k][n] = L_A^-1[k][n]
+  double* beta = MatLA + MP * LDM;          // [MP]
+  double* bbar = beta + MP;                 // [MP]
+  double* vyb = bbar + MP;                  // [MP]
+  double* XsT = vyb + MP;                   // [PC][LDT]
+  double* VT = XsT + (size_t)PC * LDT;      // [MP][LDT]  V
+  double* WT = VT + (size_t)MP * LDT;       // [MP][LDT]  W -> W_bar -> V_bar
+  double* CT = WT + (size_t)MP * LDT;       // [MP][LDT]  C_bar V  ->  Kuf_bar -> G
+  double* gbs = CT + (size_t)MP * LDT;      // [D][RB]
+  double* Cs = gbs + (size_t)D * RB;        // [MP][MP] + [MP][PC]
+  double* red = Cs + MP * MP + MP * PC;     // [32]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int e = tid; e < MP * D; e += RB) Us[e] = small[lo.us + e];
+  stage_mat<MP, false>(MatCb, small + lo.cbar, tid);
+  stage_mat<MP, false>(MatLC, small + lo.lcinv, tid);
+  stage_mat<MP, false>(MatLA, small + lo.lainv, tid);
+  if (tid < MP) {
+    beta[tid] = small[lo.beta + tid];
+    bbar[tid] = small[lo.bbar + tid];
+    vyb[tid] = small[lo.vyb + tid];
+  }
+  for (int e = tid; e < MP * MP + MP * PC; e += RB) Cs[e] = 0.0;
+  for (int d = 0; d < D; ++d) gbs[d * RB + tid] = 0.0;
+  for (int c = D + 1; c < PC; ++c) XsT[c * LDT + tid] = 0.0;
+  double sacc[MF][MF][2], pacc[MF][NF][2];
+#pragma unroll
+  for (int i = 0; i < MF; ++i) {
+#pragma unroll
+    for (int j = 0; j < MF; ++j) sacc[i][j][0] = sacc[i][j][1] = 0.0;
+#pragma unroll
+    for (int j = 0; j < NF; ++j) pacc[i][j][0] = pacc[i][j][1] = 0.0;
+  }
+  double sum_lb = 0.0;
+  const double ea = par[0];
+  const double* lamg = rowv;
+  const double* lb0g = rowv + N;
+  const double* rbg = rowv + 2 * N;
+  const double* tbg = rowv + 3 * N;
+  __syncthreads();
+  for (int64_t base = (int64_t)blockIdx.x * RB; base < N; base += (int64_t)gridDim.x * RB) {
+    const int64_t i = base + tid;
+    const bool live = i < N;
+    for (int d = 0; d < D; ++d) XsT[d * LDT + tid] = live ? X[i * D + d] * par[2 + d] : 0.0;
+    XsT[D * LDT + tid] = live ? 1.0 : 0.0;
+#pragma unroll 8
+    for (int m = 0; m < MP; ++m) {
+      VT[m * LDT + tid] = live ? VgT[(int64_t)m * N + i] : 0.0;
+      WT[m * LDT + tid] = live ? WgT[(int64_t)m * N + i] : 0.0;
+    }
+    __syncwarp();
+    warp_tile_mm<MP>(VT, MatCb, CT, warp, lane);                // CV = V C_bar
+    const double lam = live ? lamg[i] : 1.0, yi = live ? y[i] : 0.0;
+    const double il = 1.0 / lam;
+    const double rbar = live ? rbg[i] : 0.0, tbar = live ? tbg[i] : 0.0;
+    double s1 = 0.0, bw = 0.0;
+#pragma unroll 8
+    for (int m = 0; m < MP; ++m) {
+      const double w = WT[m * LDT + tid];
+      s1 = fma(VT[m * LDT + tid], CT[m * LDT + tid], s1);
+      bw = fma(bbar[m], w, bw);
+      WT[m * LDT + tid] = fma(tbar, beta[m], 2.0 * rbar * w);   // W_bar
+    }
+    const double lb = live ? (lb0g[i] - bw * yi * il * il - s1 * il * il) : 0.0;
+    sum_lb += lb;
+    __syncwarp();
+    warp_tile_mm<MP>(WT, MatLC, WT, warp, lane);                // L_C^-T W_bar
+#pragma unroll 8
+    for (int m = 0; m < MP; ++m)
+      WT[m * LDT + tid] += vyb[m] * yi * il + 2.0 * CT[m * LDT + tid] * il - 2.0 * lb * VT[m * LDT + tid];   // V_bar
+    __syncwarp();
+    tile_outer<MF, MF, false>(WT, VT, nullptr, warp, lane, sacc);   // S += V_bar' V
+    warp_tile_mm<MP>(WT, MatLA, CT, warp, lane);                // Kuf_bar = V_bar L_A^-1
+#pragma unroll 4
+    for (int m = 0; m < MP; ++m) {                              // G = Kuf_bar o Kuf (independent exps overlap)
+      double r2 = 0.0;
+      for (int d = 0; d < D; ++d) {
+        const double df = Us[m * D + d] - XsT[d * LDT + tid];
+        r2 = fma(df, df, r2);
+      }
+      CT[m * LDT + tid] = (m < M && live) ? CT[m * LDT + tid] * ea * exp(-0.5 * r2) : 0.0;
+    }
+    for (int d = 0; d < D; ++d) {                               // g_b rows: one shared-memory update per d
+      const double xd = XsT[d * LDT + tid];
+      double g0 = 0.0, g1 = 0.0, g2 = 0.0, g3 = 0.0;
+#pragma unroll
+      for (int m = 0; m < MP; m += 4) {
+        const double d0 = Us[m * D + d] - xd, d1 = Us[(m + 1) * D + d] - xd;
+        const double d2 = Us[(m + 2) * D + d] - xd, d3 = Us[(m + 3) * D + d] - xd;
+        g0 = fma(CT[m * LDT + tid], d0 * d0, g0);
+        g1 = fma(CT[(m + 1) * LDT + tid], d1 * d1, g1);
+        g2 = fma(CT[(m + 2) * LDT + tid], d2 * d2, g2);
+        g3 = fma(CT[(m + 3) * LDT + tid], d3 * d3, g3);
+      }
+      gbs[d * RB + tid] += (g0 + g1) + (g2 + g3);
+    }
+    __syncwarp();
+    tile_outer<MF, NF, false>(CT, XsT, nullptr, warp, lane, pacc);  // P += G' [xs | 1]
+    __syncwarp();
+  }
+  frags_to_smem<MF, MF>(sacc, Cs, MP, warp, lane);
+  frags_to_smem<MF, NF>(pacc, Cs + MP * MP, PC, warp, lane);
+  const int len = MP * MP + MP * PC + D + 1;
+  double* out = part + (int64_t)blockIdx.x * len;
+  for (int e = tid; e < MP * MP + MP * PC; e += RB) out[e] = Cs[e];
+  for (int d = 0; d < D; ++d) {
+    const double sg = block_sum(gbs[d * RB + tid], red);
+    if (tid == 0) out[MP * MP + MP * PC + d] = sg;
+  }
+  const double sl = block_sum(sum_lb, red);
+  if (tid == 0) out[MP * MP + MP * PC + D] = sl;
+}
+
 // ---- LOO outputs and prediction ----------------------------------------------------------------------
 __global__ void fitc_loo_kernel(const double* __restrict__ y, const double* __restrict__ rowv, int64_t N,
                                 double* __restrict__ mean, double* __restrict__ var) {
@@ -900,6 +1296,47 @@ int run_row3(gps_ctx* ctx, double* part) {
   return GPS_OK;
 }
 
+size_t smem_row1t(int MP, int D) { return ((size_t)MP * D + MP * (MP + 4) + (size_t)D * LDT + (size_t)MP * LDT + RB + MP * MP + MP) * 8; }
+size_t smem_row2t(int MP) { return ((size_t)MP * (MP + 4) + MP + (size_t)MP * LDT + 2 * RB + MP * MP + MP + 32) * 8; }
+size_t smem_row3t(int MP, int D, int PC) {
+  return ((size_t)MP * D + 3 * MP * (MP + 4) + 3 * MP + (size_t)PC * LDT + 3 * (size_t)MP * LDT + (size_t)D * RB + MP * MP +
+          MP * PC + 32) * 8;
+}
+
+template <int MP>
+int run_row1t(gps_ctx* ctx, double* part) {
+  auto& f = ctx->fitc;
+  const size_t sm = smem_row1t(MP, ctx->D);
+  GPS_CHECK(set_smem(ctx, fitc_row1_tile_kernel<MP>, sm));
+  fitc_row1_tile_kernel<MP><<<f.grid, RB, sm, ctx->stream>>>(ctx->X.p, ctx->y.p, ctx->N, ctx->D, f.M, ctx->params.p,
+                                                             f.small.p, f.V.p, f.rowv.p, part);
+  GPS_LAUNCH_CHECK();
+  return GPS_OK;
+}
+
+template <int MP>
+int run_row2t(gps_ctx* ctx, double* part) {
+  auto& f = ctx->fitc;
+  const size_t sm = smem_row2t(MP);
+  GPS_CHECK(set_smem(ctx, fitc_row2_tile_kernel<MP>, sm));
+  fitc_row2_tile_kernel<MP><<<f.grid, RB, sm, ctx->stream>>>(ctx->y.p, ctx->N, ctx->D, f.score,
+                                                             1.0 / (double)f.world_n, f.small.p, f.V.p, f.W.p,
+                                                             f.rowv.p, part);
+  GPS_LAUNCH_CHECK();
+  return GPS_OK;
+}
+
+template <int MP, int NF>
+int run_row3t(gps_ctx* ctx, double* part) {
+  auto& f = ctx->fitc;
+  const size_t sm = smem_row3t(MP, ctx->D, 8 * NF);
+  GPS_CHECK(set_smem(ctx, (fitc_row3_tile_kernel<MP, NF>), sm));
+  fitc_row3_tile_kernel<MP, NF><<<f.grid, RB, sm, ctx->stream>>>(ctx->X.p, ctx->y.p, ctx->N, ctx->D, f.M,
+                                                                 ctx->params.p, f.small.p, f.V.p, f.W.p, f.rowv.p, part);
+  GPS_LAUNCH_CHECK();
+  return GPS_OK;
+}
+
 template <int MP>
 int run_pred(gps_ctx* ctx, const double* Xs, int64_t T, double* mean, double* var) {
   auto& f = ctx->fitc;
@@ -911,6 +1348,9 @@ int run_pred(gps_ctx* ctx, const double* Xs, int64_t T, double* mean, double* va
   return GPS_OK;
 }
 
+int pre_reduce(gps_ctx* ctx, const double** part, int* nblocks, int len);
+int pc_of(int D);
+
 template <int MP>
 int run_small0(gps_ctx* ctx, const double* dU) {
   auto& f = ctx->fitc;
@@ -921,14 +1361,18 @@ int run_small0(gps_ctx* ctx, const double* dU) {
 template <int MP>
 int run_small1(gps_ctx* ctx, const double* part, double* acc1) {
   auto& f = ctx->fitc;
-  fitc_small1_kernel<MP><<<1, 128, 0, ctx->stream>>>(part, f.grid, acc1, f.small.p, ctx->D, ctx->d_info);
+  int nb = f.grid;
+  if (part) GPS_CHECK(pre_reduce(ctx, &part, &nb, MP * MP + MP));
+  fitc_small1_kernel<MP><<<1, 128, 0, ctx->stream>>>(part, nb, acc1, f.small.p, ctx->D, ctx->d_info);
   GPS_LAUNCH_CHECK();
   return GPS_OK;
 }
 template <int MP>
 int run_small2(gps_ctx* ctx, const double* part, double* acc2) {
   auto& f = ctx->fitc;
-  fitc_small2_kernel<MP><<<1, 128, 0, ctx->stream>>>(part, f.grid, acc2, f.small.p, f.M, ctx->D, f.score);
+  int nb = f.grid;
+  if (part) GPS_CHECK(pre_reduce(ctx, &part, &nb, MP * MP + MP + 1));
+  fitc_small2_kernel<MP><<<1, 128, 0, ctx->stream>>>(part, nb, acc2, f.small.p, f.M, ctx->D, f.score);
   GPS_LAUNCH_CHECK();
   return GPS_OK;
 }
@@ -945,6 +1389,31 @@ int run_small3(gps_ctx* ctx, const double* part, const double* acc2, double* acc
   }
 
 int pc_of(int D) { return (D + 1 <= 8) ? 8 : 16; }
+
+// row passes: tile formulation (default) or the thread-per-row kernels (ctx->fitc_variant == 0)
+int do_row1(gps_ctx* ctx, double* part) {
+  auto& f = ctx->fitc;
+  if (f.tile) { MP_DISPATCH(f.MP, GPS_CHECK(run_row1t<MPC>(ctx, part))); }
+  else { MP_DISPATCH(f.MP, GPS_CHECK(run_row1<MPC>(ctx, part))); }
+  return GPS_OK;
+}
+int do_row2(gps_ctx* ctx, double* part) {
+  auto& f = ctx->fitc;
+  if (f.tile) { MP_DISPATCH(f.MP, GPS_CHECK(run_row2t<MPC>(ctx, part))); }
+  else { MP_DISPATCH(f.MP, GPS_CHECK(run_row2<MPC>(ctx, part))); }
+  return GPS_OK;
+}
+int do_row3(gps_ctx* ctx, double* part) {
+  auto& f = ctx->fitc;
+  if (pc_of(ctx->D) == 8) {
+    if (f.tile) { MP_DISPATCH(f.MP, GPS_CHECK((run_row3t<MPC, 1>(ctx, part)))); }
+    else { MP_DISPATCH(f.MP, GPS_CHECK((run_row3<MPC, 1>(ctx, part)))); }
+  } else {
+    if (f.tile) { MP_DISPATCH(f.MP, GPS_CHECK((run_row3t<MPC, 2>(ctx, part)))); }
+    else { MP_DISPATCH(f.MP, GPS_CHECK((run_row3<MPC, 2>(ctx, part)))); }
+  }
+  return GPS_OK;
+}
 int len1_of(int MP) { return MP * MP + MP; }
 int len2_of(int MP) { return MP * MP + MP + 1; }
 int len3_of(int MP, int D) { return MP * MP + MP * pc_of(D) + D + 1; }
@@ -952,13 +1421,32 @@ int len3_of(int MP, int D) { return MP * MP + MP * pc_of(D) + D + 1; }
 template <int MP>
 int run_small3(gps_ctx* ctx, const double* part, const double* acc2, double* acc3, double* out) {
   auto& f = ctx->fitc;
-  fitc_small3_kernel<MP><<<1, 128, 0, ctx->stream>>>(part, f.grid, acc2, acc3, f.small.p, ctx->params.p, f.M, ctx->D,
+  int nb = f.grid;
+  if (part) GPS_CHECK(pre_reduce(ctx, &part, &nb, MP * MP + MP * pc_of(ctx->D) + ctx->D + 1));
+  fitc_small3_kernel<MP><<<1, 128, 0, ctx->stream>>>(part, nb, acc2, acc3, f.small.p, ctx->params.p, f.M, ctx->D,
                                                      pc_of(ctx->D), f.score, (double)f.world_n, out);
   GPS_LAUNCH_CHECK();
   return GPS_OK;
 }
 
+// For large grids the partials are first summed in REDUCE_GROUPS slices by many CTAs; the
+// replicated kernels (or the final reduce) then only add REDUCE_GROUPS rows.
+constexpr int REDUCE_GROUPS = 16;
+int pre_reduce(gps_ctx* ctx, const double** part, int* nblocks, int len) {
+  auto& f = ctx->fitc;
+  if (*nblocks <= 8 * REDUCE_GROUPS) return GPS_OK;
+  const int per = (*nblocks + REDUCE_GROUPS - 1) / REDUCE_GROUPS;
+  dim3 grid((len + 127) / 128, REDUCE_GROUPS);
+  fitc_reduce_stage_kernel<<<grid, 128, 0, ctx->stream>>>(*part, *nblocks, len, per, f.part2.p);
+  GPS_LAUNCH_CHECK();
+  ctx->launches++;
+  *part = f.part2.p;
+  *nblocks = REDUCE_GROUPS;
+  return GPS_OK;
+}
+
 int reduce_to(gps_ctx* ctx, const double* part, int nblocks, int len, double* acc) {
+  GPS_CHECK(pre_reduce(ctx, &part, &nblocks, len));
   fitc_reduce_kernel<<<(len + 255) / 256, 256, 0, ctx->stream>>>(part, nblocks, len, acc);
   GPS_LAUNCH_CHECK();
   ctx->launches++;
@@ -993,6 +1481,7 @@ int gps_fitc_begin(gps_ctx* ctx, const double* theta, const double* U, int M, do
   const int64_t N = ctx->N;
   f.M = M; f.MP = MP; f.score = score; f.jitter = jitter; f.world_n = world_n > 0 ? world_n : N;
   f.begun = false; f.pass2_done = false;
+  f.tile = ctx->fitc_variant != 0;
   GPS_CHECK(gps_ensure(ctx, ctx->params, PAR_LEN));
   if (!ctx->d_info) GPS_CUDA(cudaMalloc(&ctx->d_info, sizeof(int)));
   GPS_CUDA(cudaMemsetAsync(ctx->d_info, 0, sizeof(int), ctx->stream));
@@ -1005,6 +1494,7 @@ int gps_fitc_begin(gps_ctx* ctx, const double* theta, const double* U, int M, do
   GPS_CHECK(gps_ensure(ctx, f.rowv, (size_t)6 * N));
   GPS_CHECK(gps_ensure(ctx, f.small, (size_t)lo.total + M * D + 8 + D + 2 + M * D));
   GPS_CHECK(gps_ensure(ctx, f.part, (size_t)f.grid * len3_of(MP, D)));
+  GPS_CHECK(gps_ensure(ctx, f.part2, (size_t)REDUCE_GROUPS * len3_of(MP, D)));
   GPS_CHECK(gps_ensure(ctx, f.acc1, len1_of(MP)));
   GPS_CHECK(gps_ensure(ctx, f.acc2, len2_of(MP)));
   GPS_CHECK(gps_ensure(ctx, f.acc3, len3_of(MP, D)));
@@ -1022,7 +1512,7 @@ int gps_fitc_pass1(gps_ctx* ctx, double* acc1) {
   auto& f = ctx->fitc;
   if (!f.begun) return gps_fail(ctx, GPS_ESTATE, "fitc_pass1: call gps_fitc_begin first");
   GPS_CUDA(cudaSetDevice(ctx->device));
-  MP_DISPATCH(f.MP, GPS_CHECK(run_row1<MPC>(ctx, f.part.p)));
+  GPS_CHECK(do_row1(ctx, f.part.p));
   ctx->launches++;
   GPS_CHECK(reduce_to(ctx, f.part.p, f.grid, len1_of(f.MP), acc1));
   GPS_CUDA(cudaStreamSynchronize(ctx->stream));   // acc1 is handed to the caller's collective
@@ -1035,7 +1525,7 @@ int gps_fitc_pass2(gps_ctx* ctx, const double* acc1, double* acc2) {
   if (!f.begun) return gps_fail(ctx, GPS_ESTATE, "fitc_pass2: call gps_fitc_begin first");
   GPS_CUDA(cudaSetDevice(ctx->device));
   MP_DISPATCH(f.MP, GPS_CHECK(run_small1<MPC>(ctx, nullptr, const_cast<double*>(acc1))));
-  MP_DISPATCH(f.MP, GPS_CHECK(run_row2<MPC>(ctx, f.part.p)));
+  GPS_CHECK(do_row2(ctx, f.part.p));
   ctx->launches += 2;
   GPS_CHECK(reduce_to(ctx, f.part.p, f.grid, len2_of(f.MP), acc2));
   GPS_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -1049,11 +1539,7 @@ int gps_fitc_pass3(gps_ctx* ctx, const double* acc2, double* acc3) {
   if (!f.pass2_done) return gps_fail(ctx, GPS_ESTATE, "fitc_pass3: pass 2 has not run");
   GPS_CUDA(cudaSetDevice(ctx->device));
   MP_DISPATCH(f.MP, GPS_CHECK(run_small2<MPC>(ctx, nullptr, const_cast<double*>(acc2))));
-  if (pc_of(ctx->D) == 8) {
-    MP_DISPATCH(f.MP, GPS_CHECK((run_row3<MPC, 1>(ctx, f.part.p))));
-  } else {
-    MP_DISPATCH(f.MP, GPS_CHECK((run_row3<MPC, 2>(ctx, f.part.p))));
-  }
+  GPS_CHECK(do_row3(ctx, f.part.p));
   ctx->launches += 2;
   GPS_CHECK(reduce_to(ctx, f.part.p, f.grid, len3_of(f.MP, ctx->D), acc3));
   GPS_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -1103,18 +1589,14 @@ int gps_fitc_eval(gps_ctx* ctx, const double* theta, const double* U, int M, dou
   // single GPU: the same row kernels; the per-block partials are summed inside the replicated
   // kernels (no separate reduce launches, no host synchronisation between the passes):
   // 7 launches per evaluation.
-  MP_DISPATCH(f.MP, GPS_CHECK(run_row1<MPC>(ctx, f.part.p)));
+  GPS_CHECK(do_row1(ctx, f.part.p));
   MP_DISPATCH(f.MP, GPS_CHECK(run_small1<MPC>(ctx, f.part.p, f.acc1.p)));
-  MP_DISPATCH(f.MP, GPS_CHECK(run_row2<MPC>(ctx, f.part.p)));
+  GPS_CHECK(do_row2(ctx, f.part.p));
   f.pass2_done = true;
   ctx->launches += 3;
   if (grad_theta || grad_U) {
     MP_DISPATCH(f.MP, GPS_CHECK(run_small2<MPC>(ctx, f.part.p, f.acc2.p)));
-    if (pc_of(ctx->D) == 8) {
-      MP_DISPATCH(f.MP, GPS_CHECK((run_row3<MPC, 1>(ctx, f.part.p))));
-    } else {
-      MP_DISPATCH(f.MP, GPS_CHECK((run_row3<MPC, 2>(ctx, f.part.p))));
-    }
+    GPS_CHECK(do_row3(ctx, f.part.p));
     ctx->launches += 2;
     return fitc_finish_impl(ctx, f.part.p, f.acc2.p, f.acc3.p, obj, grad_theta, grad_U);
   }
