@@ -39,7 +39,7 @@ struct GemmCfg {
   static constexpr int LD_MC_A = TM_ + 4, LD_MC_B = 128 + 4;     // [BK][rows+4]: (rows+4) % 16 == 4
   static constexpr int OPER_A = (TM_ * LD_KC > BK_ * LD_MC_A) ? TM_ * LD_KC : BK_ * LD_MC_A;
   static constexpr int OPER_B = (128 * LD_KC > BK_ * LD_MC_B) ? 128 * LD_KC : BK_ * LD_MC_B;
-  static constexpr int STAGE = OPER_A + OPER_B;                  // doubles per stage
+  static constexpr int STAGE = OPER_A + OPER_B + BK_;            // doubles per stage (+ the k-scaling slice)
   static constexpr size_t SMEM = (size_t)STAGES_ * STAGE * sizeof(double);
 };
 
@@ -117,6 +117,8 @@ gemm_tile_kernel(const double* __restrict__ A, int64_t lda, const double* __rest
     if (s < nk) {
       load_panel<Cfg, TM, A_MC>(smem + (size_t)s * STAGE, A, lda, t.a_row, t.k0 + s * BK, tid);
       load_panel<Cfg, 128, B_MC>(smem + (size_t)s * STAGE + OPER_A, B, ldb, t.b_row, t.k0 + s * BK, tid);
+      if (DVEC && tid < BK / 2)   // the stage's slice of the k-scaling vector rides in the same cp.async group
+        cp_async16(smem + (size_t)s * STAGE + OPER_A + Cfg::OPER_B + tid * 2, dvec + t.k0 + s * BK + tid * 2);
     }
     cp_async_commit();
   }
@@ -130,11 +132,13 @@ gemm_tile_kernel(const double* __restrict__ A, int64_t lda, const double* __rest
         double* sl = smem + (size_t)(nx % STAGES) * STAGE;
         load_panel<Cfg, TM, A_MC>(sl, A, lda, t.a_row, t.k0 + nx * BK, tid);
         load_panel<Cfg, 128, B_MC>(sl + OPER_A, B, ldb, t.b_row, t.k0 + nx * BK, tid);
+        if (DVEC && tid < BK / 2) cp_async16(sl + OPER_A + Cfg::OPER_B + tid * 2, dvec + t.k0 + nx * BK + tid * 2);
       }
       cp_async_commit();
     }
     const double* As = smem + (size_t)(kb % STAGES) * STAGE;
     const double* Bs = As + OPER_A;
+    const double* Ds = Bs + Cfg::OPER_B;
     if (Cfg::PIPE) {
       double a[2][MF], b[2][NF];
 #pragma unroll
@@ -152,7 +156,7 @@ gemm_tile_kernel(const double* __restrict__ A, int64_t lda, const double* __rest
           for (int i = 0; i < MF; ++i) a[nxt][i] = frag<Cfg, TM, A_MC>(As, wm * WROWS + i * 8 + g, k);
         }
         if (DVEC) {
-          const double dv = __ldg(dvec + t.k0 + kb * BK + kk * 4 + tq);
+          const double dv = Ds[kk * 4 + tq];
 #pragma unroll
           for (int i = 0; i < MF; ++i) a[cur][i] *= dv;
         }
@@ -171,7 +175,7 @@ gemm_tile_kernel(const double* __restrict__ A, int64_t lda, const double* __rest
 #pragma unroll
         for (int j = 0; j < NF; ++j) b[j] = frag<Cfg, 128, B_MC>(Bs, wn * WCOLS + j * 8 + g, k);
         if (DVEC) {
-          const double dv = __ldg(dvec + t.k0 + kb * BK + k);
+          const double dv = Ds[k];
           if (MF <= NF) {
 #pragma unroll
             for (int i = 0; i < MF; ++i) a[i] *= dv;
