@@ -14,7 +14,7 @@ the reference again.  The reference holds no golden vectors of its own
 (SURVEY.md §4, §8c): these files are the pin.
 
 Reference line ranges replayed (file:first-last):
-  full GP   CRPS  KF:239-245   NLML KF:329-334   logs KF:416-424
+  full GP   CRPS  KF:239-245   NLML KF:329-334   logs KF:416-424   4-fold DSS KF:499-538
             predict + metrics  KF:267-292
   FITC      CRPS  K20:222-234  NLML K20:329-340  logs K20:434-447
             predict + metrics  K20:270-296
@@ -104,6 +104,16 @@ def run_case(name, script, X, y, Xs, ys, theta, d_b, U=None):
         if score in ("crps", "logs"):
             rec["loo_mean_" + score] = ns["mean_term"].detach().numpy().copy()
             rec["loo_var_" + score] = ns["cov_term"].detach().numpy().copy()
+    # 4-fold DSS objective (KF:499-538); the script sizes every fold with index1, so it needs 4 | N
+    if script == "KF" and X.shape[0] % 4 == 0:
+        lv = leaves(theta, d_b, U)
+        ref_shim.run_block(ns, "KF", 499, 538, **common, **lv)
+        obj = ns["dss_ave"]
+        rec["obj_dss"] = np.float64(obj.detach().numpy().reshape(-1)[0])
+        g = grads_of(obj, lv)
+        rec["grad_k_dss"] = g["para_k"]
+        rec["grad_l_dss"] = g["para_l"]
+        rec["grad_noise_dss"] = g["para_noise"]
     # prediction + test metrics with the same hyper-parameters
     lv = leaves(theta, d_b, U)
     with torch.no_grad():

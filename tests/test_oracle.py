@@ -119,3 +119,13 @@ def test_woodbury_predict(name):
     mean, var = WB.fitc_predict(g["X"], g["y"], g["U"], g["Xs"], g["theta"])
     assert relerr(mean, g["pred_mean"]) <= 1e-8
     assert relerr(var, g["pred_var"]) <= 1e-7
+
+
+# ---- 4-fold DSS (SURVEY §8f "next" #1, full GP: KF:499-538)
+@pytest.mark.parametrize("name", [n for n in golden_names(("c3",)) if "ragged" not in n])
+def test_full_dss_obj_grad(name):
+    g = load_golden(name)
+    assert "obj_dss" in g
+    val, grad = O.full_dss_obj_grad(g["X"], g["y"], g["theta"])
+    assert abs(val - g["obj_dss"]) <= OBJ_TOL * abs(g["obj_dss"])
+    assert relerr(grad, grad_vector(g, "dss")) <= GRAD_TOL
