@@ -24,7 +24,8 @@ import gpscore_b200.api as gp  # noqa: E402
 from gpscore_b200 import synth  # noqa: E402
 
 # (score, iterations, learning rate, learning rate of the inducing inputs) as in the scripts
-FULL_RUNS = [("crps", 400, 1.0, None), ("nlml", 400, 0.0005, None), ("logs", 500, 0.05, None)]         # KF:220,238 / 312,328 / 405,415
+FULL_RUNS = [("crps", 400, 1.0, None), ("nlml", 400, 0.0005, None), ("logs", 500, 0.05, None),         # KF:220,238 / 312,328 / 405,415
+             ("dss", 150, 0.001, None)]                                                                   # KF:487,498 (4-fold DSS)
 FITC_RUNS = [("crps", 2000, 1.0, 1.0), ("nlml", 3000, 0.0001, 0.001), ("logs", 3000, 0.2, 0.2)]          # K20:207,220 / 315,326 / 417,430
 
 

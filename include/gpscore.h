@@ -38,8 +38,8 @@ enum { GPS_OK = 0, GPS_EINVAL = 1, GPS_ECUDA = 2, GPS_ENOTPD = 3, GPS_ENODEVICE 
        GPS_ESTATE = 6 };
 
 /* score selector: LOO-CRPS (KF:245), LOO log score (KF:424), negative log marginal
- * likelihood (KF:331-334) */
-enum { GPS_CRPS = 0, GPS_LOGS = 1, GPS_NLML = 2 };
+ * likelihood (KF:331-334), 4-fold block-LOO DSS (KF:499-538; full GP only, needs 4 | N) */
+enum { GPS_CRPS = 0, GPS_LOGS = 1, GPS_NLML = 2, GPS_DSS = 3 };
 
 /* ---- context ------------------------------------------------------------------------------- */
 int gps_create(int device, gps_ctx** out);

@@ -346,8 +346,8 @@ class _FusedObjective(torch.autograd.Function):
         fctx.grads = (g, gU)
         fctx.meta = (pk, pl, pn, U)
         out = torch.tensor(val, dtype=pk.dtype, device=pk.device)
-        if score == "nlml":
-            out = out.reshape(1, 1)  # Neg_logL is a [1, 1] tensor in the scripts (KF:334)
+        if score in ("nlml", "dss"):
+            out = out.reshape(1, 1)  # Neg_logL / dss_ave come out of a [1, 1] product in the scripts (KF:334, KF:107)
         return out
 
     @staticmethod

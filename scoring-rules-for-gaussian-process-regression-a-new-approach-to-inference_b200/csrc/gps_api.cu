@@ -182,7 +182,7 @@ void gps_destroy(gps_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  DevBuf* bufs[] = {&ctx->X, &ctx->y, &ctx->Kb, &ctx->Xb, &ctx->Sb, &ctx->vecs, &ctx->red, &ctx->params,
+  DevBuf* bufs[] = {&ctx->X, &ctx->y, &ctx->Kb, &ctx->Xb, &ctx->Sb, &ctx->vecs, &ctx->red, &ctx->params, &ctx->Gb, &ctx->fold_vecs,
                     &ctx->fitc.V, &ctx->fitc.W, &ctx->fitc.rowv, &ctx->fitc.small, &ctx->fitc.part, &ctx->fitc.part2,
                     &ctx->fitc.acc1, &ctx->fitc.acc2, &ctx->fitc.acc3, &ctx->stage[0], &ctx->stage[1],
                     &ctx->stage[2], &ctx->stage[3]};
@@ -194,6 +194,19 @@ void gps_destroy(gps_ctx* ctx) {
   for (auto& pr : ctx->gemm_events) {
     cudaEventDestroy(pr.first);
     cudaEventDestroy(pr.second);
+  }
+  if (ctx->fold_ctx) {
+    gps_ctx* ch = ctx->fold_ctx;
+    ch->stream = nullptr;
+    ch->own_stream = nullptr;
+    DevBuf* cb[] = {&ch->Kb, &ch->Xb, &ch->Sb, &ch->vecs, &ch->red, &ch->params};
+    for (DevBuf* b : cb)
+      if (b->p) cudaFree(b->p);
+    if (ch->d_info) cudaFree(ch->d_info);
+    if (ch->d_tasks) cudaFree(ch->d_tasks);
+    for (auto e : ch->potrf_events) cudaEventDestroy(e);
+    if (ch->panel_stream) cudaStreamDestroy(ch->panel_stream);
+    delete ch;
   }
   for (auto e : ctx->potrf_events) cudaEventDestroy(e);
   for (auto e : ctx->stage_ev) if (e) cudaEventDestroy(e);
@@ -246,7 +259,7 @@ int gps_set_data(gps_ctx* ctx, const double* X, const double* y, int64_t N, int 
 int gps_full_eval(gps_ctx* ctx, const double* theta, int score, double* obj, double* grad) {
   if (!ctx) return GPS_EINVAL;
   if (ctx->N == 0) return gps_fail(ctx, GPS_ESTATE, "full_eval: call gps_set_data first");
-  if (!theta || !obj || score < GPS_CRPS || score > GPS_NLML) return gps_fail(ctx, GPS_EINVAL, "full_eval: bad arguments");
+  if (!theta || !obj || score < GPS_CRPS || score > GPS_DSS) return gps_fail(ctx, GPS_EINVAL, "full_eval: bad arguments");
   GPS_CUDA(cudaSetDevice(ctx->device));
   const int64_t N = ctx->N, Np = ctx->Np;
   const int D = ctx->D;
@@ -259,7 +272,10 @@ int gps_full_eval(gps_ctx* ctx, const double* theta, int score, double* obj, dou
   double* par = ctx->params.p;
   bool stages_full = false;
   ctx->stage_valid = false;
-  if (score != GPS_NLML) {
+  if (score == GPS_DSS) {
+    ctx->loo_valid = false;
+    GPS_CHECK(gps_full_dss(ctx, par + PAR_OBJ, par + PAR_GSUM, grad != nullptr));
+  } else if (score != GPS_NLML) {
     GPS_CHECK(gps_diag_extract(ctx, ctx->Kb.p, Np, v + V_D * Np, 0));
     GPS_CHECK(gps_loo_score(ctx, score, N, Np, v + V_ALPHA * Np, v + V_D * Np, ctx->y.p, v + V_ABAR * Np,
                             v + V_DBAR * Np, v + V_LOOM * Np, v + V_LOOV * Np, par + PAR_OBJ));

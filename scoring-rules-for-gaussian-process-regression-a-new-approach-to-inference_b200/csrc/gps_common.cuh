@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -62,6 +63,9 @@ struct gps_ctx {
   DevBuf Xb;       // L^-1 (lower block triangle; diagonal blocks fully defined)
   DevBuf Sb;       // scratch for TRTRI, then S = K^-1 diag(dbar) K^-1 (lower tiles)
   DevBuf vecs;     // alpha, d, abar, dbar, u, loo_mean, loo_var, logdiag : 8 x Np
+  DevBuf Gb;       // block-diagonal Gamma of the 4-fold DSS gradient (allocated on first use)
+  DevBuf fold_vecs;
+  gps_ctx* fold_ctx = nullptr;   // child context for the N/4-sized fold factorisations (DSS)
   DevBuf red;      // reduction scratch
   DevBuf params;   // device copy of theta-derived parameters
   int* d_info = nullptr;       // device: first failing pivot (0 = ok)
@@ -122,6 +126,7 @@ int gps_ensure_ws(gps_ctx* ctx, int64_t Np);
 int gps_upload_params(gps_ctx* ctx, const double* theta, int D, double* ea_out, double* sn2_out);
 int gps_upload_tasks2(gps_ctx* ctx, const std::vector<GemmTask>& h);
 int gps_factor_and_invert(gps_ctx* ctx, bool want_logdet);
+int gps_full_dss(gps_ctx* ctx, double* par_obj, double* par_gsum, bool want_grad);
 // offsets (doubles) into ctx->params and rows of ctx->vecs
 constexpr int PAR_OBJ = 128;
 constexpr int PAR_GSUM = 136;
