@@ -202,6 +202,53 @@ def dss(m, c, shape1, y):
                  + 0.5 * (r.T @ cho_solve((cf, low), r)).item())
 
 
+def _block_dL_dK(K, y, kind, folds=4):
+    """Value and W = dL/dK of the 4-fold block-LOO objectives on a matrix K that already includes the
+    noise: kind "dss" (KF:499-538, K20:538-582) or "kc" = block CRPS (K20:669-714).  With B = K^-1,
+    C_f = B_ff^-1: m_f = y_f - C_f (B y)_f, cov_f = C_f (dss) or diag(C_f) (kc)."""
+    n = K.shape[0]
+    if n % folds:
+        raise ValueError("the reference's fold code needs %d | N" % folds)
+    B = chol_solve(np.eye(n), K)
+    alpha = B @ y
+    nf = n // folds
+    val = 0.0
+    Gamma = np.zeros((n, n))
+    abar = np.zeros((n, 1))
+    for f in range(folds):
+        sl = slice(f * nf, (f + 1) * nf)
+        cf, low = cho_factor(B[sl, sl], lower=True)
+        Cf = cho_solve((cf, low), np.eye(nf))
+        if kind == "dss":
+            ab = Cf @ alpha[sl]
+            val += 0.5 * nf * math.log(2 * math.pi) - np.sum(np.log(np.diag(cf))) + 0.5 * (alpha[sl].T @ ab).item()
+            Gamma[sl, sl] = -0.5 * (Cf + ab @ ab.T)
+            abar[sl] = ab
+        else:
+            m = y[sl] - Cf @ alpha[sl]
+            c = np.diag(Cf).reshape(-1, 1)
+            sd = np.sqrt(c)
+            z = (y[sl] - m) / sd
+            val += float(np.mean(sd * (z * (2 * _Phi(z) - 1) + 2 * _phi(z) - 1 / math.sqrt(math.pi))))
+            mbar = -(2 * _Phi(z) - 1) / nf
+            cbar = (2 * _phi(z) - 1 / math.sqrt(math.pi)) / (2 * sd) / nf
+            Cbar = np.diag(cbar.ravel()) - 0.5 * (mbar @ alpha[sl].T + alpha[sl] @ mbar.T)
+            Gamma[sl, sl] = -Cf @ Cbar @ Cf
+            abar[sl] = -Cf @ mbar
+    u = B @ abar
+    W = -(B @ Gamma @ B + 0.5 * (u @ alpha.T + alpha @ u.T))
+    return float(val), W
+
+
+def full_block_obj_grad(X, y, theta, kind):
+    """4-fold DSS / kc objective and gradient for the full GP."""
+    a, b, c = _split(theta)
+    Kf = ARD(X, X, a, b)
+    val, W = _block_dL_dK(Kf + math.exp(c) * np.eye(X.shape[0]), y, kind)
+    ga, gb, _ = _kernel_param_grads(W, Kf, X, X, b, True)
+    return val, np.concatenate([[ga], gb, [math.exp(c) * np.trace(W)]])
+
+
 def full_dss_obj_grad(X, y, theta, folds=4):
     """KF:499-538: 4-fold block-LOO DSS.  With B = K^-1 the fold predictive is
     m_f = y_f - B_ff^-1 (B y)_f, cov_f = B_ff^-1 (KF:508-530), so
@@ -268,7 +315,10 @@ def fitc_obj_grad(X, y, U, theta, score, jitter=JITTER):
     Q_ff = Kuf.T @ AiKuf
     lam = math.exp(a) - np.diag(Q_ff) + math.exp(c)   # diag(k_ff) = e^a
     bigQ = Q_ff + np.diag(lam)        # K20:225-229
-    val, W, _, _ = _dL_dK(bigQ, y, score)
+    if score in ("dss", "kc"):
+        val, W = _block_dL_dK(bigQ, y, score)   # K20:538-582, K20:669-714
+    else:
+        val, W, _, _ = _dL_dK(bigQ, y, score)
     Wd = np.diag(W).copy()
     Wq = W - np.diag(Wd)              # dL/dQ_ff: the diagonal of big_Q does not depend on Q_ff
     T = AiKuf @ Wq                    # M x N

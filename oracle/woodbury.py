@@ -163,3 +163,107 @@ def full_obj_grad(X, y, theta, score):
     """Closed-form full GP (SURVEY App. A.1) — identical algorithm to the oracle's dense path;
     re-exported so the CPU baseline has one entry point per model."""
     return O.full_obj_grad(X, y, theta, score)
+
+
+def fitc_block_obj_grad(X, y, U, theta, kind, jitter=O.JITTER, folds=4):
+    """4-fold block-LOO objectives of the FITC model in O(N M^2): "dss" (K20:538-582) and "kc" = block
+    CRPS (K20:669-714).  With B = big_Q^-1 = Lam^-1 - Lam^-1 W' W Lam^-1 the fold block is
+    B_ff = Lam_f^-1 - (W_f Lam_f^-1)'(W_f Lam_f^-1), so by Woodbury again
+        B_ff^-1 = Lam_f + W_f' H_f^-1 W_f,   H_f = I - W_f Lam_f^-1 W_f'   (M x M per fold),
+        log|B_ff| = -sum log lam_i + log|H_f|,
+    and the fold predictive of row i is  m_i = y_i - lam_i alpha_i - W_i' h_f,  c_i = lam_i + W_i' H_f^-1 W_i
+    with g_f = sum_{i in f} W_i alpha_i, h_f = H_f^-1 g_f.  The adjoint re-enters the three-pass chain
+    of fitc_obj_grad through per-row seeds (alpha_bar_i, lam_bar_i, D_i = dL/dW_i direct):
+        S_W = beta beta_bar' + beta_bar beta' + sum_i D_i W_i',   W_bar_i = t_bar_i beta + D_i."""
+    a, b, c = O._split(theta)
+    n, D = X.shape
+    m = U.shape[0]
+    if n % folds:
+        raise ValueError("the reference's fold code needs %d | N" % folds)
+    nf = n // folds
+    ell = np.exp(np.asarray(b, dtype=np.float64).ravel())
+    if ell.size == 1:
+        ell = np.full(D, ell[0])
+    ea, sn2 = math.exp(a), math.exp(c)
+    y = y.reshape(-1)
+    I = np.eye(m)
+    Kuu = _kern(U, U, a, ell)
+    LA = cholesky(Kuu + jitter * I, lower=True)
+    Kuf = _kern(U, X, a, ell)
+    V = solve_triangular(LA, Kuf, lower=True)
+    lam = ea - np.sum(V * V, axis=0) + sn2
+    LC = cholesky(I + (V / lam) @ V.T, lower=True)
+    beta = solve_triangular(LC, V @ (y / lam), lower=True)
+    W = solve_triangular(LC, V, lower=True)
+    alpha = (y - W.T @ beta) / lam
+    # ---- per-fold M x M quantities (pass 2 reductions) --------------------------------------------
+    obj = 0.0
+    abar = np.zeros(n)
+    lam_bar = np.zeros(n)
+    Dmat = np.zeros((m, n))              # D_i
+    GW = np.zeros((m, m))
+    beta_bar = np.zeros(m)
+    for f in range(folds):
+        sl = slice(f * nf, (f + 1) * nf)
+        Wf, lf, af, yf = W[:, sl], lam[sl], alpha[sl], y[sl]
+        Pf = (Wf / lf) @ Wf.T                     # I - H_f
+        H = I - Pf
+        g = Wf @ af
+        LH = cholesky(H, lower=True)
+        h = solve_triangular(LH, solve_triangular(LH, g, lower=True), lower=True, trans="T")
+        Hinv = solve_triangular(LH, solve_triangular(LH, I, lower=True), lower=True, trans="T")
+        if kind == "dss":
+            obj += 0.5 * nf * math.log(2 * math.pi) + 0.5 * np.sum(np.log(lf)) - np.sum(np.log(np.diag(LH))) \
+                + 0.5 * np.sum(lf * af * af) + 0.5 * float(g @ h)
+            Hhat = -0.5 * Hinv - 0.5 * np.outer(h, h)
+            abar[sl] = lf * af + Wf.T @ h
+            lam_bar[sl] = 0.5 / lf + 0.5 * af * af + np.sum(Wf * (Hhat @ Wf), axis=0) / lf ** 2
+            Dmat[:, sl] = -2.0 * (Hhat @ Wf) / lf + np.outer(h, af)
+            GW += -2.0 * Hhat @ Pf + np.outer(h, g)
+            beta_bar += -h
+        else:
+            HiW = Hinv @ Wf                                   # H_f^-1 W_i
+            mu = yf - lf * af - Wf.T @ h
+            cv = lf + np.sum(Wf * HiW, axis=0)
+            sd = np.sqrt(cv)
+            z = (yf - mu) / sd
+            tpm1 = 2 * O._Phi(z) - 1
+            obj += float(np.mean(sd * (z * tpm1 + 2 * O._phi(z) - 1 / math.sqrt(math.pi))))
+            mbar = -tpm1 / nf
+            cbar = (2 * O._phi(z) - 1 / math.sqrt(math.pi)) / (2 * sd) / nf
+            # pass 2b reductions
+            hbar = -(Wf @ mbar)
+            E = (Wf * cbar) @ Wf.T                            # sum cbar_i W_i W_i'
+            gbar = Hinv @ hbar
+            Hbar = -Hinv @ E @ Hinv - 0.5 * (np.outer(gbar, h) + np.outer(h, gbar))
+            abar[sl] = -mbar * lf + Wf.T @ gbar
+            lam_bar[sl] = -mbar * af + cbar + np.sum(Wf * (Hbar @ Wf), axis=0) / lf ** 2
+            Dmat[:, sl] = -np.outer(h, mbar) + 2.0 * HiW * cbar + np.outer(gbar, af) - 2.0 * (Hbar @ Wf) / lf
+            GW += np.outer(h, hbar) + 2.0 * Hinv @ E + np.outer(gbar, g) - 2.0 * Hbar @ Pf
+            beta_bar += -hbar - Pf @ gbar
+    # ---- re-enter the three-pass adjoint ------------------------------------------------------------
+    tbar = -abar / lam
+    lam_bar = lam_bar - abar * alpha / lam
+    SW = np.outer(beta, beta_bar) + np.outer(beta_bar, beta) + GW
+    LC_bar = -np.tril(solve_triangular(LC, SW, lower=True, trans="T"))
+    C_bar = _phi_adj(LC, LC_bar)
+    vy_bar = solve_triangular(LC, beta_bar, lower=True, trans="T")
+    CV = C_bar @ V
+    lam_bar = lam_bar - (beta_bar @ W) * y / lam ** 2 - np.sum(V * CV, axis=0) / lam ** 2
+    Wbar = np.outer(beta, tbar) + Dmat
+    Vbar = solve_triangular(LC, Wbar, lower=True, trans="T") + np.outer(vy_bar, y / lam) + 2.0 * CV / lam - 2.0 * V * lam_bar
+    Kuf_bar = solve_triangular(LA, Vbar, lower=True, trans="T")
+    S = Vbar @ V.T
+    G = Kuf_bar * Kuf
+    LA_bar = -np.tril(solve_triangular(LA, S, lower=True, trans="T"))
+    G2 = _phi_adj(LA, LA_bar) * Kuu
+    g_a = ea * lam_bar.sum() + G.sum() + G2.sum()
+    g_c = sn2 * lam_bar.sum()
+    g_b = np.zeros(D)
+    g_U = np.zeros((m, D))
+    for dd in range(D):
+        dux = U[:, dd][:, None] - X[:, dd][None, :]
+        duu = U[:, dd][:, None] - U[:, dd][None, :]
+        g_b[dd] = (np.sum(G * dux * dux) + np.sum(G2 * duu * duu)) / ell[dd] ** 2
+        g_U[:, dd] = (-np.sum(G * dux, axis=1) - 2.0 * np.sum(G2 * duu, axis=1)) / ell[dd] ** 2
+    return float(obj), np.concatenate([[g_a], g_b, [g_c]]), g_U

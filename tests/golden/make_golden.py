@@ -16,7 +16,7 @@ the reference again.  The reference holds no golden vectors of its own
 Reference line ranges replayed (file:first-last):
   full GP   CRPS  KF:239-245   NLML KF:329-334   logs KF:416-424   4-fold DSS KF:499-538
             predict + metrics  KF:267-292
-  FITC      CRPS  K20:222-234  NLML K20:329-340  logs K20:434-447
+  FITC      CRPS  K20:222-234  NLML K20:329-340  logs K20:434-447  4-fold DSS K20:538-582  kc K20:669-714
             predict + metrics  K20:270-296
   SIMPLE    data  SF:161-181 / SC:161-181 (torch.manual_seed(0));
             loops SF:206-213, SF:291-296, SF:384-392 / SC:208-220, SC:321-333, SC:441-452
@@ -114,6 +114,18 @@ def run_case(name, script, X, y, Xs, ys, theta, d_b, U=None):
         rec["grad_k_dss"] = g["para_k"]
         rec["grad_l_dss"] = g["para_l"]
         rec["grad_noise_dss"] = g["para_noise"]
+    # FITC 4-fold DSS (K20:538-582) and block-CRPS "kc" (K20:669-714); same 4 | N requirement
+    if script == "K20" and X.shape[0] % 4 == 0:
+        for score, (first, last, res) in {"dss": (538, 582, "dss_ave"), "kc": (669, 714, "kc_ave")}.items():
+            lv = leaves(theta, d_b, U)
+            ref_shim.run_block(ns, "K20", first, last, **common, **lv)
+            obj = ns[res]
+            rec["obj_" + score] = np.float64(obj.detach().numpy().reshape(-1)[0])
+            g = grads_of(obj, lv)
+            rec["grad_k_" + score] = g["para_k"]
+            rec["grad_l_" + score] = g["para_l"]
+            rec["grad_noise_" + score] = g["para_noise"]
+            rec["grad_u_" + score] = g["inducing_x"]
     # prediction + test metrics with the same hyper-parameters
     lv = leaves(theta, d_b, U)
     with torch.no_grad():

@@ -129,3 +129,19 @@ def test_full_dss_obj_grad(name):
     val, grad = O.full_dss_obj_grad(g["X"], g["y"], g["theta"])
     assert abs(val - g["obj_dss"]) <= OBJ_TOL * abs(g["obj_dss"])
     assert relerr(grad, grad_vector(g, "dss")) <= GRAD_TOL
+
+
+# ---- 4-fold block objectives of the FITC model: DSS (K20:538-582) and kc = block CRPS (K20:669-714)
+@pytest.mark.parametrize("name", [n for n in golden_names(("c4",)) if "ragged" not in n])
+@pytest.mark.parametrize("kind", ["dss", "kc"])
+def test_fitc_block_objectives(name, kind):
+    g = load_golden(name)
+    ref = grad_vector(g, kind)
+    for fn in (lambda: O.fitc_obj_grad(g["X"], g["y"], g["U"], g["theta"], kind)[:3],           # dense
+               lambda: WB.fitc_block_obj_grad(g["X"], g["y"], g["U"], g["theta"], kind)):      # Woodbury
+        val, grad, gU = fn()
+        if int(g["d_b"]) == 1 and g["X"].shape[1] > 1:
+            grad = np.concatenate([[grad[0]], [grad[1:-1].sum()], [grad[-1]]])
+        assert abs(val - g["obj_" + kind]) <= OBJ_TOL * abs(g["obj_" + kind])
+        assert relerr(grad, ref) <= GRAD_TOL
+        assert relerr(gU, g["grad_u_" + kind]) <= GRAD_TOL
