@@ -38,7 +38,8 @@ enum { GPS_OK = 0, GPS_EINVAL = 1, GPS_ECUDA = 2, GPS_ENOTPD = 3, GPS_ENODEVICE 
        GPS_ESTATE = 6 };
 
 /* score selector: LOO-CRPS (KF:245), LOO log score (KF:424), negative log marginal
- * likelihood (KF:331-334), 4-fold block-LOO DSS (KF:499-538; full GP only, needs 4 | N) */
+ * likelihood (KF:331-334), 4-fold block-LOO DSS (KF:499-538, K20:538-582; needs 4 | N; the FITC
+ * version runs through gps_fitc_eval on one GPU) */
 enum { GPS_CRPS = 0, GPS_LOGS = 1, GPS_NLML = 2, GPS_DSS = 3 };
 
 /* ---- context ------------------------------------------------------------------------------- */

@@ -183,7 +183,7 @@ void gps_destroy(gps_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   DevBuf* bufs[] = {&ctx->X, &ctx->y, &ctx->Kb, &ctx->Xb, &ctx->Sb, &ctx->vecs, &ctx->red, &ctx->params, &ctx->Gb, &ctx->fold_vecs,
-                    &ctx->fitc.V, &ctx->fitc.W, &ctx->fitc.rowv, &ctx->fitc.small, &ctx->fitc.part, &ctx->fitc.part2,
+                    &ctx->fitc.V, &ctx->fitc.W, &ctx->fitc.rowv, &ctx->fitc.small, &ctx->fitc.part, &ctx->fitc.part2, &ctx->fitc.accf,
                     &ctx->fitc.acc1, &ctx->fitc.acc2, &ctx->fitc.acc3, &ctx->stage[0], &ctx->stage[1],
                     &ctx->stage[2], &ctx->stage[3]};
   for (DevBuf* b : bufs)

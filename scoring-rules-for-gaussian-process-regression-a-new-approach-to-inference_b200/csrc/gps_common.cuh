@@ -96,7 +96,8 @@ struct gps_ctx {
     DevBuf part;          // per-block partial accumulators
     DevBuf part2;         // first-stage sums of the partials (large grids)
     DevBuf acc1, acc2, acc3;  // single-GPU accumulators
-    bool begun = false, pass2_done = false, tile = true;
+    bool begun = false, pass2_done = false, tile = true, loo_ok = false;
+    DevBuf accf;          // per-fold accumulators of the block objectives
     std::vector<double> host_out;
   } fitc;
 };

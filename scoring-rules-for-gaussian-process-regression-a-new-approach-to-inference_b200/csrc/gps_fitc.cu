@@ -34,7 +34,7 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
 
 // layout of the replicated small-matrix buffer (doubles), MP-strided
 struct SmallLayout {
-  int us, la, lai, kuu, lc, lci, beta, bbar, cbar, vyb, lainv, lcinv, total;
+  int us, la, lai, kuu, lc, lci, beta, bbar, cbar, vyb, lainv, lcinv, fh, fhv, total;
   __host__ __device__ SmallLayout(int MP, int D) {
     int o = 0;
     us = o;   o += MP * D;
@@ -49,6 +49,8 @@ struct SmallLayout {
     vyb = o;  o += MP;
     lainv = o; o += MP * MP;
     lcinv = o; o += MP * MP;
+    fh = o;    o += 4 * MP * MP;   // per-fold Hhat_f (block objectives)
+    fhv = o;   o += 4 * MP;        // per-fold h_f
     total = o;
   }
 };
@@ -1060,12 +1062,17 @@ fitc_row2_tile_kernel(const double* __restrict__ y, int64_t N, int D, int score,
   if (tid == 0) part[(int64_t)blockIdx.x * len + MP * MP + MP] = o;
 }
 
-template <int MP, int NF>
+struct FoldGeom { int64_t lo[4], hi[4]; };   // local row range of each of the four folds
+
+// OBJ = 0: LOO scores (seeds lambda_bar0, r_bar, t_bar come from pass 2 through rowv)
+// OBJ = 1: 4-fold DSS: blockIdx.y is the fold; the seeds are formed here from (lambda, alpha, W)
+//          and the fold's Hhat_f, h_f:  abar = lam alpha + W'h,  D = -2 Hhat W / lam + alpha h.
+template <int MP, int NF, int OBJ>
 __global__ void __launch_bounds__(RB)
 fitc_row3_tile_kernel(const double* __restrict__ X, const double* __restrict__ y, int64_t N, int D, int M,
                       const double* __restrict__ par, const double* __restrict__ small,
                       const double* __restrict__ VgT, const double* __restrict__ WgT,
-                      const double* __restrict__ rowv, double* __restrict__ part) {
+                      const double* __restrict__ rowv, double* __restrict__ part, FoldGeom fg) {
   extern __shared__ double sh[];
   constexpr int MF = MP / 8, LDM = TileCfg<MP>::LDM;
   constexpr int PC = 8 * NF;
@@ -1084,7 +1091,15 @@ fitc_row3_tile_kernel(const double* __restrict__ X, const double* __restrict__ y
   double* gbs = CT + (size_t)MP * LDT;      // [D][RB]
   double* Cs = gbs + (size_t)D * RB;        // [MP][MP] + [MP][PC]
   double* red = Cs + MP * MP + MP * PC;     // [32]
+  double* MatH = red + 32;                  // [MP][LDM]  Hhat_f          (OBJ = 1)
+  double* hv = MatH + MP * LDM;             // [MP]       h_f             (OBJ = 1)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int fold = OBJ ? blockIdx.y : 0;
+  const int64_t row_lo = OBJ ? fg.lo[fold] : 0, row_hi = OBJ ? fg.hi[fold] : N;
+  if (OBJ) {
+    stage_mat<MP, false>(MatH, small + lo.fh + fold * MP * MP, tid);
+    if (tid < MP) hv[tid] = small[lo.fhv + fold * MP + tid];
+  }
   for (int e = tid; e < MP * D; e += RB) Us[e] = small[lo.us + e];
   stage_mat<MP, false>(MatCb, small + lo.cbar, tid);
   stage_mat<MP, false>(MatLC, small + lo.lcinv, tid);
@@ -1111,10 +1126,11 @@ fitc_row3_tile_kernel(const double* __restrict__ X, const double* __restrict__ y
   const double* lb0g = rowv + N;
   const double* rbg = rowv + 2 * N;
   const double* tbg = rowv + 3 * N;
+  const double* alg = rowv + 4 * N;
   __syncthreads();
-  for (int64_t base = (int64_t)blockIdx.x * RB; base < N; base += (int64_t)gridDim.x * RB) {
+  for (int64_t base = row_lo + (int64_t)blockIdx.x * RB; base < row_hi; base += (int64_t)gridDim.x * RB) {
     const int64_t i = base + tid;
-    const bool live = i < N;
+    const bool live = i < row_hi;
     for (int d = 0; d < D; ++d) XsT[d * LDT + tid] = live ? X[i * D + d] * par[2 + d] : 0.0;
     XsT[D * LDT + tid] = live ? 1.0 : 0.0;
 #pragma unroll 8
@@ -1123,19 +1139,45 @@ fitc_row3_tile_kernel(const double* __restrict__ X, const double* __restrict__ y
       WT[m * LDT + tid] = live ? WgT[(int64_t)m * N + i] : 0.0;
     }
     __syncwarp();
-    warp_tile_mm<MP>(VT, MatCb, CT, warp, lane);                // CV = V C_bar
     const double lam = live ? lamg[i] : 1.0, yi = live ? y[i] : 0.0;
     const double il = 1.0 / lam;
-    const double rbar = live ? rbg[i] : 0.0, tbar = live ? tbg[i] : 0.0;
-    double s1 = 0.0, bw = 0.0;
+    double lb0, bw = 0.0;
+    if (OBJ) {
+      warp_tile_mm<MP>(WT, MatH, CT, warp, lane);               // Hhat_f W
+      const double al = live ? alg[i] : 0.0;
+      double q1 = 0.0, wh = 0.0;
 #pragma unroll 8
-    for (int m = 0; m < MP; ++m) {
-      const double w = WT[m * LDT + tid];
-      s1 = fma(VT[m * LDT + tid], CT[m * LDT + tid], s1);
-      bw = fma(bbar[m], w, bw);
-      WT[m * LDT + tid] = fma(tbar, beta[m], 2.0 * rbar * w);   // W_bar
+      for (int m = 0; m < MP; ++m) {
+        const double w = WT[m * LDT + tid];
+        q1 = fma(w, CT[m * LDT + tid], q1);
+        wh = fma(w, hv[m], wh);
+        bw = fma(bbar[m], w, bw);
+      }
+      const double abar = lam * al + wh;                        // dL/dalpha_i
+      const double tbar = -abar * il;
+      lb0 = live ? (0.5 * il + 0.5 * al * al + q1 * il * il - abar * al * il) : 0.0;
+#pragma unroll 8
+      for (int m = 0; m < MP; ++m)                               // W_bar = t_bar beta + D_i
+        WT[m * LDT + tid] = live ? fma(tbar, beta[m], fma(-2.0 * il, CT[m * LDT + tid], al * hv[m])) : 0.0;
+      __syncwarp();
     }
-    const double lb = live ? (lb0g[i] - bw * yi * il * il - s1 * il * il) : 0.0;
+    warp_tile_mm<MP>(VT, MatCb, CT, warp, lane);                // CV = V C_bar
+    double s1 = 0.0;
+    if (OBJ) {
+#pragma unroll 8
+      for (int m = 0; m < MP; ++m) s1 = fma(VT[m * LDT + tid], CT[m * LDT + tid], s1);
+    } else {
+      const double rbar = live ? rbg[i] : 0.0, tbar = live ? tbg[i] : 0.0;
+      lb0 = live ? lb0g[i] : 0.0;
+#pragma unroll 8
+      for (int m = 0; m < MP; ++m) {
+        const double w = WT[m * LDT + tid];
+        s1 = fma(VT[m * LDT + tid], CT[m * LDT + tid], s1);
+        bw = fma(bbar[m], w, bw);
+        WT[m * LDT + tid] = fma(tbar, beta[m], 2.0 * rbar * w);   // W_bar
+      }
+    }
+    const double lb = live ? (lb0 - bw * yi * il * il - s1 * il * il) : 0.0;
     sum_lb += lb;
     __syncwarp();
     warp_tile_mm<MP>(WT, MatLC, WT, warp, lane);                // L_C^-T W_bar
@@ -1175,7 +1217,7 @@ fitc_row3_tile_kernel(const double* __restrict__ X, const double* __restrict__ y
   frags_to_smem<MF, MF>(sacc, Cs, MP, warp, lane);
   frags_to_smem<MF, NF>(pacc, Cs + MP * MP, PC, warp, lane);
   const int len = MP * MP + MP * PC + D + 1;
-  double* out = part + (int64_t)blockIdx.x * len;
+  double* out = part + ((int64_t)fold * gridDim.x + blockIdx.x) * len;
   for (int e = tid; e < MP * MP + MP * PC; e += RB) out[e] = Cs[e];
   for (int d = 0; d < D; ++d) {
     const double sg = block_sum(gbs[d * RB + tid], red);
@@ -1183,6 +1225,170 @@ fitc_row3_tile_kernel(const double* __restrict__ X, const double* __restrict__ y
   }
   const double sl = block_sum(sum_lb, red);
   if (tid == 0) out[MP * MP + MP * PC + D] = sl;
+}
+
+// ---- 4-fold block objectives (DSS, K20:538-582): pass 2 over fold-aligned tiles ---------------------
+// blockIdx.y = fold.  W = V L_C^-T and alpha as in pass 2; accumulates, for the fold,
+//   P_f = sum W_i W_i' / lam_i (= I - H_f),  g_f = sum W_i alpha_i,  sum log lam_i,  sum lam_i alpha_i^2
+// part[(fold * gridDim.x + blockIdx.x)] = [P_f (MP*MP) | g_f (MP) | s1 | s2]
+template <int MP>
+__global__ void __launch_bounds__(RB)
+fitc_row2_block_kernel(const double* __restrict__ y, int64_t N, int D, const double* __restrict__ small,
+                       const double* __restrict__ VgT, double* __restrict__ WgT, double* __restrict__ rowv,
+                       double* __restrict__ part, FoldGeom fg) {
+  extern __shared__ double sh[];
+  constexpr int MF = MP / 8, LDM = TileCfg<MP>::LDM;
+  const SmallLayout lo(MP, D);
+  double* MatC = sh;                      // [MP][LDM]  B[k][n] = L_C^-1[n][k]
+  double* beta = MatC + MP * LDM;         // [MP]
+  double* WT = beta + MP;                 // [MP][LDT]
+  double* scs = WT + (size_t)MP * LDT;    // [RB] 1 / lambda
+  double* als = scs + RB;                 // [RB] alpha
+  double* Cs = als + RB;                  // [MP][MP] + [MP]
+  double* red = Cs + MP * MP + MP;        // [32]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int fold = blockIdx.y;
+  const int64_t row_lo = fg.lo[fold], row_hi = fg.hi[fold];
+  stage_mat<MP, true>(MatC, small + lo.lcinv, tid);
+  if (tid < MP) beta[tid] = small[lo.beta + tid];
+  for (int e = tid; e < MP * MP + MP; e += RB) Cs[e] = 0.0;
+  double pacc[MF][MF][2], gacc[MF][2];
+#pragma unroll
+  for (int i = 0; i < MF; ++i) {
+    gacc[i][0] = gacc[i][1] = 0.0;
+#pragma unroll
+    for (int j = 0; j < MF; ++j) pacc[i][j][0] = pacc[i][j][1] = 0.0;
+  }
+  double s1 = 0.0, s2 = 0.0;
+  __syncthreads();
+  const double* lamg = rowv;
+  double* alg = rowv + 4 * N;
+  for (int64_t base = row_lo + (int64_t)blockIdx.x * RB; base < row_hi; base += (int64_t)gridDim.x * RB) {
+    const int64_t i = base + tid;
+    const bool live = i < row_hi;
+#pragma unroll 8
+    for (int m = 0; m < MP; ++m) WT[m * LDT + tid] = live ? VgT[(int64_t)m * N + i] : 0.0;
+    __syncwarp();
+    warp_tile_mm<MP>(WT, MatC, WT, warp, lane);                 // W = V L_C^-T
+    double sc = 0.0, al = 0.0;
+    if (live) {
+      double wb = 0.0;
+#pragma unroll 8
+      for (int m = 0; m < MP; ++m) {
+        const double w = WT[m * LDT + tid];
+        wb = fma(w, beta[m], wb);
+        WgT[(int64_t)m * N + i] = w;
+      }
+      const double lam = lamg[i];
+      sc = 1.0 / lam;
+      al = (y[i] - wb) * sc;
+      alg[i] = al;
+      s1 += log(lam);
+      s2 = fma(lam * al, al, s2);
+    }
+    scs[tid] = sc;
+    als[tid] = al;
+    __syncwarp();
+    tile_outer<MF, MF, true>(WT, WT, scs, warp, lane, pacc);
+    tile_col<MF>(WT, als, warp, lane, gacc);
+    __syncwarp();
+  }
+  frags_to_smem<MF, MF>(pacc, Cs, MP, warp, lane);
+  colfrag_to_smem<MF>(gacc, Cs + MP * MP, warp, lane);
+  const double t1 = block_sum(s1, red);
+  const double t2 = block_sum(s2, red);
+  const int len = MP * MP + MP + 2;
+  double* out = part + ((int64_t)fold * gridDim.x + blockIdx.x) * len;
+  for (int e = tid; e < MP * MP + MP; e += RB) out[e] = Cs[e];
+  if (tid == 0) {
+    out[MP * MP + MP] = t1;
+    out[MP * MP + MP + 1] = t2;
+  }
+}
+
+// acc[f][e] = sum_b part[(f * nblocks + b)][e]   (grid.y = fold)
+__global__ void __launch_bounds__(256)
+fitc_reduce_folds_kernel(const double* __restrict__ part, int nblocks, int len, double* __restrict__ acc) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= len) return;
+  const int f = blockIdx.y;
+  double s = 0.0;
+#pragma unroll 16
+  for (int b = 0; b < nblocks; ++b) s += part[((int64_t)f * nblocks + b) * len + e];
+  acc[(int64_t)f * len + e] = s;
+}
+
+// Replicated fold algebra of the DSS objective, one warp per fold:
+//   H_f = I - P_f = L_H L_H',  h_f = H_f^-1 g_f,  Hhat_f = -1/2 H_f^-1 - 1/2 h_f h_f'
+//   obj  = sum_f [ n_f/2 log 2pi + 1/2 s1_f - log|L_H| + 1/2 s2_f + 1/2 g_f' h_f ]
+//   beta_bar = -sum_f h_f,   G_W = sum_f ( -2 Hhat_f P_f + h_f g_f' )
+// and hands [G_W / 2 | beta_bar | obj] to the C_bar kernel in the slot layout of pass 2
+// (S_W = beta beta_bar' + 2 (G_W / 2) + beta_bar beta').
+template <int MP>
+__global__ void __launch_bounds__(128)
+fitc_block_small_kernel(const double* __restrict__ accf, double* __restrict__ small, double* __restrict__ acc2,
+                        int D, double fold_rows, int* __restrict__ info) {
+  extern __shared__ double sh[];
+  const SmallLayout lo(MP, D);
+  const int tid = threadIdx.x, lane = tid & 31, f = tid >> 5;
+  const int len = MP * MP + MP + 2;
+  double* H = sh + (size_t)f * (3 * MP * MP + 4 * MP);   // per warp: H/L_H, T = L_H^-1, Hh = Hhat, vectors
+  double* Tm = H + MP * MP;
+  double* Hh = Tm + MP * MP;
+  double* Li = Hh + MP * MP;
+  double* hv = Li + MP;
+  double* gv = hv + MP;
+  double* contrib = sh + (size_t)4 * (3 * MP * MP + 4 * MP);   // [4][MP*MP + MP + 1]
+  const double* P = accf + (size_t)f * len;
+  for (int e = lane; e < MP * MP; e += 32) {
+    const int r = e / MP, c = e - r * MP;
+    H[e] = (r == c ? 1.0 : 0.0) - P[e];
+  }
+  if (lane < MP) gv[lane] = P[MP * MP + lane];
+  __syncwarp();
+  const int bad = warp_chol<MP>(H, lane);
+  if (bad && lane == 0) atomicCAS(info, 0, 2000000 + bad);
+  if (lane < MP) Li[lane] = 1.0 / H[lane * MP + lane];
+  __syncwarp();
+  double logdet = (lane < MP) ? -log(Li[lane]) : 0.0;
+  logdet = warp_sum(logdet);
+  double hx = warp_fwd_vec<MP>(H, Li, lane < MP ? gv[lane] : 0.0, lane);
+  hx = warp_bwd_vecT<MP>(H, Li, hx, lane);                        // h_f = H^-1 g_f
+  if (lane < MP) hv[lane] = hx;
+  warp_tri_inverse<MP>(H, Li, Tm, lane);                          // L_H^-1
+  __syncwarp();
+  double gh = (lane < MP) ? gv[lane] * hx : 0.0;
+  gh = warp_sum(gh);
+  if (lane < MP) {
+    const volatile double* Tv = Tm;
+    for (int r = 0; r < MP; ++r) {                                // column `lane` of H^-1 = T' T
+      double sacc = 0.0;
+      const int k0 = r > lane ? r : lane;
+      for (int k = k0; k < MP; ++k) sacc = fma(Tv[k * MP + r], Tv[k * MP + lane], sacc);
+      const double hh = -0.5 * sacc - 0.5 * hv[r] * hx;
+      Hh[r * MP + lane] = hh;
+      small[lo.fh + f * MP * MP + r * MP + lane] = hh;
+    }
+    small[lo.fhv + f * MP + lane] = hx;
+  }
+  __syncwarp();
+  double* cf = contrib + (size_t)f * (MP * MP + MP + 1);
+  if (lane < MP) {
+    for (int r = 0; r < MP; ++r) {                                // column `lane` of -2 Hhat P + h g'
+      double sacc = 0.0;
+      for (int k = 0; k < MP; ++k) sacc = fma(Hh[r * MP + k], P[k * MP + lane], sacc);
+      cf[r * MP + lane] = -2.0 * sacc + hv[r] * gv[lane];
+    }
+    cf[MP * MP + lane] = -hx;
+  }
+  if (lane == 0)
+    cf[MP * MP + MP] = fold_rows * 0.91893853320467274178 + 0.5 * P[MP * MP + MP] - logdet + 0.5 * P[MP * MP + MP + 1] + 0.5 * gh;
+  __syncthreads();
+  for (int e = tid; e < MP * MP + MP + 1; e += 128) {
+    const double tot = ((contrib[e] + contrib[(MP * MP + MP + 1) + e]) + contrib[2 * (MP * MP + MP + 1) + e]) +
+                       contrib[3 * (MP * MP + MP + 1) + e];
+    acc2[e] = (e < MP * MP) ? 0.5 * tot : tot;
+  }
 }
 
 // ---- LOO outputs and prediction ----------------------------------------------------------------------
@@ -1299,9 +1505,11 @@ int run_row3(gps_ctx* ctx, double* part) {
 size_t smem_row1t(int MP, int D) { return ((size_t)MP * D + MP * (MP + 4) + (size_t)D * LDT + (size_t)MP * LDT + RB + MP * MP + MP) * 8; }
 size_t smem_row2t(int MP) { return ((size_t)MP * (MP + 4) + MP + (size_t)MP * LDT + 2 * RB + MP * MP + MP + 32) * 8; }
 size_t smem_row3t(int MP, int D, int PC) {
-  return ((size_t)MP * D + 3 * MP * (MP + 4) + 3 * MP + (size_t)PC * LDT + 3 * (size_t)MP * LDT + (size_t)D * RB + MP * MP +
+  return ((size_t)MP * D + 4 * MP * (MP + 4) + 4 * MP + (size_t)PC * LDT + 3 * (size_t)MP * LDT + (size_t)D * RB + MP * MP +
           MP * PC + 32) * 8;
 }
+size_t smem_row2b(int MP) { return ((size_t)MP * (MP + 4) + MP + (size_t)MP * LDT + 2 * RB + MP * MP + MP + 32) * 8; }
+size_t smem_blocksmall(int MP) { return ((size_t)4 * (3 * MP * MP + 4 * MP) + 4 * (MP * MP + MP + 1)) * 8; }
 
 template <int MP>
 int run_row1t(gps_ctx* ctx, double* part) {
@@ -1330,9 +1538,42 @@ template <int MP, int NF>
 int run_row3t(gps_ctx* ctx, double* part) {
   auto& f = ctx->fitc;
   const size_t sm = smem_row3t(MP, ctx->D, 8 * NF);
-  GPS_CHECK(set_smem(ctx, (fitc_row3_tile_kernel<MP, NF>), sm));
-  fitc_row3_tile_kernel<MP, NF><<<f.grid, RB, sm, ctx->stream>>>(ctx->X.p, ctx->y.p, ctx->N, ctx->D, f.M,
-                                                                 ctx->params.p, f.small.p, f.V.p, f.W.p, f.rowv.p, part);
+  GPS_CHECK(set_smem(ctx, (fitc_row3_tile_kernel<MP, NF, 0>), sm));
+  fitc_row3_tile_kernel<MP, NF, 0><<<f.grid, RB, sm, ctx->stream>>>(ctx->X.p, ctx->y.p, ctx->N, ctx->D, f.M, ctx->params.p,
+                                                                    f.small.p, f.V.p, f.W.p, f.rowv.p, part, FoldGeom());
+  GPS_LAUNCH_CHECK();
+  return GPS_OK;
+}
+
+template <int MP, int NF>
+int run_row3b(gps_ctx* ctx, double* part, const FoldGeom& fg, int gx) {
+  auto& f = ctx->fitc;
+  const size_t sm = smem_row3t(MP, ctx->D, 8 * NF);
+  GPS_CHECK(set_smem(ctx, (fitc_row3_tile_kernel<MP, NF, 1>), sm));
+  fitc_row3_tile_kernel<MP, NF, 1><<<dim3(gx, 4), RB, sm, ctx->stream>>>(ctx->X.p, ctx->y.p, ctx->N, ctx->D, f.M,
+                                                                         ctx->params.p, f.small.p, f.V.p, f.W.p,
+                                                                         f.rowv.p, part, fg);
+  GPS_LAUNCH_CHECK();
+  return GPS_OK;
+}
+
+template <int MP>
+int run_row2b(gps_ctx* ctx, double* part, const FoldGeom& fg, int gx) {
+  auto& f = ctx->fitc;
+  const size_t sm = smem_row2b(MP);
+  GPS_CHECK(set_smem(ctx, fitc_row2_block_kernel<MP>, sm));
+  fitc_row2_block_kernel<MP><<<dim3(gx, 4), RB, sm, ctx->stream>>>(ctx->y.p, ctx->N, ctx->D, f.small.p, f.V.p, f.W.p,
+                                                                   f.rowv.p, part, fg);
+  GPS_LAUNCH_CHECK();
+  return GPS_OK;
+}
+
+template <int MP>
+int run_blocksmall(gps_ctx* ctx, const double* accf, double* acc2, double fold_rows) {
+  auto& f = ctx->fitc;
+  const size_t sm = smem_blocksmall(MP);
+  GPS_CHECK(set_smem(ctx, fitc_block_small_kernel<MP>, sm));
+  fitc_block_small_kernel<MP><<<1, 128, sm, ctx->stream>>>(accf, f.small.p, acc2, ctx->D, fold_rows, ctx->d_info);
   GPS_LAUNCH_CHECK();
   return GPS_OK;
 }
@@ -1377,7 +1618,7 @@ int run_small2(gps_ctx* ctx, const double* part, double* acc2) {
   return GPS_OK;
 }
 template <int MP>
-int run_small3(gps_ctx* ctx, const double* part, const double* acc2, double* acc3, double* out);
+int run_small3(gps_ctx* ctx, const double* part, int nblocks, const double* acc2, double* acc3, double* out);
 
 #define MP_DISPATCH(MPV, CALL)                    \
   switch (MPV) {                                  \
@@ -1419,9 +1660,9 @@ int len2_of(int MP) { return MP * MP + MP + 1; }
 int len3_of(int MP, int D) { return MP * MP + MP * pc_of(D) + D + 1; }
 
 template <int MP>
-int run_small3(gps_ctx* ctx, const double* part, const double* acc2, double* acc3, double* out) {
+int run_small3(gps_ctx* ctx, const double* part, int nblocks, const double* acc2, double* acc3, double* out) {
   auto& f = ctx->fitc;
-  int nb = f.grid;
+  int nb = nblocks;
   if (part) GPS_CHECK(pre_reduce(ctx, &part, &nb, MP * MP + MP * pc_of(ctx->D) + ctx->D + 1));
   fitc_small3_kernel<MP><<<1, 128, 0, ctx->stream>>>(part, nb, acc2, acc3, f.small.p, ctx->params.p, f.M, ctx->D,
                                                      pc_of(ctx->D), f.score, (double)f.world_n, out);
@@ -1470,7 +1711,11 @@ int gps_fitc_begin(gps_ctx* ctx, const double* theta, const double* U, int M, do
                    int64_t world_n) {
   if (!ctx) return GPS_EINVAL;
   if (ctx->N == 0) return gps_fail(ctx, GPS_ESTATE, "fitc: call gps_set_data first");
-  if (!theta || !U || score < GPS_CRPS || score > GPS_NLML) return gps_fail(ctx, GPS_EINVAL, "fitc: bad arguments");
+  if (!theta || !U || score < GPS_CRPS || score > GPS_DSS) return gps_fail(ctx, GPS_EINVAL, "fitc: bad arguments");
+  if (score == GPS_DSS && ((world_n > 0 ? world_n : ctx->N) % 4 || world_n > ctx->N))
+    return gps_fail(ctx, GPS_EINVAL, "fitc dss: needs N %% 4 == 0 (K20:541-543) and runs on one GPU in this version");
+  if (score == GPS_DSS && ctx->fitc_variant == 0)
+    return gps_fail(ctx, GPS_EINVAL, "fitc dss: only the tile formulation of the row passes implements it");
   if (M <= 0 || M > 32)
     return gps_fail(ctx, GPS_EINVAL, "fitc: M=%d outside the fused row-kernel range 1..32", M);
   if (ctx->D > 15) return gps_fail(ctx, GPS_EINVAL, "fitc: D=%d > 15 not supported by the row kernels", ctx->D);
@@ -1493,7 +1738,11 @@ int gps_fitc_begin(gps_ctx* ctx, const double* theta, const double* U, int M, do
   GPS_CHECK(gps_ensure(ctx, f.W, (size_t)N * MP));
   GPS_CHECK(gps_ensure(ctx, f.rowv, (size_t)6 * N));
   GPS_CHECK(gps_ensure(ctx, f.small, (size_t)lo.total + M * D + 8 + D + 2 + M * D));
-  GPS_CHECK(gps_ensure(ctx, f.part, (size_t)f.grid * len3_of(MP, D)));
+  {
+    const size_t nblk = std::max<size_t>((size_t)f.grid, (size_t)4 * ctx->sm_count);
+    GPS_CHECK(gps_ensure(ctx, f.part, nblk * len3_of(MP, D)));
+  }
+  GPS_CHECK(gps_ensure(ctx, f.accf, (size_t)4 * (MP * MP + MP + 2)));
   GPS_CHECK(gps_ensure(ctx, f.part2, (size_t)REDUCE_GROUPS * len3_of(MP, D)));
   GPS_CHECK(gps_ensure(ctx, f.acc1, len1_of(MP)));
   GPS_CHECK(gps_ensure(ctx, f.acc2, len2_of(MP)));
@@ -1546,14 +1795,14 @@ int gps_fitc_pass3(gps_ctx* ctx, const double* acc2, double* acc3) {
   return GPS_OK;
 }
 
-static int fitc_finish_impl(gps_ctx* ctx, const double* part, const double* acc2, double* acc3, double* obj,
+static int fitc_finish_impl(gps_ctx* ctx, const double* part, int nblocks, const double* acc2, double* acc3, double* obj,
                            double* grad_theta, double* grad_U) {
   auto& f = ctx->fitc;
   const int D = ctx->D, M = f.M, MP = f.MP;
   const SmallLayout lo(MP, D);
   double* out = f.small.p + lo.total + M * D;   // [obj | g_theta | g_U]
   const int nout = 1 + D + 2 + M * D;
-  MP_DISPATCH(MP, GPS_CHECK(run_small3<MPC>(ctx, part, acc2, acc3, out)));
+  MP_DISPATCH(MP, GPS_CHECK(run_small3<MPC>(ctx, part, nblocks, acc2, acc3, out)));
   ctx->launches++;
   std::vector<double>& h = f.host_out;
   h.resize(nout + 1);
@@ -1578,7 +1827,7 @@ int gps_fitc_finish(gps_ctx* ctx, const double* acc2, const double* acc3, double
   auto& f = ctx->fitc;
   if (!f.pass2_done) return gps_fail(ctx, GPS_ESTATE, "fitc_finish: passes have not run");
   GPS_CUDA(cudaSetDevice(ctx->device));
-  return fitc_finish_impl(ctx, nullptr, acc2, const_cast<double*>(acc3), obj, grad_theta, grad_U);
+  return fitc_finish_impl(ctx, nullptr, 0, acc2, const_cast<double*>(acc3), obj, grad_theta, grad_U);
 }
 
 int gps_fitc_eval(gps_ctx* ctx, const double* theta, const double* U, int M, double jitter, int score,
@@ -1591,25 +1840,55 @@ int gps_fitc_eval(gps_ctx* ctx, const double* theta, const double* U, int M, dou
   // 7 launches per evaluation.
   GPS_CHECK(do_row1(ctx, f.part.p));
   MP_DISPATCH(f.MP, GPS_CHECK(run_small1<MPC>(ctx, f.part.p, f.acc1.p)));
+  if (score == GPS_DSS) {
+    // 4-fold block objective: fold-aligned tiles (blockIdx.y = fold), per-fold M x M algebra, then the
+    // same C_bar / pass 3 / finish chain with seeds formed from the fold quantities
+    const int64_t N = ctx->N, nfr = N / 4;
+    FoldGeom fg;
+    for (int k = 0; k < 4; ++k) { fg.lo[k] = k * nfr; fg.hi[k] = (k + 1) * nfr; }
+    int gx = (int)((nfr + RB - 1) / RB);
+    if (gx > ctx->sm_count) gx = ctx->sm_count;
+    const int len2b = f.MP * f.MP + f.MP + 2;
+    MP_DISPATCH(f.MP, GPS_CHECK(run_row2b<MPC>(ctx, f.part.p, fg, gx)));
+    fitc_reduce_folds_kernel<<<dim3((len2b + 255) / 256, 4), 256, 0, ctx->stream>>>(f.part.p, gx, len2b, f.accf.p);
+    GPS_LAUNCH_CHECK();
+    MP_DISPATCH(f.MP, GPS_CHECK(run_blocksmall<MPC>(ctx, f.accf.p, f.acc2.p, (double)nfr)));
+    f.pass2_done = true;
+    f.loo_ok = false;
+    ctx->launches += 5;
+    if (!(grad_theta || grad_U)) {
+      GPS_CUDA(cudaMemsetAsync(f.acc3.p, 0, len3_of(f.MP, ctx->D) * sizeof(double), ctx->stream));
+      return fitc_finish_impl(ctx, nullptr, 0, f.acc2.p, f.acc3.p, obj, nullptr, nullptr);
+    }
+    MP_DISPATCH(f.MP, GPS_CHECK(run_small2<MPC>(ctx, nullptr, f.acc2.p)));
+    if (pc_of(ctx->D) == 8) {
+      MP_DISPATCH(f.MP, GPS_CHECK((run_row3b<MPC, 1>(ctx, f.part.p, fg, gx))));
+    } else {
+      MP_DISPATCH(f.MP, GPS_CHECK((run_row3b<MPC, 2>(ctx, f.part.p, fg, gx))));
+    }
+    ctx->launches += 2;
+    return fitc_finish_impl(ctx, f.part.p, 4 * gx, f.acc2.p, f.acc3.p, obj, grad_theta, grad_U);
+  }
   GPS_CHECK(do_row2(ctx, f.part.p));
+  f.loo_ok = true;
   f.pass2_done = true;
   ctx->launches += 3;
   if (grad_theta || grad_U) {
     MP_DISPATCH(f.MP, GPS_CHECK(run_small2<MPC>(ctx, f.part.p, f.acc2.p)));
     GPS_CHECK(do_row3(ctx, f.part.p));
     ctx->launches += 2;
-    return fitc_finish_impl(ctx, f.part.p, f.acc2.p, f.acc3.p, obj, grad_theta, grad_U);
+    return fitc_finish_impl(ctx, f.part.p, f.grid, f.acc2.p, f.acc3.p, obj, grad_theta, grad_U);
   }
   // objective only: reduce pass 2 and finish with a zero pass-3 accumulator
   GPS_CHECK(reduce_to(ctx, f.part.p, f.grid, len2_of(f.MP), f.acc2.p));
   GPS_CUDA(cudaMemsetAsync(f.acc3.p, 0, len3_of(f.MP, ctx->D) * sizeof(double), ctx->stream));
-  return fitc_finish_impl(ctx, nullptr, f.acc2.p, f.acc3.p, obj, nullptr, nullptr);
+  return fitc_finish_impl(ctx, nullptr, 0, f.acc2.p, f.acc3.p, obj, nullptr, nullptr);
 }
 
 int gps_fitc_loo(gps_ctx* ctx, double* loo_mean, double* loo_var) {
   if (!ctx) return GPS_EINVAL;
   auto& f = ctx->fitc;
-  if (!f.pass2_done) return gps_fail(ctx, GPS_ESTATE, "fitc_loo: no evaluation to report");
+  if (!f.pass2_done || !f.loo_ok) return gps_fail(ctx, GPS_ESTATE, "fitc_loo: no CRPS/LOGS/NLML evaluation to report");
   if (!loo_mean || !loo_var) return gps_fail(ctx, GPS_EINVAL, "fitc_loo: null output");
   GPS_CUDA(cudaSetDevice(ctx->device));
   const int64_t N = ctx->N;
