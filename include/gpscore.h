@@ -39,8 +39,8 @@ enum { GPS_OK = 0, GPS_EINVAL = 1, GPS_ECUDA = 2, GPS_ENOTPD = 3, GPS_ENODEVICE 
 
 /* score selector: LOO-CRPS (KF:245), LOO log score (KF:424), negative log marginal
  * likelihood (KF:331-334), 4-fold block-LOO DSS (KF:499-538, K20:538-582; needs 4 | N; the FITC
- * version runs through gps_fitc_eval on one GPU) */
-enum { GPS_CRPS = 0, GPS_LOGS = 1, GPS_NLML = 2, GPS_DSS = 3 };
+ * version runs through gps_fitc_eval on one GPU), 4-fold block CRPS "kc" (K20:669-714; FITC only) */
+enum { GPS_CRPS = 0, GPS_LOGS = 1, GPS_NLML = 2, GPS_DSS = 3, GPS_KC = 4 };
 
 /* ---- context ------------------------------------------------------------------------------- */
 int gps_create(int device, gps_ctx** out);

@@ -259,7 +259,7 @@ int gps_set_data(gps_ctx* ctx, const double* X, const double* y, int64_t N, int 
 int gps_full_eval(gps_ctx* ctx, const double* theta, int score, double* obj, double* grad) {
   if (!ctx) return GPS_EINVAL;
   if (ctx->N == 0) return gps_fail(ctx, GPS_ESTATE, "full_eval: call gps_set_data first");
-  if (!theta || !obj || score < GPS_CRPS || score > GPS_DSS) return gps_fail(ctx, GPS_EINVAL, "full_eval: bad arguments");
+  if (!theta || !obj || score < GPS_CRPS || score > GPS_DSS) return gps_fail(ctx, GPS_EINVAL, "full_eval: bad arguments (kc is a FITC objective)");
   GPS_CUDA(cudaSetDevice(ctx->device));
   const int64_t N = ctx->N, Np = ctx->Np;
   const int D = ctx->D;

@@ -34,7 +34,7 @@ __device__ __forceinline__ void dmma(double& c0, double& c1, double a, double b)
 
 // layout of the replicated small-matrix buffer (doubles), MP-strided
 struct SmallLayout {
-  int us, la, lai, kuu, lc, lci, beta, bbar, cbar, vyb, lainv, lcinv, fh, fhv, total;
+  int us, la, lai, kuu, lc, lci, beta, bbar, cbar, vyb, lainv, lcinv, fh, fhv, fh2, fgv, total;
   __host__ __device__ SmallLayout(int MP, int D) {
     int o = 0;
     us = o;   o += MP * D;
@@ -51,6 +51,8 @@ struct SmallLayout {
     lcinv = o; o += MP * MP;
     fh = o;    o += 4 * MP * MP;   // per-fold Hhat_f (block objectives)
     fhv = o;   o += 4 * MP;        // per-fold h_f
+    fh2 = o;   o += 4 * MP * MP;   // per-fold H_bar_f (kc)
+    fgv = o;   o += 4 * MP;        // per-fold g_bar_f (kc)
     total = o;
   }
 };
@@ -1091,15 +1093,20 @@ fitc_row3_tile_kernel(const double* __restrict__ X, const double* __restrict__ y
   double* gbs = CT + (size_t)MP * LDT;      // [D][RB]
   double* Cs = gbs + (size_t)D * RB;        // [MP][MP] + [MP][PC]
   double* red = Cs + MP * MP + MP * PC;     // [32]
-  double* MatH = red + 32;                  // [MP][LDM]  Hhat_f          (OBJ = 1)
-  double* hv = MatH + MP * LDM;             // [MP]       h_f             (OBJ = 1)
+  double* MatH = red + 32;                  // [MP][LDM]  Hhat_f (OBJ = 1) / H_bar_f (OBJ = 2)
+  double* hv = MatH + MP * LDM;             // [MP]       h_f
+  double* MatHi = hv + MP;                  // [MP][LDM]  H_f^-1          (OBJ = 2)
+  double* gbv = MatHi + MP * LDM;           // [MP]       g_bar_f         (OBJ = 2)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int fold = OBJ ? blockIdx.y : 0;
   const int64_t row_lo = OBJ ? fg.lo[fold] : 0, row_hi = OBJ ? fg.hi[fold] : N;
-  if (OBJ) {
-    stage_mat<MP, false>(MatH, small + lo.fh + fold * MP * MP, tid);
-    if (tid < MP) hv[tid] = small[lo.fhv + fold * MP + tid];
+  if (OBJ == 1) stage_mat<MP, false>(MatH, small + lo.fh + fold * MP * MP, tid);
+  if (OBJ == 2) {
+    stage_mat<MP, false>(MatH, small + lo.fh2 + fold * MP * MP, tid);
+    stage_mat<MP, false>(MatHi, small + lo.fh + fold * MP * MP, tid);
+    if (tid < MP) gbv[tid] = small[lo.fgv + fold * MP + tid];
   }
+  if (OBJ && tid < MP) hv[tid] = small[lo.fhv + fold * MP + tid];
   for (int e = tid; e < MP * D; e += RB) Us[e] = small[lo.us + e];
   stage_mat<MP, false>(MatCb, small + lo.cbar, tid);
   stage_mat<MP, false>(MatLC, small + lo.lcinv, tid);
@@ -1135,14 +1142,40 @@ fitc_row3_tile_kernel(const double* __restrict__ X, const double* __restrict__ y
     XsT[D * LDT + tid] = live ? 1.0 : 0.0;
 #pragma unroll 8
     for (int m = 0; m < MP; ++m) {
-      VT[m * LDT + tid] = live ? VgT[(int64_t)m * N + i] : 0.0;
+      if (OBJ != 2) VT[m * LDT + tid] = live ? VgT[(int64_t)m * N + i] : 0.0;   // OBJ = 2 borrows VT first
       WT[m * LDT + tid] = live ? WgT[(int64_t)m * N + i] : 0.0;
     }
     __syncwarp();
     const double lam = live ? lamg[i] : 1.0, yi = live ? y[i] : 0.0;
     const double il = 1.0 / lam;
     double lb0, bw = 0.0;
-    if (OBJ) {
+    if (OBJ == 2) {
+      // kc seeds: D_i = 2 cbar H^-1 W - (2/lam) H_bar W - mbar h + alpha g_bar,  abar = -mbar lam + W'g_bar
+      warp_tile_mm<MP>(WT, MatH, CT, warp, lane);               // H_bar_f W
+      const double al = live ? alg[i] : 0.0;
+      const double cb = live ? rbg[i] : 0.0, mb = live ? tbg[i] : 0.0;   // cbar_i, mbar_i (pass 2b)
+      double q1 = 0.0, wg = 0.0;
+#pragma unroll 8
+      for (int m = 0; m < MP; ++m) {
+        const double w = WT[m * LDT + tid];
+        q1 = fma(w, CT[m * LDT + tid], q1);
+        wg = fma(w, gbv[m], wg);
+        bw = fma(bbar[m], w, bw);
+        VT[m * LDT + tid] = -2.0 * il * CT[m * LDT + tid];
+      }
+      __syncwarp();
+      warp_tile_mm<MP>(WT, MatHi, CT, warp, lane);              // H_f^-1 W
+      const double abar = -mb * lam + wg;
+      const double tbar = -abar * il;
+      lb0 = live ? (-mb * al + cb + q1 * il * il - abar * al * il) : 0.0;
+#pragma unroll 8
+      for (int m = 0; m < MP; ++m)
+        WT[m * LDT + tid] = live ? (tbar * beta[m] + VT[m * LDT + tid] + 2.0 * cb * CT[m * LDT + tid] - mb * hv[m] +
+                                    al * gbv[m]) : 0.0;
+#pragma unroll 8
+      for (int m = 0; m < MP; ++m) VT[m * LDT + tid] = live ? VgT[(int64_t)m * N + i] : 0.0;
+      __syncwarp();
+    } else if (OBJ) {
       warp_tile_mm<MP>(WT, MatH, CT, warp, lane);               // Hhat_f W
       const double al = live ? alg[i] : 0.0;
       double q1 = 0.0, wh = 0.0;
@@ -1327,7 +1360,7 @@ fitc_reduce_folds_kernel(const double* __restrict__ part, int nblocks, int len, 
 template <int MP>
 __global__ void __launch_bounds__(128)
 fitc_block_small_kernel(const double* __restrict__ accf, double* __restrict__ small, double* __restrict__ acc2,
-                        int D, double fold_rows, int* __restrict__ info) {
+                        int D, double fold_rows, int kc_phase_a, int* __restrict__ info) {
   extern __shared__ double sh[];
   const SmallLayout lo(MP, D);
   const int tid = threadIdx.x, lane = tid & 31, f = tid >> 5;
@@ -1365,13 +1398,14 @@ fitc_block_small_kernel(const double* __restrict__ accf, double* __restrict__ sm
       double sacc = 0.0;
       const int k0 = r > lane ? r : lane;
       for (int k = k0; k < MP; ++k) sacc = fma(Tv[k * MP + r], Tv[k * MP + lane], sacc);
-      const double hh = -0.5 * sacc - 0.5 * hv[r] * hx;
+      const double hh = kc_phase_a ? sacc : -0.5 * sacc - 0.5 * hv[r] * hx;   // kc: H^-1 itself
       Hh[r * MP + lane] = hh;
       small[lo.fh + f * MP * MP + r * MP + lane] = hh;
     }
     small[lo.fhv + f * MP + lane] = hx;
   }
   __syncwarp();
+  if (kc_phase_a) return;                                         // uniform per launch
   double* cf = contrib + (size_t)f * (MP * MP + MP + 1);
   if (lane < MP) {
     for (int r = 0; r < MP; ++r) {                                // column `lane` of -2 Hhat P + h g'
@@ -1383,6 +1417,160 @@ fitc_block_small_kernel(const double* __restrict__ accf, double* __restrict__ sm
   }
   if (lane == 0)
     cf[MP * MP + MP] = fold_rows * 0.91893853320467274178 + 0.5 * P[MP * MP + MP] - logdet + 0.5 * P[MP * MP + MP + 1] + 0.5 * gh;
+  __syncthreads();
+  for (int e = tid; e < MP * MP + MP + 1; e += 128) {
+    const double tot = ((contrib[e] + contrib[(MP * MP + MP + 1) + e]) + contrib[2 * (MP * MP + MP + 1) + e]) +
+                       contrib[3 * (MP * MP + MP + 1) + e];
+    acc2[e] = (e < MP * MP) ? 0.5 * tot : tot;
+  }
+}
+
+// ---- block CRPS "kc" (K20:669-714): pass 2b over fold-aligned tiles ------------------------------------
+// Fold predictive of row i: m_i = y_i - lam_i alpha_i - W_i' h_f, c_i = lam_i + W_i' H_f^-1 W_i.
+// Scores it with the closed-form CRPS, stores the seeds mbar_i, cbar_i and accumulates per fold
+//   E_f = sum cbar_i W_i W_i',  hbar_f = -sum mbar_i W_i,  obj_f = (1/n_f) sum crps_i.
+// part[(fold * gridDim.x + blockIdx.x)] = [E_f (MP*MP) | hbar_f (MP) | obj_f]
+template <int MP>
+__global__ void __launch_bounds__(RB)
+fitc_row2b_kc_kernel(const double* __restrict__ y, int64_t N, int D, const double* __restrict__ small,
+                     const double* __restrict__ WgT, double* __restrict__ rowv, double* __restrict__ part,
+                     FoldGeom fg, double inv_fold_rows) {
+  extern __shared__ double sh[];
+  constexpr int MF = MP / 8, LDM = TileCfg<MP>::LDM;
+  const SmallLayout lo(MP, D);
+  double* MatHi = sh;                     // [MP][LDM]  H_f^-1 (symmetric)
+  double* hv = MatHi + MP * LDM;          // [MP]
+  double* WT = hv + MP;                   // [MP][LDT]
+  double* CT = WT + (size_t)MP * LDT;     // [MP][LDT]  W H_f^-1
+  double* cbs = CT + (size_t)MP * LDT;    // [RB] cbar
+  double* mbs = cbs + RB;                 // [RB] -mbar
+  double* Cs = mbs + RB;                  // [MP][MP] + [MP]
+  double* red = Cs + MP * MP + MP;        // [32]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int fold = blockIdx.y;
+  const int64_t row_lo = fg.lo[fold], row_hi = fg.hi[fold];
+  stage_mat<MP, false>(MatHi, small + lo.fh + fold * MP * MP, tid);
+  if (tid < MP) hv[tid] = small[lo.fhv + fold * MP + tid];
+  for (int e = tid; e < MP * MP + MP; e += RB) Cs[e] = 0.0;
+  double eacc[MF][MF][2], hacc[MF][2];
+#pragma unroll
+  for (int i = 0; i < MF; ++i) {
+    hacc[i][0] = hacc[i][1] = 0.0;
+#pragma unroll
+    for (int j = 0; j < MF; ++j) eacc[i][j][0] = eacc[i][j][1] = 0.0;
+  }
+  double obj = 0.0;
+  __syncthreads();
+  const double* lamg = rowv;
+  double* cbg = rowv + 2 * N;   // cbar_i  (slot of r_bar)
+  double* mbg = rowv + 3 * N;   // mbar_i  (slot of t_bar)
+  const double* alg = rowv + 4 * N;
+  for (int64_t base = row_lo + (int64_t)blockIdx.x * RB; base < row_hi; base += (int64_t)gridDim.x * RB) {
+    const int64_t i = base + tid;
+    const bool live = i < row_hi;
+#pragma unroll 8
+    for (int m = 0; m < MP; ++m) WT[m * LDT + tid] = live ? WgT[(int64_t)m * N + i] : 0.0;
+    __syncwarp();
+    warp_tile_mm<MP>(WT, MatHi, CT, warp, lane);                // H_f^-1 W_i (rows)
+    double cb = 0.0, mb = 0.0;
+    if (live) {
+      double q = 0.0, wh = 0.0;
+#pragma unroll 8
+      for (int m = 0; m < MP; ++m) {
+        const double w = WT[m * LDT + tid];
+        q = fma(w, CT[m * LDT + tid], q);
+        wh = fma(w, hv[m], wh);
+      }
+      const double lam = lamg[i], al = alg[i], yi = y[i];
+      const double cv = lam + q;                                // fold predictive variance (K20:704)
+      const double mu = yi - lam * al - wh;                     // fold predictive mean     (K20:698)
+      const double sd = sqrt(cv), z = (yi - mu) / sd;
+      const double tpm1 = erf(z * INV_SQRT2);
+      const double phi2 = 2.0 * INV_SQRT_2PI * exp(-0.5 * z * z);
+      obj += sd * (z * tpm1 + phi2 - INV_SQRT_PI) * inv_fold_rows;
+      mb = -tpm1 * inv_fold_rows;
+      cb = (phi2 - INV_SQRT_PI) / (2.0 * sd) * inv_fold_rows;
+      cbg[i] = cb;
+      mbg[i] = mb;
+    }
+    cbs[tid] = cb;
+    mbs[tid] = -mb;
+    __syncwarp();
+    tile_outer<MF, MF, true>(WT, WT, cbs, warp, lane, eacc);    // E_f
+    tile_col<MF>(WT, mbs, warp, lane, hacc);                    // hbar_f = -sum mbar W
+    __syncwarp();
+  }
+  frags_to_smem<MF, MF>(eacc, Cs, MP, warp, lane);
+  colfrag_to_smem<MF>(hacc, Cs + MP * MP, warp, lane);
+  const double o = block_sum(obj, red);
+  const int len = MP * MP + MP + 1;
+  double* out = part + ((int64_t)fold * gridDim.x + blockIdx.x) * len;
+  for (int e = tid; e < MP * MP + MP; e += RB) out[e] = Cs[e];
+  if (tid == 0) out[MP * MP + MP] = o;
+}
+
+// Replicated fold algebra of kc, phase b (one warp per fold):
+//   g_bar = H^-1 h_bar,  H_bar = -H^-1 E H^-1 - sym(g_bar h'),
+//   beta_bar = sum_f (-h_bar - P g_bar),  G_W = sum_f ( h h_bar' + 2 H^-1 E + g_bar g' - 2 H_bar P ),  obj = sum_f obj_f
+template <int MP>
+__global__ void __launch_bounds__(128)
+fitc_block_small_kc_kernel(const double* __restrict__ accf, const double* __restrict__ accf2,
+                           double* __restrict__ small, double* __restrict__ acc2, int D) {
+  extern __shared__ double sh[];
+  const SmallLayout lo(MP, D);
+  const int tid = threadIdx.x, lane = tid & 31, f = tid >> 5;
+  const int len1 = MP * MP + MP + 2, len2 = MP * MP + MP + 1;
+  double* Hi = sh + (size_t)f * (3 * MP * MP + 4 * MP);   // H^-1
+  double* M1 = Hi + MP * MP;                              // H^-1 E
+  double* Hb = M1 + MP * MP;                              // H_bar
+  double* hv = Hb + MP * MP;
+  double* gb = hv + MP;                                   // g_bar
+  double* hb = gb + MP;                                   // h_bar
+  double* gv = hb + MP;                                   // g
+  double* contrib = sh + (size_t)4 * (3 * MP * MP + 4 * MP);
+  const double* P = accf + (size_t)f * len1;
+  const double* E = accf2 + (size_t)f * len2;
+  for (int e = lane; e < MP * MP; e += 32) Hi[e] = small[lo.fh + f * MP * MP + e];
+  if (lane < MP) {
+    hv[lane] = small[lo.fhv + f * MP + lane];
+    hb[lane] = E[MP * MP + lane];
+    gv[lane] = P[MP * MP + lane];
+  }
+  __syncwarp();
+  if (lane < MP) {
+    double sg = 0.0;
+    for (int k = 0; k < MP; ++k) sg = fma(Hi[lane * MP + k], hb[k], sg);
+    gb[lane] = sg;
+    small[lo.fgv + f * MP + lane] = sg;
+    for (int r = 0; r < MP; ++r) {                          // column `lane` of H^-1 E
+      double sacc = 0.0;
+      for (int k = 0; k < MP; ++k) sacc = fma(Hi[r * MP + k], E[k * MP + lane], sacc);
+      M1[r * MP + lane] = sacc;
+    }
+  }
+  __syncwarp();
+  if (lane < MP) {
+    for (int r = 0; r < MP; ++r) {                          // column `lane` of H_bar
+      double sacc = 0.0;
+      for (int k = 0; k < MP; ++k) sacc = fma(M1[r * MP + k], Hi[k * MP + lane], sacc);
+      const double hbv = -sacc - 0.5 * (gb[r] * hv[lane] + hv[r] * gb[lane]);
+      Hb[r * MP + lane] = hbv;
+      small[lo.fh2 + f * MP * MP + r * MP + lane] = hbv;
+    }
+  }
+  __syncwarp();
+  double* cf = contrib + (size_t)f * (MP * MP + MP + 1);
+  if (lane < MP) {
+    for (int r = 0; r < MP; ++r) {
+      double sacc = 0.0;
+      for (int k = 0; k < MP; ++k) sacc = fma(Hb[r * MP + k], P[k * MP + lane], sacc);
+      cf[r * MP + lane] = hv[r] * hb[lane] + 2.0 * M1[r * MP + lane] + gb[r] * gv[lane] - 2.0 * sacc;
+    }
+    double pg = 0.0;
+    for (int k = 0; k < MP; ++k) pg = fma(P[lane * MP + k], gb[k], pg);
+    cf[MP * MP + lane] = -hb[lane] - pg;
+  }
+  if (lane == 0) cf[MP * MP + MP] = E[MP * MP + MP];
   __syncthreads();
   for (int e = tid; e < MP * MP + MP + 1; e += 128) {
     const double tot = ((contrib[e] + contrib[(MP * MP + MP + 1) + e]) + contrib[2 * (MP * MP + MP + 1) + e]) +
@@ -1505,9 +1693,10 @@ int run_row3(gps_ctx* ctx, double* part) {
 size_t smem_row1t(int MP, int D) { return ((size_t)MP * D + MP * (MP + 4) + (size_t)D * LDT + (size_t)MP * LDT + RB + MP * MP + MP) * 8; }
 size_t smem_row2t(int MP) { return ((size_t)MP * (MP + 4) + MP + (size_t)MP * LDT + 2 * RB + MP * MP + MP + 32) * 8; }
 size_t smem_row3t(int MP, int D, int PC) {
-  return ((size_t)MP * D + 4 * MP * (MP + 4) + 4 * MP + (size_t)PC * LDT + 3 * (size_t)MP * LDT + (size_t)D * RB + MP * MP +
+  return ((size_t)MP * D + 5 * MP * (MP + 4) + 5 * MP + (size_t)PC * LDT + 3 * (size_t)MP * LDT + (size_t)D * RB + MP * MP +
           MP * PC + 32) * 8;
 }
+size_t smem_row2kc(int MP) { return ((size_t)MP * (MP + 4) + MP + 2 * (size_t)MP * LDT + 2 * RB + MP * MP + MP + 32) * 8; }
 size_t smem_row2b(int MP) { return ((size_t)MP * (MP + 4) + MP + (size_t)MP * LDT + 2 * RB + MP * MP + MP + 32) * 8; }
 size_t smem_blocksmall(int MP) { return ((size_t)4 * (3 * MP * MP + 4 * MP) + 4 * (MP * MP + MP + 1)) * 8; }
 
@@ -1557,6 +1746,39 @@ int run_row3b(gps_ctx* ctx, double* part, const FoldGeom& fg, int gx) {
   return GPS_OK;
 }
 
+template <int MP, int NF>
+int run_row3kc(gps_ctx* ctx, double* part, const FoldGeom& fg, int gx) {
+  auto& f = ctx->fitc;
+  const size_t sm = smem_row3t(MP, ctx->D, 8 * NF);
+  GPS_CHECK(set_smem(ctx, (fitc_row3_tile_kernel<MP, NF, 2>), sm));
+  fitc_row3_tile_kernel<MP, NF, 2><<<dim3(gx, 4), RB, sm, ctx->stream>>>(ctx->X.p, ctx->y.p, ctx->N, ctx->D, f.M,
+                                                                         ctx->params.p, f.small.p, f.V.p, f.W.p,
+                                                                         f.rowv.p, part, fg);
+  GPS_LAUNCH_CHECK();
+  return GPS_OK;
+}
+
+template <int MP>
+int run_row2kc(gps_ctx* ctx, double* part, const FoldGeom& fg, int gx, double inv_rows) {
+  auto& f = ctx->fitc;
+  const size_t sm = smem_row2kc(MP);
+  GPS_CHECK(set_smem(ctx, fitc_row2b_kc_kernel<MP>, sm));
+  fitc_row2b_kc_kernel<MP><<<dim3(gx, 4), RB, sm, ctx->stream>>>(ctx->y.p, ctx->N, ctx->D, f.small.p, f.W.p, f.rowv.p,
+                                                                 part, fg, inv_rows);
+  GPS_LAUNCH_CHECK();
+  return GPS_OK;
+}
+
+template <int MP>
+int run_blocksmall_kc(gps_ctx* ctx, const double* accf, const double* accf2, double* acc2) {
+  auto& f = ctx->fitc;
+  const size_t sm = smem_blocksmall(MP);
+  GPS_CHECK(set_smem(ctx, fitc_block_small_kc_kernel<MP>, sm));
+  fitc_block_small_kc_kernel<MP><<<1, 128, sm, ctx->stream>>>(accf, accf2, f.small.p, acc2, ctx->D);
+  GPS_LAUNCH_CHECK();
+  return GPS_OK;
+}
+
 template <int MP>
 int run_row2b(gps_ctx* ctx, double* part, const FoldGeom& fg, int gx) {
   auto& f = ctx->fitc;
@@ -1569,11 +1791,12 @@ int run_row2b(gps_ctx* ctx, double* part, const FoldGeom& fg, int gx) {
 }
 
 template <int MP>
-int run_blocksmall(gps_ctx* ctx, const double* accf, double* acc2, double fold_rows) {
+int run_blocksmall(gps_ctx* ctx, const double* accf, double* acc2, double fold_rows, int kc_phase_a) {
   auto& f = ctx->fitc;
   const size_t sm = smem_blocksmall(MP);
   GPS_CHECK(set_smem(ctx, fitc_block_small_kernel<MP>, sm));
-  fitc_block_small_kernel<MP><<<1, 128, sm, ctx->stream>>>(accf, f.small.p, acc2, ctx->D, fold_rows, ctx->d_info);
+  fitc_block_small_kernel<MP><<<1, 128, sm, ctx->stream>>>(accf, f.small.p, acc2, ctx->D, fold_rows, kc_phase_a,
+                                                            ctx->d_info);
   GPS_LAUNCH_CHECK();
   return GPS_OK;
 }
@@ -1711,11 +1934,12 @@ int gps_fitc_begin(gps_ctx* ctx, const double* theta, const double* U, int M, do
                    int64_t world_n) {
   if (!ctx) return GPS_EINVAL;
   if (ctx->N == 0) return gps_fail(ctx, GPS_ESTATE, "fitc: call gps_set_data first");
-  if (!theta || !U || score < GPS_CRPS || score > GPS_DSS) return gps_fail(ctx, GPS_EINVAL, "fitc: bad arguments");
-  if (score == GPS_DSS && ((world_n > 0 ? world_n : ctx->N) % 4 || world_n > ctx->N))
-    return gps_fail(ctx, GPS_EINVAL, "fitc dss: needs N %% 4 == 0 (K20:541-543) and runs on one GPU in this version");
-  if (score == GPS_DSS && ctx->fitc_variant == 0)
-    return gps_fail(ctx, GPS_EINVAL, "fitc dss: only the tile formulation of the row passes implements it");
+  if (!theta || !U || score < GPS_CRPS || score > GPS_KC) return gps_fail(ctx, GPS_EINVAL, "fitc: bad arguments");
+  const bool block_obj = score == GPS_DSS || score == GPS_KC;
+  if (block_obj && ((world_n > 0 ? world_n : ctx->N) % 4 || world_n > ctx->N))
+    return gps_fail(ctx, GPS_EINVAL, "fitc dss/kc: needs N %% 4 == 0 (K20:541-543) and runs on one GPU in this version");
+  if (block_obj && ctx->fitc_variant == 0)
+    return gps_fail(ctx, GPS_EINVAL, "fitc dss/kc: only the tile formulation of the row passes implements them");
   if (M <= 0 || M > 32)
     return gps_fail(ctx, GPS_EINVAL, "fitc: M=%d outside the fused row-kernel range 1..32", M);
   if (ctx->D > 15) return gps_fail(ctx, GPS_EINVAL, "fitc: D=%d > 15 not supported by the row kernels", ctx->D);
@@ -1742,7 +1966,7 @@ int gps_fitc_begin(gps_ctx* ctx, const double* theta, const double* U, int M, do
     const size_t nblk = std::max<size_t>((size_t)f.grid, (size_t)4 * ctx->sm_count);
     GPS_CHECK(gps_ensure(ctx, f.part, nblk * len3_of(MP, D)));
   }
-  GPS_CHECK(gps_ensure(ctx, f.accf, (size_t)4 * (MP * MP + MP + 2)));
+  GPS_CHECK(gps_ensure(ctx, f.accf, (size_t)8 * (MP * MP + MP + 2)));
   GPS_CHECK(gps_ensure(ctx, f.part2, (size_t)REDUCE_GROUPS * len3_of(MP, D)));
   GPS_CHECK(gps_ensure(ctx, f.acc1, len1_of(MP)));
   GPS_CHECK(gps_ensure(ctx, f.acc2, len2_of(MP)));
@@ -1840,7 +2064,7 @@ int gps_fitc_eval(gps_ctx* ctx, const double* theta, const double* U, int M, dou
   // 7 launches per evaluation.
   GPS_CHECK(do_row1(ctx, f.part.p));
   MP_DISPATCH(f.MP, GPS_CHECK(run_small1<MPC>(ctx, f.part.p, f.acc1.p)));
-  if (score == GPS_DSS) {
+  if (score == GPS_DSS || score == GPS_KC) {
     // 4-fold block objective: fold-aligned tiles (blockIdx.y = fold), per-fold M x M algebra, then the
     // same C_bar / pass 3 / finish chain with seeds formed from the fold quantities
     const int64_t N = ctx->N, nfr = N / 4;
@@ -1852,7 +2076,17 @@ int gps_fitc_eval(gps_ctx* ctx, const double* theta, const double* U, int M, dou
     MP_DISPATCH(f.MP, GPS_CHECK(run_row2b<MPC>(ctx, f.part.p, fg, gx)));
     fitc_reduce_folds_kernel<<<dim3((len2b + 255) / 256, 4), 256, 0, ctx->stream>>>(f.part.p, gx, len2b, f.accf.p);
     GPS_LAUNCH_CHECK();
-    MP_DISPATCH(f.MP, GPS_CHECK(run_blocksmall<MPC>(ctx, f.accf.p, f.acc2.p, (double)nfr)));
+    MP_DISPATCH(f.MP, GPS_CHECK(run_blocksmall<MPC>(ctx, f.accf.p, f.acc2.p, (double)nfr, score == GPS_KC ? 1 : 0)));
+    if (score == GPS_KC) {
+      // block CRPS: a second fold-aligned pass scores every row and accumulates E_f, hbar_f
+      const int len2c = f.MP * f.MP + f.MP + 1;
+      double* accf2 = f.accf.p + 4 * len2b;
+      MP_DISPATCH(f.MP, GPS_CHECK(run_row2kc<MPC>(ctx, f.part.p, fg, gx, 1.0 / (double)nfr)));
+      fitc_reduce_folds_kernel<<<dim3((len2c + 255) / 256, 4), 256, 0, ctx->stream>>>(f.part.p, gx, len2c, accf2);
+      GPS_LAUNCH_CHECK();
+      MP_DISPATCH(f.MP, GPS_CHECK(run_blocksmall_kc<MPC>(ctx, f.accf.p, accf2, f.acc2.p)));
+      ctx->launches += 3;
+    }
     f.pass2_done = true;
     f.loo_ok = false;
     ctx->launches += 5;
@@ -1861,7 +2095,13 @@ int gps_fitc_eval(gps_ctx* ctx, const double* theta, const double* U, int M, dou
       return fitc_finish_impl(ctx, nullptr, 0, f.acc2.p, f.acc3.p, obj, nullptr, nullptr);
     }
     MP_DISPATCH(f.MP, GPS_CHECK(run_small2<MPC>(ctx, nullptr, f.acc2.p)));
-    if (pc_of(ctx->D) == 8) {
+    if (score == GPS_KC) {
+      if (pc_of(ctx->D) == 8) {
+        MP_DISPATCH(f.MP, GPS_CHECK((run_row3kc<MPC, 1>(ctx, f.part.p, fg, gx))));
+      } else {
+        MP_DISPATCH(f.MP, GPS_CHECK((run_row3kc<MPC, 2>(ctx, f.part.p, fg, gx))));
+      }
+    } else if (pc_of(ctx->D) == 8) {
       MP_DISPATCH(f.MP, GPS_CHECK((run_row3b<MPC, 1>(ctx, f.part.p, fg, gx))));
     } else {
       MP_DISPATCH(f.MP, GPS_CHECK((run_row3b<MPC, 2>(ctx, f.part.p, fg, gx))));

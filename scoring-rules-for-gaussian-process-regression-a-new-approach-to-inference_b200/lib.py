@@ -10,8 +10,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libgpscore.so")
 
 GPS_OK, GPS_EINVAL, GPS_ECUDA, GPS_ENOTPD, GPS_ENODEVICE, GPS_ENOMEM, GPS_ESTATE = range(7)
-GPS_CRPS, GPS_LOGS, GPS_NLML, GPS_DSS = 0, 1, 2, 3
-SCORES = {"crps": GPS_CRPS, "logs": GPS_LOGS, "nlml": GPS_NLML, "dss": GPS_DSS}
+GPS_CRPS, GPS_LOGS, GPS_NLML, GPS_DSS, GPS_KC = 0, 1, 2, 3, 4
+SCORES = {"crps": GPS_CRPS, "logs": GPS_LOGS, "nlml": GPS_NLML, "dss": GPS_DSS, "kc": GPS_KC}
 GRID_KINDS = {"nlml": 0, "crps": 1, "wrong_crps": 2, "logs": 3}
 
 _dp = C.POINTER(C.c_double)

@@ -197,32 +197,35 @@ def test_fitc_row_pass_formulations_agree(ctx, m_ind):
         ctx._check(ctx._lib.gps_dbg_set_variant(ctx._h, 2, 1))
 
 
+@pytest.mark.parametrize("kind", ["dss", "kc"])
 @pytest.mark.parametrize("name", [n for n in golden_names(("c4",)) if "ragged" not in n])
-def test_fitc_dss_vs_reference_golden(ctx, name):
-    """FITC 4-fold DSS objective + gradients (K20:538-587) in Woodbury form vs the reference's autograd."""
+def test_fitc_dss_vs_reference_golden(ctx, name, kind):
+    """FITC 4-fold DSS (K20:538-587) and block-CRPS kc (K20:669-720) objectives + gradients in Woodbury
+    form vs the reference's autograd."""
     g = load_golden(name)
     ctx.set_data(_dev(g["X"]), _dev(g["y"]))
-    val, grad, gU = ctx.fitc_eval(g["theta"], g["U"], "dss")
-    assert abs(val - g["obj_dss"]) <= OBJ_TOL * abs(g["obj_dss"])
-    ref = grad_vector(g, "dss")
+    val, grad, gU = ctx.fitc_eval(g["theta"], g["U"], kind)
+    assert abs(val - g["obj_" + kind]) <= OBJ_TOL * abs(g["obj_" + kind])
+    ref = grad_vector(g, kind)
     if int(g["d_b"]) == 1 and g["X"].shape[1] > 1:
         grad = np.concatenate([[grad[0]], [grad[1:-1].sum()], [grad[-1]]])
     assert relerr(grad, ref) <= GRAD_TOL
-    assert relerr(gU, g["grad_u_dss"]) <= GRAD_TOL
+    assert relerr(gU, g["grad_u_" + kind]) <= GRAD_TOL
 
 
+@pytest.mark.parametrize("kind", ["dss", "kc"])
 @pytest.mark.parametrize("m_ind,n", [(3, 128), (20, 2000), (32, 1204)])
-def test_fitc_dss_vs_oracle(ctx, m_ind, n):
+def test_fitc_dss_vs_oracle(ctx, m_ind, n, kind):
     from gpscore_b200 import synth, lib as L
     from oracle import woodbury as WB
     X, y = synth.kin40k_like(n, seed=70)
     theta = synth.hyper_point("P2")
     U = synth.inducing_init(m_ind, seed=71) * 2 - 1
     ctx.set_data(_dev(X), _dev(y))
-    val, grad, gU = ctx.fitc_eval(theta, U, "dss")
-    oval, og, ogU = WB.fitc_block_obj_grad(X, y, U, theta, "dss")
+    val, grad, gU = ctx.fitc_eval(theta, U, kind)
+    oval, og, ogU = WB.fitc_block_obj_grad(X, y, U, theta, kind)
     assert abs(val - oval) <= OBJ_TOL * abs(oval)
     assert relerr(grad, og) <= GRAD_TOL and relerr(gU, ogU) <= GRAD_TOL
     ctx.set_data(_dev(X[:n - 1]), _dev(y[:n - 1]))      # 4 does not divide N: refused like the script's fold code
     with pytest.raises(L.GpsError):
-        ctx.fitc_eval(theta, U, "dss")
+        ctx.fitc_eval(theta, U, kind)
