@@ -26,7 +26,8 @@ from gpscore_b200 import synth  # noqa: E402
 # (score, iterations, learning rate, learning rate of the inducing inputs) as in the scripts
 FULL_RUNS = [("crps", 400, 1.0, None), ("nlml", 400, 0.0005, None), ("logs", 500, 0.05, None),         # KF:220,238 / 312,328 / 405,415
              ("dss", 150, 0.001, None)]                                                                   # KF:487,498 (4-fold DSS)
-FITC_RUNS = [("crps", 2000, 1.0, 1.0), ("nlml", 3000, 0.0001, 0.001), ("logs", 3000, 0.2, 0.2)]          # K20:207,220 / 315,326 / 417,430
+FITC_RUNS = [("crps", 2000, 1.0, 1.0), ("nlml", 3000, 0.0001, 0.001), ("logs", 3000, 0.2, 0.2),         # K20:207,220 / 315,326 / 417,430
+             ("dss", 3000, 0.001, 0.001), ("kc", 3000, 0.1, 0.1)]                                         # K20:523,537 / 655,668
 
 
 def fit(train_x, train_y, score, itr, lr, lr2, fitc, m, seed):
