@@ -68,6 +68,24 @@ def sharded_metrics(local_sums, n_total, group=None):
             "msll": (s[2] - s[4]) / n, "coverage": s[5] / n}
 
 
+def sharded_predict_metrics(ctx, theta, Xs, ys, inducing_x=None, group=None):
+    """Prediction + test scoring split by rows of the test set: every rank predicts its
+    contiguous block of test rows with its own context (which holds the full training set; for FITC the
+    M x M factors are replicated) and the six metric sums are all-reduced.  Returns the metric dict."""
+    rank, size = world()
+    t = int(Xs.shape[0])
+    lo, hi = row_block(t, rank, size)
+    if hi > lo:
+        if inducing_x is None:
+            mean, var = ctx.full_predict(theta, Xs[lo:hi])
+        else:
+            mean, var = ctx.fitc_predict(theta, inducing_x, Xs[lo:hi])
+        _, sums = ctx.test_metrics(mean, var, ys[lo:hi], return_sums=True)
+    else:
+        sums = np.zeros(6)
+    return sharded_metrics(sums, t, group)
+
+
 def sharded_grid(eval_fn, ls, sd, group=None, device=None):
     """Evaluate eval_fn(ls_subset, sd_subset) -> values on this rank's round-robin share of the grid
     and combine: every rank returns the full vector (the input of CP:114's `matrix(..., nrow=50)`)."""
