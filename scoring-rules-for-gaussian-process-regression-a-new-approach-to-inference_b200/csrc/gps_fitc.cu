@@ -1898,7 +1898,7 @@ int run_small3(gps_ctx* ctx, const double* part, int nblocks, const double* acc2
 constexpr int REDUCE_GROUPS = 16;
 int pre_reduce(gps_ctx* ctx, const double** part, int* nblocks, int len) {
   auto& f = ctx->fitc;
-  if (*nblocks <= 8 * REDUCE_GROUPS) return GPS_OK;
+  if (*nblocks <= 2 * REDUCE_GROUPS) return GPS_OK;
   const int per = (*nblocks + REDUCE_GROUPS - 1) / REDUCE_GROUPS;
   dim3 grid((len + 127) / 128, REDUCE_GROUPS);
   fitc_reduce_stage_kernel<<<grid, 128, 0, ctx->stream>>>(*part, *nblocks, len, per, f.part2.p);
