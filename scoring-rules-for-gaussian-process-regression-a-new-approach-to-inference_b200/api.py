@@ -210,17 +210,23 @@ class Context:
         self._check(self._lib.gps_fitc_loo(self._h, m.data_ptr(), v.data_ptr()))
         return m.view(-1, 1), v.view(-1, 1)
 
-    def fitc_predict(self, theta, U, Xs, jitter=JITTER, score="nlml"):
+    def fitc_predict(self, theta, U, Xs, jitter=JITTER, score="nlml", force_matrix_form=False):
         """Predictive mean / variance of K20:270-277 (diagonal only) at Xs."""
-        l1, l2, _ = self.fitc_acc_len(_host_vec(U).size // self.D)
         th = self._theta(theta)
         Uh = _host_vec(U)
         M = Uh.size // self.D
-        a1 = torch.zeros(l1, dtype=torch.float64, device=self.device)
-        a2 = torch.zeros(l2, dtype=torch.float64, device=self.device)
-        self._check(self._lib.gps_fitc_begin(self._h, _dp(th), _dp(Uh), M, float(jitter), _L.SCORES[score], self.N))
-        self._check(self._lib.gps_fitc_pass1(self._h, a1.data_ptr()))
-        self._check(self._lib.gps_fitc_pass2(self._h, a1.data_ptr(), a2.data_ptr()))
+        if M > 32 or force_matrix_form:
+            # matrix form (csrc/gps_fitc_large.cu): an objective-only evaluation leaves the factors in place
+            obj = np.zeros(1)
+            self._check(self._lib.gps_fitc_eval(self._h, _dp(th), _dp(Uh), M, float(jitter), _L.SCORES[score],
+                                                _dp(obj), None, None))
+        else:
+            l1, l2, _ = self.fitc_acc_len(M)
+            a1 = torch.zeros(l1, dtype=torch.float64, device=self.device)
+            a2 = torch.zeros(l2, dtype=torch.float64, device=self.device)
+            self._check(self._lib.gps_fitc_begin(self._h, _dp(th), _dp(Uh), M, float(jitter), _L.SCORES[score], self.N))
+            self._check(self._lib.gps_fitc_pass1(self._h, a1.data_ptr()))
+            self._check(self._lib.gps_fitc_pass2(self._h, a1.data_ptr(), a2.data_ptr()))
         Xs = _as_f64(Xs)
         T = int(Xs.shape[0])
         m = torch.empty(T, dtype=torch.float64, device=self.device)

@@ -135,6 +135,20 @@ int gps_factor_and_invert(gps_ctx* ctx, bool want_logdet) {
   return GPS_OK;
 }
 
+// free a child context (it borrows the parent's stream)
+void gps_ctx_release(gps_ctx* ch) {
+  ch->stream = nullptr;
+  ch->own_stream = nullptr;
+  DevBuf* cb[] = {&ch->Kb, &ch->Xb, &ch->Sb, &ch->vecs, &ch->red, &ch->params};
+  for (DevBuf* b : cb)
+    if (b->p) cudaFree(b->p);
+  if (ch->d_info) cudaFree(ch->d_info);
+  if (ch->d_tasks) cudaFree(ch->d_tasks);
+  for (auto e : ch->potrf_events) cudaEventDestroy(e);
+  if (ch->panel_stream) cudaStreamDestroy(ch->panel_stream);
+  delete ch;
+}
+
 extern "C" {
 
 const char* gps_version(void) { return "gpscore-b200 0.1 (sm_100a)"; }
@@ -195,19 +209,8 @@ void gps_destroy(gps_ctx* ctx) {
     cudaEventDestroy(pr.first);
     cudaEventDestroy(pr.second);
   }
-  if (ctx->fold_ctx) {
-    gps_ctx* ch = ctx->fold_ctx;
-    ch->stream = nullptr;
-    ch->own_stream = nullptr;
-    DevBuf* cb[] = {&ch->Kb, &ch->Xb, &ch->Sb, &ch->vecs, &ch->red, &ch->params};
-    for (DevBuf* b : cb)
-      if (b->p) cudaFree(b->p);
-    if (ch->d_info) cudaFree(ch->d_info);
-    if (ch->d_tasks) cudaFree(ch->d_tasks);
-    for (auto e : ch->potrf_events) cudaEventDestroy(e);
-    if (ch->panel_stream) cudaStreamDestroy(ch->panel_stream);
-    delete ch;
-  }
+  if (ctx->fold_ctx) gps_ctx_release(ctx->fold_ctx);
+  gps_fitc_large_free(ctx);
   for (auto e : ctx->potrf_events) cudaEventDestroy(e);
   for (auto e : ctx->stage_ev) if (e) cudaEventDestroy(e);
   if (ctx->panel_stream) cudaStreamDestroy(ctx->panel_stream);

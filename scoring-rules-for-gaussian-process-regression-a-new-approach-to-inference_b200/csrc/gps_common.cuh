@@ -26,6 +26,8 @@ struct DevBuf {
   size_t n = 0;  // doubles
 };
 
+struct gps_fitc_large;
+
 struct gps_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;      // stream all work is enqueued on
@@ -97,9 +99,12 @@ struct gps_ctx {
     DevBuf part2;         // first-stage sums of the partials (large grids)
     DevBuf acc1, acc2, acc3;  // single-GPU accumulators
     bool begun = false, pass2_done = false, tile = true, loo_ok = false;
+    bool large = false;   // last evaluation ran the matrix form (gps_fitc_large.cu)
     DevBuf accf;          // per-fold accumulators of the block objectives
     std::vector<double> host_out;
   } fitc;
+  gps_fitc_large* fl = nullptr;   // matrix-form FITC state (M > 32)
+  int fitc_large_min_m = 33;      // M from which gps_fitc_eval uses the matrix form (debug knob)
 };
 
 int gps_fail(gps_ctx* c, int code, const char* fmt, ...);
@@ -128,6 +133,12 @@ int gps_upload_params(gps_ctx* ctx, const double* theta, int D, double* ea_out, 
 int gps_upload_tasks2(gps_ctx* ctx, const std::vector<GemmTask>& h);
 int gps_factor_and_invert(gps_ctx* ctx, bool want_logdet);
 int gps_full_dss(gps_ctx* ctx, double* par_obj, double* par_gsum, bool want_grad);
+void gps_ctx_release(gps_ctx* child);
+// gps_fitc_large.cu
+void gps_fitc_large_free(gps_ctx* ctx);
+int gps_fitc_large_eval(gps_ctx* ctx, const double* theta, const double* U, int M, double jitter, int score,
+                        double* obj, double* grad_theta, double* grad_U);
+int gps_fitc_large_predict(gps_ctx* ctx, const double* dXs, int64_t T, double* dm, double* dv);
 // offsets (doubles) into ctx->params and rows of ctx->vecs
 constexpr int PAR_OBJ = 128;
 constexpr int PAR_GSUM = 136;

@@ -1941,7 +1941,7 @@ int gps_fitc_begin(gps_ctx* ctx, const double* theta, const double* U, int M, do
   if (block_obj && ctx->fitc_variant == 0)
     return gps_fail(ctx, GPS_EINVAL, "fitc dss/kc: only the tile formulation of the row passes implements them");
   if (M <= 0 || M > 32)
-    return gps_fail(ctx, GPS_EINVAL, "fitc: M=%d outside the fused row-kernel range 1..32", M);
+    return gps_fail(ctx, GPS_EINVAL, "fitc: M=%d outside the fused row-kernel range 1..32 (the staged/sharded protocol has no matrix form)", M);
   if (ctx->D > 15) return gps_fail(ctx, GPS_EINVAL, "fitc: D=%d > 15 not supported by the row kernels", ctx->D);
   GPS_CUDA(cudaSetDevice(ctx->device));
   auto& f = ctx->fitc;
@@ -1949,7 +1949,7 @@ int gps_fitc_begin(gps_ctx* ctx, const double* theta, const double* U, int M, do
   const int MP = (M + 7) / 8 * 8;
   const int64_t N = ctx->N;
   f.M = M; f.MP = MP; f.score = score; f.jitter = jitter; f.world_n = world_n > 0 ? world_n : N;
-  f.begun = false; f.pass2_done = false;
+  f.begun = false; f.pass2_done = false; f.large = false;
   f.tile = ctx->fitc_variant != 0;
   GPS_CHECK(gps_ensure(ctx, ctx->params, PAR_LEN));
   if (!ctx->d_info) GPS_CUDA(cudaMalloc(&ctx->d_info, sizeof(int)));
@@ -2057,6 +2057,11 @@ int gps_fitc_finish(gps_ctx* ctx, const double* acc2, const double* acc3, double
 int gps_fitc_eval(gps_ctx* ctx, const double* theta, const double* U, int M, double jitter, int score,
                   double* obj, double* grad_theta, double* grad_U) {
   if (!ctx) return GPS_EINVAL;
+  if (M >= ctx->fitc_large_min_m) {
+    if (ctx->N == 0) return gps_fail(ctx, GPS_ESTATE, "fitc: call gps_set_data first");
+    if (!theta || !U) return gps_fail(ctx, GPS_EINVAL, "fitc: bad arguments");
+    return gps_fitc_large_eval(ctx, theta, U, M, jitter, score, obj, grad_theta, grad_U);
+  }
   GPS_CHECK(gps_fitc_begin(ctx, theta, U, M, jitter, score, ctx->N));
   auto& f = ctx->fitc;
   // single GPU: the same row kernels; the per-block partials are summed inside the replicated
@@ -2168,8 +2173,12 @@ int gps_fitc_predict(gps_ctx* ctx, const double* Xs, int64_t T, double* mean, do
     dm = ctx->stage[1].p;
     dv = ctx->stage[2].p;
   }
-  MP_DISPATCH(f.MP, GPS_CHECK(run_pred<MPC>(ctx, dXs, T, dm, dv)));
-  ctx->launches++;
+  if (f.large) {
+    GPS_CHECK(gps_fitc_large_predict(ctx, dXs, T, dm, dv));
+  } else {
+    MP_DISPATCH(f.MP, GPS_CHECK(run_pred<MPC>(ctx, dXs, T, dm, dv)));
+    ctx->launches++;
+  }
   if (!dev) {
     GPS_CUDA(cudaMemcpyAsync(mean, dm, T * sizeof(double), cudaMemcpyDefault, ctx->stream));
     GPS_CUDA(cudaMemcpyAsync(var, dv, T * sizeof(double), cudaMemcpyDefault, ctx->stream));

@@ -1,0 +1,796 @@
+// FITC objective + gradient for M > 32 inducing points: the "matrix form" of the three row passes.
+//
+// The fused row kernels of gps_fitc.cu keep a row's M-vector in registers, which stops paying
+// beyond M = 32.  BASELINE.json's scaling sweep goes to M = 1024, where the work is GEMM-shaped
+// (2 N M^2 flops per product, ~10 products per evaluation), so this file runs the same Woodbury
+// algebra (oracle/woodbury.py, replacing K20:222-236 / 329-344 / 434-452) on [Mp][Npp] row-major
+// matrices with the task-list DMMA tile GEMM of gps_gemm.cu:
+//
+//   A = Kuu + jitter I = L_A L_A'          blocked POTRF/TRTRI on an M-sized child context
+//   V = L_A^-1 Kuf                          GEMM  (lower-triangular k-range)
+//   C = I + V diag(1/lam) V'                split-K GEMM with the k-scaling vector, fixed-order reduce
+//   W = L_C^-1 V                            GEMM
+//   R = W diag(rbar) W',  S = Vbar V'       split-K GEMMs
+//   CV = Cbar V,  L_C^-T Wbar,  L_A^-T Vbar GEMMs (upper-triangular k-range for the transposed factors)
+//   M x M adjoints (Cholesky adjoint Phi)   tile GEMMs on M x M operands + element-wise kernels
+//
+// Everything per-row (lambda, d, alpha, the score seeds, lambda_bar) is a column pass over the
+// [Mp][Npp] matrices with i as the coalesced index.  Pad rows (m >= M) and pad columns (i >= N)
+// hold zeros throughout, so no kernel needs bounds in the GEMMs.  Single GPU; LOO CRPS / log score
+// and NLML (the block objectives stay with the fused M <= 32 kernels).
+#include "gps_common.cuh"
+
+namespace {
+
+constexpr int DMAX = 16;
+constexpr double HALF_LOG_2PI = 0.91893853320467274178;
+
+enum { SM_KUU = 0, SM_LA, SM_LAI, SM_LC, SM_LCI, SM_R, SM_SW, SM_Y, SM_Z, SM_CBAR, SM_S, SM_ABAR, SM_COUNT };
+enum { RV_LAM = 0, RV_IL, RV_YL, RV_R, RV_ABAR, RV_DBAR, RV_LBAR, RV_RBAR, RV_TBAR, RV_LOOM, RV_LOOV, RV_COUNT };
+enum { MV_VY = 0, MV_BETA, MV_BBAR, MV_VYBAR, MV_COUNT };
+// small results copied to the host: [0] obj, [1] sum lambda_bar, then two gradient blocks
+constexpr int OUT_OBJ = 0, OUT_SUMLB = 1, OUT_G1 = 8;
+
+}  // namespace
+
+struct gps_fitc_large {
+  int64_t Npp = 0;
+  int Mp = 0, M = 0, D = 0;
+  DevBuf Kuf, V, W, T1, T2;   // [Mp][Npp]
+  DevBuf sm, rv, mv, part, out, U;
+  GemmTask* tasks = nullptr;
+  size_t tasks_cap = 0;
+  gps_ctx::Range t_low, t_up, t_full, t_mm, t_sk_low, t_sk_full;
+  int S = 1;                  // split-K chunks
+  gps_ctx* ch = nullptr;      // child context for the M-sized factorisations
+  bool ready = false;
+  std::vector<double> h_out;
+};
+
+namespace {
+
+// ---- element-wise / reduction kernels ------------------------------------------------------------
+
+// K (Mp x Mp from the Gram kernel, pad zero) -> Kuu copy (no jitter) and A = Kuu + jitter I, identity pad
+__global__ void __launch_bounds__(256)
+kuu_fix_kernel(double* __restrict__ K, int Mp, int M, double jitter, double* __restrict__ Kuu) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (int64_t)Mp * Mp) return;
+  const int r = (int)(e / Mp), c = (int)(e - (int64_t)r * Mp);
+  if (r < M && c < M) {
+    const double v = K[e];
+    Kuu[e] = v;
+    K[e] = r == c ? v + jitter : v;
+  } else {
+    Kuu[e] = 0.0;
+    K[e] = r == c ? 1.0 : 0.0;
+  }
+}
+
+// dst = tril(src): the blocked factorisation leaves the strict upper block triangle undefined
+__global__ void __launch_bounds__(256)
+tri_copy_kernel(const double* __restrict__ src, double* __restrict__ dst, int Mp) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (int64_t)Mp * Mp) return;
+  const int r = (int)(e / Mp), c = (int)(e - (int64_t)r * Mp);
+  dst[e] = c <= r ? src[e] : 0.0;
+}
+
+// lam_i = e^a + sn2 - |V_:i|^2 ; il = 1/lam ; yl = y/lam   (pad columns: il = yl = 0)
+__global__ void __launch_bounds__(256)
+col_lambda_kernel(const double* __restrict__ V, int64_t ld, int M, int64_t N, int64_t Npp,
+                  const double* __restrict__ y, const double* __restrict__ par, double* __restrict__ lam,
+                  double* __restrict__ il, double* __restrict__ yl) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Npp) return;
+  if (i >= N) {
+    lam[i] = 1.0; il[i] = 0.0; yl[i] = 0.0;
+    return;
+  }
+  double q = 0.0;
+  for (int m = 0; m < M; ++m) {
+    const double v = V[(int64_t)m * ld + i];
+    q = fma(v, v, q);
+  }
+  const double l = par[0] - q + par[1];
+  lam[i] = l;
+  il[i] = 1.0 / l;
+  yl[i] = y[i] / l;
+}
+
+// out[r] = sum_{i<n} Mat[r][i] x[i]   (one block per row, fixed order)
+__global__ void __launch_bounds__(256)
+rowdot_kernel(const double* __restrict__ Mat, int64_t ld, int64_t n, const double* __restrict__ x,
+              double* __restrict__ out) {
+  __shared__ double sh[32];
+  const double* row = Mat + (int64_t)blockIdx.x * ld;
+  double s = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) s = fma(row[i], x[i], s);
+  s = block_sum(s, sh);
+  if (threadIdx.x == 0) out[blockIdx.x] = s;
+}
+
+// out[c] = sum_k Mat[k][c] x[k]
+__global__ void __launch_bounds__(256)
+matvec_t_kernel(const double* __restrict__ Mat, int Mp, const double* __restrict__ x, double* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= Mp) return;
+  double s = 0.0;
+  for (int k = 0; k < Mp; ++k) s = fma(Mat[(int64_t)k * Mp + c], x[k], s);
+  out[c] = s;
+}
+
+// out = sum_s part[s] (+ I); lower tiles only are valid when `lower`: the upper triangle is mirrored
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(const double* __restrict__ part, int S, int Mp, double* __restrict__ out, int lower,
+                     int add_identity) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t MM = (int64_t)Mp * Mp;
+  if (e >= MM) return;
+  const int r = (int)(e / Mp), c = (int)(e - (int64_t)r * Mp);
+  int64_t src = e;
+  if (lower && (c / GPS_TILE) > (r / GPS_TILE)) src = (int64_t)c * Mp + r;
+  double s = 0.0;
+  for (int k = 0; k < S; ++k) s += part[(int64_t)k * MM + src];
+  if (add_identity && r == c) s += 1.0;
+  out[e] = s;
+}
+
+// r_i = |W_:i|^2, alpha_i = (y_i - W_:i . beta)/lam_i, d_i = 1/lam_i - r_i/lam_i^2
+__global__ void __launch_bounds__(256)
+col_w_kernel(const double* __restrict__ W, int64_t ld, int M, int64_t N, int64_t Npp,
+             const double* __restrict__ beta, const double* __restrict__ y, const double* __restrict__ il,
+             double* __restrict__ rr, double* __restrict__ alpha, double* __restrict__ dd) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Npp) return;
+  if (i >= N) {
+    rr[i] = 0.0;
+    return;
+  }
+  double r = 0.0, wb = 0.0;
+  for (int m = 0; m < M; ++m) {
+    const double w = W[(int64_t)m * ld + i];
+    r = fma(w, w, r);
+    wb = fma(w, beta[m], wb);
+  }
+  const double l = il[i];
+  rr[i] = r;
+  alpha[i] = (y[i] - wb) * l;
+  dd[i] = l - r * l * l;
+}
+
+// NLML value and seeds: obj = sum 1/2 log lam + 1/2 y alpha + N/2 log 2pi + sum log diag L_C
+__global__ void __launch_bounds__(1024)
+nlml_rows_kernel(int64_t N, int64_t Npp, const double* __restrict__ lam, const double* __restrict__ y,
+                 const double* __restrict__ alpha, const double* __restrict__ LC, int Mp, int M,
+                 double* __restrict__ abar, double* __restrict__ dbar, double* __restrict__ obj) {
+  __shared__ double sh[32];
+  double s = 0.0;
+  for (int64_t i = threadIdx.x; i < Npp; i += blockDim.x) {
+    if (i < N) {
+      s += 0.5 * log(lam[i]) + 0.5 * y[i] * alpha[i];
+      abar[i] = 0.5 * y[i];
+    } else {
+      abar[i] = 0.0;
+    }
+    dbar[i] = 0.0;
+  }
+  for (int m = threadIdx.x; m < M; m += blockDim.x) s += log(LC[(int64_t)m * Mp + m]);
+  s = block_sum(s, sh);
+  if (threadIdx.x == 0) obj[0] = s + (double)N * HALF_LOG_2PI;
+}
+
+// lam_bar0, rbar, tbar from the score seeds
+__global__ void __launch_bounds__(256)
+seed_kernel(int64_t N, int64_t Npp, int nlml, const double* __restrict__ il, const double* __restrict__ rr,
+            const double* __restrict__ alpha, const double* __restrict__ abar, const double* __restrict__ dbar,
+            double* __restrict__ lbar, double* __restrict__ rbar, double* __restrict__ tbar) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Npp) return;
+  if (i >= N) {
+    lbar[i] = 0.0; rbar[i] = 0.0; tbar[i] = 0.0;
+    return;
+  }
+  const double l = il[i], ab = abar[i], db = dbar[i], r = rr[i];
+  double lb = nlml ? 0.5 * l : 0.0;
+  lb += db * (-l * l + 2.0 * r * l * l * l) - ab * alpha[i] * l;
+  lbar[i] = lb;
+  rbar[i] = -db * l * l;
+  tbar[i] = -ab * l;
+}
+
+// SW = beta bbar' + 2 R + bbar beta'
+__global__ void __launch_bounds__(256)
+sw_kernel(const double* __restrict__ beta, const double* __restrict__ bbar, const double* __restrict__ R, int Mp,
+          double* __restrict__ SW) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (int64_t)Mp * Mp) return;
+  const int r = (int)(e / Mp), c = (int)(e - (int64_t)r * Mp);
+  SW[e] = beta[r] * bbar[c] + 2.0 * R[e] + bbar[r] * beta[c];
+}
+
+// Lbar = -tril(Y) (+ diag(1/L_mm) for the log-determinant term of the NLML)
+__global__ void __launch_bounds__(256)
+lbar_kernel(const double* __restrict__ Y, const double* __restrict__ L, int Mp, int M, int add_diag,
+            double* __restrict__ Lbar) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (int64_t)Mp * Mp) return;
+  const int r = (int)(e / Mp), c = (int)(e - (int64_t)r * Mp);
+  double v = c <= r ? -Y[e] : 0.0;
+  if (add_diag && r == c && r < M) v += 1.0 / L[e];
+  Lbar[e] = v;
+}
+
+// Z = Phi(P) + Phi(P)' with Phi = lower triangle, diagonal halved
+__global__ void __launch_bounds__(256)
+phi_sym_kernel(const double* __restrict__ P, int Mp, double* __restrict__ Z) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (int64_t)Mp * Mp) return;
+  const int r = (int)(e / Mp), c = (int)(e - (int64_t)r * Mp);
+  Z[e] = c <= r ? P[e] : P[(int64_t)c * Mp + r];
+}
+
+// pass 3 column sweep: lam_bar -= (bbar . W_:i) y_i/lam^2 + (V_:i . CV_:i)/lam^2 ; W <- Wbar in place
+__global__ void __launch_bounds__(256)
+col_pass3_kernel(const double* __restrict__ V, const double* __restrict__ CV, double* __restrict__ W, int64_t ld,
+                 int M, int64_t N, const double* __restrict__ bbar, const double* __restrict__ beta,
+                 const double* __restrict__ y, const double* __restrict__ il, const double* __restrict__ tbar,
+                 const double* __restrict__ rbar, double* __restrict__ lbar) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const double tb = tbar[i], rb2 = 2.0 * rbar[i];
+  double bw = 0.0, s1 = 0.0;
+  for (int m = 0; m < M; ++m) {
+    const int64_t o = (int64_t)m * ld + i;
+    const double w = W[o];
+    bw = fma(bbar[m], w, bw);
+    s1 = fma(V[o], CV[o], s1);
+    W[o] = fma(rb2, w, tb * beta[m]);
+  }
+  const double l = il[i];
+  lbar[i] -= (bw * y[i] + s1) * l * l;
+}
+
+// Vbar = L_C^-T Wbar (already in T2) + vybar yl' + 2 CV diag(il) - 2 V diag(lam_bar)
+__global__ void __launch_bounds__(256)
+vbar_kernel(double* __restrict__ T2, const double* __restrict__ CV, const double* __restrict__ V, int64_t ld, int M,
+            int64_t N, const double* __restrict__ vybar, const double* __restrict__ yl,
+            const double* __restrict__ il, const double* __restrict__ lbar) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int m = blockIdx.y;
+  if (i >= N || m >= M) return;
+  const int64_t o = (int64_t)m * ld + i;
+  T2[o] += vybar[m] * yl[i] + 2.0 * CV[o] * il[i] - 2.0 * V[o] * lbar[i];
+}
+
+__global__ void __launch_bounds__(1024)
+vec_sum_kernel(const double* __restrict__ x, int64_t n, double* __restrict__ out) {
+  __shared__ double sh[32];
+  double s = 0.0;
+  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) s += x[i];
+  s = block_sum(s, sh);
+  if (threadIdx.x == 0) out[0] = s;
+}
+
+// Kernel-gradient partials of G = Kbar o Kmat ([M][n], row stride ld) against the points P[n][D]:
+//   sg[m] = sum_i G_mi,  sd[m][d] = sum_i G_mi (u_md - p_id)/l_d,  sb[d] = sum_mi G_mi ((u_md - p_id)/l_d)^2
+// One block = MT rows of G x one strided share of the columns; per-block partials in fixed slots.
+template <int MT, int DMX>
+__global__ void __launch_bounds__(256)
+kgrad_kernel(const double* __restrict__ Kbar, const double* __restrict__ Kmat, int64_t ld, int M, int64_t n,
+             const double* __restrict__ U, const double* __restrict__ P, int D, const double* __restrict__ par,
+             double* __restrict__ part) {
+  constexpr int NV = MT * (1 + DMX) + DMX;
+  __shared__ double us[MT][DMX];
+  __shared__ double red[8][NV];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int m0 = blockIdx.x * MT;
+  if (tid < MT * DMX) {
+    const int mm = tid / DMX, d = tid % DMX;
+    us[mm][d] = (m0 + mm < M && d < D) ? U[(int64_t)(m0 + mm) * D + d] * par[2 + d] : 0.0;
+  }
+  __syncthreads();
+  double sg[MT], sd[MT][DMX], sb[DMX];
+#pragma unroll
+  for (int mm = 0; mm < MT; ++mm) {
+    sg[mm] = 0.0;
+#pragma unroll
+    for (int d = 0; d < DMX; ++d) sd[mm][d] = 0.0;
+  }
+#pragma unroll
+  for (int d = 0; d < DMX; ++d) sb[d] = 0.0;
+  for (int64_t i = (int64_t)blockIdx.y * 256 + tid; i < n; i += (int64_t)256 * gridDim.y) {
+    double xs[DMX];
+#pragma unroll
+    for (int d = 0; d < DMX; ++d) xs[d] = d < D ? P[i * D + d] * par[2 + d] : 0.0;
+#pragma unroll
+    for (int mm = 0; mm < MT; ++mm) {
+      if (m0 + mm < M) {
+        const int64_t o = (int64_t)(m0 + mm) * ld + i;
+        const double g = Kbar[o] * Kmat[o];
+        sg[mm] += g;
+#pragma unroll
+        for (int d = 0; d < DMX; ++d) {
+          if (d < D) {
+            const double df = us[mm][d] - xs[d];
+            const double gd = g * df;
+            sd[mm][d] += gd;
+            sb[d] = fma(gd, df, sb[d]);
+          }
+        }
+      }
+    }
+  }
+  // block reduction of the NV accumulators
+#pragma unroll
+  for (int mm = 0; mm < MT; ++mm) {
+    const double v = warp_sum(sg[mm]);
+    if (lane == 0) red[warp][mm * (1 + DMX)] = v;
+#pragma unroll
+    for (int d = 0; d < DMX; ++d) {
+      const double w = warp_sum(sd[mm][d]);
+      if (lane == 0) red[warp][mm * (1 + DMX) + 1 + d] = w;
+    }
+  }
+#pragma unroll
+  for (int d = 0; d < DMX; ++d) {
+    const double w = warp_sum(sb[d]);
+    if (lane == 0) red[warp][MT * (1 + DMX) + d] = w;
+  }
+  __syncthreads();
+  if (tid < NV) {
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[w][tid];
+    part[((int64_t)blockIdx.y * gridDim.x + blockIdx.x) * NV + tid] = s;
+  }
+}
+
+// out[0] = sum G, out[1 + d] = g_b partial, out[1 + DMAX + m*D + d] = -(1/l_d) sum_i G (u - p)/l
+template <int MT, int DMX>
+__global__ void __launch_bounds__(256)
+kgrad_reduce_kernel(const double* __restrict__ part, int gx, int gy, int M, int D, const double* __restrict__ par,
+                    double* __restrict__ out) {
+  constexpr int NV = MT * (1 + DMX) + DMX;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t == 0) {
+    double s = 0.0;
+    for (int bx = 0; bx < gx; ++bx)
+      for (int by = 0; by < gy; ++by)
+        for (int mm = 0; mm < MT; ++mm) s += part[((int64_t)by * gx + bx) * NV + mm * (1 + DMX)];
+    out[0] = s;
+  } else if (t <= D) {
+    const int d = t - 1;
+    double s = 0.0;
+    for (int bx = 0; bx < gx; ++bx)
+      for (int by = 0; by < gy; ++by) s += part[((int64_t)by * gx + bx) * NV + MT * (1 + DMX) + d];
+    out[1 + d] = s;
+  } else if (t < 1 + DMAX) {
+    return;
+  } else {
+    const int e = t - (1 + DMAX);
+    if (e >= M * D) return;
+    const int m = e / D, d = e - m * D;
+    const int bx = m / MT, mm = m - bx * MT;
+    double s = 0.0;
+    for (int by = 0; by < gy; ++by) s += part[((int64_t)by * gx + bx) * NV + mm * (1 + DMX) + 1 + d];
+    out[1 + DMAX + e] = -s * par[2 + d];
+  }
+}
+
+// prediction columns: mean = Ws_:t . beta, var = sn2 + e^a - |Vs_:t|^2 + |Ws_:t|^2   (K20:76-83)
+__global__ void __launch_bounds__(256)
+col_predict_kernel(const double* __restrict__ Vs, const double* __restrict__ Ws, int64_t ld, int M, int64_t T,
+                   const double* __restrict__ beta, const double* __restrict__ par, double* __restrict__ mean,
+                   double* __restrict__ var) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= T) return;
+  double q = 0.0, r = 0.0, mb = 0.0;
+  for (int m = 0; m < M; ++m) {
+    const double v = Vs[(int64_t)m * ld + i], w = Ws[(int64_t)m * ld + i];
+    q = fma(v, v, q);
+    r = fma(w, w, r);
+    mb = fma(w, beta[m], mb);
+  }
+  mean[i] = mb;
+  var[i] = par[1] + par[0] - q + r;
+}
+
+// ---- host side -------------------------------------------------------------------------------------
+
+inline unsigned blocks_for(int64_t n, int t = 256) { return (unsigned)((n + t - 1) / t); }
+
+GemmTask make_task(int a_row, int b_row, int k0, int k1, int c_row, int c_col) {
+  GemmTask t;
+  t.a_row = a_row; t.b_row = b_row; t.k0 = k0; t.k1 = k1; t.c_row = c_row; t.c_col = c_col;
+  t.flags = 0; t.pad = 0;
+  return t;
+}
+
+// task lists for the shape (Mp, Npp); cached on the device
+int build_tasks(gps_ctx* ctx, gps_fitc_large* fl) {
+  const int mt = fl->Mp / GPS_TILE;
+  const int64_t nt = fl->Npp / GPS_TILE;
+  const int Mp = fl->Mp;
+  std::vector<GemmTask> h;
+  auto begin = [&](gps_ctx::Range& r) { r.off = h.size(); };
+  auto end = [&](gps_ctx::Range& r) { r.cnt = h.size() - r.off; };
+  // [Mp][Npp] outputs: row tile fastest so consecutive CTAs share the column panel of the big operand
+  begin(fl->t_low);
+  for (int64_t j = 0; j < nt; ++j)
+    for (int i = 0; i < mt; ++i)
+      h.push_back(make_task(i * GPS_TILE, (int)(j * GPS_TILE), 0, (i + 1) * GPS_TILE, i * GPS_TILE, (int)(j * GPS_TILE)));
+  end(fl->t_low);
+  begin(fl->t_up);
+  for (int64_t j = 0; j < nt; ++j)
+    for (int i = 0; i < mt; ++i)
+      h.push_back(make_task(i * GPS_TILE, (int)(j * GPS_TILE), i * GPS_TILE, Mp, i * GPS_TILE, (int)(j * GPS_TILE)));
+  end(fl->t_up);
+  begin(fl->t_full);
+  for (int64_t j = 0; j < nt; ++j)
+    for (int i = 0; i < mt; ++i)
+      h.push_back(make_task(i * GPS_TILE, (int)(j * GPS_TILE), 0, Mp, i * GPS_TILE, (int)(j * GPS_TILE)));
+  end(fl->t_full);
+  begin(fl->t_mm);
+  for (int i = 0; i < mt; ++i)
+    for (int j = 0; j < mt; ++j)
+      h.push_back(make_task(i * GPS_TILE, j * GPS_TILE, 0, Mp, i * GPS_TILE, j * GPS_TILE));
+  end(fl->t_mm);
+  // split-K over the rows of the data set: enough tasks for ~4 waves of 148 task slots
+  const int tl = mt * (mt + 1) / 2;
+  int64_t want = (4 * (int64_t)ctx->sm_count + tl - 1) / tl;
+  if (want < 1) want = 1;
+  if (want > nt) want = nt;
+  const int64_t per = (nt + want - 1) / want;
+  fl->S = (int)((nt + per - 1) / per);
+  begin(fl->t_sk_low);
+  for (int s = 0; s < fl->S; ++s) {
+    const int k0 = (int)(s * per * GPS_TILE), k1 = (int)std::min<int64_t>(fl->Npp, (s + 1) * per * GPS_TILE);
+    for (int i = 0; i < mt; ++i)
+      for (int j = 0; j <= i; ++j)
+        h.push_back(make_task(i * GPS_TILE, j * GPS_TILE, k0, k1, s * Mp + i * GPS_TILE, j * GPS_TILE));
+  }
+  end(fl->t_sk_low);
+  begin(fl->t_sk_full);
+  for (int s = 0; s < fl->S; ++s) {
+    const int k0 = (int)(s * per * GPS_TILE), k1 = (int)std::min<int64_t>(fl->Npp, (s + 1) * per * GPS_TILE);
+    for (int i = 0; i < mt; ++i)
+      for (int j = 0; j < mt; ++j)
+        h.push_back(make_task(i * GPS_TILE, j * GPS_TILE, k0, k1, s * Mp + i * GPS_TILE, j * GPS_TILE));
+  }
+  end(fl->t_sk_full);
+  if (h.size() > fl->tasks_cap) {
+    if (fl->tasks) cudaFree(fl->tasks);
+    fl->tasks = nullptr;
+    GPS_CUDA(cudaMalloc(&fl->tasks, h.size() * sizeof(GemmTask)));
+    fl->tasks_cap = h.size();
+  }
+  GPS_CUDA(cudaMemcpyAsync(fl->tasks, h.data(), h.size() * sizeof(GemmTask), cudaMemcpyHostToDevice, ctx->stream));
+  GPS_CUDA(cudaStreamSynchronize(ctx->stream));
+  return GPS_OK;
+}
+
+int ensure_child(gps_ctx* ctx, gps_fitc_large* fl) {
+  if (!fl->ch) {
+    fl->ch = new gps_ctx();
+    fl->ch->device = ctx->device;
+    fl->ch->sm_count = ctx->sm_count;
+  }
+  gps_ctx* ch = fl->ch;
+  ch->gemm_variant = ctx->gemm_variant;
+  ch->potf2_variant = ctx->potf2_variant;
+  ch->stream = ctx->stream;
+  ch->own_stream = nullptr;
+  ch->time_gemm = false;
+  const int r = gps_ensure_ws(ch, fl->Mp);
+  if (r != GPS_OK) return gps_fail(ctx, r, "fitc (matrix form): %s", ch->err.c_str());
+  return GPS_OK;
+}
+
+int setup(gps_ctx* ctx, int M) {
+  if (!ctx->fl) ctx->fl = new gps_fitc_large();
+  gps_fitc_large* fl = ctx->fl;
+  const int Mp = (int)gps_pad(M);
+  const int64_t Npp = ctx->Np;
+  const int D = ctx->D;
+  const bool reshape = fl->Mp != Mp || fl->Npp != Npp || fl->D != D;
+  fl->M = M;
+  if (reshape) {
+    fl->Mp = Mp; fl->Npp = Npp; fl->D = D;
+    const size_t big = (size_t)Mp * Npp;
+    GPS_CHECK(gps_ensure(ctx, fl->Kuf, big));
+    GPS_CHECK(gps_ensure(ctx, fl->V, big));
+    GPS_CHECK(gps_ensure(ctx, fl->W, big));
+    GPS_CHECK(gps_ensure(ctx, fl->T1, big));
+    GPS_CHECK(gps_ensure(ctx, fl->T2, big));
+    GPS_CHECK(gps_ensure(ctx, fl->sm, (size_t)SM_COUNT * Mp * Mp));
+    GPS_CHECK(gps_ensure(ctx, fl->rv, (size_t)RV_COUNT * Npp));
+    GPS_CHECK(gps_ensure(ctx, fl->mv, (size_t)MV_COUNT * Mp));
+    GPS_CHECK(gps_ensure(ctx, fl->U, (size_t)Mp * D));
+    GPS_CHECK(gps_ensure(ctx, ctx->fitc.rowv, (size_t)6 * ctx->N));
+    GPS_CHECK(build_tasks(ctx, fl));
+    const size_t kg = (size_t)8 * ctx->sm_count * (8 * (1 + DMAX) + DMAX) + 4096;
+    GPS_CHECK(gps_ensure(ctx, fl->part, std::max((size_t)fl->S * Mp * Mp, kg)));
+    GPS_CHECK(gps_ensure(ctx, fl->out, (size_t)OUT_G1 + 2 * (1 + DMAX + (size_t)Mp * D)));
+  }
+  // the Gram kernel writes only the live M x N block: the pad rows/columns must read as zeros
+  GPS_CUDA(cudaMemsetAsync(fl->Kuf.p, 0, (size_t)Mp * Npp * sizeof(double), ctx->stream));
+  GPS_CHECK(ensure_child(ctx, fl));
+  return GPS_OK;
+}
+
+int mm_gemm(gps_ctx* ctx, gps_fitc_large* fl, int kind, const double* A, const double* B, double* C, double alpha) {
+  return gps_gemm_tasks(ctx, kind, A, fl->Mp, B, fl->Mp, C, fl->Mp, alpha, 0.0, nullptr, false,
+                        fl->tasks + fl->t_mm.off, fl->t_mm.cnt);
+}
+
+int big_gemm(gps_ctx* ctx, gps_fitc_large* fl, int kind, const gps_ctx::Range& r, const double* A, const double* B,
+             double* C) {
+  return gps_gemm_tasks(ctx, kind, A, fl->Mp, B, fl->Npp, C, fl->Npp, 1.0, 0.0, nullptr, false, fl->tasks + r.off, r.cnt);
+}
+
+// out (Mp x Mp) = A diag(dvec) B' over the data rows, split-K with a fixed-order reduction
+int splitk(gps_ctx* ctx, gps_fitc_large* fl, const double* A, const double* B, const double* dvec, bool lower,
+           bool add_identity, double* out) {
+  const gps_ctx::Range& r = lower ? fl->t_sk_low : fl->t_sk_full;
+  GPS_CHECK(gps_gemm_tasks(ctx, GEMM_KC_KC, A, fl->Npp, B, fl->Npp, fl->part.p, fl->Mp, 1.0, 0.0, dvec, false,
+                           fl->tasks + r.off, r.cnt));
+  splitk_reduce_kernel<<<blocks_for((int64_t)fl->Mp * fl->Mp), 256, 0, ctx->stream>>>(fl->part.p, fl->S, fl->Mp, out,
+                                                                                      lower ? 1 : 0, add_identity ? 1 : 0);
+  GPS_LAUNCH_CHECK();
+  ctx->launches++;
+  return GPS_OK;
+}
+
+// factor the matrix in ch->Kb: L -> Lout, L^-1 -> Linv (both with an explicit zero upper triangle)
+int factor(gps_ctx* ctx, gps_fitc_large* fl, double* Lout, double* Linv, const char* what) {
+  gps_ctx* ch = fl->ch;
+  const int Mp = fl->Mp;
+  GPS_CUDA(cudaMemsetAsync(ch->d_info, 0, sizeof(int), ctx->stream));
+  int r = gps_potrf(ch, ch->Kb.p, ch->Xb.p, Mp);
+  if (r == GPS_OK) r = gps_trtri(ch, ch->Kb.p, ch->Xb.p, ch->Sb.p, Mp);
+  if (r != GPS_OK) return gps_fail(ctx, r, "fitc %s: %s", what, ch->err.c_str());
+  const unsigned nb = blocks_for((int64_t)Mp * Mp);
+  tri_copy_kernel<<<nb, 256, 0, ctx->stream>>>(ch->Kb.p, Lout, Mp);
+  GPS_LAUNCH_CHECK();
+  tri_copy_kernel<<<nb, 256, 0, ctx->stream>>>(ch->Xb.p, Linv, Mp);
+  GPS_LAUNCH_CHECK();
+  ctx->launches += 2 + ch->launches;
+  ch->launches = 0;
+  int info = 0;
+  GPS_CUDA(cudaMemcpyAsync(&info, ch->d_info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  GPS_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (info != 0) return gps_fail(ctx, GPS_ENOTPD, "fitc: %s not positive definite at pivot %d", what, info);
+  return GPS_OK;
+}
+
+// Abar = 1/2 L^-T (Phi(L' Lbar) + Phi(L' Lbar)') L^-1 with Lbar = -tril(L^-T Sx) (+ diag term)
+int chol_adjoint(gps_ctx* ctx, gps_fitc_large* fl, const double* L, const double* Linv, const double* Sx,
+                 int add_diag, double* out) {
+  const int Mp = fl->Mp;
+  const unsigned nb = blocks_for((int64_t)Mp * Mp);
+  double* sm = fl->sm.p;
+  const size_t MM = (size_t)Mp * Mp;
+  double *Y = sm + SM_Y * MM, *Z = sm + SM_Z * MM;
+  GPS_CHECK(mm_gemm(ctx, fl, GEMM_MC_MC, Linv, Sx, Y, 1.0));        // L^-T Sx
+  lbar_kernel<<<nb, 256, 0, ctx->stream>>>(Y, L, Mp, fl->M, add_diag, Z);
+  GPS_LAUNCH_CHECK();
+  GPS_CHECK(mm_gemm(ctx, fl, GEMM_MC_MC, L, Z, Y, 1.0));            // L' Lbar
+  phi_sym_kernel<<<nb, 256, 0, ctx->stream>>>(Y, Mp, Z);
+  GPS_LAUNCH_CHECK();
+  GPS_CHECK(mm_gemm(ctx, fl, GEMM_MC_MC, Linv, Z, Y, 1.0));         // L^-T Z
+  GPS_CHECK(mm_gemm(ctx, fl, GEMM_KC_MC, Y, Linv, out, 0.5));       // 1/2 (L^-T Z) L^-1
+  ctx->launches += 2;
+  return GPS_OK;
+}
+
+template <int MT, int DMX>
+int kgrad(gps_ctx* ctx, gps_fitc_large* fl, const double* Kbar, const double* Kmat, int64_t ld, int64_t n,
+          const double* P, double* out) {
+  const int M = fl->M, D = fl->D;
+  const int gx = (M + MT - 1) / MT;
+  int64_t gy = (4 * (int64_t)ctx->sm_count + gx - 1) / gx;
+  const int64_t cols = (n + 255) / 256;
+  if (gy > cols) gy = cols;
+  if (gy < 1) gy = 1;
+  constexpr int NV = MT * (1 + DMX) + DMX;
+  GPS_CHECK(gps_ensure(ctx, fl->part, (size_t)gx * gy * NV));
+  kgrad_kernel<MT, DMX><<<dim3(gx, (unsigned)gy), 256, 0, ctx->stream>>>(Kbar, Kmat, ld, M, n, fl->U.p, P, D, ctx->params.p,
+                                                                    fl->part.p);
+  GPS_LAUNCH_CHECK();
+  const int nthreads = 1 + DMAX + M * D;
+  kgrad_reduce_kernel<MT, DMX><<<blocks_for(nthreads), 256, 0, ctx->stream>>>(fl->part.p, gx, (int)gy, M, D, ctx->params.p, out);
+  GPS_LAUNCH_CHECK();
+  ctx->launches += 2;
+  return GPS_OK;
+}
+
+}  // namespace
+
+void gps_fitc_large_free(gps_ctx* ctx) {
+  gps_fitc_large* fl = ctx->fl;
+  if (!fl) return;
+  for (DevBuf* b : {&fl->Kuf, &fl->V, &fl->W, &fl->T1, &fl->T2, &fl->sm, &fl->rv, &fl->mv, &fl->part, &fl->out, &fl->U})
+    if (b->p) cudaFree(b->p);
+  if (fl->tasks) cudaFree(fl->tasks);
+  if (fl->ch) gps_ctx_release(fl->ch);
+  delete fl;
+  ctx->fl = nullptr;
+}
+
+int gps_fitc_large_eval(gps_ctx* ctx, const double* theta, const double* U, int M, double jitter, int score,
+                        double* obj, double* grad_theta, double* grad_U) {
+  if (score != GPS_CRPS && score != GPS_LOGS && score != GPS_NLML)
+    return gps_fail(ctx, GPS_EINVAL, "fitc: M=%d > 32 runs the matrix form, which implements crps / logs / nlml only", M);
+  if (ctx->D > DMAX) return gps_fail(ctx, GPS_EINVAL, "fitc: D=%d > %d not supported", ctx->D, DMAX);
+  if (M > 4096) return gps_fail(ctx, GPS_EINVAL, "fitc: M=%d > 4096 not supported", M);
+  GPS_CUDA(cudaSetDevice(ctx->device));
+  auto& f = ctx->fitc;
+  f.begun = false; f.pass2_done = false; f.loo_ok = false; f.large = false;
+  GPS_CHECK(gps_ensure(ctx, ctx->params, PAR_LEN));
+  if (!ctx->d_info) GPS_CUDA(cudaMalloc(&ctx->d_info, sizeof(int)));
+  GPS_CHECK(setup(ctx, M));
+  gps_fitc_large* fl = ctx->fl;
+  fl->ready = false;
+  gps_ctx* ch = fl->ch;
+  const int64_t N = ctx->N, Npp = fl->Npp;
+  const int D = ctx->D, Mp = fl->Mp;
+  const size_t MM = (size_t)Mp * Mp;
+  const bool want_grad = grad_theta || grad_U;
+  const bool nlml = score == GPS_NLML;
+  cudaStream_t st = ctx->stream;
+  double ea = 0, sn2 = 0;
+  GPS_CHECK(gps_upload_params(ctx, theta, D, &ea, &sn2));
+  f.M = M; f.MP = Mp; f.score = score; f.jitter = jitter; f.ea = ea; f.sn2 = sn2; f.world_n = N;
+  const double* par = ctx->params.p;
+  GPS_CUDA(cudaMemsetAsync(fl->U.p, 0, (size_t)Mp * D * sizeof(double), st));
+  GPS_CUDA(cudaMemcpyAsync(fl->U.p, U, (size_t)M * D * sizeof(double), cudaMemcpyDefault, st));
+  double* sm = fl->sm.p;
+  double* rv = fl->rv.p;
+  double* mv = fl->mv.p;
+  double* alpha = f.rowv.p + 4 * N;
+  double* dd = f.rowv.p + 5 * N;
+  const unsigned nbm = blocks_for((int64_t)MM), nbn = blocks_for(Npp);
+
+  // ---- A = Kuu + jitter I = L_A L_A' --------------------------------------------------------
+  GPS_CUDA(cudaMemsetAsync(ch->Kb.p, 0, MM * sizeof(double), st));
+  GPS_CHECK(gps_gram_rect(ctx, fl->U.p, M, fl->U.p, M, D, par, ch->Kb.p, Mp));
+  kuu_fix_kernel<<<nbm, 256, 0, st>>>(ch->Kb.p, Mp, M, jitter, sm + SM_KUU * MM);
+  GPS_LAUNCH_CHECK();
+  ctx->launches++;
+  GPS_CHECK(factor(ctx, fl, sm + SM_LA * MM, sm + SM_LAI * MM, "K_uu + jitter I"));
+
+  // ---- pass 1: Kuf, V, lambda; C = I + V diag(1/lam) V', vy = V (y/lam) ------------------------
+  GPS_CHECK(gps_gram_rect(ctx, fl->U.p, M, ctx->X.p, N, D, par, fl->Kuf.p, Npp));
+  GPS_CHECK(big_gemm(ctx, fl, GEMM_KC_MC, fl->t_low, sm + SM_LAI * MM, fl->Kuf.p, fl->V.p));
+  col_lambda_kernel<<<nbn, 256, 0, st>>>(fl->V.p, Npp, M, N, Npp, ctx->y.p, par, rv + RV_LAM * Npp, rv + RV_IL * Npp,
+                                         rv + RV_YL * Npp);
+  GPS_LAUNCH_CHECK();
+  rowdot_kernel<<<Mp, 256, 0, st>>>(fl->V.p, Npp, Npp, rv + RV_YL * Npp, mv + MV_VY * Mp);
+  GPS_LAUNCH_CHECK();
+  ctx->launches += 2;
+  GPS_CHECK(splitk(ctx, fl, fl->V.p, fl->V.p, rv + RV_IL * Npp, true, true, ch->Kb.p));
+  GPS_CHECK(factor(ctx, fl, sm + SM_LC * MM, sm + SM_LCI * MM, "I + V Lambda^-1 V'"));
+  rowdot_kernel<<<Mp, 256, 0, st>>>(sm + SM_LCI * MM, Mp, Mp, mv + MV_VY * Mp, mv + MV_BETA * Mp);
+  GPS_LAUNCH_CHECK();
+
+  // ---- pass 2: W, d, alpha, score + seeds ------------------------------------------------------
+  GPS_CHECK(big_gemm(ctx, fl, GEMM_KC_MC, fl->t_low, sm + SM_LCI * MM, fl->V.p, fl->W.p));
+  col_w_kernel<<<nbn, 256, 0, st>>>(fl->W.p, Npp, M, N, Npp, mv + MV_BETA * Mp, ctx->y.p, rv + RV_IL * Npp,
+                                    rv + RV_R * Npp, alpha, dd);
+  GPS_LAUNCH_CHECK();
+  ctx->launches += 2;
+  double* d_out = fl->out.p;
+  if (nlml) {
+    nlml_rows_kernel<<<1, 1024, 0, st>>>(N, Npp, rv + RV_LAM * Npp, ctx->y.p, alpha, sm + SM_LC * MM, Mp, M,
+                                         rv + RV_ABAR * Npp, rv + RV_DBAR * Npp, d_out + OUT_OBJ);
+    GPS_LAUNCH_CHECK();
+    ctx->launches++;
+  } else {
+    // alpha / d are N long (the layout gps_fitc_loo reads); the score kernel pads its outputs to Npp
+    GPS_CHECK(gps_loo_score(ctx, score, N, Npp, alpha, dd, ctx->y.p, rv + RV_ABAR * Npp, rv + RV_DBAR * Npp,
+                            rv + RV_LOOM * Npp, rv + RV_LOOV * Npp, d_out + OUT_OBJ));
+  }
+  f.pass2_done = true;
+  f.loo_ok = true;
+  f.large = true;
+  fl->ready = true;
+  fl->h_out.assign((size_t)OUT_G1 + 2 * (1 + DMAX + (size_t)M * D), 0.0);
+  if (!want_grad) {
+    GPS_CUDA(cudaMemcpyAsync(fl->h_out.data(), d_out, sizeof(double), cudaMemcpyDeviceToHost, st));
+    GPS_CUDA(cudaStreamSynchronize(st));
+    if (obj) *obj = fl->h_out[OUT_OBJ];
+    return GPS_OK;
+  }
+  seed_kernel<<<nbn, 256, 0, st>>>(N, Npp, nlml ? 1 : 0, rv + RV_IL * Npp, rv + RV_R * Npp, alpha, rv + RV_ABAR * Npp,
+                                   rv + RV_DBAR * Npp, rv + RV_LBAR * Npp, rv + RV_RBAR * Npp, rv + RV_TBAR * Npp);
+  GPS_LAUNCH_CHECK();
+  rowdot_kernel<<<Mp, 256, 0, st>>>(fl->W.p, Npp, Npp, rv + RV_TBAR * Npp, mv + MV_BBAR * Mp);
+  GPS_LAUNCH_CHECK();
+  ctx->launches += 3;
+  GPS_CHECK(splitk(ctx, fl, fl->W.p, fl->W.p, rv + RV_RBAR * Npp, true, false, sm + SM_R * MM));
+
+  // ---- M x M algebra: C_bar, vy_bar -------------------------------------------------------------
+  sw_kernel<<<nbm, 256, 0, st>>>(mv + MV_BETA * Mp, mv + MV_BBAR * Mp, sm + SM_R * MM, Mp, sm + SM_SW * MM);
+  GPS_LAUNCH_CHECK();
+  GPS_CHECK(chol_adjoint(ctx, fl, sm + SM_LC * MM, sm + SM_LCI * MM, sm + SM_SW * MM, nlml ? 1 : 0, sm + SM_CBAR * MM));
+  matvec_t_kernel<<<blocks_for(Mp), 256, 0, st>>>(sm + SM_LCI * MM, Mp, mv + MV_BBAR * Mp, mv + MV_VYBAR * Mp);
+  GPS_LAUNCH_CHECK();
+  ctx->launches += 2;
+
+  // ---- pass 3: lambda_bar, V_bar, Kuf_bar; S = V_bar V' -------------------------------------------
+  GPS_CHECK(big_gemm(ctx, fl, GEMM_KC_MC, fl->t_full, sm + SM_CBAR * MM, fl->V.p, fl->T1.p));     // CV
+  col_pass3_kernel<<<blocks_for(N), 256, 0, st>>>(fl->V.p, fl->T1.p, fl->W.p, Npp, M, N, mv + MV_BBAR * Mp,
+                                                  mv + MV_BETA * Mp, ctx->y.p, rv + RV_IL * Npp, rv + RV_TBAR * Npp,
+                                                  rv + RV_RBAR * Npp, rv + RV_LBAR * Npp);
+  GPS_LAUNCH_CHECK();
+  GPS_CHECK(big_gemm(ctx, fl, GEMM_MC_MC, fl->t_up, sm + SM_LCI * MM, fl->W.p, fl->T2.p));        // L_C^-T Wbar
+  vbar_kernel<<<dim3(blocks_for(N), M), 256, 0, st>>>(fl->T2.p, fl->T1.p, fl->V.p, Npp, M, N, mv + MV_VYBAR * Mp,
+                                                      rv + RV_YL * Npp, rv + RV_IL * Npp, rv + RV_LBAR * Npp);
+  GPS_LAUNCH_CHECK();
+  GPS_CHECK(big_gemm(ctx, fl, GEMM_MC_MC, fl->t_up, sm + SM_LAI * MM, fl->T2.p, fl->T1.p));       // Kuf_bar
+  GPS_CHECK(splitk(ctx, fl, fl->T2.p, fl->V.p, nullptr, false, false, sm + SM_S * MM));
+  vec_sum_kernel<<<1, 1024, 0, st>>>(rv + RV_LBAR * Npp, N, d_out + OUT_SUMLB);
+  GPS_LAUNCH_CHECK();
+  ctx->launches += 3;
+  const size_t glen = 1 + DMAX + (size_t)M * D;
+  if (D <= 8) {
+    GPS_CHECK((kgrad<4, 8>(ctx, fl, fl->T1.p, fl->Kuf.p, Npp, N, ctx->X.p, d_out + OUT_G1)));
+  } else {
+    GPS_CHECK((kgrad<2, 16>(ctx, fl, fl->T1.p, fl->Kuf.p, Npp, N, ctx->X.p, d_out + OUT_G1)));
+  }
+
+  // ---- finish: A_bar through the Cholesky adjoint of L_A, Kuu gradient ----------------------------
+  GPS_CHECK(chol_adjoint(ctx, fl, sm + SM_LA * MM, sm + SM_LAI * MM, sm + SM_S * MM, 0, sm + SM_ABAR * MM));
+  if (D <= 8) {
+    GPS_CHECK((kgrad<4, 8>(ctx, fl, sm + SM_ABAR * MM, sm + SM_KUU * MM, Mp, M, fl->U.p, d_out + OUT_G1 + glen)));
+  } else {
+    GPS_CHECK((kgrad<2, 16>(ctx, fl, sm + SM_ABAR * MM, sm + SM_KUU * MM, Mp, M, fl->U.p, d_out + OUT_G1 + glen)));
+  }
+  GPS_CUDA(cudaMemcpyAsync(fl->h_out.data(), d_out, (OUT_G1 + 2 * glen) * sizeof(double), cudaMemcpyDeviceToHost, st));
+  GPS_CUDA(cudaStreamSynchronize(st));
+  const double* h = fl->h_out.data();
+  const double* g1 = h + OUT_G1;
+  const double* g2 = g1 + glen;
+  if (obj) *obj = h[OUT_OBJ];
+  if (grad_theta) {
+    grad_theta[0] = g1[0] + ea * h[OUT_SUMLB] + g2[0];
+    for (int d = 0; d < D; ++d) grad_theta[1 + d] = g1[1 + d] + g2[1 + d];
+    grad_theta[D + 1] = sn2 * h[OUT_SUMLB];
+  }
+  if (grad_U)
+    for (int e = 0; e < M * D; ++e) grad_U[e] = g1[1 + DMAX + e] + 2.0 * g2[1 + DMAX + e];
+  return GPS_OK;
+}
+
+// prediction at the factors of the last evaluation, test rows in chunks
+int gps_fitc_large_predict(gps_ctx* ctx, const double* dXs, int64_t T, double* dm, double* dv) {
+  gps_fitc_large* fl = ctx->fl;
+  if (!fl || !fl->ready) return gps_fail(ctx, GPS_ESTATE, "fitc_predict: no evaluation at this theta, U");
+  const int Mp = fl->Mp, M = fl->M, D = fl->D;
+  const size_t MM = (size_t)Mp * Mp;
+  const int mt = Mp / GPS_TILE;
+  // the evaluation's [Mp][Npp] scratch holds the chunk: Ks -> T1, Vs -> T2, Ws -> W
+  const int64_t chunk = std::min<int64_t>(fl->Npp, (int64_t)1 << 16);
+  const double* par = ctx->params.p;
+  double* sm = fl->sm.p;
+  for (int64_t t0 = 0; t0 < T; t0 += chunk) {
+    const int64_t tc = std::min(chunk, T - t0), tp = gps_pad(tc);
+    std::vector<GemmTask> tasks;
+    for (int64_t j = 0; j < tp / GPS_TILE; ++j)
+      for (int i = 0; i < mt; ++i)
+        tasks.push_back(make_task(i * GPS_TILE, (int)(j * GPS_TILE), 0, (i + 1) * GPS_TILE, i * GPS_TILE, (int)(j * GPS_TILE)));
+    GPS_CHECK(gps_upload_tasks2(ctx, tasks));
+    GPS_CUDA(cudaMemsetAsync(fl->T1.p, 0, (size_t)Mp * tp * sizeof(double), ctx->stream));
+    GPS_CHECK(gps_gram_rect(ctx, fl->U.p, M, dXs + t0 * D, tc, D, par, fl->T1.p, tp));
+    GPS_CHECK(gps_gemm_tasks(ctx, GEMM_KC_MC, sm + SM_LAI * MM, Mp, fl->T1.p, tp, fl->T2.p, tp, 1.0, 0.0, nullptr, false,
+                             ctx->d_tasks2, tasks.size()));
+    GPS_CHECK(gps_gemm_tasks(ctx, GEMM_KC_MC, sm + SM_LCI * MM, Mp, fl->T2.p, tp, fl->W.p, tp, 1.0, 0.0, nullptr, false,
+                             ctx->d_tasks2, tasks.size()));
+    col_predict_kernel<<<blocks_for(tc), 256, 0, ctx->stream>>>(fl->T2.p, fl->W.p, tp, M, tc, fl->mv.p + MV_BETA * Mp, par,
+                                                                dm + t0, dv + t0);
+    GPS_LAUNCH_CHECK();
+    ctx->launches++;
+  }
+  return GPS_OK;
+}

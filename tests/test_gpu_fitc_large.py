@@ -1,0 +1,136 @@
+"""FITC with M > 32 inducing points (-m gpu): the matrix form of csrc/gps_fitc_large.cu through the
+C-ABI against the CPU oracle and — with the switch-over lowered so that M = 20 runs it too — against
+the reference-generated goldens.  Tolerances: objective 1e-8 relative, gradients 1e-6 relative."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import golden_names, load_golden, grad_vector, relerr
+
+pytestmark = pytest.mark.gpu
+
+OBJ_TOL = 1e-8
+GRAD_TOL = 1e-6
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from gpscore_b200 import api
+    c = api.Context(0)
+    yield c
+    c.close()
+
+
+def _dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+@pytest.fixture()
+def forced(ctx):
+    """Lower the switch-over so every M runs the matrix form."""
+    ctx._check(ctx._lib.gps_dbg_set_variant(ctx._h, 3, 1))
+    yield ctx
+    ctx._check(ctx._lib.gps_dbg_set_variant(ctx._h, 3, 33))
+
+
+@pytest.mark.parametrize("name", golden_names(("c2", "c4")))
+@pytest.mark.parametrize("score", ["crps", "logs", "nlml"])
+def test_matrix_form_vs_reference_golden(forced, name, score):
+    g = load_golden(name)
+    forced.set_data(_dev(g["X"]), _dev(g["y"]))
+    val, grad, gU = forced.fitc_eval(g["theta"], g["U"], score)
+    assert abs(val - g["obj_" + score]) <= OBJ_TOL * abs(g["obj_" + score])
+    ref = grad_vector(g, score)
+    if int(g["d_b"]) == 1 and g["X"].shape[1] > 1:
+        grad = np.concatenate([[grad[0]], [grad[1:-1].sum()], [grad[-1]]])
+    assert relerr(grad, ref) <= GRAD_TOL
+    assert relerr(gU, g["grad_u_" + score]) <= GRAD_TOL
+    if score != "nlml":
+        mu, s2 = forced.fitc_loo()
+        assert relerr(mu.cpu().numpy(), g["loo_mean_" + score]) <= 1e-8
+        assert relerr(s2.cpu().numpy(), g["loo_var_" + score]) <= 1e-8
+
+
+@pytest.mark.parametrize("name", golden_names(("c4",))[:2])
+def test_matrix_form_predict_vs_golden(forced, name):
+    g = load_golden(name)
+    forced.set_data(_dev(g["X"]), _dev(g["y"]))
+    mean, var = forced.fitc_predict(g["theta"], g["U"], _dev(g["Xs"]), force_matrix_form=True)
+    assert relerr(mean.cpu().numpy(), g["pred_mean"]) <= 1e-8
+    assert relerr(var.cpu().numpy(), g["pred_var"]) <= 1e-7
+
+
+@pytest.mark.parametrize("m_ind,n,d", [(33, 700, 8), (128, 1000, 8), (200, 1500, 8), (300, 900, 3), (64, 777, 12)])
+def test_large_m_vs_oracle(ctx, m_ind, n, d):
+    from oracle import woodbury as Wd
+    rng = np.random.default_rng(100 + m_ind)
+    X = rng.uniform(-1, 1, (n, d))
+    y = np.sin(X @ rng.standard_normal(d)) + 0.1 * rng.standard_normal(n)
+    U = rng.uniform(-1, 1, (m_ind, d))
+    theta = np.concatenate([[0.3], np.log(rng.uniform(0.8, 2.0, d)), [-2.0]])
+    ctx.set_data(_dev(X), _dev(y))
+    for score in ("crps", "logs", "nlml"):
+        from oracle import gp_oracle as O
+        val, grad, gU = ctx.fitc_eval(theta, U, score)
+        oval, og, ogU, lm, lv = Wd.fitc_obj_grad(X, y, U, theta, O.SCORES[score])
+        assert abs(val - oval) <= OBJ_TOL * abs(oval), score
+        assert relerr(grad, og) <= GRAD_TOL, score
+        assert relerr(gU, ogU) <= GRAD_TOL, score
+        mu, s2 = ctx.fitc_loo()
+        assert relerr(mu.cpu().numpy().ravel(), lm) <= 1e-7
+        assert relerr(s2.cpu().numpy().ravel(), lv) <= 1e-7
+        val2, _, _ = ctx.fitc_eval(theta, U, score)
+        assert val2 == val                          # fixed reduction order: bit-reproducible
+
+
+def test_large_m_predict_vs_oracle(ctx):
+    from oracle import woodbury as Wd
+    rng = np.random.default_rng(7)
+    n, d, m_ind, t = 1100, 8, 96, 333
+    X = rng.uniform(-1, 1, (n, d))
+    y = np.cos(X @ rng.standard_normal(d)) + 0.05 * rng.standard_normal(n)
+    Xs = rng.uniform(-1, 1, (t, d))
+    U = rng.uniform(-1, 1, (m_ind, d))
+    theta = np.concatenate([[0.1], np.log(rng.uniform(0.8, 2.0, d)), [-3.0]])
+    ctx.set_data(_dev(X), _dev(y))
+    mean, var = ctx.fitc_predict(theta, U, _dev(Xs))
+    om, ov = Wd.fitc_predict(X, y, U, Xs, theta)
+    assert relerr(mean.cpu().numpy(), om) <= 1e-7
+    assert relerr(var.cpu().numpy(), ov) <= 1e-7
+
+
+def test_large_m_objective_only_and_errors(ctx):
+    from gpscore_b200 import lib as L
+    rng = np.random.default_rng(9)
+    X = rng.uniform(-1, 1, (600, 8))
+    y = rng.standard_normal(600)
+    U = rng.uniform(-1, 1, (40, 8))
+    theta = np.zeros(10)
+    ctx.set_data(_dev(X), _dev(y))
+    full = ctx.fitc_eval(theta, U, "crps")
+    obj = np.zeros(1)
+    from gpscore_b200.api import _dp, _host_vec
+    ctx._check(ctx._lib.gps_fitc_eval(ctx._h, _dp(theta), _dp(_host_vec(U)), 40, 1e-3, 0, _dp(obj), None, None))
+    assert obj[0] == full[0]
+    with pytest.raises(L.GpsError):                 # block objectives stay with the fused M <= 32 kernels
+        ctx.fitc_eval(theta, U, "dss")
+
+
+def test_large_m_finite_difference(ctx):
+    """M = 256, N = 20 000: directional finite difference over theta and U."""
+    from gpscore_b200 import synth
+    X, y = synth.kin40k_like(20000, seed=3)
+    theta = synth.hyper_point("P1")
+    rng = np.random.default_rng(11)
+    U = X[rng.choice(20000, 256, replace=False)] + 0.01 * rng.standard_normal((256, 8))
+    ctx.set_data(_dev(X), _dev(y))
+    vt = rng.standard_normal(theta.size)
+    vu = rng.standard_normal(U.shape)
+    for score in ("crps", "nlml"):
+        _, g, gU = ctx.fitc_eval(theta, U, score)
+        an = g @ vt + np.sum(gU * vu)
+        h = 1e-5
+        fp = ctx.fitc_eval(theta + h * vt, U + h * vu, score)[0]
+        fm = ctx.fitc_eval(theta - h * vt, U - h * vu, score)[0]
+        fd = (fp - fm) / (2 * h)
+        assert abs(fd - an) <= 2e-5 * max(abs(an), 1e-3), (score, fd, an)
