@@ -402,6 +402,29 @@ def run_ours(args):
                      "frac": bytes_b / (ms_b * 1e-3) / 1e9 / world / hbm_peak, "peak_how": hbm_how,
                      "note": "per-GPU algorithmic bytes (3 passes x 8 N (D+1)) over the whole-evaluation time; the row "
                              "passes also do ~5.6 kflop/row of fp64 work, so this path sits on the HBM/ALU ridge"}}
+    # ---- the same sweep at M = 256 and M = 1024: the matrix form (csrc/gps_fitc_large.cu), one GPU ---------
+    if world == 1:
+        rng_m = np.random.default_rng(1)
+        for m_big in (256, 1024):
+            Ub = Xb[rng_m.choice(N_BIG, m_big, replace=False)] + 0.01 * rng_m.standard_normal((m_big, D))
+            for _ in range(2):
+                cb.fitc_eval(theta, Ub, "crps")
+            reps_m = 3
+            e0.record(stream)
+            for _ in range(reps_m):
+                cb.fitc_eval(theta, Ub, "crps")
+            e1.record(stream)
+            stream.synchronize()
+            ms_m = e0.elapsed_time(e1) / reps_m
+            flops_m = 10.0 * m_big * m_big * N_BIG
+            fitc["sweep_N1e6_M%d" % m_big] = {
+                "workload": "synthetic 8-D FITC N=1e6 M=%d LOO-CRPS obj+grad, matrix form on one GPU" % m_big,
+                "evals_per_s": 1e3 / ms_m, "ms_per_eval": ms_m, "algorithmic_flops_per_eval": flops_m,
+                "roofline": {"bound": "tensor", "achieved": flops_m / (ms_m * 1e-3) / 1e12, "peak": roofline["peak"],
+                             "unit": "TFLOP/s", "frac": flops_m / (ms_m * 1e-3) / 1e12 / roofline["peak"],
+                             "note": "10 M^2 N useful fp64 flops (eight N x M x M products, triangular / symmetric "
+                                     "halves not counted) over the whole-evaluation time, against the cuBLAS DGEMM "
+                                     "rate measured in this run"}}
     cb.close()
     del Xb, yb
 

@@ -37,13 +37,15 @@ struct gps_fitc_large {
   int64_t Npp = 0;
   int Mp = 0, M = 0, D = 0;
   DevBuf Kuf, V, W, T1, T2;   // [Mp][Npp]
-  DevBuf sm, rv, mv, part, out, U;
+  DevBuf sm, rv, mv, part, out, U, dotp;
   GemmTask* tasks = nullptr;
   size_t tasks_cap = 0;
   gps_ctx::Range t_low, t_up, t_full, t_mm, t_sk_low, t_sk_full;
   int S = 1;                  // split-K chunks
   gps_ctx* ch = nullptr;      // child context for the M-sized factorisations
   bool ready = false;
+  int kuf_M = -1;             // live block of Kuf the pad zeros were laid out for
+  int64_t kuf_N = -1;
   std::vector<double> h_out;
 };
 
@@ -98,16 +100,34 @@ col_lambda_kernel(const double* __restrict__ V, int64_t ld, int M, int64_t N, in
   yl[i] = y[i] / l;
 }
 
-// out[r] = sum_{i<n} Mat[r][i] x[i]   (one block per row, fixed order)
+// part[c][r] = sum over chunk c of Mat[r][i] x[i]   (grid = rows x chunks; fixed order)
 __global__ void __launch_bounds__(256)
 rowdot_kernel(const double* __restrict__ Mat, int64_t ld, int64_t n, const double* __restrict__ x,
-              double* __restrict__ out) {
+              double* __restrict__ part) {
   __shared__ double sh[32];
   const double* row = Mat + (int64_t)blockIdx.x * ld;
+  const int64_t per = ((n + gridDim.y - 1) / gridDim.y + 1) & ~(int64_t)1;
+  const int64_t lo = blockIdx.y * per, hi = lo + per < n ? lo + per : n;
+  double s0 = 0.0, s1 = 0.0;
+  // rows and chunks start on even offsets of 16-byte aligned rows: 16-byte loads
+  for (int64_t i = lo + 2 * threadIdx.x; i + 1 < hi; i += 2 * blockDim.x) {
+    const double2 a = *reinterpret_cast<const double2*>(row + i);
+    const double2 b = *reinterpret_cast<const double2*>(x + i);
+    s0 = fma(a.x, b.x, s0);
+    s1 = fma(a.y, b.y, s1);
+  }
+  if (threadIdx.x == 0 && ((hi - lo) & 1) && hi > lo) s0 = fma(row[hi - 1], x[hi - 1], s0);
+  const double s = block_sum(s0 + s1, sh);
+  if (threadIdx.x == 0) part[(int64_t)blockIdx.y * gridDim.x + blockIdx.x] = s;
+}
+
+__global__ void __launch_bounds__(256)
+rowdot_reduce_kernel(const double* __restrict__ part, int rows, int chunks, double* __restrict__ out) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= rows) return;
   double s = 0.0;
-  for (int64_t i = threadIdx.x; i < n; i += blockDim.x) s = fma(row[i], x[i], s);
-  s = block_sum(s, sh);
-  if (threadIdx.x == 0) out[blockIdx.x] = s;
+  for (int c = 0; c < chunks; ++c) s += part[(int64_t)c * rows + r];
+  out[r] = s;
 }
 
 // out[c] = sum_k Mat[k][c] x[k]
@@ -275,13 +295,15 @@ vec_sum_kernel(const double* __restrict__ x, int64_t n, double* __restrict__ out
 // Kernel-gradient partials of G = Kbar o Kmat ([M][n], row stride ld) against the points P[n][D]:
 //   sg[m] = sum_i G_mi,  sd[m][d] = sum_i G_mi (u_md - p_id)/l_d,  sb[d] = sum_mi G_mi ((u_md - p_id)/l_d)^2
 // One block = MT rows of G x one strided share of the columns; per-block partials in fixed slots.
-template <int MT, int DMX>
-__global__ void __launch_bounds__(256)
+template <int MT, int DMX, bool DPOW2>
+__global__ void __launch_bounds__(256, 2)
 kgrad_kernel(const double* __restrict__ Kbar, const double* __restrict__ Kmat, int64_t ld, int M, int64_t n,
              const double* __restrict__ U, const double* __restrict__ P, int D, const double* __restrict__ par,
              double* __restrict__ part) {
   constexpr int NV = MT * (1 + DMX) + DMX;
   __shared__ double us[MT][DMX];
+  __shared__ double ils[DMX];
+  __shared__ double xs[DMX][257];
   __shared__ double red[8][NV];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int m0 = blockIdx.x * MT;
@@ -289,6 +311,7 @@ kgrad_kernel(const double* __restrict__ Kbar, const double* __restrict__ Kmat, i
     const int mm = tid / DMX, d = tid % DMX;
     us[mm][d] = (m0 + mm < M && d < D) ? U[(int64_t)(m0 + mm) * D + d] * par[2 + d] : 0.0;
   }
+  if (tid < DMX) ils[tid] = tid < D ? par[2 + tid] : 0.0;
   __syncthreads();
   double sg[MT], sd[MT][DMX], sb[DMX];
 #pragma unroll
@@ -299,24 +322,59 @@ kgrad_kernel(const double* __restrict__ Kbar, const double* __restrict__ Kmat, i
   }
 #pragma unroll
   for (int d = 0; d < DMX; ++d) sb[d] = 0.0;
-  for (int64_t i = (int64_t)blockIdx.y * 256 + tid; i < n; i += (int64_t)256 * gridDim.y) {
-    double xs[DMX];
+  // A tile of 256 points is staged (scaled, transposed) in shared memory with coalesced loads (a
+  // thread reading its own row of P would touch 16 cache lines per warp-load); the next tile's
+  // operands are fetched into registers while the current one is consumed.
+  const int64_t stride = (int64_t)256 * gridDim.y;
+  double gn[MT], xr[DMX];
+  // element k of this thread in the [256][D] tile: row / shared-memory slot, fixed for the whole kernel
+  // (computed once: an integer division by the run-time D inside the loop costs more than the arithmetic)
+  int rk[DMX], sk[DMX];
 #pragma unroll
-    for (int d = 0; d < DMX; ++d) xs[d] = d < D ? P[i * D + d] * par[2 + d] : 0.0;
+  for (int k = 0; k < DMX; ++k) {
+    const int e = tid + k * 256;
+    const int r = DPOW2 ? e / DMX : e / D, d = DPOW2 ? e % DMX : e - r * D;   // DPOW2: D == DMX, shifts
+    rk[k] = r;
+    sk[k] = d * 257 + r;
+  }
+  auto fetch = [&](int64_t base) {
+    const int64_t i = base + tid;
 #pragma unroll
     for (int mm = 0; mm < MT; ++mm) {
-      if (m0 + mm < M) {
-        const int64_t o = (int64_t)(m0 + mm) * ld + i;
-        const double g = Kbar[o] * Kmat[o];
-        sg[mm] += g;
+      const int64_t o = (int64_t)(m0 + mm) * ld + i;
+      const bool live = i < n && m0 + mm < M;
+      const double a = live ? Kbar[o] : 0.0, b = live ? Kmat[o] : 0.0;
+      gn[mm] = a * b;
+    }
 #pragma unroll
-        for (int d = 0; d < DMX; ++d) {
-          if (d < D) {
-            const double df = us[mm][d] - xs[d];
-            const double gd = g * df;
-            sd[mm][d] += gd;
-            sb[d] = fma(gd, df, sb[d]);
-          }
+    for (int k = 0; k < DMX; ++k)
+      xr[k] = (k < D && base + rk[k] < n) ? P[base * D + tid + k * 256] : 0.0;
+  };
+  int64_t base = (int64_t)blockIdx.y * 256;
+  if (base < n) fetch(base);
+#pragma unroll 1
+  for (; base < n; base += stride) {
+    double gv[MT];
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < DMX; ++k)
+      if (k < D) (&xs[0][0])[sk[k]] = xr[k];
+#pragma unroll
+    for (int mm = 0; mm < MT; ++mm) gv[mm] = gn[mm];
+    __syncthreads();
+    if (base + stride < n) fetch(base + stride);
+#pragma unroll
+    for (int mm = 0; mm < MT; ++mm) sg[mm] += gv[mm];
+#pragma unroll
+    for (int d = 0; d < DMX; ++d) {
+      if (d < D) {
+        const double xv = xs[d][tid] * ils[d];
+#pragma unroll
+        for (int mm = 0; mm < MT; ++mm) {
+          const double df = us[mm][d] - xv;
+          const double gd = gv[mm] * df;
+          sd[mm][d] += gd;
+          sb[d] = fma(gd, df, sb[d]);
         }
       }
     }
@@ -436,10 +494,18 @@ int build_tasks(gps_ctx* ctx, gps_fitc_large* fl) {
     for (int j = 0; j < mt; ++j)
       h.push_back(make_task(i * GPS_TILE, j * GPS_TILE, 0, Mp, i * GPS_TILE, j * GPS_TILE));
   end(fl->t_mm);
-  // split-K over the rows of the data set: enough tasks for ~4 waves of 148 task slots
+  // split-K over the rows of the data set: the chunk count that fills whole waves of task slots
+  // (one slot = one 128 x 128 task = two CTAs of the shipped policy, sm_count slots per wave)
   const int tl = mt * (mt + 1) / 2;
-  int64_t want = (4 * (int64_t)ctx->sm_count + tl - 1) / tl;
-  if (want < 1) want = 1;
+  const int64_t slots = ctx->sm_count;
+  int64_t want = 1;
+  double best = -1.0;
+  const int64_t s_lo = std::min<int64_t>(nt, (slots + tl - 1) / tl), s_hi = std::min<int64_t>(nt, (16 * slots + tl - 1) / tl);
+  for (int64_t s = s_lo; s <= s_hi; ++s) {
+    const int64_t tasks = s * tl, waves = (tasks + slots - 1) / slots;
+    const double eff = (double)tasks / (double)(waves * slots);
+    if (eff > best + 1e-9) { best = eff; want = s; }
+  }
   if (want > nt) want = nt;
   const int64_t per = (nt + want - 1) / want;
   fl->S = (int)((nt + per - 1) / per);
@@ -514,8 +580,26 @@ int setup(gps_ctx* ctx, int M) {
     GPS_CHECK(gps_ensure(ctx, fl->out, (size_t)OUT_G1 + 2 * (1 + DMAX + (size_t)Mp * D)));
   }
   // the Gram kernel writes only the live M x N block: the pad rows/columns must read as zeros
-  GPS_CUDA(cudaMemsetAsync(fl->Kuf.p, 0, (size_t)Mp * Npp * sizeof(double), ctx->stream));
+  if (reshape || fl->kuf_M != M || fl->kuf_N != ctx->N) {
+    GPS_CUDA(cudaMemsetAsync(fl->Kuf.p, 0, (size_t)Mp * Npp * sizeof(double), ctx->stream));
+    fl->kuf_M = M;
+    fl->kuf_N = ctx->N;
+  }
   GPS_CHECK(ensure_child(ctx, fl));
+  return GPS_OK;
+}
+
+// out[r] = Mat[r][:n] . x for r < rows
+int rowdot(gps_ctx* ctx, gps_fitc_large* fl, const double* Mat, int64_t ld, int rows, int64_t n, const double* x,
+           double* out) {
+  int64_t chunks = (4 * (int64_t)ctx->sm_count + rows - 1) / rows;
+  chunks = std::max<int64_t>(1, std::min<int64_t>(chunks, n / 4096 + 1));
+  GPS_CHECK(gps_ensure(ctx, fl->dotp, (size_t)rows * chunks));
+  rowdot_kernel<<<dim3(rows, (unsigned)chunks), 256, 0, ctx->stream>>>(Mat, ld, n, x, fl->dotp.p);
+  GPS_LAUNCH_CHECK();
+  rowdot_reduce_kernel<<<blocks_for(rows), 256, 0, ctx->stream>>>(fl->dotp.p, rows, (int)chunks, out);
+  GPS_LAUNCH_CHECK();
+  ctx->launches += 2;
   return GPS_OK;
 }
 
@@ -584,18 +668,25 @@ int chol_adjoint(gps_ctx* ctx, gps_fitc_large* fl, const double* L, const double
   return GPS_OK;
 }
 
-template <int MT, int DMX>
+template <int MT, int DMX, bool DPOW2>
 int kgrad(gps_ctx* ctx, gps_fitc_large* fl, const double* Kbar, const double* Kmat, int64_t ld, int64_t n,
           const double* P, double* out) {
   const int M = fl->M, D = fl->D;
   const int gx = (M + MT - 1) / MT;
-  int64_t gy = (4 * (int64_t)ctx->sm_count + gx - 1) / gx;
-  const int64_t cols = (n + 255) / 256;
+  // column shares: the count that fills whole waves of 2 resident blocks per SM best (2..8 waves)
+  const int64_t slots = 2 * (int64_t)ctx->sm_count, cols = (n + 255) / 256;
+  int64_t gy = 1;
+  double best = -1.0;
+  for (int w = 2; w <= 8; ++w) {
+    const int64_t c = std::max<int64_t>(1, w * slots / gx);
+    const int64_t waves = (gx * c + slots - 1) / slots;
+    const double eff = (double)(gx * c) / (double)(waves * slots);
+    if (eff > best + 1e-9) { best = eff; gy = c; }
+  }
   if (gy > cols) gy = cols;
-  if (gy < 1) gy = 1;
   constexpr int NV = MT * (1 + DMX) + DMX;
   GPS_CHECK(gps_ensure(ctx, fl->part, (size_t)gx * gy * NV));
-  kgrad_kernel<MT, DMX><<<dim3(gx, (unsigned)gy), 256, 0, ctx->stream>>>(Kbar, Kmat, ld, M, n, fl->U.p, P, D, ctx->params.p,
+  kgrad_kernel<MT, DMX, DPOW2><<<dim3(gx, (unsigned)gy), 256, 0, ctx->stream>>>(Kbar, Kmat, ld, M, n, fl->U.p, P, D, ctx->params.p,
                                                                     fl->part.p);
   GPS_LAUNCH_CHECK();
   const int nthreads = 1 + DMAX + M * D;
@@ -605,12 +696,20 @@ int kgrad(gps_ctx* ctx, gps_fitc_large* fl, const double* Kbar, const double* Km
   return GPS_OK;
 }
 
+// D = 8 (the kin40k shape) gets the compile-time tile indexing and four rows per block
+int kgrad_any(gps_ctx* ctx, gps_fitc_large* fl, const double* Kbar, const double* Kmat, int64_t ld, int64_t n,
+              const double* P, double* out) {
+  if (fl->D == 8) return kgrad<4, 8, true>(ctx, fl, Kbar, Kmat, ld, n, P, out);
+  if (fl->D < 8) return kgrad<2, 8, false>(ctx, fl, Kbar, Kmat, ld, n, P, out);
+  return kgrad<1, 16, false>(ctx, fl, Kbar, Kmat, ld, n, P, out);
+}
+
 }  // namespace
 
 void gps_fitc_large_free(gps_ctx* ctx) {
   gps_fitc_large* fl = ctx->fl;
   if (!fl) return;
-  for (DevBuf* b : {&fl->Kuf, &fl->V, &fl->W, &fl->T1, &fl->T2, &fl->sm, &fl->rv, &fl->mv, &fl->part, &fl->out, &fl->U})
+  for (DevBuf* b : {&fl->Kuf, &fl->V, &fl->W, &fl->T1, &fl->T2, &fl->sm, &fl->rv, &fl->mv, &fl->part, &fl->out, &fl->U, &fl->dotp})
     if (b->p) cudaFree(b->p);
   if (fl->tasks) cudaFree(fl->tasks);
   if (fl->ch) gps_ctx_release(fl->ch);
@@ -666,20 +765,18 @@ int gps_fitc_large_eval(gps_ctx* ctx, const double* theta, const double* U, int 
   col_lambda_kernel<<<nbn, 256, 0, st>>>(fl->V.p, Npp, M, N, Npp, ctx->y.p, par, rv + RV_LAM * Npp, rv + RV_IL * Npp,
                                          rv + RV_YL * Npp);
   GPS_LAUNCH_CHECK();
-  rowdot_kernel<<<Mp, 256, 0, st>>>(fl->V.p, Npp, Npp, rv + RV_YL * Npp, mv + MV_VY * Mp);
-  GPS_LAUNCH_CHECK();
-  ctx->launches += 2;
+  ctx->launches++;
+  GPS_CHECK(rowdot(ctx, fl, fl->V.p, Npp, Mp, Npp, rv + RV_YL * Npp, mv + MV_VY * Mp));
   GPS_CHECK(splitk(ctx, fl, fl->V.p, fl->V.p, rv + RV_IL * Npp, true, true, ch->Kb.p));
   GPS_CHECK(factor(ctx, fl, sm + SM_LC * MM, sm + SM_LCI * MM, "I + V Lambda^-1 V'"));
-  rowdot_kernel<<<Mp, 256, 0, st>>>(sm + SM_LCI * MM, Mp, Mp, mv + MV_VY * Mp, mv + MV_BETA * Mp);
-  GPS_LAUNCH_CHECK();
+  GPS_CHECK(rowdot(ctx, fl, sm + SM_LCI * MM, Mp, Mp, Mp, mv + MV_VY * Mp, mv + MV_BETA * Mp));
 
   // ---- pass 2: W, d, alpha, score + seeds ------------------------------------------------------
   GPS_CHECK(big_gemm(ctx, fl, GEMM_KC_MC, fl->t_low, sm + SM_LCI * MM, fl->V.p, fl->W.p));
   col_w_kernel<<<nbn, 256, 0, st>>>(fl->W.p, Npp, M, N, Npp, mv + MV_BETA * Mp, ctx->y.p, rv + RV_IL * Npp,
                                     rv + RV_R * Npp, alpha, dd);
   GPS_LAUNCH_CHECK();
-  ctx->launches += 2;
+  ctx->launches++;
   double* d_out = fl->out.p;
   if (nlml) {
     nlml_rows_kernel<<<1, 1024, 0, st>>>(N, Npp, rv + RV_LAM * Npp, ctx->y.p, alpha, sm + SM_LC * MM, Mp, M,
@@ -705,9 +802,8 @@ int gps_fitc_large_eval(gps_ctx* ctx, const double* theta, const double* U, int 
   seed_kernel<<<nbn, 256, 0, st>>>(N, Npp, nlml ? 1 : 0, rv + RV_IL * Npp, rv + RV_R * Npp, alpha, rv + RV_ABAR * Npp,
                                    rv + RV_DBAR * Npp, rv + RV_LBAR * Npp, rv + RV_RBAR * Npp, rv + RV_TBAR * Npp);
   GPS_LAUNCH_CHECK();
-  rowdot_kernel<<<Mp, 256, 0, st>>>(fl->W.p, Npp, Npp, rv + RV_TBAR * Npp, mv + MV_BBAR * Mp);
-  GPS_LAUNCH_CHECK();
-  ctx->launches += 3;
+  ctx->launches++;
+  GPS_CHECK(rowdot(ctx, fl, fl->W.p, Npp, Mp, Npp, rv + RV_TBAR * Npp, mv + MV_BBAR * Mp));
   GPS_CHECK(splitk(ctx, fl, fl->W.p, fl->W.p, rv + RV_RBAR * Npp, true, false, sm + SM_R * MM));
 
   // ---- M x M algebra: C_bar, vy_bar -------------------------------------------------------------
@@ -734,19 +830,11 @@ int gps_fitc_large_eval(gps_ctx* ctx, const double* theta, const double* U, int 
   GPS_LAUNCH_CHECK();
   ctx->launches += 3;
   const size_t glen = 1 + DMAX + (size_t)M * D;
-  if (D <= 8) {
-    GPS_CHECK((kgrad<4, 8>(ctx, fl, fl->T1.p, fl->Kuf.p, Npp, N, ctx->X.p, d_out + OUT_G1)));
-  } else {
-    GPS_CHECK((kgrad<2, 16>(ctx, fl, fl->T1.p, fl->Kuf.p, Npp, N, ctx->X.p, d_out + OUT_G1)));
-  }
+  GPS_CHECK(kgrad_any(ctx, fl, fl->T1.p, fl->Kuf.p, Npp, N, ctx->X.p, d_out + OUT_G1));
 
   // ---- finish: A_bar through the Cholesky adjoint of L_A, Kuu gradient ----------------------------
   GPS_CHECK(chol_adjoint(ctx, fl, sm + SM_LA * MM, sm + SM_LAI * MM, sm + SM_S * MM, 0, sm + SM_ABAR * MM));
-  if (D <= 8) {
-    GPS_CHECK((kgrad<4, 8>(ctx, fl, sm + SM_ABAR * MM, sm + SM_KUU * MM, Mp, M, fl->U.p, d_out + OUT_G1 + glen)));
-  } else {
-    GPS_CHECK((kgrad<2, 16>(ctx, fl, sm + SM_ABAR * MM, sm + SM_KUU * MM, Mp, M, fl->U.p, d_out + OUT_G1 + glen)));
-  }
+  GPS_CHECK(kgrad_any(ctx, fl, sm + SM_ABAR * MM, sm + SM_KUU * MM, Mp, M, fl->U.p, d_out + OUT_G1 + glen));
   GPS_CUDA(cudaMemcpyAsync(fl->h_out.data(), d_out, (OUT_G1 + 2 * glen) * sizeof(double), cudaMemcpyDeviceToHost, st));
   GPS_CUDA(cudaStreamSynchronize(st));
   const double* h = fl->h_out.data();

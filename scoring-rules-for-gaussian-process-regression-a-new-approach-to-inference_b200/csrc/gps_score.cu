@@ -46,7 +46,9 @@ __global__ void diag_kernel(const double* __restrict__ A, int64_t Np, double* __
   }
 }
 
-// LOO transform, score value and adjoint seeds.  One block: deterministic.
+// LOO transform, score value and adjoint seeds.  One block writes the value itself; a larger grid
+// (N > 32768) writes one partial per block, summed in block order by partial_sum_kernel:
+// deterministic either way.
 __global__ void __launch_bounds__(1024)
 loo_score_kernel(int score, int64_t N, int64_t Np, const double* __restrict__ alpha,
                  const double* __restrict__ dg, const double* __restrict__ y, double* __restrict__ abar,
@@ -55,7 +57,7 @@ loo_score_kernel(int score, int64_t N, int64_t Np, const double* __restrict__ al
   __shared__ double sh[32];
   const double invN = 1.0 / (double)N;
   double sum = 0.0;
-  for (int64_t i = threadIdx.x; i < Np; i += blockDim.x) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < Np; i += (int64_t)blockDim.x * gridDim.x) {
     if (i >= N) {
       abar[i] = 0.0;
       dbar[i] = 0.0;
@@ -82,7 +84,16 @@ loo_score_kernel(int score, int64_t N, int64_t Np, const double* __restrict__ al
     }
   }
   sum = block_sum(sum, sh);
-  if (threadIdx.x == 0) obj[0] = sum * invN;
+  if (threadIdx.x == 0) obj[blockIdx.x] = gridDim.x == 1 ? sum * invN : sum;
+}
+
+__global__ void __launch_bounds__(256)
+partial_sum_kernel(const double* __restrict__ part, int n, double scale, double* __restrict__ out) {
+  __shared__ double sh[32];
+  double s = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += part[i];
+  s = block_sum(s, sh);
+  if (threadIdx.x == 0) out[0] = s * scale;
 }
 
 __global__ void __launch_bounds__(1024)
@@ -285,10 +296,21 @@ int gps_diag_extract(gps_ctx* ctx, const double* A, int64_t Np, double* d, int d
 int gps_loo_score(gps_ctx* ctx, int score, int64_t N, int64_t Np, const double* alpha, const double* d,
                   const double* y, double* abar, double* dbar, double* loo_mean, double* loo_var,
                   double* obj_dev) {
-  loo_score_kernel<<<1, 1024, 0, ctx->stream>>>(score, N, Np, alpha, d, y, abar, dbar, loo_mean, loo_var,
-                                                obj_dev);
+  if (N <= 32768) {
+    loo_score_kernel<<<1, 1024, 0, ctx->stream>>>(score, N, Np, alpha, d, y, abar, dbar, loo_mean, loo_var,
+                                                  obj_dev);
+    GPS_LAUNCH_CHECK();
+    ctx->launches++;
+    return GPS_OK;
+  }
+  const int grid = (int)std::min<int64_t>((Np + 1023) / 1024, (int64_t)2 * ctx->sm_count);
+  GPS_CHECK(gps_ensure(ctx, ctx->red, (size_t)grid));
+  loo_score_kernel<<<grid, 1024, 0, ctx->stream>>>(score, N, Np, alpha, d, y, abar, dbar, loo_mean, loo_var,
+                                                   ctx->red.p);
   GPS_LAUNCH_CHECK();
-  ctx->launches++;
+  partial_sum_kernel<<<1, 256, 0, ctx->stream>>>(ctx->red.p, grid, 1.0 / (double)N, obj_dev);
+  GPS_LAUNCH_CHECK();
+  ctx->launches += 2;
   return GPS_OK;
 }
 
