@@ -85,7 +85,10 @@ int gps_full_predict(gps_ctx* ctx, const double* theta, const double* Xs, int64_
  * grad_theta[D+2], grad_U[M*D] host.  For row-sharded multi-GPU runs the three passes are also
  * exposed separately so the host can all-reduce the packed accumulators between them
  * (acc buffers are DEVICE pointers owned by the caller; their lengths come from
- * gps_fitc_acc_len).  world_n is the global number of rows (the mean in KF:67 divides by it). */
+ * gps_fitc_acc_len).  world_n is the global number of rows (the mean in KF:67 divides by it).
+ * M <= 32: fused row kernels (all five objectives, staged protocol available).  32 < M <= 4096:
+ * gps_fitc_eval runs the matrix form on the tile-GEMM engine (GPS_CRPS / GPS_LOGS / GPS_NLML, one GPU;
+ * gps_fitc_loo and gps_fitc_predict work after it); the staged calls return GPS_EINVAL there. */
 int gps_fitc_eval(gps_ctx* ctx, const double* theta, const double* U, int M, double jitter, int score,
                   double* obj, double* grad_theta, double* grad_U);
 int gps_fitc_acc_len(int M, int D, int64_t* len1, int64_t* len2, int64_t* len3);
