@@ -280,7 +280,7 @@ int gps_full_eval(gps_ctx* ctx, const double* theta, int score, double* obj, dou
     GPS_CHECK(gps_full_dss(ctx, par + PAR_OBJ, par + PAR_GSUM, grad != nullptr));
   } else if (score != GPS_NLML) {
     GPS_CHECK(gps_diag_extract(ctx, ctx->Kb.p, Np, v + V_D * Np, 0));
-    GPS_CHECK(gps_loo_score(ctx, score, N, Np, v + V_ALPHA * Np, v + V_D * Np, ctx->y.p, v + V_ABAR * Np,
+    GPS_CHECK(gps_loo_score(ctx, score, N, Np, N, v + V_ALPHA * Np, v + V_D * Np, ctx->y.p, v + V_ABAR * Np,
                             v + V_DBAR * Np, v + V_LOOM * Np, v + V_LOOV * Np, par + PAR_OBJ));
     ctx->loo_valid = true;
     if (grad) {

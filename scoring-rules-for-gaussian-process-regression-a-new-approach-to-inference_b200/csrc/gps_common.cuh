@@ -139,6 +139,14 @@ void gps_fitc_large_free(gps_ctx* ctx);
 int gps_fitc_large_eval(gps_ctx* ctx, const double* theta, const double* U, int M, double jitter, int score,
                         double* obj, double* grad_theta, double* grad_U);
 int gps_fitc_large_predict(gps_ctx* ctx, const double* dXs, int64_t T, double* dm, double* dv);
+int gps_fitc_large_acc_len(int M, int D, int64_t* len1, int64_t* len2, int64_t* len3);
+int gps_fitc_large_begin(gps_ctx* ctx, const double* theta, const double* U, int M, double jitter, int score,
+                         int64_t world_n);
+int gps_fitc_large_pass1(gps_ctx* ctx, double* acc1);
+int gps_fitc_large_pass2(gps_ctx* ctx, const double* acc1, double* acc2, bool want_grad);
+int gps_fitc_large_pass3(gps_ctx* ctx, const double* acc2, double* acc3);
+int gps_fitc_large_finish(gps_ctx* ctx, const double* acc2, const double* acc3, double* obj, double* grad_theta,
+                          double* grad_U);
 // offsets (doubles) into ctx->params and rows of ctx->vecs
 constexpr int PAR_OBJ = 128;
 constexpr int PAR_GSUM = 136;
@@ -189,7 +197,7 @@ int gps_check_info(gps_ctx* ctx);
 // gps_score.cu
 int gps_symv(gps_ctx* ctx, const double* A, int64_t Np, const double* x, double* y);
 int gps_diag_extract(gps_ctx* ctx, const double* A, int64_t Np, double* d, int do_log);
-int gps_loo_score(gps_ctx* ctx, int score, int64_t N, int64_t Np, const double* alpha, const double* d,
+int gps_loo_score(gps_ctx* ctx, int score, int64_t N, int64_t Np, int64_t norm_n, const double* alpha, const double* d,
                   const double* y, double* abar, double* dbar, double* loo_mean, double* loo_var,
                   double* obj_dev);
 int gps_nlml_value(gps_ctx* ctx, int64_t N, int64_t Np, const double* logdiag, const double* alpha,

@@ -1922,6 +1922,7 @@ int reduce_to(gps_ctx* ctx, const double* part, int nblocks, int len, double* ac
 extern "C" {
 
 int gps_fitc_acc_len(int M, int D, int64_t* len1, int64_t* len2, int64_t* len3) {
+  if (M > 32 && M <= 4096 && D > 0 && D <= 16) return gps_fitc_large_acc_len(M, D, len1, len2, len3);
   if (M <= 0 || M > 32 || D <= 0 || D > 15) return GPS_EINVAL;
   const int MP = (M + 7) / 8 * 8;
   if (len1) *len1 = len1_of(MP);
@@ -1935,13 +1936,14 @@ int gps_fitc_begin(gps_ctx* ctx, const double* theta, const double* U, int M, do
   if (!ctx) return GPS_EINVAL;
   if (ctx->N == 0) return gps_fail(ctx, GPS_ESTATE, "fitc: call gps_set_data first");
   if (!theta || !U || score < GPS_CRPS || score > GPS_KC) return gps_fail(ctx, GPS_EINVAL, "fitc: bad arguments");
+  if (M > 32) return gps_fitc_large_begin(ctx, theta, U, M, jitter, score, world_n);   // matrix form, same protocol
   const bool block_obj = score == GPS_DSS || score == GPS_KC;
   if (block_obj && ((world_n > 0 ? world_n : ctx->N) % 4 || world_n > ctx->N))
     return gps_fail(ctx, GPS_EINVAL, "fitc dss/kc: needs N %% 4 == 0 (K20:541-543) and runs on one GPU in this version");
   if (block_obj && ctx->fitc_variant == 0)
     return gps_fail(ctx, GPS_EINVAL, "fitc dss/kc: only the tile formulation of the row passes implements them");
   if (M <= 0 || M > 32)
-    return gps_fail(ctx, GPS_EINVAL, "fitc: M=%d outside the fused row-kernel range 1..32 (the staged/sharded protocol has no matrix form)", M);
+    return gps_fail(ctx, GPS_EINVAL, "fitc: M=%d outside 1..4096", M);
   if (ctx->D > 15) return gps_fail(ctx, GPS_EINVAL, "fitc: D=%d > 15 not supported by the row kernels", ctx->D);
   GPS_CUDA(cudaSetDevice(ctx->device));
   auto& f = ctx->fitc;
@@ -1985,6 +1987,11 @@ int gps_fitc_pass1(gps_ctx* ctx, double* acc1) {
   auto& f = ctx->fitc;
   if (!f.begun) return gps_fail(ctx, GPS_ESTATE, "fitc_pass1: call gps_fitc_begin first");
   GPS_CUDA(cudaSetDevice(ctx->device));
+  if (f.large) {
+    GPS_CHECK(gps_fitc_large_pass1(ctx, acc1));
+    GPS_CUDA(cudaStreamSynchronize(ctx->stream));
+    return GPS_OK;
+  }
   GPS_CHECK(do_row1(ctx, f.part.p));
   ctx->launches++;
   GPS_CHECK(reduce_to(ctx, f.part.p, f.grid, len1_of(f.MP), acc1));
@@ -1997,6 +2004,11 @@ int gps_fitc_pass2(gps_ctx* ctx, const double* acc1, double* acc2) {
   auto& f = ctx->fitc;
   if (!f.begun) return gps_fail(ctx, GPS_ESTATE, "fitc_pass2: call gps_fitc_begin first");
   GPS_CUDA(cudaSetDevice(ctx->device));
+  if (f.large) {
+    GPS_CHECK(gps_fitc_large_pass2(ctx, acc1, acc2, true));
+    GPS_CUDA(cudaStreamSynchronize(ctx->stream));
+    return GPS_OK;
+  }
   MP_DISPATCH(f.MP, GPS_CHECK(run_small1<MPC>(ctx, nullptr, const_cast<double*>(acc1))));
   GPS_CHECK(do_row2(ctx, f.part.p));
   ctx->launches += 2;
@@ -2011,6 +2023,11 @@ int gps_fitc_pass3(gps_ctx* ctx, const double* acc2, double* acc3) {
   auto& f = ctx->fitc;
   if (!f.pass2_done) return gps_fail(ctx, GPS_ESTATE, "fitc_pass3: pass 2 has not run");
   GPS_CUDA(cudaSetDevice(ctx->device));
+  if (f.large) {
+    GPS_CHECK(gps_fitc_large_pass3(ctx, acc2, acc3));
+    GPS_CUDA(cudaStreamSynchronize(ctx->stream));
+    return GPS_OK;
+  }
   MP_DISPATCH(f.MP, GPS_CHECK(run_small2<MPC>(ctx, nullptr, const_cast<double*>(acc2))));
   GPS_CHECK(do_row3(ctx, f.part.p));
   ctx->launches += 2;
@@ -2051,6 +2068,7 @@ int gps_fitc_finish(gps_ctx* ctx, const double* acc2, const double* acc3, double
   auto& f = ctx->fitc;
   if (!f.pass2_done) return gps_fail(ctx, GPS_ESTATE, "fitc_finish: passes have not run");
   GPS_CUDA(cudaSetDevice(ctx->device));
+  if (f.large) return gps_fitc_large_finish(ctx, acc2, acc3, obj, grad_theta, grad_U);
   return fitc_finish_impl(ctx, nullptr, 0, acc2, const_cast<double*>(acc3), obj, grad_theta, grad_U);
 }
 

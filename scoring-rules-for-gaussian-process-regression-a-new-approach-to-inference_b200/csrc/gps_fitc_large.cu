@@ -29,7 +29,7 @@ enum { SM_KUU = 0, SM_LA, SM_LAI, SM_LC, SM_LCI, SM_R, SM_SW, SM_Y, SM_Z, SM_CBA
 enum { RV_LAM = 0, RV_IL, RV_YL, RV_R, RV_ABAR, RV_DBAR, RV_LBAR, RV_RBAR, RV_TBAR, RV_LOOM, RV_LOOV, RV_COUNT };
 enum { MV_VY = 0, MV_BETA, MV_BBAR, MV_VYBAR, MV_COUNT };
 // small results copied to the host: [0] obj, [1] sum lambda_bar, then two gradient blocks
-constexpr int OUT_OBJ = 0, OUT_SUMLB = 1, OUT_G1 = 8;
+constexpr int OUT_OBJ = 0, OUT_LOGDET = 2, OUT_G1 = 8;
 
 }  // namespace
 
@@ -37,7 +37,7 @@ struct gps_fitc_large {
   int64_t Npp = 0;
   int Mp = 0, M = 0, D = 0;
   DevBuf Kuf, V, W, T1, T2;   // [Mp][Npp]
-  DevBuf sm, rv, mv, part, out, U, dotp;
+  DevBuf sm, rv, mv, part, out, U, dotp, acc;
   GemmTask* tasks = nullptr;
   size_t tasks_cap = 0;
   gps_ctx::Range t_low, t_up, t_full, t_mm, t_sk_low, t_sk_full;
@@ -179,11 +179,12 @@ col_w_kernel(const double* __restrict__ W, int64_t ld, int M, int64_t N, int64_t
   dd[i] = l - r * l * l;
 }
 
-// NLML value and seeds: obj = sum 1/2 log lam + 1/2 y alpha + N/2 log 2pi + sum log diag L_C
+// NLML over this context's rows: obj share = sum 1/2 log lam + 1/2 y alpha; seeds abar = y/2, dbar = 0
+// (the replicated terms N/2 log 2pi + sum log diag L_C are added once, on the host)
 __global__ void __launch_bounds__(1024)
 nlml_rows_kernel(int64_t N, int64_t Npp, const double* __restrict__ lam, const double* __restrict__ y,
-                 const double* __restrict__ alpha, const double* __restrict__ LC, int Mp, int M,
-                 double* __restrict__ abar, double* __restrict__ dbar, double* __restrict__ obj) {
+                 const double* __restrict__ alpha, double* __restrict__ abar, double* __restrict__ dbar,
+                 double* __restrict__ obj) {
   __shared__ double sh[32];
   double s = 0.0;
   for (int64_t i = threadIdx.x; i < Npp; i += blockDim.x) {
@@ -195,9 +196,25 @@ nlml_rows_kernel(int64_t N, int64_t Npp, const double* __restrict__ lam, const d
     }
     dbar[i] = 0.0;
   }
-  for (int m = threadIdx.x; m < M; m += blockDim.x) s += log(LC[(int64_t)m * Mp + m]);
   s = block_sum(s, sh);
-  if (threadIdx.x == 0) obj[0] = s + (double)N * HALF_LOG_2PI;
+  if (threadIdx.x == 0) obj[0] = s;
+}
+
+__global__ void __launch_bounds__(256)
+logdiag_sum_kernel(const double* __restrict__ L, int Mp, int M, double* __restrict__ out) {
+  __shared__ double sh[32];
+  double s = 0.0;
+  for (int m = threadIdx.x; m < M; m += blockDim.x) s += log(L[(int64_t)m * Mp + m]);
+  s = block_sum(s, sh);
+  if (threadIdx.x == 0) out[0] = s;
+}
+
+// out = A + I
+__global__ void __launch_bounds__(256)
+add_identity_kernel(const double* __restrict__ A, int Mp, double* __restrict__ out) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (int64_t)Mp * Mp) return;
+  out[e] = A[e] + ((e / Mp) == (e % Mp) ? 1.0 : 0.0);
 }
 
 // lam_bar0, rbar, tbar from the score seeds
@@ -709,7 +726,7 @@ int kgrad_any(gps_ctx* ctx, gps_fitc_large* fl, const double* Kbar, const double
 void gps_fitc_large_free(gps_ctx* ctx) {
   gps_fitc_large* fl = ctx->fl;
   if (!fl) return;
-  for (DevBuf* b : {&fl->Kuf, &fl->V, &fl->W, &fl->T1, &fl->T2, &fl->sm, &fl->rv, &fl->mv, &fl->part, &fl->out, &fl->U, &fl->dotp})
+  for (DevBuf* b : {&fl->Kuf, &fl->V, &fl->W, &fl->T1, &fl->T2, &fl->sm, &fl->rv, &fl->mv, &fl->part, &fl->out, &fl->U, &fl->dotp, &fl->acc})
     if (b->p) cudaFree(b->p);
   if (fl->tasks) cudaFree(fl->tasks);
   if (fl->ch) gps_ctx_release(fl->ch);
@@ -717,138 +734,220 @@ void gps_fitc_large_free(gps_ctx* ctx) {
   ctx->fl = nullptr;
 }
 
-int gps_fitc_large_eval(gps_ctx* ctx, const double* theta, const double* U, int M, double jitter, int score,
-                        double* obj, double* grad_theta, double* grad_U) {
+// ---- staged evaluation: begin / pass1 / pass2 / pass3 / finish ------------------------------------------
+// The same protocol as the fused M <= 32 path (include/gpscore.h): each pass leaves a packed
+// accumulator of this context's rows on the device; multi-GPU runs all-reduce it before the next
+// pass, gps_fitc_large_eval just chains the passes on its own buffers.
+//   acc1 = [C - I (Mp*Mp) | v_y (Mp)]
+//   acc2 = [R (Mp*Mp) | beta_bar (Mp) | obj: the rows' share]
+//   acc3 = [S (Mp*Mp) | kernel-gradient block of K_uf (1 + 16 + M*D) | sum lambda_bar]
+
+int gps_fitc_large_acc_len(int M, int D, int64_t* len1, int64_t* len2, int64_t* len3) {
+  const int64_t Mp = gps_pad(M), MM = Mp * Mp;
+  // even lengths: packed back to back, every accumulator stays 16-byte aligned (S is a GEMM operand)
+  if (len1) *len1 = MM + Mp;
+  if (len2) *len2 = MM + Mp + 2;
+  if (len3) *len3 = (MM + (1 + DMAX + (int64_t)M * D) + 2) & ~(int64_t)1;
+  return GPS_OK;
+}
+
+int gps_fitc_large_begin(gps_ctx* ctx, const double* theta, const double* U, int M, double jitter, int score,
+                         int64_t world_n) {
   if (score != GPS_CRPS && score != GPS_LOGS && score != GPS_NLML)
     return gps_fail(ctx, GPS_EINVAL, "fitc: M=%d > 32 runs the matrix form, which implements crps / logs / nlml only", M);
   if (ctx->D > DMAX) return gps_fail(ctx, GPS_EINVAL, "fitc: D=%d > %d not supported", ctx->D, DMAX);
   if (M > 4096) return gps_fail(ctx, GPS_EINVAL, "fitc: M=%d > 4096 not supported", M);
   GPS_CUDA(cudaSetDevice(ctx->device));
   auto& f = ctx->fitc;
-  f.begun = false; f.pass2_done = false; f.loo_ok = false; f.large = false;
+  f.begun = false; f.pass2_done = false; f.loo_ok = false; f.large = true;
   GPS_CHECK(gps_ensure(ctx, ctx->params, PAR_LEN));
   if (!ctx->d_info) GPS_CUDA(cudaMalloc(&ctx->d_info, sizeof(int)));
   GPS_CHECK(setup(ctx, M));
   gps_fitc_large* fl = ctx->fl;
   fl->ready = false;
   gps_ctx* ch = fl->ch;
-  const int64_t N = ctx->N, Npp = fl->Npp;
   const int D = ctx->D, Mp = fl->Mp;
   const size_t MM = (size_t)Mp * Mp;
-  const bool want_grad = grad_theta || grad_U;
-  const bool nlml = score == GPS_NLML;
   cudaStream_t st = ctx->stream;
   double ea = 0, sn2 = 0;
   GPS_CHECK(gps_upload_params(ctx, theta, D, &ea, &sn2));
-  f.M = M; f.MP = Mp; f.score = score; f.jitter = jitter; f.ea = ea; f.sn2 = sn2; f.world_n = N;
-  const double* par = ctx->params.p;
+  f.M = M; f.MP = Mp; f.score = score; f.jitter = jitter; f.ea = ea; f.sn2 = sn2;
+  f.world_n = world_n > 0 ? world_n : ctx->N;
   GPS_CUDA(cudaMemsetAsync(fl->U.p, 0, (size_t)Mp * D * sizeof(double), st));
   GPS_CUDA(cudaMemcpyAsync(fl->U.p, U, (size_t)M * D * sizeof(double), cudaMemcpyDefault, st));
   double* sm = fl->sm.p;
-  double* rv = fl->rv.p;
-  double* mv = fl->mv.p;
-  double* alpha = f.rowv.p + 4 * N;
-  double* dd = f.rowv.p + 5 * N;
-  const unsigned nbm = blocks_for((int64_t)MM), nbn = blocks_for(Npp);
-
-  // ---- A = Kuu + jitter I = L_A L_A' --------------------------------------------------------
+  // A = Kuu + jitter I = L_A L_A' (replicated)
   GPS_CUDA(cudaMemsetAsync(ch->Kb.p, 0, MM * sizeof(double), st));
-  GPS_CHECK(gps_gram_rect(ctx, fl->U.p, M, fl->U.p, M, D, par, ch->Kb.p, Mp));
-  kuu_fix_kernel<<<nbm, 256, 0, st>>>(ch->Kb.p, Mp, M, jitter, sm + SM_KUU * MM);
+  GPS_CHECK(gps_gram_rect(ctx, fl->U.p, M, fl->U.p, M, D, ctx->params.p, ch->Kb.p, Mp));
+  kuu_fix_kernel<<<blocks_for((int64_t)MM), 256, 0, st>>>(ch->Kb.p, Mp, M, jitter, sm + SM_KUU * MM);
   GPS_LAUNCH_CHECK();
   ctx->launches++;
   GPS_CHECK(factor(ctx, fl, sm + SM_LA * MM, sm + SM_LAI * MM, "K_uu + jitter I"));
+  f.begun = true;
+  return GPS_OK;
+}
 
-  // ---- pass 1: Kuf, V, lambda; C = I + V diag(1/lam) V', vy = V (y/lam) ------------------------
+// pass 1: Kuf, V, lambda; acc1 = [V diag(1/lam) V' | V (y/lam)] over this context's rows
+int gps_fitc_large_pass1(gps_ctx* ctx, double* acc1) {
+  gps_fitc_large* fl = ctx->fl;
+  const int64_t N = ctx->N, Npp = fl->Npp;
+  const int D = ctx->D, Mp = fl->Mp, M = fl->M;
+  const size_t MM = (size_t)Mp * Mp;
+  cudaStream_t st = ctx->stream;
+  const double* par = ctx->params.p;
+  double *sm = fl->sm.p, *rv = fl->rv.p;
   GPS_CHECK(gps_gram_rect(ctx, fl->U.p, M, ctx->X.p, N, D, par, fl->Kuf.p, Npp));
   GPS_CHECK(big_gemm(ctx, fl, GEMM_KC_MC, fl->t_low, sm + SM_LAI * MM, fl->Kuf.p, fl->V.p));
-  col_lambda_kernel<<<nbn, 256, 0, st>>>(fl->V.p, Npp, M, N, Npp, ctx->y.p, par, rv + RV_LAM * Npp, rv + RV_IL * Npp,
-                                         rv + RV_YL * Npp);
+  col_lambda_kernel<<<blocks_for(Npp), 256, 0, st>>>(fl->V.p, Npp, M, N, Npp, ctx->y.p, par, rv + RV_LAM * Npp,
+                                                     rv + RV_IL * Npp, rv + RV_YL * Npp);
   GPS_LAUNCH_CHECK();
   ctx->launches++;
-  GPS_CHECK(rowdot(ctx, fl, fl->V.p, Npp, Mp, Npp, rv + RV_YL * Npp, mv + MV_VY * Mp));
-  GPS_CHECK(splitk(ctx, fl, fl->V.p, fl->V.p, rv + RV_IL * Npp, true, true, ch->Kb.p));
-  GPS_CHECK(factor(ctx, fl, sm + SM_LC * MM, sm + SM_LCI * MM, "I + V Lambda^-1 V'"));
-  GPS_CHECK(rowdot(ctx, fl, sm + SM_LCI * MM, Mp, Mp, Mp, mv + MV_VY * Mp, mv + MV_BETA * Mp));
+  GPS_CHECK(rowdot(ctx, fl, fl->V.p, Npp, Mp, Npp, rv + RV_YL * Npp, acc1 + MM));
+  GPS_CHECK(splitk(ctx, fl, fl->V.p, fl->V.p, rv + RV_IL * Npp, true, false, acc1));
+  return GPS_OK;
+}
 
-  // ---- pass 2: W, d, alpha, score + seeds ------------------------------------------------------
+// pass 2: C = I + acc1 -> L_C, beta; W, d, alpha, score + seeds; acc2 = [W diag(rbar) W' | W tbar | obj]
+int gps_fitc_large_pass2(gps_ctx* ctx, const double* acc1, double* acc2, bool want_grad) {
+  gps_fitc_large* fl = ctx->fl;
+  auto& f = ctx->fitc;
+  gps_ctx* ch = fl->ch;
+  const int64_t N = ctx->N, Npp = fl->Npp;
+  const int Mp = fl->Mp, M = fl->M;
+  const size_t MM = (size_t)Mp * Mp;
+  const bool nlml = f.score == GPS_NLML;
+  cudaStream_t st = ctx->stream;
+  double *sm = fl->sm.p, *rv = fl->rv.p, *mv = fl->mv.p;
+  double* alpha = f.rowv.p + 4 * N;
+  double* dd = f.rowv.p + 5 * N;
+  const unsigned nbn = blocks_for(Npp);
+  add_identity_kernel<<<blocks_for((int64_t)MM), 256, 0, st>>>(acc1, Mp, ch->Kb.p);
+  GPS_LAUNCH_CHECK();
+  ctx->launches++;
+  GPS_CHECK(factor(ctx, fl, sm + SM_LC * MM, sm + SM_LCI * MM, "I + V Lambda^-1 V'"));
+  GPS_CHECK(rowdot(ctx, fl, sm + SM_LCI * MM, Mp, Mp, Mp, acc1 + MM, mv + MV_BETA * Mp));
   GPS_CHECK(big_gemm(ctx, fl, GEMM_KC_MC, fl->t_low, sm + SM_LCI * MM, fl->V.p, fl->W.p));
   col_w_kernel<<<nbn, 256, 0, st>>>(fl->W.p, Npp, M, N, Npp, mv + MV_BETA * Mp, ctx->y.p, rv + RV_IL * Npp,
                                     rv + RV_R * Npp, alpha, dd);
   GPS_LAUNCH_CHECK();
   ctx->launches++;
-  double* d_out = fl->out.p;
+  double* d_obj = acc2 + MM + Mp;
   if (nlml) {
-    nlml_rows_kernel<<<1, 1024, 0, st>>>(N, Npp, rv + RV_LAM * Npp, ctx->y.p, alpha, sm + SM_LC * MM, Mp, M,
-                                         rv + RV_ABAR * Npp, rv + RV_DBAR * Npp, d_out + OUT_OBJ);
+    nlml_rows_kernel<<<1, 1024, 0, st>>>(N, Npp, rv + RV_LAM * Npp, ctx->y.p, alpha, rv + RV_ABAR * Npp,
+                                         rv + RV_DBAR * Npp, d_obj);
     GPS_LAUNCH_CHECK();
-    ctx->launches++;
+    logdiag_sum_kernel<<<1, 256, 0, st>>>(sm + SM_LC * MM, Mp, M, fl->out.p + OUT_LOGDET);
+    GPS_LAUNCH_CHECK();
+    ctx->launches += 2;
   } else {
     // alpha / d are N long (the layout gps_fitc_loo reads); the score kernel pads its outputs to Npp
-    GPS_CHECK(gps_loo_score(ctx, score, N, Npp, alpha, dd, ctx->y.p, rv + RV_ABAR * Npp, rv + RV_DBAR * Npp,
-                            rv + RV_LOOM * Npp, rv + RV_LOOV * Npp, d_out + OUT_OBJ));
+    // and divides by the global row count, so the ranks' shares add up to the mean of KF:67
+    GPS_CHECK(gps_loo_score(ctx, f.score, N, Npp, f.world_n, alpha, dd, ctx->y.p, rv + RV_ABAR * Npp,
+                            rv + RV_DBAR * Npp, rv + RV_LOOM * Npp, rv + RV_LOOV * Npp, d_obj));
   }
   f.pass2_done = true;
   f.loo_ok = true;
-  f.large = true;
   fl->ready = true;
-  fl->h_out.assign((size_t)OUT_G1 + 2 * (1 + DMAX + (size_t)M * D), 0.0);
-  if (!want_grad) {
-    GPS_CUDA(cudaMemcpyAsync(fl->h_out.data(), d_out, sizeof(double), cudaMemcpyDeviceToHost, st));
-    GPS_CUDA(cudaStreamSynchronize(st));
-    if (obj) *obj = fl->h_out[OUT_OBJ];
-    return GPS_OK;
-  }
+  if (!want_grad) return GPS_OK;
   seed_kernel<<<nbn, 256, 0, st>>>(N, Npp, nlml ? 1 : 0, rv + RV_IL * Npp, rv + RV_R * Npp, alpha, rv + RV_ABAR * Npp,
                                    rv + RV_DBAR * Npp, rv + RV_LBAR * Npp, rv + RV_RBAR * Npp, rv + RV_TBAR * Npp);
   GPS_LAUNCH_CHECK();
   ctx->launches++;
-  GPS_CHECK(rowdot(ctx, fl, fl->W.p, Npp, Mp, Npp, rv + RV_TBAR * Npp, mv + MV_BBAR * Mp));
-  GPS_CHECK(splitk(ctx, fl, fl->W.p, fl->W.p, rv + RV_RBAR * Npp, true, false, sm + SM_R * MM));
+  GPS_CHECK(rowdot(ctx, fl, fl->W.p, Npp, Mp, Npp, rv + RV_TBAR * Npp, acc2 + MM));
+  GPS_CHECK(splitk(ctx, fl, fl->W.p, fl->W.p, rv + RV_RBAR * Npp, true, false, acc2));
+  return GPS_OK;
+}
 
-  // ---- M x M algebra: C_bar, vy_bar -------------------------------------------------------------
-  sw_kernel<<<nbm, 256, 0, st>>>(mv + MV_BETA * Mp, mv + MV_BBAR * Mp, sm + SM_R * MM, Mp, sm + SM_SW * MM);
+// pass 3: C_bar, vy_bar (replicated); lambda_bar, V_bar, Kuf_bar; acc3 = [V_bar V' | kernel gradient | sum lam_bar]
+int gps_fitc_large_pass3(gps_ctx* ctx, const double* acc2, double* acc3) {
+  gps_fitc_large* fl = ctx->fl;
+  auto& f = ctx->fitc;
+  const int64_t N = ctx->N, Npp = fl->Npp;
+  const int D = ctx->D, Mp = fl->Mp, M = fl->M;
+  const size_t MM = (size_t)Mp * Mp;
+  const bool nlml = f.score == GPS_NLML;
+  cudaStream_t st = ctx->stream;
+  double *sm = fl->sm.p, *rv = fl->rv.p, *mv = fl->mv.p;
+  const double* bbar = acc2 + MM;
+  const size_t glen = 1 + DMAX + (size_t)M * D;
+  sw_kernel<<<blocks_for((int64_t)MM), 256, 0, st>>>(mv + MV_BETA * Mp, bbar, acc2, Mp, sm + SM_SW * MM);
   GPS_LAUNCH_CHECK();
   GPS_CHECK(chol_adjoint(ctx, fl, sm + SM_LC * MM, sm + SM_LCI * MM, sm + SM_SW * MM, nlml ? 1 : 0, sm + SM_CBAR * MM));
-  matvec_t_kernel<<<blocks_for(Mp), 256, 0, st>>>(sm + SM_LCI * MM, Mp, mv + MV_BBAR * Mp, mv + MV_VYBAR * Mp);
+  matvec_t_kernel<<<blocks_for(Mp), 256, 0, st>>>(sm + SM_LCI * MM, Mp, bbar, mv + MV_VYBAR * Mp);
   GPS_LAUNCH_CHECK();
   ctx->launches += 2;
-
-  // ---- pass 3: lambda_bar, V_bar, Kuf_bar; S = V_bar V' -------------------------------------------
   GPS_CHECK(big_gemm(ctx, fl, GEMM_KC_MC, fl->t_full, sm + SM_CBAR * MM, fl->V.p, fl->T1.p));     // CV
-  col_pass3_kernel<<<blocks_for(N), 256, 0, st>>>(fl->V.p, fl->T1.p, fl->W.p, Npp, M, N, mv + MV_BBAR * Mp,
-                                                  mv + MV_BETA * Mp, ctx->y.p, rv + RV_IL * Npp, rv + RV_TBAR * Npp,
-                                                  rv + RV_RBAR * Npp, rv + RV_LBAR * Npp);
+  col_pass3_kernel<<<blocks_for(N), 256, 0, st>>>(fl->V.p, fl->T1.p, fl->W.p, Npp, M, N, bbar, mv + MV_BETA * Mp,
+                                                  ctx->y.p, rv + RV_IL * Npp, rv + RV_TBAR * Npp, rv + RV_RBAR * Npp,
+                                                  rv + RV_LBAR * Npp);
   GPS_LAUNCH_CHECK();
   GPS_CHECK(big_gemm(ctx, fl, GEMM_MC_MC, fl->t_up, sm + SM_LCI * MM, fl->W.p, fl->T2.p));        // L_C^-T Wbar
   vbar_kernel<<<dim3(blocks_for(N), M), 256, 0, st>>>(fl->T2.p, fl->T1.p, fl->V.p, Npp, M, N, mv + MV_VYBAR * Mp,
                                                       rv + RV_YL * Npp, rv + RV_IL * Npp, rv + RV_LBAR * Npp);
   GPS_LAUNCH_CHECK();
   GPS_CHECK(big_gemm(ctx, fl, GEMM_MC_MC, fl->t_up, sm + SM_LAI * MM, fl->T2.p, fl->T1.p));       // Kuf_bar
-  GPS_CHECK(splitk(ctx, fl, fl->T2.p, fl->V.p, nullptr, false, false, sm + SM_S * MM));
-  vec_sum_kernel<<<1, 1024, 0, st>>>(rv + RV_LBAR * Npp, N, d_out + OUT_SUMLB);
+  GPS_CHECK(splitk(ctx, fl, fl->T2.p, fl->V.p, nullptr, false, false, acc3));
+  vec_sum_kernel<<<1, 1024, 0, st>>>(rv + RV_LBAR * Npp, N, acc3 + MM + glen);
   GPS_LAUNCH_CHECK();
   ctx->launches += 3;
-  const size_t glen = 1 + DMAX + (size_t)M * D;
-  GPS_CHECK(kgrad_any(ctx, fl, fl->T1.p, fl->Kuf.p, Npp, N, ctx->X.p, d_out + OUT_G1));
+  GPS_CHECK(kgrad_any(ctx, fl, fl->T1.p, fl->Kuf.p, Npp, N, ctx->X.p, acc3 + MM));
+  return GPS_OK;
+}
 
-  // ---- finish: A_bar through the Cholesky adjoint of L_A, Kuu gradient ----------------------------
-  GPS_CHECK(chol_adjoint(ctx, fl, sm + SM_LA * MM, sm + SM_LAI * MM, sm + SM_S * MM, 0, sm + SM_ABAR * MM));
-  GPS_CHECK(kgrad_any(ctx, fl, sm + SM_ABAR * MM, sm + SM_KUU * MM, Mp, M, fl->U.p, d_out + OUT_G1 + glen));
-  GPS_CUDA(cudaMemcpyAsync(fl->h_out.data(), d_out, (OUT_G1 + 2 * glen) * sizeof(double), cudaMemcpyDeviceToHost, st));
+// finish (replicated): A_bar through the Cholesky adjoint of L_A, Kuu gradient, assembly on the host
+int gps_fitc_large_finish(gps_ctx* ctx, const double* acc2, const double* acc3, double* obj, double* grad_theta,
+                          double* grad_U) {
+  gps_fitc_large* fl = ctx->fl;
+  auto& f = ctx->fitc;
+  const int D = ctx->D, Mp = fl->Mp, M = fl->M;
+  const size_t MM = (size_t)Mp * Mp;
+  const size_t glen = 1 + DMAX + (size_t)M * D;
+  cudaStream_t st = ctx->stream;
+  double* sm = fl->sm.p;
+  double* d_out = fl->out.p;
+  const bool want_grad = grad_theta || grad_U;
+  std::vector<double>& h = fl->h_out;
+  h.assign(OUT_G1 + 2 * glen + 2, 0.0);
+  GPS_CUDA(cudaMemcpyAsync(&h[OUT_OBJ], acc2 + MM + Mp, sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (f.score == GPS_NLML)
+    GPS_CUDA(cudaMemcpyAsync(&h[OUT_LOGDET], d_out + OUT_LOGDET, sizeof(double), cudaMemcpyDeviceToHost, st));
+  if (want_grad) {
+    GPS_CHECK(chol_adjoint(ctx, fl, sm + SM_LA * MM, sm + SM_LAI * MM, acc3, 0, sm + SM_ABAR * MM));
+    GPS_CHECK(kgrad_any(ctx, fl, sm + SM_ABAR * MM, sm + SM_KUU * MM, Mp, M, fl->U.p, d_out + OUT_G1 + glen));
+    GPS_CUDA(cudaMemcpyAsync(&h[OUT_G1], acc3 + MM, (glen + 1) * sizeof(double), cudaMemcpyDeviceToHost, st));
+    GPS_CUDA(cudaMemcpyAsync(&h[OUT_G1 + glen + 1], d_out + OUT_G1 + glen, glen * sizeof(double), cudaMemcpyDeviceToHost, st));
+  }
   GPS_CUDA(cudaStreamSynchronize(st));
-  const double* h = fl->h_out.data();
-  const double* g1 = h + OUT_G1;
-  const double* g2 = g1 + glen;
-  if (obj) *obj = h[OUT_OBJ];
+  double value = h[OUT_OBJ];
+  if (f.score == GPS_NLML) value += (double)f.world_n * HALF_LOG_2PI + h[OUT_LOGDET];   // replicated terms, added once
+  if (obj) *obj = value;
+  if (!want_grad) return GPS_OK;
+  const double* g1 = &h[OUT_G1];
+  const double sum_lbar = g1[glen];
+  const double* g2 = g1 + glen + 1;
   if (grad_theta) {
-    grad_theta[0] = g1[0] + ea * h[OUT_SUMLB] + g2[0];
+    grad_theta[0] = g1[0] + f.ea * sum_lbar + g2[0];
     for (int d = 0; d < D; ++d) grad_theta[1 + d] = g1[1 + d] + g2[1 + d];
-    grad_theta[D + 1] = sn2 * h[OUT_SUMLB];
+    grad_theta[D + 1] = f.sn2 * sum_lbar;
   }
   if (grad_U)
     for (int e = 0; e < M * D; ++e) grad_U[e] = g1[1 + DMAX + e] + 2.0 * g2[1 + DMAX + e];
   return GPS_OK;
+}
+
+int gps_fitc_large_eval(gps_ctx* ctx, const double* theta, const double* U, int M, double jitter, int score,
+                        double* obj, double* grad_theta, double* grad_U) {
+  GPS_CHECK(gps_fitc_large_begin(ctx, theta, U, M, jitter, score, ctx->N));
+  gps_fitc_large* fl = ctx->fl;
+  int64_t l1, l2, l3;
+  gps_fitc_large_acc_len(M, ctx->D, &l1, &l2, &l3);
+  GPS_CHECK(gps_ensure(ctx, fl->acc, (size_t)(l1 + l2 + l3)));
+  double *a1 = fl->acc.p, *a2 = a1 + l1, *a3 = a2 + l2;
+  const bool want_grad = grad_theta || grad_U;
+  GPS_CHECK(gps_fitc_large_pass1(ctx, a1));
+  GPS_CHECK(gps_fitc_large_pass2(ctx, a1, a2, want_grad));
+  if (want_grad) GPS_CHECK(gps_fitc_large_pass3(ctx, a2, a3));
+  return gps_fitc_large_finish(ctx, a2, a3, obj, grad_theta, grad_U);
 }
 
 // prediction at the factors of the last evaluation, test rows in chunks

@@ -50,12 +50,12 @@ __global__ void diag_kernel(const double* __restrict__ A, int64_t Np, double* __
 // (N > 32768) writes one partial per block, summed in block order by partial_sum_kernel:
 // deterministic either way.
 __global__ void __launch_bounds__(1024)
-loo_score_kernel(int score, int64_t N, int64_t Np, const double* __restrict__ alpha,
+loo_score_kernel(int score, int64_t N, int64_t Np, int64_t norm_n, const double* __restrict__ alpha,
                  const double* __restrict__ dg, const double* __restrict__ y, double* __restrict__ abar,
                  double* __restrict__ dbar, double* __restrict__ loo_mean, double* __restrict__ loo_var,
                  double* __restrict__ obj) {
   __shared__ double sh[32];
-  const double invN = 1.0 / (double)N;
+  const double invN = 1.0 / (double)norm_n;   // the mean runs over all rows of the data set (KF:67)
   double sum = 0.0;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < Np; i += (int64_t)blockDim.x * gridDim.x) {
     if (i >= N) {
@@ -293,11 +293,11 @@ int gps_diag_extract(gps_ctx* ctx, const double* A, int64_t Np, double* d, int d
   return GPS_OK;
 }
 
-int gps_loo_score(gps_ctx* ctx, int score, int64_t N, int64_t Np, const double* alpha, const double* d,
+int gps_loo_score(gps_ctx* ctx, int score, int64_t N, int64_t Np, int64_t norm_n, const double* alpha, const double* d,
                   const double* y, double* abar, double* dbar, double* loo_mean, double* loo_var,
                   double* obj_dev) {
   if (N <= 32768) {
-    loo_score_kernel<<<1, 1024, 0, ctx->stream>>>(score, N, Np, alpha, d, y, abar, dbar, loo_mean, loo_var,
+    loo_score_kernel<<<1, 1024, 0, ctx->stream>>>(score, N, Np, norm_n, alpha, d, y, abar, dbar, loo_mean, loo_var,
                                                   obj_dev);
     GPS_LAUNCH_CHECK();
     ctx->launches++;
@@ -305,10 +305,10 @@ int gps_loo_score(gps_ctx* ctx, int score, int64_t N, int64_t Np, const double* 
   }
   const int grid = (int)std::min<int64_t>((Np + 1023) / 1024, (int64_t)2 * ctx->sm_count);
   GPS_CHECK(gps_ensure(ctx, ctx->red, (size_t)grid));
-  loo_score_kernel<<<grid, 1024, 0, ctx->stream>>>(score, N, Np, alpha, d, y, abar, dbar, loo_mean, loo_var,
+  loo_score_kernel<<<grid, 1024, 0, ctx->stream>>>(score, N, Np, norm_n, alpha, d, y, abar, dbar, loo_mean, loo_var,
                                                    ctx->red.p);
   GPS_LAUNCH_CHECK();
-  partial_sum_kernel<<<1, 256, 0, ctx->stream>>>(ctx->red.p, grid, 1.0 / (double)N, obj_dev);
+  partial_sum_kernel<<<1, 256, 0, ctx->stream>>>(ctx->red.p, grid, 1.0 / (double)norm_n, obj_dev);
   GPS_LAUNCH_CHECK();
   ctx->launches += 2;
   return GPS_OK;

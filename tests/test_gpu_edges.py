@@ -64,8 +64,8 @@ def test_argument_errors_are_reported(ctx):
     X = np.random.default_rng(0).standard_normal((50, 2))
     y = np.zeros((50, 1))
     ctx.set_data(_dev(X), _dev(y))
-    with pytest.raises(L.GpsError):                       # the staged (sharded) protocol stops at M = 32
-        ctx.fitc_acc_len(33)
+    with pytest.raises(L.GpsError):                       # no accumulator layout beyond the matrix form
+        ctx.fitc_acc_len(4097)
     with pytest.raises(L.GpsError):                       # block objectives stop at M = 32 too
         ctx.fitc_eval(np.zeros(4), np.random.default_rng(1).standard_normal((33, 2)), "kc")
     with pytest.raises(L.GpsError):                       # M beyond the matrix form

@@ -116,6 +116,53 @@ def test_large_m_objective_only_and_errors(ctx):
         ctx.fitc_eval(theta, U, "dss")
 
 
+@pytest.mark.parametrize("score", ["crps", "logs", "nlml"])
+def test_large_m_row_sharded_equals_single(ctx, score):
+    """Three contexts holding uneven row blocks (the multi-GPU layout, emulated on one GPU with a python
+    sum standing in for the NCCL all-reduce) reproduce the single-context matrix-form result."""
+    from gpscore_b200 import api, lib as L
+    from gpscore_b200.api import _dp, _host_vec
+    rng = np.random.default_rng(21)
+    n, d, m_ind = 1501, 8, 96
+    X = rng.uniform(-1, 1, (n, d))
+    y = np.sin(X @ rng.standard_normal(d)) + 0.1 * rng.standard_normal(n)
+    U = rng.uniform(-1, 1, (m_ind, d))
+    theta = np.concatenate([[0.2], np.log(rng.uniform(0.8, 2.0, d)), [-2.5]])
+    ctx.set_data(_dev(X), _dev(y))
+    ref = ctx.fitc_eval(theta, U, score)
+    cuts = [0, 300, 1100, n]
+    parts = []
+    for r in range(3):
+        c = api.Context(0)
+        c.set_data(_dev(X[cuts[r]:cuts[r + 1]]), _dev(y[cuts[r]:cuts[r + 1]]))
+        parts.append(c)
+    th, Uh = np.ascontiguousarray(theta), _host_vec(U)
+    lens = ctx.fitc_acc_len(m_ind)
+    accs = [[torch.zeros(k, dtype=torch.float64, device="cuda") for k in lens] for _ in parts]
+    for c in parts:
+        c._check(c._lib.gps_fitc_begin(c._h, _dp(th), _dp(Uh), m_ind, 1e-3, L.SCORES[score], n))
+    for k, fn in enumerate(("gps_fitc_pass1", "gps_fitc_pass2", "gps_fitc_pass3")):
+        for c, a in zip(parts, accs):
+            if k == 0:
+                c._check(getattr(c._lib, fn)(c._h, a[0].data_ptr()))
+            else:
+                c._check(getattr(c._lib, fn)(c._h, a[k - 1].data_ptr(), a[k].data_ptr()))
+        tot = accs[0][k] + accs[1][k] + accs[2][k]
+        for a in accs:
+            a[k].copy_(tot)
+    for c, a in zip(parts, accs):
+        obj, g, gU = np.zeros(1), np.zeros(d + 2), np.zeros(m_ind * d)
+        c._check(c._lib.gps_fitc_finish(c._h, a[1].data_ptr(), a[2].data_ptr(), _dp(obj), _dp(g), _dp(gU)))
+        assert abs(obj[0] - ref[0]) <= 1e-11 * abs(ref[0])
+        assert relerr(g, ref[1]) <= 1e-9
+        assert relerr(gU.reshape(m_ind, d), ref[2]) <= 1e-9
+    # the public sharded entry point with a one-rank "all-reduce"
+    one = ctx.fitc_eval_sharded(theta, U, score, n, lambda t: t)
+    assert abs(one[0] - ref[0]) <= 1e-13 * abs(ref[0]) and relerr(one[1], ref[1]) <= 1e-12
+    for c in parts:
+        c.close()
+
+
 def test_large_m_finite_difference(ctx):
     """M = 256, N = 20 000: directional finite difference over theta and U."""
     from gpscore_b200 import synth
