@@ -156,7 +156,7 @@ def run_reference(args):
         "e2e": {"value": val, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -402,29 +402,36 @@ def run_ours(args):
                      "frac": bytes_b / (ms_b * 1e-3) / 1e9 / world / hbm_peak, "peak_how": hbm_how,
                      "note": "per-GPU algorithmic bytes (3 passes x 8 N (D+1)) over the whole-evaluation time; the row "
                              "passes also do ~5.6 kflop/row of fp64 work, so this path sits on the HBM/ALU ridge"}}
-    # ---- the same sweep at M = 256 and M = 1024: the matrix form (csrc/gps_fitc_large.cu), one GPU ---------
-    if world == 1:
-        rng_m = np.random.default_rng(1)
-        for m_big in (256, 1024):
-            Ub = Xb[rng_m.choice(N_BIG, m_big, replace=False)] + 0.01 * rng_m.standard_normal((m_big, D))
-            for _ in range(2):
-                cb.fitc_eval(theta, Ub, "crps")
-            reps_m = 3
-            e0.record(stream)
-            for _ in range(reps_m):
-                cb.fitc_eval(theta, Ub, "crps")
-            e1.record(stream)
-            stream.synchronize()
-            ms_m = e0.elapsed_time(e1) / reps_m
-            flops_m = 10.0 * m_big * m_big * N_BIG
+    # ---- the same sweep at M = 256 and M = 1024: the matrix form (csrc/gps_fitc_large.cu), rows sharded ------
+    rng_m = np.random.default_rng(1)
+    peak_tf = roofline["peak"] if rank == 0 else None
+    for m_big in (256, 1024):
+        Ub = Xb[rng_m.choice(N_BIG, m_big, replace=False)] + 0.01 * rng_m.standard_normal((m_big, D))
+        if world == 1:
+            run_m = lambda: cb.fitc_eval(theta, Ub, "crps")
+        else:
+            run_m = lambda: cb.fitc_eval_sharded(th0, Ub, "crps", N_BIG, allreduce_b)
+        for _ in range(2):
+            run_m()
+        barrier()
+        reps_m = 3
+        e0.record(stream)
+        for _ in range(reps_m):
+            run_m()
+        e1.record(stream)
+        barrier()
+        ms_m = max_over_ranks(e0.elapsed_time(e1)) / reps_m
+        flops_m = 10.0 * m_big * m_big * N_BIG
+        if rank == 0:
             fitc["sweep_N1e6_M%d" % m_big] = {
-                "workload": "synthetic 8-D FITC N=1e6 M=%d LOO-CRPS obj+grad, matrix form on one GPU" % m_big,
+                "workload": "synthetic 8-D FITC N=1e6 M=%d LOO-CRPS obj+grad, matrix form; rows sharded over %d GPU(s)%s" % (
+                    m_big, world, "" if world == 1 else " with 3 NCCL all-reduces of M x M accumulators per evaluation"),
                 "evals_per_s": 1e3 / ms_m, "ms_per_eval": ms_m, "algorithmic_flops_per_eval": flops_m,
-                "roofline": {"bound": "tensor", "achieved": flops_m / (ms_m * 1e-3) / 1e12, "peak": roofline["peak"],
-                             "unit": "TFLOP/s", "frac": flops_m / (ms_m * 1e-3) / 1e12 / roofline["peak"],
-                             "note": "10 M^2 N useful fp64 flops (eight N x M x M products, triangular / symmetric "
-                                     "halves not counted) over the whole-evaluation time, against the cuBLAS DGEMM "
-                                     "rate measured in this run"}}
+                "roofline": {"bound": "tensor", "achieved": flops_m / (ms_m * 1e-3) / 1e12 / world, "peak": peak_tf,
+                             "unit": "TFLOP/s", "frac": flops_m / (ms_m * 1e-3) / 1e12 / world / peak_tf,
+                             "note": "per-GPU share of 10 M^2 N useful fp64 flops (eight N x M x M products, triangular / "
+                                     "symmetric halves not counted) over the whole-evaluation time, against the cuBLAS "
+                                     "DGEMM rate measured in this run"}}
     cb.close()
     del Xb, yb
 
@@ -449,7 +456,7 @@ def run_ours(args):
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clk, "fitc": fitc,
         }
-        print(json.dumps(line))
+        emit(line)
     barrier()
     ctx.close()
     if world > 1:
@@ -457,7 +464,29 @@ def run_ours(args):
     return 0
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Point fd 1 at stderr while the run is in progress: libraries (NCCL's version banner, torchrun
+    notices) write to stdout, and the contract is ONE JSON line there."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    if _REAL_STDOUT is not None:
+        os.dup2(_REAL_STDOUT, 1)
+    print(json.dumps(line), flush=True)
+    if _REAL_STDOUT is not None:
+        os.dup2(2, 1)
+
+
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
