@@ -31,7 +31,8 @@ int gps_dbg_fp64_peak(gps_ctx* ctx, int iters, double* dmma_tflops, double* dfma
  * 7: 6 + double-buffering, 8: 6 with 64 x 32 warp tiles); what = 1 selects the diagonal-block kernel of
  * POTRF (0: register-cyclic, 1: 32-blocked DMMA = default); what = 2 selects the FITC row passes
  * (0: thread-per-row, 1: tile/DMMA formulation = default); what = 3 sets the number of inducing points from
- * which gps_fitc_eval switches to the matrix form (default 33; lower it to A/B the two paths at M <= 32). */
+ * which gps_fitc_eval switches to the matrix form (default 33; lower it to A/B the two paths at M <= 32);
+ * what = 4 turns the POTRF / TRTRI overlap of the full-GP evaluation off (0) or on (1 = default). */
 int gps_dbg_set_variant(gps_ctx* ctx, int what, int value);
 
 /* clock64 phase stamps of the last diagonal-block kernel launch (first call arms the recording):

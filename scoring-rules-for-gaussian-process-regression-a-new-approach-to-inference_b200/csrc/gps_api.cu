@@ -124,10 +124,17 @@ int gps_factor_and_invert(gps_ctx* ctx, bool want_logdet) {
   GPS_CHECK(stage_mark(ctx, gps_ctx::ST_BEGIN));
   GPS_CHECK(gps_gram_sym(ctx, ctx->X.p, N, Np, ctx->D, ctx->params.p, ctx->Kb.p));
   GPS_CHECK(stage_mark(ctx, gps_ctx::ST_GRAM));
-  GPS_CHECK(gps_potrf(ctx, ctx->Kb.p, ctx->Xb.p, Np));
-  if (want_logdet) GPS_CHECK(gps_diag_extract(ctx, ctx->Kb.p, Np, v + V_LOGD * Np, 1));
-  GPS_CHECK(stage_mark(ctx, gps_ctx::ST_POTRF));
-  GPS_CHECK(gps_trtri(ctx, ctx->Kb.p, ctx->Xb.p, ctx->Sb.p, Np));
+  if (ctx->overlap_trtri) {
+    // POTRF and the inversion merges overlap: the two stages are reported as one ("potrf" = both, "trtri" = 0)
+    GPS_CHECK(gps_potrf_trtri(ctx, ctx->Kb.p, ctx->Xb.p, ctx->Sb.p, Np));
+    if (want_logdet) GPS_CHECK(gps_diag_extract(ctx, ctx->Kb.p, Np, v + V_LOGD * Np, 1));
+    GPS_CHECK(stage_mark(ctx, gps_ctx::ST_POTRF));
+  } else {
+    GPS_CHECK(gps_potrf(ctx, ctx->Kb.p, ctx->Xb.p, Np));
+    if (want_logdet) GPS_CHECK(gps_diag_extract(ctx, ctx->Kb.p, Np, v + V_LOGD * Np, 1));
+    GPS_CHECK(stage_mark(ctx, gps_ctx::ST_POTRF));
+    GPS_CHECK(gps_trtri(ctx, ctx->Kb.p, ctx->Xb.p, ctx->Sb.p, Np));
+  }
   GPS_CHECK(stage_mark(ctx, gps_ctx::ST_TRTRI));
   GPS_CHECK(gps_lauum(ctx, ctx->Xb.p, ctx->Kb.p, Np));
   GPS_CHECK(stage_mark(ctx, gps_ctx::ST_LAUUM));
@@ -214,6 +221,10 @@ void gps_destroy(gps_ctx* ctx) {
   for (auto e : ctx->potrf_events) cudaEventDestroy(e);
   for (auto e : ctx->stage_ev) if (e) cudaEventDestroy(e);
   if (ctx->panel_stream) cudaStreamDestroy(ctx->panel_stream);
+  if (ctx->trail_stream) cudaStreamDestroy(ctx->trail_stream);
+  if (ctx->tri_stream) cudaStreamDestroy(ctx->tri_stream);
+  for (cudaEvent_t e : {ctx->fork_ev, ctx->join_trail_ev, ctx->join_tri_ev})
+    if (e) cudaEventDestroy(e);
   cudaEventDestroy(ctx->ev0);
   cudaEventDestroy(ctx->ev1);
   cudaStreamDestroy(ctx->own_stream);

@@ -439,6 +439,60 @@ int gps_build_tasks(gps_ctx* ctx, int64_t Np) {
     ctx->trtri_p.push_back(rp);
     ctx->trtri_x.push_back(rx);
   }
+  // TRTRI again, in the order the overlapped driver issues it.  Work is released in few, large
+  // launches so that it can fill the idle SMs of the POTRF tail (eagerly issuing every small merge
+  // serialises hundreds of few-CTA launches on the low-priority stream and fills nothing): for a node
+  // [lo, mid, hi) the whole left subtree, batched by depth, and the node's P phase (L21 * X11) are
+  // issued after the outer step that factors tile column mid-1; the right subtree is scheduled the
+  // same way recursively; the X phases (-X22 * P) follow at the step that finishes the right half.
+  ctx->trtri_sched.clear();
+  {
+    auto p_tasks = [&](const Node& n) {
+      for (int j = n.lo; j < n.mid; ++j)
+        for (int i = n.mid; i < n.hi; ++i) push(i * T, j * T, j * T, n.mid * T, i, j);
+    };
+    auto x_tasks = [&](const Node& n) {
+      for (int i = n.hi - 1; i >= n.mid; --i)
+        for (int j = n.lo; j < n.mid; ++j) push(i * T, j * T, n.mid * T, (i + 1) * T, i, j);
+    };
+    auto emit = [&](int step, int phase, size_t off) {
+      gps_ctx::TriLaunch tl{step, phase, {}};
+      tl.r.off = off;
+      tl.r.cnt = h.size() - off;
+      if (tl.r.cnt) ctx->trtri_sched.push_back(tl);
+    };
+    auto subtree = [&](int lo, int hi, int step) {   // every node inside [lo, hi), deepest level first
+      for (int d = maxd; d >= 0; --d) {
+        size_t off = h.size();
+        for (auto& n : nodes)
+          if (n.depth == d && n.lo >= lo && n.hi <= hi) p_tasks(n);
+        emit(step, 0, off);
+        off = h.size();
+        for (auto& n : nodes)
+          if (n.depth == d && n.lo >= lo && n.hi <= hi) x_tasks(n);
+        emit(step, 1, off);
+      }
+    };
+    // walk down the right spine of the tree
+    std::vector<Node> spine;
+    int lo = 0, hi = nb;
+    while (hi - lo > 1) {
+      const int mid = lo + (hi - lo) / 2;
+      Node n{lo, mid, hi, 0};
+      const int step = (mid - 1) / OB;
+      subtree(lo, mid, step);
+      size_t off = h.size();
+      p_tasks(n);
+      emit(step, 0, off);
+      spine.push_back(n);
+      lo = mid;
+    }
+    for (int s = (int)spine.size() - 1; s >= 0; --s) {
+      size_t off = h.size();
+      x_tasks(spine[s]);
+      emit((spine[s].hi - 1) / OB, 1, off);
+    }
+  }
   // LAUUM: lower tiles, k in [i, nb); longest first
   ctx->lauum.off = h.size();
   for (int i = 0; i < nb; ++i)
@@ -552,6 +606,101 @@ int gps_trtri(gps_ctx* ctx, const double* L, double* Xinv, double* scratch, int6
     GPS_CHECK(gps_gemm_tasks(ctx, GEMM_KC_MC, Xinv, Np, scratch, Np, Xinv, Np, -1.0, 0.0, nullptr, false,
                              ctx->d_tasks + ctx->trtri_x[lv].off, ctx->trtri_x[lv].cnt));
   }
+  return GPS_OK;
+}
+
+// POTRF (as gps_potrf) with its trailing updates on an internal mid-priority stream and the TRTRI
+// merges on a lowest-priority stream, each issued right after the outer step that finalises its
+// operands.  The exposed tail of POTRF (the serial chain of diagonal blocks, with trailing updates
+// too small to fill the GPU) is filled with inversion work that would otherwise start after it.
+int gps_potrf_trtri(gps_ctx* ctx, double* K, double* Xinv, double* scratch, int64_t Np) {
+  const int nb = (int)(Np / T);
+  const int OB = GPS_POTRF_OB;
+  const int no = (nb + OB - 1) / OB;
+  if (!ctx->overlap_trtri || no < 3) {
+    GPS_CHECK(gps_potrf(ctx, K, Xinv, Np));
+    return gps_trtri(ctx, K, Xinv, scratch, Np);
+  }
+  static bool configured = false;
+  if (!configured) {
+    GPS_CUDA(cudaFuncSetAttribute(potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTF2_SMEM));
+    GPS_CUDA(cudaFuncSetAttribute(potf2_inv_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)POTF2V2_SMEM));
+    configured = true;
+  }
+  if (!ctx->panel_stream || !ctx->trail_stream) {
+    int lo = 0, hi = 0;
+    GPS_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));   // lo = least, hi = greatest (numerically smaller)
+    if (!ctx->panel_stream) GPS_CUDA(cudaStreamCreateWithPriority(&ctx->panel_stream, cudaStreamNonBlocking, hi));
+    const int mid = (lo - 1 >= hi) ? lo - 1 : lo;
+    GPS_CUDA(cudaStreamCreateWithPriority(&ctx->trail_stream, cudaStreamNonBlocking, mid));
+    GPS_CUDA(cudaStreamCreateWithPriority(&ctx->tri_stream, cudaStreamNonBlocking, lo));
+    GPS_CUDA(cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming));
+    GPS_CUDA(cudaEventCreateWithFlags(&ctx->join_trail_ev, cudaEventDisableTiming));
+    GPS_CUDA(cudaEventCreateWithFlags(&ctx->join_tri_ev, cudaEventDisableTiming));
+  }
+  while ((int)ctx->potrf_events.size() < 2 * no + 2) {
+    cudaEvent_t e;
+    GPS_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ctx->potrf_events.push_back(e);
+  }
+  cudaStream_t s_user = ctx->stream, s_trail = ctx->trail_stream, s_pan = ctx->panel_stream, s_tri = ctx->tri_stream;
+  GPS_CUDA(cudaMemsetAsync(ctx->d_info, 0, sizeof(int), s_user));
+  GPS_CUDA(cudaEventRecord(ctx->fork_ev, s_user));
+  GPS_CUDA(cudaStreamWaitEvent(s_trail, ctx->fork_ev, 0));
+  GPS_CUDA(cudaStreamWaitEvent(s_tri, ctx->fork_ev, 0));
+  GPS_CUDA(cudaEventRecord(ctx->potrf_events[0], s_trail));
+  int rc = GPS_OK;
+  size_t next_tri = 0;
+  for (int o = 0; o < no && rc == GPS_OK; ++o) {
+    const int c0 = o * OB, c1 = std::min(nb, c0 + OB);
+    GPS_CUDA(cudaStreamWaitEvent(s_pan, ctx->potrf_events[2 * o], 0));
+    ctx->stream = s_pan;
+    for (int k = c0; k < c1 && rc == GPS_OK; ++k) {
+      if (ctx->potf2_variant == 0)
+        potf2_inv_kernel<<<1, 256, POTF2_SMEM, s_pan>>>(K, Xinv, Np, k, ctx->d_info);
+      else
+        potf2_inv_dmma_kernel<<<1, 256, POTF2V2_SMEM, s_pan>>>(K, Xinv, Np, k, ctx->d_info, ctx->potf2_prof);
+      if (cudaGetLastError() != cudaSuccess) rc = gps_fail(ctx, GPS_ECUDA, "potf2 launch failed");
+      ctx->launches++;
+      if (rc == GPS_OK)
+        rc = gps_gemm_tasks(ctx, GEMM_KC_KC, K, Np, Xinv, Np, K, Np, 1.0, 0.0, nullptr, false,
+                            ctx->d_tasks + ctx->potrf_panel[k].off, ctx->potrf_panel[k].cnt);
+      if (rc == GPS_OK)
+        rc = gps_gemm_tasks(ctx, GEMM_KC_KC, K, Np, K, Np, K, Np, -1.0, 1.0, nullptr, false,
+                            ctx->d_tasks + ctx->potrf_inner[k].off, ctx->potrf_inner[k].cnt);
+    }
+    if (rc != GPS_OK) break;
+    GPS_CUDA(cudaEventRecord(ctx->potrf_events[2 * o + 1], s_pan));
+    // trailing update from block column o
+    ctx->stream = s_trail;
+    GPS_CUDA(cudaStreamWaitEvent(s_trail, ctx->potrf_events[2 * o + 1], 0));
+    rc = gps_gemm_tasks(ctx, GEMM_KC_KC, K, Np, K, Np, K, Np, -1.0, 1.0, nullptr, false,
+                        ctx->d_tasks + ctx->potrf_trailA[o].off, ctx->potrf_trailA[o].cnt);
+    if (rc != GPS_OK) break;
+    GPS_CUDA(cudaEventRecord(ctx->potrf_events[2 * o + 2], s_trail));
+    rc = gps_gemm_tasks(ctx, GEMM_KC_KC, K, Np, K, Np, K, Np, -1.0, 1.0, nullptr, false,
+                        ctx->d_tasks + ctx->potrf_trailB[o].off, ctx->potrf_trailB[o].cnt);
+    if (rc != GPS_OK) break;
+    // inversion merges whose operands are final after this step
+    ctx->stream = s_tri;
+    GPS_CUDA(cudaStreamWaitEvent(s_tri, ctx->potrf_events[2 * o + 1], 0));
+    while (next_tri < ctx->trtri_sched.size() && ctx->trtri_sched[next_tri].step == o && rc == GPS_OK) {
+      const auto& tl = ctx->trtri_sched[next_tri++];
+      if (tl.phase == 0)   // P = L21 * X11
+        rc = gps_gemm_tasks(ctx, GEMM_KC_MC, K, Np, Xinv, Np, scratch, Np, 1.0, 0.0, nullptr, false,
+                            ctx->d_tasks + tl.r.off, tl.r.cnt);
+      else                 // X21 = -X22 * P
+        rc = gps_gemm_tasks(ctx, GEMM_KC_MC, Xinv, Np, scratch, Np, Xinv, Np, -1.0, 0.0, nullptr, false,
+                            ctx->d_tasks + tl.r.off, tl.r.cnt);
+    }
+  }
+  ctx->stream = s_user;
+  if (rc != GPS_OK) return rc;
+  GPS_CUDA(cudaEventRecord(ctx->join_trail_ev, s_trail));
+  GPS_CUDA(cudaEventRecord(ctx->join_tri_ev, s_tri));
+  GPS_CUDA(cudaStreamWaitEvent(s_user, ctx->join_trail_ev, 0));
+  GPS_CUDA(cudaStreamWaitEvent(s_user, ctx->join_tri_ev, 0));
   return GPS_OK;
 }
 

@@ -84,6 +84,14 @@ struct gps_ctx {
   cudaStream_t panel_stream = nullptr;          // high-priority stream for the POTRF look-ahead
   std::vector<cudaEvent_t> potrf_events;
   std::vector<Range> trtri_p, trtri_x;
+  // TRTRI re-ordered for the overlapped driver: launches in issue order, each tagged with the POTRF
+  // outer step after which its operands are final
+  struct TriLaunch { int step; int phase; Range r; };
+  std::vector<TriLaunch> trtri_sched;
+  cudaStream_t trail_stream = nullptr;          // POTRF trailing updates (mid priority)
+  cudaStream_t tri_stream = nullptr;            // overlapped TRTRI (lowest priority)
+  cudaEvent_t fork_ev = nullptr, join_trail_ev = nullptr, join_tri_ev = nullptr;
+  int overlap_trtri = 1;                        // 0: POTRF then TRTRI back to back (A/B knob)
   Range lauum, symprod;
 
   // ---- FITC state ----------------------------------------------------------------------------
@@ -191,6 +199,8 @@ int gps_gemm_tasks(gps_ctx* ctx, int kind, const double* A, int64_t lda, const d
 int gps_build_tasks(gps_ctx* ctx, int64_t Np);
 int gps_potrf(gps_ctx* ctx, double* K, double* Xinv, int64_t Np);       // K -> L in place; diag-block inverses -> Xinv
 int gps_trtri(gps_ctx* ctx, const double* L, double* Xinv, double* scratch, int64_t Np);
+// POTRF with the TRTRI merges issued on a low-priority stream as soon as their block columns are final
+int gps_potrf_trtri(gps_ctx* ctx, double* K, double* Xinv, double* scratch, int64_t Np);
 int gps_lauum(gps_ctx* ctx, const double* Xinv, double* Kinv, int64_t Np);
 int gps_symprod(gps_ctx* ctx, const double* Kinv, const double* dvec, double* S, int64_t Np);
 int gps_check_info(gps_ctx* ctx);
