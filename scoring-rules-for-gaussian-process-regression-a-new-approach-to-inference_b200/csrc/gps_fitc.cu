@@ -1090,13 +1090,15 @@ fitc_row3_tile_kernel(const double* __restrict__ X, const double* __restrict__ y
   double* VT = XsT + (size_t)PC * LDT;      // [MP][LDT]  V
   double* WT = VT + (size_t)MP * LDT;       // [MP][LDT]  W -> W_bar -> V_bar
   double* CT = WT + (size_t)MP * LDT;       // [MP][LDT]  C_bar V  ->  Kuf_bar -> G
-  double* gbs = CT + (size_t)MP * LDT;      // [D][RB]
-  double* Cs = gbs + (size_t)D * RB;        // [MP][MP] + [MP][PC]
-  double* red = Cs + MP * MP + MP * PC;     // [32]
+  double* Cs = CT;                          // [MP][MP] + [MP][PC]: the block's sums, staged over CT after the loop
+  double* red = CT + (size_t)MP * LDT;      // [32]
+  // fold matrices of the block objectives only (OBJ = 0 stops here: 2 CTAs per SM at M <= 24, D <= 8)
   double* MatH = red + 32;                  // [MP][LDM]  Hhat_f (OBJ = 1) / H_bar_f (OBJ = 2)
   double* hv = MatH + MP * LDM;             // [MP]       h_f
   double* MatHi = hv + MP;                  // [MP][LDM]  H_f^-1          (OBJ = 2)
   double* gbv = MatHi + MP * LDM;           // [MP]       g_bar_f         (OBJ = 2)
+  double* gbs = (OBJ ? gbv + MP : red + 32);   // [D][4]  g_b accumulators, one per warp (warp-reduced every tile)
+  static_assert(MP * MP + MP * PC <= MP * LDT, "block sums must fit in one tile");
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int fold = OBJ ? blockIdx.y : 0;
   const int64_t row_lo = OBJ ? fg.lo[fold] : 0, row_hi = OBJ ? fg.hi[fold] : N;
@@ -1116,9 +1118,8 @@ fitc_row3_tile_kernel(const double* __restrict__ X, const double* __restrict__ y
     bbar[tid] = small[lo.bbar + tid];
     vyb[tid] = small[lo.vyb + tid];
   }
-  for (int e = tid; e < MP * MP + MP * PC; e += RB) Cs[e] = 0.0;
-  for (int d = 0; d < D; ++d) gbs[d * RB + tid] = 0.0;
   for (int c = D + 1; c < PC; ++c) XsT[c * LDT + tid] = 0.0;
+  if (tid < 4 * D) gbs[tid] = 0.0;
   double sacc[MF][MF][2], pacc[MF][NF][2];
 #pragma unroll
   for (int i = 0; i < MF; ++i) {
@@ -1229,7 +1230,7 @@ fitc_row3_tile_kernel(const double* __restrict__ X, const double* __restrict__ y
       }
       CT[m * LDT + tid] = (m < M && live) ? CT[m * LDT + tid] * ea * exp(-0.5 * r2) : 0.0;
     }
-    for (int d = 0; d < D; ++d) {                               // g_b rows: one shared-memory update per d
+    auto gb_row = [&](int d) {                                  // sum_m G_im ((u_md - x_id)/l_d)^2 for this row
       const double xd = XsT[d * LDT + tid];
       double g0 = 0.0, g1 = 0.0, g2 = 0.0, g3 = 0.0;
 #pragma unroll
@@ -1241,21 +1242,25 @@ fitc_row3_tile_kernel(const double* __restrict__ X, const double* __restrict__ y
         g2 = fma(CT[(m + 2) * LDT + tid], d2 * d2, g2);
         g3 = fma(CT[(m + 3) * LDT + tid], d3 * d3, g3);
       }
-      gbs[d * RB + tid] += (g0 + g1) + (g2 + g3);
+      return (g0 + g1) + (g2 + g3);
+    };
+    for (int d = 0; d < D; ++d) {
+      const double v = warp_sum(gb_row(d));
+      if (lane == 0) gbs[d * 4 + warp] += v;
     }
     __syncwarp();
     tile_outer<MF, NF, false>(CT, XsT, nullptr, warp, lane, pacc);  // P += G' [xs | 1]
     __syncwarp();
   }
+  __syncthreads();                                              // every warp is done with its CT rows
+  for (int e = tid; e < MP * MP + MP * PC; e += RB) Cs[e] = 0.0;
+  __syncthreads();
   frags_to_smem<MF, MF>(sacc, Cs, MP, warp, lane);
   frags_to_smem<MF, NF>(pacc, Cs + MP * MP, PC, warp, lane);
   const int len = MP * MP + MP * PC + D + 1;
   double* out = part + ((int64_t)fold * gridDim.x + blockIdx.x) * len;
   for (int e = tid; e < MP * MP + MP * PC; e += RB) out[e] = Cs[e];
-  for (int d = 0; d < D; ++d) {
-    const double sg = block_sum(gbs[d * RB + tid], red);
-    if (tid == 0) out[MP * MP + MP * PC + d] = sg;
-  }
+  if (tid < D) out[MP * MP + MP * PC + tid] = (gbs[tid * 4] + gbs[tid * 4 + 1]) + (gbs[tid * 4 + 2] + gbs[tid * 4 + 3]);
   const double sl = block_sum(sum_lb, red);
   if (tid == 0) out[MP * MP + MP * PC + D] = sl;
 }
@@ -1692,9 +1697,11 @@ int run_row3(gps_ctx* ctx, double* part) {
 
 size_t smem_row1t(int MP, int D) { return ((size_t)MP * D + MP * (MP + 4) + (size_t)D * LDT + (size_t)MP * LDT + RB + MP * MP + MP) * 8; }
 size_t smem_row2t(int MP) { return ((size_t)MP * (MP + 4) + MP + (size_t)MP * LDT + 2 * RB + MP * MP + MP + 32) * 8; }
-size_t smem_row3t(int MP, int D, int PC) {
-  return ((size_t)MP * D + 5 * MP * (MP + 4) + 5 * MP + (size_t)PC * LDT + 3 * (size_t)MP * LDT + (size_t)D * RB + MP * MP +
-          MP * PC + 32) * 8;
+size_t smem_row3t(int MP, int D, int PC, int obj) {
+  size_t n = (size_t)MP * D + 3 * MP * (MP + 4) + 3 * MP + (size_t)PC * LDT + 3 * (size_t)MP * LDT + 32;
+  if (obj) n += (size_t)2 * MP * (MP + 4) + 2 * MP;   // fold matrices of the block objectives
+  n += (size_t)4 * D;                                 // per-warp g_b accumulators
+  return n * 8;
 }
 size_t smem_row2kc(int MP) { return ((size_t)MP * (MP + 4) + MP + 2 * (size_t)MP * LDT + 2 * RB + MP * MP + MP + 32) * 8; }
 size_t smem_row2b(int MP) { return ((size_t)MP * (MP + 4) + MP + (size_t)MP * LDT + 2 * RB + MP * MP + MP + 32) * 8; }
@@ -1726,7 +1733,7 @@ int run_row2t(gps_ctx* ctx, double* part) {
 template <int MP, int NF>
 int run_row3t(gps_ctx* ctx, double* part) {
   auto& f = ctx->fitc;
-  const size_t sm = smem_row3t(MP, ctx->D, 8 * NF);
+  const size_t sm = smem_row3t(MP, ctx->D, 8 * NF, 0);
   GPS_CHECK(set_smem(ctx, (fitc_row3_tile_kernel<MP, NF, 0>), sm));
   fitc_row3_tile_kernel<MP, NF, 0><<<f.grid, RB, sm, ctx->stream>>>(ctx->X.p, ctx->y.p, ctx->N, ctx->D, f.M, ctx->params.p,
                                                                     f.small.p, f.V.p, f.W.p, f.rowv.p, part, FoldGeom());
@@ -1737,7 +1744,7 @@ int run_row3t(gps_ctx* ctx, double* part) {
 template <int MP, int NF>
 int run_row3b(gps_ctx* ctx, double* part, const FoldGeom& fg, int gx) {
   auto& f = ctx->fitc;
-  const size_t sm = smem_row3t(MP, ctx->D, 8 * NF);
+  const size_t sm = smem_row3t(MP, ctx->D, 8 * NF, 1);
   GPS_CHECK(set_smem(ctx, (fitc_row3_tile_kernel<MP, NF, 1>), sm));
   fitc_row3_tile_kernel<MP, NF, 1><<<dim3(gx, 4), RB, sm, ctx->stream>>>(ctx->X.p, ctx->y.p, ctx->N, ctx->D, f.M,
                                                                          ctx->params.p, f.small.p, f.V.p, f.W.p,
@@ -1749,7 +1756,7 @@ int run_row3b(gps_ctx* ctx, double* part, const FoldGeom& fg, int gx) {
 template <int MP, int NF>
 int run_row3kc(gps_ctx* ctx, double* part, const FoldGeom& fg, int gx) {
   auto& f = ctx->fitc;
-  const size_t sm = smem_row3t(MP, ctx->D, 8 * NF);
+  const size_t sm = smem_row3t(MP, ctx->D, 8 * NF, 1);
   GPS_CHECK(set_smem(ctx, (fitc_row3_tile_kernel<MP, NF, 2>), sm));
   fitc_row3_tile_kernel<MP, NF, 2><<<dim3(gx, 4), RB, sm, ctx->stream>>>(ctx->X.p, ctx->y.p, ctx->N, ctx->D, f.M,
                                                                          ctx->params.p, f.small.p, f.V.p, f.W.p,
