@@ -527,7 +527,7 @@ int gps_potrf(gps_ctx* ctx, double* K, double* Xinv, int64_t Np) {
   const int nb = (int)(Np / T);
   const int OB = GPS_POTRF_OB;
   const int no = (nb + OB - 1) / OB;
-  static bool configured = false;
+  GPS_ONCE_PER_DEVICE(ctx);
   if (!configured) {
     GPS_CUDA(cudaFuncSetAttribute(potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)POTF2_SMEM));
@@ -621,7 +621,7 @@ int gps_potrf_trtri(gps_ctx* ctx, double* K, double* Xinv, double* scratch, int6
     GPS_CHECK(gps_potrf(ctx, K, Xinv, Np));
     return gps_trtri(ctx, K, Xinv, scratch, Np);
   }
-  static bool configured = false;
+  GPS_ONCE_PER_DEVICE(ctx);
   if (!configured) {
     GPS_CUDA(cudaFuncSetAttribute(potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTF2_SMEM));
     GPS_CUDA(cudaFuncSetAttribute(potf2_inv_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -133,6 +133,11 @@ int gps_fail(gps_ctx* c, int code, const char* fmt, ...);
 
 #define GPS_LAUNCH_CHECK() GPS_CUDA(cudaGetLastError())
 
+// function attributes (dynamic shared-memory limits) are per device: one flag per device ordinal
+#define GPS_ONCE_PER_DEVICE(ctx)        \
+  static bool once__[64] = {};          \
+  bool& configured = once__[(ctx)->device & 63]
+
 int gps_ensure(gps_ctx* ctx, DevBuf& b, size_t n);
 bool gps_is_device_ptr(const void* p);
 int gps_stage_in(gps_ctx* ctx, const double* p, size_t n, DevBuf& tmp, const double** out);

@@ -1653,12 +1653,14 @@ size_t smem_pred(int MP, int D) { return ((size_t)MP * D + 2 * MP * MP + 3 * MP 
 // raise the dynamic shared-memory limit of a kernel once per (kernel, size)
 template <typename K>
 int set_smem(gps_ctx* ctx, K kern, size_t bytes) {
-  static size_t configured = 0;   // one instance per kernel type K... per template instantiation of set_smem
-  static K last = nullptr;
-  if (last == kern && configured >= bytes) return GPS_OK;
+  // one slot per (kernel type K, device): kernels sharing a signature share the slot, hence `last`
+  static size_t configured[64] = {};
+  static K last[64] = {};
+  const int dv = ctx->device & 63;
+  if (last[dv] == kern && configured[dv] >= bytes) return GPS_OK;
   GPS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-  last = kern;
-  configured = bytes;
+  last[dv] = kern;
+  configured[dv] = bytes;
   return GPS_OK;
 }
 

@@ -222,7 +222,7 @@ template <class Cfg, bool A_MC, bool B_MC, bool DVEC, bool MIRROR>
 int launch(gps_ctx* ctx, const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc,
            double alpha, double beta, const double* dvec, const GemmTask* tasks, size_t ntasks) {
   auto kern = gemm_tile_kernel<Cfg, A_MC, B_MC, DVEC, MIRROR>;
-  static bool configured = false;
+  GPS_ONCE_PER_DEVICE(ctx);
   if (!configured) {
     GPS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM));
     configured = true;

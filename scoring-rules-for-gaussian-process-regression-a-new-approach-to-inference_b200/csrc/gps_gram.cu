@@ -137,7 +137,7 @@ int gps_gram_sym(gps_ctx* ctx, const double* X, int64_t N, int64_t Np, int D, co
   const int64_t nb = Np / TS;
   const int64_t tiles = nb * (nb + 1) / 2;
   const size_t smem = (size_t)2 * D * TS * sizeof(double);
-  static bool configured = false;
+  GPS_ONCE_PER_DEVICE(ctx);
   if (!configured) {
     GPS_CUDA(cudaFuncSetAttribute(gram_sym_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)(2 * MAXD * TS * sizeof(double))));
@@ -156,7 +156,7 @@ int gps_gram_rect(gps_ctx* ctx, const double* x, int64_t n, const double* xp, in
   if (D > MAXD) return gps_fail(ctx, GPS_EINVAL, "D=%d exceeds %d", D, MAXD);
   if (n == 0 || m == 0) return GPS_OK;
   const size_t smem = (size_t)2 * D * TS * sizeof(double);
-  static bool configured = false;
+  GPS_ONCE_PER_DEVICE(ctx);
   if (!configured) {
     GPS_CUDA(cudaFuncSetAttribute(gram_rect_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)(2 * MAXD * TS * sizeof(double))));

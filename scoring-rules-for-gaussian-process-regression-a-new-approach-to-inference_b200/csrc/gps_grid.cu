@@ -157,7 +157,7 @@ extern "C" int gps_grid_eval(gps_ctx* ctx, const double* x, const double* y, int
     GPS_CUDA(cudaMemcpyAsync(dls, ls, G * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     GPS_CUDA(cudaMemcpyAsync(dsd, noise_sd, G * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     const size_t smem = ((size_t)n * (n + 1) + 4 * n + 32) * sizeof(double);
-    static bool configured = false;
+    GPS_ONCE_PER_DEVICE(ctx);
     if (!configured) {
       GPS_CUDA(cudaFuncSetAttribute(grid_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)(((size_t)128 * 129 + 4 * 128 + 32) * sizeof(double))));

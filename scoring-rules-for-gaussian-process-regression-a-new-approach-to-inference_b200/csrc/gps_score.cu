@@ -330,7 +330,7 @@ int gps_grad_contract(gps_ctx* ctx, int mode, const double* Mx, int64_t N, int64
   const int nred = D + 2;
   GPS_CHECK(gps_ensure(ctx, ctx->red, (size_t)tiles * nred));
   const size_t smem = ((size_t)2 * D * GPS_TILE + 4 * GPS_TILE + 8 * nred) * sizeof(double);
-  static bool configured = false;
+  GPS_ONCE_PER_DEVICE(ctx);
   if (!configured) {
     GPS_CUDA(cudaFuncSetAttribute(grad_contract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)(((size_t)2 * 64 * GPS_TILE + 4 * GPS_TILE + 8 * 66) * sizeof(double))));

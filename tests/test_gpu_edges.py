@@ -95,3 +95,22 @@ def test_full_size_prediction_is_finite_and_bounded(ctx):
     m2, v2 = ctx.full_predict(theta, _dev(Xs[9990:10010]))
     assert relerr(m2.cpu().numpy(), mean[9990:10010].cpu().numpy()) <= 1e-10
     assert relerr(v2.cpu().numpy(), var[9990:10010].cpu().numpy()) <= 1e-10
+
+
+def test_two_devices_in_one_process():
+    """Contexts on two GPUs of one process (kernel attributes are configured per device): both reproduce
+    the single-device result.  Skipped on a one-GPU box."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from gpscore_b200 import api, synth
+    X, y = synth.kin40k_like(1500, seed=5)
+    theta = synth.hyper_point("P1")
+    U = synth.inducing_init(20, seed=6)
+    outs = []
+    for dev in (0, 1):
+        c = api.Context(dev)
+        c.set_data(torch.from_numpy(X).to("cuda:%d" % dev), torch.from_numpy(y).to("cuda:%d" % dev))
+        outs.append((c.full_eval(theta, "crps"), c.fitc_eval(theta, U, "logs")))
+        c.close()
+    assert outs[0][0][0] == outs[1][0][0] and np.array_equal(outs[0][0][1], outs[1][0][1])
+    assert outs[0][1][0] == outs[1][1][0] and np.array_equal(outs[0][1][2], outs[1][1][2])
