@@ -449,6 +449,10 @@ def run_ours(args):
         # ---- CPU baseline (oracle port) on a bounded sample ------------------------------------------------
         n_s = pick_sample_rows(25.0, 1)
         dt = cpu_eval_seconds(n_s)
+        if n_s < N_FULL and dt * (N_FULL / float(n_s)) ** 3 <= 30.0:
+            # the probe at N = 1500 over-predicts: the full workload fits the budget after all, so time it unscaled
+            n_s = N_FULL
+            dt = cpu_eval_seconds(n_s)
         scale = (N_FULL / float(n_s)) ** 3
         cpu_baseline = {"value": 1.0 / (dt * scale), "unit": "evals/s", "cores": os.cpu_count() or 1,
                         "threads": cpu_threads(), "kind": "port",
