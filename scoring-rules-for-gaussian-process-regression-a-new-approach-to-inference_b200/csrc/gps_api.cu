@@ -151,8 +151,12 @@ void gps_ctx_release(gps_ctx* ch) {
     if (b->p) cudaFree(b->p);
   if (ch->d_info) cudaFree(ch->d_info);
   if (ch->d_tasks) cudaFree(ch->d_tasks);
-  for (auto e : ch->potrf_events) cudaEventDestroy(e);
-  if (ch->panel_stream) cudaStreamDestroy(ch->panel_stream);
+  for (auto* v : {&ch->potrf_events, &ch->tile_events, &ch->below_events})
+    for (auto e : *v) cudaEventDestroy(e);
+  for (cudaStream_t s : {ch->panel_stream, ch->panel2_stream, ch->trail_stream, ch->tri_stream})
+    if (s) cudaStreamDestroy(s);
+  for (cudaEvent_t e : {ch->fork_ev, ch->join_trail_ev, ch->join_tri_ev})
+    if (e) cudaEventDestroy(e);
   delete ch;
 }
 
@@ -218,7 +222,9 @@ void gps_destroy(gps_ctx* ctx) {
   }
   if (ctx->fold_ctx) gps_ctx_release(ctx->fold_ctx);
   gps_fitc_large_free(ctx);
-  for (auto e : ctx->potrf_events) cudaEventDestroy(e);
+  for (auto* v : {&ctx->potrf_events, &ctx->tile_events, &ctx->below_events})
+    for (auto e : *v) cudaEventDestroy(e);
+  if (ctx->panel2_stream) cudaStreamDestroy(ctx->panel2_stream);
   for (auto e : ctx->stage_ev) if (e) cudaEventDestroy(e);
   if (ctx->panel_stream) cudaStreamDestroy(ctx->panel_stream);
   if (ctx->trail_stream) cudaStreamDestroy(ctx->trail_stream);

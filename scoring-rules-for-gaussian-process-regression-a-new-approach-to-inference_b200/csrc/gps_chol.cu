@@ -392,6 +392,7 @@ int gps_build_tasks(gps_ctx* ctx, int64_t Np) {
   const int no = (nb + OB - 1) / OB;
   ctx->potrf_panel.assign(nb, {});
   ctx->potrf_inner.assign(nb, {});
+  ctx->potrf_innerB.assign(nb, {});
   ctx->potrf_trailA.assign(no, {});
   ctx->potrf_trailB.assign(no, {});
   for (int o = 0; o < no; ++o) {
@@ -400,10 +401,15 @@ int gps_build_tasks(gps_ctx* ctx, int64_t Np) {
       ctx->potrf_panel[k].off = h.size();
       for (int i = k + 1; i < nb; ++i) push(i * T, k * T, k * T, (k + 1) * T, i, k);
       ctx->potrf_panel[k].cnt = h.size() - ctx->potrf_panel[k].off;
+      // inner update, rows of the diagonal block (on the chain) and rows below it (second panel stream)
       ctx->potrf_inner[k].off = h.size();
       for (int j = k + 1; j < c1; ++j)
-        for (int i = j; i < nb; ++i) push(i * T, j * T, k * T, (k + 1) * T, i, j);
+        for (int i = j; i < c1; ++i) push(i * T, j * T, k * T, (k + 1) * T, i, j);
       ctx->potrf_inner[k].cnt = h.size() - ctx->potrf_inner[k].off;
+      ctx->potrf_innerB[k].off = h.size();
+      for (int j = k + 1; j < c1; ++j)
+        for (int i = c1; i < nb; ++i) push(i * T, j * T, k * T, (k + 1) * T, i, j);
+      ctx->potrf_innerB[k].cnt = h.size() - ctx->potrf_innerB[k].off;
     }
     const int n1 = std::min(nb, c1 + OB);
     ctx->potrf_trailA[o].off = h.size();
@@ -523,69 +529,151 @@ int gps_build_tasks(gps_ctx* ctx, int64_t Np) {
   return GPS_OK;
 }
 
-int gps_potrf(gps_ctx* ctx, double* K, double* Xinv, int64_t Np) {
-  const int nb = (int)(Np / T);
-  const int OB = GPS_POTRF_OB;
-  const int no = (nb + OB - 1) / OB;
+namespace {
+
+int ensure_potrf_streams(gps_ctx* ctx, int nb, int no) {
   GPS_ONCE_PER_DEVICE(ctx);
   if (!configured) {
-    GPS_CUDA(cudaFuncSetAttribute(potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)POTF2_SMEM));
+    GPS_CUDA(cudaFuncSetAttribute(potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTF2_SMEM));
     GPS_CUDA(cudaFuncSetAttribute(potf2_inv_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)POTF2V2_SMEM));
     configured = true;
   }
   if (!ctx->panel_stream) {
     int lo = 0, hi = 0;
-    GPS_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    GPS_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));   // lo = least, hi = greatest (numerically smaller)
     GPS_CUDA(cudaStreamCreateWithPriority(&ctx->panel_stream, cudaStreamNonBlocking, hi));
+    GPS_CUDA(cudaStreamCreateWithPriority(&ctx->panel2_stream, cudaStreamNonBlocking, hi));
+    const int mid = (lo - 1 >= hi) ? lo - 1 : lo;
+    GPS_CUDA(cudaStreamCreateWithPriority(&ctx->trail_stream, cudaStreamNonBlocking, mid));
+    GPS_CUDA(cudaStreamCreateWithPriority(&ctx->tri_stream, cudaStreamNonBlocking, lo));
+    GPS_CUDA(cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming));
+    GPS_CUDA(cudaEventCreateWithFlags(&ctx->join_trail_ev, cudaEventDisableTiming));
+    GPS_CUDA(cudaEventCreateWithFlags(&ctx->join_tri_ev, cudaEventDisableTiming));
   }
-  while ((int)ctx->potrf_events.size() < 2 * no + 2) {
-    cudaEvent_t e;
-    GPS_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    ctx->potrf_events.push_back(e);
+  auto grow = [&](std::vector<cudaEvent_t>& v, size_t n) -> int {
+    while (v.size() < n) {
+      cudaEvent_t e;
+      GPS_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      v.push_back(e);
+    }
+    return GPS_OK;
+  };
+  GPS_CHECK(grow(ctx->potrf_events, (size_t)2 * no + 2));
+  GPS_CHECK(grow(ctx->tile_events, (size_t)nb));
+  GPS_CHECK(grow(ctx->below_events, (size_t)no));
+  return GPS_OK;
+}
+
+// Blocked right-looking POTRF, two levels (outer block columns of OB tiles), three concurrent lanes:
+//   chain   (s_pan,  highest priority): for each tile column k of the block column — diagonal kernel,
+//           panel solve and inner update of the rows INSIDE the diagonal 512 x 512 block only
+//           (<= 3 + 6 tiles): the serial path is as short as it can be with 128-wide steps;
+//   below   (s_pan2, highest priority): the same panel solve / inner update for the rows below the
+//           diagonal block, one step behind the chain (tile event k);
+//   trail   (s_trail): the k = 512 update of the rest of the matrix, part A (what the next block column
+//           needs) first so that the next chain starts while part B still runs (look-ahead).
+// with_trtri: the inversion merges are released on a fourth, lowest-priority stream as their operands
+// become final (see gps_build_tasks); s_trail is then an internal mid-priority stream, otherwise the
+// caller's stream.
+int potrf_driver(gps_ctx* ctx, double* K, double* Xinv, double* scratch, int64_t Np, bool with_trtri) {
+  const int nb = (int)(Np / T);
+  const int OB = GPS_POTRF_OB;
+  const int no = (nb + OB - 1) / OB;
+  GPS_CHECK(ensure_potrf_streams(ctx, nb, no));
+  cudaStream_t s_user = ctx->stream, s_pan = ctx->panel_stream, s_pan2 = ctx->panel2_stream, s_tri = ctx->tri_stream;
+  cudaStream_t s_trail = with_trtri ? ctx->trail_stream : s_user;
+  GPS_CUDA(cudaMemsetAsync(ctx->d_info, 0, sizeof(int), s_user));
+  if (with_trtri) {
+    GPS_CUDA(cudaEventRecord(ctx->fork_ev, s_user));
+    GPS_CUDA(cudaStreamWaitEvent(s_trail, ctx->fork_ev, 0));
+    GPS_CUDA(cudaStreamWaitEvent(s_tri, ctx->fork_ev, 0));
   }
-  cudaStream_t s_main = ctx->stream, s_pan = ctx->panel_stream;
-  GPS_CUDA(cudaMemsetAsync(ctx->d_info, 0, sizeof(int), s_main));
-  // event 2*o: block column o has received every update (recorded on s_main);
-  // event 2*o + 1: block column o is factored (recorded on s_pan)
-  GPS_CUDA(cudaEventRecord(ctx->potrf_events[0], s_main));
+  // event 2*o: block column o has received every update (s_trail); 2*o + 1: its diagonal block chain is done
+  // (s_pan); tile_events[k]: tile column k factored inside the diagonal block; below_events[o]: rows below done
+  GPS_CUDA(cudaEventRecord(ctx->potrf_events[0], s_trail));
   int rc = GPS_OK;
+  size_t next_tri = 0;
+  auto gemm_nt = [&](const double* B, double alpha, double beta, const gps_ctx::Range& r, size_t skip, size_t cnt) {
+    return gps_gemm_tasks(ctx, GEMM_KC_KC, K, Np, B, Np, K, Np, alpha, beta, nullptr, false,
+                          ctx->d_tasks + r.off + skip, cnt);
+  };
   for (int o = 0; o < no && rc == GPS_OK; ++o) {
     const int c0 = o * OB, c1 = std::min(nb, c0 + OB);
-    // ---- factor block column o on the panel stream ------------------------------------------
     GPS_CUDA(cudaStreamWaitEvent(s_pan, ctx->potrf_events[2 * o], 0));
-    ctx->stream = s_pan;
+    GPS_CUDA(cudaStreamWaitEvent(s_pan2, ctx->potrf_events[2 * o], 0));
     for (int k = c0; k < c1 && rc == GPS_OK; ++k) {
+      const size_t n_in = (size_t)(c1 - k - 1);   // panel tiles inside the diagonal block come first in the list
+      ctx->stream = s_pan;
       if (ctx->potf2_variant == 0)
         potf2_inv_kernel<<<1, 256, POTF2_SMEM, s_pan>>>(K, Xinv, Np, k, ctx->d_info);
       else
         potf2_inv_dmma_kernel<<<1, 256, POTF2V2_SMEM, s_pan>>>(K, Xinv, Np, k, ctx->d_info, ctx->potf2_prof);
       if (cudaGetLastError() != cudaSuccess) rc = gps_fail(ctx, GPS_ECUDA, "potf2 launch failed");
       ctx->launches++;
-      // panel: L_ik = A_ik * inv(L_kk)'
-      if (rc == GPS_OK)
-        rc = gps_gemm_tasks(ctx, GEMM_KC_KC, K, Np, Xinv, Np, K, Np, 1.0, 0.0, nullptr, false,
-                            ctx->d_tasks + ctx->potrf_panel[k].off, ctx->potrf_panel[k].cnt);
-      // remaining columns of this block column: A_ij -= L_ik L_jk'
-      if (rc == GPS_OK)
-        rc = gps_gemm_tasks(ctx, GEMM_KC_KC, K, Np, K, Np, K, Np, -1.0, 1.0, nullptr, false,
-                            ctx->d_tasks + ctx->potrf_inner[k].off, ctx->potrf_inner[k].cnt);
+      // panel: L_ik = A_ik * inv(L_kk)';  inner: A_ij -= L_ik L_jk' for the remaining columns of the block column
+      if (rc == GPS_OK) rc = gemm_nt(Xinv, 1.0, 0.0, ctx->potrf_panel[k], 0, n_in);
+      if (rc == GPS_OK) rc = gemm_nt(K, -1.0, 1.0, ctx->potrf_inner[k], 0, ctx->potrf_inner[k].cnt);
+      if (rc != GPS_OK) break;
+      GPS_CUDA(cudaEventRecord(ctx->tile_events[k], s_pan));
+      ctx->stream = s_pan2;
+      GPS_CUDA(cudaStreamWaitEvent(s_pan2, ctx->tile_events[k], 0));
+      rc = gemm_nt(Xinv, 1.0, 0.0, ctx->potrf_panel[k], n_in, ctx->potrf_panel[k].cnt - n_in);
+      if (rc == GPS_OK) rc = gemm_nt(K, -1.0, 1.0, ctx->potrf_innerB[k], 0, ctx->potrf_innerB[k].cnt);
     }
-    ctx->stream = s_main;
     if (rc != GPS_OK) break;
     GPS_CUDA(cudaEventRecord(ctx->potrf_events[2 * o + 1], s_pan));
-    // ---- trailing update from block column o on the main stream ------------------------------
-    GPS_CUDA(cudaStreamWaitEvent(s_main, ctx->potrf_events[2 * o + 1], 0));
-    rc = gps_gemm_tasks(ctx, GEMM_KC_KC, K, Np, K, Np, K, Np, -1.0, 1.0, nullptr, false,
-                        ctx->d_tasks + ctx->potrf_trailA[o].off, ctx->potrf_trailA[o].cnt);
+    GPS_CUDA(cudaEventRecord(ctx->below_events[o], s_pan2));
+    // trailing update from block column o
+    ctx->stream = s_trail;
+    GPS_CUDA(cudaStreamWaitEvent(s_trail, ctx->potrf_events[2 * o + 1], 0));
+    GPS_CUDA(cudaStreamWaitEvent(s_trail, ctx->below_events[o], 0));
+    rc = gemm_nt(K, -1.0, 1.0, ctx->potrf_trailA[o], 0, ctx->potrf_trailA[o].cnt);
     if (rc != GPS_OK) break;
-    GPS_CUDA(cudaEventRecord(ctx->potrf_events[2 * o + 2], s_main));
-    rc = gps_gemm_tasks(ctx, GEMM_KC_KC, K, Np, K, Np, K, Np, -1.0, 1.0, nullptr, false,
-                        ctx->d_tasks + ctx->potrf_trailB[o].off, ctx->potrf_trailB[o].cnt);
+    GPS_CUDA(cudaEventRecord(ctx->potrf_events[2 * o + 2], s_trail));
+    rc = gemm_nt(K, -1.0, 1.0, ctx->potrf_trailB[o], 0, ctx->potrf_trailB[o].cnt);
+    if (rc != GPS_OK || !with_trtri) continue;
+    // inversion merges whose operands are final after this step
+    ctx->stream = s_tri;
+    GPS_CUDA(cudaStreamWaitEvent(s_tri, ctx->potrf_events[2 * o + 1], 0));
+    GPS_CUDA(cudaStreamWaitEvent(s_tri, ctx->below_events[o], 0));
+    while (next_tri < ctx->trtri_sched.size() && ctx->trtri_sched[next_tri].step == o && rc == GPS_OK) {
+      const auto& tl = ctx->trtri_sched[next_tri++];
+      if (tl.phase == 0)   // P = L21 * X11
+        rc = gps_gemm_tasks(ctx, GEMM_KC_MC, K, Np, Xinv, Np, scratch, Np, 1.0, 0.0, nullptr, false,
+                            ctx->d_tasks + tl.r.off, tl.r.cnt);
+      else                 // X21 = -X22 * P
+        rc = gps_gemm_tasks(ctx, GEMM_KC_MC, Xinv, Np, scratch, Np, Xinv, Np, -1.0, 0.0, nullptr, false,
+                            ctx->d_tasks + tl.r.off, tl.r.cnt);
+    }
   }
-  ctx->stream = s_main;
-  return rc;
+  ctx->stream = s_user;
+  if (rc != GPS_OK) return rc;
+  if (with_trtri) {
+    GPS_CUDA(cudaEventRecord(ctx->join_trail_ev, s_trail));
+    GPS_CUDA(cudaEventRecord(ctx->join_tri_ev, s_tri));
+    GPS_CUDA(cudaStreamWaitEvent(s_user, ctx->join_trail_ev, 0));
+    GPS_CUDA(cudaStreamWaitEvent(s_user, ctx->join_tri_ev, 0));
+  }
+  return GPS_OK;
+}
+
+}  // namespace
+
+int gps_potrf(gps_ctx* ctx, double* K, double* Xinv, int64_t Np) {
+  return potrf_driver(ctx, K, Xinv, nullptr, Np, false);
+}
+
+// POTRF with the TRTRI merges issued on a lowest-priority stream right after the outer step that
+// finalises their operands: the tail of POTRF (serial chain of diagonal blocks, trailing updates too
+// small to fill the GPU) is filled with inversion work that would otherwise start after it.
+int gps_potrf_trtri(gps_ctx* ctx, double* K, double* Xinv, double* scratch, int64_t Np) {
+  const int no = (int)((Np / T + GPS_POTRF_OB - 1) / GPS_POTRF_OB);
+  if (!ctx->overlap_trtri || no < 3) {
+    GPS_CHECK(gps_potrf(ctx, K, Xinv, Np));
+    return gps_trtri(ctx, K, Xinv, scratch, Np);
+  }
+  return potrf_driver(ctx, K, Xinv, scratch, Np, true);
 }
 
 int gps_check_info(gps_ctx* ctx) {
@@ -606,101 +694,6 @@ int gps_trtri(gps_ctx* ctx, const double* L, double* Xinv, double* scratch, int6
     GPS_CHECK(gps_gemm_tasks(ctx, GEMM_KC_MC, Xinv, Np, scratch, Np, Xinv, Np, -1.0, 0.0, nullptr, false,
                              ctx->d_tasks + ctx->trtri_x[lv].off, ctx->trtri_x[lv].cnt));
   }
-  return GPS_OK;
-}
-
-// POTRF (as gps_potrf) with its trailing updates on an internal mid-priority stream and the TRTRI
-// merges on a lowest-priority stream, each issued right after the outer step that finalises its
-// operands.  The exposed tail of POTRF (the serial chain of diagonal blocks, with trailing updates
-// too small to fill the GPU) is filled with inversion work that would otherwise start after it.
-int gps_potrf_trtri(gps_ctx* ctx, double* K, double* Xinv, double* scratch, int64_t Np) {
-  const int nb = (int)(Np / T);
-  const int OB = GPS_POTRF_OB;
-  const int no = (nb + OB - 1) / OB;
-  if (!ctx->overlap_trtri || no < 3) {
-    GPS_CHECK(gps_potrf(ctx, K, Xinv, Np));
-    return gps_trtri(ctx, K, Xinv, scratch, Np);
-  }
-  GPS_ONCE_PER_DEVICE(ctx);
-  if (!configured) {
-    GPS_CUDA(cudaFuncSetAttribute(potf2_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)POTF2_SMEM));
-    GPS_CUDA(cudaFuncSetAttribute(potf2_inv_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)POTF2V2_SMEM));
-    configured = true;
-  }
-  if (!ctx->panel_stream || !ctx->trail_stream) {
-    int lo = 0, hi = 0;
-    GPS_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));   // lo = least, hi = greatest (numerically smaller)
-    if (!ctx->panel_stream) GPS_CUDA(cudaStreamCreateWithPriority(&ctx->panel_stream, cudaStreamNonBlocking, hi));
-    const int mid = (lo - 1 >= hi) ? lo - 1 : lo;
-    GPS_CUDA(cudaStreamCreateWithPriority(&ctx->trail_stream, cudaStreamNonBlocking, mid));
-    GPS_CUDA(cudaStreamCreateWithPriority(&ctx->tri_stream, cudaStreamNonBlocking, lo));
-    GPS_CUDA(cudaEventCreateWithFlags(&ctx->fork_ev, cudaEventDisableTiming));
-    GPS_CUDA(cudaEventCreateWithFlags(&ctx->join_trail_ev, cudaEventDisableTiming));
-    GPS_CUDA(cudaEventCreateWithFlags(&ctx->join_tri_ev, cudaEventDisableTiming));
-  }
-  while ((int)ctx->potrf_events.size() < 2 * no + 2) {
-    cudaEvent_t e;
-    GPS_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    ctx->potrf_events.push_back(e);
-  }
-  cudaStream_t s_user = ctx->stream, s_trail = ctx->trail_stream, s_pan = ctx->panel_stream, s_tri = ctx->tri_stream;
-  GPS_CUDA(cudaMemsetAsync(ctx->d_info, 0, sizeof(int), s_user));
-  GPS_CUDA(cudaEventRecord(ctx->fork_ev, s_user));
-  GPS_CUDA(cudaStreamWaitEvent(s_trail, ctx->fork_ev, 0));
-  GPS_CUDA(cudaStreamWaitEvent(s_tri, ctx->fork_ev, 0));
-  GPS_CUDA(cudaEventRecord(ctx->potrf_events[0], s_trail));
-  int rc = GPS_OK;
-  size_t next_tri = 0;
-  for (int o = 0; o < no && rc == GPS_OK; ++o) {
-    const int c0 = o * OB, c1 = std::min(nb, c0 + OB);
-    GPS_CUDA(cudaStreamWaitEvent(s_pan, ctx->potrf_events[2 * o], 0));
-    ctx->stream = s_pan;
-    for (int k = c0; k < c1 && rc == GPS_OK; ++k) {
-      if (ctx->potf2_variant == 0)
-        potf2_inv_kernel<<<1, 256, POTF2_SMEM, s_pan>>>(K, Xinv, Np, k, ctx->d_info);
-      else
-        potf2_inv_dmma_kernel<<<1, 256, POTF2V2_SMEM, s_pan>>>(K, Xinv, Np, k, ctx->d_info, ctx->potf2_prof);
-      if (cudaGetLastError() != cudaSuccess) rc = gps_fail(ctx, GPS_ECUDA, "potf2 launch failed");
-      ctx->launches++;
-      if (rc == GPS_OK)
-        rc = gps_gemm_tasks(ctx, GEMM_KC_KC, K, Np, Xinv, Np, K, Np, 1.0, 0.0, nullptr, false,
-                            ctx->d_tasks + ctx->potrf_panel[k].off, ctx->potrf_panel[k].cnt);
-      if (rc == GPS_OK)
-        rc = gps_gemm_tasks(ctx, GEMM_KC_KC, K, Np, K, Np, K, Np, -1.0, 1.0, nullptr, false,
-                            ctx->d_tasks + ctx->potrf_inner[k].off, ctx->potrf_inner[k].cnt);
-    }
-    if (rc != GPS_OK) break;
-    GPS_CUDA(cudaEventRecord(ctx->potrf_events[2 * o + 1], s_pan));
-    // trailing update from block column o
-    ctx->stream = s_trail;
-    GPS_CUDA(cudaStreamWaitEvent(s_trail, ctx->potrf_events[2 * o + 1], 0));
-    rc = gps_gemm_tasks(ctx, GEMM_KC_KC, K, Np, K, Np, K, Np, -1.0, 1.0, nullptr, false,
-                        ctx->d_tasks + ctx->potrf_trailA[o].off, ctx->potrf_trailA[o].cnt);
-    if (rc != GPS_OK) break;
-    GPS_CUDA(cudaEventRecord(ctx->potrf_events[2 * o + 2], s_trail));
-    rc = gps_gemm_tasks(ctx, GEMM_KC_KC, K, Np, K, Np, K, Np, -1.0, 1.0, nullptr, false,
-                        ctx->d_tasks + ctx->potrf_trailB[o].off, ctx->potrf_trailB[o].cnt);
-    if (rc != GPS_OK) break;
-    // inversion merges whose operands are final after this step
-    ctx->stream = s_tri;
-    GPS_CUDA(cudaStreamWaitEvent(s_tri, ctx->potrf_events[2 * o + 1], 0));
-    while (next_tri < ctx->trtri_sched.size() && ctx->trtri_sched[next_tri].step == o && rc == GPS_OK) {
-      const auto& tl = ctx->trtri_sched[next_tri++];
-      if (tl.phase == 0)   // P = L21 * X11
-        rc = gps_gemm_tasks(ctx, GEMM_KC_MC, K, Np, Xinv, Np, scratch, Np, 1.0, 0.0, nullptr, false,
-                            ctx->d_tasks + tl.r.off, tl.r.cnt);
-      else                 // X21 = -X22 * P
-        rc = gps_gemm_tasks(ctx, GEMM_KC_MC, Xinv, Np, scratch, Np, Xinv, Np, -1.0, 0.0, nullptr, false,
-                            ctx->d_tasks + tl.r.off, tl.r.cnt);
-    }
-  }
-  ctx->stream = s_user;
-  if (rc != GPS_OK) return rc;
-  GPS_CUDA(cudaEventRecord(ctx->join_trail_ev, s_trail));
-  GPS_CUDA(cudaEventRecord(ctx->join_tri_ev, s_tri));
-  GPS_CUDA(cudaStreamWaitEvent(s_user, ctx->join_trail_ev, 0));
-  GPS_CUDA(cudaStreamWaitEvent(s_user, ctx->join_tri_ev, 0));
   return GPS_OK;
 }
 
