@@ -303,7 +303,7 @@ int gps_full_eval(gps_ctx* ctx, const double* theta, int score, double* obj, dou
     if (grad) {
       GPS_CHECK(gps_symv(ctx, ctx->Kb.p, Np, v + V_ABAR * Np, v + V_U * Np));
       GPS_CHECK(stage_mark(ctx, gps_ctx::ST_SCORE));
-      GPS_CHECK(gps_symprod(ctx, ctx->Kb.p, v + V_DBAR * Np, ctx->Sb.p, Np));
+      GPS_CHECK(gps_symprod(ctx, ctx->Kb.p, v + V_DBAR * Np, ctx->Xb.p, ctx->Sb.p, Np));   // L^-1 in Xb is dead after LAUUM
       GPS_CHECK(stage_mark(ctx, gps_ctx::ST_SYMPROD));
       GPS_CHECK(gps_grad_contract(ctx, 0, ctx->Sb.p, N, Np, ctx->X.p, D, par, v + V_ALPHA * Np, v + V_U * Np,
                                   par + PAR_GSUM));

@@ -702,7 +702,33 @@ int gps_lauum(gps_ctx* ctx, const double* Xinv, double* Kinv, int64_t Np) {
                         ctx->d_tasks + ctx->lauum.off, ctx->lauum.cnt);
 }
 
-int gps_symprod(gps_ctx* ctx, const double* Kinv, const double* dvec, double* S, int64_t Np) {
-  return gps_gemm_tasks(ctx, GEMM_KC_KC, Kinv, Np, Kinv, Np, S, Np, 1.0, 0.0, dvec, false,
+namespace {
+// T = Kinv * diag(dvec): 16-byte loads/stores over the full matrix
+__global__ void __launch_bounds__(256)
+scale_cols_kernel(const double* __restrict__ A, const double* __restrict__ dvec, double* __restrict__ Tm, int64_t Np) {
+  const int64_t e = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
+  if (e >= Np * Np) return;
+  const int64_t c = e % Np;
+  const double2 a = *reinterpret_cast<const double2*>(A + e);
+  const double2 d = *reinterpret_cast<const double2*>(dvec + c);
+  double2 o;
+  o.x = a.x * d.x;
+  o.y = a.y * d.y;
+  *reinterpret_cast<double2*>(Tm + e) = o;
+}
+}  // namespace
+
+// S = Kinv diag(dvec) Kinv (lower tiles).  The k-scaling can ride in the GEMM's fragment loop (scratch ==
+// nullptr), but that costs 5 % of the DMMA rate (32.4 vs 34.2 TFLOP/s at n = 10112, tools/symprod_probe.py);
+// one HBM-bound pass that writes T = Kinv diag(dvec) (0.3 ms at N = 10^4) and a plain T * Kinv' is faster.
+int gps_symprod(gps_ctx* ctx, const double* Kinv, const double* dvec, double* scratch, double* S, int64_t Np) {
+  if (!scratch)
+    return gps_gemm_tasks(ctx, GEMM_KC_KC, Kinv, Np, Kinv, Np, S, Np, 1.0, 0.0, dvec, false,
+                          ctx->d_tasks + ctx->symprod.off, ctx->symprod.cnt);
+  const int64_t pairs = Np * Np / 2;
+  scale_cols_kernel<<<(unsigned)((pairs + 255) / 256), 256, 0, ctx->stream>>>(Kinv, dvec, scratch, Np);
+  GPS_LAUNCH_CHECK();
+  ctx->launches++;
+  return gps_gemm_tasks(ctx, GEMM_KC_KC, scratch, Np, Kinv, Np, S, Np, 1.0, 0.0, nullptr, false,
                         ctx->d_tasks + ctx->symprod.off, ctx->symprod.cnt);
 }

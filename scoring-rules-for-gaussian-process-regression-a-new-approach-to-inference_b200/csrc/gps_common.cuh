@@ -208,7 +208,7 @@ int gps_trtri(gps_ctx* ctx, const double* L, double* Xinv, double* scratch, int6
 // POTRF with the TRTRI merges issued on a low-priority stream as soon as their block columns are final
 int gps_potrf_trtri(gps_ctx* ctx, double* K, double* Xinv, double* scratch, int64_t Np);
 int gps_lauum(gps_ctx* ctx, const double* Xinv, double* Kinv, int64_t Np);
-int gps_symprod(gps_ctx* ctx, const double* Kinv, const double* dvec, double* S, int64_t Np);
+int gps_symprod(gps_ctx* ctx, const double* Kinv, const double* dvec, double* scratch, double* S, int64_t Np);
 int gps_check_info(gps_ctx* ctx);
 // gps_score.cu
 int gps_symv(gps_ctx* ctx, const double* A, int64_t Np, const double* x, double* y);
