@@ -276,10 +276,10 @@ def run_ours(args):
     ctx.set_data(Xd, yd)
 
     # ---- roofline of the dominant kernel (separate pass: per-launch events switched on) ---------------
-    # The shipped schedule runs the TRTRI merges concurrently with POTRF on priority streams; events around a
-    # launch that shares the GPU with another stream's launch bracket both, so the per-launch durations are
-    # taken with that overlap switched off (knob 4): every GEMM launch is then timed running alone.
-    ctx._check(ctx._lib.gps_dbg_set_variant(ctx._h, 4, 0))
+    # The shipped schedule runs the POTRF lanes and the TRTRI merges concurrently on priority streams; events
+    # around a launch that shares the GPU with another stream's launch bracket both, so the per-launch
+    # durations are taken with every launch on one stream (knob 4 = 2): each GEMM launch is timed running alone.
+    ctx._check(ctx._lib.gps_dbg_set_variant(ctx._h, 4, 2))
     ctx.set_gemm_timing(True)
     gms, gl = [], 0
     for _ in range(2):
@@ -300,10 +300,10 @@ def run_ours(args):
     if rank == 0:
         traffic, traffic_how = None, None
         try:   # DRAM bytes of the tile-GEMM launches of one evaluation, from the committed ncu launch list
-            with open(os.path.join(ROOT, "profiles", "r01_launch_summary_N10000_v7.json")) as fh:
+            with open(os.path.join(ROOT, "profiles", "r01_launch_summary_N10000_v8.json")) as fh:
                 traffic = float(json.load(fh)["gemm_dram_bytes_per_eval"])
                 traffic_how = ("dram__bytes_read.sum + dram__bytes_write.sum summed over the tile-GEMM launches of one "
-                               "evaluation, ncu launch list profiles/r01_launches_N10000_v7.csv (bytes per step, like "
+                               "evaluation, ncu launch list profiles/r01_launches_N10000_v8.csv (bytes per step, like "
                                "achieved); the kernel is tensor-bound: DRAM runs at ~6% of peak")
         except Exception:
             pass
@@ -313,11 +313,10 @@ def run_ours(args):
                     "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic, "traffic_how": traffic_how,
                     "launches_per_step": gl, "avg_launch_ms": gemm_ms / max(gl, 1),
                     "algorithmic_flops_per_step": flops, "kernel_share_of_step": min(1.0, gemm_ms / sum(stages_serial.values())),
-                    "share_note": "sum of per-launch CUDA-event durations / device time of the same (non-overlapped) "
-                                  "evaluation; launches on the POTRF look-ahead stream still overlap the main stream, so "
-                                  "the raw ratio can exceed 1 (raw %.3f)" % (gemm_ms / sum(stages_serial.values())),
-                    "stages_ms": stages, "stages_ms_without_overlap": stages_serial,
-                    "timing_note": "per-launch durations taken with the POTRF/TRTRI overlap switched off so that each "
+                    "share_note": "sum of per-launch CUDA-event durations / device time of the same serialised "
+                                  "evaluation (raw %.3f)" % (gemm_ms / sum(stages_serial.values())),
+                    "stages_ms": stages, "stages_ms_serialised": stages_serial,
+                    "timing_note": "per-launch durations taken with all launches serialised on one stream so that each "
                                    "launch is timed running alone; ms_per_step / value are the shipped (overlapped) schedule",
                     "stage_note": "POTRF and the TRTRI merges run overlapped (trailing updates / inversion merges on "
                                   "separate priority streams): 'potrf' is the time of both, 'trtri' the join",

@@ -32,7 +32,9 @@ int gps_dbg_fp64_peak(gps_ctx* ctx, int iters, double* dmma_tflops, double* dfma
  * POTRF (0: register-cyclic, 1: 32-blocked DMMA = default); what = 2 selects the FITC row passes
  * (0: thread-per-row, 1: tile/DMMA formulation = default); what = 3 sets the number of inducing points from
  * which gps_fitc_eval switches to the matrix form (default 33; lower it to A/B the two paths at M <= 32);
- * what = 4 turns the POTRF / TRTRI overlap of the full-GP evaluation off (0) or on (1 = default). */
+ * what = 4 selects the schedule of the full-GP factorisation: 1 = POTRF and the TRTRI merges overlapped on
+ * priority streams (default), 0 = POTRF (with its look-ahead lanes) then TRTRI, 2 = every launch on the caller's
+ * stream, one at a time (used to time launches alone). */
 int gps_dbg_set_variant(gps_ctx* ctx, int what, int value);
 
 /* clock64 phase stamps of the last diagonal-block kernel launch (first call arms the recording):

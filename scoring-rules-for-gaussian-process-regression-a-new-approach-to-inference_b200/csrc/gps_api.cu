@@ -124,7 +124,7 @@ int gps_factor_and_invert(gps_ctx* ctx, bool want_logdet) {
   GPS_CHECK(stage_mark(ctx, gps_ctx::ST_BEGIN));
   GPS_CHECK(gps_gram_sym(ctx, ctx->X.p, N, Np, ctx->D, ctx->params.p, ctx->Kb.p));
   GPS_CHECK(stage_mark(ctx, gps_ctx::ST_GRAM));
-  if (ctx->overlap_trtri) {
+  if (ctx->overlap_trtri == 1) {
     // POTRF and the inversion merges overlap: the two stages are reported as one ("potrf" = both, "trtri" = 0)
     GPS_CHECK(gps_potrf_trtri(ctx, ctx->Kb.p, ctx->Xb.p, ctx->Sb.p, Np));
     if (want_logdet) GPS_CHECK(gps_diag_extract(ctx, ctx->Kb.p, Np, v + V_LOGD * Np, 1));

@@ -581,7 +581,11 @@ int potrf_driver(gps_ctx* ctx, double* K, double* Xinv, double* scratch, int64_t
   const int OB = GPS_POTRF_OB;
   const int no = (nb + OB - 1) / OB;
   GPS_CHECK(ensure_potrf_streams(ctx, nb, no));
-  cudaStream_t s_user = ctx->stream, s_pan = ctx->panel_stream, s_pan2 = ctx->panel2_stream, s_tri = ctx->tri_stream;
+  // overlap_trtri == 2 (debug): every lane on the caller's stream, so that launches run one at a time and
+  // CUDA events around a launch bracket only that launch (the kernel-timing pass of bench.py)
+  const bool serial = ctx->overlap_trtri == 2;
+  cudaStream_t s_user = ctx->stream, s_tri = ctx->tri_stream;
+  cudaStream_t s_pan = serial ? s_user : ctx->panel_stream, s_pan2 = serial ? s_user : ctx->panel2_stream;
   cudaStream_t s_trail = with_trtri ? ctx->trail_stream : s_user;
   GPS_CUDA(cudaMemsetAsync(ctx->d_info, 0, sizeof(int), s_user));
   if (with_trtri) {
@@ -669,7 +673,7 @@ int gps_potrf(gps_ctx* ctx, double* K, double* Xinv, int64_t Np) {
 // small to fill the GPU) is filled with inversion work that would otherwise start after it.
 int gps_potrf_trtri(gps_ctx* ctx, double* K, double* Xinv, double* scratch, int64_t Np) {
   const int no = (int)((Np / T + GPS_POTRF_OB - 1) / GPS_POTRF_OB);
-  if (!ctx->overlap_trtri || no < 3) {
+  if (ctx->overlap_trtri != 1 || no < 3) {
     GPS_CHECK(gps_potrf(ctx, K, Xinv, Np));
     return gps_trtri(ctx, K, Xinv, scratch, Np);
   }

@@ -13,7 +13,7 @@ X, y = synth.kin40k_like(N)
 theta = synth.hyper_point("P1")
 ctx = api.Context(0)
 ctx.set_data(torch.from_numpy(X).cuda(), torch.from_numpy(y).cuda())
-for mode in (0, 1, 0, 1):
+for mode in (2, 0, 1, 1):
     ctx._check(ctx._lib.gps_dbg_set_variant(ctx._h, 4, mode))
     for _ in range(2):
         v, g = ctx.full_eval(theta, "crps")
