@@ -171,6 +171,15 @@ def test_descend_equals_python_loop(ctx):
         assert abs(v - trace[i]) <= 1e-12 * abs(v)
         ref, Ur = ref - 0.2 * g, Ur - 0.1 * gU
     assert relerr(th, ref) <= 1e-12 and relerr(Uo, Ur) <= 1e-12
+    # the same loop beyond 32 inducing points (matrix form of the FITC passes)
+    U = X[:48] + 0.01
+    th, Uo, trace = ctx.fitc_descend(theta, U, "crps", 0.2, 0.1, 3)
+    ref, Ur = theta.copy(), U.copy()
+    for i in range(3):
+        v, g, gU = ctx.fitc_eval(ref, Ur, "crps")
+        assert abs(v - trace[i]) <= 1e-12 * abs(v)
+        ref, Ur = ref - 0.2 * g, Ur - 0.1 * gU
+    assert relerr(th, ref) <= 1e-12 and relerr(Uo, Ur) <= 1e-12
 
 
 @pytest.mark.parametrize("name", [n for n in golden_names(("c3",)) if "ragged" not in n])
