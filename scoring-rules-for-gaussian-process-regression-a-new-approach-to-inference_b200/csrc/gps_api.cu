@@ -157,6 +157,8 @@ void gps_ctx_release(gps_ctx* ch) {
     if (s) cudaStreamDestroy(s);
   for (cudaEvent_t e : {ch->fork_ev, ch->join_trail_ev, ch->join_tri_ev})
     if (e) cudaEventDestroy(e);
+  for (cudaEvent_t e : ch->stage_ev)
+    if (e) cudaEventDestroy(e);
   delete ch;
 }
 
@@ -221,6 +223,13 @@ void gps_destroy(gps_ctx* ctx) {
     cudaEventDestroy(pr.second);
   }
   if (ctx->fold_ctx) gps_ctx_release(ctx->fold_ctx);
+  for (gps_ctx* ln : ctx->grid_lanes) {
+    cudaStream_t s = ln->own_stream;
+    for (DevBuf* b : {&ln->X, &ln->y})
+      if (b->p) cudaFree(b->p);
+    gps_ctx_release(ln);
+    if (s) cudaStreamDestroy(s);
+  }
   gps_fitc_large_free(ctx);
   for (auto* v : {&ctx->potrf_events, &ctx->tile_events, &ctx->below_events})
     for (auto e : *v) cudaEventDestroy(e);

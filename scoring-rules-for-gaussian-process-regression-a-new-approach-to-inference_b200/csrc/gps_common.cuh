@@ -68,6 +68,7 @@ struct gps_ctx {
   DevBuf Gb;       // block-diagonal Gamma of the 4-fold DSS gradient (allocated on first use)
   DevBuf fold_vecs;
   gps_ctx* fold_ctx = nullptr;   // child context for the N/4-sized fold factorisations (DSS)
+  std::vector<gps_ctx*> grid_lanes;   // lane contexts of the large-n grid sweep (own streams and workspaces)
   DevBuf red;      // reduction scratch
   DevBuf params;   // device copy of theta-derived parameters
   int* d_info = nullptr;       // device: first failing pivot (0 = ok)

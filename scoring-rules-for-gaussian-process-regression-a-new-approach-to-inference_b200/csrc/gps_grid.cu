@@ -125,8 +125,9 @@ grid_small_kernel(const double* __restrict__ x, const double* __restrict__ y, in
 __global__ void __launch_bounds__(1024)
 grid_rows_kernel(int which, int64_t n, const double* __restrict__ y, const double* __restrict__ alpha,
                  const double* __restrict__ d, const double* __restrict__ logd, double j2,
-                 double* __restrict__ out) {
+                 double* __restrict__ out, const int* __restrict__ info, int* __restrict__ latch, int point) {
   __shared__ double red[32];
+  if (threadIdx.x == 0 && *info != 0 && *latch == 0) *latch = point + 1;   // the lane's next POTRF clears info
   double s = 0.0;
   for (int64_t i = threadIdx.x; i < n; i += blockDim.x)
     s += grid_row_value(which, y[i], alpha[i], d[i], j2, which == GPS_GRID_NLML ? logd[i] : 0.0);
@@ -171,25 +172,73 @@ extern "C" int gps_grid_eval(gps_ctx* ctx, const double* x, const double* y, int
     GPS_CUDA(cudaMemcpyAsync(out, dout, G * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     return gps_check_info(ctx);
   }
-  // large n: the blocked factorisation per grid point (1-D inputs, a = 0, b = log l, c = 2 log j)
-  GPS_CHECK(gps_set_data(ctx, x, y, n, 1));
-  const int64_t Np = ctx->Np;
-  GPS_CHECK(gps_ensure_ws(ctx, Np));
-  double* v = ctx->vecs.p;
-  for (int64_t g = 0; g < G; ++g) {
-    const double theta[3] = {0.0, log(ls[g]), 2.0 * log(noise_sd[g])};
-    GPS_CHECK(gps_upload_params(ctx, theta, 1, nullptr, nullptr));
-    ctx->gemm_events_used = 0;
-    GPS_CHECK(gps_factor_and_invert(ctx, which == GPS_GRID_NLML));
-    GPS_CHECK(gps_diag_extract(ctx, ctx->Kb.p, Np, v + V_D * Np, 0));
-    grid_rows_kernel<<<1, 1024, 0, ctx->stream>>>(which, n, ctx->y.p, v + V_ALPHA * Np, v + V_D * Np,
-                                                  v + V_LOGD * Np, noise_sd[g] * noise_sd[g],
-                                                  ctx->params.p + PAR_OBJ);
-    GPS_LAUNCH_CHECK();
-    ctx->launches++;
-    GPS_CUDA(cudaMemcpyAsync(out + g, ctx->params.p + PAR_OBJ, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    GPS_CHECK(gps_check_info(ctx));
+  // large n: the blocked factorisation per grid point (1-D inputs, a = 0, b = log l, c = 2 log j).
+  // At these sizes one evaluation is bound by the serial chain of diagonal blocks (1.6 ms at n = 2048 with
+  // most SMs idle), so the points are dealt round-robin to LANES lane contexts, each with its own stream and
+  // workspaces: their chains overlap and the GEMM launches of one lane fill the gaps of the others.  Nothing
+  // is read back until every lane has drained; a failed factorisation is latched per lane.
+  const int64_t Np = gps_pad(n);
+  const int LANES = (int)std::min<int64_t>(G, Np <= 4096 ? 8 : (Np <= 8192 ? 2 : 1));
+  while ((int)ctx->grid_lanes.size() < LANES) {
+    gps_ctx* ln = new gps_ctx();
+    ln->device = ctx->device;
+    ln->sm_count = ctx->sm_count;
+    if (cudaStreamCreateWithFlags(&ln->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+      delete ln;
+      return gps_fail(ctx, GPS_ECUDA, "grid_eval: cannot create a lane stream");
+    }
+    ln->stream = ln->own_stream;
+    ctx->grid_lanes.push_back(ln);
   }
-  ctx->loo_valid = false;
+  GPS_CHECK(gps_ensure(ctx, ctx->stage[2], (size_t)G + 8));
+  double* dres = ctx->stage[2].p;
+  int* dlatch = reinterpret_cast<int*>(dres + G);   // one latch per lane: 1 + index of its first failed point
+  GPS_CUDA(cudaMemsetAsync(dlatch, 0, 8 * sizeof(int), ctx->stream));
+  GPS_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (int l = 0; l < LANES; ++l) {
+    gps_ctx* ln = ctx->grid_lanes[l];
+    ln->gemm_variant = ctx->gemm_variant;
+    ln->potf2_variant = ctx->potf2_variant;
+    ln->overlap_trtri = ctx->overlap_trtri;
+    ln->time_gemm = false;
+    int r = gps_set_data(ln, x, y, n, 1);
+    if (r == GPS_OK) r = gps_ensure_ws(ln, Np);
+    if (r != GPS_OK) return gps_fail(ctx, r, "grid_eval lane %d: %s", l, ln->err.c_str());
+  }
+  int rc = GPS_OK;
+  for (int64_t g = 0; g < G && rc == GPS_OK; ++g) {
+    gps_ctx* ln = ctx->grid_lanes[g % LANES];
+    double* v = ln->vecs.p;
+    const double theta[3] = {0.0, log(ls[g]), 2.0 * log(noise_sd[g])};
+    rc = gps_upload_params(ln, theta, 1, nullptr, nullptr);
+    if (rc == GPS_OK) rc = gps_factor_and_invert(ln, which == GPS_GRID_NLML);
+    if (rc == GPS_OK) rc = gps_diag_extract(ln, ln->Kb.p, Np, v + V_D * Np, 0);
+    if (rc != GPS_OK) {
+      gps_fail(ctx, rc, "grid_eval point %lld: %s", (long long)g, ln->err.c_str());
+      break;
+    }
+    grid_rows_kernel<<<1, 1024, 0, ln->stream>>>(which, n, ln->y.p, v + V_ALPHA * Np, v + V_D * Np, v + V_LOGD * Np,
+                                                 noise_sd[g] * noise_sd[g], dres + g, ln->d_info,
+                                                 dlatch + (g % LANES), (int)g);
+    if (cudaGetLastError() != cudaSuccess) rc = gps_fail(ctx, GPS_ECUDA, "grid_eval: launch failed");
+  }
+  for (int l = 0; l < LANES; ++l) {
+    gps_ctx* ln = ctx->grid_lanes[l];
+    if (cudaStreamSynchronize(ln->stream) != cudaSuccess && rc == GPS_OK) rc = gps_fail(ctx, GPS_ECUDA, "grid_eval: lane %d failed", l);
+    ctx->launches += ln->launches + 0;
+    ln->launches = 0;
+  }
+  ctx->launches += G;
+  if (rc != GPS_OK) return rc;
+  int latch[8];
+  GPS_CUDA(cudaMemcpyAsync(out, dres, G * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  GPS_CUDA(cudaMemcpyAsync(latch, dlatch, sizeof latch, cudaMemcpyDeviceToHost, ctx->stream));
+  GPS_CUDA(cudaStreamSynchronize(ctx->stream));
+  int64_t bad = -1;
+  for (int l = 0; l < LANES; ++l)
+    if (latch[l] && (bad < 0 || latch[l] - 1 < bad)) bad = latch[l] - 1;
+  if (bad >= 0)
+    return gps_fail(ctx, GPS_ENOTPD, "grid_eval: K + j^2 I not positive definite at grid point %lld (l = %g, j = %g)",
+                    (long long)bad, ls[bad], noise_sd[bad]);
   return GPS_OK;
 }
