@@ -114,3 +114,19 @@ def test_two_devices_in_one_process():
         c.close()
     assert outs[0][0][0] == outs[1][0][0] and np.array_equal(outs[0][0][1], outs[1][0][1])
     assert outs[0][1][0] == outs[1][1][0] and np.array_equal(outs[0][1][2], outs[1][1][2])
+
+
+def test_full_many_input_dimensions(ctx):
+    """D = 40 inputs (the Gram and contraction kernels stage D x 128 panels in shared memory; limit 64)."""
+    from oracle import gp_oracle as O
+    rng = np.random.default_rng(77)
+    n, d = 300, 40
+    X = rng.standard_normal((n, d))
+    y = rng.standard_normal((n, 1))
+    theta = np.concatenate([[0.1], np.log(rng.uniform(3.0, 6.0, d)), [-1.5]])
+    ctx.set_data(_dev(X), _dev(y))
+    for score in ("crps", "logs", "nlml"):
+        val, grad = ctx.full_eval(theta, score)
+        oval, og = O.full_obj_grad(X, y, theta, O.SCORES[score])
+        assert abs(val - oval) <= 1e-8 * abs(oval), score
+        assert relerr(grad, og) <= 1e-6, score

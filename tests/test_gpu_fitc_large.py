@@ -181,3 +181,22 @@ def test_large_m_finite_difference(ctx):
         fm = ctx.fitc_eval(theta - h * vt, U - h * vu, score)[0]
         fd = (fp - fm) / (2 * h)
         assert abs(fd - an) <= 2e-5 * max(abs(an), 1e-3), (score, fd, an)
+
+
+@pytest.mark.parametrize("n,m_ind,d", [(30, 40, 2), (129, 33, 1), (128, 128, 5), (40, 129, 16)])
+def test_large_m_tiny_and_boundary_shapes(ctx, n, m_ind, d):
+    """Fewer rows than inducing points, sizes on / next to the 128 padding boundary, D = 1 and D = 16."""
+    from oracle import gp_oracle as O
+    from oracle import woodbury as Wd
+    rng = np.random.default_rng(1000 + n + m_ind)
+    X = rng.uniform(-1, 1, (n, d))
+    y = rng.standard_normal(n)
+    U = rng.uniform(-1, 1, (m_ind, d))
+    theta = np.concatenate([[0.2], np.log(rng.uniform(0.7, 1.5, d)), [-1.0]])
+    ctx.set_data(_dev(X), _dev(y))
+    for score in ("crps", "logs", "nlml"):
+        val, grad, gU = ctx.fitc_eval(theta, U, score)
+        oval, og, ogU, _, _ = Wd.fitc_obj_grad(X, y, U, theta, O.SCORES[score])
+        assert abs(val - oval) <= OBJ_TOL * abs(oval), score
+        assert relerr(grad, og) <= GRAD_TOL, score
+        assert relerr(gU, ogU) <= GRAD_TOL, score
