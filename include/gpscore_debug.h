@@ -37,6 +37,11 @@ int gps_dbg_fp64_peak(gps_ctx* ctx, int iters, double* dmma_tflops, double* dfma
  * stream, one at a time (used to time launches alone). */
 int gps_dbg_set_variant(gps_ctx* ctx, int what, int value);
 
+/* Timeline of the factorisation lanes of the last full-GP evaluation (arm with gps_dbg_set_variant(ctx, 6, 1)):
+ * codes[i] = lane * 1000 + outer step (lane 1 diagonal-block chain, 2 rows below, 3 trailing update, 4 inversion
+ * merges), ms[i] = time since the factorisation started.  Returns the number of entries (<= cap). */
+int gps_dbg_trace(gps_ctx* ctx, int cap, int* codes, double* ms);
+
 /* clock64 phase stamps of the last diagonal-block kernel launch (first call arms the recording):
  * cycles17[k] = cycles since kernel start at phase boundary k (load, 4 x {factor, panel, update},
  * sub-block inverses, off-diagonal inverse, write-back). */

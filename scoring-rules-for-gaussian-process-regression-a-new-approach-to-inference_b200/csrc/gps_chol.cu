@@ -576,6 +576,19 @@ int ensure_potrf_streams(gps_ctx* ctx, int nb, int no) {
 // with_trtri: the inversion merges are released on a fourth, lowest-priority stream as their operands
 // become final (see gps_build_tasks); s_trail is then an internal mid-priority stream, otherwise the
 // caller's stream.
+int trace_mark(gps_ctx* ctx, int code, cudaStream_t s) {
+  if (!ctx->trace_on) return GPS_OK;
+  if (ctx->trace_used == ctx->trace.size()) {
+    cudaEvent_t e;
+    GPS_CUDA(cudaEventCreate(&e));
+    ctx->trace.push_back({code, e});
+  }
+  ctx->trace[ctx->trace_used].first = code;
+  GPS_CUDA(cudaEventRecord(ctx->trace[ctx->trace_used].second, s));
+  ctx->trace_used++;
+  return GPS_OK;
+}
+
 int potrf_driver(gps_ctx* ctx, double* K, double* Xinv, double* scratch, int64_t Np, bool with_trtri) {
   const int nb = (int)(Np / T);
   const int OB = GPS_POTRF_OB;
@@ -596,6 +609,8 @@ int potrf_driver(gps_ctx* ctx, double* K, double* Xinv, double* scratch, int64_t
   // event 2*o: block column o has received every update (s_trail); 2*o + 1: its diagonal block chain is done
   // (s_pan); tile_events[k]: tile column k factored inside the diagonal block; below_events[o]: rows below done
   GPS_CUDA(cudaEventRecord(ctx->potrf_events[0], s_trail));
+  ctx->trace_used = 0;
+  GPS_CHECK(trace_mark(ctx, 0, s_trail));
   int rc = GPS_OK;
   size_t next_tri = 0;
   auto gemm_nt = [&](const double* B, double alpha, double beta, const gps_ctx::Range& r, size_t skip, size_t cnt) {
@@ -628,6 +643,8 @@ int potrf_driver(gps_ctx* ctx, double* K, double* Xinv, double* scratch, int64_t
     if (rc != GPS_OK) break;
     GPS_CUDA(cudaEventRecord(ctx->potrf_events[2 * o + 1], s_pan));
     GPS_CUDA(cudaEventRecord(ctx->below_events[o], s_pan2));
+    GPS_CHECK(trace_mark(ctx, 1000 + o, s_pan));
+    GPS_CHECK(trace_mark(ctx, 2000 + o, s_pan2));
     // trailing update from block column o
     ctx->stream = s_trail;
     GPS_CUDA(cudaStreamWaitEvent(s_trail, ctx->potrf_events[2 * o + 1], 0));
@@ -636,6 +653,7 @@ int potrf_driver(gps_ctx* ctx, double* K, double* Xinv, double* scratch, int64_t
     if (rc != GPS_OK) break;
     GPS_CUDA(cudaEventRecord(ctx->potrf_events[2 * o + 2], s_trail));
     rc = gemm_nt(K, -1.0, 1.0, ctx->potrf_trailB[o], 0, ctx->potrf_trailB[o].cnt);
+    if (rc == GPS_OK) rc = trace_mark(ctx, 3000 + o, s_trail);
     if (rc != GPS_OK || !with_trtri) continue;
     // inversion merges whose operands are final after this step
     ctx->stream = s_tri;
@@ -650,6 +668,7 @@ int potrf_driver(gps_ctx* ctx, double* K, double* Xinv, double* scratch, int64_t
         rc = gps_gemm_tasks(ctx, GEMM_KC_MC, Xinv, Np, scratch, Np, Xinv, Np, -1.0, 0.0, nullptr, false,
                             ctx->d_tasks + tl.r.off, tl.r.cnt);
     }
+    if (rc == GPS_OK) rc = trace_mark(ctx, 4000 + o, s_tri);
   }
   ctx->stream = s_user;
   if (rc != GPS_OK) return rc;

@@ -94,6 +94,10 @@ struct gps_ctx {
   cudaStream_t tri_stream = nullptr;            // overlapped TRTRI (lowest priority)
   cudaEvent_t fork_ev = nullptr, join_trail_ev = nullptr, join_tri_ev = nullptr;
   int overlap_trtri = 1;                        // 0: POTRF then TRTRI back to back (A/B knob)
+  // debug timeline of the factorisation lanes (knob 6): (code, event) pairs, code = lane * 1000 + outer step
+  bool trace_on = false;
+  std::vector<std::pair<int, cudaEvent_t>> trace;
+  size_t trace_used = 0;
   Range lauum, symprod;
 
   // ---- FITC state ----------------------------------------------------------------------------

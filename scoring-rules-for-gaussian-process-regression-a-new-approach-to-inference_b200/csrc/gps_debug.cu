@@ -149,8 +149,24 @@ int gps_dbg_set_variant(gps_ctx* ctx, int what, int value) {
   else if (what == 2) ctx->fitc_variant = value;
   else if (what == 3) ctx->fitc_large_min_m = value;
   else if (what == 4) ctx->overlap_trtri = value;
+  else if (what == 6) ctx->trace_on = value != 0;
   else return gps_fail(ctx, GPS_EINVAL, "dbg_set_variant: unknown knob %d", what);
   return GPS_OK;
+}
+
+int gps_dbg_trace(gps_ctx* ctx, int cap, int* codes, double* ms) {
+  if (!ctx || !codes || !ms) return GPS_EINVAL;
+  GPS_CUDA(cudaSetDevice(ctx->device));
+  GPS_CUDA(cudaStreamSynchronize(ctx->stream));
+  int n = 0;
+  for (size_t i = 0; i < ctx->trace_used && n < cap; ++i, ++n) {
+    float t = 0;
+    GPS_CUDA(cudaEventSynchronize(ctx->trace[i].second));
+    GPS_CUDA(cudaEventElapsedTime(&t, ctx->trace[0].second, ctx->trace[i].second));
+    codes[n] = ctx->trace[i].first;
+    ms[n] = t;
+  }
+  return n;
 }
 
 int gps_dbg_potf2_phases(gps_ctx* ctx, int64_t* cycles17) {

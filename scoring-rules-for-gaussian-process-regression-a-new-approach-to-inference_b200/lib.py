@@ -58,6 +58,7 @@ DEBUG_SIGNATURES = {
     "gps_dbg_fp64_peak": (C.c_int, [_vp, C.c_int, _dp, _dp]),
     "gps_dbg_set_variant": (C.c_int, [_vp, C.c_int, C.c_int]),
     "gps_dbg_potf2_phases": (C.c_int, [_vp, C.POINTER(C.c_int64)]),
+    "gps_dbg_trace": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double)]),
     "gps_dbg_gram": (C.c_int, [_vp, _dp, _vp]),
 }
 
