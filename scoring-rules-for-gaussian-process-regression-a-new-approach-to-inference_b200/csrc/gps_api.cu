@@ -159,6 +159,7 @@ void gps_ctx_release(gps_ctx* ch) {
     if (e) cudaEventDestroy(e);
   for (cudaEvent_t e : ch->stage_ev)
     if (e) cudaEventDestroy(e);
+  for (auto& pr : ch->trace) cudaEventDestroy(pr.second);
   delete ch;
 }
 
@@ -218,6 +219,7 @@ void gps_destroy(gps_ctx* ctx) {
   if (ctx->d_info) cudaFree(ctx->d_info);
   if (ctx->d_tasks) cudaFree(ctx->d_tasks);
   if (ctx->d_tasks2) cudaFree(ctx->d_tasks2);
+  for (auto& pr : ctx->trace) cudaEventDestroy(pr.second);
   for (auto& pr : ctx->gemm_events) {
     cudaEventDestroy(pr.first);
     cudaEventDestroy(pr.second);
