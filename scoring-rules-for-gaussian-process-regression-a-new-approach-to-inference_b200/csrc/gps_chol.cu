@@ -631,8 +631,10 @@ int potrf_driver(gps_ctx* ctx, double* K, double* Xinv, double* scratch, int64_t
       if (cudaGetLastError() != cudaSuccess) rc = gps_fail(ctx, GPS_ECUDA, "potf2 launch failed");
       ctx->launches++;
       // panel: L_ik = A_ik * inv(L_kk)';  inner: A_ij -= L_ik L_jk' for the remaining columns of the block column
+      ctx->gemm_strip_policy = ctx->chain_strip;
       if (rc == GPS_OK) rc = gemm_nt(Xinv, 1.0, 0.0, ctx->potrf_panel[k], 0, n_in);
       if (rc == GPS_OK) rc = gemm_nt(K, -1.0, 1.0, ctx->potrf_inner[k], 0, ctx->potrf_inner[k].cnt);
+      ctx->gemm_strip_policy = 0;
       if (rc != GPS_OK) break;
       GPS_CUDA(cudaEventRecord(ctx->tile_events[k], s_pan));
       ctx->stream = s_pan2;

@@ -40,6 +40,8 @@ struct gps_ctx {
   long long* potf2_prof = nullptr;    // device buffer for clock64 phase stamps of the diagonal kernel (debug)
   int potf2_variant = 1;              // 0: register-cyclic diagonal kernel, 1: 32-blocked DMMA diagonal kernel
   int gemm_variant = 6;               // tile-GEMM policy (see gps_gemm.cu); switched by gps_dbg_set_variant
+  int gemm_strip_policy = 0;          // 32 / 16: row-strip policy, set around the few-tile launches of POTRF's chain
+  int chain_strip = 16;               // A/B knob 7: strip height used on the chain (0 = the normal policy)
   // GEMM timing of the last full eval
   bool time_gemm = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> gemm_events;

@@ -271,6 +271,13 @@ int gps_gemm_tasks(gps_ctx* ctx, int kind, const double* A, int64_t lda, const d
   }
   int r;
 #define GPS_GEMM_ARGS ctx, kind, A, lda, B, ldb, C, ldc, alpha, beta, dvec, mirror, d_tasks, ntasks
+  // strip policies for the few-tile, k = 128 launches on POTRF's serial chain: a 128 x 128 task is split over
+  // 4 (or 8) CTAs of 32 (16) rows, so the eight dependent k-steps each carry a quarter (eighth) of the DMMA work
+  if (ctx->gemm_strip_policy == 32) {
+    r = dispatch<GemmCfg<32, 16, 3, 1, 4, false, 2>>(GPS_GEMM_ARGS);
+  } else if (ctx->gemm_strip_policy == 16) {
+    r = dispatch<GemmCfg<16, 16, 3, 1, 4, false, 2>>(GPS_GEMM_ARGS);
+  } else
   switch (ctx->gemm_variant) {            //            TM  BK  ST WM WN PIPE  MINB
     case 0: r = dispatch<GemmCfg<128, 16, 4, 2, 4, false, 1>>(GPS_GEMM_ARGS); break;
     case 2: r = dispatch<GemmCfg<128, 32, 3, 2, 4, false, 1>>(GPS_GEMM_ARGS); break;

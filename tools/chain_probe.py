@@ -11,7 +11,10 @@ from gpscore_b200 import api, synth  # noqa: E402
 ctx = api.Context(0)
 ctx._check(ctx._lib.gps_dbg_set_variant(ctx._h, 4, 0))
 theta = synth.hyper_point("P1")
-for N in (512, 1024, 2048, 4096):
+strip = int(sys.argv[1]) if len(sys.argv) > 1 else 16
+ctx._check(ctx._lib.gps_dbg_set_variant(ctx._h, 7, strip))
+print("chain strip policy", strip)
+for N in (512, 2048):
     X, y = synth.kin40k_like(N)
     ctx.set_data(torch.from_numpy(X).cuda(), torch.from_numpy(y).cuda())
     for _ in range(3):
