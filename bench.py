@@ -325,6 +325,18 @@ def run_ours(args):
                                      "symprod": float(N_FULL) ** 3 / (stages["symprod"] * 1e-3) / 1e12},
                     "peak_how": "cuBLAS DGEMM 6144^3 (torch.matmul fp64), best of 5, CUDA events, measured in "
                                 "this run — MEASURED_PEAKS.json has no fp64 figure"}
+    # the other objectives of the path on the same workload (rank 0, device-timed, 2 evaluations each)
+    objectives = None
+    if rank == 0:
+        objectives = {}
+        for sc in ("crps", "logs", "nlml", "dss"):
+            ctx.full_eval(theta, sc)
+            e0.record(stream)
+            for _ in range(2):
+                ctx.full_eval(theta, sc)
+            e1.record(stream)
+            stream.synchronize()
+            objectives["full_" + sc + "_ms"] = e0.elapsed_time(e1) / 2
     barrier()
 
     # ---- FITC M = 20 (same JSON line, secondary) ---------------------------------------------------------
@@ -340,9 +352,20 @@ def run_ours(args):
     e1.record(stream)
     barrier()
     ms_f = max_over_ranks(e0.elapsed_time(e1))
+    lf1 = ctx.launch_count()
+    if rank == 0:
+        for sc in ("crps", "logs", "nlml", "dss", "kc"):
+            ctx.fitc_eval(theta, U, sc)
+            e0.record(stream)
+            for _ in range(20):
+                ctx.fitc_eval(theta, U, sc)
+            e1.record(stream)
+            stream.synchronize()
+            objectives["fitc20_" + sc + "_ms"] = e0.elapsed_time(e1) / 20
+    barrier()
     fitc = {"workload": "KIN40K-FITC-20 N=10000 D=8 M=20 LOO-CRPS obj+grad incl. inducing inputs (K20:222-251)",
             "replicas_evals_per_s": world * steps_f / (ms_f * 1e-3), "ms_per_eval": ms_f / steps_f,
-            "launches_per_eval": (ctx.launch_count() - lf0) / steps_f,
+            "launches_per_eval": (lf1 - lf0) / steps_f,
             "algorithmic_bytes_per_eval": 3 * 8 * N_FULL * (D + 1)}
     if world > 1:
         # row-sharded evaluation of ONE problem: each rank holds N/world rows, three NCCL all-reduces
@@ -467,7 +490,7 @@ def run_ours(args):
                        "l2": "working set 3 x 818 MB fp64 matrices >> 126 MB L2, no flush needed",
                        "objective": float(val), "grad_norm": float(np.linalg.norm(grad))},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
-            "clocks": clk, "fitc": fitc,
+            "clocks": clk, "fitc": fitc, "objectives_ms_per_eval": objectives,
         }
         emit(line)
     barrier()
