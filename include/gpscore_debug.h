@@ -34,7 +34,9 @@ int gps_dbg_fp64_peak(gps_ctx* ctx, int iters, double* dmma_tflops, double* dfma
  * which gps_fitc_eval switches to the matrix form (default 33; lower it to A/B the two paths at M <= 32);
  * what = 4 selects the schedule of the full-GP factorisation: 1 = POTRF and the TRTRI merges overlapped on
  * priority streams (default), 0 = POTRF (with its look-ahead lanes) then TRTRI, 2 = every launch on the caller's
- * stream, one at a time (used to time launches alone). */
+ * stream, one at a time (used to time launches alone); what = 6 arms the lane timeline (gps_dbg_trace);
+ * what = 7 sets the row-strip height of the few-tile launches on POTRF's serial chain (16 = default, 32, 0 = the
+ * normal policy); what = 8 switches the automatic strip policies for under-filled launches off (0) or on (1). */
 int gps_dbg_set_variant(gps_ctx* ctx, int what, int value);
 
 /* Timeline of the factorisation lanes of the last full-GP evaluation (arm with gps_dbg_set_variant(ctx, 6, 1)):

@@ -42,6 +42,7 @@ struct gps_ctx {
   int gemm_variant = 6;               // tile-GEMM policy (see gps_gemm.cu); switched by gps_dbg_set_variant
   int gemm_strip_policy = 0;          // 32 / 16: row-strip policy, set around the few-tile launches of POTRF's chain
   int chain_strip = 16;               // A/B knob 7: strip height used on the chain (0 = the normal policy)
+  int gemm_auto_strip = 1;            // A/B knob 8: strip policies for every launch with too few tasks to fill the SMs
   // GEMM timing of the last full eval
   bool time_gemm = false;
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> gemm_events;

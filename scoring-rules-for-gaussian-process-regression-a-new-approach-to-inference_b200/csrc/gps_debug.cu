@@ -151,6 +151,7 @@ int gps_dbg_set_variant(gps_ctx* ctx, int what, int value) {
   else if (what == 4) ctx->overlap_trtri = value;
   else if (what == 6) ctx->trace_on = value != 0;
   else if (what == 7) ctx->chain_strip = value;
+  else if (what == 8) ctx->gemm_auto_strip = value;
   else return gps_fail(ctx, GPS_EINVAL, "dbg_set_variant: unknown knob %d", what);
   return GPS_OK;
 }

@@ -273,9 +273,18 @@ int gps_gemm_tasks(gps_ctx* ctx, int kind, const double* A, int64_t lda, const d
 #define GPS_GEMM_ARGS ctx, kind, A, lda, B, ldb, C, ldc, alpha, beta, dvec, mirror, d_tasks, ntasks
   // strip policies for the few-tile, k = 128 launches on POTRF's serial chain: a 128 x 128 task is split over
   // 4 (or 8) CTAs of 32 (16) rows, so the eight dependent k-steps each carry a quarter (eighth) of the DMMA work
-  if (ctx->gemm_strip_policy == 32) {
+  // ... and every other launch too small to fill the SMs with the shipped policy (deep TRTRI merges, the last
+  // POTRF block columns, M x M products of the FITC matrix form, mid-size grid sweeps): 8 CTAs per task up to
+  // sm_count / 8 tasks, 4 CTAs per task up to sm_count / 4.  The k-order per output element is the same in
+  // every policy, so results do not depend on the choice.
+  int strip = ctx->gemm_strip_policy;
+  if (strip == 0 && ctx->gemm_auto_strip) {
+    if (ntasks * 8 <= (size_t)ctx->sm_count) strip = 16;
+    else if (ntasks * 4 <= (size_t)ctx->sm_count) strip = 32;
+  }
+  if (strip == 32) {
     r = dispatch<GemmCfg<32, 16, 3, 1, 4, false, 2>>(GPS_GEMM_ARGS);
-  } else if (ctx->gemm_strip_policy == 16) {
+  } else if (strip == 16) {
     r = dispatch<GemmCfg<16, 16, 3, 1, 4, false, 2>>(GPS_GEMM_ARGS);
   } else
   switch (ctx->gemm_variant) {            //            TM  BK  ST WM WN PIPE  MINB
