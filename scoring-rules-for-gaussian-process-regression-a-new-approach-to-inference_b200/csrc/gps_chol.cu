@@ -160,14 +160,6 @@ __device__ __forceinline__ void dmma4(double& c0, double& c1, double a, double b
                : "d"(a), "d"(b));
 }
 __device__ __forceinline__ int blk_idx(int i, int j) { return i * (i + 1) / 2 + j; }
-// r[lane] without dynamic register indexing
-__device__ __forceinline__ double r_diag(const double (&r)[32], int lane) {
-  double v = r[0];
-#pragma unroll
-  for (int j = 1; j < 32; ++j) v = (lane == j) ? r[j] : v;
-  return v;
-}
-
 // c[nf] += sgn * A[strip mf] * B'   (A, B blocks with k contiguous)
 __device__ __forceinline__ void strip_nt(const double* __restrict__ A, const double* __restrict__ B, int mf, int lane,
                                          double sgn, double (&c)[4][2]) {
@@ -241,26 +233,44 @@ potf2_inv_dmma_kernel(double* __restrict__ K, double* __restrict__ Xinv, int64_t
     // (1) one warp: Cholesky of the 32 x 32 diagonal sub-block, rows in registers
     if (warp == 0) {
       double r[SB];
+      double* colbuf = Tb;   // 2 x 32 doubles of the scratch blocks (idle during the factorisation)
 #pragma unroll
       for (int j = 0; j < SB; ++j) r[j] = D[lane * SLD + j];
+      // The pivot chain runs on a private copy of the row's diagonal entry: dg -= l_j^2 needs only the lane's
+      // own l_j, so the next pivot is broadcast (and its rsqrt started) before column j has gone through shared
+      // memory for the bulk update — the serial path per pivot is shuffle + rsqrt + two multiplies.
+      double dg = D[lane * SLD + lane];
+      double li = 0.0;
+      int first_bad = -1;
+      double piv = __shfl_sync(0xffffffffu, dg, 0);
 #pragma unroll
       for (int j = 0; j < SB; ++j) {
-        double piv = __shfl_sync(0xffffffffu, r[j], j);
-        if (!(piv > 0.0)) {
-          if (lane == 0) atomicCAS(info, 0, blk * T + kb * SB + j + 1);
-          piv = 1.0;
-        }
-        const double lj = r[j] * rsqrt(piv);   // (an fp32-seeded Newton rsqrt measured slower: 16.2k vs 11.2k cycles per sub-block)
+        const bool bad = !(piv > 0.0);
+        first_bad = (bad && first_bad < 0) ? j : first_bad;
+        const double rinv = rsqrt(bad ? 1.0 : piv);   // (an fp32-seeded Newton rsqrt measured slower)
+        const double lj = r[j] * rinv;
+        li = (lane == j) ? rinv : li;
+        dg = fma(-lj, lj, dg);
+        if (j + 1 < SB) piv = __shfl_sync(0xffffffffu, dg, j + 1);
+        // column j of L goes through shared memory (double-buffered: one __syncwarp per pivot) and comes back as
+        // broadcast 16-byte loads: 16 LDS instead of 62 SHFL per pivot
+        double* cb = colbuf + (j & 1) * SB;
+        cb[lane] = lj;
+        __syncwarp();
 #pragma unroll
-        for (int c = j + 1; c < SB; ++c) {
-          const double lc = __shfl_sync(0xffffffffu, lj, c);
-          r[c] = fma(-lj, lc, r[c]);
+        for (int c = 0; c < SB; c += 2) {          // pairs (c, c + 1); j and c are compile-time after unrolling
+          if (c + 1 > j) {
+            const double2 l2 = *reinterpret_cast<const double2*>(cb + c);
+            if (c > j) r[c] = fma(-lj, l2.x, r[c]);
+            r[c + 1] = fma(-lj, l2.y, r[c + 1]);
+          }
         }
         r[j] = lj;
       }
+      if (first_bad >= 0 && lane == 0) atomicCAS(info, 0, blk * T + kb * SB + first_bad + 1);
 #pragma unroll
       for (int j = 0; j < SB; ++j) D[lane * SLD + j] = (j <= lane) ? r[j] : 0.0;
-      Li[kb * SB + lane] = 1.0 / r_diag(r, lane);
+      Li[kb * SB + lane] = li;
     }
     __syncthreads();
     GPS_PROF();   // 2 + 3 kb: sub-block factored
@@ -342,18 +352,18 @@ potf2_inv_dmma_kernel(double* __restrict__ K, double* __restrict__ Xinv, int64_t
   GPS_PROF();   // 15: off-diagonal blocks of the inverse
   // write back: full 128 x 128 tiles of L and L^-1 with explicit zeros above the diagonal
 #pragma unroll 8
-  for (int q = 0; q < T * T / 256; ++q) {
-    const int e = tid + q * 256;
+  for (int q = 0; q < T * T / 512; ++q) {          // 16-byte stores: two columns per thread
+    const int e = (tid + q * 256) * 2;
     const int r = e >> 7, c = e & 127;
     const int bi = r >> 5, bj = c >> 5;
-    double lv = 0.0, xv = 0.0;
+    double2 lv = make_double2(0.0, 0.0), xv = make_double2(0.0, 0.0);
     if (bj <= bi) {
       const int o = blk_idx(bi, bj) * SBLK + (r & 31) * SLD + (c & 31);
-      lv = Lb[o];
-      xv = Xb[o];
+      lv = *reinterpret_cast<const double2*>(Lb + o);
+      xv = *reinterpret_cast<const double2*>(Xb + o);
     }
-    Kd[(int64_t)r * ld + c] = lv;
-    Xd[(int64_t)r * ld + c] = xv;
+    *reinterpret_cast<double2*>(Kd + (int64_t)r * ld + c) = lv;
+    *reinterpret_cast<double2*>(Xd + (int64_t)r * ld + c) = xv;
   }
   __syncthreads();
   GPS_PROF();   // 16: written back
