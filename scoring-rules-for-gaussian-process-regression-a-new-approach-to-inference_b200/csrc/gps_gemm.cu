@@ -192,6 +192,8 @@ gemm_tile_kernel(const double* __restrict__ A, int64_t lda, const double* __rest
     }
   }
   cp_async_wait<0>();
+  static_assert(!MIRROR || (size_t)128 * (TM + 1) * sizeof(double) <= Cfg::SMEM, "transpose buffer must fit in the operand ring");
+  if (MIRROR) __syncthreads();   // the operand ring is reused as the transpose buffer below
 
   // epilogue: thread holds C[row][col..col+1] of each fragment
 #pragma unroll
@@ -211,9 +213,20 @@ gemm_tile_kernel(const double* __restrict__ A, int64_t lda, const double* __rest
       }
       *p = v;
       if (MIRROR && !diag_tile) {
-        C[(int64_t)col * ldc + row] = v.x;
-        C[(int64_t)(col + 1) * ldc + row] = v.y;
+        // stage the transposed slice in the (now idle) operand ring: Ts[col][row], leading dimension TM + 1
+        const int lr = wm * WROWS + i * 8 + g, lc = wn * WCOLS + j * 8 + 2 * tq;
+        smem[lc * (TM + 1) + lr] = v.x;
+        smem[(lc + 1) * (TM + 1) + lr] = v.y;
       }
+    }
+  }
+  if (MIRROR && !diag_tile) {
+    // mirrored tile C[c_col + n][c_row + m]: each warp writes rows of TM contiguous doubles (coalesced) instead
+    // of every thread scattering 8-byte stores with stride ldc
+    __syncthreads();
+    for (int n = warp; n < 128; n += Cfg::THREADS / 32) {
+      double* dst = C + (int64_t)(t.c_col + n) * ldc + t.c_row;
+      for (int m = lane; m < TM; m += 32) dst[m] = smem[n * (TM + 1) + m];
     }
   }
 }
