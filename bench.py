@@ -300,10 +300,10 @@ def run_ours(args):
     if rank == 0:
         traffic, traffic_how = None, None
         try:   # DRAM bytes of the tile-GEMM launches of one evaluation, from the committed ncu launch list
-            with open(os.path.join(ROOT, "profiles", "r01_launch_summary_N10000_v8.json")) as fh:
+            with open(os.path.join(ROOT, "profiles", "r01_launch_summary_N10000_v13.json")) as fh:
                 traffic = float(json.load(fh)["gemm_dram_bytes_per_eval"])
                 traffic_how = ("dram__bytes_read.sum + dram__bytes_write.sum summed over the tile-GEMM launches of one "
-                               "evaluation, ncu launch list profiles/r01_launches_N10000_v8.csv (bytes per step, like "
+                               "evaluation, ncu launch list profiles/r01_launches_N10000_v13.csv (bytes per step, like "
                                "achieved); the kernel is tensor-bound: DRAM runs at ~6% of peak")
         except Exception:
             pass
