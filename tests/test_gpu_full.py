@@ -229,3 +229,47 @@ def test_factorisation_schedules_are_bit_identical(ctx):
                     assert v == key[0] and np.array_equal(g, key[1]), (mode, score, rep)
     finally:
         ctx._check(ctx._lib.gps_dbg_set_variant(ctx._h, 4, 1))
+
+
+def test_gemm_policies_do_not_change_results(ctx):
+    """The row-strip policies (chain launches, knob 7; automatic for under-filled launches, knob 8) split a tile
+    over more CTAs but keep the k-order per output element: objective and gradient are bit-identical."""
+    from gpscore_b200 import synth
+    X, y = synth.kin40k_like(1700, seed=13)
+    theta = synth.hyper_point("P1")
+    ctx.set_data(_dev(X), _dev(y))
+    try:
+        ref = None
+        for chain, auto in ((16, 1), (32, 1), (0, 1), (16, 0), (0, 0)):
+            ctx._check(ctx._lib.gps_dbg_set_variant(ctx._h, 7, chain))
+            ctx._check(ctx._lib.gps_dbg_set_variant(ctx._h, 8, auto))
+            v, g = ctx.full_eval(theta, "crps")
+            ref = ref or (v, g)
+            assert v == ref[0] and np.array_equal(g, ref[1]), (chain, auto)
+    finally:
+        ctx._check(ctx._lib.gps_dbg_set_variant(ctx._h, 7, 16))
+        ctx._check(ctx._lib.gps_dbg_set_variant(ctx._h, 8, 1))
+
+
+def test_lane_trace_reports_every_outer_step(ctx):
+    """gps_dbg_trace: one entry per lane and outer step, times non-decreasing within a lane."""
+    import ctypes as C
+    from gpscore_b200 import synth
+    X, y = synth.kin40k_like(2000, seed=14)          # 16 tiles = 4 outer steps
+    ctx.set_data(_dev(X), _dev(y))
+    try:
+        ctx._check(ctx._lib.gps_dbg_set_variant(ctx._h, 6, 1))
+        ctx.full_eval(synth.hyper_point("P1"), "crps")
+        codes, ms = (C.c_int * 64)(), (C.c_double * 64)()
+        n = ctx._lib.gps_dbg_trace(ctx._h, 64, codes, ms)
+        assert n > 0
+        lanes = {}
+        for i in range(n):
+            lanes.setdefault(codes[i] // 1000, []).append((codes[i] % 1000, ms[i]))
+        for lane in (1, 2, 3, 4):
+            steps = [s for s, _ in lanes[lane]]
+            assert steps == [0, 1, 2, 3], (lane, steps)
+            times = [t for _, t in lanes[lane]]
+            assert all(b >= a for a, b in zip(times, times[1:]))
+    finally:
+        ctx._check(ctx._lib.gps_dbg_set_variant(ctx._h, 6, 0))
