@@ -599,6 +599,25 @@ int trace_mark(gps_ctx* ctx, int code, cudaStream_t s) {
   return GPS_OK;
 }
 
+// Launch a list of EQUAL-length tasks so that a partial last wave does not cost a whole wave time: the tiles
+// beyond the last full wave of sm_count tasks go into a second launch with the 32-row strip policy (four CTAs of
+// half the duration per tile), which slot in as the last full wave drains.
+int gemm_equal_tasks(gps_ctx* ctx, const double* A, const double* B, double* C, int64_t Np, double alpha, double beta,
+                     const GemmTask* tasks, size_t cnt) {
+  const size_t wave = (size_t)ctx->sm_count;
+  size_t rest = cnt % wave;
+  if (cnt < 4 * wave || rest * 3 > wave * 2) rest = 0;   // small launches / a well-filled last wave: one launch
+  GPS_CHECK(gps_gemm_tasks(ctx, GEMM_KC_KC, A, Np, B, Np, C, Np, alpha, beta, nullptr, false, tasks, cnt - rest));
+  if (rest) {
+    const int saved = ctx->gemm_strip_policy;
+    ctx->gemm_strip_policy = 32;
+    const int r = gps_gemm_tasks(ctx, GEMM_KC_KC, A, Np, B, Np, C, Np, alpha, beta, nullptr, false, tasks + (cnt - rest), rest);
+    ctx->gemm_strip_policy = saved;
+    GPS_CHECK(r);
+  }
+  return GPS_OK;
+}
+
 int potrf_driver(gps_ctx* ctx, double* K, double* Xinv, double* scratch, int64_t Np, bool with_trtri) {
   const int nb = (int)(Np / T);
   const int OB = GPS_POTRF_OB;
@@ -664,7 +683,7 @@ int potrf_driver(gps_ctx* ctx, double* K, double* Xinv, double* scratch, int64_t
     rc = gemm_nt(K, -1.0, 1.0, ctx->potrf_trailA[o], 0, ctx->potrf_trailA[o].cnt);
     if (rc != GPS_OK) break;
     GPS_CUDA(cudaEventRecord(ctx->potrf_events[2 * o + 2], s_trail));
-    rc = gemm_nt(K, -1.0, 1.0, ctx->potrf_trailB[o], 0, ctx->potrf_trailB[o].cnt);
+    rc = gemm_nt(K, -1.0, 1.0, ctx->potrf_trailB[o], 0, ctx->potrf_trailB[o].cnt);   // (gemm_equal_tasks here: no gain, the other lanes fill the tail)
     if (rc == GPS_OK) rc = trace_mark(ctx, 3000 + o, s_trail);
     if (rc != GPS_OK || !with_trtri) continue;
     // inversion merges whose operands are final after this step
@@ -764,6 +783,6 @@ int gps_symprod(gps_ctx* ctx, const double* Kinv, const double* dvec, double* sc
   scale_cols_kernel<<<(unsigned)((pairs + 255) / 256), 256, 0, ctx->stream>>>(Kinv, dvec, scratch, Np);
   GPS_LAUNCH_CHECK();
   ctx->launches++;
-  return gps_gemm_tasks(ctx, GEMM_KC_KC, scratch, Np, Kinv, Np, S, Np, 1.0, 0.0, nullptr, false,
-                        ctx->d_tasks + ctx->symprod.off, ctx->symprod.cnt);
+  // equal-length tasks (full k): 3160 tiles = 21.35 lock-step waves at N = 10^4 — see gemm_equal_tasks
+  return gemm_equal_tasks(ctx, scratch, Kinv, S, Np, 1.0, 0.0, ctx->d_tasks + ctx->symprod.off, ctx->symprod.cnt);
 }
