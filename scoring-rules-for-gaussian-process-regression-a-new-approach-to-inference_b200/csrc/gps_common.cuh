@@ -72,6 +72,8 @@ struct gps_ctx {
   DevBuf fold_vecs;
   gps_ctx* fold_ctx = nullptr;   // child context for the N/4-sized fold factorisations (DSS)
   std::vector<gps_ctx*> grid_lanes;   // lane contexts of the large-n grid sweep (own streams and workspaces)
+  std::vector<gps_ctx*> fold_lanes;   // one lane context per DSS fold
+  cudaEvent_t dss_fork = nullptr, dss_join[4] = {};
   DevBuf red;      // reduction scratch
   DevBuf params;   // device copy of theta-derived parameters
   int* d_info = nullptr;       // device: first failing pivot (0 = ok)

@@ -55,6 +55,15 @@ fold_value_kernel(const double* __restrict__ logdiag, const double* __restrict__
   if (threadIdx.x == 0) obj[0] = (first ? 0.0 : obj[0]) + s;
 }
 
+// obj = sum over folds of their values, in fold order (one thread: fixed order)
+__global__ void fold_sum_kernel(const double* __restrict__ fv, int64_t stride, int64_t at, int folds, double* __restrict__ obj) {
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int f = 0; f < folds; ++f) s += fv[f * stride + at];
+    obj[0] = s;
+  }
+}
+
 }  // namespace
 
 int gps_full_dss(gps_ctx* ctx, double* par_obj, double* par_gsum, bool want_grad) {
@@ -64,59 +73,81 @@ int gps_full_dss(gps_ctx* ctx, double* par_obj, double* par_gsum, bool want_grad
   if (N % FOLDS) return gps_fail(ctx, GPS_EINVAL, "dss: the reference's 4-fold code needs N %% 4 == 0 (KF:521-530), N=%lld", (long long)N);
   const int64_t nf = N / FOLDS, Fp = gps_pad(nf);
   double* v = ctx->vecs.p;
-  // child context: the N/4-sized factorisations reuse the blocked drivers with their own task lists
-  if (!ctx->fold_ctx) {
-    ctx->fold_ctx = new gps_ctx();
-    ctx->fold_ctx->device = ctx->device;
-    ctx->fold_ctx->sm_count = ctx->sm_count;
-    ctx->fold_ctx->gemm_variant = ctx->gemm_variant;
-    ctx->fold_ctx->potf2_variant = ctx->potf2_variant;
+  // Four child contexts, one per fold, each with its own stream and workspaces: the N/4-sized factorisations
+  // reuse the blocked drivers (own task lists) and, being bound by their serial diagonal-block chains, run
+  // side by side instead of one after the other.
+  while ((int)ctx->fold_lanes.size() < FOLDS) {
+    gps_ctx* ln = new gps_ctx();
+    ln->device = ctx->device;
+    ln->sm_count = ctx->sm_count;
+    if (cudaStreamCreateWithFlags(&ln->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+      delete ln;
+      return gps_fail(ctx, GPS_ECUDA, "dss: cannot create a fold stream");
+    }
+    ln->stream = ln->own_stream;
+    ctx->fold_lanes.push_back(ln);
   }
-  gps_ctx* ch = ctx->fold_ctx;
-  ch->stream = ctx->stream;
-  ch->own_stream = nullptr;
-  ch->time_gemm = false;
-  {
-    const int r = gps_ensure_ws(ch, Fp);
-    if (r != GPS_OK) return gps_fail(ctx, r, "dss: %s", ch->err.c_str());
+  if (!ctx->dss_fork) {
+    GPS_CUDA(cudaEventCreateWithFlags(&ctx->dss_fork, cudaEventDisableTiming));
+    for (auto& e : ctx->dss_join) GPS_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
   }
   GPS_CHECK(gps_ensure(ctx, ctx->Gb, (size_t)Np * Np));
-  GPS_CHECK(gps_ensure(ctx, ctx->fold_vecs, (size_t)3 * Fp));
-  double* af = ctx->fold_vecs.p;           // alpha_f padded
-  double* abf = af + Fp;                   // abar_f
-  double* ldf = abf + Fp;                  // log diag(L_f)
+  GPS_CHECK(gps_ensure(ctx, ctx->fold_vecs, (size_t)FOLDS * (3 * Fp + 8)));
   GPS_CUDA(cudaMemsetAsync(ctx->Gb.p, 0, (size_t)Np * Np * sizeof(double), ctx->stream));
   GPS_CUDA(cudaMemsetAsync(v + V_ABAR * Np, 0, Np * sizeof(double), ctx->stream));
-  for (int f = 0; f < FOLDS; ++f) {
+  GPS_CUDA(cudaEventRecord(ctx->dss_fork, ctx->stream));
+  int rc = GPS_OK;
+  for (int f = 0; f < FOLDS && rc == GPS_OK; ++f) {
+    gps_ctx* ch = ctx->fold_lanes[f];
+    ch->gemm_variant = ctx->gemm_variant;
+    ch->potf2_variant = ctx->potf2_variant;
+    ch->overlap_trtri = ctx->overlap_trtri;
+    ch->time_gemm = false;
+    rc = gps_ensure_ws(ch, Fp);
+    if (rc != GPS_OK) return gps_fail(ctx, rc, "dss fold %d: %s", f, ch->err.c_str());
+    cudaStream_t fs = ch->stream;
+    GPS_CUDA(cudaStreamWaitEvent(fs, ctx->dss_fork, 0));
+    double* af = ctx->fold_vecs.p + (size_t)f * (3 * Fp + 8);   // alpha_f padded
+    double* abf = af + Fp;                                        // abar_f
+    double* ldf = abf + Fp;                                       // log diag(L_f)
+    double* objf = ldf + Fp;                                      // this fold's value
     const int64_t off = f * nf;
-    fold_copy_kernel<<<(unsigned)((Fp * Fp + 255) / 256), 256, 0, ctx->stream>>>(ctx->Kb.p, Np, off, nf, Fp, ch->Kb.p);
+    fold_copy_kernel<<<(unsigned)((Fp * Fp + 255) / 256), 256, 0, fs>>>(ctx->Kb.p, Np, off, nf, Fp, ch->Kb.p);
     GPS_LAUNCH_CHECK();
-    fold_vec_kernel<<<(unsigned)((Fp + 255) / 256), 256, 0, ctx->stream>>>(v + V_ALPHA * Np, off, nf, Fp, af);
+    fold_vec_kernel<<<(unsigned)((Fp + 255) / 256), 256, 0, fs>>>(v + V_ALPHA * Np, off, nf, Fp, af);
     GPS_LAUNCH_CHECK();
     ctx->launches += 2;
-    int r = gps_potrf(ch, ch->Kb.p, ch->Xb.p, Fp);
-    if (r == GPS_OK) r = gps_diag_extract(ch, ch->Kb.p, Fp, ldf, 1);
-    if (r == GPS_OK) r = gps_trtri(ch, ch->Kb.p, ch->Xb.p, ch->Sb.p, Fp);
-    if (r == GPS_OK) r = gps_lauum(ch, ch->Xb.p, ch->Kb.p, Fp);          // C_f = B_ff^-1
-    if (r == GPS_OK) r = gps_symv(ch, ch->Kb.p, Fp, af, abf);              // abar_f = C_f a_f
-    if (r != GPS_OK) return gps_fail(ctx, r, "dss fold %d: %s", f, ch->err.c_str());
-    fold_value_kernel<<<1, 1024, 0, ctx->stream>>>(ldf, af, abf, nf, par_obj, f == 0);
+    rc = gps_potrf(ch, ch->Kb.p, ch->Xb.p, Fp);
+    if (rc == GPS_OK) rc = gps_diag_extract(ch, ch->Kb.p, Fp, ldf, 1);
+    if (rc == GPS_OK) rc = gps_trtri(ch, ch->Kb.p, ch->Xb.p, ch->Sb.p, Fp);
+    if (rc == GPS_OK) rc = gps_lauum(ch, ch->Xb.p, ch->Kb.p, Fp);          // C_f = B_ff^-1
+    if (rc == GPS_OK) rc = gps_symv(ch, ch->Kb.p, Fp, af, abf);              // abar_f = C_f a_f
+    if (rc != GPS_OK) return gps_fail(ctx, rc, "dss fold %d: %s", f, ch->err.c_str());
+    fold_value_kernel<<<1, 1024, 0, fs>>>(ldf, af, abf, nf, objf, 1);
     GPS_LAUNCH_CHECK();
     ctx->launches++;
     if (want_grad) {
-      fold_gamma_kernel<<<(unsigned)((nf * nf + 255) / 256), 256, 0, ctx->stream>>>(ch->Kb.p, abf, Fp, nf, off, Np, ctx->Gb.p,
-                                                                                   v + V_ABAR * Np);
+      fold_gamma_kernel<<<(unsigned)((nf * nf + 255) / 256), 256, 0, fs>>>(ch->Kb.p, abf, Fp, nf, off, Np, ctx->Gb.p,
+                                                                          v + V_ABAR * Np);
       GPS_LAUNCH_CHECK();
       ctx->launches++;
     }
-    // a failed fold factorisation is reported like a failed K factorisation
+    GPS_CUDA(cudaEventRecord(ctx->dss_join[f], fs));
+  }
+  for (int f = 0; f < FOLDS; ++f) GPS_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->dss_join[f], 0));
+  // value = sum of the fold values in fold order; a failed fold factorisation is reported like a failed K
+  fold_sum_kernel<<<1, 32, 0, ctx->stream>>>(ctx->fold_vecs.p, 3 * Fp + 8, 3 * Fp, FOLDS, par_obj);
+  GPS_LAUNCH_CHECK();
+  ctx->launches++;
+  for (int f = 0; f < FOLDS; ++f) {
+    gps_ctx* ch = ctx->fold_lanes[f];
     int info = 0;
-    GPS_CUDA(cudaMemcpyAsync(&info, ch->d_info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-    GPS_CUDA(cudaStreamSynchronize(ctx->stream));
+    GPS_CUDA(cudaMemcpyAsync(&info, ch->d_info, sizeof(int), cudaMemcpyDeviceToHost, ch->stream));
+    GPS_CUDA(cudaStreamSynchronize(ch->stream));
+    ctx->launches += ch->launches;
+    ch->launches = 0;
     if (info != 0) return gps_fail(ctx, GPS_ENOTPD, "dss: fold %d block of K^-1 not positive definite at pivot %d", f, info);
   }
-  ctx->launches += ch->launches;
-  ch->launches = 0;
   if (!want_grad) return GPS_OK;
   // u = B abar
   GPS_CHECK(gps_symv(ctx, ctx->Kb.p, Np, v + V_ABAR * Np, v + V_U * Np));
