@@ -224,7 +224,6 @@ void gps_destroy(gps_ctx* ctx) {
     cudaEventDestroy(pr.first);
     cudaEventDestroy(pr.second);
   }
-  if (ctx->fold_ctx) gps_ctx_release(ctx->fold_ctx);
   for (cudaEvent_t e : {ctx->dss_fork, ctx->dss_join[0], ctx->dss_join[1], ctx->dss_join[2], ctx->dss_join[3]})
     if (e) cudaEventDestroy(e);
   for (gps_ctx* ln : ctx->fold_lanes) ctx->grid_lanes.push_back(ln);   // released with the grid lanes below

@@ -70,7 +70,6 @@ struct gps_ctx {
   DevBuf vecs;     // alpha, d, abar, dbar, u, loo_mean, loo_var, logdiag : 8 x Np
   DevBuf Gb;       // block-diagonal Gamma of the 4-fold DSS gradient (allocated on first use)
   DevBuf fold_vecs;
-  gps_ctx* fold_ctx = nullptr;   // child context for the N/4-sized fold factorisations (DSS)
   std::vector<gps_ctx*> grid_lanes;   // lane contexts of the large-n grid sweep (own streams and workspaces)
   std::vector<gps_ctx*> fold_lanes;   // one lane context per DSS fold
   cudaEvent_t dss_fork = nullptr, dss_join[4] = {};
