@@ -666,10 +666,12 @@ int potrf_driver(gps_ctx* ctx, double* K, double* Xinv, double* scratch, int64_t
       ctx->gemm_strip_policy = 0;
       if (rc != GPS_OK) break;
       GPS_CUDA(cudaEventRecord(ctx->tile_events[k], s_pan));
+      GPS_CHECK(trace_mark(ctx, 5000 + k, s_pan));
       ctx->stream = s_pan2;
       GPS_CUDA(cudaStreamWaitEvent(s_pan2, ctx->tile_events[k], 0));
       rc = gemm_nt(Xinv, 1.0, 0.0, ctx->potrf_panel[k], n_in, ctx->potrf_panel[k].cnt - n_in);
       if (rc == GPS_OK) rc = gemm_nt(K, -1.0, 1.0, ctx->potrf_innerB[k], 0, ctx->potrf_innerB[k].cnt);
+      if (rc == GPS_OK) rc = trace_mark(ctx, 6000 + k, s_pan2);
     }
     if (rc != GPS_OK) break;
     GPS_CUDA(cudaEventRecord(ctx->potrf_events[2 * o + 1], s_pan));
@@ -683,6 +685,7 @@ int potrf_driver(gps_ctx* ctx, double* K, double* Xinv, double* scratch, int64_t
     rc = gemm_nt(K, -1.0, 1.0, ctx->potrf_trailA[o], 0, ctx->potrf_trailA[o].cnt);
     if (rc != GPS_OK) break;
     GPS_CUDA(cudaEventRecord(ctx->potrf_events[2 * o + 2], s_trail));
+    GPS_CHECK(trace_mark(ctx, 7000 + o, s_trail));
     rc = gemm_nt(K, -1.0, 1.0, ctx->potrf_trailB[o], 0, ctx->potrf_trailB[o].cnt);   // (gemm_equal_tasks here: no gain, the other lanes fill the tail)
     if (rc == GPS_OK) rc = trace_mark(ctx, 3000 + o, s_trail);
     if (rc != GPS_OK || !with_trtri) continue;
