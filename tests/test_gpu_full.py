@@ -260,8 +260,8 @@ def test_lane_trace_reports_every_outer_step(ctx):
     try:
         ctx._check(ctx._lib.gps_dbg_set_variant(ctx._h, 6, 1))
         ctx.full_eval(synth.hyper_point("P1"), "crps")
-        codes, ms = (C.c_int * 64)(), (C.c_double * 64)()
-        n = ctx._lib.gps_dbg_trace(ctx._h, 64, codes, ms)
+        codes, ms = (C.c_int * 256)(), (C.c_double * 256)()
+        n = ctx._lib.gps_dbg_trace(ctx._h, 256, codes, ms)
         assert n > 0
         lanes = {}
         for i in range(n):
