@@ -151,7 +151,7 @@ void gps_ctx_release(gps_ctx* ch) {
     if (b->p) cudaFree(b->p);
   if (ch->d_info) cudaFree(ch->d_info);
   if (ch->d_tasks) cudaFree(ch->d_tasks);
-  for (auto* v : {&ch->potrf_events, &ch->tile_events, &ch->below_events})
+  for (auto* v : {&ch->potrf_events, &ch->tile_events, &ch->below_events, &ch->trailA1_events})
     for (auto e : *v) cudaEventDestroy(e);
   for (cudaStream_t s : {ch->panel_stream, ch->panel2_stream, ch->trail_stream, ch->tri_stream})
     if (s) cudaStreamDestroy(s);
@@ -235,7 +235,7 @@ void gps_destroy(gps_ctx* ctx) {
     if (s) cudaStreamDestroy(s);
   }
   gps_fitc_large_free(ctx);
-  for (auto* v : {&ctx->potrf_events, &ctx->tile_events, &ctx->below_events})
+  for (auto* v : {&ctx->potrf_events, &ctx->tile_events, &ctx->below_events, &ctx->trailA1_events})
     for (auto e : *v) cudaEventDestroy(e);
   if (ctx->panel2_stream) cudaStreamDestroy(ctx->panel2_stream);
   for (auto e : ctx->stage_ev) if (e) cudaEventDestroy(e);

@@ -404,6 +404,7 @@ int gps_build_tasks(gps_ctx* ctx, int64_t Np) {
   ctx->potrf_inner.assign(nb, {});
   ctx->potrf_innerB.assign(nb, {});
   ctx->potrf_trailA.assign(no, {});
+  ctx->potrf_trailA1.assign(no, {});
   ctx->potrf_trailB.assign(no, {});
   for (int o = 0; o < no; ++o) {
     const int c0 = o * OB, c1 = std::min(nb, c0 + OB);
@@ -422,10 +423,16 @@ int gps_build_tasks(gps_ctx* ctx, int64_t Np) {
       ctx->potrf_innerB[k].cnt = h.size() - ctx->potrf_innerB[k].off;
     }
     const int n1 = std::min(nb, c1 + OB);
+    // part A of the trailing update = the next block column, its diagonal 512 x 512 block (what the next chain
+    // waits for: <= 10 tiles) ahead of the rows below it (what the next below-lane waits for)
     ctx->potrf_trailA[o].off = h.size();
     for (int j = c1; j < n1; ++j)
-      for (int i = j; i < nb; ++i) push(i * T, j * T, c0 * T, c1 * T, i, j);
+      for (int i = j; i < n1; ++i) push(i * T, j * T, c0 * T, c1 * T, i, j);
     ctx->potrf_trailA[o].cnt = h.size() - ctx->potrf_trailA[o].off;
+    ctx->potrf_trailA1[o].off = h.size();
+    for (int j = c1; j < n1; ++j)
+      for (int i = n1; i < nb; ++i) push(i * T, j * T, c0 * T, c1 * T, i, j);
+    ctx->potrf_trailA1[o].cnt = h.size() - ctx->potrf_trailA1[o].off;
     ctx->potrf_trailB[o].off = h.size();
     for (int j = n1; j < nb; ++j)
       for (int i = j; i < nb; ++i) push(i * T, j * T, c0 * T, c1 * T, i, j);
@@ -572,6 +579,7 @@ int ensure_potrf_streams(gps_ctx* ctx, int nb, int no) {
   GPS_CHECK(grow(ctx->potrf_events, (size_t)2 * no + 2));
   GPS_CHECK(grow(ctx->tile_events, (size_t)nb));
   GPS_CHECK(grow(ctx->below_events, (size_t)no));
+  GPS_CHECK(grow(ctx->trailA1_events, (size_t)no));
   return GPS_OK;
 }
 
@@ -649,7 +657,7 @@ int potrf_driver(gps_ctx* ctx, double* K, double* Xinv, double* scratch, int64_t
   for (int o = 0; o < no && rc == GPS_OK; ++o) {
     const int c0 = o * OB, c1 = std::min(nb, c0 + OB);
     GPS_CUDA(cudaStreamWaitEvent(s_pan, ctx->potrf_events[2 * o], 0));
-    GPS_CUDA(cudaStreamWaitEvent(s_pan2, ctx->potrf_events[2 * o], 0));
+    GPS_CUDA(cudaStreamWaitEvent(s_pan2, o ? ctx->trailA1_events[o - 1] : ctx->potrf_events[0], 0));
     for (int k = c0; k < c1 && rc == GPS_OK; ++k) {
       const size_t n_in = (size_t)(c1 - k - 1);   // panel tiles inside the diagonal block come first in the list
       ctx->stream = s_pan;
@@ -686,6 +694,9 @@ int potrf_driver(gps_ctx* ctx, double* K, double* Xinv, double* scratch, int64_t
     if (rc != GPS_OK) break;
     GPS_CUDA(cudaEventRecord(ctx->potrf_events[2 * o + 2], s_trail));
     GPS_CHECK(trace_mark(ctx, 7000 + o, s_trail));
+    rc = gemm_nt(K, -1.0, 1.0, ctx->potrf_trailA1[o], 0, ctx->potrf_trailA1[o].cnt);
+    if (rc != GPS_OK) break;
+    GPS_CUDA(cudaEventRecord(ctx->trailA1_events[o], s_trail));
     rc = gemm_nt(K, -1.0, 1.0, ctx->potrf_trailB[o], 0, ctx->potrf_trailB[o].cnt);   // (gemm_equal_tasks here: no gain, the other lanes fill the tail)
     if (rc == GPS_OK) rc = trace_mark(ctx, 3000 + o, s_trail);
     if (rc != GPS_OK || !with_trtri) continue;

@@ -85,9 +85,9 @@ struct gps_ctx {
   bool loo_valid = false;
   // cached task-list layout for ws_Np (offsets into d_tasks)
   struct Range { size_t off = 0, cnt = 0; };
-  std::vector<Range> potrf_panel, potrf_inner, potrf_innerB, potrf_trailA, potrf_trailB;
+  std::vector<Range> potrf_panel, potrf_inner, potrf_innerB, potrf_trailA, potrf_trailA1, potrf_trailB;
   cudaStream_t panel_stream = nullptr;          // high-priority stream for the POTRF look-ahead
-  std::vector<cudaEvent_t> potrf_events, tile_events, below_events;
+  std::vector<cudaEvent_t> potrf_events, tile_events, below_events, trailA1_events;
   cudaStream_t panel2_stream = nullptr;         // POTRF panel work below the diagonal block (high priority)
   std::vector<Range> trtri_p, trtri_x;
   // TRTRI re-ordered for the overlapped driver: launches in issue order, each tagged with the POTRF
