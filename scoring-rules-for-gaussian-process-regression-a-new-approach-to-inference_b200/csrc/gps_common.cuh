@@ -10,7 +10,7 @@
 #include "../../include/gpscore.h"
 
 #define GPS_TILE 128  // matrix tile edge: every N x N buffer is padded to a multiple of it
-#define GPS_POTRF_OB 4  // POTRF outer block column = 4 tiles (k = 512 trailing updates)
+#define GPS_POTRF_OB 8  // POTRF outer block column = 8 tiles (k = 1024 trailing updates; 4, 12 and 16 measured slower)
 
 struct GemmTask {  // one 128 x 128 output tile of a tile-GEMM launch
   int32_t a_row;   // first row (KC operand) / first column (MC operand) of the A panel

@@ -255,21 +255,24 @@ def test_lane_trace_reports_every_outer_step(ctx):
     """gps_dbg_trace: one entry per lane and outer step, times non-decreasing within a lane."""
     import ctypes as C
     from gpscore_b200 import synth
-    X, y = synth.kin40k_like(2000, seed=14)          # 16 tiles = 4 outer steps
+    X, y = synth.kin40k_like(5000, seed=14)          # 40 tiles: at least three outer steps for any block width <= 13
     ctx.set_data(_dev(X), _dev(y))
     try:
         ctx._check(ctx._lib.gps_dbg_set_variant(ctx._h, 6, 1))
         ctx.full_eval(synth.hyper_point("P1"), "crps")
-        codes, ms = (C.c_int * 256)(), (C.c_double * 256)()
-        n = ctx._lib.gps_dbg_trace(ctx._h, 256, codes, ms)
-        assert n > 0
+        codes, ms = (C.c_int * 512)(), (C.c_double * 512)()
+        n = ctx._lib.gps_dbg_trace(ctx._h, 512, codes, ms)
+        assert 0 < n < 512
         lanes = {}
         for i in range(n):
             lanes.setdefault(codes[i] // 1000, []).append((codes[i] % 1000, ms[i]))
+        steps = [s for s, _ in lanes[1]]
+        assert len(steps) >= 3 and steps == list(range(len(steps)))
+        for lane in (2, 3, 4):
+            assert [s for s, _ in lanes[lane]] == steps, lane
         for lane in (1, 2, 3, 4):
-            steps = [s for s, _ in lanes[lane]]
-            assert steps == [0, 1, 2, 3], (lane, steps)
             times = [t for _, t in lanes[lane]]
             assert all(b >= a for a, b in zip(times, times[1:]))
+        assert [k for k, _ in lanes[5]] == list(range(40))      # one mark per 128-wide step of the chain
     finally:
         ctx._check(ctx._lib.gps_dbg_set_variant(ctx._h, 6, 0))
