@@ -2,22 +2,34 @@
 """bench.py — scoring-rule objective+gradient evaluations per second (BASELINE.json's metric).
 
     python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
-    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on host cores
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path on host cores
 
 Headline workload (`config.workload`): kin40k-FULL — KIN40K-shaped synthetic data, N = 10 000 rows,
 D = 8, full-GP LOO-CRPS objective + gradient wrt the D + 2 hyper-parameters (KF:239-252).  One
 "step" is one such evaluation.  The full GP stays on one GPU (north_star), so for N > 1 every rank
 runs its own replica at its own hyper-parameter restart ("replicas only", weak scaling, no
-collective on the data path).  The same JSON line also carries the FITC M = 20 numbers
-(`fitc`: single-GPU evals/s and, for N > 1, the row-sharded evaluation with three NCCL all-reduces).
+collective on the data path).  The same JSON line carries the other half of the metric and the
+partitioned paths:
 
-value    device-timed (CUDA events on the launching stream), inputs resident in HBM
-e2e      same metric through the C-ABI with HOST buffers: every step copies X, y and theta from
-         pinned host memory and reads objective + gradient back (gps_set_data + gps_full_eval)
-roofline dominant kernel = the DMMA tile GEMM; algorithmic flops of one evaluation (2 N^3) over
-         the summed CUDA-event durations of its launches; peak = cuBLAS DGEMM measured in this run
-         (MEASURED_PEAKS.json holds no fp64 number)
-cpu_baseline  the oracle port (numpy/scipy, all host threads) on a bounded sample of the workload
+fitc      FITC M = 20 at N = 10 000 (single-GPU evaluation, device-resident descent loop, launch floor)
+          and, for N > 1, the row-sharded evaluation with the all-reduces inside the library (NCCL);
+          the N = 1e6 sweep points (M = 20 / 256 / 1024)
+sharded   test-point prediction + scoring split by rows (N = 10 000 train, T = 30 000 test) and the
+          64 x 64 hyper-parameter grid (n = 20 and n = 2048) dealt round-robin over the ranks
+parity    every number above is checked IN THIS RUN against the CPU oracle (objective 1e-8, gradient
+          1e-6 relative — BASELINE.json's tolerances) and, under torchrun, the sharded results
+          against the single-GPU ones (1e-10); a failed gate makes the run exit non-zero
+
+value     device-timed (CUDA events on the launching stream), inputs resident in HBM
+e2e       same metric through the C-ABI with HOST buffers: every step copies X, y and theta from
+          pinned host memory and reads objective + gradient back (gps_set_data + gps_full_eval)
+roofline  dominant kernel = the DMMA tile GEMM; algorithmic flops of one evaluation (2 N^3) over
+          the summed CUDA-event durations of its launches; peak = cuBLAS DGEMM measured in this run
+          (MEASURED_PEAKS.json holds no fp64 number)
+cpu_baseline  rank 0, one GPU only: the oracle port (numpy/scipy closed form) AND the reference as
+          written (torch autograd, oracle/ref_as_written.py), both timed unscaled at N = 10 000
+library_baseline  cuSOLVER/cuBLAS through torch (cholesky + cholesky_inverse + two matmuls) at
+          N = 10 000 on the same GPU — informational, not on the product path
 """
 import argparse
 import json
@@ -34,9 +46,13 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 N_FULL = 10000
+T_TEST = 30000
 D = 8
 M_FITC = 20
+N_BIG = 1000000
 METRIC = "scoring-rule obj+grad evals/sec (KIN40K full N=10k LOO-CRPS; FITC M=20 alongside)"
+WORKLOAD = "kin40k-FULL N=10000 D=8 full-GP LOO-CRPS obj+grad (KF:239-252)"
+OBJ_TOL, GRAD_TOL, SHARD_TOL = 1e-8, 1e-6, 1e-10
 
 
 def env_int(name, default):
@@ -44,6 +60,11 @@ def env_int(name, default):
         return int(os.environ.get(name, default))
     except ValueError:
         return default
+
+
+def relmax(a, b):
+    a, b = np.asarray(a, dtype=np.float64).ravel(), np.asarray(b, dtype=np.float64).ravel()
+    return float(np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300))
 
 
 # --------------------------------------------------------------------------------------------------
@@ -97,30 +118,8 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------------
-# reference arm / cpu baseline: the oracle port on host cores
+# CPU legs (rank 0): the oracle port and the reference as written, both at the STATED workload
 # --------------------------------------------------------------------------------------------------
-def cpu_eval_seconds(n, reps=1):
-    from gpscore_b200 import synth
-    from oracle import gp_oracle as O
-    X, y = synth.kin40k_like(n)
-    theta = synth.hyper_point("P1")
-    best = 1e30
-    for _ in range(reps):
-        t0 = time.perf_counter()
-        O.full_obj_grad(X, y, theta, O.SCORE_CRPS)
-        best = min(best, time.perf_counter() - t0)
-    return best
-
-
-def pick_sample_rows(budget_s, evals):
-    """Largest sample size whose predicted run time fits the budget (cubic scaling from N = 1500)."""
-    t = cpu_eval_seconds(1500)
-    for n in (10000, 8000, 6000, 5000, 4000, 3000, 2000):
-        if t * (n / 1500.0) ** 3 * evals <= budget_s:
-            return n
-    return 1500
-
-
 def cpu_threads():
     try:
         import torch
@@ -129,31 +128,74 @@ def cpu_threads():
         return os.cpu_count() or 1
 
 
+def workload_inputs(seed=2):
+    from gpscore_b200 import synth
+    X, y = synth.kin40k_like(N_FULL)
+    return X, y, synth.hyper_point("P1", seed=seed)
+
+
+def port_eval(X, y, theta):
+    """One full-GP LOO-CRPS obj+grad with the numpy/scipy closed-form port; returns (seconds, value, grad)."""
+    from oracle import gp_oracle as O
+    t0 = time.perf_counter()
+    val, grad = O.full_obj_grad(X, y, theta, O.SCORE_CRPS)
+    return time.perf_counter() - t0, val, grad
+
+
+def as_written_leg(full_size):
+    """The reference's own operation sequence (torch autograd, float64): KF:239-252 forward + backward.
+    N = 500 and N = 2000 always (median of 3 after one warm-up), N = 10 000 once when `full_size`."""
+    import torch
+    from gpscore_b200 import synth
+    from oracle import ref_as_written as RW
+    torch.set_num_threads(os.cpu_count() or 1)
+    theta = synth.hyper_point("P1")
+    out = {"kind": "reference-as-written", "what": "oracle/ref_as_written.py: ARD (mm + bmm + exp), two cholesky + four LU "
+           "solves on the factors (chol_solve KF:25-29 twice), crps, autograd .backward() — float64 torch CPU",
+           "threads": cpu_threads(), "unit": "s per obj+grad step"}
+    for n in (500, 2000):
+        X, y = synth.kin40k_like(n)
+        RW.full_step(X, y, theta)
+        ts = sorted(RW.time_full_step(X, y, theta)[0] for _ in range(3))
+        out["N%d_s" % n] = ts[1]
+    if full_size:
+        X, y = synth.kin40k_like(N_FULL)
+        t, (val, grad) = RW.time_full_step(X, y, theta)
+        out["N10000_s"] = t
+        out["N10000_evals_per_s"] = 1.0 / t
+        out["N10000_objective"] = val
+        out["_grad"] = grad
+    return out
+
+
 def run_reference(args):
+    """The reference arm: the reference's CPU algorithm for the stated workload (N = 10 000, no sampling, no
+    scaling), all host threads.  value = the closed-form port (the FASTER of the two CPU legs, so the ratio the
+    driver computes is the conservative one); the reference-as-written torch-autograd leg is timed once beside it."""
     rank = env_int("RANK", 0)
     if rank != 0:
         return 0
     cores = os.cpu_count() or 1
-    n_s = pick_sample_rows(150.0, args.steps + args.warmup)
-    for _ in range(args.warmup):
-        cpu_eval_seconds(n_s)
+    X, y, theta = workload_inputs()
+    t_warm, val, grad = port_eval(X, y, theta)      # one untimed evaluation (page-in, thread pools); CPU has no more to warm
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        cpu_eval_seconds(n_s)
+        port_eval(X, y, theta)
     dt = (time.perf_counter() - t0) / args.steps
-    scale = (N_FULL / float(n_s)) ** 3
-    sec_full = dt * scale
-    val = 1.0 / sec_full
-    sample = ("oracle port (numpy/scipy dense path, oracle/gp_oracle.py) — one full-GP LOO-CRPS obj+grad at N=%d "
-              "rows per step, %.2f s measured; scaled by (10000/%d)^3 = %.1f to the N=10000 workload"
-              % (n_s, dt, n_s, scale))
+    aw = as_written_leg(True)
+    aw_grad = aw.pop("_grad")
+    aw["parity_vs_port"] = {"obj_rel": abs(aw["N10000_objective"] - val) / abs(val), "grad_rel": relmax(aw_grad, grad)}
+    sample = ("oracle port (numpy/scipy closed form, oracle/gp_oracle.py): %d full-GP LOO-CRPS obj+grad evaluations at "
+              "the stated N=%d, %.2f s each, measured directly (no sampling, no scaling); 1 untimed warm-up evaluation"
+              % (args.steps, N_FULL, dt))
     line = {
-        "impl": "reference", "metric": METRIC, "value": val, "unit": "evals/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec_full * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "kin40k-FULL N=10000 D=8 full-GP LOO-CRPS obj+grad (KF:239-252)"},
-        "cpu_baseline": {"value": val, "unit": "evals/s", "cores": cores, "kind": "port", "sample": sample},
-        "e2e": {"value": val, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "impl": "reference", "metric": METRIC, "value": 1.0 / dt, "unit": "evals/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "warmup_effective": 1, "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "objective": float(val)},
+        "cpu_baseline": {"value": 1.0 / dt, "unit": "evals/s", "cores": cores, "threads": cpu_threads(), "kind": "port",
+                         "sample": sample, "reference_as_written": aw},
+        "e2e": {"value": 1.0 / dt, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     emit(line)
@@ -183,6 +225,34 @@ def measure_fp64_peak(torch):
     return 2.0 * n ** 3 / (best * 1e-3) / 1e12
 
 
+def library_baseline(torch, Kd):
+    """cuSOLVER potrf + potri and two cuBLAS DGEMMs through torch on the same GPU: what the vendor libraries
+    deliver for the same 2 N^3 flops (factor, invert, K^-1 diag K^-1 as two products).  Informational only."""
+    n = Kd.shape[0]
+    dv = torch.rand(n, dtype=torch.float64, device="cuda")
+
+    def once():
+        L = torch.linalg.cholesky(Kd)
+        Ki = torch.cholesky_inverse(L)
+        Tm = Ki * dv
+        return torch.matmul(Tm, Ki)
+
+    once()
+    torch.cuda.synchronize()
+    best = 1e30
+    for _ in range(2):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        once()
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    return {"ms_per_eval": best, "evals_per_s": 1e3 / best,
+            "what": "torch.linalg.cholesky + torch.cholesky_inverse (cuSOLVER potrf/potri) + K^-1 diag(d) K^-1 as one "
+                    "cuBLAS DGEMM at N=%d, fp64, best of 2 — the dense stages of one evaluation by vendor libraries "
+                    "(no Gram, scores or gradient contraction)" % n}
+
+
 def measured_hbm_peak():
     """HBM copy bandwidth of this pool's B200s as measured by the driver (MEASURED_PEAKS.json),
     else the profiling recipe's fallback."""
@@ -191,6 +261,21 @@ def measured_hbm_peak():
             return float(json.load(fh)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
     except Exception:
         return 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
+
+
+class Gates:
+    """Parity gates of the run: every entry is (error, tolerance); a failed one fails the bench."""
+
+    def __init__(self):
+        self.block = {}
+        self.failed = []
+
+    def check(self, name, err, tol, **extra):
+        ok = bool(err <= tol)
+        self.block[name] = dict(err=float(err), tol=tol, ok=ok, **extra)
+        if not ok:
+            self.failed.append(name)
+        return ok
 
 
 def run_ours(args):
@@ -216,24 +301,35 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t[0])
 
-    def sum_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t[0])
-
     from gpscore_b200 import api, synth
+    from gpscore_b200 import dist as gdist
 
+    gates = Gates()
     stream = torch.cuda.Stream()
     ctx = api.Context(local)
     ctx.set_stream(stream)
+    if world > 1:
+        ctx.comm_init()         # NCCL communicator inside the library (unique id travels over torch.distributed)
     X, y = synth.kin40k_like(N_FULL)
     # replicas only: rank r evaluates its own restart point (K20:211-213 style initialisation)
     theta = synth.hyper_point("P1", seed=2 + rank)
+    th0 = synth.hyper_point("P1")
     Xd, yd = torch.from_numpy(X).cuda(), torch.from_numpy(y).cuda()
     Xh, yh = torch.from_numpy(X).pin_memory(), torch.from_numpy(y).pin_memory()
     ctx.set_data(Xd, yd)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def timed(fn, reps, warm=1):
+        """device time per call of fn (ms), events on the library's stream, max over ranks"""
+        for _ in range(warm):
+            fn()
+        barrier()
+        e0.record(stream)
+        for _ in range(reps):
+            out = fn()
+        e1.record(stream)
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1)) / reps, out
 
     # ---- device-resident timing ------------------------------------------------------------------
     clocks = ClockSampler(local)
@@ -243,7 +339,6 @@ def run_ours(args):
         ctx.full_eval(theta, "crps")
     barrier()
     l0 = ctx.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     e0.record(stream)
     for _ in range(args.steps):
@@ -272,7 +367,7 @@ def run_ours(args):
     e2e = {"value": world * args.steps / (ms_e2e * 1e-3), "unit": "evals/s",
            "h2d_bytes_per_step": 8 * (N_FULL * D + N_FULL + D + 2), "d2h_bytes_per_step": 8 * (1 + D + 2),
            "ms_per_step": ms_e2e / args.steps}
-    assert abs(ev - val) <= 1e-12 * abs(val)
+    gates.check("e2e_equals_device_resident", abs(ev - val) / abs(val), 1e-12)
     ctx.set_data(Xd, yd)
 
     # ---- roofline of the dominant kernel (separate pass: per-launch events switched on) ---------------
@@ -289,26 +384,33 @@ def run_ours(args):
     ctx.set_gemm_timing(False)
     ctx.full_eval(theta, "crps")
     stages_serial = ctx.last_stage_ms()
+    ctx._check(ctx._lib.gps_dbg_set_variant(ctx._h, 4, 0))      # POTRF (with its look-ahead lanes), THEN TRTRI
+    ctx.full_eval(theta, "crps")
+    ctx.full_eval(theta, "crps")
+    stages_split = ctx.last_stage_ms()
     ctx._check(ctx._lib.gps_dbg_set_variant(ctx._h, 4, 1))
     ctx.full_eval(theta, "crps")
     stages = ctx.last_stage_ms()
     gemm_ms = min(gms)
     flops = 2.0 * float(N_FULL) ** 3
     roofline = None
-    fitc = None
     cpu_baseline = None
+    lib_base = None
     if rank == 0:
         traffic, traffic_how = None, None
-        try:   # DRAM bytes of the tile-GEMM launches of one evaluation, from the committed ncu launch list
-            with open(os.path.join(ROOT, "profiles", "r01_launch_summary_N10000_v13.json")) as fh:
-                traffic = float(json.load(fh)["gemm_dram_bytes_per_eval"])
-                traffic_how = ("dram__bytes_read.sum + dram__bytes_write.sum summed over the tile-GEMM launches of one "
-                               "evaluation, ncu launch list profiles/r01_launches_N10000_v13.csv (bytes per step, like "
-                               "achieved); the kernel is tensor-bound: DRAM runs at ~6% of peak")
-        except Exception:
-            pass
+        for name in ("r02_launch_summary_N10000.json", "r01_launch_summary_N10000_v13.json"):
+            try:   # DRAM bytes of the tile-GEMM launches of one evaluation, from the committed ncu launch list
+                with open(os.path.join(ROOT, "profiles", name)) as fh:
+                    traffic = float(json.load(fh)["gemm_dram_bytes_per_eval"])
+                    traffic_how = ("dram__bytes_read.sum + dram__bytes_write.sum summed over the tile-GEMM launches of one "
+                                   "evaluation, ncu launch list summarised in profiles/%s (bytes per step, like achieved); "
+                                   "the kernel is tensor-bound: DRAM runs at ~6%% of peak" % name)
+                break
+            except Exception:
+                pass
         peak = measure_fp64_peak(torch)
         ach = flops / (gemm_ms * 1e-3) / 1e12
+        n3 = float(N_FULL) ** 3
         roofline = {"bound": "tensor", "kernel": "gemm_tile_kernel (FP64 DMMA m8n8k4, sm_100a)", "achieved": ach,
                     "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": traffic, "traffic_how": traffic_how,
                     "launches_per_step": gl, "avg_launch_ms": gemm_ms / max(gl, 1),
@@ -316,13 +418,18 @@ def run_ours(args):
                     "share_note": "sum of per-launch CUDA-event durations / device time of the same serialised "
                                   "evaluation (raw %.3f)" % (gemm_ms / sum(stages_serial.values())),
                     "stages_ms": stages, "stages_ms_serialised": stages_serial,
+                    "stages_ms_potrf_alone": stages_split,
                     "timing_note": "per-launch durations taken with all launches serialised on one stream so that each "
                                    "launch is timed running alone; ms_per_step / value are the shipped (overlapped) schedule",
-                    "stage_note": "POTRF and the TRTRI merges run overlapped (trailing updates / inversion merges on "
-                                  "separate priority streams): 'potrf' is the time of both, 'trtri' the join",
-                    "stage_tflops": {"potrf+trtri": 2.0 * N_FULL ** 3 / 3.0 / ((stages["potrf"] + stages["trtri"]) * 1e-3) / 1e12,
-                                     "lauum": N_FULL ** 3 / 3.0 / (stages["lauum"] * 1e-3) / 1e12,
-                                     "symprod": float(N_FULL) ** 3 / (stages["symprod"] * 1e-3) / 1e12},
+                    "stage_note": "stages_ms: POTRF and the TRTRI merges run overlapped (trailing updates / inversion merges on "
+                                  "separate priority streams): 'potrf' is the time of both, 'trtri' the join; "
+                                  "stages_ms_potrf_alone: knob 4 = 0, POTRF then TRTRI back to back",
+                    "stage_tflops": {"potrf+trtri": 2.0 * n3 / 3.0 / ((stages["potrf"] + stages["trtri"]) * 1e-3) / 1e12,
+                                     "potrf_alone": n3 / 3.0 / (stages_split["potrf"] * 1e-3) / 1e12,
+                                     "trtri_alone": n3 / 3.0 / (stages_split["trtri"] * 1e-3) / 1e12,
+                                     "lauum": n3 / 3.0 / (stages["lauum"] * 1e-3) / 1e12,
+                                     "symprod": n3 / (stages["symprod"] * 1e-3) / 1e12},
+                    "stage_frac_of_peak": {"potrf_alone": n3 / 3.0 / (stages_split["potrf"] * 1e-3) / 1e12 / peak},
                     "peak_how": "cuBLAS DGEMM 6144^3 (torch.matmul fp64), best of 5, CUDA events, measured in "
                                 "this run — MEASURED_PEAKS.json has no fp64 figure"}
     # the other objectives of the path on the same workload (rank 0, device-timed, 2 evaluations each)
@@ -339,20 +446,17 @@ def run_ours(args):
             objectives["full_" + sc + "_ms"] = e0.elapsed_time(e1) / 2
     barrier()
 
-    # ---- FITC M = 20 (same JSON line, secondary) ---------------------------------------------------------
+    # ---- FITC M = 20, N = 10 000 (the other half of the metric) ------------------------------------------
     U = synth.inducing_init(M_FITC)
-    steps_f = max(args.steps * 20, 50)
-    for _ in range(5):
-        ctx.fitc_eval(theta, U, "crps")
-    barrier()
+    steps_f = max(args.steps * 20, 100)
     lf0 = ctx.launch_count()
-    e0.record(stream)
-    for _ in range(steps_f):
-        fv, fg, fgu = ctx.fitc_eval(theta, U, "crps")
-    e1.record(stream)
-    barrier()
-    ms_f = max_over_ranks(e0.elapsed_time(e1))
+    ms_f, (fv, fg, fgu) = timed(lambda: ctx.fitc_eval(theta, U, "crps"), steps_f, warm=5)
     lf1 = ctx.launch_count()
+    # the scripts' optimiser loop (K20:219-251) with theta and U resident on the device: `iters` evaluations +
+    # updates inside one call, no host round trip in between
+    iters_d = 200
+    ms_desc, _ = timed(lambda: ctx.fitc_descend(theta, U, "crps", 1e-3, 1e-3, iters_d), 3, warm=1)
+    floor_us = ctx.launch_floor_us()
     if rank == 0:
         for sc in ("crps", "logs", "nlml", "dss", "kc"):
             ctx.fitc_eval(theta, U, sc)
@@ -364,139 +468,195 @@ def run_ours(args):
             objectives["fitc20_" + sc + "_ms"] = e0.elapsed_time(e1) / 20
     barrier()
     fitc = {"workload": "KIN40K-FITC-20 N=10000 D=8 M=20 LOO-CRPS obj+grad incl. inducing inputs (K20:222-251)",
-            "replicas_evals_per_s": world * steps_f / (ms_f * 1e-3), "ms_per_eval": ms_f / steps_f,
-            "launches_per_eval": (lf1 - lf0) / steps_f,
-            "algorithmic_bytes_per_eval": 3 * 8 * N_FULL * (D + 1)}
+            "replicas_evals_per_s": world * steps_f / (ms_f * steps_f * 1e-3), "ms_per_eval": ms_f,
+            "launches_per_eval": (lf1 - lf0) / (steps_f + 5),
+            "descend": {"iters": iters_d, "ms_per_iter": ms_desc / iters_d, "evals_per_s": 1e3 * iters_d / ms_desc,
+                        "what": "gps_fitc_descend: evaluation + update of theta and the inducing inputs, device-resident "
+                                "(K20:243-251 with the two learning rates of K20:326-327), per iteration"},
+            "algorithmic_bytes_per_eval": 3 * 8 * N_FULL * (D + 1),
+            "roofline": {"bound": "launch", "unit": "us", "floor_us": floor_us, "achieved_us": ms_f * 1e3,
+                         "frac": floor_us / (ms_f * 1e3),
+                         "note": "N=10^4, M=20 is launch/latency-bound (2.2 MB, 56 MFLOP of algorithmic work = ~2 us): the "
+                                 "roofline of this point is the measured floor of what one evaluation call must do — the "
+                                 "same launches with empty kernels, one result read-back and one stream synchronisation "
+                                 "(gps_dbg_launch_floor)"}}
+    if rank == 0:
+        from oracle import gp_oracle as O
+        from oracle import woodbury as WB
+        ov, og, ogu = WB.fitc_obj_grad(X, y, U, theta, O.SCORE_CRPS)[:3]
+        gates.check("fitc20_N10000_obj_vs_oracle", abs(fv - ov) / abs(ov), OBJ_TOL)
+        gates.check("fitc20_N10000_grad_vs_oracle", max(relmax(fg, og), relmax(fgu, ogu)), GRAD_TOL)
     if world > 1:
-        # row-sharded evaluation of ONE problem: each rank holds N/world rows, three NCCL all-reduces
-        lo, hi = (N_FULL * rank) // world, (N_FULL * (rank + 1)) // world
+        # row-sharded evaluation of ONE problem: each rank holds N/world rows, the three all-reduces run inside
+        # the library on the context's stream (NCCL)
+        lo, hi = gdist.row_block(N_FULL, rank, world)
         cs = api.Context(local)
         cs.set_stream(stream)
+        cs.comm_init()
         cs.set_data(Xd[lo:hi].contiguous(), yd[lo:hi].contiguous())
-        th0 = synth.hyper_point("P1")
-
-        def allreduce(t):
-            with torch.cuda.stream(stream):
-                dist.all_reduce(t, op=dist.ReduceOp.SUM)
-            stream.synchronize()
-
-        for _ in range(5):
-            sv = cs.fitc_eval_sharded(th0, U, "crps", N_FULL, allreduce)
-        barrier()
-        e0.record(stream)
-        for _ in range(steps_f):
-            sv = cs.fitc_eval_sharded(th0, U, "crps", N_FULL, allreduce)
-        e1.record(stream)
-        barrier()
-        ms_s = max_over_ranks(e0.elapsed_time(e1))
-        fitc["row_sharded_evals_per_s"] = steps_f / (ms_s * 1e-3)
-        fitc["row_sharded_ms_per_eval"] = ms_s / steps_f
-        fitc["row_sharded_note"] = ("one evaluation split by rows over %d GPUs with 3 NCCL all-reduces; at N=10^4, "
-                                    "M=20 it is launch/collective-latency bound, sharding pays at N=10^6" % world)
+        ms_s, (sv, sg, sgu) = timed(lambda: cs.fitc_eval_sharded(th0, U, "crps", N_FULL), steps_f, warm=5)
+        fitc["row_sharded_evals_per_s"] = 1e3 / ms_s
+        fitc["row_sharded_ms_per_eval"] = ms_s
+        fitc["row_sharded_note"] = ("one evaluation split by rows over %d GPUs, 3 in-library NCCL all-reduces, no host "
+                                    "synchronisation between the passes; at N=10^4, M=20 it is latency bound, sharding "
+                                    "pays at N=10^6" % world)
+        # parity on hardware: the NCCL row-sharded result equals the single-GPU result of the same problem
+        v1, g1, gu1 = ctx.fitc_eval(th0, U, "crps")
+        gates.check("fitc20_N10000_sharded_vs_single", max(abs(sv - v1) / abs(v1), relmax(sg, g1), relmax(sgu, gu1)), SHARD_TOL,
+                    world=world)
         cs.close()
 
     # ---- FITC scaling-sweep point: N = 1e6 rows, M = 20 (BASELINE configs[4]) -----------------------------
-    N_BIG = 1000000
     Xb, yb = synth.kin40k_like(N_BIG, seed=7)
     hbm_peak, hbm_how = measured_hbm_peak()
     cb = api.Context(local)
     cb.set_stream(stream)
-    lo, hi = (N_BIG * rank) // world, (N_BIG * (rank + 1)) // world
+    lo, hi = gdist.row_block(N_BIG, rank, world)
+    Xbd, ybd = torch.from_numpy(Xb[lo:hi]).cuda(), torch.from_numpy(yb[lo:hi]).cuda()
+    cb.set_data(Xbd, ybd)
     if world == 1:
-        cb.set_data(torch.from_numpy(Xb).cuda(), torch.from_numpy(yb).cuda())
-        run_big = lambda: cb.fitc_eval(theta, U, "crps")
+        run_big = lambda Uq: cb.fitc_eval(th0, Uq, "crps")
     else:
-        cb.set_data(torch.from_numpy(Xb[lo:hi]).cuda(), torch.from_numpy(yb[lo:hi]).cuda())
-
-        def allreduce_b(t):
-            with torch.cuda.stream(stream):
-                dist.all_reduce(t, op=dist.ReduceOp.SUM)
-            stream.synchronize()
-
-        th0 = synth.hyper_point("P1")
-        run_big = lambda: cb.fitc_eval_sharded(th0, U, "crps", N_BIG, allreduce_b)
-    for _ in range(3):
-        run_big()
-    barrier()
+        cb.comm_init()
+        run_big = lambda Uq: cb.fitc_eval_sharded(th0, Uq, "crps", N_BIG)
     steps_b = max(args.steps * 4, 20)
-    e0.record(stream)
-    for _ in range(steps_b):
-        run_big()
-    e1.record(stream)
-    barrier()
-    ms_b = max_over_ranks(e0.elapsed_time(e1)) / steps_b
+    ms_b, (bv, bg, bgu) = timed(lambda: run_big(U), steps_b, warm=3)
     bytes_b = 3 * 8 * N_BIG * (D + 1)
+    flops_b = 9.9e3 * N_BIG
     fitc["sweep_N1e6_M20"] = {
         "workload": "synthetic 8-D FITC N=1e6 M=20 LOO-CRPS obj+grad; rows sharded over %d GPU(s)%s" % (
-            world, "" if world == 1 else " with 3 NCCL all-reduces per evaluation"),
+            world, "" if world == 1 else " with 3 in-library NCCL all-reduces per evaluation"),
         "evals_per_s": 1e3 / ms_b, "ms_per_eval": ms_b, "algorithmic_bytes_per_eval": bytes_b,
         "roofline": {"bound": "hbm", "achieved": bytes_b / (ms_b * 1e-3) / 1e9 / world, "peak": hbm_peak, "unit": "GB/s",
                      "frac": bytes_b / (ms_b * 1e-3) / 1e9 / world / hbm_peak, "peak_how": hbm_how,
+                     "fp64_tflops": flops_b / (ms_b * 1e-3) / 1e12 / world,
                      "note": "per-GPU algorithmic bytes (3 passes x 8 N (D+1)) over the whole-evaluation time; the row "
-                             "passes also do ~5.6 kflop/row of fp64 work, so this path sits on the HBM/ALU ridge"}}
+                             "passes do ~9.9 kflop/row of fp64 work (DESIGN.md §4), so this point is bound by the FP64 "
+                             "pipe, not by HBM: fp64_tflops is the per-GPU rate of that count"}}
+    if rank == 0:
+        from oracle import gp_oracle as O
+        from oracle import woodbury as WB
+        ov, og, ogu = WB.fitc_obj_grad(Xb, yb, U, th0, O.SCORE_CRPS)[:3]
+        gates.check("fitc20_N1e6_obj_vs_oracle", abs(bv - ov) / abs(ov), OBJ_TOL, world=world)
+        gates.check("fitc20_N1e6_grad_vs_oracle", max(relmax(bg, og), relmax(bgu, ogu)), GRAD_TOL, world=world)
     # ---- the same sweep at M = 256 and M = 1024: the matrix form (csrc/gps_fitc_large.cu), rows sharded ------
     rng_m = np.random.default_rng(1)
     peak_tf = roofline["peak"] if rank == 0 else None
+    sub = {256: 20000, 1024: 8000}
     for m_big in (256, 1024):
         Ub = Xb[rng_m.choice(N_BIG, m_big, replace=False)] + 0.01 * rng_m.standard_normal((m_big, D))
-        if world == 1:
-            run_m = lambda: cb.fitc_eval(theta, Ub, "crps")
-        else:
-            run_m = lambda: cb.fitc_eval_sharded(th0, Ub, "crps", N_BIG, allreduce_b)
-        for _ in range(2):
-            run_m()
-        barrier()
-        reps_m = 3
-        e0.record(stream)
-        for _ in range(reps_m):
-            run_m()
-        e1.record(stream)
-        barrier()
-        ms_m = max_over_ranks(e0.elapsed_time(e1)) / reps_m
+        ms_m, _ = timed(lambda: run_big(Ub), 3, warm=2)
         flops_m = 10.0 * m_big * m_big * N_BIG
         if rank == 0:
             fitc["sweep_N1e6_M%d" % m_big] = {
                 "workload": "synthetic 8-D FITC N=1e6 M=%d LOO-CRPS obj+grad, matrix form; rows sharded over %d GPU(s)%s" % (
-                    m_big, world, "" if world == 1 else " with 3 NCCL all-reduces of M x M accumulators per evaluation"),
+                    m_big, world, "" if world == 1 else " with 3 in-library NCCL all-reduces of M x M accumulators"),
                 "evals_per_s": 1e3 / ms_m, "ms_per_eval": ms_m, "algorithmic_flops_per_eval": flops_m,
                 "roofline": {"bound": "tensor", "achieved": flops_m / (ms_m * 1e-3) / 1e12 / world, "peak": peak_tf,
                              "unit": "TFLOP/s", "frac": flops_m / (ms_m * 1e-3) / 1e12 / world / peak_tf,
                              "note": "per-GPU share of 10 M^2 N useful fp64 flops (eight N x M x M products, triangular / "
                                      "symmetric halves not counted) over the whole-evaluation time, against the cuBLAS "
                                      "DGEMM rate measured in this run"}}
+            # parity of the matrix form on a row sub-sample the CPU Woodbury port finishes in seconds
+            ns = sub[m_big]
+            cq = api.Context(local)
+            cq.set_stream(stream)
+            cq.set_data(torch.from_numpy(Xb[:ns]).cuda(), torch.from_numpy(yb[:ns]).cuda())
+            qv, qg, qgu = cq.fitc_eval(th0, Ub, "crps")
+            cq.close()
+            ov, og, ogu = WB.fitc_obj_grad(Xb[:ns], yb[:ns], Ub, th0, O.SCORE_CRPS)[:3]
+            gates.check("fitc_M%d_rows%d_obj_vs_oracle" % (m_big, ns), abs(qv - ov) / abs(ov), OBJ_TOL)
+            gates.check("fitc_M%d_rows%d_grad_vs_oracle" % (m_big, ns), max(relmax(qg, og), relmax(qgu, ogu)), GRAD_TOL)
     cb.close()
-    del Xb, yb
+    del Xb, yb, Xbd, ybd
+    barrier()
+
+    # ---- the two other partitioned paths: prediction + scoring by test rows, the 64 x 64 grid round-robin -------
+    _, _, Xs, ys = synth.kin40k_like(N_FULL, T_TEST)
+    Xsd, ysd = torch.from_numpy(Xs).cuda(), torch.from_numpy(ys).cuda()
+    sharded = {}
+    ms_p, met = timed(lambda: gdist.sharded_predict_metrics(ctx, th0, Xsd, ysd), 2, warm=1)
+    sharded["full_predict_metrics"] = {
+        "workload": "kin40k-FULL prediction + test scoring (KF:267-292): N=%d train, T=%d test rows split over %d GPU(s); "
+                    "every rank factors K (replicated), predicts its rows, six metric sums all-reduced" % (N_FULL, T_TEST, world),
+        "ms": ms_p, "test_rows_per_s": T_TEST / (ms_p * 1e-3), "metrics": met,
+        "bound": "tensor: T x N x N cross-Gram product (2 T N^2 = %.1e flop over the ranks) after the replicated 2/3 N^3 "
+                 "factor+invert" % (2.0 * T_TEST * N_FULL * N_FULL)}
+    ms_pf, metf = timed(lambda: gdist.sharded_predict_metrics(ctx, th0, Xsd, ysd, inducing_x=U), 5, warm=1)
+    sharded["fitc20_predict_metrics"] = {
+        "workload": "KIN40K-FITC-20 prediction + test scoring (K20:270-304): T=%d test rows split over %d GPU(s)" % (T_TEST, world),
+        "ms": ms_pf, "test_rows_per_s": T_TEST / (ms_pf * 1e-3), "metrics": metf, "bound": "launch/latency"}
+    if world > 1:
+        # hardware parity: the row-split metrics equal rank 0's single-GPU metrics over all T rows
+        if rank == 0:
+            m1, v1 = ctx.full_predict(th0, Xsd)
+            single = ctx.test_metrics(m1, v1, ysd)
+            gates.check("sharded_predict_metrics_vs_single", max(abs(met[k] - single[k]) / max(abs(single[k]), 1e-300)
+                                                                for k in single), SHARD_TOL, world=world)
+    # grid: CP:109-144 objective surfaces, 64 x 64 points of (length scale, noise s.d.)
+    ls = np.repeat(np.linspace(0.01, 2.0, 64), 64)
+    sd = np.tile(np.linspace(0.01, 1.0, 64), 64)
+    for n_g, reps in ((20, 3), (2048, 1)):
+        rg = np.random.default_rng(5)
+        xg = np.linspace(-6, 6, n_g) if n_g == 20 else np.sort(rg.uniform(-6, 6, n_g))
+        yg = np.sin(xg) + 0.1 * rg.standard_normal(n_g)
+        xgd, ygd = torch.from_numpy(xg).cuda(), torch.from_numpy(yg).cuda()
+        fn = lambda l_, s_: ctx.grid_eval(xgd, ygd, l_, s_, "crps")
+        ms_g, surf = timed(lambda: gdist.sharded_grid(fn, ls, sd, device="cuda"), reps, warm=1)
+        sharded["grid64x64_n%d" % n_g] = {
+            "workload": "contour-plot grid (CP:109-144): 64 x 64 (length scale, noise s.d.) points of the LOO-CRPS surface, "
+                        "n=%d 1-D inputs, points dealt round-robin over %d GPU(s), one all-reduce of the result vector" % (n_g, world),
+            "ms": ms_g, "points_per_s": 4096 / (ms_g * 1e-3),
+            "bound": "latency (one CTA per point, all in shared memory)" if n_g <= 128 else
+                     "tensor/latency: %d blocked n=%d factorisations, 4/3 n^3 flop each" % (4096, n_g)}
+        if rank == 0 and n_g == 20:
+            from oracle import gp_oracle as O
+            idx = np.arange(0, 4096, 97)
+            ref = np.array([O.cal_m_crps(xg, yg, ls[i], sd[i]) for i in idx])
+            gates.check("grid_n20_vs_oracle", relmax(surf[idx], ref), OBJ_TOL)
+    barrier()
 
     if rank == 0:
-        # ---- CPU baseline (oracle port) on a bounded sample ------------------------------------------------
-        n_s = pick_sample_rows(25.0, 1)
-        dt = cpu_eval_seconds(n_s)
-        if n_s < N_FULL and dt * (N_FULL / float(n_s)) ** 3 <= 30.0:
-            # the probe at N = 1500 over-predicts: the full workload fits the budget after all, so time it unscaled
-            n_s = N_FULL
-            dt = cpu_eval_seconds(n_s)
-        scale = (N_FULL / float(n_s)) ** 3
-        cpu_baseline = {"value": 1.0 / (dt * scale), "unit": "evals/s", "cores": os.cpu_count() or 1,
+        lib_base = library_baseline(torch, torch.from_numpy(np.eye(N_FULL)).cuda() * 2.0 +
+                                    ctx.ard(Xd, Xd, th0[0], th0[1:-1]))
+        # ---- CPU baselines (rank 0): the port at the stated N, unscaled; its result IS the parity oracle of the headline
+        X0, y0, theta0 = workload_inputs(seed=2)
+        dt, oval, ograd = port_eval(X0, y0, theta0)
+        gates.check("full_N10000_obj_vs_oracle", abs(val - oval) / abs(oval), OBJ_TOL)
+        gates.check("full_N10000_grad_vs_oracle", relmax(grad, ograd), GRAD_TOL)
+        cpu_baseline = {"value": 1.0 / dt, "unit": "evals/s", "cores": os.cpu_count() or 1,
                         "threads": cpu_threads(), "kind": "port",
-                        "sample": "oracle port (numpy/scipy dense path) — one full-GP LOO-CRPS obj+grad at N=%d rows "
-                                  "(%.2f s), scaled by (10000/%d)^3 = %.1f" % (n_s, dt, n_s, scale)}
+                        "sample": "oracle port (numpy/scipy closed form) — one full-GP LOO-CRPS obj+grad at the stated N=%d "
+                                  "rows, %.2f s, measured directly (no scaling)" % (N_FULL, dt)}
+        if world == 1:
+            aw = as_written_leg(True)
+            aw_grad = aw.pop("_grad")
+            gates.check("full_N10000_obj_vs_reference_as_written", abs(val - aw["N10000_objective"]) / abs(val), OBJ_TOL)
+            gates.check("full_N10000_grad_vs_reference_as_written", relmax(grad, aw_grad), GRAD_TOL)
+            cpu_baseline["reference_as_written"] = aw
         line = {
             "metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "kin40k-FULL N=10000 D=8 full-GP LOO-CRPS obj+grad (KF:239-252)",
+            "config": {"workload": WORKLOAD,
                        "parallelism": "replicas only: one evaluation per GPU, rank r at restart point r; "
                                       "no data-path collective",
                        "l2": "working set 3 x 818 MB fp64 matrices >> 126 MB L2, no flush needed",
                        "objective": float(val), "grad_norm": float(np.linalg.norm(grad))},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
-            "clocks": clk, "fitc": fitc, "objectives_ms_per_eval": objectives,
+            "clocks": clk, "fitc": fitc, "sharded": sharded, "objectives_ms_per_eval": objectives,
+            "library_baseline": lib_base,
+            "parity": {"ok": not gates.failed, "failed": gates.failed, "gates": gates.block,
+                       "tolerances": {"objective": OBJ_TOL, "gradient": GRAD_TOL, "sharded_vs_single": SHARD_TOL}},
         }
         emit(line)
     barrier()
     ctx.close()
     if world > 1:
         dist.destroy_process_group()
+    if rank == 0 and gates.failed:
+        print("bench.py: parity gate(s) failed: %s" % ", ".join(gates.failed), file=sys.stderr)
+        return 3
     return 0
 
 

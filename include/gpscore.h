@@ -86,9 +86,11 @@ int gps_full_predict(gps_ctx* ctx, const double* theta, const double* Xs, int64_
  * exposed separately so the host can all-reduce the packed accumulators between them
  * (acc buffers are DEVICE pointers owned by the caller; their lengths come from
  * gps_fitc_acc_len).  world_n is the global number of rows (the mean in KF:67 divides by it).
- * M <= 32: fused row kernels (all five objectives, staged protocol available).  32 < M <= 4096:
- * gps_fitc_eval runs the matrix form on the tile-GEMM engine (GPS_CRPS / GPS_LOGS / GPS_NLML, one GPU;
- * gps_fitc_loo and gps_fitc_predict work after it); the staged calls return GPS_EINVAL there. */
+ * M <= 31, CRPS / LOGS / NLML: gps_fitc_eval is three fused kernels (preamble + row pass + reduction each) and one
+ * stream synchronisation; DSS / KC and M = 32 use the staged row kernels.  32 < M <= 4096: the matrix form on the
+ * tile-GEMM engine (GPS_CRPS / GPS_LOGS / GPS_NLML; gps_fitc_loo and gps_fitc_predict work after it).  The staged
+ * begin / pass1 / pass2 / pass3 / finish protocol (caller-side all-reduce of the accumulators) implements the
+ * row-additive objectives only and rejects DSS / KC; new code should use gps_fitc_eval_sharded below. */
 int gps_fitc_eval(gps_ctx* ctx, const double* theta, const double* U, int M, double jitter, int score,
                   double* obj, double* grad_theta, double* grad_U);
 int gps_fitc_acc_len(int M, int D, int64_t* len1, int64_t* len2, int64_t* len3);
@@ -99,6 +101,24 @@ int gps_fitc_pass2(gps_ctx* ctx, const double* acc1, double* acc2); /* acc2 = [R
 int gps_fitc_pass3(gps_ctx* ctx, const double* acc2, double* acc3); /* acc3 = [S | P = G [xs|1] | g_b rows (D) | sum lam_bar] */
 int gps_fitc_finish(gps_ctx* ctx, const double* acc2, const double* acc3, double* obj, double* grad_theta,
                     double* grad_U);
+/* ---- row-sharded FITC with the collective inside the library (FITC rows split over ranks, NCCL
+ *      all-reduce of the M x M accumulators and gradient partials) ------------------------------------------------
+ * One process per GPU.  Rank 0 obtains a 128-byte NCCL unique id (gps_comm_unique_id) and hands it to the other
+ * ranks by any means (the Python layer broadcasts it over torch.distributed); every rank then calls
+ * gps_comm_init on its context.  gps_fitc_eval_sharded evaluates ONE problem whose world_n rows are spread over
+ * the ranks in contiguous blocks (this context's gps_set_data holds this rank's block): the three row passes
+ * run with ncclAllReduce(sum, double) of the packed accumulators in between, all enqueued on the context's
+ * stream — no host synchronisation before the final result read-back.  Every rank returns the same objective
+ * and gradients.  CRPS / LOGS / NLML; M <= 31 runs the fused kernels, larger M the matrix form.
+ * libnccl is bound with dlopen at the first gps_comm_* call (gps_comm_set_library names a specific copy). */
+int gps_comm_set_library(const char* path);
+int gps_comm_unique_id(void* out128);
+int gps_comm_init(gps_ctx* ctx, const void* uid128, int rank, int world);
+int gps_comm_info(gps_ctx* ctx, int* rank, int* world, int* nccl_version);
+int gps_comm_destroy(gps_ctx* ctx);
+int gps_comm_allreduce_sum(gps_ctx* ctx, double* buf, int64_t n);   /* in-place sum of a DEVICE buffer over the ranks */
+int gps_fitc_eval_sharded(gps_ctx* ctx, const double* theta, const double* U, int M, double jitter, int score,
+                          int64_t world_n, double* obj, double* grad_theta, double* grad_U);
 int gps_fitc_loo(gps_ctx* ctx, double* loo_mean, double* loo_var);
 /* replaces K20:270-277 → spgp_cal_mean_and_cov K20:76-83 (diagonal only). Needs a finished
  * gps_fitc_eval / pass1+pass2 at the same theta, U (uses its L_A, L_C, beta). */
@@ -108,7 +128,10 @@ int gps_fitc_predict(gps_ctx* ctx, const double* Xs, int64_t T, double* mean, do
 /* `iters` steps of fixed-step gradient descent, theta -= lr_theta * grad (and U -= lr_u * grad_U for
  * FITC: the two learning rates of K20:326-327), without returning to the caller between steps.
  * theta[D+2] and U[M*D] are host arrays updated in place; obj_trace (host, may be NULL) receives
- * the objective before each step.  Stops early with GPS_ENOTPD if a factorisation fails. */
+ * the objective before each step.  Stops early with GPS_ENOTPD if a factorisation fails.
+ * gps_fitc_descend with M <= 31 and CRPS / LOGS / NLML keeps theta and U RESIDENT ON THE DEVICE: every iteration
+ * is three evaluation kernels and one update kernel enqueued back to back, with a single synchronisation and
+ * read-back after the last one (a failed factorisation freezes the parameters at that iteration). */
 int gps_full_descend(gps_ctx* ctx, double* theta, int score, double lr_theta, int iters, double* obj_trace);
 int gps_fitc_descend(gps_ctx* ctx, double* theta, double* U, int M, double jitter, int score, double lr_theta,
                      double lr_u, int iters, double* obj_trace);
@@ -128,6 +151,9 @@ int gps_ard(gps_ctx* ctx, const double* x, int64_t n, const double* xp, int64_t 
             const double* b, int nb, double* out);
 /* chol_solve(B, A) KF:25-29: out[n,nrhs] = A^-1 B for SPD A[n,n]. */
 int gps_chol_solve(gps_ctx* ctx, const double* B, const double* A, int64_t n, int64_t nrhs, double* out);
+/* torch.mm twin for the products inside Q (KF:38), cal_mean_and_cov (KF:124-125) and spgp_cal_mean_and_cov
+ * (K20:81-82): out[m,n] = A[m,k] B[k,n], UVA pointers, any sizes (padded internally to the 128 tile). */
+int gps_matmul(gps_ctx* ctx, const double* A, const double* B, int64_t m, int64_t k, int64_t n, double* out);
 /* crps(m, c, y) KF:60-68 / logs(m, c, y) KF:52-57: c is the VARIANCE. which = GPS_CRPS | GPS_LOGS. */
 int gps_score(gps_ctx* ctx, const double* m, const double* c, const double* y, int64_t n, int which,
               double* out);

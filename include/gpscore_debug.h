@@ -49,6 +49,11 @@ int gps_dbg_trace(gps_ctx* ctx, int cap, int* codes, double* ms);
  * sub-block inverses, off-diagonal inverse, write-back). */
 int gps_dbg_potf2_phases(gps_ctx* ctx, int64_t* cycles17);
 
+/* Launch floor of an evaluation call: `launches` empty kernels on the context's stream followed by one stream
+ * synchronisation, best wall-clock microseconds of `reps` repetitions.  bench.py prints it as the roofline of the
+ * latency-bound FITC M = 20, N = 10^4 point. */
+int gps_dbg_launch_floor(gps_ctx* ctx, int launches, int reps, double* us);
+
 /* Training Gram K = ARD(X,X) + sn2 I of the current data set at theta, N x N (UVA out). */
 int gps_dbg_gram(gps_ctx* ctx, const double* theta, double* K);
 

@@ -267,3 +267,126 @@ def fitc_block_obj_grad(X, y, U, theta, kind, jitter=O.JITTER, folds=4):
         g_b[dd] = (np.sum(G * dux * dux) + np.sum(G2 * duu * duu)) / ell[dd] ** 2
         g_U[:, dd] = (-np.sum(G * dux, axis=1) - 2.0 * np.sum(G2 * duu, axis=1)) / ell[dd] ** 2
     return float(obj), np.concatenate([[g_a], g_b, [g_c]]), g_U
+
+
+def fitc_obj_grad_kspace(X, y, U, theta, score, jitter=O.JITTER, row_slices=None):
+    """Arithmetic prototype of the fused row kernels (csrc/gps_fitc_fused.cu): passes 1 and 2 as in
+    `fitc_obj_grad` with explicit triangular inverses (V = L_A^-1 k, W = T2 k, T2 = L_C^-1 L_A^-1), pass 3
+    in "k-space": per row only k_i is needed,
+        Kuf_bar_i = t_i a1 + (y_i/lam_i) a2 + [2 r_i E1 + (2/lam_i) E2 - 2 lam_bar_i E3] k_i
+        E1 = T2'T2,  E2 = L_A^-T C_bar L_A^-1,  E3 = A^-1,  a1 = T2' beta,  a2 = L_A^-T vy_bar,
+    the row reductions are Z = sum lam_bar_i k_i k_i', P = sum G_i [x_i | 1], sum_i x_id^2 sum_m G_im, and
+    the S = sum V_bar_i V_i' that the Cholesky adjoint of L_A needs is assembled from the M x M accumulators
+    of all three passes:
+        S = b1 (L_C beta_bar)' + vy_bar vy' + 2 L_C^-T R L_C' + 2 C_bar (C - I) - 2 L_A^-1 Z L_A^-T.
+    Same values and gradients as `fitc_obj_grad` up to rounding (tests/test_oracle.py)."""
+    a, b, c = O._split(theta)
+    n, D = X.shape
+    m = U.shape[0]
+    ell = np.exp(np.asarray(b, dtype=np.float64).ravel())
+    if ell.size == 1:
+        ell = np.full(D, ell[0])
+    ea, sn2 = math.exp(a), math.exp(c)
+    y = y.reshape(-1)
+    if row_slices is None:
+        row_slices = [slice(0, n)]
+    Us = U / ell
+    Kuu = _kern(U, U, a, ell)
+    LA = cholesky(Kuu + jitter * np.eye(m), lower=True)
+    LAi = solve_triangular(LA, np.eye(m), lower=True)
+    # pass 1
+    Cm = np.zeros((m, m))
+    vy = np.zeros(m)
+    st = []
+    for sl in row_slices:
+        K = _kern(U, X[sl], a, ell)
+        V = LAi @ K
+        lam = ea - np.sum(V * V, axis=0) + sn2
+        Cm += (V / lam) @ V.T
+        vy += V @ (y[sl] / lam)
+        st.append(dict(K=K, lam=lam, y=y[sl], Xs=X[sl] / ell))
+    LC = cholesky(np.eye(m) + Cm, lower=True)
+    LCi = solve_triangular(LC, np.eye(m), lower=True)
+    beta = LCi @ vy
+    T2 = LCi @ LAi
+    c2 = T2.T @ beta
+    # pass 2
+    obj = 0.0
+    beta_bar = np.zeros(m)
+    R = np.zeros((m, m))
+    for s in st:
+        W = T2 @ s["K"]
+        r = np.sum(W * W, axis=0)
+        lam = s["lam"]
+        d = 1.0 / lam - r / lam ** 2
+        alpha = (s["y"] - c2 @ s["K"]) / lam
+        if score == O.SCORE_NLML:
+            obj += 0.5 * np.sum(np.log(lam)) + 0.5 * float(s["y"] @ alpha)
+            abar, dbar = 0.5 * s["y"], np.zeros_like(d)
+            lb0 = 0.5 / lam
+        else:
+            v, abar, dbar = O._score_and_seeds(alpha.reshape(-1, 1), d.reshape(-1, 1), score)
+            kk = alpha.shape[0] / n
+            obj += v * kk
+            abar, dbar = abar.ravel() * kk, dbar.ravel() * kk
+            lb0 = np.zeros_like(lam)
+        lb0 = lb0 + dbar * (-1.0 / lam ** 2 + 2.0 * r / lam ** 3) - abar * alpha / lam
+        rbar = -dbar / lam ** 2
+        tbar = -abar / lam
+        beta_bar += W @ tbar
+        R += (W * rbar) @ W.T
+        s.update(lb0=lb0, rbar=rbar, tbar=tbar, alpha=alpha, d=d)
+    if score == O.SCORE_NLML:
+        obj += 0.5 * n * math.log(2 * math.pi) + np.sum(np.log(np.diag(LC)))
+        LC_bar0 = np.diag(1.0 / np.diag(LC))
+    else:
+        LC_bar0 = np.zeros((m, m))
+    SW = np.outer(beta, beta_bar) + 2.0 * R + np.outer(beta_bar, beta)
+    LC_bar = -np.tril(LCi.T @ SW) + LC_bar0
+    C_bar = _phi_adj(LC, LC_bar)
+    vy_bar = LCi.T @ beta_bar
+    E1 = T2.T @ T2
+    E2 = LAi.T @ C_bar @ LAi
+    E3 = LAi.T @ LAi
+    a1 = c2
+    a2 = LAi.T @ vy_bar
+    c1 = T2.T @ beta_bar
+    # pass 3 (k-space)
+    Z = np.zeros((m, m))
+    P = np.zeros((m, D))
+    S0 = np.zeros(m)
+    xq = np.zeros(D)
+    sum_lb = 0.0
+    for s in st:
+        K, lam, ys = s["K"], s["lam"], s["y"]
+        P2 = E2 @ K
+        s1 = np.sum(K * P2, axis=0)
+        bw = c1 @ K
+        lb = s["lb0"] - bw * ys / lam ** 2 - s1 / lam ** 2
+        Kb = np.outer(a1, s["tbar"]) + np.outer(a2, ys / lam) + 2.0 * (E1 @ K) * s["rbar"] + 2.0 * P2 / lam \
+            - 2.0 * (E3 @ K) * lb
+        G = Kb * K
+        Z += (K * lb) @ K.T
+        P += G @ s["Xs"]
+        S0 += G.sum(axis=1)
+        xq += (s["Xs"] ** 2).T @ G.sum(axis=0)
+        sum_lb += lb.sum()
+    # finish
+    b1 = LCi.T @ beta
+    S = np.outer(b1, LC @ beta_bar) + np.outer(vy_bar, vy) + 2.0 * LCi.T @ R @ LC.T + 2.0 * C_bar @ Cm \
+        - 2.0 * LAi @ Z @ LAi.T
+    LA_bar = -np.tril(LAi.T @ S)
+    A_bar = _phi_adj(LA, LA_bar)
+    G2 = A_bar * Kuu
+    g_a = ea * sum_lb + G2.sum() + S0.sum()
+    g_c = sn2 * sum_lb
+    g_b = np.zeros(D)
+    g_U = np.zeros((m, D))
+    for dd in range(D):
+        u = Us[:, dd]
+        diff = u[:, None] - u[None, :]
+        g_b[dd] = np.sum(u * u * S0) - 2.0 * np.sum(u * P[:, dd]) + xq[dd] + np.sum(G2 * diff * diff)
+        g_U[:, dd] = (-(u * S0 - P[:, dd]) - 2.0 * np.sum(G2 * diff, axis=1)) / ell[dd]
+    loo_mean = np.concatenate([s["y"] - s["alpha"] / s["d"] for s in st])
+    loo_var = np.concatenate([1.0 / s["d"] for s in st])
+    return float(obj), np.concatenate([[g_a], g_b, [g_c]]), g_U, loo_mean, loo_var

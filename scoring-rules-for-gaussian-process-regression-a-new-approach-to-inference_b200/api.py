@@ -10,11 +10,18 @@ The reference has no importable module: its hot path is loop-body code in four s
     with torch.no_grad(): para_l -= lr * para_l.grad ...                                   # KF:254-260 unchanged
 
 torch tensors are buffers only: every number is produced by libgpscore.so through ctypes
-(lib.py).  Hyper-parameterisation as in the reference: para_k = log sf^2, para_l = log l
+(lib.py) — including the matrix products inside the twins `Q`, `cal_mean_and_cov` and
+`spgp_cal_mean_and_cov` (`gps_matmul`).
+
+Stream ordering: unless a stream is pinned with `Context.set_stream`, every call first points the
+library at torch's CURRENT stream on the context's device, so tensors produced by torch ops
+(`.double()`, `.cuda()`, NCCL all-reduces) and the library's kernels are ordered like any two torch
+ops would be.  Hyper-parameterisation as in the reference: para_k = log sf^2, para_l = log l
 (one element or [1, D]), para_noise = log sn^2 (KF:7-12, KF:239).
 """
 import ctypes as C
 import math
+import weakref
 
 import numpy as np
 import torch
@@ -75,6 +82,8 @@ class Context:
         self.N = 0
         self.D = 0
         self._data_key = None
+        self._pinned = False        # set_stream(stream) pins; otherwise torch's current stream is followed
+        self._cur_stream = None
 
     def close(self):
         if getattr(self, "_h", None):
@@ -90,15 +99,27 @@ class Context:
     def _check(self, code):
         _L.check(self._h, code)
 
+    def _enter(self):
+        """Order the library behind torch: enqueue on torch's current stream of this device (the
+        legacy default stream is passed as cudaStreamLegacy = 1; NULL would select the context's own)."""
+        if self._pinned:
+            return
+        s = torch.cuda.current_stream(self.device).cuda_stream or 1
+        if s != self._cur_stream:
+            self._check(self._lib.gps_set_stream(self._h, s))
+            self._cur_stream = s
+
     # ---- data --------------------------------------------------------------------------------
     def set_data(self, X, y):
         """train_x [N, D], train_y [N] or [N, 1] (KF:208-209); host or device."""
+        self._enter()
         X = _as_f64(X)
         y = _as_f64(y).reshape(-1)
         if X.dim() != 2 or y.numel() != X.shape[0]:
             raise ValueError("set_data: X must be [N, D] and y must have N elements")
         self._check(self._lib.gps_set_data(self._h, X.data_ptr(), y.data_ptr(), X.shape[0], X.shape[1]))
         self.N, self.D = int(X.shape[0]), int(X.shape[1])
+        self._data_key = None       # whatever _bind_data cached no longer describes the context
         self._y_stats = (float(y.mean()), float(y.var(unbiased=True)) if y.numel() > 1 else 0.0)
 
     def _theta(self, theta):
@@ -112,6 +133,7 @@ class Context:
     # ---- full GP -----------------------------------------------------------------------------
     def full_eval(self, theta, score, grad=True):
         """Objective and gradient wrt theta = [a, b_1..b_D, c] (KF:239-252 / 329-339 / 416-428)."""
+        self._enter()
         th = self._theta(theta)
         obj = np.zeros(1)
         g = np.zeros(self.D + 2)
@@ -122,6 +144,7 @@ class Context:
     def full_descend(self, theta, score, lr, iters):
         """`iters` steps of the scripts' fixed-step gradient descent (KF:237-260) in one call.
         Returns (theta after the last step, objective before each step)."""
+        self._enter()
         th = self._theta(theta).copy()
         trace = np.zeros(int(iters))
         sc = _L.SCORES[score] if isinstance(score, str) else int(score)
@@ -130,6 +153,7 @@ class Context:
 
     def fitc_descend(self, theta, U, score, lr, lr_u, iters, jitter=JITTER):
         """K20:219-251 in one call: theta -= lr * grad, inducing_x -= lr_u * grad (K20:326-327)."""
+        self._enter()
         th = self._theta(theta).copy()
         Uh = _host_vec(U).copy()
         M = Uh.size // self.D
@@ -141,6 +165,7 @@ class Context:
 
     def full_loo(self):
         """mean_term, cov_term of KF:243-244 for the last crps/logs evaluation, as [N, 1] tensors."""
+        self._enter()
         m = torch.empty(self.N, dtype=torch.float64, device=self.device)
         v = torch.empty(self.N, dtype=torch.float64, device=self.device)
         self._check(self._lib.gps_full_loo(self._h, m.data_ptr(), v.data_ptr()))
@@ -148,6 +173,7 @@ class Context:
 
     def full_predict(self, theta, Xs):
         """Predictive mean and variance (diagonal of KF:121-126's covariance) at Xs [T, D]."""
+        self._enter()
         th = self._theta(theta)
         Xs = _as_f64(Xs)
         T = int(Xs.shape[0])
@@ -159,6 +185,7 @@ class Context:
     # ---- FITC --------------------------------------------------------------------------------
     def fitc_eval(self, theta, U, score, jitter=JITTER):
         """Objective and gradients (theta, inducing inputs) of K20:222-236 / 329-344 / 434-452."""
+        self._enter()
         th = self._theta(theta)
         Uh = _host_vec(U)
         M = Uh.size // self.D
@@ -176,15 +203,64 @@ class Context:
             raise _L.GpsError(code, "fitc_acc_len")
         return a.value, b.value, c.value
 
-    def fitc_eval_sharded(self, theta, U, score, world_n, allreduce, jitter=JITTER):
-        """Row-sharded FITC evaluation: this context holds a contiguous block of rows; `allreduce`
-        sums a 1-D float64 device tensor in place across ranks (torch.distributed over NCCL in
-        production, gloo or a python stand-in in the CPU tests).  Three all-reduces per
-        evaluation."""
+    # ---- row-sharded FITC (one process per GPU) ----------------------------------------------
+    def comm_init(self, group=None):
+        """Create this context's NCCL communicator inside the library.  Rank 0 draws the unique id and
+        torch.distributed (any backend) carries its 128 bytes to the other ranks; after that the
+        all-reduces of `fitc_eval_sharded` are issued by libgpscore itself on the context's stream."""
+        import torch.distributed as dist
+        self._enter()
+        try:    # bind the libnccl this process already uses (torch's bundled copy), not a second one
+            import nvidia.nccl
+            import os
+            for base in list(getattr(nvidia.nccl, "__path__", [])):
+                cand = os.path.join(base, "lib", "libnccl.so.2")
+                if os.path.isfile(cand):
+                    self._lib.gps_comm_set_library(cand.encode())
+                    break
+        except Exception:
+            pass
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        uid = (C.c_char * 128)()
+        if rank == 0:
+            code = self._lib.gps_comm_unique_id(uid)
+            if code != _L.GPS_OK:
+                raise _L.GpsError(code, "gps_comm_unique_id failed (libnccl.so.2 not loadable?)")
+        backend = dist.get_backend(group)
+        t = torch.frombuffer(bytearray(uid.raw), dtype=torch.uint8).clone()
+        if backend == "nccl":
+            t = t.to(self.device)
+        dist.broadcast(t, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        raw = bytes(t.cpu().numpy().tobytes())
+        self._check(self._lib.gps_comm_init(self._h, C.c_char_p(raw), rank, world))
+        self.rank, self.world = rank, world
+
+    def comm_allreduce_(self, t):
+        """In-place sum of a float64 device tensor over the context's communicator (library NCCL)."""
+        self._enter()
+        assert t.dtype == torch.float64 and t.is_cuda and t.is_contiguous()
+        self._check(self._lib.gps_comm_allreduce_sum(self._h, t.data_ptr(), t.numel()))
+        return t
+
+    def fitc_eval_sharded(self, theta, U, score, world_n, allreduce=None, jitter=JITTER):
+        """Row-sharded FITC evaluation: this context holds a contiguous block of the `world_n` rows.
+        allreduce=None (production): gps_fitc_eval_sharded — the three all-reduces run inside the
+        library over its NCCL communicator (`comm_init`), nothing synchronises the host between the
+        passes.  A callable (`allreduce(tensor)` sums a 1-D float64 device tensor in place across
+        ranks) selects the staged protocol of include/gpscore.h instead, for callers that bring their
+        own collective."""
+        self._enter()
         th = self._theta(theta)
         Uh = _host_vec(U)
         M = Uh.size // self.D
         sc = _L.SCORES[score] if isinstance(score, str) else int(score)
+        obj = np.zeros(1)
+        g = np.zeros(self.D + 2)
+        gU = np.zeros(M * self.D)
+        if allreduce is None:
+            self._check(self._lib.gps_fitc_eval_sharded(self._h, _dp(th), _dp(Uh), M, float(jitter), sc, int(world_n),
+                                                        _dp(obj), _dp(g), _dp(gU)))
+            return float(obj[0]), g, gU.reshape(M, self.D)
         l1, l2, l3 = self.fitc_acc_len(M)
         key = (M, self.D)
         if getattr(self, "_acc_key", None) != key:
@@ -194,17 +270,26 @@ class Context:
         self._check(self._lib.gps_fitc_begin(self._h, _dp(th), _dp(Uh), M, float(jitter), sc, int(world_n)))
         self._check(self._lib.gps_fitc_pass1(self._h, a1.data_ptr()))
         allreduce(a1)
+        self._after_collective()
         self._check(self._lib.gps_fitc_pass2(self._h, a1.data_ptr(), a2.data_ptr()))
         allreduce(a2)
+        self._after_collective()
         self._check(self._lib.gps_fitc_pass3(self._h, a2.data_ptr(), a3.data_ptr()))
         allreduce(a3)
-        obj = np.zeros(1)
-        g = np.zeros(self.D + 2)
-        gU = np.zeros(M * self.D)
+        self._after_collective()
         self._check(self._lib.gps_fitc_finish(self._h, a2.data_ptr(), a3.data_ptr(), _dp(obj), _dp(g), _dp(gU)))
         return float(obj[0]), g, gU.reshape(M, self.D)
 
+    def _after_collective(self):
+        """The caller's collective ran on torch's current stream.  Following that stream keeps the
+        next pass ordered behind it; a context pinned to another stream has to wait for it."""
+        if self._pinned:
+            torch.cuda.current_stream(self.device).synchronize()
+        else:
+            self._enter()
+
     def fitc_loo(self):
+        self._enter()
         m = torch.empty(self.N, dtype=torch.float64, device=self.device)
         v = torch.empty(self.N, dtype=torch.float64, device=self.device)
         self._check(self._lib.gps_fitc_loo(self._h, m.data_ptr(), v.data_ptr()))
@@ -212,21 +297,14 @@ class Context:
 
     def fitc_predict(self, theta, U, Xs, jitter=JITTER, score="nlml", force_matrix_form=False):
         """Predictive mean / variance of K20:270-277 (diagonal only) at Xs."""
+        self._enter()
         th = self._theta(theta)
         Uh = _host_vec(U)
         M = Uh.size // self.D
-        if M > 32 or force_matrix_form:
-            # matrix form (csrc/gps_fitc_large.cu): an objective-only evaluation leaves the factors in place
-            obj = np.zeros(1)
-            self._check(self._lib.gps_fitc_eval(self._h, _dp(th), _dp(Uh), M, float(jitter), _L.SCORES[score],
-                                                _dp(obj), None, None))
-        else:
-            l1, l2, _ = self.fitc_acc_len(M)
-            a1 = torch.zeros(l1, dtype=torch.float64, device=self.device)
-            a2 = torch.zeros(l2, dtype=torch.float64, device=self.device)
-            self._check(self._lib.gps_fitc_begin(self._h, _dp(th), _dp(Uh), M, float(jitter), _L.SCORES[score], self.N))
-            self._check(self._lib.gps_fitc_pass1(self._h, a1.data_ptr()))
-            self._check(self._lib.gps_fitc_pass2(self._h, a1.data_ptr(), a2.data_ptr()))
+        # an objective-only evaluation leaves the factors (L_A, L_C, beta) in place on every path
+        obj = np.zeros(1)
+        self._check(self._lib.gps_fitc_eval(self._h, _dp(th), _dp(Uh), M, float(jitter), _L.SCORES[score],
+                                            _dp(obj), None, None))
         Xs = _as_f64(Xs)
         T = int(Xs.shape[0])
         m = torch.empty(T, dtype=torch.float64, device=self.device)
@@ -237,6 +315,7 @@ class Context:
     # ---- metrics / element-wise twins ---------------------------------------------------------
     def test_metrics(self, mean, var, y, y_train=None, return_sums=False):
         """mse, SMSE (KF:128-134), logs, crps, MSLL (KF:110-119), +-2 sd coverage (KF:288-292)."""
+        self._enter()
         mean, var, y = _as_f64(mean).reshape(-1), _as_f64(var).reshape(-1), _as_f64(y).reshape(-1)
         if y_train is not None:
             yt = _as_f64(y_train).reshape(-1)
@@ -252,6 +331,7 @@ class Context:
         return res
 
     def ard(self, x, xp, a, b):
+        self._enter()
         x, xp = _as_f64(x), _as_f64(xp)
         bh = _host_vec(b)
         out = torch.empty(x.shape[0], xp.shape[0], dtype=torch.float64, device=x.device)
@@ -260,6 +340,7 @@ class Context:
         return out
 
     def chol_solve(self, B, A):
+        self._enter()
         B2, A2 = _as_f64(B), _as_f64(A)
         n = A2.shape[0]
         B2 = B2.reshape(n, -1)
@@ -268,6 +349,7 @@ class Context:
         return out
 
     def score(self, m, c, y, which):
+        self._enter()
         m, c, y = _as_f64(m).reshape(-1), _as_f64(c).reshape(-1), _as_f64(y).reshape(-1)
         out = np.zeros(1)
         self._check(self._lib.gps_score(self._h, m.data_ptr(), c.data_ptr(), y.data_ptr(), m.numel(),
@@ -276,6 +358,7 @@ class Context:
 
     def grid_eval(self, x, y, ls, noise_sd, which):
         """CP:109-144: objective `which` at every (length scale, noise s.d.) pair."""
+        self._enter()
         x, y = _as_f64(x).reshape(-1), _as_f64(y).reshape(-1)
         ls, sd = _host_vec(ls), _host_vec(noise_sd)
         out = np.zeros(ls.size)
@@ -285,11 +368,36 @@ class Context:
 
     # ---- accounting --------------------------------------------------------------------------
     def set_stream(self, stream=None):
-        """Enqueue on a torch stream (so torch.cuda.Event brackets the work); None = own stream."""
-        self._check(self._lib.gps_set_stream(self._h, None if stream is None else stream.cuda_stream))
+        """Pin the context to a torch stream (so torch.cuda.Event on it brackets the work); None
+        un-pins: the context follows torch's current stream again."""
+        if stream is None:
+            self._pinned = False
+            self._cur_stream = None
+            return
+        self._check(self._lib.gps_set_stream(self._h, stream.cuda_stream or 1))
+        self._pinned = True
+        self._cur_stream = stream.cuda_stream or 1
+
+    def matmul(self, A, B):
+        """torch.mm twin on the library's tile GEMM (gps_matmul)."""
+        self._enter()
+        A2, B2 = _as_f64(A), _as_f64(B)
+        if A2.dim() != 2 or B2.dim() != 2 or A2.shape[1] != B2.shape[0]:
+            raise ValueError("matmul: shapes %s x %s" % (tuple(A2.shape), tuple(B2.shape)))
+        out = torch.empty(A2.shape[0], B2.shape[1], dtype=torch.float64, device=A2.device)
+        self._check(self._lib.gps_matmul(self._h, A2.data_ptr(), B2.data_ptr(), A2.shape[0], A2.shape[1], B2.shape[1],
+                                         out.data_ptr()))
+        return out
 
     def set_gemm_timing(self, on):
         self._check(self._lib.gps_set_gemm_timing(self._h, 1 if on else 0))
+
+    def launch_floor_us(self, launches=3, reps=50):
+        """Wall-clock floor of an evaluation call: `launches` empty kernels + one stream synchronisation."""
+        self._enter()
+        us = C.c_double()
+        self._check(self._lib.gps_dbg_launch_floor(self._h, int(launches), int(reps), C.byref(us)))
+        return us.value
 
     def launch_count(self):
         return int(self._lib.gps_launch_count(self._h))
@@ -321,10 +429,19 @@ def default_context(device=None):
 
 
 def _bind_data(ctx, X, y):
-    key = (X.data_ptr(), tuple(X.shape), X._version, y.data_ptr(), y._version) if isinstance(X, torch.Tensor) else None
-    if key is None or ctx._data_key != key:
+    """Upload the training set unless THESE tensor objects, unmodified, are what the context holds.
+    Identity is by weak reference (a new tensor that the caching allocator places at a freed tensor's
+    address is a different object), modification by torch's version counters; anything else —
+    numpy arrays, tensors whose objects died — is uploaded again: N D doubles are nothing next to
+    the evaluation."""
+    if isinstance(X, torch.Tensor) and isinstance(y, torch.Tensor):
+        k = ctx._data_key
+        if (k is not None and k[0]() is X and k[1]() is y and k[2] == (X._version, y._version, tuple(X.shape), tuple(y.shape))):
+            return
         ctx.set_data(X, y)
-        ctx._data_key = key
+        ctx._data_key = (weakref.ref(X), weakref.ref(y), (X._version, y._version, tuple(X.shape), tuple(y.shape)))
+    else:
+        ctx.set_data(X, y)
 
 
 def _theta_from_leaves(pk, pl, pn, D):
@@ -420,7 +537,7 @@ def Q(a, u, b, para_k=None, para_l=None, jitter=JITTER):
     K_uu = ARD(u, u, pk, pl)
     K_uu = K_uu + jitter * torch.eye(K_uu.shape[0], dtype=K_uu.dtype, device=K_uu.device)
     K_ub = ARD(u, b, pk, pl)
-    return K_au.mm(chol_solve(K_ub, K_uu))
+    return default_context().matmul(K_au, chol_solve(K_ub, K_uu))
 
 
 def crps(m, c, data_y):
@@ -446,8 +563,9 @@ def cal_mean_and_cov(k1, k2, k3, num, eye_num, data_y, sigma_noise_sq=None):
     eye = torch.eye(eye_num, dtype=k2.dtype, device=k2.device)
     Kn = k2 + sn2 * eye
     sol = chol_solve(torch.cat([data_y.reshape(eye_num, -1), k1.t()], dim=1), Kn)
-    res_mean = k1.mm(sol[:, :1])
-    res_cov = sn2 * torch.eye(num, dtype=k2.dtype, device=k2.device) + k3 - k1.mm(sol[:, 1:])
+    prod = default_context().matmul(k1, sol)      # [k1 Kn^-1 y | k1 Kn^-1 k1'] in one product
+    res_mean = prod[:, :1]
+    res_cov = sn2 * torch.eye(num, dtype=k2.dtype, device=k2.device) + k3 - prod[:, 1:]
     return res_mean, res_cov
 
 
@@ -456,8 +574,9 @@ def spgp_cal_mean_and_cov(k1, Q1, Q2, k2, num_test, num_jitter, data_y, sigma_no
     sn2 = _noise(sigma_noise_sq)
     G = torch.diag(torch.diag(k1 - Q1) + sn2)
     sol = chol_solve(torch.cat([data_y.reshape(num_jitter, -1), Q2.t()], dim=1), Q1 + G)
-    mean_term = Q2.mm(sol[:, :1])
-    cov_term = sn2 * torch.eye(num_test, dtype=k2.dtype, device=k2.device) + k2 - Q2.mm(sol[:, 1:])
+    prod = default_context().matmul(Q2, sol)
+    mean_term = prod[:, :1]
+    cov_term = sn2 * torch.eye(num_test, dtype=k2.dtype, device=k2.device) + k2 - prod[:, 1:]
     return mean_term, cov_term
 
 

@@ -235,6 +235,8 @@ void gps_destroy(gps_ctx* ctx) {
     if (s) cudaStreamDestroy(s);
   }
   gps_fitc_large_free(ctx);
+  gps_fitc_fused_free(ctx);
+  gps_comm_free(ctx);
   for (auto* v : {&ctx->potrf_events, &ctx->tile_events, &ctx->below_events, &ctx->trailA1_events})
     for (auto e : *v) cudaEventDestroy(e);
   if (ctx->panel2_stream) cudaStreamDestroy(ctx->panel2_stream);
@@ -286,6 +288,7 @@ int gps_set_data(gps_ctx* ctx, const double* X, const double* y, int64_t N, int 
   ctx->loo_valid = false;
   ctx->fitc.begun = false;
   ctx->fitc.pass2_done = false;
+  ctx->fitc.fused = false;
   return GPS_OK;
 }
 
@@ -371,6 +374,9 @@ int gps_fitc_descend(gps_ctx* ctx, double* theta, double* U, int M, double jitte
                      double lr_u, int iters, double* obj_trace) {
   if (!ctx) return GPS_EINVAL;
   if (!theta || !U || M <= 0 || iters < 0) return gps_fail(ctx, GPS_EINVAL, "fitc_descend: bad arguments");
+  if (ctx->N == 0) return gps_fail(ctx, GPS_ESTATE, "fitc_descend: call gps_set_data first");
+  if (ctx->fitc_variant == 2 && M < ctx->fitc_large_min_m && gps_fitc_fused_supports(ctx, M, score))
+    return gps_fitc_fused_descend(ctx, theta, U, M, jitter, score, lr_theta, lr_u, iters, obj_trace);   // device-resident loop
   const int P = ctx->D + 2, Q = M * ctx->D;
   std::vector<double> g(P), gU(Q);
   for (int it = 0; it < iters; ++it) {

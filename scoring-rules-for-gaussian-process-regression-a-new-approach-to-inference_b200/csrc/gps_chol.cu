@@ -626,7 +626,17 @@ int gemm_equal_tasks(gps_ctx* ctx, const double* A, const double* B, double* C, 
   return GPS_OK;
 }
 
-int potrf_driver(gps_ctx* ctx, double* K, double* Xinv, double* scratch, int64_t Np, bool with_trtri) {
+// restores the context's stream and strip policy on every exit path of the factorisation driver (its GPS_CUDA /
+// GPS_CHECK macros return from the middle of the lane loop)
+struct LaneGuard {
+  gps_ctx* c;
+  cudaStream_t s;
+  int policy;
+  explicit LaneGuard(gps_ctx* ctx) : c(ctx), s(ctx->stream), policy(ctx->gemm_strip_policy) {}
+  ~LaneGuard() { c->stream = s; c->gemm_strip_policy = policy; }
+};
+
+int potrf_lanes(gps_ctx* ctx, double* K, double* Xinv, double* scratch, int64_t Np, bool with_trtri) {
   const int nb = (int)(Np / T);
   const int OB = GPS_POTRF_OB;
   const int no = (nb + OB - 1) / OB;
@@ -715,15 +725,29 @@ int potrf_driver(gps_ctx* ctx, double* K, double* Xinv, double* scratch, int64_t
     }
     if (rc == GPS_OK) rc = trace_mark(ctx, 4000 + o, s_tri);
   }
-  ctx->stream = s_user;
-  if (rc != GPS_OK) return rc;
-  if (with_trtri) {
-    GPS_CUDA(cudaEventRecord(ctx->join_trail_ev, s_trail));
-    GPS_CUDA(cudaEventRecord(ctx->join_tri_ev, s_tri));
-    GPS_CUDA(cudaStreamWaitEvent(s_user, ctx->join_trail_ev, 0));
-    GPS_CUDA(cudaStreamWaitEvent(s_user, ctx->join_tri_ev, 0));
+  return rc;
+}
+
+int potrf_driver(gps_ctx* ctx, double* K, double* Xinv, double* scratch, int64_t Np, bool with_trtri) {
+  cudaStream_t s_user = ctx->stream;
+  int rc;
+  {
+    LaneGuard guard(ctx);
+    rc = potrf_lanes(ctx, K, Xinv, scratch, Np, with_trtri);
   }
-  return GPS_OK;
+  // join every forked lane into the caller's stream, also after an error: later calls on this context must not
+  // overtake work still queued on the internal streams
+  int jrc = GPS_OK;
+  for (cudaStream_t s : {ctx->panel_stream, ctx->panel2_stream, ctx->trail_stream, ctx->tri_stream}) {
+    if (!s || s == s_user) continue;
+    cudaEvent_t ev = (s == ctx->tri_stream) ? ctx->join_tri_ev : ctx->join_trail_ev;
+    if (!ev) continue;
+    if (cudaEventRecord(ev, s) != cudaSuccess || cudaStreamWaitEvent(s_user, ev, 0) != cudaSuccess) {
+      cudaGetLastError();
+      if (jrc == GPS_OK) jrc = gps_fail(ctx, GPS_ECUDA, "potrf: joining the factorisation lanes failed");
+    }
+  }
+  return rc != GPS_OK ? rc : jrc;
 }
 
 }  // namespace

@@ -1,0 +1,159 @@
+// The collective of the row-sharded FITC evaluation, inside the library: one NCCL communicator per context
+// (one process per GPU), all-reduces of the packed accumulators enqueued on the context's stream between the
+// row passes — no host synchronisation, no Python callback on the data path.
+//
+// libnccl is bound at run time (dlopen): libgpscore.so has no link-time dependency on it, so the library still
+// loads on a box without NCCL and single-GPU use never touches it.  Lookup order: the copy the process already
+// has (torch's bundled libnccl.so.2, found with RTLD_NOLOAD), a path given with gps_comm_set_library, then the
+// system's libnccl.so.2.  Only the C API that has been stable since NCCL 2.0 is used.
+#include <dlfcn.h>
+#include <nccl.h>
+#include <string.h>
+
+#include "gps_common.cuh"
+
+struct gps_comm {
+  ncclComm_t comm = nullptr;
+  int rank = 0, world = 1;
+};
+
+namespace {
+
+struct NcclApi {
+  void* lib = nullptr;
+  decltype(&ncclGetUniqueId) GetUniqueId = nullptr;
+  decltype(&ncclCommInitRank) CommInitRank = nullptr;
+  decltype(&ncclAllReduce) AllReduce = nullptr;
+  decltype(&ncclCommDestroy) CommDestroy = nullptr;
+  decltype(&ncclGetErrorString) GetErrorString = nullptr;
+  decltype(&ncclGetVersion) GetVersion = nullptr;
+  std::string path_hint, err;
+};
+
+NcclApi g_nccl;
+
+bool nccl_load() {
+  if (g_nccl.lib) return true;
+  void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+  if (!h && !g_nccl.path_hint.empty()) h = dlopen(g_nccl.path_hint.c_str(), RTLD_NOW | RTLD_GLOBAL);
+  if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h) {
+    const char* e = dlerror();
+    g_nccl.err = e ? e : "dlopen(libnccl.so.2) failed";
+    return false;
+  }
+#define GPS_NCCL_SYM(name)                                                     \
+  g_nccl.name = reinterpret_cast<decltype(g_nccl.name)>(dlsym(h, "nccl" #name)); \
+  if (!g_nccl.name) {                                                          \
+    g_nccl.err = "libnccl lacks nccl" #name;                                   \
+    return false;                                                              \
+  }
+  GPS_NCCL_SYM(GetUniqueId)
+  GPS_NCCL_SYM(CommInitRank)
+  GPS_NCCL_SYM(AllReduce)
+  GPS_NCCL_SYM(CommDestroy)
+  GPS_NCCL_SYM(GetErrorString)
+  GPS_NCCL_SYM(GetVersion)
+#undef GPS_NCCL_SYM
+  g_nccl.lib = h;
+  return true;
+}
+
+}  // namespace
+
+void gps_comm_free(gps_ctx* ctx) {
+  if (!ctx->comm) return;
+  if (ctx->comm->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm->comm);
+  delete ctx->comm;
+  ctx->comm = nullptr;
+}
+
+// in-place sum of n doubles over the communicator's ranks, enqueued on the context's stream
+int gps_comm_allreduce(gps_ctx* ctx, double* buf, size_t n) {
+  if (!ctx->comm || !ctx->comm->comm) return gps_fail(ctx, GPS_ESTATE, "no communicator: call gps_comm_init first");
+  const ncclResult_t r = g_nccl.AllReduce(buf, buf, n, ncclDouble, ncclSum, ctx->comm->comm, ctx->stream);
+  if (r != ncclSuccess) return gps_fail(ctx, GPS_ECUDA, "ncclAllReduce: %s", g_nccl.GetErrorString(r));
+  return GPS_OK;
+}
+
+extern "C" {
+
+int gps_comm_set_library(const char* path) {
+  g_nccl.path_hint = path ? path : "";
+  return GPS_OK;
+}
+
+int gps_comm_unique_id(void* out128) {
+  if (!out128) return GPS_EINVAL;
+  if (!nccl_load()) return GPS_ESTATE;
+  ncclUniqueId id;
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  if (g_nccl.GetUniqueId(&id) != ncclSuccess) return GPS_ECUDA;
+  memcpy(out128, &id, sizeof id);
+  return GPS_OK;
+}
+
+int gps_comm_init(gps_ctx* ctx, const void* uid128, int rank, int world) {
+  if (!ctx) return GPS_EINVAL;
+  if (!uid128 || world < 1 || rank < 0 || rank >= world) return gps_fail(ctx, GPS_EINVAL, "comm_init: bad arguments");
+  if (!nccl_load()) return gps_fail(ctx, GPS_ESTATE, "comm_init: %s", g_nccl.err.c_str());
+  GPS_CUDA(cudaSetDevice(ctx->device));
+  gps_comm_free(ctx);
+  ctx->comm = new gps_comm();
+  ctx->comm->rank = rank;
+  ctx->comm->world = world;
+  ncclUniqueId id;
+  memcpy(&id, uid128, sizeof id);
+  const ncclResult_t r = g_nccl.CommInitRank(&ctx->comm->comm, world, id, rank);
+  if (r != ncclSuccess) {
+    const int rc = gps_fail(ctx, GPS_ECUDA, "ncclCommInitRank: %s", g_nccl.GetErrorString(r));
+    delete ctx->comm;
+    ctx->comm = nullptr;
+    return rc;
+  }
+  return GPS_OK;
+}
+
+int gps_comm_info(gps_ctx* ctx, int* rank, int* world, int* nccl_version) {
+  if (!ctx) return GPS_EINVAL;
+  if (rank) *rank = ctx->comm ? ctx->comm->rank : 0;
+  if (world) *world = ctx->comm ? ctx->comm->world : 1;
+  if (nccl_version) {
+    *nccl_version = 0;
+    if (g_nccl.lib) g_nccl.GetVersion(nccl_version);
+  }
+  return GPS_OK;
+}
+
+int gps_comm_destroy(gps_ctx* ctx) {
+  if (!ctx) return GPS_EINVAL;
+  gps_comm_free(ctx);
+  return GPS_OK;
+}
+
+// in-place sum of a device buffer over the ranks (test hook and building block of the sharded helpers)
+int gps_comm_allreduce_sum(gps_ctx* ctx, double* buf, int64_t n) {
+  if (!ctx) return GPS_EINVAL;
+  if (!buf || n <= 0) return gps_fail(ctx, GPS_EINVAL, "allreduce: bad arguments");
+  GPS_CUDA(cudaSetDevice(ctx->device));
+  GPS_CHECK(gps_comm_allreduce(ctx, buf, (size_t)n));
+  return GPS_OK;
+}
+
+// Row-sharded FITC objective + gradient: this context holds a contiguous block of the world_n rows; the packed
+// accumulators of the three passes are all-reduced on the context's stream (replaces the three
+// all-reduces a host would otherwise issue between gps_fitc_pass1 / pass2 / pass3).
+int gps_fitc_eval_sharded(gps_ctx* ctx, const double* theta, const double* U, int M, double jitter, int score,
+                          int64_t world_n, double* obj, double* grad_theta, double* grad_U) {
+  if (!ctx) return GPS_EINVAL;
+  if (ctx->N == 0) return gps_fail(ctx, GPS_ESTATE, "fitc: call gps_set_data first");
+  if (!theta || !U || M <= 0 || world_n < ctx->N) return gps_fail(ctx, GPS_EINVAL, "fitc_eval_sharded: bad arguments");
+  if (score != GPS_CRPS && score != GPS_LOGS && score != GPS_NLML)
+    return gps_fail(ctx, GPS_EINVAL, "fitc_eval_sharded: crps / logs / nlml only (the block objectives run on one GPU)");
+  if (!ctx->comm) return gps_fail(ctx, GPS_ESTATE, "fitc_eval_sharded: call gps_comm_init first");
+  if (M < ctx->fitc_large_min_m && gps_fitc_fused_supports(ctx, M, score))
+    return gps_fitc_fused_eval(ctx, theta, U, M, jitter, score, world_n, gps_comm_allreduce, obj, grad_theta, grad_U);
+  return gps_fitc_large_eval_sharded(ctx, theta, U, M, jitter, score, world_n, gps_comm_allreduce, obj, grad_theta, grad_U);
+}
+
+}  // extern "C"

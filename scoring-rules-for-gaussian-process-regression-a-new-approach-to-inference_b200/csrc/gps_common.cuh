@@ -27,6 +27,8 @@ struct DevBuf {
 };
 
 struct gps_fitc_large;
+struct gps_fitc_fused;
+struct gps_comm;
 
 struct gps_ctx {
   int device = 0;
@@ -36,7 +38,7 @@ struct gps_ctx {
   std::string err;
   int64_t launches = 0;
   int sm_count = 148;
-  int fitc_variant = 1;               // 0: thread-per-row FITC passes, 1: tile (DMMA) formulation
+  int fitc_variant = 2;               // 0: thread-per-row FITC passes, 1: tile (DMMA) formulation, 2: fused three-kernel path (gps_fitc_fused.cu)
   long long* potf2_prof = nullptr;    // device buffer for clock64 phase stamps of the diagonal kernel (debug)
   int potf2_variant = 1;              // 0: register-cyclic diagonal kernel, 1: 32-blocked DMMA diagonal kernel
   int gemm_variant = 6;               // tile-GEMM policy (see gps_gemm.cu); switched by gps_dbg_set_variant
@@ -118,10 +120,13 @@ struct gps_ctx {
     DevBuf acc1, acc2, acc3;  // single-GPU accumulators
     bool begun = false, pass2_done = false, tile = true, loo_ok = false;
     bool large = false;   // last evaluation ran the matrix form (gps_fitc_large.cu)
+    bool fused = false;   // last evaluation ran the fused three-kernel path (gps_fitc_fused.cu)
     DevBuf accf;          // per-fold accumulators of the block objectives
     std::vector<double> host_out;
   } fitc;
   gps_fitc_large* fl = nullptr;   // matrix-form FITC state (M > 32)
+  gps_fitc_fused* fu = nullptr;   // fused three-kernel FITC state (M <= 31)
+  gps_comm* comm = nullptr;       // NCCL communicator of row-sharded runs (gps_comm.cu)
   int fitc_large_min_m = 33;      // M from which gps_fitc_eval uses the matrix form (debug knob)
 };
 
@@ -170,6 +175,23 @@ int gps_fitc_large_pass2(gps_ctx* ctx, const double* acc1, double* acc2, bool wa
 int gps_fitc_large_pass3(gps_ctx* ctx, const double* acc2, double* acc3);
 int gps_fitc_large_finish(gps_ctx* ctx, const double* acc2, const double* acc3, double* obj, double* grad_theta,
                           double* grad_U);
+// gps_fitc_fused.cu
+typedef int (*gps_allreduce_fn)(gps_ctx* ctx, double* buf, size_t n);   // in-place sum over the ranks, on ctx->stream
+bool gps_fitc_fused_supports(const gps_ctx* ctx, int M, int score);
+void gps_fitc_fused_free(gps_ctx* ctx);
+int gps_fitc_fused_eval(gps_ctx* ctx, const double* theta, const double* U, int M, double jitter, int score,
+                        int64_t world_n, gps_allreduce_fn allreduce, double* obj, double* grad_theta, double* grad_U);
+int gps_fitc_fused_descend(gps_ctx* ctx, double* theta, double* U, int M, double jitter, int score, double lr_theta,
+                           double lr_u, int iters, double* obj_trace);
+int gps_fitc_fused_loo(gps_ctx* ctx, double* dm, double* dv);
+int gps_fitc_fused_predict(gps_ctx* ctx, const double* dXs, int64_t T, double* dm, double* dv);
+int gps_launch_floor_us(gps_ctx* ctx, int launches, int reps, double* us);
+int gps_fitc_large_eval_sharded(gps_ctx* ctx, const double* theta, const double* U, int M, double jitter, int score,
+                                int64_t world_n, gps_allreduce_fn allreduce, double* obj, double* grad_theta,
+                                double* grad_U);
+// gps_comm.cu
+void gps_comm_free(gps_ctx* ctx);
+int gps_comm_allreduce(gps_ctx* ctx, double* buf, size_t n);
 // offsets (doubles) into ctx->params and rows of ctx->vecs
 constexpr int PAR_OBJ = 128;
 constexpr int PAR_GSUM = 136;

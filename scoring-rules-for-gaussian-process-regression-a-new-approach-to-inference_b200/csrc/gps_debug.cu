@@ -187,6 +187,11 @@ int gps_dbg_potf2_phases(gps_ctx* ctx, int64_t* cycles17) {
   return GPS_OK;
 }
 
+int gps_dbg_launch_floor(gps_ctx* ctx, int launches, int reps, double* us) {
+  if (!ctx || !us || launches < 0 || reps < 1) return GPS_EINVAL;
+  return gps_launch_floor_us(ctx, launches, reps, us);
+}
+
 int gps_dbg_gram(gps_ctx* ctx, const double* theta, double* K) {
   if (!ctx) return GPS_EINVAL;
   if (ctx->N == 0) return gps_fail(ctx, GPS_ESTATE, "dbg_gram: no data");

@@ -66,7 +66,22 @@ __global__ void fold_sum_kernel(const double* __restrict__ fv, int64_t stride, i
 
 }  // namespace
 
+static int full_dss_body(gps_ctx* ctx, double* par_obj, double* par_gsum, bool want_grad);
+
 int gps_full_dss(gps_ctx* ctx, double* par_obj, double* par_gsum, bool want_grad) {
+  const int rc = full_dss_body(ctx, par_obj, par_gsum, want_grad);
+  if (rc != GPS_OK && ctx->dss_fork) {
+    // error exit: the fold streams may still hold queued work that reads the parent's buffers; join them into
+    // the caller's stream so that nothing issued later on this context can overtake it
+    for (size_t f = 0; f < ctx->fold_lanes.size() && f < 4; ++f)
+      if (cudaEventRecord(ctx->dss_join[f], ctx->fold_lanes[f]->stream) == cudaSuccess)
+        cudaStreamWaitEvent(ctx->stream, ctx->dss_join[f], 0);
+    cudaGetLastError();
+  }
+  return rc;
+}
+
+static int full_dss_body(gps_ctx* ctx, double* par_obj, double* par_gsum, bool want_grad) {
   const int64_t N = ctx->N, Np = ctx->Np;
   const int D = ctx->D;
   constexpr int FOLDS = 4;

@@ -759,7 +759,7 @@ int gps_fitc_large_begin(gps_ctx* ctx, const double* theta, const double* U, int
   if (M > 4096) return gps_fail(ctx, GPS_EINVAL, "fitc: M=%d > 4096 not supported", M);
   GPS_CUDA(cudaSetDevice(ctx->device));
   auto& f = ctx->fitc;
-  f.begun = false; f.pass2_done = false; f.loo_ok = false; f.large = true;
+  f.begun = false; f.pass2_done = false; f.loo_ok = false; f.large = true; f.fused = false;
   GPS_CHECK(gps_ensure(ctx, ctx->params, PAR_LEN));
   if (!ctx->d_info) GPS_CUDA(cudaMalloc(&ctx->d_info, sizeof(int)));
   GPS_CHECK(setup(ctx, M));
@@ -947,6 +947,29 @@ int gps_fitc_large_eval(gps_ctx* ctx, const double* theta, const double* U, int 
   GPS_CHECK(gps_fitc_large_pass1(ctx, a1));
   GPS_CHECK(gps_fitc_large_pass2(ctx, a1, a2, want_grad));
   if (want_grad) GPS_CHECK(gps_fitc_large_pass3(ctx, a2, a3));
+  return gps_fitc_large_finish(ctx, a2, a3, obj, grad_theta, grad_U);
+}
+
+// row-sharded evaluation: the same chain with the packed accumulators summed over the ranks between the passes
+int gps_fitc_large_eval_sharded(gps_ctx* ctx, const double* theta, const double* U, int M, double jitter, int score,
+                                int64_t world_n, gps_allreduce_fn allreduce, double* obj, double* grad_theta,
+                                double* grad_U) {
+  if (M < 1 || M > 4096) return gps_fail(ctx, GPS_EINVAL, "fitc_eval_sharded: M=%d outside 1..4096", M);
+  GPS_CHECK(gps_fitc_large_begin(ctx, theta, U, M, jitter, score, world_n));
+  gps_fitc_large* fl = ctx->fl;
+  int64_t l1, l2, l3;
+  gps_fitc_large_acc_len(M, ctx->D, &l1, &l2, &l3);
+  GPS_CHECK(gps_ensure(ctx, fl->acc, (size_t)(l1 + l2 + l3)));
+  double *a1 = fl->acc.p, *a2 = a1 + l1, *a3 = a2 + l2;
+  const bool want_grad = grad_theta || grad_U;
+  GPS_CHECK(gps_fitc_large_pass1(ctx, a1));
+  GPS_CHECK(allreduce(ctx, a1, (size_t)l1));
+  GPS_CHECK(gps_fitc_large_pass2(ctx, a1, a2, want_grad));
+  GPS_CHECK(allreduce(ctx, a2, (size_t)l2));
+  if (want_grad) {
+    GPS_CHECK(gps_fitc_large_pass3(ctx, a2, a3));
+    GPS_CHECK(allreduce(ctx, a3, (size_t)l3));
+  }
   return gps_fitc_large_finish(ctx, a2, a3, obj, grad_theta, grad_U);
 }
 

@@ -151,4 +151,40 @@ int gps_chol_solve(gps_ctx* ctx, const double* B, const double* A, int64_t n, in
   return GPS_OK;
 }
 
+// out[m,n] = A[m,k] B[k,n] for arbitrary sizes (UVA pointers): zero-padded copies to the 128 tile, one task-list
+// launch of the DMMA tile GEMM, 2-D copy back.  Serves the same-signature twins of Q (KF:32-39),
+// cal_mean_and_cov (KF:121-126) and spgp_cal_mean_and_cov (K20:76-83), whose products the reference does with
+// torch.mm.
+int gps_matmul(gps_ctx* ctx, const double* A, const double* B, int64_t m, int64_t k, int64_t n, double* out) {
+  if (!ctx) return GPS_EINVAL;
+  if (!A || !B || !out || m <= 0 || k <= 0 || n <= 0) return gps_fail(ctx, GPS_EINVAL, "matmul: bad arguments");
+  GPS_CUDA(cudaSetDevice(ctx->device));
+  const int64_t Mp = gps_pad(m), Kp = gps_pad(k), Npp = gps_pad(n);
+  GPS_CHECK(gps_ensure(ctx, ctx->stage[0], (size_t)Mp * Kp));
+  GPS_CHECK(gps_ensure(ctx, ctx->stage[1], (size_t)Kp * Npp));
+  GPS_CHECK(gps_ensure(ctx, ctx->stage[2], (size_t)Mp * Npp));
+  GPS_CUDA(cudaMemsetAsync(ctx->stage[0].p, 0, (size_t)Mp * Kp * sizeof(double), ctx->stream));
+  GPS_CUDA(cudaMemsetAsync(ctx->stage[1].p, 0, (size_t)Kp * Npp * sizeof(double), ctx->stream));
+  GPS_CUDA(cudaMemcpy2DAsync(ctx->stage[0].p, Kp * sizeof(double), A, k * sizeof(double), k * sizeof(double), m,
+                             cudaMemcpyDefault, ctx->stream));
+  GPS_CUDA(cudaMemcpy2DAsync(ctx->stage[1].p, Npp * sizeof(double), B, n * sizeof(double), n * sizeof(double), k,
+                             cudaMemcpyDefault, ctx->stream));
+  std::vector<GemmTask> tasks;
+  for (int ti = 0; ti < Mp / GPS_TILE; ++ti)
+    for (int tj = 0; tj < Npp / GPS_TILE; ++tj) {
+      GemmTask t;
+      t.a_row = ti * GPS_TILE; t.b_row = tj * GPS_TILE; t.k0 = 0; t.k1 = (int)Kp;
+      t.c_row = ti * GPS_TILE; t.c_col = tj * GPS_TILE; t.flags = 0; t.pad = 0;
+      tasks.push_back(t);
+    }
+  GPS_CHECK(gps_upload_tasks2(ctx, tasks));
+  ctx->gemm_events_used = 0;
+  GPS_CHECK(gps_gemm_tasks(ctx, GEMM_KC_MC, ctx->stage[0].p, Kp, ctx->stage[1].p, Npp, ctx->stage[2].p, Npp, 1.0, 0.0,
+                           nullptr, false, ctx->d_tasks2, tasks.size()));
+  GPS_CUDA(cudaMemcpy2DAsync(out, n * sizeof(double), ctx->stage[2].p, Npp * sizeof(double), n * sizeof(double), m,
+                             cudaMemcpyDefault, ctx->stream));
+  GPS_CUDA(cudaStreamSynchronize(ctx->stream));
+  return GPS_OK;
+}
+
 }  // extern "C"

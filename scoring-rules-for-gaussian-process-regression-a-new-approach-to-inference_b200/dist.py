@@ -43,15 +43,22 @@ def allreduce_sum_(t, group=None):
 
 class ShardedFitc:
     """Row-sharded FITC evaluation.  `backend` holds THIS rank's rows and implements
-    fitc_eval_sharded(theta, U, score, world_n, allreduce) -> (obj, g_theta, g_U) — for
-    api.Context that is the three CUDA row passes with the all-reduces in between."""
+    fitc_eval_sharded(theta, U, score, world_n, allreduce) -> (obj, g_theta, g_U).
 
-    def __init__(self, backend, world_n, group=None):
+    library_comm=True (production, api.Context after `comm_init`): the three all-reduces are issued by
+    libgpscore itself on the context's stream (NCCL inside the call, no host synchronisation between the
+    passes).  Otherwise the staged protocol runs with torch.distributed doing the all-reduces (gloo in
+    the CPU tests, with a numpy stand-in for the compute)."""
+
+    def __init__(self, backend, world_n, group=None, library_comm=False):
         self.backend = backend
         self.world_n = int(world_n)
         self.group = group
+        self.library_comm = bool(library_comm)
 
     def eval(self, theta, U, score):
+        if self.library_comm:
+            return self.backend.fitc_eval_sharded(theta, U, score, self.world_n)
         return self.backend.fitc_eval_sharded(theta, U, score, self.world_n,
                                               lambda t: allreduce_sum_(t, self.group))
 

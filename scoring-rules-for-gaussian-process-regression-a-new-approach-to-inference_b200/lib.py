@@ -40,6 +40,13 @@ SIGNATURES = {
     "gps_fitc_pass2": (C.c_int, [_vp, _vp, _vp]),
     "gps_fitc_pass3": (C.c_int, [_vp, _vp, _vp]),
     "gps_fitc_finish": (C.c_int, [_vp, _vp, _vp, _dp, _dp, _dp]),
+    "gps_comm_set_library": (C.c_int, [C.c_char_p]),
+    "gps_comm_unique_id": (C.c_int, [_vp]),
+    "gps_comm_init": (C.c_int, [_vp, _vp, C.c_int, C.c_int]),
+    "gps_comm_info": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "gps_comm_destroy": (C.c_int, [_vp]),
+    "gps_comm_allreduce_sum": (C.c_int, [_vp, _vp, _i64]),
+    "gps_fitc_eval_sharded": (C.c_int, [_vp, _dp, _dp, C.c_int, C.c_double, C.c_int, _i64, _dp, _dp, _dp]),
     "gps_fitc_loo": (C.c_int, [_vp, _vp, _vp]),
     "gps_fitc_predict": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
     "gps_full_descend": (C.c_int, [_vp, _dp, C.c_int, C.c_double, C.c_int, _dp]),
@@ -47,6 +54,7 @@ SIGNATURES = {
     "gps_test_metrics": (C.c_int, [_vp, _vp, _vp, _vp, _i64, C.c_double, C.c_double, _dp]),
     "gps_ard": (C.c_int, [_vp, _vp, _i64, _vp, _i64, C.c_int, C.c_double, _dp, C.c_int, _vp]),
     "gps_chol_solve": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _vp]),
+    "gps_matmul": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _i64, _vp]),
     "gps_score": (C.c_int, [_vp, _vp, _vp, _vp, _i64, C.c_int, _dp]),
     "gps_grid_eval": (C.c_int, [_vp, _vp, _vp, C.c_int, _dp, _dp, _i64, C.c_int, _dp]),
 }
@@ -60,6 +68,7 @@ DEBUG_SIGNATURES = {
     "gps_dbg_potf2_phases": (C.c_int, [_vp, C.POINTER(C.c_int64)]),
     "gps_dbg_trace": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double)]),
     "gps_dbg_gram": (C.c_int, [_vp, _dp, _vp]),
+    "gps_dbg_launch_floor": (C.c_int, [_vp, C.c_int, C.c_int, _dp]),
 }
 
 _lib = None

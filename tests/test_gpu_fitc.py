@@ -176,10 +176,11 @@ def test_fitc_script_loop(ctx):
     assert relerr(inducing_x.detach().numpy(), U) <= 1e-6
 
 
-@pytest.mark.parametrize("m_ind", [5, 20, 32])
+@pytest.mark.parametrize("m_ind", [5, 16, 20, 24, 31, 32])
 def test_fitc_row_pass_formulations_agree(ctx, m_ind):
-    """thread-per-row passes (variant 0) and the tile/DMMA formulation (variant 1, default) are the same
-    computation: objective and all gradients agree to rounding."""
+    """thread-per-row passes (variant 0), the tile/DMMA formulation (variant 1) and the fused three-kernel
+    path (variant 2, default; M = 32 falls back to the tile kernels) are the same computation: objective and
+    all gradients agree to rounding."""
     from gpscore_b200 import synth
     X, y = synth.kin40k_like(900, seed=60)
     theta = synth.hyper_point("P2")
@@ -187,14 +188,15 @@ def test_fitc_row_pass_formulations_agree(ctx, m_ind):
     ctx.set_data(_dev(X), _dev(y))
     try:
         res = {}
-        for variant in (0, 1):
+        for variant in (0, 1, 2):
             ctx._check(ctx._lib.gps_dbg_set_variant(ctx._h, 2, variant))
             res[variant] = [ctx.fitc_eval(theta, U, s) for s in ("crps", "logs", "nlml")]
-        for a, b in zip(res[0], res[1]):
-            assert abs(a[0] - b[0]) <= 1e-11 * abs(a[0])
-            assert relerr(a[1], b[1]) <= 1e-9 and relerr(a[2], b[2]) <= 1e-9
+        for other in (1, 2):
+            for a, b in zip(res[0], res[other]):
+                assert abs(a[0] - b[0]) <= 1e-11 * abs(a[0]), other
+                assert relerr(a[1], b[1]) <= 1e-9 and relerr(a[2], b[2]) <= 1e-9, other
     finally:
-        ctx._check(ctx._lib.gps_dbg_set_variant(ctx._h, 2, 1))
+        ctx._check(ctx._lib.gps_dbg_set_variant(ctx._h, 2, 2))
 
 
 @pytest.mark.parametrize("kind", ["dss", "kc"])
