@@ -54,6 +54,12 @@ int gps_dbg_potf2_phases(gps_ctx* ctx, int64_t* cycles17);
  * latency-bound FITC M = 20, N = 10^4 point. */
 int gps_dbg_launch_floor(gps_ctx* ctx, int launches, int reps, double* us);
 
+/* Phase timeline of the last fused FITC evaluation (M <= 31): globaltimer nanoseconds, 16 slots per kernel
+ * (pass 1 at 0, pass 2 at 16, pass 3 at 32): +0 kernel start, +1 preamble done, +2 row loop done, +3 CTA partial
+ * formed (all by CTA 0), +4 total reduced (last CTA), +5 finishing step done (pass 3).  The first call arms the
+ * recording and returns zeros. */
+int gps_dbg_fused_phases(gps_ctx* ctx, int64_t* ns48);
+
 /* Training Gram K = ARD(X,X) + sn2 I of the current data set at theta, N x N (UVA out). */
 int gps_dbg_gram(gps_ctx* ctx, const double* theta, double* K);
 

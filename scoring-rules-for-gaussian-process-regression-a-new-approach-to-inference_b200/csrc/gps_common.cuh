@@ -186,6 +186,7 @@ int gps_fitc_fused_descend(gps_ctx* ctx, double* theta, double* U, int M, double
 int gps_fitc_fused_loo(gps_ctx* ctx, double* dm, double* dv);
 int gps_fitc_fused_predict(gps_ctx* ctx, const double* dXs, int64_t T, double* dm, double* dv);
 int gps_launch_floor_us(gps_ctx* ctx, int launches, int reps, double* us);
+int gps_fitc_fused_phases(gps_ctx* ctx, long long* out48);
 int gps_fitc_large_eval_sharded(gps_ctx* ctx, const double* theta, const double* U, int M, double jitter, int score,
                                 int64_t world_n, gps_allreduce_fn allreduce, double* obj, double* grad_theta,
                                 double* grad_U);

@@ -192,6 +192,11 @@ int gps_dbg_launch_floor(gps_ctx* ctx, int launches, int reps, double* us) {
   return gps_launch_floor_us(ctx, launches, reps, us);
 }
 
+int gps_dbg_fused_phases(gps_ctx* ctx, int64_t* ns48) {
+  if (!ctx || !ns48) return GPS_EINVAL;
+  return gps_fitc_fused_phases(ctx, reinterpret_cast<long long*>(ns48));
+}
+
 int gps_dbg_gram(gps_ctx* ctx, const double* theta, double* K) {
   if (!ctx) return GPS_EINVAL;
   if (ctx->N == 0) return gps_fail(ctx, GPS_ESTATE, "dbg_gram: no data");

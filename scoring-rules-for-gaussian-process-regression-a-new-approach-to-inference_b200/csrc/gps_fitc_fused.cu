@@ -27,6 +27,7 @@
 // dot product with every row rides along in the tile product for free (pass 1: y_i / sqrt(lam_i) -> v_y,
 // pass 2: c2 = T2' beta -> W_i . beta, and t_i -> beta_bar in the accumulation).
 #include <math.h>
+#include <string.h>
 
 #include "gps_common.cuh"
 #include "gps_exp.cuh"
@@ -42,6 +43,38 @@ constexpr double F_INV_SQRT_PI = 0.56418958354775628695;
 constexpr double F_INV_SQRT_2PI = 0.39894228040143267794;
 constexpr double F_INV_SQRT2 = 0.70710678118654752440;
 constexpr double F_HALF_LOG_2PI = 0.91893853320467274178;
+
+__device__ __forceinline__ void cp_async8(double* smem, const double* gmem, bool ok) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  const int n = ok ? 8 : 0;                                   // src-size 0: the 8 bytes are zero-filled
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(sa), "l"(gmem), "r"(n));
+}
+__device__ __forceinline__ void cp_async_commit_group();
+__device__ __forceinline__ void cp_async16(double* smem, const double* gmem) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem));
+}
+// K_uf tile of `rows` (16 or 32) data rows starting at r0 into smem [KP][rows + 4] (rows beyond N hold whatever the
+// padded buffer holds: every use is masked).  16-byte chunks: r0 and ldk are multiples of 8.
+template <int ROWS>
+__device__ __forceinline__ void fetch_k_tile(double* kt, const double* __restrict__ Kst, int64_t ldk, int64_t r0, int64_t N,
+                                             int M, int lane) {
+  constexpr int CPR = ROWS / 2;                               // chunks per m-row
+  if (r0 < N) {
+    for (int c = lane; c < M * CPR; c += 32) {
+      const int m = c / CPR, q = c - m * CPR;
+      cp_async16(kt + m * (ROWS + 4) + 2 * q, Kst + (int64_t)m * ldk + r0 + 2 * q);
+    }
+  }
+}
+// `cnt` doubles (a multiple of 2) starting at src (16-byte aligned) into dst; chunks dealt to the lanes from `lane0`
+__device__ __forceinline__ void fetch_span(double* dst, const double* __restrict__ src, int cnt, bool on, int lane, int lane0) {
+  if (on)
+    for (int c = (lane - lane0) & 31; 2 * c < cnt; c += 32) cp_async16(dst + 2 * c, src + 2 * c);
+}
+__device__ __forceinline__ void cp_async_commit_group() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int NPEND>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;\n" ::"n"(NPEND)); }
 
 __host__ __device__ constexpr int lda_of(int kp) {   // operand stride: conflict-free half-warp fragment loads
   int l = kp;
@@ -96,10 +129,28 @@ struct FusedArgs {
   double* out_dev;        // [2 + D + 2 + M*D]  obj | g_theta | g_U | info
   double* out_host;       // same, mapped host memory (may be null)
   int* info;
+  long long* prof;        // debug: globaltimer stamps of the phases (null = off), 16 slots per kernel
   int64_t N, ldk;
   int D, M, score, finish;   // finish: pass 3 also runs the finishing step (single GPU)
   double jitter, invN, world_n;
 };
+
+// pass 1 takes theta | U BY VALUE in its launch parameters when they fit (D + 2 + M D <= THU_INLINE doubles; 170 at
+// M = 20, D = 8): no staging copy, no extra stream operation in front of the evaluation
+constexpr int THU_INLINE = 400;
+struct FusedArgsP1 {
+  FusedArgs a;
+  int inline_thu;
+  double thu[THU_INLINE];
+};
+
+__device__ __forceinline__ void stamp(const FusedArgs& a, int slot) {
+  if (a.prof) {
+    long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    a.prof[slot] = t;
+  }
+}
 
 __host__ __device__ inline int len1_of(int MP) { return MP * MP; }
 __host__ __device__ inline int len2_of(int MP) { return MP * MP + 1; }
@@ -107,30 +158,46 @@ __host__ __device__ inline int len3_of(int MP, int DT) { return MP * MP + MP * D
 
 // ---- small dense products on DMMA: C[i][j] = alpha * sum_k opA(i,k) opB(k,j) + cbeta * C[i][j] --------------------
 // A, B: MP x MP in shared memory, tight stride MP.  Output tiles are dealt round-robin to the CTA's warps.
+// __noinline__: the preambles and the finishing step call it ~25 times; one shared copy stays in the instruction
+// cache, whereas 25 inlined copies are code that runs once (those phases are instruction-fetch bound)
 template <int MT, bool TA, bool TB>
-__device__ __forceinline__ void smm(const double* A, const double* B, double* C, int ldc, int ncols, double alpha,
-                                    double cbeta, int warp, int lane) {
+__device__ __noinline__ void smm(const double* A, const double* B, double* C, int ldc, int ncols, double alpha,
+                                 double cbeta, int warp, int lane) {
   constexpr int MP = 8 * MT;
+  constexpr int TPW = (MT * MT + FW - 1) / FW;          // output tiles per warp: their DMMA chains are interleaved
   const int g = lane >> 2, t = lane & 3;
-  for (int idx = warp; idx < MT * MT; idx += FW) {
-    const int i = idx / MT, j = idx - i * MT;
-    double c0 = 0.0, c1 = 0.0;
+  double c[TPW][2];
+  int ti[TPW], tj[TPW];
 #pragma unroll
-    for (int s = 0; s < 2 * MT; ++s) {
-      const int k = 4 * s + t;
-      const double a = TA ? A[k * MP + 8 * i + g] : A[(8 * i + g) * MP + k];
-      const double b = TB ? B[(8 * j + g) * MP + k] : B[k * MP + 8 * j + g];
-      dmma(c0, c1, a, b);
+  for (int q = 0; q < TPW; ++q) {
+    const int idx = warp + q * FW;
+    ti[q] = idx < MT * MT ? idx / MT : 0;
+    tj[q] = idx < MT * MT ? idx - (idx / MT) * MT : 0;
+    c[q][0] = c[q][1] = 0.0;
+  }
+#pragma unroll
+  for (int s = 0; s < 2 * MT; ++s) {
+    const int k = 4 * s + t;
+#pragma unroll
+    for (int q = 0; q < TPW; ++q) {
+      const double a = TA ? A[k * MP + 8 * ti[q] + g] : A[(8 * ti[q] + g) * MP + k];
+      const double b = TB ? B[(8 * tj[q] + g) * MP + k] : B[k * MP + 8 * tj[q] + g];
+      dmma(c[q][0], c[q][1], a, b);
     }
-    const int r = 8 * i + g, cc = 8 * j + 2 * t;
-    if (cc < ncols) C[r * ldc + cc] = alpha * c0 + (cbeta != 0.0 ? cbeta * C[r * ldc + cc] : 0.0);
-    if (cc + 1 < ncols) C[r * ldc + cc + 1] = alpha * c1 + (cbeta != 0.0 ? cbeta * C[r * ldc + cc + 1] : 0.0);
+  }
+#pragma unroll
+  for (int q = 0; q < TPW; ++q) {
+    if (warp + q * FW < MT * MT) {
+      const int r = 8 * ti[q] + g, cc = 8 * tj[q] + 2 * t;
+      if (cc < ncols) C[r * ldc + cc] = alpha * c[q][0] + (cbeta != 0.0 ? cbeta * C[r * ldc + cc] : 0.0);
+      if (cc + 1 < ncols) C[r * ldc + cc + 1] = alpha * c[q][1] + (cbeta != 0.0 ? cbeta * C[r * ldc + cc + 1] : 0.0);
+    }
   }
 }
 
 // y[i] = sum_k op(A)(i,k) x[k]   (threads < MP)
 template <int MP, bool TA>
-__device__ __forceinline__ void smv(const double* A, const double* x, double* y, int tid) {
+__device__ __noinline__ void smv(const double* A, const double* x, double* y, int tid) {
   if (tid < MP) {
     double s = 0.0;
 #pragma unroll 8
@@ -159,6 +226,10 @@ __device__ __forceinline__ void chol_adjoint_smm(const double* L, const double* 
   smm<MT, true, false>(Linv, T, Abar, MP, MP, 0.5, 0.0, warp, lane);    // Abar = 1/2 L^-T T
   __syncthreads();
 }
+
+// (A loop-over-shared-memory Cholesky / triangular inverse of ~60 instructions was tried in place of the
+// register-resident, fully unrolled ones of gps_fitc_small.cuh, to cut the instruction-fetch cost of code that runs
+// once per kernel: its dependent LDS -> DFMA -> STS chains made the preambles 2.6x SLOWER (7.5 -> 19.7 us) — dropped.)
 
 // ---- reduce-scatter over the 8 lane groups (lane bits 2..4) ----------------------------------------------------
 // v[2 gi + e] holds this lane's share for tile row 8 gi + 2 t + e; on return lane (g, t) holds the full sum of
@@ -231,26 +302,39 @@ __device__ __forceinline__ void tri_accumulate(double (&acc)[C::NTRI][2], const 
 }
 
 // ---- CTA partial -> group partial -> total, by the last CTA to arrive at each level --------------------------------
-// Returns true in the CTA that completed the total (its `acc` is final and visible to that CTA).
+// Returns true in the CTA that completed the total (its `acc` is final and visible to that CTA).  Partials are
+// stored with an even stride and summed with 16-byte loads, all loads of a step in flight before the first add
+// (the sums are latency-bound: each level is store -> fence -> ticket -> fence -> load).  Groups are 8 CTAs, 16 on
+// grids beyond 128 CTAs; the order of every sum is fixed by the grid, so results are reproducible bit for bit.
+__device__ __forceinline__ int group_size(int G) { return G > 128 ? 2 * GRP : GRP; }
+
 __device__ __forceinline__ bool ticket_reduce(const double* __restrict__ cta_vals_smem, int len, double* part,
                                               double* gpart, int* cnt, double* acc, int tid) {
   __shared__ int s_flag;
   const int b = blockIdx.x, G = gridDim.x;
-  const int grp = b / GRP, ngrp = (G + GRP - 1) / GRP;
-  const int gsz = min(GRP, G - grp * GRP);
-  for (int e = tid; e < len; e += FT) part[(int64_t)b * len + e] = cta_vals_smem[e];
+  const int gs = group_size(G);
+  const int grp = b / gs, ngrp = (G + gs - 1) / gs;
+  const int gsz = min(gs, G - grp * gs);
+  const int lenp = (len + 1) & ~1, nv = lenp >> 1;          // even stride: 16-byte aligned rows
+  for (int e = tid; e < lenp; e += FT) part[(int64_t)b * lenp + e] = (e < len) ? cta_vals_smem[e] : 0.0;
   __threadfence();
   __syncthreads();
   if (tid == 0) s_flag = (atomicAdd(&cnt[1 + grp], 1) == gsz - 1);
   __syncthreads();
   if (!s_flag) return false;
   __threadfence();
-  for (int e = tid; e < len; e += FT) {
-    double s = 0.0;
+  {
+    const double2* src = reinterpret_cast<const double2*>(part + (int64_t)grp * gs * lenp);
+    double2* dst = reinterpret_cast<double2*>(gpart + (int64_t)grp * lenp);
+    for (int e = tid; e < nv; e += FT) {
+      double2 v[2 * GRP];
 #pragma unroll
-    for (int k = 0; k < GRP; ++k)
-      if (k < gsz) s += __ldcg(part + (int64_t)(grp * GRP + k) * len + e);
-    gpart[(int64_t)grp * len + e] = s;
+      for (int k = 0; k < 2 * GRP; ++k) v[k] = (k < gsz) ? __ldcg(src + (int64_t)k * nv + e) : make_double2(0.0, 0.0);
+      double2 s = v[0];
+#pragma unroll
+      for (int k = 1; k < 2 * GRP; ++k) { s.x += v[k].x; s.y += v[k].y; }
+      dst[e] = s;
+    }
   }
   __threadfence();
   __syncthreads();
@@ -261,11 +345,20 @@ __device__ __forceinline__ bool ticket_reduce(const double* __restrict__ cta_val
   __syncthreads();
   if (!s_flag) return false;
   __threadfence();
-  for (int e = tid; e < len; e += FT) {
-    double s = 0.0;
-#pragma unroll 8
-    for (int k = 0; k < ngrp; ++k) s += __ldcg(gpart + (int64_t)k * len + e);
-    acc[e] = s;
+  {
+    const double2* src = reinterpret_cast<const double2*>(gpart);
+    for (int e = tid; e < nv; e += FT) {
+      double2 s = make_double2(0.0, 0.0);
+      for (int k0 = 0; k0 < ngrp; k0 += 16) {
+        double2 v[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) v[k] = (k0 + k < ngrp) ? __ldcg(src + (int64_t)(k0 + k) * nv + e) : make_double2(0.0, 0.0);
+#pragma unroll
+        for (int k = 0; k < 16; ++k) { s.x += v[k].x; s.y += v[k].y; }
+      }
+      if (2 * e < len) acc[2 * e] = s.x;
+      if (2 * e + 1 < len) acc[2 * e + 1] = s.y;
+    }
   }
   if (tid == 0) cnt[0] = 0;
   __threadfence();
@@ -301,7 +394,8 @@ __device__ __forceinline__ double sym_lower(const double* __restrict__ A, int MP
 // pass 1
 // =====================================================================================================================
 template <class C>
-__global__ void __launch_bounds__(FT, 2) fused_p1_kernel(FusedArgs a) {
+__global__ void __launch_bounds__(FT, 3) fused_p1_kernel(const __grid_constant__ FusedArgsP1 ap) {
+  const FusedArgs& a = ap.a;
   constexpr int MP = C::MP, KS = C::KS, MT = C::MT, DT = C::DT, LDA = C::LDA, LDU = C::LDU;
   extern __shared__ __align__(16) double sh[];
   double* par = sh;                       // [24]   ea, sn2, invl[DT]
@@ -311,22 +405,28 @@ __global__ void __launch_bounds__(FT, 2) fused_p1_kernel(FusedArgs a) {
   double* B1 = B0 + MP * MP;              // [MP][MP]
   double* Li = B1 + MP * MP;              // [MP]
   double* scr = Li + MP;                  // [FW][2][TR]
+  double* xtl = scr + FW * 2 * TR;        // [FW][2][TR][LDU]  double-buffered raw X tiles (cp.async)
+  double* ytl = xtl + FW * 2 * TR * LDU;  // [FW][2][TR]       ... and their targets
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
   const int D = a.D, M = a.M;
   const FL fl(MP, D);
+  const bool st0 = blockIdx.x == 0 && tid == 0;
+  if (st0) stamp(a, 0);
   // ---- preamble: kernel parameters, K_uu, L_A, L_A^-1 --------------------------------------------------------------
+  if (st0) *a.info = 0;                   // only CTA 0 ever raises the flag (below): no memset in front of the launch
+  const double* thU = ap.inline_thu ? ap.thu : a.thU;
   if (tid < 24) {
     double v = 0.0;
-    if (tid == 0) v = exp(a.thU[0]);
-    else if (tid == 1) v = exp(a.thU[D + 1]);
-    else if (tid - 2 < D) v = exp(-a.thU[1 + (tid - 2)]);
+    if (tid == 0) v = exp(thU[0]);
+    else if (tid == 1) v = exp(thU[D + 1]);
+    else if (tid - 2 < D) v = exp(-thU[1 + (tid - 2)]);
     par[tid] = v;
   }
   __syncthreads();
   const double ea = par[0], sn2 = par[1];
   for (int e = tid; e < C::KP * LDU; e += FT) {
     const int m = e / LDU, d = e - m * LDU;
-    Us[e] = (m < M && d < D) ? a.thU[D + 2 + m * D + d] * par[2 + d] : 0.0;
+    Us[e] = (m < M && d < D) ? thU[D + 2 + m * D + d] * par[2 + d] : 0.0;
   }
   __syncthreads();
   for (int e = tid; e < MP * MP; e += FT) {
@@ -369,6 +469,7 @@ __global__ void __launch_bounds__(FT, 2) fused_p1_kernel(FusedArgs a) {
     }
   }
   __syncthreads();
+  if (st0) stamp(a, 1);
   // ---- row pass ---------------------------------------------------------------------------------------------------------
   const int iE = MT - 1, gE = M & 7;
   double* sc = scr + warp * 2 * TR;
@@ -380,7 +481,32 @@ __global__ void __launch_bounds__(FT, 2) fused_p1_kernel(FusedArgs a) {
   for (int d = 0; d < DT; ++d) invl[d] = par[2 + d];
   const int64_t N = a.N;
   double* lamg = a.rowv;
-  for (int64_t r0 = ((int64_t)blockIdx.x * FW + warp) * TR; r0 < N; r0 += (int64_t)gridDim.x * FW * TR) {
+  // X tiles arrive through an 8-byte cp.async double buffer per warp: the loads of tile n + 1 are in flight while
+  // tile n is processed (the row loop is otherwise exposed to the full HBM latency once per tile)
+  double* xt = xtl + warp * 2 * TR * LDU;
+  for (int e = lane; e < 2 * TR * LDU; e += 32) xt[e] = 0.0;            // pad columns d >= D stay zero
+  __syncwarp();
+  const int64_t rstep = (int64_t)gridDim.x * FW * TR;
+  auto fetch_tile = [&](int64_t r0, int buf) {
+    if (r0 < N) {
+      const double* src = a.X + r0 * D;
+      const int64_t left = (N - r0) * D;
+      for (int c = lane; c < TR * D; c += 32) {
+        const int row = c / D, d = c - row * D;
+        cp_async8(xt + (buf * TR + row) * LDU + d, src + (c < left ? c : 0), c < left);
+      }
+      fetch_span(ytl + (warp * 2 + buf) * TR, a.y + r0, TR, true, lane, 0);   // y is zero-padded to the 128 tile
+    }
+    cp_async_commit_group();
+  };
+  int buf = 0;
+  fetch_tile(((int64_t)blockIdx.x * FW + warp) * TR, 0);
+  for (int64_t r0 = ((int64_t)blockIdx.x * FW + warp) * TR; r0 < N; r0 += rstep) {
+    fetch_tile(r0 + rstep, buf ^ 1);
+    cp_async_wait_group<1>();
+    __syncwarp();
+    const double* xb = xt + buf * TR * LDU;
+    buf ^= 1;
     double vT[4][MT][2];
     double q8[8];
 #pragma unroll
@@ -389,7 +515,7 @@ __global__ void __launch_bounds__(FT, 2) fused_p1_kernel(FusedArgs a) {
       const bool live = row < N;
       double xs[DT];
 #pragma unroll
-      for (int d = 0; d < DT; ++d) xs[d] = (live && d < D) ? a.X[row * D + d] * invl[d] : 0.0;
+      for (int d = 0; d < DT; ++d) xs[d] = xb[(8 * gi + g) * LDU + d] * invl[d];
       double kb[KS];
 #pragma unroll
       for (int s = 0; s < KS; ++s) {
@@ -420,7 +546,7 @@ __global__ void __launch_bounds__(FT, 2) fused_p1_kernel(FusedArgs a) {
     const bool olive = orow < N;
     const double lam = ea + sn2 - q;
     const double rsq = olive ? 1.0 / sqrt(lam) : 0.0;
-    const double yv = olive ? a.y[orow] : 0.0;
+    const double yv = olive ? ytl[(warp * 2 + (buf ^ 1)) * TR + rho] : 0.0;    // (buf was flipped after the wait)
     if (olive) lamg[orow] = lam;
     sc[rho] = rsq;
     sc[TR + rho] = yv * rsq;
@@ -445,33 +571,41 @@ __global__ void __launch_bounds__(FT, 2) fused_p1_kernel(FusedArgs a) {
   }
   // ---- reduction ------------------------------------------------------------------------------------------------------
   __syncthreads();
+  if (st0) stamp(a, 2);
   for (int e = tid; e < MP * MP; e += FT) B0[e] = 0.0;
   __syncthreads();
   tri_frags_to_smem<C>(cacc, B0, warp, lane);
-  ticket_reduce(B0, len1_of(MP), a.part, a.gpart, a.cnt, a.acc1, tid);
+  if (st0) stamp(a, 3);
+  if (ticket_reduce(B0, len1_of(MP), a.part, a.gpart, a.cnt, a.acc1, tid) && tid == 0) stamp(a, 4);
 }
 
 // =====================================================================================================================
 // pass 2
 // =====================================================================================================================
 template <class C>
-__global__ void __launch_bounds__(FT, 2) fused_p2_kernel(FusedArgs a) {
+__global__ void __launch_bounds__(FT, 3) fused_p2_kernel(FusedArgs a) {
   constexpr int MP = C::MP, KS = C::KS, MT = C::MT, LDA = C::LDA;
   extern __shared__ __align__(16) double sh[];
   double* Aop = sh;                       // [MP][LDA]   T2 with c2 in row M
-  double* B0 = Aop + MP * LDA;            // C -> L_C
-  double* B1 = B0 + MP * MP;              // L_C^-1
-  double* B2 = B1 + MP * MP;              // L_A^-1
-  double* B3 = B2 + MP * MP;              // T2
-  double* Li = B3 + MP * MP;              // [MP]
+  double* Li = Aop + MP * LDA;            // [MP]
   double* vy = Li + MP;                   // [MP]
   double* beta = vy + MP;                 // [MP]
   double* c2 = beta + MP;                 // [MP]
   double* scr = c2 + MP;                  // [FW][3][TR]
   double* red = scr + FW * 3 * TR;        // [32]
+  double* rvl = red + 32;                 // [FW][2][2][TR]  lambda and y of the double-buffered tiles
+  // one region, two lives: the preamble's four M x M matrices, then the double-buffered K_uf tiles of the row loop
+  // (and the CTA partial after it) — keeps the kernel at three CTAs per SM
+  double* B0 = rvl + FW * 4 * TR;         // C -> L_C
+  double* B1 = B0 + MP * MP;              // L_C^-1
+  double* B2 = B1 + MP * MP;              // L_A^-1
+  double* B3 = B2 + MP * MP;              // T2
+  double* ktl = B0;                       // [FW][2][KP][TR + 4]  K_uf tiles (cp.async)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
   const int D = a.D, M = a.M;
   const FL fl(MP, D);
+  const bool st0 = blockIdx.x == 0 && tid == 0;
+  if (st0) stamp(a, 16);
   // ---- preamble: C = I + acc1, L_C, L_C^-1, beta, T2 = L_C^-1 L_A^-1, c2 = T2' beta ------------------------------------
   for (int e = tid; e < MP * MP; e += FT) {
     const int r = e / MP, c = e - r * MP;
@@ -513,6 +647,7 @@ __global__ void __launch_bounds__(FT, 2) fused_p2_kernel(FusedArgs a) {
     }
   }
   __syncthreads();
+  if (st0) stamp(a, 17);
   // ---- row pass ---------------------------------------------------------------------------------------------------------
   const int iE = MT - 1, gE = M & 7;
   double* sc = scr + warp * 3 * TR;
@@ -529,7 +664,25 @@ __global__ void __launch_bounds__(FT, 2) fused_p2_kernel(FusedArgs a) {
   double* tbg = a.rowv + 3 * ld;
   double* alg = a.rowv + 4 * ld;
   double* dg = a.rowv + 5 * ld;
-  for (int64_t r0 = ((int64_t)blockIdx.x * FW + warp) * TR; r0 < N; r0 += (int64_t)gridDim.x * FW * TR) {
+  constexpr int LDK2 = TR + 4;
+  double* ktw = ktl + warp * 2 * C::KP * LDK2;
+  const int64_t rstep = (int64_t)gridDim.x * FW * TR;
+  int buf = 0;
+  double* rvw = rvl + warp * 4 * TR;
+  auto fetch2 = [&](int64_t r0, int b) {
+    fetch_k_tile<TR>(ktw + b * C::KP * LDK2, a.Kst, ld, r0, N, M, lane);
+    fetch_span(rvw + b * 2 * TR, lamg + r0, TR, r0 < N, lane, 0);
+    fetch_span(rvw + b * 2 * TR + TR, a.y + r0, TR, r0 < N, lane, 16);
+    cp_async_commit_group();
+  };
+  fetch2(((int64_t)blockIdx.x * FW + warp) * TR, 0);
+  for (int64_t r0 = ((int64_t)blockIdx.x * FW + warp) * TR; r0 < N; r0 += rstep) {
+    fetch2(r0 + rstep, buf ^ 1);
+    cp_async_wait_group<1>();
+    __syncwarp();
+    const double* kt = ktw + buf * C::KP * LDK2;
+    const double* rv = rvw + buf * 2 * TR;
+    buf ^= 1;
     double wT[4][MT][2];
     double r8[8];
 #pragma unroll
@@ -540,7 +693,7 @@ __global__ void __launch_bounds__(FT, 2) fused_p2_kernel(FusedArgs a) {
 #pragma unroll
       for (int s = 0; s < KS; ++s) {
         const int m = 4 * s + t;
-        kb[s] = (live && m < M) ? a.Kst[(int64_t)m * ld + row] : 0.0;
+        kb[s] = (live && m < M) ? kt[m * LDK2 + 8 * gi + g] : 0.0;
       }
       tile_product<C, true>(Aop, kb, g, t, wT[gi]);
       double s0 = 0.0, s1 = 0.0;
@@ -565,7 +718,7 @@ __global__ void __launch_bounds__(FT, 2) fused_p2_kernel(FusedArgs a) {
     double rbar = 0.0, tbar = 0.0;
     if (olive) {
       const double wb = sc[2 * TR + rho];
-      const double lam = lamg[orow], yi = a.y[orow];
+      const double lam = rv[rho], yi = rv[TR + rho];
       const double il = 1.0 / lam;
       const double d = il - r * il * il;
       const double alpha = (yi - wb) * il;
@@ -620,13 +773,15 @@ __global__ void __launch_bounds__(FT, 2) fused_p2_kernel(FusedArgs a) {
   }
   // ---- reduction ------------------------------------------------------------------------------------------------------
   __syncthreads();
+  if (st0) stamp(a, 18);
   for (int e = tid; e < MP * MP + 1; e += FT) B0[e] = 0.0;     // B0 | B1 are contiguous: MP*MP + 1 doubles fit
   __syncthreads();
   tri_frags_to_smem<C>(racc, B0, warp, lane);
   const double o = block_sum(obj, red);
   if (tid == 0) B0[MP * MP] = o;
   __syncthreads();
-  ticket_reduce(B0, len2_of(MP), a.part, a.gpart, a.cnt, a.acc2, tid);
+  if (st0) stamp(a, 19);
+  if (ticket_reduce(B0, len2_of(MP), a.part, a.gpart, a.cnt, a.acc2, tid) && tid == 0) stamp(a, 20);
 }
 
 // =====================================================================================================================
@@ -680,6 +835,7 @@ __device__ void fused_finish(const FusedArgs& a, double* sh, int tid, int warp, 
     S0[tid] = in ? __ldcg(S0g + tid) : 0.0;
   }
   __syncthreads();
+  if (tid == 0) stamp(a, 40);
   smv<MP, true>(LCi, beta, b1, tid);      // b1 = L_C^-T beta
   smv<MP, false>(LC, bbar, lcb, tid);     // L_C beta_bar
   smm<MT, false, true>(Rm, LC, T1, MP, MP, 1.0, 0.0, warp, lane);       // T1 = R L_C'
@@ -696,6 +852,7 @@ __device__ void fused_finish(const FusedArgs& a, double* sh, int tid, int warp, 
     S[e] += b1[r] * lcb[c] + vyb[r] * vy[c];
   }
   __syncthreads();
+  if (tid == 0) stamp(a, 41);
   smm<MT, true, false>(LAi, S, T1, MP, MP, 1.0, 0.0, warp, lane);       // L_A^-T S
   __syncthreads();
   for (int e = tid; e < MP * MP; e += FT) {
@@ -709,65 +866,88 @@ __device__ void fused_finish(const FusedArgs& a, double* sh, int tid, int warp, 
     T1[e] = (r < M && c < M) ? S[e] * __ldcg(a.fs + fl.kuu + e) : 0.0;  // G2 = A_bar o K_uu
   }
   __syncthreads();
-  const double* us = a.fs + fl.us;            // [MP][16]
-  const double* par = a.fs + fl.par;
-  const double ea = __ldcg(par), sn2 = __ldcg(par + 1);
-  const double sum_lb = __ldcg(xq + DT);
-  double* out = a.out_dev;
-  double sa = 0.0;
-  for (int e = tid; e < MP * MP; e += FT) sa += T1[e];
-  for (int m = tid; m < MP; m += FT) sa += S0[m];
-  sa = block_sum(sa, red);
+  if (tid == 0) stamp(a, 42);
   if (tid == 0) {
-    double obj = __ldcg(a.acc2 + MP * MP);
-    if (a.score == GPS_NLML) {
-      obj += 0.5 * a.world_n * 1.83787706640934548356;                  // N/2 log 2 pi
-      for (int m = 0; m < M; ++m) obj += log(LC[m * MP + m]);           // + sum log diag(L_C)
-    }
-    out[0] = obj;
-    out[1] = ea * sum_lb + sa;
-    out[1 + D + 1] = sn2 * sum_lb;
-    if (a.out_host) {
-      a.out_host[0] = obj;
-      a.out_host[1] = out[1];
-      a.out_host[1 + D + 1] = out[1 + D + 1];
-    }
-  }
-  for (int d = 0; d < D; ++d) {
-    double sb = 0.0;
-    for (int e = tid; e < MP * MP; e += FT) {
-      const int i = e / MP, j = e - i * MP;
-      const double df = __ldcg(us + i * 16 + d) - __ldcg(us + j * 16 + d);
-      sb = fma(T1[e], df * df, sb);
-    }
-    for (int m = tid; m < M; m += FT) {
-      const double u = __ldcg(us + m * 16 + d);
-      sb += u * u * S0[m] - 2.0 * u * __ldcg(Pm + m * DT + d);
-    }
-    sb = block_sum(sb, red);
-    if (tid == 0) {
-      const double v = sb + __ldcg(xq + d);
-      out[2 + d] = v;
-      if (a.out_host) a.out_host[2 + d] = v;
-    }
-  }
-  for (int e = tid; e < M * D; e += FT) {
-    const int m = e / D, d = e - m * D;
-    const double u = __ldcg(us + m * 16 + d);
-    double tt = 0.0;
-    for (int j = 0; j < M; ++j) tt = fma(T1[m * MP + j], u - __ldcg(us + j * 16 + d), tt);
-    const double v = -__ldcg(par + 2 + d) * (u * S0[m] - __ldcg(Pm + m * DT + d)) - 2.0 * __ldcg(par + 2 + d) * tt;
-    out[1 + D + 2 + e] = v;
-    if (a.out_host) a.out_host[1 + D + 2 + e] = v;
+    double ld = 0.0;
+    if (a.score == GPS_NLML)
+      for (int m = 0; m < M; ++m) ld += log(LC[m * MP + m]);                 // sum log diag(L_C)
+    red[0] = ld;
   }
   __syncthreads();
-  if (tid == 0) {
-    const double code = (double)atomicAdd(a.info, 0);
-    out[1 + D + 2 + M * D] = code;
-    if (a.out_host) {
-      __threadfence_system();
-      a.out_host[1 + D + 2 + M * D] = code;
+  const double logdet_c = red[0];
+  // the gradient loops below touch us / P / par many times: stage them over the (now dead) matrices LAi .. Zm
+  // (7 MP^2 >= 16 MP + MP DT + 24 + DT + 1 doubles for every supported MP)
+  double* us = LAi;                           // [MP][16]
+  double* Ps = us + MP * 16;                  // [MP][DT]
+  double* par = Ps + MP * DT;                 // [24]
+  double* xqs = par + 24;                     // [DT + 1]
+  static_assert(7 * MP * MP >= MP * 16 + MP * DT + 24 + DT + 1, "finish staging must fit in the dead matrices");
+  for (int e = tid; e < MP * 16; e += FT) us[e] = __ldcg(a.fs + fl.us + e);
+  for (int e = tid; e < MP * DT; e += FT) Ps[e] = __ldcg(Pm + e);
+  if (tid < 24) par[tid] = __ldcg(a.fs + fl.par + tid);
+  if (tid <= DT) xqs[tid] = __ldcg(xq + tid);
+  __syncthreads();
+  const double ea = par[0], sn2 = par[1];
+  const double sum_lb = xqs[DT];
+  double* out = a.out_dev;
+  // one sweep over G2 = A_bar o K_uu for the amplitude sum and all D length-scale sums (D + 1 accumulators per
+  // thread, one block reduction), instead of D + 1 sweeps with two barriers each
+  double acc[DT + 1];
+#pragma unroll
+  for (int d = 0; d <= DT; ++d) acc[d] = 0.0;
+  for (int e = tid; e < MP * MP; e += FT) {
+    const int i = e / MP, j = e - i * MP;
+    const double g2 = T1[e];
+    acc[DT] += g2;
+#pragma unroll
+    for (int d = 0; d < DT; ++d) {
+      const double df = us[i * 16 + d] - us[j * 16 + d];
+      acc[d] = fma(g2, df * df, acc[d]);
     }
+  }
+  for (int m = tid; m < M; m += FT) {
+    acc[DT] += S0[m];
+#pragma unroll
+    for (int d = 0; d < DT; ++d) {
+      const double u = us[m * 16 + d];
+      acc[d] += u * u * S0[m] - 2.0 * u * Ps[m * DT + d];
+    }
+  }
+  double* wred = S;                            // [FW][DT + 1]  (A_bar is folded into G2: S is free)
+#pragma unroll
+  for (int d = 0; d <= DT; ++d) {
+    const double v = warp_sum(acc[d]);
+    if (lane == 0) wred[warp * (DT + 1) + d] = v;
+  }
+  __syncthreads();
+  if (tid <= DT) {
+    double v = 0.0;
+#pragma unroll
+    for (int w = 0; w < FW; ++w) v += wred[w * (DT + 1) + tid];
+    if (tid == DT) {
+      double obj = __ldcg(a.acc2 + MP * MP);
+      if (a.score == GPS_NLML) obj += 0.5 * a.world_n * 1.83787706640934548356 + logdet_c;   // N/2 log 2 pi + sum log diag(L_C)
+      out[0] = obj;
+      out[1] = ea * sum_lb + v;
+      out[1 + D + 1] = sn2 * sum_lb;
+    } else if (tid < D) {
+      out[2 + tid] = v + xqs[tid];
+    }
+  }
+  if (tid == 0) stamp(a, 43);
+  for (int e = tid; e < M * D; e += FT) {
+    const int m = e / D, d = e - m * D;
+    const double u = us[m * 16 + d];
+    double tt = 0.0;
+    for (int j = 0; j < M; ++j) tt = fma(T1[m * MP + j], u - us[j * 16 + d], tt);
+    out[1 + D + 2 + e] = -par[2 + d] * (u * S0[m] - Ps[m * DT + d]) - 2.0 * par[2 + d] * tt;
+  }
+  if (tid == 0) out[1 + D + 2 + M * D] = (double)atomicAdd(a.info, 0);
+  __syncthreads();
+  // results to mapped host memory in one coalesced sweep (single stores from one thread crawl over PCIe)
+  if (a.out_host) {
+    const int nout = 2 + D + 2 + M * D;
+    for (int e = tid; e < nout; e += FT) a.out_host[e] = out[e];
   }
 }
 
@@ -785,10 +965,15 @@ __global__ void __launch_bounds__(FT, 2) fused_p3_kernel(FusedArgs a) {
   double* vec = E + 3 * MP * LDA;         // a1, a2, c1, invl : [4][MP]  (invl: DT <= MP entries)
   double* scr = vec + 4 * MP;             // [FW][R3]
   double* red = scr + FW * R3;            // [32]
-  double* W0 = red + 32;                  // preamble / reduction / finish workspace
+  double* ktl = red + 32;                 // [FW][2][KP][R3 + 4]  double-buffered K_uf tiles (cp.async)
+  double* rvl = ktl + FW * 2 * C::KP * (R3 + 4);   // [FW][2][5][R3]   ... lambda, lb0, rbar, tbar, y of the tile
+  double* xrl = rvl + FW * 2 * 5 * R3;             // [FW][2][R3][DT]  ... and its raw X rows
+  double* W0 = xrl + FW * 2 * R3 * DT;             // preamble / reduction / finish workspace
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
   const int D = a.D, M = a.M;
   const FL fl(MP, D);
+  const bool st0 = blockIdx.x == 0 && tid == 0;
+  if (st0) stamp(a, 32);
   // ---- preamble ---------------------------------------------------------------------------------------------------------
   {
     double* LC = W0;
@@ -847,6 +1032,7 @@ __global__ void __launch_bounds__(FT, 2) fused_p3_kernel(FusedArgs a) {
     }
     __syncthreads();
   }
+  if (st0) stamp(a, 33);
   // ---- row pass ---------------------------------------------------------------------------------------------------------
   double* sc = scr + warp * R3;
   double zacc[C::NTRI][2], pacc[MT][NXT][2], s0acc[MT], xqacc[NXT];
@@ -878,7 +1064,33 @@ __global__ void __launch_bounds__(FT, 2) fused_p3_kernel(FusedArgs a) {
   const double* E1 = E;
   const double* E2 = E + MP * LDA;
   const double* E3 = E + 2 * MP * LDA;
-  for (int64_t r0 = ((int64_t)blockIdx.x * FW + warp) * R3; r0 < N; r0 += (int64_t)gridDim.x * FW * R3) {
+  constexpr int LDK3 = R3 + 4;
+  double* ktw = ktl + warp * 2 * C::KP * LDK3;
+  const int64_t rstep = (int64_t)gridDim.x * FW * R3;
+  int buf = 0;
+  double* rvw = rvl + warp * 2 * 5 * R3;
+  double* xrw = xrl + warp * 2 * R3 * DT;
+  auto fetch3 = [&](int64_t r0, int b) {
+    const bool on = r0 < N;
+    fetch_k_tile<R3>(ktw + b * C::KP * LDK3, a.Kst, ld, r0, N, M, lane);
+    double* rvb = rvw + b * 5 * R3;
+    fetch_span(rvb, lamg + r0, R3, on, lane, 0);
+    fetch_span(rvb + R3, lb0g + r0, R3, on, lane, 8);
+    fetch_span(rvb + 2 * R3, rbg + r0, R3, on, lane, 16);
+    fetch_span(rvb + 3 * R3, tbg + r0, R3, on, lane, 24);
+    fetch_span(rvb + 4 * R3, a.y + r0, R3, on, lane, 4);
+    fetch_span(xrw + b * R3 * DT, a.X + r0 * D, R3 * D, on, lane, 12);       // X is zero-padded to the 128 tile
+    cp_async_commit_group();
+  };
+  fetch3(((int64_t)blockIdx.x * FW + warp) * R3, 0);
+  for (int64_t r0 = ((int64_t)blockIdx.x * FW + warp) * R3; r0 < N; r0 += rstep) {
+    fetch3(r0 + rstep, buf ^ 1);
+    cp_async_wait_group<1>();
+    __syncwarp();
+    const double* kt = ktw + buf * C::KP * LDK3;
+    const double* rv = rvw + buf * 5 * R3;
+    const double* xr = xrw + buf * R3 * DT;
+    buf ^= 1;
     double kT[2][MT][2], pq[2][MT][2], p3[2][MT][2];
     double s4[4], b4[4];
 #pragma unroll
@@ -891,23 +1103,24 @@ __global__ void __launch_bounds__(FT, 2) fused_p3_kernel(FusedArgs a) {
 #pragma unroll
       for (int s = 0; s < KS; ++s) {
         const int m = 4 * s + t;
-        kb[s] = (live && m < M) ? a.Kst[(int64_t)m * ld + row] : 0.0;
+        kb[s] = (live && m < M) ? kt[m * LDK3 + 8 * gi + g] : 0.0;
       }
 #pragma unroll
       for (int i = 0; i < MT; ++i) {
         const int m = 8 * i + g;
         double2 kk = make_double2(0.0, 0.0);
-        if (m < M && l0) kk = *reinterpret_cast<const double2*>(a.Kst + (int64_t)m * ld + rT);
+        if (m < M && l0) kk = *reinterpret_cast<const double2*>(kt + m * LDK3 + 8 * gi + 2 * t);
         kT[gi][i][0] = kk.x;
         kT[gi][i][1] = l1 ? kk.y : 0.0;
       }
       double2 lam2 = make_double2(1.0, 1.0), y2 = make_double2(0.0, 0.0), rb2 = y2, tb2 = y2;
       if (l0) {
-        lam2 = *reinterpret_cast<const double2*>(lamg + rT);
-        rb2 = *reinterpret_cast<const double2*>(rbg + rT);
-        tb2 = *reinterpret_cast<const double2*>(tbg + rT);
-        y2.x = a.y[rT];
-        if (l1) y2.y = a.y[rT + 1];
+        const int o = 8 * gi + 2 * t;
+        lam2 = *reinterpret_cast<const double2*>(rv + o);
+        rb2 = *reinterpret_cast<const double2*>(rv + 2 * R3 + o);
+        tb2 = *reinterpret_cast<const double2*>(rv + 3 * R3 + o);
+        y2 = *reinterpret_cast<const double2*>(rv + 4 * R3 + o);
+        if (!l1) y2.y = 0.0;
       }
       if (!l1) { lam2.y = 1.0; rb2.y = 0.0; tb2.y = 0.0; }
       const double il0 = 1.0 / lam2.x, il1 = 1.0 / lam2.y;
@@ -936,8 +1149,8 @@ __global__ void __launch_bounds__(FT, 2) fused_p3_kernel(FusedArgs a) {
     const int64_t orow = r0 + rho;
     double lb = 0.0;
     if (orow < N) {
-      const double il = 1.0 / lamg[orow];
-      lb = lb0g[orow] - bw * a.y[orow] * il * il - s1 * il * il;
+      const double il = 1.0 / rv[rho];
+      lb = rv[R3 + rho] - bw * rv[4 * R3 + rho] * il * il - s1 * il * il;
     }
     if ((g & 1) == 0) {
       sum_lb += lb;
@@ -969,8 +1182,9 @@ __global__ void __launch_bounds__(FT, 2) fused_p3_kernel(FusedArgs a) {
 #pragma unroll
       for (int j = 0; j < NXT; ++j) {
         const int c = 8 * j + g;
-        const double x0 = (c < D && rT < N) ? a.X[rT * D + c] * invx[j] : 0.0;
-        const double x1 = (c < D && rT + 1 < N) ? a.X[(rT + 1) * D + c] * invx[j] : 0.0;
+        const int o = (8 * gi + 2 * t) * D + c;
+        const double x0 = (c < D && rT < N) ? xr[o] * invx[j] : 0.0;
+        const double x1 = (c < D && rT + 1 < N) ? xr[o + D] * invx[j] : 0.0;
 #pragma unroll
         for (int i = 0; i < MT; ++i) {
           dmma(pacc[i][j][0], pacc[i][j][1], gT[i][0], x0);                       // P += G' xs
@@ -983,6 +1197,7 @@ __global__ void __launch_bounds__(FT, 2) fused_p3_kernel(FusedArgs a) {
   }
   // ---- reduction ------------------------------------------------------------------------------------------------------
   __syncthreads();
+  if (st0) stamp(a, 34);
   const int len3 = len3_of(MP, DT);
   double* Zs = W0;                         // [MP][MP] | P [MP][DT] | S0 [MP] | xq [DT] | sum_lb
   double* Ps = Zs + MP * MP;
@@ -1022,8 +1237,13 @@ __global__ void __launch_bounds__(FT, 2) fused_p3_kernel(FusedArgs a) {
   const double sl = block_sum(sum_lb, red);
   if (tid == 0) xqs[DT] = sl;
   __syncthreads();
+  if (st0) stamp(a, 35);
   const bool last = ticket_reduce(Zs, len3, a.part, a.gpart, a.cnt, a.acc3, tid);
-  if (last && a.finish) fused_finish<C>(a, W0, tid, warp, lane);
+  if (last && tid == 0) stamp(a, 36);
+  if (last && a.finish) {
+    fused_finish<C>(a, W0, tid, warp, lane);
+    if (tid == 0) stamp(a, 37);
+  }
 }
 
 // finishing step as its own kernel (row-sharded runs: after the all-reduce of acc3)
@@ -1142,10 +1362,13 @@ __global__ void fused_loo_kernel(const double* __restrict__ y, const double* __r
 __global__ void empty_kernel() {}
 
 // ---- shared-memory sizes (doubles) ------------------------------------------------------------------------------------
-template <class C> constexpr int smem_p1() { return 24 + C::KP * C::LDU + C::MP * C::LDA + 2 * C::MP * C::MP + C::MP + FW * 2 * TR; }
-template <class C> constexpr int smem_p2() { return C::MP * C::LDA + 4 * C::MP * C::MP + 4 * C::MP + FW * 3 * TR + 32; }
+template <class C> constexpr int smem_p1() { return 24 + C::KP * C::LDU + C::MP * C::LDA + 2 * C::MP * C::MP + C::MP + FW * 2 * TR + FW * 2 * TR * C::LDU + FW * 2 * TR; }
+template <class C> constexpr int smem_p2() {
+  return C::MP * C::LDA + 4 * C::MP + FW * 3 * TR + 32 + FW * 4 * TR +
+         (4 * C::MP * C::MP > FW * 2 * C::KP * (TR + 4) ? 4 * C::MP * C::MP : FW * 2 * C::KP * (TR + 4));
+}
 template <class C> constexpr int smem_p3() {
-  return 3 * C::MP * C::LDA + 4 * C::MP + FW * 16 + 32 +
+  return 3 * C::MP * C::LDA + 4 * C::MP + FW * 16 + 32 + FW * 2 * C::KP * (16 + 4) + FW * 2 * 5 * 16 + FW * 2 * 16 * C::DT +
          (finish_smem_doubles(C::MP) > len3_of(C::MP, C::DT) ? finish_smem_doubles(C::MP) : len3_of(C::MP, C::DT));
 }
 template <class C> constexpr int smem_pred() { return 24 + C::KP * C::LDU + 2 * C::MP * C::LDA + FW * TR; }
@@ -1164,12 +1387,14 @@ int set_smem_attr(gps_ctx* ctx, K kern, size_t bytes) {
 struct gps_fitc_fused {
   int M = 0, D = 0, MT = 0, KS = 0, DT = 0, MP = 0;
   int64_t N = 0, ldk = 0;
-  int grid = 0;
+  int grid = 0;              // CTAs that cover the rows once (one 32-row tile per warp)
+  int occ[4] = {3, 3, 2, 1}; // resident CTAs per SM of passes 1..3 (registers): persistent grids are capped at occ x SMs
   DevBuf Kst, rowv, fs, part, gpart, acc1, acc2, acc3, dthU, dout, trace;
   int* cnt = nullptr;       // 3 x (1 + ngrp_max) tickets + fail_it
   int cnt_stride = 0;
   double* h_in = nullptr;   // mapped pinned: theta | U
   double* h_out = nullptr;  // mapped pinned: obj | g_theta | g_U | info
+  long long* prof = nullptr; // debug phase stamps (gps_dbg_fused_phases)
   size_t h_cap = 0;
   bool configured[64] = {};
   bool ready = false;       // passes 1 + 2 have run at the current (theta, U): loo / predict are valid
@@ -1217,12 +1442,21 @@ int configure_kernels(gps_ctx* ctx) {
 }
 
 template <class CF>
-int launch_pass(gps_ctx* ctx, gps_fitc_fused* fu, int pass, const FusedArgs& a) {
+int launch_pass(gps_ctx* ctx, gps_fitc_fused* fu, int pass, const FusedArgs& a, const double* host_thu = nullptr) {
   FusedArgs b = a;
   b.cnt = fu->cnt + (pass - 1) * fu->cnt_stride;
-  if (pass == 1) fused_p1_kernel<CF><<<fu->grid, FT, smem_p1<CF>() * 8, ctx->stream>>>(b);
-  else if (pass == 2) fused_p2_kernel<CF><<<fu->grid, FT, smem_p2<CF>() * 8, ctx->stream>>>(b);
-  else if (pass == 3) fused_p3_kernel<CF><<<fu->grid, FT, smem_p3<CF>() * 8, ctx->stream>>>(b);
+  const int cap = ctx->sm_count * fu->occ[pass <= 3 ? pass - 1 : 3];
+  const int grid = fu->grid < cap ? fu->grid : cap;
+  if (pass == 1) {
+    FusedArgsP1 bp;
+    bp.a = b;
+    const int nthu = fu->D + 2 + fu->M * fu->D;
+    bp.inline_thu = (host_thu && nthu <= THU_INLINE) ? 1 : 0;
+    if (bp.inline_thu) memcpy(bp.thu, host_thu, (size_t)nthu * sizeof(double));
+    fused_p1_kernel<CF><<<grid, FT, smem_p1<CF>() * 8, ctx->stream>>>(bp);
+  }
+  else if (pass == 2) fused_p2_kernel<CF><<<grid, FT, smem_p2<CF>() * 8, ctx->stream>>>(b);
+  else if (pass == 3) fused_p3_kernel<CF><<<grid, FT, smem_p3<CF>() * 8, ctx->stream>>>(b);
   else fused_finish_kernel<CF><<<1, FT, finish_smem_doubles(CF::MP) * 8, ctx->stream>>>(b);
   GPS_LAUNCH_CHECK();
   ctx->launches++;
@@ -1254,6 +1488,7 @@ void gps_fitc_fused_free(gps_ctx* ctx) {
   if (fu->cnt) cudaFree(fu->cnt);
   if (fu->h_in) cudaFreeHost(fu->h_in);
   if (fu->h_out) cudaFreeHost(fu->h_out);
+  if (fu->prof) cudaFree(fu->prof);
   delete fu;
   ctx->fu = nullptr;
 }
@@ -1267,12 +1502,12 @@ int gps_fitc_fused_prepare(gps_ctx* ctx, int M) {
   const Combo cb = combo_of(M);
   fu->M = M; fu->D = D; fu->MT = cb.MT; fu->KS = cb.KS; fu->DT = D <= 8 ? 8 : 16; fu->MP = 8 * cb.MT;
   fu->N = N;
-  fu->ldk = (N + 7) / 8 * 8;
-  int64_t blocks = (N + FW * TR - 1) / (FW * TR);
-  const int64_t cap = (int64_t)ctx->sm_count * 2;
-  fu->grid = (int)(blocks < cap ? blocks : cap);
+  fu->ldk = (N + TR - 1) / TR * TR;        // whole warp tiles: the cp.async tile fetches never leave a row of K_uf
+  const int64_t blocks = (N + FW * TR - 1) / (FW * TR);
+  const int64_t cap = (int64_t)ctx->sm_count * 3;
+  fu->grid = (int)blocks;
   const int MP = fu->MP;
-  const size_t maxlen = (size_t)len3_of(MP, fu->DT);
+  const size_t maxlen = ((size_t)len3_of(MP, fu->DT) + 1) & ~(size_t)1;   // partial rows use an even stride
   const FL fl(MP, D);
   GPS_CHECK(gps_ensure(ctx, fu->Kst, (size_t)M * fu->ldk));
   GPS_CHECK(gps_ensure(ctx, fu->rowv, (size_t)6 * fu->ldk));
@@ -1311,10 +1546,11 @@ int gps_fitc_fused_prepare(gps_ctx* ctx, int M) {
 
 static FusedArgs make_args(gps_ctx* ctx, gps_fitc_fused* fu, const double* thU, double jitter, int score, int64_t world_n,
                            int finish, bool host_out) {
-  FusedArgs a;
+  FusedArgs a = {};
   a.X = ctx->X.p; a.y = ctx->y.p; a.thU = thU; a.fs = fu->fs.p; a.Kst = fu->Kst.p; a.rowv = fu->rowv.p;
   a.part = fu->part.p; a.gpart = fu->gpart.p; a.cnt = fu->cnt; a.acc1 = fu->acc1.p; a.acc2 = fu->acc2.p;
   a.acc3 = fu->acc3.p; a.out_dev = fu->dout.p; a.out_host = host_out ? fu->h_out : nullptr; a.info = ctx->d_info;
+  a.prof = fu->prof;
   a.N = fu->N; a.ldk = fu->ldk; a.D = fu->D; a.M = fu->M; a.score = score; a.finish = finish;
   a.jitter = jitter; a.invN = 1.0 / (double)world_n; a.world_n = (double)world_n;
   return a;
@@ -1326,11 +1562,11 @@ typedef int (*gps_allreduce_fn)(gps_ctx* ctx, double* buf, size_t n);
 // Enqueue one evaluation at the parameters in `thU` (device or mapped host memory): 3 launches on one GPU,
 // 4 + three all-reduces when `allreduce` is given.  No host synchronisation.
 int gps_fitc_fused_enqueue(gps_ctx* ctx, const double* thU, double jitter, int score, int64_t world_n, bool want_grad,
-                           bool host_out, gps_allreduce_fn allreduce) {
+                           bool host_out, gps_allreduce_fn allreduce, const double* host_thu = nullptr) {
   gps_fitc_fused* fu = ctx->fu;
   const FusedArgs a = make_args(ctx, fu, thU, jitter, score, world_n, allreduce ? 0 : 1, host_out);
   const int MP = fu->MP;
-  FUSED_DISPATCH(fu, GPS_CHECK((launch_pass<CF>(ctx, fu, 1, a))));
+  FUSED_DISPATCH(fu, GPS_CHECK((launch_pass<CF>(ctx, fu, 1, a, host_thu))));
   if (allreduce) GPS_CHECK(allreduce(ctx, fu->acc1.p, (size_t)len1_of(MP)));
   FUSED_DISPATCH(fu, GPS_CHECK((launch_pass<CF>(ctx, fu, 2, a))));
   if (allreduce) GPS_CHECK(allreduce(ctx, fu->acc2.p, (size_t)len2_of(MP)));
@@ -1396,9 +1632,13 @@ int gps_fitc_fused_eval(gps_ctx* ctx, const double* theta, const double* U, int 
   const int D = ctx->D;
   for (int k = 0; k < D + 2; ++k) fu->h_in[k] = theta[k];
   for (int k = 0; k < M * D; ++k) fu->h_in[D + 2 + k] = U[k];
-  GPS_CUDA(cudaMemsetAsync(ctx->d_info, 0, sizeof(int), ctx->stream));
+  // theta | U travel in pass 1's launch parameters when they fit, else pinned staging buffer -> device (a kernel
+  // reading mapped host memory directly pays a PCIe round trip per dependent load: 25 us of pass 1 in the first version)
+  const bool inl = D + 2 + M * D <= THU_INLINE;
+  if (!inl)
+    GPS_CUDA(cudaMemcpyAsync(fu->dthU.p, fu->h_in, (size_t)(D + 2 + M * D) * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   const bool want_grad = grad_theta || grad_U;
-  GPS_CHECK(gps_fitc_fused_enqueue(ctx, fu->h_in, jitter, score, world_n, want_grad, true, allreduce));
+  GPS_CHECK(gps_fitc_fused_enqueue(ctx, fu->dthU.p, jitter, score, world_n, want_grad, true, allreduce, inl ? fu->h_in : nullptr));
   GPS_CHECK(fused_collect(ctx, fu, want_grad, obj, grad_theta, grad_U));
   if (!want_grad && score == GPS_NLML && obj) GPS_CHECK(nlml_objective_terms(ctx, fu, world_n, obj));
   ctx->fitc.pass2_done = true;
@@ -1463,6 +1703,22 @@ int gps_fitc_fused_predict(gps_ctx* ctx, const double* dXs, int64_t T, double* d
   gps_fitc_fused* fu = ctx->fu;
   if (!fu || !fu->ready) return gps_fail(ctx, GPS_ESTATE, "fitc_predict: run an evaluation at this theta, U first");
   FUSED_DISPATCH(fu, GPS_CHECK((launch_predict<CF>(ctx, fu, dXs, T, dm, dv))));
+  return GPS_OK;
+}
+
+// debug: globaltimer stamps (ns) of the phases of the last evaluation; the first call arms the recording
+int gps_fitc_fused_phases(gps_ctx* ctx, long long* out48) {
+  gps_fitc_fused* fu = ctx->fu;
+  if (!fu) return gps_fail(ctx, GPS_ESTATE, "fused phases: no fused evaluation yet");
+  GPS_CUDA(cudaSetDevice(ctx->device));
+  if (!fu->prof) {
+    GPS_CUDA(cudaMalloc(&fu->prof, 48 * sizeof(long long)));
+    GPS_CUDA(cudaMemset(fu->prof, 0, 48 * sizeof(long long)));
+    for (int k = 0; k < 48; ++k) out48[k] = 0;
+    return GPS_OK;
+  }
+  GPS_CUDA(cudaStreamSynchronize(ctx->stream));
+  GPS_CUDA(cudaMemcpy(out48, fu->prof, 48 * sizeof(long long), cudaMemcpyDeviceToHost));
   return GPS_OK;
 }
 

@@ -8,6 +8,7 @@
 //
 // par (device): [0] = e^a, [1] = e^c (noise variance), [2 + d] = 1 / l_d.
 #include "gps_common.cuh"
+#include "gps_exp.cuh"
 
 namespace {
 
@@ -70,8 +71,8 @@ gram_sym_kernel(const double* __restrict__ X, int64_t N, int64_t Np, int D, cons
     for (int c = 0; c < 4; ++c) {
       const int64_t j = (int64_t)bj * TS + 32 * c + 2 * tx;
       double2 v;
-      v.x = ea * exp(-0.5 * acc[r][2 * c]);
-      v.y = ea * exp(-0.5 * acc[r][2 * c + 1]);
+      v.x = ea * exp_neg(-0.5 * acc[r][2 * c]);
+      v.y = ea * exp_neg(-0.5 * acc[r][2 * c + 1]);
       if (i >= N || j >= N) v.x = 0.0;
       if (i >= N || j + 1 >= N) v.y = 0.0;
       if (i == j) v.x = (i < N) ? v.x + sn2 : 1.0;
@@ -125,7 +126,7 @@ gram_rect_kernel(const double* __restrict__ x, int64_t n, const double* __restri
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
       const int64_t j = j0 + tx + 16 * c;
-      if (j < m) out[i * ldo + j] = ea * exp(-0.5 * acc[r][c]);
+      if (j < m) out[i * ldo + j] = ea * exp_neg(-0.5 * acc[r][c]);
     }
   }
 }

@@ -68,6 +68,7 @@ DEBUG_SIGNATURES = {
     "gps_dbg_potf2_phases": (C.c_int, [_vp, C.POINTER(C.c_int64)]),
     "gps_dbg_trace": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_double)]),
     "gps_dbg_gram": (C.c_int, [_vp, _dp, _vp]),
+    "gps_dbg_fused_phases": (C.c_int, [_vp, C.POINTER(C.c_int64)]),
     "gps_dbg_launch_floor": (C.c_int, [_vp, C.c_int, C.c_int, _dp]),
 }
 

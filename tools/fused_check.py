@@ -42,3 +42,18 @@ for n in (10000, 100000, 1000000):
         t0 = time.perf_counter(); ctx.fitc_descend(th, U, "crps", 1e-3, 1e-3, 500); t1 = time.perf_counter()
         print("descend 500 iters: %.1f us/iter" % ((t1 - t0) * 1e6 / 500), flush=True)
         print("launch floor (3 launches + sync): %.1f us" % ctx.launch_floor_us(3, 100), flush=True)
+# phase timeline (ns) of one evaluation at N = 1e4 and N = 1e6
+import ctypes as C
+for n in (10000, 1000000):
+    X, y = synth.kin40k_like(n, seed=7)
+    ctx.set_data(torch.from_numpy(X).cuda(), torch.from_numpy(y).cuda())
+    buf = (C.c_int64 * 48)()
+    ctx.fitc_eval(th, U, "crps")
+    ctx._check(ctx._lib.gps_dbg_fused_phases(ctx._h, buf))
+    for _ in range(3): ctx.fitc_eval(th, U, "crps")
+    ctx._check(ctx._lib.gps_dbg_fused_phases(ctx._h, buf))
+    v = list(buf); t0 = v[0]
+    names = ["start", "preamble", "rows", "cta-partial", "reduced", "finish"]
+    for k in range(3):
+        print("N=%d pass %d:" % (n, k + 1), "  ".join("%s %+.1f" % (names[j], (v[16 * k + j] - t0) / 1e3) for j in range(6) if v[16 * k + j]), flush=True)
+    print("   finish detail: loaded %+.1f  S assembled %+.1f  adjoint done %+.1f  theta grads done %+.1f" % tuple((v[40 + j] - t0) / 1e3 for j in range(4)))
