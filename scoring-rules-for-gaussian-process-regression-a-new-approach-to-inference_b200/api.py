@@ -120,7 +120,8 @@ class Context:
         self._check(self._lib.gps_set_data(self._h, X.data_ptr(), y.data_ptr(), X.shape[0], X.shape[1]))
         self.N, self.D = int(X.shape[0]), int(X.shape[1])
         self._data_key = None       # whatever _bind_data cached no longer describes the context
-        self._y_stats = (float(y.mean()), float(y.var(unbiased=True)) if y.numel() > 1 else 0.0)
+        self._y_train = y           # mean / unbiased variance of the targets (KF:113-114) are formed on first use
+        self._y_stats = None
 
     def _theta(self, theta):
         th = _host_vec(theta)
@@ -321,6 +322,9 @@ class Context:
             yt = _as_f64(y_train).reshape(-1)
             ytm, ytv = float(yt.mean()), float(yt.var(unbiased=True))
         else:
+            if self._y_stats is None:
+                yt = self._y_train
+                self._y_stats = (float(yt.mean()), float(yt.var(unbiased=True)) if yt.numel() > 1 else 0.0)
             ytm, ytv = self._y_stats
         out = np.zeros(12)
         self._check(self._lib.gps_test_metrics(self._h, mean.data_ptr(), var.data_ptr(), y.data_ptr(), mean.numel(),

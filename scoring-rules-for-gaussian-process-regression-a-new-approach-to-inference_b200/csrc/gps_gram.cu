@@ -19,7 +19,7 @@ constexpr int MAXD = 64;
 // tiles complete).  Rows/cols >= N are the identity so that the padded matrix stays SPD and
 // the padding never mixes with the data.  256 threads; thread (ty, tx) writes rows
 // ty + 16 r and, per row, four coalesced 16-byte pairs at columns 32 c + 2 tx.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 gram_sym_kernel(const double* __restrict__ X, int64_t N, int64_t Np, int D, const double* __restrict__ par,
                 double* __restrict__ K) {
   extern __shared__ double sh[];
@@ -42,42 +42,47 @@ gram_sym_kernel(const double* __restrict__ X, int64_t N, int64_t Np, int D, cons
   }
   __syncthreads();
   const int ty = tid >> 4, tx = tid & 15;
-  double acc[8][8];
-#pragma unroll
-  for (int r = 0; r < 8; ++r)
-#pragma unroll
-    for (int c = 0; c < 8; ++c) acc[r][c] = 0.0;
-  for (int d = 0; d < D; ++d) {
-    double a[8], b[8];
-#pragma unroll
-    for (int r = 0; r < 8; ++r) a[r] = xi[d * TS + ty + 16 * r];
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      b[2 * c] = xj[d * TS + 32 * c + 2 * tx];
-      b[2 * c + 1] = xj[d * TS + 32 * c + 2 * tx + 1];
-    }
+  // two column halves in turn (8 x 4 accumulators instead of 8 x 8): 94 registers instead of 172, so two CTAs share
+  // an SM and one CTA's exp chains / stores overlap the other's distance loop (ncu: FP64 pipe 42 % at one CTA per SM)
+#pragma unroll 1
+  for (int h = 0; h < 2; ++h) {
+    double acc[8][4];
 #pragma unroll
     for (int r = 0; r < 8; ++r)
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const double df = a[r] - b[c];
-        acc[r][c] = fma(df, df, acc[r][c]);
+      for (int c = 0; c < 4; ++c) acc[r][c] = 0.0;
+    for (int d = 0; d < D; ++d) {
+      double a[8], b[4];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) a[r] = xi[d * TS + ty + 16 * r];
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        b[2 * c] = xj[d * TS + 32 * (2 * h + c) + 2 * tx];
+        b[2 * c + 1] = xj[d * TS + 32 * (2 * h + c) + 2 * tx + 1];
       }
-  }
 #pragma unroll
-  for (int r = 0; r < 8; ++r) {
-    const int64_t i = (int64_t)bi * TS + ty + 16 * r;
+      for (int r = 0; r < 8; ++r)
 #pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const int64_t j = (int64_t)bj * TS + 32 * c + 2 * tx;
-      double2 v;
-      v.x = ea * exp_neg(-0.5 * acc[r][2 * c]);
-      v.y = ea * exp_neg(-0.5 * acc[r][2 * c + 1]);
-      if (i >= N || j >= N) v.x = 0.0;
-      if (i >= N || j + 1 >= N) v.y = 0.0;
-      if (i == j) v.x = (i < N) ? v.x + sn2 : 1.0;
-      if (i == j + 1) v.y = (i < N) ? v.y + sn2 : 1.0;
-      *reinterpret_cast<double2*>(K + i * Np + j) = v;
+        for (int c = 0; c < 4; ++c) {
+          const double df = a[r] - b[c];
+          acc[r][c] = fma(df, df, acc[r][c]);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const int64_t i = (int64_t)bi * TS + ty + 16 * r;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int64_t j = (int64_t)bj * TS + 32 * (2 * h + c) + 2 * tx;
+        double2 v;
+        v.x = ea * exp_neg(-0.5 * acc[r][2 * c]);
+        v.y = ea * exp_neg(-0.5 * acc[r][2 * c + 1]);
+        if (i >= N || j >= N) v.x = 0.0;
+        if (i >= N || j + 1 >= N) v.y = 0.0;
+        if (i == j) v.x = (i < N) ? v.x + sn2 : 1.0;
+        if (i == j + 1) v.y = (i < N) ? v.y + sn2 : 1.0;
+        *reinterpret_cast<double2*>(K + i * Np + j) = v;
+      }
     }
   }
 }

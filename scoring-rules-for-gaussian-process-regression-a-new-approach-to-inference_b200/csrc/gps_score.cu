@@ -112,7 +112,7 @@ nlml_value_kernel(int64_t N, const double* __restrict__ logdiag, const double* _
 //   mode 1 (NLML):       W_ij = ( Kinv_ij - a_i a_j ) / 2
 // partial[tile][0] = sum W K_f, [1 + d] = sum W K_f ((x_id - x_jd)/l_d)^2, [1 + D] = trace part.
 // Off-diagonal tiles count twice (symmetry).
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 grad_contract_kernel(int mode, const double* __restrict__ Mx, int64_t N, int64_t Np,
                      const double* __restrict__ X, int D, const double* __restrict__ par,
                      const double* __restrict__ alpha, const double* __restrict__ u,
@@ -146,95 +146,96 @@ grad_contract_kernel(int mode, const double* __restrict__ Mx, int64_t N, int64_t
   const int ty = tid >> 4, tx = tid & 15;
   const double ea = par[0];
   const double wgt = (bi == bj) ? 1.0 : 2.0;
-  double G[8][8];
+  const int nred = D + 2;
+  // The thread's 8 x 8 block is processed as two 8 x 4 column halves (two CTAs per SM instead of one spilling at 255
+  // registers).  Per input dimension
+  //   sum_ij G_ij (x_id - x_jd)^2 = sum_i x_id^2 rowsum_i(G) + sum_j x_jd^2 colsum_j(G) - 2 sum_i x_id (G x_d)_i
+  // (32 + 12 fmas per half instead of 3 x 32; the relative cancellation of the expansion is ~1e-15 |G| x^2, far inside
+  // the 1e-6 gradient tolerance — the objective does not pass through here).
+  double rs[8];
 #pragma unroll
-  for (int r = 0; r < 8; ++r)
-#pragma unroll
-    for (int c = 0; c < 8; ++c) G[r][c] = 0.0;
-  for (int d = 0; d < D; ++d) {
-    double a[8], b[8];
-#pragma unroll
-    for (int r = 0; r < 8; ++r) a[r] = xi[d * TS + ty + 16 * r];
-#pragma unroll
-    for (int c = 0; c < 8; ++c) b[c] = xj[d * TS + tx + 16 * c];
+  for (int r = 0; r < 8; ++r) rs[r] = 0.0;
+  double s_a = 0.0, s_tr = 0.0;
+#pragma unroll 1
+  for (int h = 0; h < 2; ++h) {
+    double G[8][4];
 #pragma unroll
     for (int r = 0; r < 8; ++r)
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const double df = a[r] - b[c];
-        G[r][c] = fma(df, df, G[r][c]);
+      for (int c = 0; c < 4; ++c) G[r][c] = 0.0;
+    for (int d = 0; d < D; ++d) {
+      double a[8], b[4];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) a[r] = xi[d * TS + ty + 16 * r];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) b[c] = xj[d * TS + tx + 16 * (4 * h + c)];
+#pragma unroll
+      for (int r = 0; r < 8; ++r)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const double df = a[r] - b[c];
+          G[r][c] = fma(df, df, G[r][c]);
+        }
+    }
+    double cs[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int r = 0; r < 8; ++r) {
+      const int il = ty + 16 * r;
+      const int64_t i = (int64_t)bi * TS + il;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int jl = tx + 16 * (4 * h + c);
+        const int64_t j = (int64_t)bj * TS + jl;
+        const double m = Mx[i * Np + j];
+        double w;
+        if (mode == 0)
+          w = -(0.5 * (ai[TS + il] * ai[2 * TS + jl] + ai[il] * ai[3 * TS + jl]) + m);
+        else
+          w = 0.5 * (m - ai[il] * ai[2 * TS + jl]);
+        if (i >= N || j >= N) w = 0.0;
+        if (i == j) s_tr += w;
+        const double g = wgt * w * ea * exp_neg(-0.5 * G[r][c]);
+        G[r][c] = g;
+        s_a += g;
+        rs[r] += g;
+        cs[c] += g;
       }
-  }
-  double s_a = 0.0, s_tr = 0.0;
+    }
+    for (int d = 0; d < D; ++d) {
+      double b[4];
 #pragma unroll
-  for (int r = 0; r < 8; ++r) {
-    const int il = ty + 16 * r;
-    const int64_t i = (int64_t)bi * TS + il;
+      for (int c = 0; c < 4; ++c) b[c] = xj[d * TS + tx + 16 * (4 * h + c)];
+      double s = 0.0, cross = 0.0;
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-      const int jl = tx + 16 * c;
-      const int64_t j = (int64_t)bj * TS + jl;
-      const double m = Mx[i * Np + j];
-      double w;
-      if (mode == 0)
-        w = -(0.5 * (ai[TS + il] * ai[2 * TS + jl] + ai[il] * ai[3 * TS + jl]) + m);
-      else
-        w = 0.5 * (m - ai[il] * ai[2 * TS + jl]);
-      if (i >= N || j >= N) w = 0.0;
-      if (i == j) s_tr += w;
-      const double g = wgt * w * ea * exp_neg(-0.5 * G[r][c]);
-      G[r][c] = g;
-      s_a += g;
+      for (int r = 0; r < 8; ++r) {
+        const double t0 = fma(G[r][0], b[0], G[r][1] * b[1]), t1 = fma(G[r][2], b[2], G[r][3] * b[3]);
+        cross = fma(xi[d * TS + ty + 16 * r], t0 + t1, cross);
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) s = fma(b[c] * b[c], cs[c], s);
+      s = fma(-2.0, cross, s);
+      s = warp_sum(s);
+      if (lane == 0) {
+        if (h == 0) red[warp * nred + 1 + d] = s;
+        else red[warp * nred + 1 + d] += s;
+      }
     }
   }
-  const int nred = D + 2;
   s_a = warp_sum(s_a);
   s_tr = warp_sum(s_tr);
   if (lane == 0) {
     red[warp * nred] = s_a;
     red[warp * nred + 1 + D] = s_tr;
   }
-  // sum_ij G_ij (x_id - x_jd)^2 = sum_i x_id^2 rowsum_i(G) + sum_j x_jd^2 colsum_j(G) - 2 sum_i x_id (G x_d)_i:
-  // 64 + 24 fmas per thread and input dimension instead of 3 x 64 (the relative cancellation of the expansion is
-  // ~1e-15 |G| x^2, far inside the 1e-6 gradient tolerance; the objective does not pass through here)
-  double rs[8], cs[8];
-#pragma unroll
-  for (int r = 0; r < 8; ++r) {
-    double t = 0.0;
-#pragma unroll
-    for (int c = 0; c < 8; ++c) t += G[r][c];
-    rs[r] = t;
-  }
-#pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    double t = 0.0;
-#pragma unroll
-    for (int r = 0; r < 8; ++r) t += G[r][c];
-    cs[c] = t;
-  }
   for (int d = 0; d < D; ++d) {
-    double a[8], b[8];
-#pragma unroll
-    for (int r = 0; r < 8; ++r) a[r] = xi[d * TS + ty + 16 * r];
-#pragma unroll
-    for (int c = 0; c < 8; ++c) b[c] = xj[d * TS + tx + 16 * c];
-    double s = 0.0, cross = 0.0;
+    double s = 0.0;
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
-      double t0 = 0.0, t1 = 0.0;
-#pragma unroll
-      for (int c = 0; c < 8; c += 2) {
-        t0 = fma(G[r][c], b[c], t0);
-        t1 = fma(G[r][c + 1], b[c + 1], t1);
-      }
-      cross = fma(a[r], t0 + t1, cross);
-      s = fma(a[r] * a[r], rs[r], s);
+      const double a = xi[d * TS + ty + 16 * r];
+      s = fma(a * a, rs[r], s);
     }
-#pragma unroll
-    for (int c = 0; c < 8; ++c) s = fma(b[c] * b[c], cs[c], s);
-    s = fma(-2.0, cross, s);
     s = warp_sum(s);
-    if (lane == 0) red[warp * nred + 1 + d] = s;
+    if (lane == 0) red[warp * nred + 1 + d] += s;
   }
   __syncthreads();
   if (tid < nred) {
