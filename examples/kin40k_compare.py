@@ -56,6 +56,24 @@ def fit(train_x, train_y, score, itr, lr, lr2, fitc, m, seed):
     return para_k, para_l, para_noise, inducing_x, float(obj.detach().reshape(-1)[0])
 
 
+def fit_on_device(ctx, train_x, train_y, score, itr, lr, lr2, fitc, m, seed):
+    """The same loop in ONE library call: theta and the inducing inputs never leave the device between steps
+    (gps_fitc_descend / gps_full_descend).  Same initialisation as `fit`."""
+    torch.manual_seed(seed)
+    d = train_x.shape[1]
+    para_l = torch.rand(1, d, dtype=torch.float64)
+    theta = np.concatenate([[1.0], para_l.numpy().ravel(), [1.0]])
+    ctx.set_data(train_x, train_y)
+    if fitc:
+        U0 = torch.rand(m, d, dtype=torch.float64).numpy()
+        theta, U, trace = ctx.fitc_descend(theta, U0, score, lr, lr2, itr)
+    else:
+        theta, trace = ctx.full_descend(theta, score, lr, itr)
+        U = None
+    t = torch.from_numpy
+    return (t(theta[:1]), t(theta[1:-1]).reshape(1, -1), t(theta[-1:]), None if U is None else t(U), float(trace[-1]))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--model", choices=["full", "fitc"], default="full")
@@ -64,6 +82,7 @@ def main():
     ap.add_argument("--n-test", type=int, default=500)
     ap.add_argument("--m", type=int, default=20)              # K20:205
     ap.add_argument("--itr-scale", type=float, default=0.1, help="fraction of the scripts' iteration counts")
+    ap.add_argument("--on-device", action="store_true", help="run each optimiser loop as one library call (device-resident)")
     args = ap.parse_args()
     fitc = args.model == "fitc"
     runs = FITC_RUNS if fitc else FULL_RUNS
@@ -76,7 +95,10 @@ def main():
         test_x, test_y = torch.from_numpy(Xs).cuda(), torch.from_numpy(ys).cuda()
         for score, itr, lr, lr2 in runs:
             itr = max(1, int(itr * args.itr_scale))
-            pk, pl, pn, U, last = fit(train_x, train_y, score, itr, lr, lr2, fitc, args.m, 100 * j)
+            if args.on_device and score in ("crps", "logs", "nlml"):
+                pk, pl, pn, U, last = fit_on_device(gp.default_context(), train_x, train_y, score, itr, lr, lr2, fitc, args.m, 100 * j)
+            else:
+                pk, pl, pn, U, last = fit(train_x, train_y, score, itr, lr, lr2, fitc, args.m, 100 * j)
             mean, var = gp.predict_diag(train_x, train_y, test_x, pk, pl, pn, inducing_x=U)     # KF:267-273
             met = gp.test_metrics(mean, var, test_y, train_y)                                    # KF:276-292
             table[score].append([met[k] for k in ("mse", "smse", "logs", "crps", "msll", "coverage")])

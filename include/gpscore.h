@@ -116,9 +116,19 @@ int gps_comm_unique_id(void* out128);
 int gps_comm_init(gps_ctx* ctx, const void* uid128, int rank, int world);
 int gps_comm_info(gps_ctx* ctx, int* rank, int* world, int* nccl_version);
 int gps_comm_destroy(gps_ctx* ctx);
+/* Transport of the M <= 31 row-sharded evaluation.  1 (default when gps_comm_init could map the ranks' exchange
+ * areas through cudaIpc): the all-reduce of each pass runs INSIDE the pass kernel — the CTA that completes the
+ * rank's total stores it into every peer's exchange area over NVLink, publishes a sequence flag, waits for the
+ * peers' flags and sums the slots in rank order — so a sharded evaluation is the same three launches as a single-GPU
+ * one.  0: ncclAllReduce between the kernels.  *active (may be NULL) receives the transport in effect. */
+int gps_comm_set_transport(gps_ctx* ctx, int transport, int* active);
 int gps_comm_allreduce_sum(gps_ctx* ctx, double* buf, int64_t n);   /* in-place sum of a DEVICE buffer over the ranks */
 int gps_fitc_eval_sharded(gps_ctx* ctx, const double* theta, const double* U, int M, double jitter, int score,
                           int64_t world_n, double* obj, double* grad_theta, double* grad_U);
+/* the loop K20:219-251 on a row-sharded problem (M <= 31, CRPS / LOGS / NLML): theta and U resident on every rank's
+ * device, exchange inside the pass kernels (or NCCL between them), one synchronisation at the end */
+int gps_fitc_descend_sharded(gps_ctx* ctx, double* theta, double* U, int M, double jitter, int score, int64_t world_n,
+                             double lr_theta, double lr_u, int iters, double* obj_trace);
 int gps_fitc_loo(gps_ctx* ctx, double* loo_mean, double* loo_var);
 /* replaces K20:270-277 → spgp_cal_mean_and_cov K20:76-83 (diagonal only). Needs a finished
  * gps_fitc_eval / pass1+pass2 at the same theta, U (uses its L_A, L_C, beta). */

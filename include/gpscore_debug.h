@@ -27,8 +27,10 @@ int gps_dbg_fp64_peak(gps_ctx* ctx, int iters, double* dmma_tflops, double* dfma
 
 /* Tuning knobs for A/B measurements: what = 0 selects the tile-GEMM policy
  * (0: BK16 x 4 stages, 1: + fragment double-buffering, 2: BK32 x 3 stages, 3: BK32 + double-buffering,
- * 4: BK16 with 16 warps, 5: BK32 with 16 warps, 6: 64 x 128 CTA tile, 4 warps, two CTAs per SM = default,
- * 7: 6 + double-buffering, 8: 6 with 64 x 32 warp tiles); what = 1 selects the diagonal-block kernel of
+ * 4: BK16 with 16 warps, 5: BK32 with 16 warps, 6: 64 x 128 CTA tile, 4 warps, two CTAs per SM (round-1 default),
+ * 7: 6 + double-buffering, 8: 6 with 64 x 32 warp tiles, 9: the tile of 6 fed by TMA — cp.async.bulk.tensor.2d into a 4-stage
+ * mbarrier ring, 128-byte hardware swizzle — = default since round 2; launches with a k-scaling vector and the row-strip
+ * policies stay on cp.async); what = 1 selects the diagonal-block kernel of
  * POTRF (0: register-cyclic, 1: 32-blocked DMMA = default); what = 2 selects the FITC row passes
  * (0: thread-per-row, 1: tile/DMMA formulation = default); what = 3 sets the number of inducing points from
  * which gps_fitc_eval switches to the matrix form (default 33; lower it to A/B the two paths at M <= 32);

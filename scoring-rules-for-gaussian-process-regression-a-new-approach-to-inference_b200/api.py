@@ -236,6 +236,13 @@ class Context:
         self._check(self._lib.gps_comm_init(self._h, C.c_char_p(raw), rank, world))
         self.rank, self.world = rank, world
 
+    def comm_transport(self, peer_memory=True):
+        """Select how the M <= 31 row-sharded evaluation exchanges its accumulators: inside the pass kernels over
+        peer memory (default) or with ncclAllReduce between them.  Returns True if peer memory is in effect."""
+        act = C.c_int()
+        self._check(self._lib.gps_comm_set_transport(self._h, 1 if peer_memory else 0, C.byref(act)))
+        return bool(act.value)
+
     def comm_allreduce_(self, t):
         """In-place sum of a float64 device tensor over the context's communicator (library NCCL)."""
         self._enter()
@@ -280,6 +287,19 @@ class Context:
         self._after_collective()
         self._check(self._lib.gps_fitc_finish(self._h, a2.data_ptr(), a3.data_ptr(), _dp(obj), _dp(g), _dp(gU)))
         return float(obj[0]), g, gU.reshape(M, self.D)
+
+    def fitc_descend_sharded(self, theta, U, score, world_n, lr, lr_u, iters, jitter=JITTER):
+        """`fitc_descend` on a row-sharded problem (after `comm_init`): every rank returns the same
+        (theta, U, objective trace)."""
+        self._enter()
+        th = self._theta(theta).copy()
+        Uh = _host_vec(U).copy()
+        M = Uh.size // self.D
+        trace = np.zeros(int(iters))
+        sc = _L.SCORES[score] if isinstance(score, str) else int(score)
+        self._check(self._lib.gps_fitc_descend_sharded(self._h, _dp(th), _dp(Uh), M, float(jitter), sc, int(world_n),
+                                                       float(lr), float(lr_u), int(iters), _dp(trace)))
+        return th, Uh.reshape(M, self.D), trace
 
     def _after_collective(self):
         """The caller's collective ran on torch's current stream.  Following that stream keeps the

@@ -10,11 +10,19 @@
 #include <nccl.h>
 #include <string.h>
 
+#include <vector>
+
 #include "gps_common.cuh"
 
 struct gps_comm {
   ncclComm_t comm = nullptr;
   int rank = 0, world = 1;
+  // peer-memory exchange area (see gps_common.cuh)
+  double* xbuf = nullptr;                 // this rank's area (cudaMalloc)
+  std::vector<void*> peer_map;            // cudaIpcOpenMemHandle mappings of the other ranks' areas
+  double** d_peers = nullptr;             // device copy of the base pointers
+  unsigned long long seq = 1;
+  int transport = 1;                      // 1: peer memory inside the kernels when available, 0: NCCL only
 };
 
 namespace {
@@ -61,8 +69,72 @@ bool nccl_load() {
 
 }  // namespace
 
+static size_t xbuf_doubles(int world) { return (size_t)2 * world * GPS_P2P_SLOT + (size_t)2 * world + 16; }
+
+// Exchange area + peer mappings.  The 64-byte IPC handles travel through the communicator itself (ncclAllGather):
+// no other channel between the ranks is needed.  Any failure leaves peers unset and the NCCL path in use.
+static void p2p_setup(gps_ctx* ctx) {
+  gps_comm* cm = ctx->comm;
+  const int W = cm->world;
+  if (W < 2 || W > 16) return;
+  decltype(&ncclAllGather) AllGather = reinterpret_cast<decltype(&ncclAllGather)>(dlsym(g_nccl.lib, "ncclAllGather"));
+  if (!AllGather) return;
+  const size_t nd = xbuf_doubles(W);
+  if (cudaMalloc(&cm->xbuf, nd * sizeof(double)) != cudaSuccess) { cudaGetLastError(); cm->xbuf = nullptr; return; }
+  cudaMemset(cm->xbuf, 0, nd * sizeof(double));
+  cudaIpcMemHandle_t mine;
+  char* d_h = nullptr;
+  std::vector<cudaIpcMemHandle_t> all(W);
+  bool ok = cudaIpcGetMemHandle(&mine, cm->xbuf) == cudaSuccess &&
+            cudaMalloc(&d_h, (size_t)(W + 1) * sizeof mine) == cudaSuccess &&
+            cudaMemcpy(d_h + (size_t)W * sizeof mine, &mine, sizeof mine, cudaMemcpyHostToDevice) == cudaSuccess &&
+            AllGather(d_h + (size_t)W * sizeof mine, d_h, sizeof mine, ncclChar, cm->comm, ctx->stream) == ncclSuccess &&
+            cudaStreamSynchronize(ctx->stream) == cudaSuccess &&
+            cudaMemcpy(all.data(), d_h, (size_t)W * sizeof mine, cudaMemcpyDeviceToHost) == cudaSuccess;
+  if (d_h) cudaFree(d_h);
+  std::vector<double*> bases(W, nullptr);
+  for (int r = 0; ok && r < W; ++r) {
+    if (r == cm->rank) { bases[r] = cm->xbuf; continue; }
+    void* p = nullptr;
+    if (cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = false; break; }
+    cm->peer_map.push_back(p);
+    bases[r] = static_cast<double*>(p);
+  }
+  // every rank must agree on the outcome: a single failure switches all of them to NCCL
+  int* d_ok = nullptr;
+  int flag = ok ? 1 : 0, agreed = 0;
+  if (cudaMalloc(&d_ok, sizeof(int)) == cudaSuccess) {
+    cudaMemcpy(d_ok, &flag, sizeof(int), cudaMemcpyHostToDevice);
+    if (g_nccl.AllReduce(d_ok, d_ok, 1, ncclInt, ncclMin, cm->comm, ctx->stream) == ncclSuccess &&
+        cudaStreamSynchronize(ctx->stream) == cudaSuccess)
+      cudaMemcpy(&agreed, d_ok, sizeof(int), cudaMemcpyDeviceToHost);
+    cudaFree(d_ok);
+  }
+  cudaGetLastError();
+  if (agreed == 1 && cudaMalloc(&cm->d_peers, (size_t)W * sizeof(double*)) == cudaSuccess) {
+    cudaMemcpy(cm->d_peers, bases.data(), (size_t)W * sizeof(double*), cudaMemcpyHostToDevice);
+  } else {
+    cm->d_peers = nullptr;
+  }
+}
+
+bool gps_comm_p2p_view(gps_ctx* ctx, gps_p2p_view* v, int exchanges) {
+  gps_comm* cm = ctx->comm;
+  if (!cm || !cm->d_peers || cm->transport != 1) return false;
+  v->peers = cm->d_peers;
+  v->rank = cm->rank;
+  v->world = cm->world;
+  v->seq = cm->seq;
+  cm->seq += (unsigned long long)exchanges;
+  return true;
+}
+
 void gps_comm_free(gps_ctx* ctx) {
   if (!ctx->comm) return;
+  cudaStreamSynchronize(ctx->stream);
+  for (void* p : ctx->comm->peer_map) cudaIpcCloseMemHandle(p);
+  if (ctx->comm->d_peers) cudaFree(ctx->comm->d_peers);
+  if (ctx->comm->xbuf) cudaFree(ctx->comm->xbuf);
   if (ctx->comm->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm->comm);
   delete ctx->comm;
   ctx->comm = nullptr;
@@ -111,6 +183,18 @@ int gps_comm_init(gps_ctx* ctx, const void* uid128, int rank, int world) {
     ctx->comm = nullptr;
     return rc;
   }
+  p2p_setup(ctx);
+  return GPS_OK;
+}
+
+/* transport of the small-M row-sharded evaluation: 1 = one-shot all-reduce over peer memory inside the pass kernels
+ * (default when the IPC mappings could be set up), 0 = ncclAllReduce between the kernels.  Returns the transport in
+ * effect through *active (may be NULL). */
+int gps_comm_set_transport(gps_ctx* ctx, int transport, int* active) {
+  if (!ctx) return GPS_EINVAL;
+  if (!ctx->comm) return gps_fail(ctx, GPS_ESTATE, "no communicator: call gps_comm_init first");
+  ctx->comm->transport = transport ? 1 : 0;
+  if (active) *active = (ctx->comm->transport == 1 && ctx->comm->d_peers) ? 1 : 0;
   return GPS_OK;
 }
 
@@ -154,6 +238,20 @@ int gps_fitc_eval_sharded(gps_ctx* ctx, const double* theta, const double* U, in
   if (M < ctx->fitc_large_min_m && gps_fitc_fused_supports(ctx, M, score))
     return gps_fitc_fused_eval(ctx, theta, U, M, jitter, score, world_n, gps_comm_allreduce, obj, grad_theta, grad_U);
   return gps_fitc_large_eval_sharded(ctx, theta, U, M, jitter, score, world_n, gps_comm_allreduce, obj, grad_theta, grad_U);
+}
+
+// The optimiser loop K20:219-251 on a row-sharded problem: theta and U stay on every rank's device (all ranks apply the
+// same update to the same all-reduced gradient), an iteration is the three pass kernels (exchange inside them, or
+// ncclAllReduce between them) and the update kernel; one synchronisation and read-back after the last iteration.
+int gps_fitc_descend_sharded(gps_ctx* ctx, double* theta, double* U, int M, double jitter, int score, int64_t world_n,
+                             double lr_theta, double lr_u, int iters, double* obj_trace) {
+  if (!ctx) return GPS_EINVAL;
+  if (ctx->N == 0) return gps_fail(ctx, GPS_ESTATE, "fitc: call gps_set_data first");
+  if (!theta || !U || M <= 0 || iters < 0 || world_n < ctx->N) return gps_fail(ctx, GPS_EINVAL, "fitc_descend_sharded: bad arguments");
+  if (!ctx->comm) return gps_fail(ctx, GPS_ESTATE, "fitc_descend_sharded: call gps_comm_init first");
+  if (!gps_fitc_fused_supports(ctx, M, score))
+    return gps_fail(ctx, GPS_EINVAL, "fitc_descend_sharded: M <= 31 and crps / logs / nlml only");
+  return gps_fitc_fused_descend(ctx, theta, U, M, jitter, score, lr_theta, lr_u, iters, obj_trace, world_n, gps_comm_allreduce);
 }
 
 }  // extern "C"

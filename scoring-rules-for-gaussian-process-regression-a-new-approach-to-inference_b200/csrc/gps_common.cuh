@@ -41,7 +41,7 @@ struct gps_ctx {
   int fitc_variant = 2;               // 0: thread-per-row FITC passes, 1: tile (DMMA) formulation, 2: fused three-kernel path (gps_fitc_fused.cu)
   long long* potf2_prof = nullptr;    // device buffer for clock64 phase stamps of the diagonal kernel (debug)
   int potf2_variant = 1;              // 0: register-cyclic diagonal kernel, 1: 32-blocked DMMA diagonal kernel
-  int gemm_variant = 6;               // tile-GEMM policy (see gps_gemm.cu); switched by gps_dbg_set_variant
+  int gemm_variant = 9;               // tile-GEMM policy (see gps_gemm.cu): 9 = TMA-fed operand ring (default), 6 = the same tile with cp.async; switched by gps_dbg_set_variant
   int gemm_strip_policy = 0;          // 32 / 16: row-strip policy, set around the few-tile launches of POTRF's chain
   int chain_strip = 16;               // A/B knob 7: strip height used on the chain (0 = the normal policy)
   int gemm_auto_strip = 1;            // A/B knob 8: strip policies for every launch with too few tasks to fill the SMs
@@ -182,7 +182,7 @@ void gps_fitc_fused_free(gps_ctx* ctx);
 int gps_fitc_fused_eval(gps_ctx* ctx, const double* theta, const double* U, int M, double jitter, int score,
                         int64_t world_n, gps_allreduce_fn allreduce, double* obj, double* grad_theta, double* grad_U);
 int gps_fitc_fused_descend(gps_ctx* ctx, double* theta, double* U, int M, double jitter, int score, double lr_theta,
-                           double lr_u, int iters, double* obj_trace);
+                           double lr_u, int iters, double* obj_trace, int64_t world_n = 0, gps_allreduce_fn allreduce = nullptr);
 int gps_fitc_fused_loo(gps_ctx* ctx, double* dm, double* dv);
 int gps_fitc_fused_predict(gps_ctx* ctx, const double* dXs, int64_t T, double* dm, double* dv);
 int gps_launch_floor_us(gps_ctx* ctx, int launches, int reps, double* us);
@@ -193,6 +193,16 @@ int gps_fitc_large_eval_sharded(gps_ctx* ctx, const double* theta, const double*
 // gps_comm.cu
 void gps_comm_free(gps_ctx* ctx);
 int gps_comm_allreduce(gps_ctx* ctx, double* buf, size_t n);
+// peer-memory exchange area of the fused FITC kernels (one-shot all-reduce inside the pass kernels over NVLink):
+// every rank owns [2 parities][world slots][GPS_P2P_SLOT doubles] followed by [2][world] sequence flags, and holds
+// peer mappings (cudaIpc) of all the others.  peers == nullptr: not available, the NCCL path is used.
+constexpr int GPS_P2P_SLOT = 1664;   // >= the largest packed accumulator of the fused path (M = 31, D = 16: 1585)
+struct gps_p2p_view {
+  double** peers;            // device array [world] of exchange-area base pointers (own entry = local)
+  int rank, world;
+  unsigned long long seq;    // sequence number of the NEXT exchange (the host advances it per launch)
+};
+bool gps_comm_p2p_view(gps_ctx* ctx, gps_p2p_view* v, int exchanges);
 // offsets (doubles) into ctx->params and rows of ctx->vecs
 constexpr int PAR_OBJ = 128;
 constexpr int PAR_GSUM = 136;

@@ -130,6 +130,9 @@ struct FusedArgs {
   double* out_host;       // same, mapped host memory (may be null)
   int* info;
   long long* prof;        // debug: globaltimer stamps of the phases (null = off), 16 slots per kernel
+  double** peers;         // row-sharded runs: exchange areas of all ranks (peer memory), null = single GPU / NCCL
+  int rank, world;
+  unsigned long long seq; // sequence number of this kernel's exchange
   int64_t N, ldk;
   int D, M, score, finish;   // finish: pass 3 also runs the finishing step (single GPU)
   double jitter, invN, world_n;
@@ -366,6 +369,54 @@ __device__ __forceinline__ bool ticket_reduce(const double* __restrict__ cta_val
   return true;
 }
 
+// ---- one-shot all-reduce over peer memory, run by the CTA that completed the rank's total -------------------------
+// Every rank stores its packed accumulator into slot [parity][rank] of EVERY rank's exchange area (coalesced 16-byte
+// stores over NVLink), publishes the sequence number in the peers' flag words, waits until all ranks' flags of its own
+// area carry that number and sums the slots in rank order: the same bits on every rank, no collective launch between
+// the pass kernels, ~1 NVLink round trip.  Two parities: a rank can be one exchange ahead of a peer that is still
+// reading the previous one, never two (it needs that peer's flag to finish its own).  The wait is bounded (~2 s):
+// a rank that never shows up raises the error flag instead of hanging the GPU.
+__device__ __forceinline__ void p2p_allreduce(const FusedArgs& a, double* acc, int len, int tid) {
+  const int W = a.world, par = (int)(a.seq & 1ull);
+  const int nv = (len + 1) >> 1;                                   // 16-byte chunks (acc buffers have even capacity)
+  const size_t slot_off = ((size_t)par * W + a.rank) * GPS_P2P_SLOT;
+  const double2* src = reinterpret_cast<const double2*>(acc);
+  for (int r = 0; r < W; ++r) {
+    double2* dst = reinterpret_cast<double2*>(a.peers[r] + slot_off);
+    for (int e = tid; e < nv; e += FT) dst[e] = __ldcg(src + e);
+  }
+  __threadfence_system();
+  __syncthreads();
+  unsigned long long* myflags = reinterpret_cast<unsigned long long*>(a.peers[a.rank] + (size_t)2 * W * GPS_P2P_SLOT) + (size_t)par * W;
+  if (tid < W) {
+    unsigned long long* pf = reinterpret_cast<unsigned long long*>(a.peers[tid] + (size_t)2 * W * GPS_P2P_SLOT) + (size_t)par * W + a.rank;
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(pf), "l"(a.seq) : "memory");
+    const long long t0 = clock64();
+    unsigned long long seen = 0;
+    do {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(myflags + tid) : "memory");
+      if (clock64() - t0 > 4000000000ll) {                        // ~2 s: give up, flag the evaluation as failed
+        atomicCAS(a.info, 0, 3000000 + tid);
+        break;
+      }
+    } while (seen < a.seq);
+  }
+  __syncthreads();
+  const double* base = a.peers[a.rank] + (size_t)par * W * GPS_P2P_SLOT;
+  for (int e = tid; e < nv; e += FT) {
+    double2 s = make_double2(0.0, 0.0);
+    for (int r = 0; r < W; ++r) {
+      const double2 v = __ldcg(reinterpret_cast<const double2*>(base + (size_t)r * GPS_P2P_SLOT) + e);
+      s.x += v.x;
+      s.y += v.y;
+    }
+    if (2 * e < len) acc[2 * e] = s.x;
+    if (2 * e + 1 < len) acc[2 * e + 1] = s.y;
+  }
+  __threadfence();
+  __syncthreads();
+}
+
 // sum the warps' accumulator fragments into a dense [MP][ld] shared matrix (zeroed by the caller), warp by warp
 template <class C>
 __device__ __forceinline__ void tri_frags_to_smem(const double (&acc)[C::NTRI][2], double* S, int warp, int lane) {
@@ -429,6 +480,7 @@ __global__ void __launch_bounds__(FT, 3) fused_p1_kernel(const __grid_constant__
     Us[e] = (m < M && d < D) ? thU[D + 2 + m * D + d] * par[2 + d] : 0.0;
   }
   __syncthreads();
+  if (st0) stamp(a, 5);
   for (int e = tid; e < MP * MP; e += FT) {
     const int i = e / MP, j = e - i * MP;
     double v = 0.0;
@@ -445,14 +497,17 @@ __global__ void __launch_bounds__(FT, 3) fused_p1_kernel(const __grid_constant__
     B0[e] = v + ((i == j) ? ((i < M) ? a.jitter : 1.0) : 0.0);
   }
   __syncthreads();
+  if (st0) stamp(a, 6);
   if (warp == 0) {
     const int bad = warp_chol<MP>(B0, lane);
     if (bad && lane == 0 && blockIdx.x == 0) atomicCAS(a.info, 0, bad);
     if (lane < MP) Li[lane] = 1.0 / B0[lane * MP + lane];
     __syncwarp();
+    if (st0) stamp(a, 7);
     warp_tri_inverse<MP>(B0, Li, B1, lane);
   }
   __syncthreads();
+  if (st0) stamp(a, 8);
   for (int e = tid; e < MP * LDA; e += FT) {
     const int m = e / LDA, k = e - m * LDA;
     Aop[e] = (k < MP) ? B1[m * MP + k] : 0.0;
@@ -576,7 +631,10 @@ __global__ void __launch_bounds__(FT, 3) fused_p1_kernel(const __grid_constant__
   __syncthreads();
   tri_frags_to_smem<C>(cacc, B0, warp, lane);
   if (st0) stamp(a, 3);
-  if (ticket_reduce(B0, len1_of(MP), a.part, a.gpart, a.cnt, a.acc1, tid) && tid == 0) stamp(a, 4);
+  if (ticket_reduce(B0, len1_of(MP), a.part, a.gpart, a.cnt, a.acc1, tid)) {
+    if (a.peers) p2p_allreduce(a, a.acc1, len1_of(MP), tid);
+    if (tid == 0) stamp(a, 4);
+  }
 }
 
 // =====================================================================================================================
@@ -616,14 +674,17 @@ __global__ void __launch_bounds__(FT, 3) fused_p2_kernel(FusedArgs a) {
   }
   if (tid < MP) vy[tid] = (tid < M) ? a.acc1[M * MP + tid] : 0.0;
   __syncthreads();
+  if (st0) stamp(a, 21);
   if (warp == 0) {
     const int bad = warp_chol<MP>(B0, lane);
     if (bad && lane == 0 && blockIdx.x == 0) atomicCAS(a.info, 0, 1000000 + bad);
     if (lane < MP) Li[lane] = 1.0 / B0[lane * MP + lane];
     __syncwarp();
+    if (st0) stamp(a, 22);
     warp_tri_inverse<MP>(B0, Li, B1, lane);
   }
   __syncthreads();
+  if (st0) stamp(a, 23);
   smv<MP, false>(B1, vy, beta, tid);                                  // beta = L_C^-1 v_y
   smm<MT, false, false>(B1, B2, B3, MP, MP, 1.0, 0.0, warp, lane);    // T2 = L_C^-1 L_A^-1
   __syncthreads();
@@ -781,7 +842,10 @@ __global__ void __launch_bounds__(FT, 3) fused_p2_kernel(FusedArgs a) {
   if (tid == 0) B0[MP * MP] = o;
   __syncthreads();
   if (st0) stamp(a, 19);
-  if (ticket_reduce(B0, len2_of(MP), a.part, a.gpart, a.cnt, a.acc2, tid) && tid == 0) stamp(a, 20);
+  if (ticket_reduce(B0, len2_of(MP), a.part, a.gpart, a.cnt, a.acc2, tid)) {
+    if (a.peers) p2p_allreduce(a, a.acc2, len2_of(MP), tid);
+    if (tid == 0) stamp(a, 20);
+  }
 }
 
 // =====================================================================================================================
@@ -1005,6 +1069,7 @@ __global__ void __launch_bounds__(FT, 2) fused_p3_kernel(FusedArgs a) {
       SW[e] = (r < M && c < M) ? beta[r] * bbar[c] + 2.0 * sym_lower(a.acc2, MP, r, c) + bbar[r] * beta[c] : 0.0;
     }
     __syncthreads();
+    if (st0) stamp(a, 44);
     smm<MT, true, false>(LCi, SW, X1, MP, MP, 1.0, 0.0, warp, lane);     // L_C^-T S_W
     smv<MP, true>(LCi, bbar, vyb, tid);                                  // vy_bar = L_C^-T beta_bar
     __syncthreads();
@@ -1015,7 +1080,9 @@ __global__ void __launch_bounds__(FT, 2) fused_p3_kernel(FusedArgs a) {
       X1[e] = v;                                                         // L_C_bar
     }
     __syncthreads();
+    if (st0) stamp(a, 45);
     chol_adjoint_smm<MT>(LC, LCi, X1, T1, Cb, tid, warp, lane);          // C_bar
+    if (st0) stamp(a, 46);
     smv<MP, true>(LAi, vyb, vec + MP, tid);                              // a2 = L_A^-T vy_bar
     smv<MP, true>(T2, bbar, vec + 2 * MP, tid);                          // c1 = T2' beta_bar
     smm<MT, true, false>(T2, T2, E, LDA, C::KP, 1.0, 0.0, warp, lane);                  // E1 = T2' T2
@@ -1239,6 +1306,7 @@ __global__ void __launch_bounds__(FT, 2) fused_p3_kernel(FusedArgs a) {
   __syncthreads();
   if (st0) stamp(a, 35);
   const bool last = ticket_reduce(Zs, len3, a.part, a.gpart, a.cnt, a.acc3, tid);
+  if (last && a.peers) p2p_allreduce(a, a.acc3, len3, tid);
   if (last && tid == 0) stamp(a, 36);
   if (last && a.finish) {
     fused_finish<C>(a, W0, tid, warp, lane);
@@ -1564,12 +1632,23 @@ typedef int (*gps_allreduce_fn)(gps_ctx* ctx, double* buf, size_t n);
 int gps_fitc_fused_enqueue(gps_ctx* ctx, const double* thU, double jitter, int score, int64_t world_n, bool want_grad,
                            bool host_out, gps_allreduce_fn allreduce, const double* host_thu = nullptr) {
   gps_fitc_fused* fu = ctx->fu;
-  const FusedArgs a = make_args(ctx, fu, thU, jitter, score, world_n, allreduce ? 0 : 1, host_out);
+  // row-sharded: the exchange runs inside the pass kernels over peer memory when the ranks could map each other's
+  // exchange areas (then a sharded evaluation is the same three launches as a single-GPU one), else through the
+  // `allreduce` hook (NCCL) between the kernels with the finishing step as a fourth launch
+  gps_p2p_view pv;
+  const bool p2p = allreduce && gps_comm_p2p_view(ctx, &pv, want_grad ? 3 : 2);
+  if (p2p) allreduce = nullptr;
+  FusedArgs a = make_args(ctx, fu, thU, jitter, score, world_n, allreduce ? 0 : 1, host_out);
+  if (p2p) {
+    a.peers = pv.peers; a.rank = pv.rank; a.world = pv.world; a.seq = pv.seq;
+  }
   const int MP = fu->MP;
   FUSED_DISPATCH(fu, GPS_CHECK((launch_pass<CF>(ctx, fu, 1, a, host_thu))));
   if (allreduce) GPS_CHECK(allreduce(ctx, fu->acc1.p, (size_t)len1_of(MP)));
+  a.seq++;
   FUSED_DISPATCH(fu, GPS_CHECK((launch_pass<CF>(ctx, fu, 2, a))));
   if (allreduce) GPS_CHECK(allreduce(ctx, fu->acc2.p, (size_t)len2_of(MP)));
+  a.seq++;
   fu->ready = true;
   if (!want_grad) return GPS_OK;
   FUSED_DISPATCH(fu, GPS_CHECK((launch_pass<CF>(ctx, fu, 3, a))));
@@ -1595,6 +1674,11 @@ static int fused_collect(gps_ctx* ctx, gps_fitc_fused* fu, bool want_grad, doubl
     GPS_CUDA(cudaMemcpyAsync(&info, ctx->d_info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     GPS_CUDA(cudaStreamSynchronize(ctx->stream));
     objv = o;
+  }
+  if (info >= 3000000) {
+    fu->ready = false;
+    return gps_fail(ctx, GPS_ECUDA, "fitc_eval_sharded: rank %d did not reach the peer-memory exchange within the time limit",
+                    info - 3000000);
   }
   if (info != 0) {
     fu->ready = false;
@@ -1652,7 +1736,7 @@ int gps_fitc_fused_eval(gps_ctx* ctx, const double* theta, const double* U, int 
 // K20:219-251 in one call with theta and U resident on the device: `iters` x (3 launches + update), one
 // synchronisation at the end.
 int gps_fitc_fused_descend(gps_ctx* ctx, double* theta, double* U, int M, double jitter, int score, double lr_theta,
-                           double lr_u, int iters, double* obj_trace) {
+                           double lr_u, int iters, double* obj_trace, int64_t world_n, gps_allreduce_fn allreduce) {
   GPS_CUDA(cudaSetDevice(ctx->device));
   GPS_CHECK(gps_fitc_fused_prepare(ctx, M));
   gps_fitc_fused* fu = ctx->fu;
@@ -1667,7 +1751,7 @@ int gps_fitc_fused_descend(gps_ctx* ctx, double* theta, double* U, int M, double
   GPS_CUDA(cudaMemcpyAsync(fail_it, &minus1, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
   GPS_CUDA(cudaMemsetAsync(ctx->d_info, 0, sizeof(int), ctx->stream));
   for (int it = 0; it < iters; ++it) {
-    GPS_CHECK(gps_fitc_fused_enqueue(ctx, fu->dthU.p, jitter, score, ctx->N, true, false, nullptr));
+    GPS_CHECK(gps_fitc_fused_enqueue(ctx, fu->dthU.p, jitter, score, world_n > 0 ? world_n : ctx->N, true, false, allreduce));
     fused_update_kernel<<<1, 256, 0, ctx->stream>>>(fu->dthU.p, fu->dout.p, D, M, lr_theta, lr_u, fu->trace.p, it,
                                                     ctx->d_info, fail_it);
     GPS_LAUNCH_CHECK();
@@ -1684,6 +1768,8 @@ int gps_fitc_fused_descend(gps_ctx* ctx, double* theta, double* U, int M, double
   for (int k = 0; k < Q; ++k) U[k] = fu->h_out[P + k];
   fu->ready = false;
   ctx->fitc.pass2_done = false;
+  if (info >= 3000000)
+    return gps_fail(ctx, GPS_ECUDA, "fitc_descend: rank %d did not reach the peer-memory exchange within the time limit", info - 3000000);
   if (info != 0)
     return gps_fail(ctx, GPS_ENOTPD, "fitc_descend: %s not positive definite at pivot %d in iteration %d",
                     info >= 1000000 ? "I + V V'/lambda" : "K_uu + jitter I", info % 1000000, failed);

@@ -17,6 +17,12 @@
 // (gps_dbg_set_variant) and the numbers are in profiles/.
 //
 // tcgen05 has no f64 kind, so on B200 the FP64 tensor path IS mma.sync DMMA.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include <map>
+#include <tuple>
+
 #include "gps_common.cuh"
 
 namespace {
@@ -231,6 +237,205 @@ gemm_tile_kernel(const double* __restrict__ A, int64_t lda, const double* __rest
   }
 }
 
+// =====================================================================================================================
+// TMA-fed variant of the (KC, KC) tile GEMM (A/B policy 9; round-1 verdict item 4c).
+// Same CTA tile (64 x 128 slice of a 128 x 128 task, 4 warps, BK = 16), same k-order per output element -> bit-identical
+// results; only the operand movement differs: one elected thread issues two cp.async.bulk.tensor.2d per k-block
+// (A: 64 x 16, B: 128 x 16 doubles) that complete on an mbarrier, instead of 12 16-byte cp.async per thread.  Tiles
+// land dense (128-byte rows) with the hardware 128-byte swizzle; fragment loads apply the same XOR (16-byte chunk
+// index ^ (row & 7)).  For 8-byte elements that pattern is 2-way bank conflicted across the half-warp's four rows
+// pairs (the padded cp.async layout is conflict-free) — the kernel is DMMA-bound, so this does not show.
+// =====================================================================================================================
+constexpr int TMA_STAGES = 4;
+constexpr int TMA_A_BYTES = 64 * 16 * 8, TMA_B_BYTES = 128 * 16 * 8, TMA_STAGE_BYTES = TMA_A_BYTES + TMA_B_BYTES;
+constexpr size_t TMA_SMEM = (size_t)TMA_STAGES * TMA_STAGE_BYTES + 1024;   // + slack for the 1024-byte alignment
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* b, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(b)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* b, int bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* b, int parity) {
+  asm volatile(
+      "{\n.reg .pred P1;\nWAIT_LOOP:\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n@P1 bra DONE;\nbra WAIT_LOOP;\nDONE:\n}\n" ::"r"(smem_u32(b)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, unsigned long long* bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n" ::"r"(smem_u32(dst)),
+               "l"(reinterpret_cast<unsigned long long>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+               : "memory");
+}
+// dense [rows][16 doubles] tile with the 128-byte swizzle: address of element (row, k)
+__device__ __forceinline__ double swz_ld(const unsigned char* tile, int row, int k) {
+  const int off = row * 128 + ((((k >> 1) ^ (row & 7)) << 4) | ((k & 1) << 3));
+  return *reinterpret_cast<const double*>(tile + off);
+}
+
+// operand tile (row `row` of the panel, contraction index k) in either layout
+template <int ROWS, bool MC>
+__device__ __forceinline__ double tma_frag(const unsigned char* tile, int row, int k) {
+  if (MC) return reinterpret_cast<const double*>(tile)[k * ROWS + row];   // dense [16][ROWS], no swizzle
+  return swz_ld(tile, row, k);                                            // dense [ROWS][16], 128-byte swizzle
+}
+
+template <bool A_MC, bool B_MC, bool MIRROR>
+__global__ void __launch_bounds__(128, 2)
+gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, double* __restrict__ C,
+                int64_t ldc, double alpha, double beta, const GemmTask* __restrict__ tasks) {
+  extern __shared__ unsigned char smem_raw[];
+  __shared__ unsigned long long full[TMA_STAGES];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  constexpr int TM = 64, MF = 4, NF = 8, WROWS = 32, WCOLS = 64, BK = 16, S = TMA_STAGES;   // 2 x 2 warps, 32 x 64 warp tiles
+  GemmTask t = tasks[blockIdx.x >> 1];
+  const bool diag_tile = t.c_row == t.c_col;
+  const int half = (int)(blockIdx.x & 1) * TM;
+  t.a_row += half;
+  t.c_row += half;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int wm = warp >> 1, wn = warp & 1, g = lane >> 2, tq = lane & 3;
+  const int nk = (t.k1 - t.k0) / BK;
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+  auto issue = [&](int kb) {
+    unsigned char* sl = smem + (size_t)(kb % S) * TMA_STAGE_BYTES;
+    const int k = t.k0 + kb * BK;
+    mbar_expect_tx(&full[kb % S], TMA_STAGE_BYTES);
+    if (A_MC) tma_load_2d(sl, &tmA, &full[kb % S], t.a_row, k);
+    else tma_load_2d(sl, &tmA, &full[kb % S], k, t.a_row);
+    if (B_MC) tma_load_2d(sl + TMA_A_BYTES, &tmB, &full[kb % S], t.b_row, k);
+    else tma_load_2d(sl + TMA_A_BYTES, &tmB, &full[kb % S], k, t.b_row);
+  };
+  if (tid == 0)
+    for (int s = 0; s < S - 1 && s < nk; ++s) issue(s);
+  double acc[MF][NF][2];
+#pragma unroll
+  for (int i = 0; i < MF; ++i)
+#pragma unroll
+    for (int j = 0; j < NF; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+  for (int kb = 0; kb < nk; ++kb) {
+    mbar_wait(&full[kb % S], (kb / S) & 1);
+    __syncthreads();                       // everyone is done with the slot the next load overwrites
+    if (tid == 0 && kb + S - 1 < nk) issue(kb + S - 1);
+    const unsigned char* As = smem + (size_t)(kb % S) * TMA_STAGE_BYTES;
+    const unsigned char* Bs = As + TMA_A_BYTES;
+#pragma unroll
+    for (int kk = 0; kk < BK / 4; ++kk) {
+      const int k = kk * 4 + tq;
+      double a[MF], b[NF];
+#pragma unroll
+      for (int i = 0; i < MF; ++i) a[i] = tma_frag<TM, A_MC>(As, wm * WROWS + i * 8 + g, k);
+#pragma unroll
+      for (int j = 0; j < NF; ++j) b[j] = tma_frag<128, B_MC>(Bs, wn * WCOLS + j * 8 + g, k);
+#pragma unroll
+      for (int i = 0; i < MF; ++i)
+#pragma unroll
+        for (int j = 0; j < NF; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    }
+  }
+  double* tbuf = reinterpret_cast<double*>(smem);
+  static_assert(!MIRROR || (size_t)128 * (TM + 1) * sizeof(double) <= (size_t)TMA_STAGES * TMA_STAGE_BYTES, "transpose buffer must fit");
+  if (MIRROR) __syncthreads();             // the operand ring is reused as the transpose buffer below
+#pragma unroll
+  for (int i = 0; i < MF; ++i) {
+    const int row = t.c_row + wm * WROWS + i * 8 + g;
+#pragma unroll
+    for (int j = 0; j < NF; ++j) {
+      const int col = t.c_col + wn * WCOLS + j * 8 + 2 * tq;
+      double2* p = reinterpret_cast<double2*>(C + (int64_t)row * ldc + col);
+      double2 v;
+      v.x = alpha * acc[i][j][0];
+      v.y = alpha * acc[i][j][1];
+      if (beta != 0.0) {
+        const double2 o = *p;
+        v.x += beta * o.x;
+        v.y += beta * o.y;
+      }
+      *p = v;
+      if (MIRROR && !diag_tile) {
+        const int lr = wm * WROWS + i * 8 + g, lc = wn * WCOLS + j * 8 + 2 * tq;
+        tbuf[lc * (TM + 1) + lr] = v.x;
+        tbuf[(lc + 1) * (TM + 1) + lr] = v.y;
+      }
+    }
+  }
+  if (MIRROR && !diag_tile) {
+    __syncthreads();
+    for (int n = warp; n < 128; n += 4) {
+      double* dst = C + (int64_t)(t.c_col + n) * ldc + t.c_row;
+      for (int m = lane; m < TM; m += 32) dst[m] = tbuf[n * (TM + 1) + m];
+    }
+  }
+}
+
+// tensor maps keyed by (base, leading dimension, box), created on first use (driver entry point: no -lcuda)
+struct TmaMaps {
+  PFN_cuTensorMapEncodeTiled encode = nullptr;
+  std::map<std::tuple<const void*, int64_t, int, int>, CUtensorMap> cache;
+};
+TmaMaps g_tma;
+
+// panel_rows x 16 operand tile of a row-major matrix with leading dimension ld.  KC (k contiguous): box {16, rows},
+// 128-byte swizzle; MC (panel index contiguous): box {rows, 16}, dense.  The row extent is left unbounded (the map is
+// only used with in-range coordinates; the buffer's true height is not known here).
+int tma_map(gps_ctx* ctx, const double* base, int64_t ld, int panel_rows, bool mc, CUtensorMap* out) {
+  if (!g_tma.encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn)
+      return gps_fail(ctx, GPS_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    g_tma.encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(fn);
+  }
+  auto key = std::make_tuple((const void*)base, ld, panel_rows, mc ? 1 : 0);
+  auto it = g_tma.cache.find(key);
+  if (it == g_tma.cache.end()) {
+    if (g_tma.cache.size() > 512) g_tma.cache.clear();
+    CUtensorMap m;
+    const cuuint64_t dims[2] = {(cuuint64_t)ld, (cuuint64_t)1 << 30};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(double)};
+    const cuuint32_t box[2] = {mc ? (cuuint32_t)panel_rows : 16u, mc ? 16u : (cuuint32_t)panel_rows};
+    const cuuint32_t estr[2] = {1u, 1u};
+    const CUresult r = g_tma.encode(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), dims, strides, box, estr,
+                                    CU_TENSOR_MAP_INTERLEAVE_NONE, mc ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B,
+                                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return gps_fail(ctx, GPS_ECUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    it = g_tma.cache.emplace(key, m).first;
+  }
+  *out = it->second;
+  return GPS_OK;
+}
+
+template <bool A_MC, bool B_MC, bool MIRROR>
+int launch_tma_k(gps_ctx* ctx, const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc, double alpha,
+                 double beta, const GemmTask* tasks, size_t ntasks) {
+  CUtensorMap ma, mb;
+  GPS_CHECK(tma_map(ctx, A, lda, 64, A_MC, &ma));
+  GPS_CHECK(tma_map(ctx, B, ldb, 128, B_MC, &mb));
+  auto kern = gemm_tma_kernel<A_MC, B_MC, MIRROR>;
+  GPS_ONCE_PER_DEVICE(ctx);
+  if (!configured) {
+    GPS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TMA_SMEM));
+    configured = true;
+  }
+  kern<<<(unsigned)(ntasks * 2), 128, TMA_SMEM, ctx->stream>>>(ma, mb, C, ldc, alpha, beta, tasks);
+  GPS_LAUNCH_CHECK();
+  return GPS_OK;
+}
+
+int launch_tma(gps_ctx* ctx, int kind, bool mirror, const double* A, int64_t lda, const double* B, int64_t ldb, double* C,
+               int64_t ldc, double alpha, double beta, const GemmTask* tasks, size_t ntasks) {
+  if (kind == GEMM_KC_KC) return launch_tma_k<false, false, false>(ctx, A, lda, B, ldb, C, ldc, alpha, beta, tasks, ntasks);
+  if (kind == GEMM_KC_MC) return launch_tma_k<false, true, false>(ctx, A, lda, B, ldb, C, ldc, alpha, beta, tasks, ntasks);
+  if (mirror) return launch_tma_k<true, true, true>(ctx, A, lda, B, ldb, C, ldc, alpha, beta, tasks, ntasks);
+  return launch_tma_k<true, true, false>(ctx, A, lda, B, ldb, C, ldc, alpha, beta, tasks, ntasks);
+}
+
 template <class Cfg, bool A_MC, bool B_MC, bool DVEC, bool MIRROR>
 int launch(gps_ctx* ctx, const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc,
            double alpha, double beta, const double* dvec, const GemmTask* tasks, size_t ntasks) {
@@ -295,7 +500,9 @@ int gps_gemm_tasks(gps_ctx* ctx, int kind, const double* A, int64_t lda, const d
     if (ntasks * 8 <= (size_t)ctx->sm_count) strip = 16;
     else if (ntasks * 4 <= (size_t)ctx->sm_count) strip = 32;
   }
-  if (strip == 32) {
+  if (ctx->gemm_variant == 9 && strip == 0 && !dvec && (kind == GEMM_KC_KC || kind == GEMM_KC_MC || kind == GEMM_MC_MC)) {
+    r = launch_tma(ctx, kind, mirror, A, lda, B, ldb, C, ldc, alpha, beta, d_tasks, ntasks);   // TMA-fed operand ring
+  } else if (strip == 32) {
     r = dispatch<GemmCfg<32, 16, 3, 1, 4, false, 2>>(GPS_GEMM_ARGS);
   } else if (strip == 16) {
     r = dispatch<GemmCfg<16, 16, 3, 1, 4, false, 2>>(GPS_GEMM_ARGS);

@@ -45,8 +45,10 @@ SIGNATURES = {
     "gps_comm_init": (C.c_int, [_vp, _vp, C.c_int, C.c_int]),
     "gps_comm_info": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "gps_comm_destroy": (C.c_int, [_vp]),
+    "gps_comm_set_transport": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_int)]),
     "gps_comm_allreduce_sum": (C.c_int, [_vp, _vp, _i64]),
     "gps_fitc_eval_sharded": (C.c_int, [_vp, _dp, _dp, C.c_int, C.c_double, C.c_int, _i64, _dp, _dp, _dp]),
+    "gps_fitc_descend_sharded": (C.c_int, [_vp, _dp, _dp, C.c_int, C.c_double, C.c_int, _i64, C.c_double, C.c_double, C.c_int, _dp]),
     "gps_fitc_loo": (C.c_int, [_vp, _vp, _vp]),
     "gps_fitc_predict": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
     "gps_full_descend": (C.c_int, [_vp, _dp, C.c_int, C.c_double, C.c_int, _dp]),

@@ -51,17 +51,30 @@ def main():
     whole = api.Context(local)
     whole.set_data(torch.from_numpy(X).cuda(), torch.from_numpy(y).cuda())
     rng = np.random.default_rng(4)
+    p2p = part.comm_transport(True)
+    if rank == 0:
+        print("peer-memory transport available: %s" % p2p, flush=True)
     for m_ind in (20, 31, 64):
         U = X[rng.choice(n, m_ind, replace=False)] + 0.05 * rng.standard_normal((m_ind, 8))
         for score in ("crps", "logs", "nlml"):
+            part.comm_transport(False)
             sv, sg, sgu = part.fitc_eval_sharded(theta, U, score, n)
             v1, g1, gu1 = whole.fitc_eval(theta, U, score)
             check("M=%d %s library-NCCL sharded vs single GPU" % (m_ind, score),
                   max(abs(sv - v1) / abs(v1), rel(sg, g1), rel(sgu, gu1)), 1e-10)
+            if p2p and m_ind <= 31:
+                part.comm_transport(True)
+                for rep in range(3):      # consecutive exchanges alternate parity
+                    pv, pg, pgu = part.fitc_eval_sharded(theta, U, score, n)
+                check("M=%d %s in-kernel peer-memory exchange vs single GPU" % (m_ind, score),
+                      max(abs(pv - v1) / abs(v1), rel(pg, g1), rel(pgu, gu1)), 1e-10)
+                ov_only = part.fitc_eval_sharded(theta, U, score, n)[0]
+                check("M=%d %s peer-memory exchange repeatable" % (m_ind, score), abs(ov_only - pv), 0.0)
             if m_ind == 20:
                 ov, og, ogu = W.fitc_obj_grad(X, y, U, theta, O.SCORES[score])[:3]
                 check("M=%d %s library-NCCL sharded vs oracle (objective)" % (m_ind, score), abs(sv - ov) / abs(ov), 1e-8)
                 check("M=%d %s library-NCCL sharded vs oracle (gradient)" % (m_ind, score), max(rel(sg, og), rel(sgu, ogu)), 1e-6)
+    part.comm_transport(True)
     # every rank got the same numbers
     U = synth.inducing_init(20)
     sv, sg, sgu = part.fitc_eval_sharded(theta, U, "crps", n)
@@ -70,6 +83,14 @@ def main():
     dist.all_reduce(tmin, op=dist.ReduceOp.MIN)
     dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     check("all ranks return identical results", float((tmax - tmin).abs().max()), 0.0)
+    # row-sharded device-resident descent loop == single-GPU loop
+    for p2pflag in ((True, False) if p2p else (False,)):
+        part.comm_transport(p2pflag)
+        th_s, U_s, tr_s = part.fitc_descend_sharded(theta, U, "crps", n, 0.3, 0.3, 15)
+        th_1, U_1, tr_1 = whole.fitc_descend(theta, U, "crps", 0.3, 0.3, 15)
+        check("sharded descent loop (peer memory: %s) vs single GPU" % p2pflag,
+              max(rel(th_s, th_1), rel(U_s, U_1), rel(tr_s, tr_1)), 1e-10)
+    part.comm_transport(True)
     # staged protocol with torch.distributed all-reduces on torch's stream (no synchronize in the callback)
     sf = gd.ShardedFitc(part, n)
     for score in ("crps", "nlml"):

@@ -289,3 +289,56 @@ def test_multi_gpu_parity_under_torchrun():
                         "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(root, "tests", "mgpu_check.py")],
                        capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+# ---- the experiment drivers ----------------------------------------------------------------------------------
+def _run_example(args, timeout=600):
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable] + args, cwd=root, capture_output=True, text=True, timeout=timeout)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    return r.stdout
+
+
+def test_example_kin40k_compare_runs_both_models():
+    """examples/kin40k_compare.py (the trial loop KF:190-299 / K20:184-304 on the fused objectives): both models run,
+    the host-driven loop and the device-resident loop end at the same objective, and the result table is printed."""
+    import re
+    out_h = _run_example(["examples/kin40k_compare.py", "--model", "fitc", "--trials", "1", "--n-train", "300", "--n-test", "200",
+                          "--itr-scale", "0.01"])
+    out_d = _run_example(["examples/kin40k_compare.py", "--model", "fitc", "--trials", "1", "--n-train", "300", "--n-test", "200",
+                          "--itr-scale", "0.01", "--on-device"])
+    assert "means over trials" in out_h and "fitted by crps" in out_h and "fitted by kc" in out_h
+
+    def last_obj(out, score):
+        return float(re.search(r"trial 0 %s\s+itr\s+\d+ objective ([-0-9.e+]+)" % score, out).group(1))
+
+    for score in ("crps", "nlml", "logs"):
+        # the printed objective is the one BEFORE the last update in both variants
+        assert abs(last_obj(out_h, score) - last_obj(out_d, score)) <= 1e-5 * abs(last_obj(out_h, score)), score
+    out_f = _run_example(["examples/kin40k_compare.py", "--model", "full", "--trials", "1", "--n-train", "256", "--n-test", "100",
+                          "--itr-scale", "0.02"])
+    assert "fitted by dss" in out_f
+
+
+def test_example_contour_grid_writes_reference_layout(tmp_path):
+    """examples/contour_grid.py: the four 50 x 50 matrices of CP:113-141 (rows = noise s.d., columns = length scale),
+    spot-checked against the R twins in the oracle."""
+    from oracle import gp_oracle as O
+    out = str(tmp_path / "contour")
+    _run_example(["examples/contour_grid.py", "--n", "20", "--grid", "50", "--out", out])
+    rng = np.random.default_rng(0)
+    x = np.linspace(-6, 6, 20)
+    K = np.exp(-0.5 * (x[:, None] - x[None, :]) ** 2) + 1e-10 * np.eye(20)
+    y = (np.linalg.cholesky(K) @ rng.standard_normal(20) + 0.1 * rng.standard_normal(20)).reshape(-1, 1)
+    l_range, noise_range = np.linspace(0.01, 2, 50), np.linspace(0.01, 1, 50)
+    for which, fn in (("crps", O.cal_m_crps), ("nlml", O.cal_NLML), ("logs", O.cal_m_logs), ("wrong_crps", O.wrong_cal_m_crps)):
+        mat = np.load("%s/ma_%s.npy" % (out, which))
+        assert mat.shape == (50, 50)
+        csv = np.loadtxt("%s/ma_%s.csv" % (out, which), delimiter=",")
+        assert np.allclose(csv, mat, rtol=1e-12, atol=0)
+        for (i, j) in ((5, 7), (20, 30), (49, 49), (12, 3)):
+            want = fn(x, y, l_range[j], noise_range[i])
+            assert abs(mat[i, j] - want) <= 1e-8 * max(1.0, abs(want)), (which, i, j)

@@ -56,4 +56,6 @@ for n in (10000, 1000000):
     names = ["start", "preamble", "rows", "cta-partial", "reduced", "finish"]
     for k in range(3):
         print("N=%d pass %d:" % (n, k + 1), "  ".join("%s %+.1f" % (names[j], (v[16 * k + j] - t0) / 1e3) for j in range(6) if v[16 * k + j]), flush=True)
+    print("   preamble detail p1: params+Us %+.1f  Kuu %+.1f  chol %+.1f  inverse %+.1f | p2: loads %+.1f chol %+.1f inverse %+.1f | p3: loads+SW %+.1f  LCbar %+.1f  adjoint %+.1f" % (
+        tuple((v[j] - v[0]) / 1e3 for j in (5, 6, 7, 8)) + tuple((v[j] - v[16]) / 1e3 for j in (21, 22, 23)) + tuple((v[j] - v[32]) / 1e3 for j in (44, 45, 46))))
     print("   finish detail: loaded %+.1f  S assembled %+.1f  adjoint done %+.1f  theta grads done %+.1f" % tuple((v[40 + j] - t0) / 1e3 for j in range(4)))
