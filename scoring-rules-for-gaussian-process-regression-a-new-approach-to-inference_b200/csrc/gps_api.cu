@@ -210,7 +210,7 @@ void gps_destroy(gps_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  DevBuf* bufs[] = {&ctx->X, &ctx->y, &ctx->Kb, &ctx->Xb, &ctx->Sb, &ctx->vecs, &ctx->red, &ctx->params, &ctx->Gb, &ctx->fold_vecs,
+  DevBuf* bufs[] = {&ctx->X, &ctx->y, &ctx->Kb, &ctx->Xb, &ctx->Sb, &ctx->vecs, &ctx->red, &ctx->params, &ctx->Gb, &ctx->fold_vecs, &ctx->descend_buf,
                     &ctx->fitc.V, &ctx->fitc.W, &ctx->fitc.rowv, &ctx->fitc.small, &ctx->fitc.part, &ctx->fitc.part2, &ctx->fitc.accf,
                     &ctx->fitc.acc1, &ctx->fitc.acc2, &ctx->fitc.acc3, &ctx->stage[0], &ctx->stage[1],
                     &ctx->stage[2], &ctx->stage[3]};
@@ -292,31 +292,26 @@ int gps_set_data(gps_ctx* ctx, const double* X, const double* y, int64_t N, int 
   return GPS_OK;
 }
 
-int gps_full_eval(gps_ctx* ctx, const double* theta, int score, double* obj, double* grad) {
-  if (!ctx) return GPS_EINVAL;
-  if (ctx->N == 0) return gps_fail(ctx, GPS_ESTATE, "full_eval: call gps_set_data first");
-  if (!theta || !obj || score < GPS_CRPS || score > GPS_DSS) return gps_fail(ctx, GPS_EINVAL, "full_eval: bad arguments (kc is a FITC objective)");
-  GPS_CUDA(cudaSetDevice(ctx->device));
+// Everything of one full-GP evaluation that runs on the device, enqueued on the context's streams; the kernel
+// parameters (e^a, e^c, 1/l) are already in ctx->params.  Leaves the objective in params[PAR_OBJ] and the raw
+// gradient sums in params[PAR_GSUM ..] (the noise entry still lacks its chain-rule factor e^c).
+static int full_eval_enqueue(gps_ctx* ctx, int score, bool want_grad, bool* stages_full) {
   const int64_t N = ctx->N, Np = ctx->Np;
   const int D = ctx->D;
-  GPS_CHECK(gps_ensure_ws(ctx, Np));
-  double ea, sn2;
-  GPS_CHECK(gps_upload_params(ctx, theta, D, &ea, &sn2));
-  gemm_timing_begin(ctx);
   GPS_CHECK(gps_factor_and_invert(ctx, score == GPS_NLML));
   double* v = ctx->vecs.p;
   double* par = ctx->params.p;
-  bool stages_full = false;
+  *stages_full = false;
   ctx->stage_valid = false;
   if (score == GPS_DSS) {
     ctx->loo_valid = false;
-    GPS_CHECK(gps_full_dss(ctx, par + PAR_OBJ, par + PAR_GSUM, grad != nullptr));
+    GPS_CHECK(gps_full_dss(ctx, par + PAR_OBJ, par + PAR_GSUM, want_grad));
   } else if (score != GPS_NLML) {
     GPS_CHECK(gps_diag_extract(ctx, ctx->Kb.p, Np, v + V_D * Np, 0));
     GPS_CHECK(gps_loo_score(ctx, score, N, Np, N, v + V_ALPHA * Np, v + V_D * Np, ctx->y.p, v + V_ABAR * Np,
                             v + V_DBAR * Np, v + V_LOOM * Np, v + V_LOOV * Np, par + PAR_OBJ));
     ctx->loo_valid = true;
-    if (grad) {
+    if (want_grad) {
       GPS_CHECK(gps_symv(ctx, ctx->Kb.p, Np, v + V_ABAR * Np, v + V_U * Np));
       GPS_CHECK(stage_mark(ctx, gps_ctx::ST_SCORE));
       GPS_CHECK(gps_symprod(ctx, ctx->Kb.p, v + V_DBAR * Np, ctx->Xb.p, ctx->Sb.p, Np));   // L^-1 in Xb is dead after LAUUM
@@ -324,15 +319,32 @@ int gps_full_eval(gps_ctx* ctx, const double* theta, int score, double* obj, dou
       GPS_CHECK(gps_grad_contract(ctx, 0, ctx->Sb.p, N, Np, ctx->X.p, D, par, v + V_ALPHA * Np, v + V_U * Np,
                                   par + PAR_GSUM));
       GPS_CHECK(stage_mark(ctx, gps_ctx::ST_CONTRACT));
-      stages_full = true;
+      *stages_full = true;
     }
   } else {
     ctx->loo_valid = false;
     GPS_CHECK(gps_nlml_value(ctx, N, Np, v + V_LOGD * Np, v + V_ALPHA * Np, ctx->y.p, par + PAR_OBJ));
-    if (grad)
+    if (want_grad)
       GPS_CHECK(gps_grad_contract(ctx, 1, ctx->Kb.p, N, Np, ctx->X.p, D, par, v + V_ALPHA * Np, nullptr,
                                   par + PAR_GSUM));
   }
+  return GPS_OK;
+}
+
+int gps_full_eval(gps_ctx* ctx, const double* theta, int score, double* obj, double* grad) {
+  if (!ctx) return GPS_EINVAL;
+  if (ctx->N == 0) return gps_fail(ctx, GPS_ESTATE, "full_eval: call gps_set_data first");
+  if (!theta || !obj || score < GPS_CRPS || score > GPS_DSS) return gps_fail(ctx, GPS_EINVAL, "full_eval: bad arguments (kc is a FITC objective)");
+  GPS_CUDA(cudaSetDevice(ctx->device));
+  const int64_t Np = ctx->Np;
+  const int D = ctx->D;
+  GPS_CHECK(gps_ensure_ws(ctx, Np));
+  double ea, sn2;
+  GPS_CHECK(gps_upload_params(ctx, theta, D, &ea, &sn2));
+  gemm_timing_begin(ctx);
+  bool stages_full = false;
+  GPS_CHECK(full_eval_enqueue(ctx, score, grad != nullptr, &stages_full));
+  double* par = ctx->params.p;
   double h[8 + 66];
   GPS_CUDA(cudaMemcpyAsync(h, par + PAR_OBJ, (size_t)(PAR_GSUM - PAR_OBJ + D + 2) * sizeof(double),
                            cudaMemcpyDeviceToHost, ctx->stream));
@@ -356,17 +368,86 @@ int gps_full_eval(gps_ctx* ctx, const double* theta, int score, double* obj, dou
   return GPS_OK;
 }
 
+// ---- the optimiser loop KF:237-260 with theta resident on the device ------------------------------------------------
+// theta_dev[D + 2] -> params (e^a, e^c, 1/l_d): what gps_upload_params does on the host
+__global__ void theta_params_kernel(const double* __restrict__ th, int D, double* __restrict__ par) {
+  const int t = threadIdx.x;
+  if (t == 0) par[0] = exp(th[0]);
+  else if (t == 1) par[1] = exp(th[D + 1]);
+  else if (t - 2 < D) par[t] = exp(-th[1 + (t - 2)]);
+}
+// theta -= lr * grad (noise entry with its e^c factor), trace[it] = objective before the step.  A failed
+// factorisation (info != 0; the next iteration's factorisation clears the flag) freezes theta and is latched.
+__global__ void full_update_kernel(double* __restrict__ th, const double* __restrict__ par, int D, double lr,
+                                   double* __restrict__ trace, int it, const int* __restrict__ info, int* __restrict__ fail) {
+  if (*info != 0 || fail[0] != 0) {
+    if (threadIdx.x == 0 && fail[0] == 0) {
+      fail[0] = *info;
+      fail[1] = it;
+    }
+    return;
+  }
+  const int t = threadIdx.x;
+  const double* gs = par + PAR_GSUM;
+  if (t < D + 1) th[t] -= lr * gs[t];
+  else if (t == D + 1) th[t] -= lr * par[1] * gs[t];
+  if (t == 0) trace[it] = par[PAR_OBJ];
+}
+
 int gps_full_descend(gps_ctx* ctx, double* theta, int score, double lr_theta, int iters, double* obj_trace) {
   if (!ctx) return GPS_EINVAL;
   if (!theta || iters < 0) return gps_fail(ctx, GPS_EINVAL, "full_descend: bad arguments");
   const int P = ctx->D + 2;
-  std::vector<double> g(P);
-  for (int it = 0; it < iters; ++it) {
-    double obj = 0.0;
-    GPS_CHECK(gps_full_eval(ctx, theta, score, &obj, g.data()));
-    if (obj_trace) obj_trace[it] = obj;
-    for (int k = 0; k < P; ++k) theta[k] -= lr_theta * g[k];   // KF:254-257
+  if (ctx->N == 0) return gps_fail(ctx, GPS_ESTATE, "full_descend: call gps_set_data first");
+  if (score < GPS_CRPS || score > GPS_DSS) return gps_fail(ctx, GPS_EINVAL, "full_descend: bad score");
+  if (score == GPS_DSS || iters == 0) {
+    // the 4-fold objective checks its fold factorisations on the host: one evaluation per round trip
+    std::vector<double> g(P);
+    for (int it = 0; it < iters; ++it) {
+      double obj = 0.0;
+      GPS_CHECK(gps_full_eval(ctx, theta, score, &obj, g.data()));
+      if (obj_trace) obj_trace[it] = obj;
+      for (int k = 0; k < P; ++k) theta[k] -= lr_theta * g[k];   // KF:254-257
+    }
+    return GPS_OK;
   }
+  // theta stays on the device: per iteration the parameter kernel, the whole evaluation and the update kernel are
+  // enqueued back to back; one synchronisation and read-back after the last iteration
+  GPS_CUDA(cudaSetDevice(ctx->device));
+  const int D = ctx->D;
+  GPS_CHECK(gps_ensure_ws(ctx, ctx->Np));
+  GPS_CHECK(gps_ensure(ctx, ctx->descend_buf, (size_t)P + (size_t)iters + 4));
+  double* d_th = ctx->descend_buf.p;
+  double* d_trace = d_th + P;
+  int* d_fail = reinterpret_cast<int*>(d_trace + iters);
+  GPS_CUDA(cudaMemcpyAsync(d_th, theta, (size_t)P * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  GPS_CUDA(cudaMemsetAsync(d_fail, 0, 2 * sizeof(int), ctx->stream));
+  GPS_CUDA(cudaStreamSynchronize(ctx->stream));   // theta may be pageable host memory
+  ctx->gemm_events_used = 0;
+  const bool timing = ctx->time_gemm;
+  ctx->time_gemm = false;
+  int rc = GPS_OK;
+  for (int it = 0; it < iters && rc == GPS_OK; ++it) {
+    theta_params_kernel<<<1, 96, 0, ctx->stream>>>(d_th, D, ctx->params.p);
+    bool sf = false;
+    rc = full_eval_enqueue(ctx, score, true, &sf);
+    if (rc != GPS_OK) break;
+    full_update_kernel<<<1, 96, 0, ctx->stream>>>(d_th, ctx->params.p, D, lr_theta, d_trace, it, ctx->d_info, d_fail);
+    ctx->launches += 2;
+  }
+  ctx->time_gemm = timing;
+  ctx->stage_valid = false;
+  GPS_CHECK(rc);
+  GPS_LAUNCH_CHECK();
+  int fail[2] = {0, 0};
+  GPS_CUDA(cudaMemcpyAsync(theta, d_th, (size_t)P * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  GPS_CUDA(cudaMemcpyAsync(fail, d_fail, sizeof fail, cudaMemcpyDeviceToHost, ctx->stream));
+  if (obj_trace)
+    GPS_CUDA(cudaMemcpyAsync(obj_trace, d_trace, (size_t)iters * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  GPS_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->loo_valid = false;
+  if (fail[0] != 0)
+    return gps_fail(ctx, GPS_ENOTPD, "full_descend: K + sn2 I not positive definite at pivot %d in iteration %d", fail[0], fail[1]);
   return GPS_OK;
 }
 

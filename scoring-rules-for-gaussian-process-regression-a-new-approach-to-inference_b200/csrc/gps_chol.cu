@@ -372,12 +372,29 @@ potf2_inv_dmma_kernel(double* __restrict__ K, double* __restrict__ Xinv, int64_t
 
 struct Node { int lo, mid, hi, depth; };
 
-void collect(int lo, int hi, int depth, std::vector<Node>& out) {
+// Split point of a TRTRI node.  Halving puts 39 % of all inversion flops into the top node's X phase
+// (X21 = -X22 P), which cannot start before the whole right half is factored AND inverted: with the merges
+// overlapped behind POTRF that phase is a 4.8 ms tail after the factorisation has finished (lane trace, round 2).
+// Large nodes are therefore split off-centre (pct % of the tiles to the left, rounded to the POTRF outer block so the
+// early P phase is released at an outer-step boundary): the late X phase shrinks with the square of the right part,
+// the work moves into the P phase, which runs while POTRF still leaves SMs idle.
+int split_point(int lo, int hi, int pct) {
+  const int n = hi - lo;
+  if (n < 16 || pct == 50) return lo + n / 2;
+  int mid = lo + (n * pct + 50) / 100;
+  const int al = (mid + GPS_POTRF_OB / 2) / GPS_POTRF_OB * GPS_POTRF_OB;
+  if (al > lo && al < hi) mid = al;
+  if (mid <= lo) mid = lo + 1;
+  if (mid >= hi) mid = hi - 1;
+  return mid;
+}
+
+void collect(int lo, int hi, int depth, int pct, std::vector<Node>& out) {
   if (hi - lo <= 1) return;
-  const int mid = lo + (hi - lo) / 2;
+  const int mid = split_point(lo, hi, pct);
   out.push_back({lo, mid, hi, depth});
-  collect(lo, mid, depth + 1, out);
-  collect(mid, hi, depth + 1, out);
+  collect(lo, mid, depth + 1, pct, out);
+  collect(mid, hi, depth + 1, pct, out);
 }
 
 }  // namespace
@@ -433,6 +450,9 @@ int gps_build_tasks(gps_ctx* ctx, int64_t Np) {
     for (int j = c1; j < n1; ++j)
       for (int i = n1; i < nb; ++i) push(i * T, j * T, c0 * T, c1 * T, i, j);
     ctx->potrf_trailA1[o].cnt = h.size() - ctx->potrf_trailA1[o].off;
+    // (super-tile order for this list and for LAUUM was measured in round 2: DRAM traffic of the (KC, KC) launches
+    // 14.3 -> 13.2 GB and LAUUM 4.0 -> 3.0 GB per evaluation, but LAUUM 10.41 -> 10.65 ms and no gain here — the
+    // launches are DMMA-bound at ~5 % of HBM bandwidth, so the plain orders stay)
     ctx->potrf_trailB[o].off = h.size();
     for (int j = n1; j < nb; ++j)
       for (int i = j; i < nb; ++i) push(i * T, j * T, c0 * T, c1 * T, i, j);
@@ -440,7 +460,7 @@ int gps_build_tasks(gps_ctx* ctx, int64_t Np) {
   }
   // TRTRI: nodes by depth, deepest first
   std::vector<Node> nodes;
-  collect(0, nb, 0, nodes);
+  collect(0, nb, 0, ctx->trtri_split_pct, nodes);
   int maxd = -1;
   for (auto& n : nodes) maxd = std::max(maxd, n.depth);
   ctx->trtri_p.clear();
@@ -500,7 +520,7 @@ int gps_build_tasks(gps_ctx* ctx, int64_t Np) {
     std::vector<Node> spine;
     int lo = 0, hi = nb;
     while (hi - lo > 1) {
-      const int mid = lo + (hi - lo) / 2;
+      const int mid = split_point(lo, hi, ctx->trtri_split_pct);
       Node n{lo, mid, hi, 0};
       const int step = (mid - 1) / OB;
       subtree(lo, mid, step);

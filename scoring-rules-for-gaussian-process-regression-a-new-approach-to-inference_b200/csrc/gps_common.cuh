@@ -76,6 +76,7 @@ struct gps_ctx {
   std::vector<gps_ctx*> fold_lanes;   // one lane context per DSS fold
   cudaEvent_t dss_fork = nullptr, dss_join[4] = {};
   DevBuf red;      // reduction scratch
+  DevBuf descend_buf;   // device-resident theta | objective trace | failure latch of gps_full_descend
   DevBuf params;   // device copy of theta-derived parameters
   int* d_info = nullptr;       // device: first failing pivot (0 = ok)
   GemmTask* d_tasks = nullptr; // device task lists (cached per ws_Np)
@@ -100,6 +101,7 @@ struct gps_ctx {
   cudaStream_t tri_stream = nullptr;            // overlapped TRTRI (lowest priority)
   cudaEvent_t fork_ev = nullptr, join_trail_ev = nullptr, join_tri_ev = nullptr;
   int overlap_trtri = 1;                        // 0: POTRF then TRTRI back to back (A/B knob)
+  int trtri_split_pct = 50;                     // share of a large TRTRI node's tiles that goes to its left child (A/B knob 9)
   // debug timeline of the factorisation lanes (knob 6): (code, event) pairs, code = lane * 1000 + outer step
   bool trace_on = false;
   std::vector<std::pair<int, cudaEvent_t>> trace;

@@ -258,10 +258,14 @@ __device__ __forceinline__ void mbar_expect_tx(unsigned long long* b, int bytes)
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(b)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(unsigned long long* b, int parity) {
-  asm volatile(
-      "{\n.reg .pred P1;\nWAIT_LOOP:\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n@P1 bra DONE;\nbra WAIT_LOOP;\nDONE:\n}\n" ::"r"(smem_u32(b)),
-      "r"(parity)
-      : "memory");
+  // no PTX labels: the function is inlined at several sites of one kernel
+  unsigned done;
+  do {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(done)
+                 : "r"(smem_u32(b)), "r"(parity)
+                 : "memory");
+  } while (!done);
 }
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, unsigned long long* bar, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n" ::"r"(smem_u32(dst)),
@@ -284,9 +288,9 @@ __device__ __forceinline__ double tma_frag(const unsigned char* tile, int row, i
 template <bool A_MC, bool B_MC, bool MIRROR>
 __global__ void __launch_bounds__(128, 2)
 gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, double* __restrict__ C,
-                int64_t ldc, double alpha, double beta, const GemmTask* __restrict__ tasks) {
+                int64_t ldc, double alpha, double beta, const GemmTask* __restrict__ tasks, int mode) {
   extern __shared__ unsigned char smem_raw[];
-  __shared__ unsigned long long full[TMA_STAGES];
+  __shared__ unsigned long long full[TMA_STAGES], empty[TMA_STAGES];
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   constexpr int TM = 64, MF = 4, NF = 8, WROWS = 32, WCOLS = 64, BK = 16, S = TMA_STAGES;   // 2 x 2 warps, 32 x 64 warp tiles
   GemmTask t = tasks[blockIdx.x >> 1];
@@ -299,7 +303,10 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int nk = (t.k1 - t.k0) / BK;
   if (tid == 0) {
 #pragma unroll
-    for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
+    for (int s = 0; s < S; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], mode == 2 ? 128 : 4);   // arrivals per phase: one per warp (mode 1) or per thread (mode 2)
+    }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   __syncthreads();
@@ -320,9 +327,23 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 #pragma unroll
     for (int j = 0; j < NF; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
   for (int kb = 0; kb < nk; ++kb) {
-    mbar_wait(&full[kb % S], (kb / S) & 1);
-    __syncthreads();                       // everyone is done with the slot the next load overwrites
-    if (tid == 0 && kb + S - 1 < nk) issue(kb + S - 1);
+    // No CTA-wide barrier in the main loop: the producer thread alone waits until all four warps have released the
+    // slot it is about to refill (the one read in iteration kb - 1), the other warps run ahead up to S - 1 stages.
+    if (mode == 0) {
+      mbar_wait(&full[kb % S], (kb / S) & 1);
+      __syncthreads();                     // everyone is done with the slot the next load overwrites
+      if (tid == 0 && kb + S - 1 < nk) issue(kb + S - 1);
+    } else {
+      if (tid == 0 && kb + S - 1 < nk) {
+        if (kb >= 1) mbar_wait(&empty[(kb - 1) % S], ((kb - 1) / S) & 1);
+        issue(kb + S - 1);
+      }
+      // the producer lane spins alone inside the branch above: bring warp 0 back together before the warp-wide
+      // mma.sync below (with independent thread scheduling the other 31 lanes are otherwise free to run ahead of
+      // it — a first build without this line produced wrong tiles now and then)
+      __syncwarp();
+      mbar_wait(&full[kb % S], (kb / S) & 1);
+    }
     const unsigned char* As = smem + (size_t)(kb % S) * TMA_STAGE_BYTES;
     const unsigned char* Bs = As + TMA_A_BYTES;
 #pragma unroll
@@ -337,6 +358,13 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       for (int i = 0; i < MF; ++i)
 #pragma unroll
         for (int j = 0; j < NF; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    }
+    if (mode == 1) {
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(&empty[kb % S])) : "memory");
+    } else if (mode == 2) {
+      asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+      asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(&empty[kb % S])) : "memory");
     }
   }
   double* tbuf = reinterpret_cast<double*>(smem);
@@ -423,7 +451,7 @@ int launch_tma_k(gps_ctx* ctx, const double* A, int64_t lda, const double* B, in
     GPS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TMA_SMEM));
     configured = true;
   }
-  kern<<<(unsigned)(ntasks * 2), 128, TMA_SMEM, ctx->stream>>>(ma, mb, C, ldc, alpha, beta, tasks);
+  kern<<<(unsigned)(ntasks * 2), 128, TMA_SMEM, ctx->stream>>>(ma, mb, C, ldc, alpha, beta, tasks, ctx->gemm_variant - 9);
   GPS_LAUNCH_CHECK();
   return GPS_OK;
 }
@@ -500,7 +528,7 @@ int gps_gemm_tasks(gps_ctx* ctx, int kind, const double* A, int64_t lda, const d
     if (ntasks * 8 <= (size_t)ctx->sm_count) strip = 16;
     else if (ntasks * 4 <= (size_t)ctx->sm_count) strip = 32;
   }
-  if (ctx->gemm_variant == 9 && strip == 0 && !dvec && (kind == GEMM_KC_KC || kind == GEMM_KC_MC || kind == GEMM_MC_MC)) {
+  if (ctx->gemm_variant >= 9 && ctx->gemm_variant <= 11 && strip == 0 && !dvec && (kind == GEMM_KC_KC || kind == GEMM_KC_MC || kind == GEMM_MC_MC)) {
     r = launch_tma(ctx, kind, mirror, A, lda, B, ldb, C, ldc, alpha, beta, d_tasks, ntasks);   // TMA-fed operand ring
   } else if (strip == 32) {
     r = dispatch<GemmCfg<32, 16, 3, 1, 4, false, 2>>(GPS_GEMM_ARGS);

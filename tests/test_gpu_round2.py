@@ -342,3 +342,32 @@ def test_example_contour_grid_writes_reference_layout(tmp_path):
         for (i, j) in ((5, 7), (20, 30), (49, 49), (12, 3)):
             want = fn(x, y, l_range[j], noise_range[i])
             assert abs(mat[i, j] - want) <= 1e-8 * max(1.0, abs(want)), (which, i, j)
+
+
+@pytest.mark.parametrize("score,lr", [("crps", 0.5), ("logs", 0.05), ("nlml", 5e-4)])
+def test_full_descend_device_resident_equals_host_loop(ctx, score, lr):
+    """gps_full_descend keeps theta on the device for crps / logs / nlml (parameter kernel, evaluation, update kernel
+    enqueued back to back, KF:237-260): identical trajectory to the loop driven one evaluation at a time."""
+    from gpscore_b200 import synth
+    X, y = synth.kin40k_like(700, seed=31)
+    theta = synth.hyper_point("P1")
+    ctx.set_data(_dev(X), _dev(y))
+    th, trace = theta.copy(), []
+    for _ in range(8):
+        v, g = ctx.full_eval(th, score)
+        trace.append(v)
+        th = th - lr * g
+    th2, tr2 = ctx.full_descend(theta, score, lr, 8)
+    assert relerr(tr2, np.array(trace)) <= 1e-12 and relerr(th2, th) <= 1e-12
+
+
+def test_full_descend_reports_failed_factorisation(ctx):
+    from gpscore_b200 import lib as L
+    rng = np.random.default_rng(2)
+    X = np.repeat(rng.standard_normal((40, 2)), 5, axis=0)          # duplicated rows ...
+    y = rng.standard_normal((200, 1))
+    ctx.set_data(_dev(X), _dev(y))
+    theta = np.array([0.0, 0.0, 0.0, -800.0])                       # ... and no noise: K is singular
+    with pytest.raises(L.NotPositiveDefinite):
+        ctx.full_descend(theta, "crps", 0.1, 3)
+    assert np.isfinite(ctx.full_eval(np.array([0.0, 0.0, 0.0, 0.0]), "crps")[0])

@@ -43,7 +43,7 @@ def main(src, dst):
         a[1] += t
         a[2] += d.get("dram__bytes_read.sum", 0) + d.get("dram__bytes_write.sum", 0)
         tot += t
-    gem = [d for d in seg if "gemm_tile" in d["name"]]
+    gem = [d for d in seg if "gemm_tile" in d["name"] or "gemm_tma" in d["name"]]
     out = {
         "source": "ncu launch list of tools/one_eval.py (second full-GP evaluation); times are cold-cache and "
                   "serialised: compare shares, not absolutes",
