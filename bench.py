@@ -495,11 +495,17 @@ def run_ours(args):
         cs.comm_init()
         cs.set_data(Xd[lo:hi].contiguous(), yd[lo:hi].contiguous())
         ms_s, (sv, sg, sgu) = timed(lambda: cs.fitc_eval_sharded(th0, U, "crps", N_FULL), steps_f, warm=5)
+        p2p = cs.comm_transport(True)
+        ms_sd, _ = timed(lambda: cs.fitc_descend_sharded(th0, U, "crps", N_FULL, 1e-3, 1e-3, iters_d), 3, warm=1)
         fitc["row_sharded_evals_per_s"] = 1e3 / ms_s
         fitc["row_sharded_ms_per_eval"] = ms_s
-        fitc["row_sharded_note"] = ("one evaluation split by rows over %d GPUs, 3 in-library NCCL all-reduces, no host "
-                                    "synchronisation between the passes; at N=10^4, M=20 it is latency bound, sharding "
-                                    "pays at N=10^6" % world)
+        fitc["row_sharded_descend_ms_per_iter"] = ms_sd / iters_d
+        fitc["row_sharded_transport"] = ("one-shot all-reduce over peer memory (cudaIpc mappings, NVLink) INSIDE the pass "
+                                         "kernels" if p2p else "ncclAllReduce between the pass kernels")
+        fitc["row_sharded_note"] = ("one evaluation split by rows over %d GPUs: the same three launches as on one GPU, the "
+                                    "accumulators exchanged inside them, no host synchronisation between the passes; at "
+                                    "N=10^4, M=20 it is latency bound (every rank still runs the replicated M x M algebra), "
+                                    "sharding pays at N=10^6" % world)
         # parity on hardware: the NCCL row-sharded result equals the single-GPU result of the same problem
         v1, g1, gu1 = ctx.fitc_eval(th0, U, "crps")
         gates.check("fitc20_N10000_sharded_vs_single", max(abs(sv - v1) / abs(v1), relmax(sg, g1), relmax(sgu, gu1)), SHARD_TOL,
@@ -521,18 +527,23 @@ def run_ours(args):
         run_big = lambda Uq: cb.fitc_eval_sharded(th0, Uq, "crps", N_BIG)
     steps_b = max(args.steps * 4, 20)
     ms_b, (bv, bg, bgu) = timed(lambda: run_big(U), steps_b, warm=3)
+    if world == 1:
+        ms_bd, _ = timed(lambda: cb.fitc_descend(th0, U, "crps", 1e-4, 1e-4, 100), 2, warm=1)
+    else:
+        ms_bd, _ = timed(lambda: cb.fitc_descend_sharded(th0, U, "crps", N_BIG, 1e-4, 1e-4, 100), 2, warm=1)
     bytes_b = 3 * 8 * N_BIG * (D + 1)
     flops_b = 9.9e3 * N_BIG
     fitc["sweep_N1e6_M20"] = {
         "workload": "synthetic 8-D FITC N=1e6 M=20 LOO-CRPS obj+grad; rows sharded over %d GPU(s)%s" % (
             world, "" if world == 1 else " with 3 in-library NCCL all-reduces per evaluation"),
-        "evals_per_s": 1e3 / ms_b, "ms_per_eval": ms_b, "algorithmic_bytes_per_eval": bytes_b,
+        "evals_per_s": 1e3 / ms_b, "ms_per_eval": ms_b, "descend_ms_per_iter": ms_bd / 100, "algorithmic_bytes_per_eval": bytes_b,
         "roofline": {"bound": "hbm", "achieved": bytes_b / (ms_b * 1e-3) / 1e9 / world, "peak": hbm_peak, "unit": "GB/s",
                      "frac": bytes_b / (ms_b * 1e-3) / 1e9 / world / hbm_peak, "peak_how": hbm_how,
                      "fp64_tflops": flops_b / (ms_b * 1e-3) / 1e12 / world,
                      "note": "per-GPU algorithmic bytes (3 passes x 8 N (D+1)) over the whole-evaluation time; the row "
-                             "passes do ~9.9 kflop/row of fp64 work (DESIGN.md §4), so this point is bound by the FP64 "
-                             "pipe, not by HBM: fp64_tflops is the per-GPU rate of that count"}}
+                             "passes do ~9.9 kflop/row of fp64 work (109 DMMA + ~1.1 k DFMA-class instructions per 8 rows, "
+                             "DESIGN.md §4), so this point is bound by the FP64 pipes, not by HBM: fp64_tflops is the per-GPU "
+                             "rate of that count; ncu pipe utilisation per pass in profiles/r02_ncu_fused_N1e6.txt"}}
     if rank == 0:
         from oracle import gp_oracle as O
         from oracle import woodbury as WB

@@ -32,16 +32,40 @@ def main(rep, out):
     hdr, units, data = rows[0], rows[1], rows[2:]
     src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
     stalls, cur, h = [], None, None
+    names = []
     for r in csv.reader(src.splitlines()):
         if r and r[0] == "Kernel Name":
             cur = {}
             stalls.append(cur)
+            names.append(r[1])
         elif r and r[0] == "Address":
             h = r
         elif cur is not None and h is not None and len(r) > 10:
             for i, c in enumerate(h):
                 if c.startswith("stall_") and "Not Issued" not in c and r[i]:
                     cur[c] = cur.get(c, 0) + int(r[i])
+    # the source page may list a launch more than once (several views): match the blocks to the raw rows by kernel
+    # name, in order, skipping repeated views of the same launch
+    def norm(n):
+        return "".join(ch for ch in n.replace("(int)", "").replace("(bool)", "") if not ch.isspace())
+    by_name = {}
+    for n, st in zip(names, stalls):
+        lst = by_name.setdefault(norm(n), [])
+        if not lst or lst[-1] != st:
+            lst.append(st)
+    counts = {}
+    for r in data:
+        counts[norm(r[hdr.index("Kernel Name")])] = counts.get(norm(r[hdr.index("Kernel Name")]), 0) + 1
+    matched = []
+    used = {}
+    for r in data:
+        n = norm(r[hdr.index("Kernel Name")])
+        lst = by_name.get(n, [])
+        step = max(1, len(lst) // max(1, counts[n]))
+        i = used.get(n, 0)
+        matched.append(lst[i * step] if i * step < len(lst) else {})
+        used[n] = i + 1
+    stalls = matched
     with open(out, "w") as f:
         f.write("source: %s (ncu --set full --clock-control none; one block per profiled launch)\n" % rep)
         for k, r in enumerate(data):
