@@ -21,6 +21,7 @@
 #include <cudaTypedefs.h>
 
 #include <map>
+#include <mutex>
 #include <tuple>
 
 #include "gps_common.cuh"
@@ -406,6 +407,7 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 struct TmaMaps {
   PFN_cuTensorMapEncodeTiled encode = nullptr;
   std::map<std::tuple<const void*, int64_t, int, int>, CUtensorMap> cache;
+  std::mutex mu;   // contexts may be driven from different host threads; the cache is process-wide
 };
 TmaMaps g_tma;
 
@@ -413,6 +415,7 @@ TmaMaps g_tma;
 // 128-byte swizzle; MC (panel index contiguous): box {rows, 16}, dense.  The row extent is left unbounded (the map is
 // only used with in-range coordinates; the buffer's true height is not known here).
 int tma_map(gps_ctx* ctx, const double* base, int64_t ld, int panel_rows, bool mc, CUtensorMap* out) {
+  std::lock_guard<std::mutex> lock(g_tma.mu);
   if (!g_tma.encode) {
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
