@@ -49,6 +49,8 @@ def _as_f64(a, device=None):
 
 
 def _host_vec(a):
+    if isinstance(a, np.ndarray) and a.dtype == np.float64 and a.flags.c_contiguous:
+        return a.reshape(-1)
     if isinstance(a, torch.Tensor):
         a = a.detach().cpu().double().numpy()
     return np.ascontiguousarray(np.asarray(a, dtype=np.float64).ravel())
@@ -62,6 +64,20 @@ def _scalar(v):
     if isinstance(v, torch.Tensor):
         return float(v.detach().reshape(-1)[0])
     return float(np.asarray(v).reshape(-1)[0])
+
+
+class _IO:
+    """Host-side staging of one evaluation's small arguments (theta, U -> objective, gradients) with the ctypes
+    pointers made once: building five `ndarray.ctypes.data_as(...)` pointers and three fresh arrays per call costs
+    more host time than the three kernel launches of a FITC evaluation."""
+
+    def __init__(self, D, M):
+        self.th = np.zeros(D + 2)
+        self.U = np.zeros(max(M * D, 1))
+        self.obj = np.zeros(1)
+        self.g = np.zeros(D + 2)
+        self.gU = np.zeros(max(M * D, 1))
+        self.p_th, self.p_U, self.p_obj, self.p_g, self.p_gU = (_dp(a) for a in (self.th, self.U, self.obj, self.g, self.gU))
 
 
 class Context:
@@ -84,6 +100,7 @@ class Context:
         self._data_key = None
         self._pinned = False        # set_stream(stream) pins; otherwise torch's current stream is followed
         self._cur_stream = None
+        self._io_cache = {}
 
     def close(self):
         if getattr(self, "_h", None):
@@ -123,6 +140,13 @@ class Context:
         self._y_train = y           # mean / unbiased variance of the targets (KF:113-114) are formed on first use
         self._y_stats = None
 
+    def _io(self, M):
+        key = (self.D, M)
+        io = self._io_cache.get(key)
+        if io is None:
+            io = self._io_cache[key] = _IO(self.D, M)
+        return io
+
     def _theta(self, theta):
         th = _host_vec(theta)
         if th.size == 3 and self.D > 1:  # isotropic 1-element para_l (K20:422): broadcast (KF:8)
@@ -135,12 +159,11 @@ class Context:
     def full_eval(self, theta, score, grad=True):
         """Objective and gradient wrt theta = [a, b_1..b_D, c] (KF:239-252 / 329-339 / 416-428)."""
         self._enter()
-        th = self._theta(theta)
-        obj = np.zeros(1)
-        g = np.zeros(self.D + 2)
+        io = self._io(0)
+        io.th[:] = self._theta(theta)
         sc = _L.SCORES[score] if isinstance(score, str) else int(score)
-        self._check(self._lib.gps_full_eval(self._h, _dp(th), sc, _dp(obj), _dp(g) if grad else None))
-        return float(obj[0]), (g if grad else None)
+        self._check(self._lib.gps_full_eval(self._h, io.p_th, sc, io.p_obj, io.p_g if grad else None))
+        return float(io.obj[0]), (io.g.copy() if grad else None)
 
     def full_descend(self, theta, score, lr, iters):
         """`iters` steps of the scripts' fixed-step gradient descent (KF:237-260) in one call.
@@ -187,15 +210,14 @@ class Context:
     def fitc_eval(self, theta, U, score, jitter=JITTER):
         """Objective and gradients (theta, inducing inputs) of K20:222-236 / 329-344 / 434-452."""
         self._enter()
-        th = self._theta(theta)
         Uh = _host_vec(U)
         M = Uh.size // self.D
-        obj = np.zeros(1)
-        g = np.zeros(self.D + 2)
-        gU = np.zeros(M * self.D)
+        io = self._io(M)
+        io.th[:] = self._theta(theta)
+        io.U[:] = Uh
         sc = _L.SCORES[score] if isinstance(score, str) else int(score)
-        self._check(self._lib.gps_fitc_eval(self._h, _dp(th), _dp(Uh), M, float(jitter), sc, _dp(obj), _dp(g), _dp(gU)))
-        return float(obj[0]), g, gU.reshape(M, self.D)
+        self._check(self._lib.gps_fitc_eval(self._h, io.p_th, io.p_U, M, float(jitter), sc, io.p_obj, io.p_g, io.p_gU))
+        return float(io.obj[0]), io.g.copy(), io.gU.copy().reshape(M, self.D)
 
     def fitc_acc_len(self, M):
         a, b, c = C.c_int64(), C.c_int64(), C.c_int64()
