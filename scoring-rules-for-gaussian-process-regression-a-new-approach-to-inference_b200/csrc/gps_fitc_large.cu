@@ -16,8 +16,10 @@
 //
 // Everything per-row (lambda, d, alpha, the score seeds, lambda_bar) is a column pass over the
 // [Mp][Npp] matrices with i as the coalesced index.  Pad rows (m >= M) and pad columns (i >= N)
-// hold zeros throughout, so no kernel needs bounds in the GEMMs.  Single GPU; LOO CRPS / log score
-// and NLML (the block objectives stay with the fused M <= 32 kernels).
+// hold zeros throughout, so no kernel needs bounds in the GEMMs.  LOO CRPS / log score and NLML on one
+// GPU or row-sharded; the 4-fold block objectives (DSS K20:538-587, block CRPS "kc" K20:669-720) on one GPU:
+// per fold the M x M matrices P_f = W_f Lam_f^-1 W_f', H_f = I - P_f (factorised on the child context) and
+// two [Mp][fold columns] products (H^-1 W_f / Hbar_f W_f) — see the "block objectives" section below.
 #include "gps_common.cuh"
 
 namespace {
@@ -25,9 +27,13 @@ namespace {
 constexpr int DMAX = 16;
 constexpr double HALF_LOG_2PI = 0.91893853320467274178;
 
-enum { SM_KUU = 0, SM_LA, SM_LAI, SM_LC, SM_LCI, SM_R, SM_SW, SM_Y, SM_Z, SM_CBAR, SM_S, SM_ABAR, SM_COUNT };
+enum { SM_KUU = 0, SM_LA, SM_LAI, SM_LC, SM_LCI, SM_R, SM_SW, SM_Y, SM_Z, SM_CBAR, SM_S, SM_ABAR, SM_COUNT,
+       // block objectives only (allocated on first use): P_f, L_H, L_H^-1, H^-1, Hhat / Hbar, E, one scratch
+       SM_PF = SM_COUNT, SM_LH, SM_LHI, SM_HINV, SM_HX, SM_E, SM_X2, SM_COUNT_BLOCK };
 enum { RV_LAM = 0, RV_IL, RV_YL, RV_R, RV_ABAR, RV_DBAR, RV_LBAR, RV_RBAR, RV_TBAR, RV_LOOM, RV_LOOV, RV_COUNT };
-enum { MV_VY = 0, MV_BETA, MV_BBAR, MV_VYBAR, MV_COUNT };
+// block objectives: aliases of slots the LOO scores use (R, DBAR, LOOM, LOOV are free there)
+enum { RV_FV = RV_R, RV_MBAR = RV_DBAR, RV_CBARV = RV_LOOM, RV_ROWOBJ = RV_LOOV };
+enum { MV_VY = 0, MV_BETA, MV_BBAR, MV_VYBAR, MV_G, MV_H, MV_HBAR, MV_GBAR, MV_COUNT };
 // small results copied to the host: [0] obj, [1] sum lambda_bar, then two gradient blocks
 constexpr int OUT_OBJ = 0, OUT_LOGDET = 2, OUT_G1 = 8;
 
@@ -38,6 +44,14 @@ struct gps_fitc_large {
   int Mp = 0, M = 0, D = 0;
   DevBuf Kuf, V, W, T1, T2;   // [Mp][Npp]
   DevBuf sm, rv, mv, part, out, U, dotp, acc;
+  DevBuf fs;                  // block objectives: per-fold scalars [4][2] = (sum log diag L_H, g.h)
+  GemmTask* ftasks = nullptr; // block objectives: split-K task lists of the four folds' column ranges
+  size_t ftasks_cap = 0;
+  gps_ctx::Range t_fold[4];
+  int fold_S[4] = {0, 0, 0, 0};
+  int64_t fold_key_N = -1;
+  int fold_key_Mp = -1, fold_key_S = -1;
+  bool block_seeds = false;   // pass 2 left the block objectives' direct dL/dW in T2
   GemmTask* tasks = nullptr;
   size_t tasks_cap = 0;
   gps_ctx::Range t_low, t_up, t_full, t_mm, t_sk_low, t_sk_full;
@@ -236,14 +250,14 @@ seed_kernel(int64_t N, int64_t Npp, int nlml, const double* __restrict__ il, con
   tbar[i] = -ab * l;
 }
 
-// SW = beta bbar' + 2 R + bbar beta'
+// SW = beta bbar' + rs R + bbar beta'   (rs = 2 for R = W diag(rbar) W', 1 for the block objectives' G_W)
 __global__ void __launch_bounds__(256)
 sw_kernel(const double* __restrict__ beta, const double* __restrict__ bbar, const double* __restrict__ R, int Mp,
-          double* __restrict__ SW) {
+          double rs, double* __restrict__ SW) {
   const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= (int64_t)Mp * Mp) return;
   const int r = (int)(e / Mp), c = (int)(e - (int64_t)r * Mp);
-  SW[e] = beta[r] * bbar[c] + 2.0 * R[e] + bbar[r] * beta[c];
+  SW[e] = beta[r] * bbar[c] + rs * R[e] + bbar[r] * beta[c];
 }
 
 // Lbar = -tril(Y) (+ diag(1/L_mm) for the log-determinant term of the NLML)
@@ -267,12 +281,210 @@ phi_sym_kernel(const double* __restrict__ P, int Mp, double* __restrict__ Z) {
   Z[e] = c <= r ? P[e] : P[(int64_t)c * Mp + r];
 }
 
+// ---- block objectives (4-fold DSS K20:538-587, block CRPS "kc" K20:669-720): element-wise kernels ---------
+// Algebra: oracle/woodbury.py::fitc_block_obj_grad.  A fold is a contiguous range [lo, hi) of columns.
+
+constexpr double INV_SQRT_PI = 0.56418958354775628695;
+constexpr double INV_SQRT_2PI = 0.39894228040143267794;
+constexpr double INV_SQRT2 = 0.70710678118654752440;
+
+// out[i] = src[i] inside [lo, hi), 0 in the rest of the 16-rounded range [lo_r, hi_r) the GEMM k-range covers
+__global__ void __launch_bounds__(256)
+mask_range_kernel(const double* __restrict__ src, int64_t lo, int64_t hi, int64_t lo_r, int64_t hi_r,
+                  double* __restrict__ out) {
+  const int64_t i = lo_r + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= hi_r) return;
+  out[i] = (i >= lo && i < hi) ? src[i] : 0.0;
+}
+
+// H = I - P
+__global__ void __launch_bounds__(256)
+h_from_p_kernel(const double* __restrict__ P, int Mp, double* __restrict__ H) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (int64_t)Mp * Mp) return;
+  H[e] = ((e / Mp) == (e % Mp) ? 1.0 : 0.0) - P[e];
+}
+
+// fs[0] = sum_m log diag(L_H), fs[1] = g . h
+__global__ void __launch_bounds__(256)
+fold_scalar_kernel(const double* __restrict__ LH, int Mp, int M, const double* __restrict__ g,
+                   const double* __restrict__ h, double* __restrict__ fs) {
+  __shared__ double sh[32];
+  double s = 0.0, t = 0.0;
+  for (int m = threadIdx.x; m < M; m += blockDim.x) {
+    s += log(LH[(int64_t)m * Mp + m]);
+    t = fma(g[m], h[m], t);
+  }
+  s = block_sum(s, sh);
+  if (threadIdx.x == 0) fs[0] = s;
+  t = block_sum(t, sh);
+  if (threadIdx.x == 0) fs[1] = t;
+}
+
+// DSS: Hhat = -1/2 H^-1 - 1/2 h h'
+__global__ void __launch_bounds__(256)
+hhat_kernel(const double* __restrict__ Hinv, const double* __restrict__ h, int Mp, int M, double* __restrict__ out) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (int64_t)Mp * Mp) return;
+  const int r = (int)(e / Mp), c = (int)(e - (int64_t)r * Mp);
+  out[e] = (r < M && c < M) ? -0.5 * Hinv[e] - 0.5 * h[r] * h[c] : 0.0;
+}
+
+// kc: Hbar = -(H^-1 E H^-1) - 1/2 (gbar h' + h gbar')
+__global__ void __launch_bounds__(256)
+hbar_kernel(const double* __restrict__ Z, const double* __restrict__ h, const double* __restrict__ gbar, int Mp, int M,
+            double* __restrict__ out) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (int64_t)Mp * Mp) return;
+  const int r = (int)(e / Mp), c = (int)(e - (int64_t)r * Mp);
+  out[e] = (r < M && c < M) ? -Z[e] - 0.5 * (gbar[r] * h[c] + h[r] * gbar[c]) : 0.0;
+}
+
+// x <- -x (hbar = -(W_f mbar))
+__global__ void __launch_bounds__(256)
+negate_kernel(double* __restrict__ x, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) x[i] = -x[i];
+}
+
+// DSS column sweep of one fold: T = Hhat W_f
+//   abar_i = lam_i alpha_i + W_i.h ; lam_bar0_i = 1/(2 lam) + alpha^2/2 + (W_i.T_i)/lam^2
+//   D_i = -2 T_i/lam_i + h alpha_i ; row objective 1/2 log lam + 1/2 lam alpha^2
+__global__ void __launch_bounds__(256)
+col_dss_kernel(const double* __restrict__ W, const double* __restrict__ T, double* __restrict__ Dm, int64_t ld, int M,
+               int64_t lo, int64_t hi, const double* __restrict__ h, const double* __restrict__ lam,
+               const double* __restrict__ alpha, double* __restrict__ abar, double* __restrict__ lbar0,
+               double* __restrict__ rowobj) {
+  const int64_t i = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= hi) return;
+  const double l = lam[i], il = 1.0 / l, al = alpha[i];
+  rowobj[i] = 0.5 * log(l) + 0.5 * l * al * al;
+  if (!T) return;                                      // objective only
+  double hw = 0.0, q = 0.0;
+  for (int m = 0; m < M; ++m) {
+    const int64_t o = (int64_t)m * ld + i;
+    const double w = W[o], t = T[o];
+    hw = fma(w, h[m], hw);
+    q = fma(w, t, q);
+    Dm[o] = fma(-2.0 * il, t, h[m] * al);
+  }
+  abar[i] = l * al + hw;
+  lbar0[i] = 0.5 * il + 0.5 * al * al + q * il * il;
+}
+
+// kc column sweep A of one fold: T = H^-1 W_f.  Fold predictive mu_i = y_i - lam_i alpha_i - W_i.h,
+// c_i = lam_i + W_i.T_i; CRPS share (mean over the fold), seeds mbar_i, cbar_i; D_i = -h mbar_i + 2 T_i cbar_i
+__global__ void __launch_bounds__(256)
+col_kca_kernel(const double* __restrict__ W, const double* __restrict__ T, double* __restrict__ Dm, int64_t ld, int M,
+               int64_t lo, int64_t hi, const double* __restrict__ h, const double* __restrict__ lam,
+               const double* __restrict__ alpha, double inv_nf, double* __restrict__ mbar, double* __restrict__ cbar,
+               double* __restrict__ rowobj) {
+  const int64_t i = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= hi) return;
+  double hw = 0.0, q = 0.0;
+  for (int m = 0; m < M; ++m) {
+    const int64_t o = (int64_t)m * ld + i;
+    const double w = W[o];
+    hw = fma(w, h[m], hw);
+    q = fma(w, T[o], q);
+  }
+  const double l = lam[i];
+  const double sd = sqrt(l + q);
+  const double z = (l * alpha[i] + hw) / sd;          // (y - mu)/sd
+  const double tpm1 = erf(z * INV_SQRT2);
+  const double pdf = INV_SQRT_2PI * exp(-0.5 * z * z);
+  rowobj[i] = sd * (z * tpm1 + 2.0 * pdf - INV_SQRT_PI) * inv_nf;
+  const double mb = -tpm1 * inv_nf;
+  const double cb = (2.0 * pdf - INV_SQRT_PI) / (2.0 * sd) * inv_nf;
+  mbar[i] = mb;
+  cbar[i] = cb;
+  for (int m = 0; m < M; ++m) {
+    const int64_t o = (int64_t)m * ld + i;
+    Dm[o] = fma(2.0 * cb, T[o], -h[m] * mb);
+  }
+}
+
+// kc column sweep B: T = Hbar W_f.  abar_i = -mbar lam + W_i.gbar ; lam_bar0 = -mbar alpha + cbar + (W_i.T_i)/lam^2 ;
+// D_i += gbar alpha_i - 2 T_i/lam_i
+__global__ void __launch_bounds__(256)
+col_kcb_kernel(const double* __restrict__ W, const double* __restrict__ T, double* __restrict__ Dm, int64_t ld, int M,
+               int64_t lo, int64_t hi, const double* __restrict__ gbar, const double* __restrict__ lam,
+               const double* __restrict__ alpha, const double* __restrict__ mbar, const double* __restrict__ cbar,
+               double* __restrict__ abar, double* __restrict__ lbar0) {
+  const int64_t i = lo + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= hi) return;
+  const double l = lam[i], il = 1.0 / l, al = alpha[i];
+  double gw = 0.0, q = 0.0;
+  for (int m = 0; m < M; ++m) {
+    const int64_t o = (int64_t)m * ld + i;
+    const double w = W[o], t = T[o];
+    gw = fma(w, gbar[m], gw);
+    q = fma(w, t, q);
+    Dm[o] += fma(-2.0 * il, t, gbar[m] * al);
+  }
+  abar[i] = -mbar[i] * l + gw;
+  lbar0[i] = -mbar[i] * al + cbar[i] + q * il * il;
+}
+
+// DSS: GW += X (= -2 Hhat P_f) + h g' ; bbar -= h
+__global__ void __launch_bounds__(256)
+gw_dss_kernel(const double* __restrict__ X, const double* __restrict__ h, const double* __restrict__ g, int Mp,
+              double* __restrict__ GW, double* __restrict__ bbar) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (int64_t)Mp * Mp) return;
+  const int r = (int)(e / Mp), c = (int)(e - (int64_t)r * Mp);
+  GW[e] += X[e] + h[r] * g[c];
+  if (c == 0) bbar[r] -= h[r];
+}
+
+// kc: GW += h hbar' + 2 Y (= H^-1 E) + gbar g' + X (= -2 Hbar P_f) ; bbar += -hbar - P_f gbar
+__global__ void __launch_bounds__(256)
+gw_kc_kernel(const double* __restrict__ X, const double* __restrict__ Y, const double* __restrict__ P,
+             const double* __restrict__ h, const double* __restrict__ hbar, const double* __restrict__ g,
+             const double* __restrict__ gbar, int Mp, double* __restrict__ GW, double* __restrict__ bbar) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (int64_t)Mp * Mp) return;
+  const int r = (int)(e / Mp), c = (int)(e - (int64_t)r * Mp);
+  GW[e] += h[r] * hbar[c] + 2.0 * Y[e] + gbar[r] * g[c] + X[e];
+  if (c == 0) {
+    double s = 0.0;
+    for (int k = 0; k < Mp; ++k) s = fma(P[(int64_t)r * Mp + k], gbar[k], s);
+    bbar[r] -= hbar[r] + s;
+  }
+}
+
+// seeds of the shared adjoint chain: tbar = -abar/lam ; lam_bar = lam_bar0 - abar alpha/lam ; rbar = 0
+__global__ void __launch_bounds__(256)
+block_seed_kernel(int64_t N, int64_t Npp, const double* __restrict__ il, const double* __restrict__ alpha,
+                  const double* __restrict__ abar, double* __restrict__ lbar, double* __restrict__ rbar,
+                  double* __restrict__ tbar) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Npp) return;
+  rbar[i] = 0.0;
+  if (i >= N) {
+    lbar[i] = 0.0; tbar[i] = 0.0;
+    return;
+  }
+  const double l = il[i], ab = abar[i];
+  lbar[i] -= ab * alpha[i] * l;
+  tbar[i] = -ab * l;
+}
+
+// objective: rows' sum (+ DSS: sum_f nf/2 log 2pi - sum log diag L_H_f + 1/2 g_f.h_f), fixed order
+__global__ void block_obj_kernel(const double* __restrict__ rows, const double* __restrict__ fs, int dss, double nf,
+                                 double* __restrict__ obj) {
+  double v = rows[0];
+  if (dss)
+    for (int f = 0; f < 4; ++f) v += nf * HALF_LOG_2PI - fs[2 * f] + 0.5 * fs[2 * f + 1];
+  obj[0] = v;
+}
+
 // pass 3 column sweep: lam_bar -= (bbar . W_:i) y_i/lam^2 + (V_:i . CV_:i)/lam^2 ; W <- Wbar in place
 __global__ void __launch_bounds__(256)
 col_pass3_kernel(const double* __restrict__ V, const double* __restrict__ CV, double* __restrict__ W, int64_t ld,
                  int M, int64_t N, const double* __restrict__ bbar, const double* __restrict__ beta,
                  const double* __restrict__ y, const double* __restrict__ il, const double* __restrict__ tbar,
-                 const double* __restrict__ rbar, double* __restrict__ lbar) {
+                 const double* __restrict__ rbar, double* __restrict__ lbar, const double* __restrict__ Dm) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
   const double tb = tbar[i], rb2 = 2.0 * rbar[i];
@@ -282,7 +494,8 @@ col_pass3_kernel(const double* __restrict__ V, const double* __restrict__ CV, do
     const double w = W[o];
     bw = fma(bbar[m], w, bw);
     s1 = fma(V[o], CV[o], s1);
-    W[o] = fma(rb2, w, tb * beta[m]);
+    // LOO scores: Wbar = beta tbar' + 2 W diag(rbar); block objectives: beta tbar' + D (the direct dL/dW)
+    W[o] = Dm ? fma(tb, beta[m], Dm[o]) : fma(rb2, w, tb * beta[m]);
   }
   const double l = il[i];
   lbar[i] -= (bw * y[i] + s1) * l * l;
@@ -570,7 +783,7 @@ int ensure_child(gps_ctx* ctx, gps_fitc_large* fl) {
   return GPS_OK;
 }
 
-int setup(gps_ctx* ctx, int M) {
+int setup(gps_ctx* ctx, int M, bool block) {
   if (!ctx->fl) ctx->fl = new gps_fitc_large();
   gps_fitc_large* fl = ctx->fl;
   const int Mp = (int)gps_pad(M);
@@ -586,7 +799,6 @@ int setup(gps_ctx* ctx, int M) {
     GPS_CHECK(gps_ensure(ctx, fl->W, big));
     GPS_CHECK(gps_ensure(ctx, fl->T1, big));
     GPS_CHECK(gps_ensure(ctx, fl->T2, big));
-    GPS_CHECK(gps_ensure(ctx, fl->sm, (size_t)SM_COUNT * Mp * Mp));
     GPS_CHECK(gps_ensure(ctx, fl->rv, (size_t)RV_COUNT * Npp));
     GPS_CHECK(gps_ensure(ctx, fl->mv, (size_t)MV_COUNT * Mp));
     GPS_CHECK(gps_ensure(ctx, fl->U, (size_t)Mp * D));
@@ -596,6 +808,8 @@ int setup(gps_ctx* ctx, int M) {
     GPS_CHECK(gps_ensure(ctx, fl->part, std::max((size_t)fl->S * Mp * Mp, kg)));
     GPS_CHECK(gps_ensure(ctx, fl->out, (size_t)OUT_G1 + 2 * (1 + DMAX + (size_t)Mp * D)));
   }
+  // nothing in `sm` outlives an evaluation except the factors begin() writes after this point
+  GPS_CHECK(gps_ensure(ctx, fl->sm, (size_t)(block ? SM_COUNT_BLOCK : SM_COUNT) * Mp * Mp));
   // the Gram kernel writes only the live M x N block: the pad rows/columns must read as zeros
   if (reshape || fl->kuf_M != M || fl->kuf_N != ctx->N) {
     GPS_CUDA(cudaMemsetAsync(fl->Kuf.p, 0, (size_t)Mp * Npp * sizeof(double), ctx->stream));
@@ -721,14 +935,180 @@ int kgrad_any(gps_ctx* ctx, gps_fitc_large* fl, const double* Kbar, const double
   return kgrad<1, 16, false>(ctx, fl, Kbar, Kmat, ld, n, P, out);
 }
 
+// ---- block objectives: host side -----------------------------------------------------------------------
+// split-K task lists of the four folds: fold f contracts over its 16-rounded column range, the operands'
+// stray columns inside that range are zeroed by the masked k-scaling vector
+int build_fold_tasks(gps_ctx* ctx, gps_fitc_large* fl, int64_t N) {
+  if (fl->fold_key_N == N && fl->fold_key_Mp == fl->Mp && fl->fold_key_S == fl->S && fl->ftasks) return GPS_OK;
+  const int mt = fl->Mp / GPS_TILE, Mp = fl->Mp;
+  const int64_t nf = N / 4;
+  std::vector<GemmTask> h;
+  for (int f = 0; f < 4; ++f) {
+    const int64_t lo_r = (f * nf) & ~(int64_t)15, hi_r = std::min<int64_t>(fl->Npp, ((f + 1) * nf + 15) & ~(int64_t)15);
+    const int64_t blocks = (hi_r - lo_r) / 16;
+    int64_t Sf = std::max<int64_t>(1, std::min<int64_t>((fl->S + 3) / 4, (blocks + 7) / 8));
+    const int64_t per = ((blocks + Sf - 1) / Sf) * 16;
+    Sf = (hi_r - lo_r + per - 1) / per;
+    fl->fold_S[f] = (int)Sf;
+    fl->t_fold[f].off = h.size();
+    for (int s = 0; s < (int)Sf; ++s) {
+      const int k0 = (int)(lo_r + s * per), k1 = (int)std::min<int64_t>(hi_r, lo_r + (s + 1) * per);
+      for (int i = 0; i < mt; ++i)
+        for (int j = 0; j <= i; ++j)
+          h.push_back(make_task(i * GPS_TILE, j * GPS_TILE, k0, k1, s * Mp + i * GPS_TILE, j * GPS_TILE));
+    }
+    fl->t_fold[f].cnt = h.size() - fl->t_fold[f].off;
+  }
+  if (h.size() > fl->ftasks_cap) {
+    if (fl->ftasks) cudaFree(fl->ftasks);
+    fl->ftasks = nullptr;
+    GPS_CUDA(cudaMalloc(&fl->ftasks, h.size() * sizeof(GemmTask)));
+    fl->ftasks_cap = h.size();
+  }
+  GPS_CUDA(cudaMemcpyAsync(fl->ftasks, h.data(), h.size() * sizeof(GemmTask), cudaMemcpyHostToDevice, ctx->stream));
+  GPS_CUDA(cudaStreamSynchronize(ctx->stream));
+  fl->fold_key_N = N; fl->fold_key_Mp = fl->Mp; fl->fold_key_S = fl->S;
+  return GPS_OK;
+}
+
+// out (Mp x Mp, full symmetric) = W_f diag(src_f) W_f' over the columns [lo, hi) of fold f
+int fold_splitk(gps_ctx* ctx, gps_fitc_large* fl, int f, int64_t lo, int64_t hi, const double* src, double* out) {
+  const int64_t lo_r = lo & ~(int64_t)15, hi_r = std::min<int64_t>(fl->Npp, (hi + 15) & ~(int64_t)15);
+  double* fv = fl->rv.p + RV_FV * fl->Npp;
+  mask_range_kernel<<<blocks_for(hi_r - lo_r), 256, 0, ctx->stream>>>(src, lo, hi, lo_r, hi_r, fv);
+  GPS_LAUNCH_CHECK();
+  GPS_CHECK(gps_gemm_tasks(ctx, GEMM_KC_KC, fl->W.p, fl->Npp, fl->W.p, fl->Npp, fl->part.p, fl->Mp, 1.0, 0.0, fv, false,
+                           fl->ftasks + fl->t_fold[f].off, fl->t_fold[f].cnt));
+  splitk_reduce_kernel<<<blocks_for((int64_t)fl->Mp * fl->Mp), 256, 0, ctx->stream>>>(fl->part.p, fl->fold_S[f], fl->Mp,
+                                                                                      out, 1, 0);
+  GPS_LAUNCH_CHECK();
+  ctx->launches += 2;
+  return GPS_OK;
+}
+
+// out[m] = sum over the fold's columns of W[m][i] src[i]
+int fold_rowdot(gps_ctx* ctx, gps_fitc_large* fl, int64_t lo, int64_t hi, const double* src, double* out) {
+  const int64_t lo_r = lo & ~(int64_t)15, hi_r = std::min<int64_t>(fl->Npp, (hi + 15) & ~(int64_t)15);
+  double* fv = fl->rv.p + RV_FV * fl->Npp;
+  mask_range_kernel<<<blocks_for(hi_r - lo_r), 256, 0, ctx->stream>>>(src, lo, hi, lo_r, hi_r, fv);
+  GPS_LAUNCH_CHECK();
+  ctx->launches++;
+  return rowdot(ctx, fl, fl->W.p + lo_r, fl->Npp, fl->Mp, hi_r - lo_r, fv + lo_r, out);
+}
+
+// T1[:, the fold's column tiles] = Mat (Mp x Mp) W
+int fold_apply(gps_ctx* ctx, gps_fitc_large* fl, int64_t lo, int64_t hi, const double* Mat) {
+  const int mt = fl->Mp / GPS_TILE;
+  const int64_t j0 = lo / GPS_TILE, j1 = (hi + GPS_TILE - 1) / GPS_TILE;
+  return gps_gemm_tasks(ctx, GEMM_KC_MC, Mat, fl->Mp, fl->W.p, fl->Npp, fl->T1.p, fl->Npp, 1.0, 0.0, nullptr, false,
+                        fl->tasks + fl->t_full.off + j0 * mt, (size_t)((j1 - j0) * mt));
+}
+
+// Pass 2 of the block objectives, after W / alpha / lambda: per fold the M x M chain and the column sweeps that
+// leave the seeds (tbar, lam_bar0, D in T2) of the shared adjoint chain; acc2 = [G_W | beta_bar | obj]
+int block_pass2(gps_ctx* ctx, double* acc2, bool want_grad) {
+  gps_fitc_large* fl = ctx->fl;
+  auto& f = ctx->fitc;
+  gps_ctx* ch = fl->ch;
+  const int64_t N = ctx->N, Npp = fl->Npp, nf = N / 4;
+  const int Mp = fl->Mp, M = fl->M;
+  const size_t MM = (size_t)Mp * Mp;
+  const bool dss = f.score == GPS_DSS;
+  cudaStream_t st = ctx->stream;
+  double *sm = fl->sm.p, *rv = fl->rv.p, *mv = fl->mv.p;
+  const double* alpha = f.rowv.p + 4 * N;
+  const unsigned nbm = blocks_for((int64_t)MM);
+  GPS_CHECK(build_fold_tasks(ctx, fl, N));
+  GPS_CHECK(gps_ensure(ctx, fl->fs, 8));
+  double *GW = acc2, *bbar = acc2 + MM, *d_obj = acc2 + MM + Mp;
+  GPS_CUDA(cudaMemsetAsync(acc2, 0, (MM + Mp + 2) * sizeof(double), st));
+  double *Pf = sm + SM_PF * MM, *LH = sm + SM_LH * MM, *LHi = sm + SM_LHI * MM, *Hinv = sm + SM_HINV * MM,
+         *HX = sm + SM_HX * MM, *E = sm + SM_E * MM, *X2 = sm + SM_X2 * MM, *Y = sm + SM_Y * MM, *Z = sm + SM_Z * MM;
+  double *g = mv + MV_G * Mp, *h = mv + MV_H * Mp, *hbar = mv + MV_HBAR * Mp, *gbar = mv + MV_GBAR * Mp;
+  double *lam = rv + RV_LAM * Npp, *il = rv + RV_IL * Npp, *abar = rv + RV_ABAR * Npp, *lbar = rv + RV_LBAR * Npp,
+         *mbar = rv + RV_MBAR * Npp, *cbar = rv + RV_CBARV * Npp, *rowobj = rv + RV_ROWOBJ * Npp;
+  for (int fo = 0; fo < 4; ++fo) {
+    const int64_t lo = fo * nf, hi = lo + nf;
+    const unsigned nbf = blocks_for(nf);
+    GPS_CHECK(fold_splitk(ctx, fl, fo, lo, hi, il, Pf));                       // P_f = W_f Lam_f^-1 W_f'
+    GPS_CHECK(fold_rowdot(ctx, fl, lo, hi, alpha, g));                         // g_f = W_f alpha_f
+    h_from_p_kernel<<<nbm, 256, 0, st>>>(Pf, Mp, ch->Kb.p);
+    GPS_LAUNCH_CHECK();
+    GPS_CHECK(factor(ctx, fl, LH, LHi, "I - W_f Lambda_f^-1 W_f' (fold)"));
+    GPS_CHECK(mm_gemm(ctx, fl, GEMM_MC_MC, LHi, LHi, Hinv, 1.0));              // H^-1 = L_H^-T L_H^-1
+    matvec_t_kernel<<<blocks_for(Mp), 256, 0, st>>>(Hinv, Mp, g, h);           // h = H^-1 g (H^-1 symmetric)
+    GPS_LAUNCH_CHECK();
+    fold_scalar_kernel<<<1, 256, 0, st>>>(LH, Mp, M, g, h, fl->fs.p + 2 * fo);
+    GPS_LAUNCH_CHECK();
+    ctx->launches += 3;
+    if (dss) {
+      if (!want_grad) {                                                        // the rows' share needs no product
+        col_dss_kernel<<<nbf, 256, 0, st>>>(fl->W.p, nullptr, fl->T2.p, Npp, M, lo, hi, h, lam, alpha, abar, lbar, rowobj);
+        GPS_LAUNCH_CHECK();
+        ctx->launches++;
+        continue;
+      }
+      hhat_kernel<<<nbm, 256, 0, st>>>(Hinv, h, Mp, M, HX);
+      GPS_LAUNCH_CHECK();
+      GPS_CHECK(fold_apply(ctx, fl, lo, hi, HX));                              // T1 = Hhat W_f
+      col_dss_kernel<<<nbf, 256, 0, st>>>(fl->W.p, fl->T1.p, fl->T2.p, Npp, M, lo, hi, h, lam, alpha, abar, lbar, rowobj);
+      GPS_LAUNCH_CHECK();
+      GPS_CHECK(mm_gemm(ctx, fl, GEMM_KC_MC, HX, Pf, X2, -2.0));               // -2 Hhat P_f
+      gw_dss_kernel<<<nbm, 256, 0, st>>>(X2, h, g, Mp, GW, bbar);
+      GPS_LAUNCH_CHECK();
+      ctx->launches += 3;
+    } else {
+      GPS_CHECK(fold_apply(ctx, fl, lo, hi, Hinv));                            // T1 = H^-1 W_f
+      col_kca_kernel<<<nbf, 256, 0, st>>>(fl->W.p, fl->T1.p, fl->T2.p, Npp, M, lo, hi, h, lam, alpha, 1.0 / (double)nf,
+                                          mbar, cbar, rowobj);
+      GPS_LAUNCH_CHECK();
+      ctx->launches++;
+      if (!want_grad) continue;
+      GPS_CHECK(fold_rowdot(ctx, fl, lo, hi, mbar, hbar));                     // hbar = -W_f mbar
+      negate_kernel<<<blocks_for(Mp), 256, 0, st>>>(hbar, Mp);
+      GPS_LAUNCH_CHECK();
+      GPS_CHECK(fold_splitk(ctx, fl, fo, lo, hi, cbar, E));                    // E = W_f diag(cbar) W_f'
+      matvec_t_kernel<<<blocks_for(Mp), 256, 0, st>>>(Hinv, Mp, hbar, gbar);   // gbar = H^-1 hbar
+      GPS_LAUNCH_CHECK();
+      GPS_CHECK(mm_gemm(ctx, fl, GEMM_KC_MC, Hinv, E, Y, 1.0));                // Y = H^-1 E
+      GPS_CHECK(mm_gemm(ctx, fl, GEMM_KC_MC, Y, Hinv, Z, 1.0));                // Z = H^-1 E H^-1
+      hbar_kernel<<<nbm, 256, 0, st>>>(Z, h, gbar, Mp, M, HX);
+      GPS_LAUNCH_CHECK();
+      GPS_CHECK(fold_apply(ctx, fl, lo, hi, HX));                              // T1 = Hbar W_f
+      col_kcb_kernel<<<nbf, 256, 0, st>>>(fl->W.p, fl->T1.p, fl->T2.p, Npp, M, lo, hi, gbar, lam, alpha, mbar, cbar, abar,
+                                          lbar);
+      GPS_LAUNCH_CHECK();
+      GPS_CHECK(mm_gemm(ctx, fl, GEMM_KC_MC, HX, Pf, X2, -2.0));               // -2 Hbar P_f
+      gw_kc_kernel<<<nbm, 256, 0, st>>>(X2, Y, Pf, h, hbar, g, gbar, Mp, GW, bbar);
+      GPS_LAUNCH_CHECK();
+      ctx->launches += 5;
+    }
+  }
+  vec_sum_kernel<<<1, 1024, 0, st>>>(rowobj, N, fl->out.p + OUT_LOGDET);
+  GPS_LAUNCH_CHECK();
+  block_obj_kernel<<<1, 1, 0, st>>>(fl->out.p + OUT_LOGDET, fl->fs.p, dss ? 1 : 0, (double)nf, d_obj);
+  GPS_LAUNCH_CHECK();
+  ctx->launches += 2;
+  f.pass2_done = true;
+  f.loo_ok = false;
+  fl->ready = true;
+  fl->block_seeds = want_grad;
+  if (!want_grad) return GPS_OK;
+  block_seed_kernel<<<blocks_for(Npp), 256, 0, st>>>(N, Npp, il, alpha, abar, lbar, rv + RV_RBAR * Npp, rv + RV_TBAR * Npp);
+  GPS_LAUNCH_CHECK();
+  ctx->launches++;
+  return GPS_OK;
+}
+
 }  // namespace
 
 void gps_fitc_large_free(gps_ctx* ctx) {
   gps_fitc_large* fl = ctx->fl;
   if (!fl) return;
-  for (DevBuf* b : {&fl->Kuf, &fl->V, &fl->W, &fl->T1, &fl->T2, &fl->sm, &fl->rv, &fl->mv, &fl->part, &fl->out, &fl->U, &fl->dotp, &fl->acc})
+  for (DevBuf* b : {&fl->Kuf, &fl->V, &fl->W, &fl->T1, &fl->T2, &fl->sm, &fl->rv, &fl->mv, &fl->part, &fl->out, &fl->U, &fl->dotp, &fl->acc, &fl->fs})
     if (b->p) cudaFree(b->p);
   if (fl->tasks) cudaFree(fl->tasks);
+  if (fl->ftasks) cudaFree(fl->ftasks);
   if (fl->ch) gps_ctx_release(fl->ch);
   delete fl;
   ctx->fl = nullptr;
@@ -753,8 +1133,10 @@ int gps_fitc_large_acc_len(int M, int D, int64_t* len1, int64_t* len2, int64_t* 
 
 int gps_fitc_large_begin(gps_ctx* ctx, const double* theta, const double* U, int M, double jitter, int score,
                          int64_t world_n) {
-  if (score != GPS_CRPS && score != GPS_LOGS && score != GPS_NLML)
-    return gps_fail(ctx, GPS_EINVAL, "fitc: M=%d > 32 runs the matrix form, which implements crps / logs / nlml only", M);
+  if (score < GPS_CRPS || score > GPS_KC) return gps_fail(ctx, GPS_EINVAL, "fitc: unknown score %d", score);
+  const bool block = score == GPS_DSS || score == GPS_KC;
+  if (block && (ctx->N % 4 != 0 || (world_n > 0 && world_n != ctx->N)))
+    return gps_fail(ctx, GPS_EINVAL, "fitc dss/kc: needs N %% 4 == 0 (K20:541-543) and runs on one GPU in this version");
   if (ctx->D > DMAX) return gps_fail(ctx, GPS_EINVAL, "fitc: D=%d > %d not supported", ctx->D, DMAX);
   if (M > 4096) return gps_fail(ctx, GPS_EINVAL, "fitc: M=%d > 4096 not supported", M);
   GPS_CUDA(cudaSetDevice(ctx->device));
@@ -762,7 +1144,7 @@ int gps_fitc_large_begin(gps_ctx* ctx, const double* theta, const double* U, int
   f.begun = false; f.pass2_done = false; f.loo_ok = false; f.large = true; f.fused = false;
   GPS_CHECK(gps_ensure(ctx, ctx->params, PAR_LEN));
   if (!ctx->d_info) GPS_CUDA(cudaMalloc(&ctx->d_info, sizeof(int)));
-  GPS_CHECK(setup(ctx, M));
+  GPS_CHECK(setup(ctx, M, block));
   gps_fitc_large* fl = ctx->fl;
   fl->ready = false;
   gps_ctx* ch = fl->ch;
@@ -831,6 +1213,8 @@ int gps_fitc_large_pass2(gps_ctx* ctx, const double* acc1, double* acc2, bool wa
                                     rv + RV_R * Npp, alpha, dd);
   GPS_LAUNCH_CHECK();
   ctx->launches++;
+  if (f.score == GPS_DSS || f.score == GPS_KC) return block_pass2(ctx, acc2, want_grad);
+  fl->block_seeds = false;
   double* d_obj = acc2 + MM + Mp;
   if (nlml) {
     nlml_rows_kernel<<<1, 1024, 0, st>>>(N, Npp, rv + RV_LAM * Npp, ctx->y.p, alpha, rv + RV_ABAR * Npp,
@@ -870,7 +1254,8 @@ int gps_fitc_large_pass3(gps_ctx* ctx, const double* acc2, double* acc3) {
   double *sm = fl->sm.p, *rv = fl->rv.p, *mv = fl->mv.p;
   const double* bbar = acc2 + MM;
   const size_t glen = 1 + DMAX + (size_t)M * D;
-  sw_kernel<<<blocks_for((int64_t)MM), 256, 0, st>>>(mv + MV_BETA * Mp, bbar, acc2, Mp, sm + SM_SW * MM);
+  const bool block = fl->block_seeds;
+  sw_kernel<<<blocks_for((int64_t)MM), 256, 0, st>>>(mv + MV_BETA * Mp, bbar, acc2, Mp, block ? 1.0 : 2.0, sm + SM_SW * MM);
   GPS_LAUNCH_CHECK();
   GPS_CHECK(chol_adjoint(ctx, fl, sm + SM_LC * MM, sm + SM_LCI * MM, sm + SM_SW * MM, nlml ? 1 : 0, sm + SM_CBAR * MM));
   matvec_t_kernel<<<blocks_for(Mp), 256, 0, st>>>(sm + SM_LCI * MM, Mp, bbar, mv + MV_VYBAR * Mp);
@@ -879,7 +1264,7 @@ int gps_fitc_large_pass3(gps_ctx* ctx, const double* acc2, double* acc3) {
   GPS_CHECK(big_gemm(ctx, fl, GEMM_KC_MC, fl->t_full, sm + SM_CBAR * MM, fl->V.p, fl->T1.p));     // CV
   col_pass3_kernel<<<blocks_for(N), 256, 0, st>>>(fl->V.p, fl->T1.p, fl->W.p, Npp, M, N, bbar, mv + MV_BETA * Mp,
                                                   ctx->y.p, rv + RV_IL * Npp, rv + RV_TBAR * Npp, rv + RV_RBAR * Npp,
-                                                  rv + RV_LBAR * Npp);
+                                                  rv + RV_LBAR * Npp, block ? fl->T2.p : nullptr);
   GPS_LAUNCH_CHECK();
   GPS_CHECK(big_gemm(ctx, fl, GEMM_MC_MC, fl->t_up, sm + SM_LCI * MM, fl->W.p, fl->T2.p));        // L_C^-T Wbar
   vbar_kernel<<<dim3(blocks_for(N), M), 256, 0, st>>>(fl->T2.p, fl->T1.p, fl->V.p, Npp, M, N, mv + MV_VYBAR * Mp,

@@ -112,7 +112,8 @@ def test_large_m_objective_only_and_errors(ctx):
     from gpscore_b200.api import _dp, _host_vec
     ctx._check(ctx._lib.gps_fitc_eval(ctx._h, _dp(theta), _dp(_host_vec(U)), 40, 1e-3, 0, _dp(obj), None, None))
     assert obj[0] == full[0]
-    with pytest.raises(L.GpsError):                 # block objectives stay with the fused M <= 32 kernels
+    with pytest.raises(L.GpsError):                 # the fold code needs 4 | N (K20:541-543)
+        ctx.set_data(_dev(X[:598]), _dev(y[:598]))
         ctx.fitc_eval(theta, U, "dss")
 
 
@@ -200,3 +201,86 @@ def test_large_m_tiny_and_boundary_shapes(ctx, n, m_ind, d):
         assert abs(val - oval) <= OBJ_TOL * abs(oval), score
         assert relerr(grad, og) <= GRAD_TOL, score
         assert relerr(gU, ogU) <= GRAD_TOL, score
+
+
+# ---- block objectives in the matrix form (4-fold DSS K20:538-587, block CRPS "kc" K20:669-720) ---------------
+
+@pytest.mark.parametrize("kind", ["dss", "kc"])
+@pytest.mark.parametrize("name", [n for n in golden_names(("c4",)) if "ragged" not in n])
+def test_matrix_form_block_objectives_vs_reference_golden(forced, name, kind):
+    """Switch-over lowered: the goldens' M = 20 runs the matrix form; values and gradients are the reference's
+    own autograd results."""
+    g = load_golden(name)
+    forced.set_data(_dev(g["X"]), _dev(g["y"]))
+    val, grad, gU = forced.fitc_eval(g["theta"], g["U"], kind)
+    assert abs(val - g["obj_" + kind]) <= OBJ_TOL * abs(g["obj_" + kind])
+    ref = grad_vector(g, kind)
+    if int(g["d_b"]) == 1 and g["X"].shape[1] > 1:
+        grad = np.concatenate([[grad[0]], [grad[1:-1].sum()], [grad[-1]]])
+    assert relerr(grad, ref) <= GRAD_TOL
+    assert relerr(gU, g["grad_u_" + kind]) <= GRAD_TOL
+
+
+@pytest.mark.parametrize("kind", ["dss", "kc"])
+@pytest.mark.parametrize("m_ind,n,d", [(33, 700, 8), (64, 1204, 8), (130, 2000, 8), (200, 1500, 3), (40, 36, 2)])
+def test_large_m_block_objectives_vs_oracle(ctx, m_ind, n, d, kind):
+    """Fold boundaries off the 16-column k-granularity (n/4 = 175, 301, 375, 9) and off the 128-column tiles."""
+    from oracle import woodbury as Wd
+    rng = np.random.default_rng(300 + m_ind)
+    X = rng.uniform(-1, 1, (n, d))
+    y = np.sin(X @ rng.standard_normal(d)) + 0.1 * rng.standard_normal(n)
+    U = rng.uniform(-1, 1, (m_ind, d))
+    theta = np.concatenate([[0.3], np.log(rng.uniform(0.8, 2.0, d)), [-2.0]])
+    ctx.set_data(_dev(X), _dev(y))
+    val, grad, gU = ctx.fitc_eval(theta, U, kind)
+    oval, og, ogU = Wd.fitc_block_obj_grad(X, y, U, theta, kind)
+    assert abs(val - oval) <= OBJ_TOL * abs(oval)
+    assert relerr(grad, og) <= GRAD_TOL
+    assert relerr(gU, ogU) <= GRAD_TOL
+    val2, grad2, gU2 = ctx.fitc_eval(theta, U, kind)
+    assert val2 == val and np.array_equal(grad, grad2) and np.array_equal(gU, gU2)   # fixed reduction order
+    # objective only (no gradient pointers) takes the short path and returns the same value
+    from gpscore_b200.api import _dp, _host_vec
+    from gpscore_b200 import lib as L
+    obj = np.zeros(1)
+    ctx._check(ctx._lib.gps_fitc_eval(ctx._h, _dp(theta), _dp(_host_vec(U)), m_ind, 1e-3, L.SCORES[kind], _dp(obj), None, None))
+    assert abs(obj[0] - val) <= 1e-13 * abs(val)
+
+
+@pytest.mark.parametrize("kind", ["dss", "kc"])
+def test_matrix_form_block_objectives_equal_fused_small_m(ctx, kind):
+    """The same objective through the M <= 32 row kernels and (switch-over lowered) the matrix form."""
+    rng = np.random.default_rng(41)
+    X = rng.uniform(-1, 1, (1600, 8))
+    y = np.sin(X @ rng.standard_normal(8)) + 0.1 * rng.standard_normal(1600)
+    U = rng.uniform(-1, 1, (24, 8))
+    theta = np.concatenate([[0.2], np.log(rng.uniform(0.8, 2.0, 8)), [-2.5]])
+    ctx.set_data(_dev(X), _dev(y))
+    a = ctx.fitc_eval(theta, U, kind)
+    ctx._check(ctx._lib.gps_dbg_set_variant(ctx._h, 3, 1))
+    try:
+        b = ctx.fitc_eval(theta, U, kind)
+    finally:
+        ctx._check(ctx._lib.gps_dbg_set_variant(ctx._h, 3, 33))
+    assert abs(a[0] - b[0]) <= 1e-10 * abs(a[0])
+    assert relerr(a[1], b[1]) <= 1e-8 and relerr(a[2], b[2]) <= 1e-8
+
+
+def test_large_m_block_objective_after_loo_score_and_back(ctx):
+    """Alternating score families on one context: the block path's scratch aliases the LOO vectors."""
+    from oracle import woodbury as Wd
+    from oracle import gp_oracle as O
+    rng = np.random.default_rng(43)
+    X = rng.uniform(-1, 1, (800, 4))
+    y = np.sin(X @ rng.standard_normal(4)) + 0.1 * rng.standard_normal(800)
+    U = rng.uniform(-1, 1, (48, 4))
+    theta = np.concatenate([[0.1], np.zeros(4), [-2.0]])
+    ctx.set_data(_dev(X), _dev(y))
+    for kind in ("crps", "dss", "nlml", "kc", "logs"):
+        val, grad, gU = ctx.fitc_eval(theta, U, kind)
+        if kind in ("dss", "kc"):
+            oval, og, ogU = Wd.fitc_block_obj_grad(X, y, U, theta, kind)
+        else:
+            oval, og, ogU = Wd.fitc_obj_grad(X, y, U, theta, O.SCORES[kind])[:3]
+        assert abs(val - oval) <= OBJ_TOL * abs(oval), kind
+        assert relerr(grad, og) <= GRAD_TOL and relerr(gU, ogU) <= GRAD_TOL, kind
