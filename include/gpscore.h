@@ -38,8 +38,9 @@ enum { GPS_OK = 0, GPS_EINVAL = 1, GPS_ECUDA = 2, GPS_ENOTPD = 3, GPS_ENODEVICE 
        GPS_ESTATE = 6 };
 
 /* score selector: LOO-CRPS (KF:245), LOO log score (KF:424), negative log marginal
- * likelihood (KF:331-334), 4-fold block-LOO DSS (KF:499-538, K20:538-582; needs 4 | N; the FITC
- * version runs through gps_fitc_eval on one GPU), 4-fold block CRPS "kc" (K20:669-714; FITC only) */
+ * likelihood (KF:331-334), 4-fold block-LOO DSS (KF:499-538, K20:538-582; needs 4 | N), 4-fold block CRPS "kc"
+ * (K20:669-714; FITC only).  The FITC block objectives run through gps_fitc_eval (any M <= 4096) and, row-sharded,
+ * through gps_fitc_eval_sharded. */
 enum { GPS_CRPS = 0, GPS_LOGS = 1, GPS_NLML = 2, GPS_DSS = 3, GPS_KC = 4 };
 
 /* ---- context ------------------------------------------------------------------------------- */
@@ -88,7 +89,8 @@ int gps_full_predict(gps_ctx* ctx, const double* theta, const double* Xs, int64_
  * gps_fitc_acc_len).  world_n is the global number of rows (the mean in KF:67 divides by it).
  * M <= 31, CRPS / LOGS / NLML: gps_fitc_eval is three fused kernels (preamble + row pass + reduction each) and one
  * stream synchronisation; DSS / KC and M = 32 use the staged row kernels.  32 < M <= 4096: the matrix form on the
- * tile-GEMM engine (GPS_CRPS / GPS_LOGS / GPS_NLML; gps_fitc_loo and gps_fitc_predict work after it).  The staged
+ * tile-GEMM engine, all five scores (gps_fitc_predict works after any of them, gps_fitc_loo after CRPS / LOGS;
+ * DSS / KC add, per fold, two M x M split-K products, one factorisation and one or two [M][N/4] products).  The staged
  * begin / pass1 / pass2 / pass3 / finish protocol (caller-side all-reduce of the accumulators) implements the
  * row-additive objectives only and rejects DSS / KC; new code should use gps_fitc_eval_sharded below. */
 int gps_fitc_eval(gps_ctx* ctx, const double* theta, const double* U, int M, double jitter, int score,
@@ -109,7 +111,10 @@ int gps_fitc_finish(gps_ctx* ctx, const double* acc2, const double* acc3, double
  * the ranks in contiguous blocks (this context's gps_set_data holds this rank's block): the three row passes
  * run with ncclAllReduce(sum, double) of the packed accumulators in between, all enqueued on the context's
  * stream — no host synchronisation before the final result read-back.  Every rank returns the same objective
- * and gradients.  CRPS / LOGS / NLML; M <= 31 runs the fused kernels, larger M the matrix form.
+ * and gradients.  CRPS / LOGS / NLML: M <= 31 runs the fused kernels, larger M the matrix form.  DSS / KC (4 | world_n):
+ * the matrix form for every M; the folds are quarters of the GLOBAL row order, so the ranks' blocks must be
+ * consecutive in rank order (the row counts are exchanged through the communicator and checked against world_n);
+ * per evaluation two more all-reduces carry the folds' [P_f | g_f] (and for KC [E_f | hbar_f]) accumulators.
  * libnccl is bound with dlopen at the first gps_comm_* call (gps_comm_set_library names a specific copy). */
 int gps_comm_set_library(const char* path);
 int gps_comm_unique_id(void* out128);

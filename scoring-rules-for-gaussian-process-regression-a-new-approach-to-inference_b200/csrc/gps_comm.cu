@@ -23,6 +23,7 @@ struct gps_comm {
   double** d_peers = nullptr;             // device copy of the base pointers
   unsigned long long seq = 1;
   int transport = 1;                      // 1: peer memory inside the kernels when available, 0: NCCL only
+  double* d_rows = nullptr;               // [world] row counts of the ranks (block objectives: fold geometry)
 };
 
 namespace {
@@ -135,6 +136,7 @@ void gps_comm_free(gps_ctx* ctx) {
   for (void* p : ctx->comm->peer_map) cudaIpcCloseMemHandle(p);
   if (ctx->comm->d_peers) cudaFree(ctx->comm->d_peers);
   if (ctx->comm->xbuf) cudaFree(ctx->comm->xbuf);
+  if (ctx->comm->d_rows) cudaFree(ctx->comm->d_rows);
   if (ctx->comm->comm && g_nccl.CommDestroy) g_nccl.CommDestroy(ctx->comm->comm);
   delete ctx->comm;
   ctx->comm = nullptr;
@@ -145,6 +147,30 @@ int gps_comm_allreduce(gps_ctx* ctx, double* buf, size_t n) {
   if (!ctx->comm || !ctx->comm->comm) return gps_fail(ctx, GPS_ESTATE, "no communicator: call gps_comm_init first");
   const ncclResult_t r = g_nccl.AllReduce(buf, buf, n, ncclDouble, ncclSum, ctx->comm->comm, ctx->stream);
   if (r != ncclSuccess) return gps_fail(ctx, GPS_ECUDA, "ncclAllReduce: %s", g_nccl.GetErrorString(r));
+  return GPS_OK;
+}
+
+// First global row of this rank's block: the ranks hold consecutive blocks in rank order, their row counts are
+// exchanged through the communicator (exact in doubles) and must add up to world_n.
+static int row_offset_of(gps_ctx* ctx, int64_t world_n, int64_t* off) {
+  gps_comm* cm = ctx->comm;
+  const int W = cm->world;
+  if (!cm->d_rows) GPS_CUDA(cudaMalloc(&cm->d_rows, (size_t)W * sizeof(double)));
+  std::vector<double> h(W, 0.0);
+  h[cm->rank] = (double)ctx->N;
+  GPS_CUDA(cudaMemcpyAsync(cm->d_rows, h.data(), (size_t)W * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  GPS_CHECK(gps_comm_allreduce(ctx, cm->d_rows, (size_t)W));
+  GPS_CUDA(cudaMemcpyAsync(h.data(), cm->d_rows, (size_t)W * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  GPS_CUDA(cudaStreamSynchronize(ctx->stream));
+  int64_t before = 0, total = 0;
+  for (int r = 0; r < W; ++r) {
+    if (r < cm->rank) before += (int64_t)h[r];
+    total += (int64_t)h[r];
+  }
+  if (total != world_n)
+    return gps_fail(ctx, GPS_EINVAL, "fitc_eval_sharded: the ranks hold %lld rows, world_n = %lld", (long long)total,
+                    (long long)world_n);
+  *off = before;
   return GPS_OK;
 }
 
@@ -232,12 +258,19 @@ int gps_fitc_eval_sharded(gps_ctx* ctx, const double* theta, const double* U, in
   if (!ctx) return GPS_EINVAL;
   if (ctx->N == 0) return gps_fail(ctx, GPS_ESTATE, "fitc: call gps_set_data first");
   if (!theta || !U || M <= 0 || world_n < ctx->N) return gps_fail(ctx, GPS_EINVAL, "fitc_eval_sharded: bad arguments");
-  if (score != GPS_CRPS && score != GPS_LOGS && score != GPS_NLML)
-    return gps_fail(ctx, GPS_EINVAL, "fitc_eval_sharded: crps / logs / nlml only (the block objectives run on one GPU)");
+  if (score < GPS_CRPS || score > GPS_KC) return gps_fail(ctx, GPS_EINVAL, "fitc_eval_sharded: unknown score %d", score);
   if (!ctx->comm) return gps_fail(ctx, GPS_ESTATE, "fitc_eval_sharded: call gps_comm_init first");
   if (M < ctx->fitc_large_min_m && gps_fitc_fused_supports(ctx, M, score))
     return gps_fitc_fused_eval(ctx, theta, U, M, jitter, score, world_n, gps_comm_allreduce, obj, grad_theta, grad_U);
-  return gps_fitc_large_eval_sharded(ctx, theta, U, M, jitter, score, world_n, gps_comm_allreduce, obj, grad_theta, grad_U);
+  // the block objectives (4-fold DSS, kc) shard through the matrix form for every M: their folds are ranges of the
+  // GLOBAL row order, so the ranks' blocks must be consecutive in rank order
+  int64_t row_offset = 0;
+  if (score == GPS_DSS || score == GPS_KC) {
+    GPS_CUDA(cudaSetDevice(ctx->device));
+    GPS_CHECK(row_offset_of(ctx, world_n, &row_offset));
+  }
+  return gps_fitc_large_eval_sharded(ctx, theta, U, M, jitter, score, world_n, row_offset, gps_comm_allreduce, obj, grad_theta,
+                                     grad_U);
 }
 
 // The optimiser loop K20:219-251 on a row-sharded problem: theta and U stay on every rank's device (all ranks apply the

@@ -190,8 +190,8 @@ int gps_fitc_fused_predict(gps_ctx* ctx, const double* dXs, int64_t T, double* d
 int gps_launch_floor_us(gps_ctx* ctx, int launches, int reps, double* us);
 int gps_fitc_fused_phases(gps_ctx* ctx, long long* out48);
 int gps_fitc_large_eval_sharded(gps_ctx* ctx, const double* theta, const double* U, int M, double jitter, int score,
-                                int64_t world_n, gps_allreduce_fn allreduce, double* obj, double* grad_theta,
-                                double* grad_U);
+                                int64_t world_n, int64_t row_offset, gps_allreduce_fn allreduce, double* obj,
+                                double* grad_theta, double* grad_U);
 // gps_comm.cu
 void gps_comm_free(gps_ctx* ctx);
 int gps_comm_allreduce(gps_ctx* ctx, double* buf, size_t n);

@@ -28,8 +28,8 @@ constexpr int DMAX = 16;
 constexpr double HALF_LOG_2PI = 0.91893853320467274178;
 
 enum { SM_KUU = 0, SM_LA, SM_LAI, SM_LC, SM_LCI, SM_R, SM_SW, SM_Y, SM_Z, SM_CBAR, SM_S, SM_ABAR, SM_COUNT,
-       // block objectives only (allocated on first use): P_f, L_H, L_H^-1, H^-1, Hhat / Hbar, E, one scratch
-       SM_PF = SM_COUNT, SM_LH, SM_LHI, SM_HINV, SM_HX, SM_E, SM_X2, SM_COUNT_BLOCK };
+       // block objectives only: L_H, L_H^-1, Hhat / Hbar, one scratch
+       SM_LH = SM_COUNT, SM_LHI, SM_HX, SM_X2, SM_COUNT_BLOCK };
 enum { RV_LAM = 0, RV_IL, RV_YL, RV_R, RV_ABAR, RV_DBAR, RV_LBAR, RV_RBAR, RV_TBAR, RV_LOOM, RV_LOOV, RV_COUNT };
 // block objectives: aliases of slots the LOO scores use (R, DBAR, LOOM, LOOV are free there)
 enum { RV_FV = RV_R, RV_MBAR = RV_DBAR, RV_CBARV = RV_LOOM, RV_ROWOBJ = RV_LOOV };
@@ -49,8 +49,10 @@ struct gps_fitc_large {
   size_t ftasks_cap = 0;
   gps_ctx::Range t_fold[4];
   int fold_S[4] = {0, 0, 0, 0};
-  int64_t fold_key_N = -1;
-  int fold_key_Mp = -1, fold_key_S = -1;
+  int64_t fold_key[10] = {-1, -1, -1, -1, -1, -1, -1, -1, -1, -1};
+  DevBuf fb;                  // block objectives: per-fold accumulators and replicated M x M matrices
+  int64_t row_off = 0;        // first global row of this context's block (row-sharded block objectives)
+  gps_allreduce_fn allreduce = nullptr;   // set for the duration of a row-sharded evaluation
   bool block_seeds = false;   // pass 2 left the block objectives' direct dL/dW in T2
   GemmTask* tasks = nullptr;
   size_t tasks_cap = 0;
@@ -471,8 +473,7 @@ block_seed_kernel(int64_t N, int64_t Npp, const double* __restrict__ il, const d
 }
 
 // objective: rows' sum (+ DSS: sum_f nf/2 log 2pi - sum log diag L_H_f + 1/2 g_f.h_f), fixed order
-__global__ void block_obj_kernel(const double* __restrict__ rows, const double* __restrict__ fs, int dss, double nf,
-                                 double* __restrict__ obj) {
+__global__ void block_obj_kernel(const double* rows, const double* __restrict__ fs, int dss, double nf, double* obj) {
   double v = rows[0];
   if (dss)
     for (int f = 0; f < 4; ++f) v += nf * HALF_LOG_2PI - fs[2 * f] + 0.5 * fs[2 * f + 1];
@@ -802,12 +803,13 @@ int setup(gps_ctx* ctx, int M, bool block) {
     GPS_CHECK(gps_ensure(ctx, fl->rv, (size_t)RV_COUNT * Npp));
     GPS_CHECK(gps_ensure(ctx, fl->mv, (size_t)MV_COUNT * Mp));
     GPS_CHECK(gps_ensure(ctx, fl->U, (size_t)Mp * D));
-    GPS_CHECK(gps_ensure(ctx, ctx->fitc.rowv, (size_t)6 * ctx->N));
     GPS_CHECK(build_tasks(ctx, fl));
     const size_t kg = (size_t)8 * ctx->sm_count * (8 * (1 + DMAX) + DMAX) + 4096;
     GPS_CHECK(gps_ensure(ctx, fl->part, std::max((size_t)fl->S * Mp * Mp, kg)));
     GPS_CHECK(gps_ensure(ctx, fl->out, (size_t)OUT_G1 + 2 * (1 + DMAX + (size_t)Mp * D)));
   }
+  // per-row scalars are laid out with stride N (the layout gps_fitc_loo reads): N may grow inside one padded shape
+  GPS_CHECK(gps_ensure(ctx, ctx->fitc.rowv, (size_t)6 * ctx->N));
   // nothing in `sm` outlives an evaluation except the factors begin() writes after this point
   GPS_CHECK(gps_ensure(ctx, fl->sm, (size_t)(block ? SM_COUNT_BLOCK : SM_COUNT) * Mp * Mp));
   // the Gram kernel writes only the live M x N block: the pad rows/columns must read as zeros
@@ -936,46 +938,74 @@ int kgrad_any(gps_ctx* ctx, gps_fitc_large* fl, const double* Kbar, const double
 }
 
 // ---- block objectives: host side -----------------------------------------------------------------------
+// Row-sharded layout: this context holds the rows [row_off, row_off + N) of world_n; fold f is the global range
+// [f nf, (f+1) nf), nf = world_n / 4, of which [lo, hi) (possibly empty) lives here.
+struct FoldRange { int64_t lo, hi; };
+
+FoldRange fold_range(const gps_ctx* ctx, int f) {
+  const gps_fitc_large* fl = ctx->fl;
+  const int64_t nf = ctx->fitc.world_n / 4;
+  FoldRange r;
+  r.lo = std::min<int64_t>(ctx->N, std::max<int64_t>(0, f * nf - fl->row_off));
+  r.hi = std::min<int64_t>(ctx->N, std::max<int64_t>(0, (f + 1) * nf - fl->row_off));
+  return r;
+}
+
 // split-K task lists of the four folds: fold f contracts over its 16-rounded column range, the operands'
 // stray columns inside that range are zeroed by the masked k-scaling vector
-int build_fold_tasks(gps_ctx* ctx, gps_fitc_large* fl, int64_t N) {
-  if (fl->fold_key_N == N && fl->fold_key_Mp == fl->Mp && fl->fold_key_S == fl->S && fl->ftasks) return GPS_OK;
+int build_fold_tasks(gps_ctx* ctx, gps_fitc_large* fl) {
+  int64_t key[10];
+  for (int f = 0; f < 4; ++f) {
+    const FoldRange r = fold_range(ctx, f);
+    key[2 * f] = r.lo; key[2 * f + 1] = r.hi;
+  }
+  key[8] = fl->Mp; key[9] = fl->S;
+  if (fl->ftasks && std::equal(key, key + 10, fl->fold_key)) return GPS_OK;
   const int mt = fl->Mp / GPS_TILE, Mp = fl->Mp;
-  const int64_t nf = N / 4;
   std::vector<GemmTask> h;
   for (int f = 0; f < 4; ++f) {
-    const int64_t lo_r = (f * nf) & ~(int64_t)15, hi_r = std::min<int64_t>(fl->Npp, ((f + 1) * nf + 15) & ~(int64_t)15);
-    const int64_t blocks = (hi_r - lo_r) / 16;
-    int64_t Sf = std::max<int64_t>(1, std::min<int64_t>((fl->S + 3) / 4, (blocks + 7) / 8));
-    const int64_t per = ((blocks + Sf - 1) / Sf) * 16;
-    Sf = (hi_r - lo_r + per - 1) / per;
-    fl->fold_S[f] = (int)Sf;
+    const int64_t lo = key[2 * f], hi = key[2 * f + 1];
     fl->t_fold[f].off = h.size();
-    for (int s = 0; s < (int)Sf; ++s) {
-      const int k0 = (int)(lo_r + s * per), k1 = (int)std::min<int64_t>(hi_r, lo_r + (s + 1) * per);
-      for (int i = 0; i < mt; ++i)
-        for (int j = 0; j <= i; ++j)
-          h.push_back(make_task(i * GPS_TILE, j * GPS_TILE, k0, k1, s * Mp + i * GPS_TILE, j * GPS_TILE));
+    fl->fold_S[f] = 0;
+    if (hi > lo) {
+      const int64_t lo_r = lo & ~(int64_t)15, hi_r = std::min<int64_t>(fl->Npp, (hi + 15) & ~(int64_t)15);
+      const int64_t blocks = (hi_r - lo_r) / 16;
+      int64_t Sf = std::max<int64_t>(1, std::min<int64_t>((fl->S + 3) / 4, (blocks + 7) / 8));
+      const int64_t per = ((blocks + Sf - 1) / Sf) * 16;
+      Sf = (hi_r - lo_r + per - 1) / per;
+      fl->fold_S[f] = (int)Sf;
+      for (int s = 0; s < (int)Sf; ++s) {
+        const int k0 = (int)(lo_r + s * per), k1 = (int)std::min<int64_t>(hi_r, lo_r + (s + 1) * per);
+        for (int i = 0; i < mt; ++i)
+          for (int j = 0; j <= i; ++j)
+            h.push_back(make_task(i * GPS_TILE, j * GPS_TILE, k0, k1, s * Mp + i * GPS_TILE, j * GPS_TILE));
+      }
     }
     fl->t_fold[f].cnt = h.size() - fl->t_fold[f].off;
   }
-  if (h.size() > fl->ftasks_cap) {
+  if (h.size() > fl->ftasks_cap || !fl->ftasks) {
     if (fl->ftasks) cudaFree(fl->ftasks);
     fl->ftasks = nullptr;
-    GPS_CUDA(cudaMalloc(&fl->ftasks, h.size() * sizeof(GemmTask)));
-    fl->ftasks_cap = h.size();
+    GPS_CUDA(cudaMalloc(&fl->ftasks, std::max<size_t>(1, h.size()) * sizeof(GemmTask)));
+    fl->ftasks_cap = std::max<size_t>(1, h.size());
   }
-  GPS_CUDA(cudaMemcpyAsync(fl->ftasks, h.data(), h.size() * sizeof(GemmTask), cudaMemcpyHostToDevice, ctx->stream));
-  GPS_CUDA(cudaStreamSynchronize(ctx->stream));
-  fl->fold_key_N = N; fl->fold_key_Mp = fl->Mp; fl->fold_key_S = fl->S;
+  if (!h.empty()) {
+    GPS_CUDA(cudaMemcpyAsync(fl->ftasks, h.data(), h.size() * sizeof(GemmTask), cudaMemcpyHostToDevice, ctx->stream));
+    GPS_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  std::copy(key, key + 10, fl->fold_key);
   return GPS_OK;
 }
 
-// out (Mp x Mp, full symmetric) = W_f diag(src_f) W_f' over the columns [lo, hi) of fold f
-int fold_splitk(gps_ctx* ctx, gps_fitc_large* fl, int f, int64_t lo, int64_t hi, const double* src, double* out) {
-  const int64_t lo_r = lo & ~(int64_t)15, hi_r = std::min<int64_t>(fl->Npp, (hi + 15) & ~(int64_t)15);
+// out (Mp x Mp, full symmetric) = W_f diag(src_f) W_f' over this context's columns [lo, hi) of fold f
+int fold_splitk(gps_ctx* ctx, gps_fitc_large* fl, int f, FoldRange r, const double* src, double* out) {
+  if (r.hi <= r.lo) {
+    GPS_CUDA(cudaMemsetAsync(out, 0, (size_t)fl->Mp * fl->Mp * sizeof(double), ctx->stream));
+    return GPS_OK;
+  }
+  const int64_t lo_r = r.lo & ~(int64_t)15, hi_r = std::min<int64_t>(fl->Npp, (r.hi + 15) & ~(int64_t)15);
   double* fv = fl->rv.p + RV_FV * fl->Npp;
-  mask_range_kernel<<<blocks_for(hi_r - lo_r), 256, 0, ctx->stream>>>(src, lo, hi, lo_r, hi_r, fv);
+  mask_range_kernel<<<blocks_for(hi_r - lo_r), 256, 0, ctx->stream>>>(src, r.lo, r.hi, lo_r, hi_r, fv);
   GPS_LAUNCH_CHECK();
   GPS_CHECK(gps_gemm_tasks(ctx, GEMM_KC_KC, fl->W.p, fl->Npp, fl->W.p, fl->Npp, fl->part.p, fl->Mp, 1.0, 0.0, fv, false,
                            fl->ftasks + fl->t_fold[f].off, fl->t_fold[f].cnt));
@@ -986,107 +1016,114 @@ int fold_splitk(gps_ctx* ctx, gps_fitc_large* fl, int f, int64_t lo, int64_t hi,
   return GPS_OK;
 }
 
-// out[m] = sum over the fold's columns of W[m][i] src[i]
-int fold_rowdot(gps_ctx* ctx, gps_fitc_large* fl, int64_t lo, int64_t hi, const double* src, double* out) {
-  const int64_t lo_r = lo & ~(int64_t)15, hi_r = std::min<int64_t>(fl->Npp, (hi + 15) & ~(int64_t)15);
+// out[m] = sum over this context's columns of the fold of W[m][i] src[i]
+int fold_rowdot(gps_ctx* ctx, gps_fitc_large* fl, FoldRange r, const double* src, double* out) {
+  if (r.hi <= r.lo) {
+    GPS_CUDA(cudaMemsetAsync(out, 0, (size_t)fl->Mp * sizeof(double), ctx->stream));
+    return GPS_OK;
+  }
+  const int64_t lo_r = r.lo & ~(int64_t)15, hi_r = std::min<int64_t>(fl->Npp, (r.hi + 15) & ~(int64_t)15);
   double* fv = fl->rv.p + RV_FV * fl->Npp;
-  mask_range_kernel<<<blocks_for(hi_r - lo_r), 256, 0, ctx->stream>>>(src, lo, hi, lo_r, hi_r, fv);
+  mask_range_kernel<<<blocks_for(hi_r - lo_r), 256, 0, ctx->stream>>>(src, r.lo, r.hi, lo_r, hi_r, fv);
   GPS_LAUNCH_CHECK();
   ctx->launches++;
   return rowdot(ctx, fl, fl->W.p + lo_r, fl->Npp, fl->Mp, hi_r - lo_r, fv + lo_r, out);
 }
 
 // T1[:, the fold's column tiles] = Mat (Mp x Mp) W
-int fold_apply(gps_ctx* ctx, gps_fitc_large* fl, int64_t lo, int64_t hi, const double* Mat) {
+int fold_apply(gps_ctx* ctx, gps_fitc_large* fl, FoldRange r, const double* Mat) {
   const int mt = fl->Mp / GPS_TILE;
-  const int64_t j0 = lo / GPS_TILE, j1 = (hi + GPS_TILE - 1) / GPS_TILE;
+  const int64_t j0 = r.lo / GPS_TILE, j1 = (r.hi + GPS_TILE - 1) / GPS_TILE;
   return gps_gemm_tasks(ctx, GEMM_KC_MC, Mat, fl->Mp, fl->W.p, fl->Npp, fl->T1.p, fl->Npp, 1.0, 0.0, nullptr, false,
                         fl->tasks + fl->t_full.off + j0 * mt, (size_t)((j1 - j0) * mt));
 }
 
-// Pass 2 of the block objectives, after W / alpha / lambda: per fold the M x M chain and the column sweeps that
-// leave the seeds (tbar, lam_bar0, D in T2) of the shared adjoint chain; acc2 = [G_W | beta_bar | obj]
+// Pass 2 of the block objectives, after W / alpha / lambda.  Stages (each a loop over the four folds):
+//   A  rows:        acc4[f] = [P_f = W_f Lam_f^-1 W_f' | g_f = W_f alpha_f] over this context's rows   -> all-reduce
+//   B  replicated:  H_f = I - P_f = L_H L_H', H_f^-1, h_f = H_f^-1 g_f;  rows: T = (Hhat_f | H_f^-1) W_f, column sweep
+//                   (fold predictive, objective share, seeds);  DSS: G_W, beta_bar (replicated)
+//   C  rows (kc):   acc5[f] = [E_f = W_f diag(cbar) W_f' | hbar_f = -W_f mbar]                         -> all-reduce
+//   D  (kc)         replicated: gbar_f, Hbar_f;  rows: T = Hbar_f W_f, second column sweep;  G_W, beta_bar
+// and leaves the seeds (tbar, lam_bar0, D in T2) of the shared adjoint chain; acc2 = [G_W | beta_bar | obj].
+// One GPU: allreduce == nullptr.
 int block_pass2(gps_ctx* ctx, double* acc2, bool want_grad) {
   gps_fitc_large* fl = ctx->fl;
   auto& f = ctx->fitc;
   gps_ctx* ch = fl->ch;
-  const int64_t N = ctx->N, Npp = fl->Npp, nf = N / 4;
+  const int64_t N = ctx->N, Npp = fl->Npp, nf = f.world_n / 4;
   const int Mp = fl->Mp, M = fl->M;
-  const size_t MM = (size_t)Mp * Mp;
+  const size_t MM = (size_t)Mp * Mp, AF = MM + Mp;
   const bool dss = f.score == GPS_DSS;
+  gps_allreduce_fn allreduce = fl->allreduce;
   cudaStream_t st = ctx->stream;
-  double *sm = fl->sm.p, *rv = fl->rv.p, *mv = fl->mv.p;
+  double *sm = fl->sm.p, *rv = fl->rv.p;
   const double* alpha = f.rowv.p + 4 * N;
-  const unsigned nbm = blocks_for((int64_t)MM);
-  GPS_CHECK(build_fold_tasks(ctx, fl, N));
+  const unsigned nbm = blocks_for((int64_t)MM), nbv = blocks_for(Mp);
+  GPS_CHECK(build_fold_tasks(ctx, fl));
   GPS_CHECK(gps_ensure(ctx, fl->fs, 8));
+  // fold buffer: acc4 [4][MM + Mp] | acc5 [4][MM + Mp] | H^-1 [4][MM] | h [4][Mp] | gbar [4][Mp]
+  GPS_CHECK(gps_ensure(ctx, fl->fb, 8 * AF + 4 * MM + 8 * (size_t)Mp));
+  double *A4 = fl->fb.p, *A5 = A4 + 4 * AF, *HI = A5 + 4 * AF, *HV = HI + 4 * MM, *GB = HV + 4 * (size_t)Mp;
   double *GW = acc2, *bbar = acc2 + MM, *d_obj = acc2 + MM + Mp;
   GPS_CUDA(cudaMemsetAsync(acc2, 0, (MM + Mp + 2) * sizeof(double), st));
-  double *Pf = sm + SM_PF * MM, *LH = sm + SM_LH * MM, *LHi = sm + SM_LHI * MM, *Hinv = sm + SM_HINV * MM,
-         *HX = sm + SM_HX * MM, *E = sm + SM_E * MM, *X2 = sm + SM_X2 * MM, *Y = sm + SM_Y * MM, *Z = sm + SM_Z * MM;
-  double *g = mv + MV_G * Mp, *h = mv + MV_H * Mp, *hbar = mv + MV_HBAR * Mp, *gbar = mv + MV_GBAR * Mp;
+  double *LH = sm + SM_LH * MM, *LHi = sm + SM_LHI * MM, *HX = sm + SM_HX * MM, *X2 = sm + SM_X2 * MM,
+         *Y = sm + SM_Y * MM, *Z = sm + SM_Z * MM;
   double *lam = rv + RV_LAM * Npp, *il = rv + RV_IL * Npp, *abar = rv + RV_ABAR * Npp, *lbar = rv + RV_LBAR * Npp,
          *mbar = rv + RV_MBAR * Npp, *cbar = rv + RV_CBARV * Npp, *rowobj = rv + RV_ROWOBJ * Npp;
+  FoldRange fr[4];
+  for (int fo = 0; fo < 4; ++fo) fr[fo] = fold_range(ctx, fo);
+  // ---- A
   for (int fo = 0; fo < 4; ++fo) {
-    const int64_t lo = fo * nf, hi = lo + nf;
-    const unsigned nbf = blocks_for(nf);
-    GPS_CHECK(fold_splitk(ctx, fl, fo, lo, hi, il, Pf));                       // P_f = W_f Lam_f^-1 W_f'
-    GPS_CHECK(fold_rowdot(ctx, fl, lo, hi, alpha, g));                         // g_f = W_f alpha_f
+    GPS_CHECK(fold_splitk(ctx, fl, fo, fr[fo], il, A4 + fo * AF));
+    GPS_CHECK(fold_rowdot(ctx, fl, fr[fo], alpha, A4 + fo * AF + MM));
+  }
+  if (allreduce) GPS_CHECK(allreduce(ctx, A4, 4 * AF));
+  // ---- B
+  for (int fo = 0; fo < 4; ++fo) {
+    const FoldRange r = fr[fo];
+    const bool rows = r.hi > r.lo;
+    const unsigned nbf = blocks_for(std::max<int64_t>(1, r.hi - r.lo));
+    double *Pf = A4 + fo * AF, *g = Pf + MM, *Hinv = HI + fo * MM, *h = HV + fo * (size_t)Mp;
     h_from_p_kernel<<<nbm, 256, 0, st>>>(Pf, Mp, ch->Kb.p);
     GPS_LAUNCH_CHECK();
     GPS_CHECK(factor(ctx, fl, LH, LHi, "I - W_f Lambda_f^-1 W_f' (fold)"));
     GPS_CHECK(mm_gemm(ctx, fl, GEMM_MC_MC, LHi, LHi, Hinv, 1.0));              // H^-1 = L_H^-T L_H^-1
-    matvec_t_kernel<<<blocks_for(Mp), 256, 0, st>>>(Hinv, Mp, g, h);           // h = H^-1 g (H^-1 symmetric)
+    matvec_t_kernel<<<nbv, 256, 0, st>>>(Hinv, Mp, g, h);                      // h = H^-1 g (H^-1 symmetric)
     GPS_LAUNCH_CHECK();
     fold_scalar_kernel<<<1, 256, 0, st>>>(LH, Mp, M, g, h, fl->fs.p + 2 * fo);
     GPS_LAUNCH_CHECK();
     ctx->launches += 3;
-    if (dss) {
-      if (!want_grad) {                                                        // the rows' share needs no product
-        col_dss_kernel<<<nbf, 256, 0, st>>>(fl->W.p, nullptr, fl->T2.p, Npp, M, lo, hi, h, lam, alpha, abar, lbar, rowobj);
+    if (dss && !want_grad) {                                                   // the rows' share needs no product
+      if (rows) {
+        col_dss_kernel<<<nbf, 256, 0, st>>>(fl->W.p, nullptr, fl->T2.p, Npp, M, r.lo, r.hi, h, lam, alpha, abar, lbar, rowobj);
         GPS_LAUNCH_CHECK();
         ctx->launches++;
-        continue;
       }
+    } else if (dss) {
       hhat_kernel<<<nbm, 256, 0, st>>>(Hinv, h, Mp, M, HX);
       GPS_LAUNCH_CHECK();
-      GPS_CHECK(fold_apply(ctx, fl, lo, hi, HX));                              // T1 = Hhat W_f
-      col_dss_kernel<<<nbf, 256, 0, st>>>(fl->W.p, fl->T1.p, fl->T2.p, Npp, M, lo, hi, h, lam, alpha, abar, lbar, rowobj);
-      GPS_LAUNCH_CHECK();
+      if (rows) {
+        GPS_CHECK(fold_apply(ctx, fl, r, HX));                                 // T1 = Hhat W_f
+        col_dss_kernel<<<nbf, 256, 0, st>>>(fl->W.p, fl->T1.p, fl->T2.p, Npp, M, r.lo, r.hi, h, lam, alpha, abar, lbar, rowobj);
+        GPS_LAUNCH_CHECK();
+      }
       GPS_CHECK(mm_gemm(ctx, fl, GEMM_KC_MC, HX, Pf, X2, -2.0));               // -2 Hhat P_f
       gw_dss_kernel<<<nbm, 256, 0, st>>>(X2, h, g, Mp, GW, bbar);
       GPS_LAUNCH_CHECK();
       ctx->launches += 3;
-    } else {
-      GPS_CHECK(fold_apply(ctx, fl, lo, hi, Hinv));                            // T1 = H^-1 W_f
-      col_kca_kernel<<<nbf, 256, 0, st>>>(fl->W.p, fl->T1.p, fl->T2.p, Npp, M, lo, hi, h, lam, alpha, 1.0 / (double)nf,
+    } else if (rows) {
+      GPS_CHECK(fold_apply(ctx, fl, r, Hinv));                                 // T1 = H^-1 W_f
+      col_kca_kernel<<<nbf, 256, 0, st>>>(fl->W.p, fl->T1.p, fl->T2.p, Npp, M, r.lo, r.hi, h, lam, alpha, 1.0 / (double)nf,
                                           mbar, cbar, rowobj);
       GPS_LAUNCH_CHECK();
       ctx->launches++;
-      if (!want_grad) continue;
-      GPS_CHECK(fold_rowdot(ctx, fl, lo, hi, mbar, hbar));                     // hbar = -W_f mbar
-      negate_kernel<<<blocks_for(Mp), 256, 0, st>>>(hbar, Mp);
-      GPS_LAUNCH_CHECK();
-      GPS_CHECK(fold_splitk(ctx, fl, fo, lo, hi, cbar, E));                    // E = W_f diag(cbar) W_f'
-      matvec_t_kernel<<<blocks_for(Mp), 256, 0, st>>>(Hinv, Mp, hbar, gbar);   // gbar = H^-1 hbar
-      GPS_LAUNCH_CHECK();
-      GPS_CHECK(mm_gemm(ctx, fl, GEMM_KC_MC, Hinv, E, Y, 1.0));                // Y = H^-1 E
-      GPS_CHECK(mm_gemm(ctx, fl, GEMM_KC_MC, Y, Hinv, Z, 1.0));                // Z = H^-1 E H^-1
-      hbar_kernel<<<nbm, 256, 0, st>>>(Z, h, gbar, Mp, M, HX);
-      GPS_LAUNCH_CHECK();
-      GPS_CHECK(fold_apply(ctx, fl, lo, hi, HX));                              // T1 = Hbar W_f
-      col_kcb_kernel<<<nbf, 256, 0, st>>>(fl->W.p, fl->T1.p, fl->T2.p, Npp, M, lo, hi, gbar, lam, alpha, mbar, cbar, abar,
-                                          lbar);
-      GPS_LAUNCH_CHECK();
-      GPS_CHECK(mm_gemm(ctx, fl, GEMM_KC_MC, HX, Pf, X2, -2.0));               // -2 Hbar P_f
-      gw_kc_kernel<<<nbm, 256, 0, st>>>(X2, Y, Pf, h, hbar, g, gbar, Mp, GW, bbar);
-      GPS_LAUNCH_CHECK();
-      ctx->launches += 5;
     }
   }
-  vec_sum_kernel<<<1, 1024, 0, st>>>(rowobj, N, fl->out.p + OUT_LOGDET);
+  // objective: the rows' shares add over the ranks, the fold terms are replicated and added once
+  vec_sum_kernel<<<1, 1024, 0, st>>>(rowobj, N, d_obj);
   GPS_LAUNCH_CHECK();
-  block_obj_kernel<<<1, 1, 0, st>>>(fl->out.p + OUT_LOGDET, fl->fs.p, dss ? 1 : 0, (double)nf, d_obj);
+  if (allreduce) GPS_CHECK(allreduce(ctx, d_obj, 2));
+  block_obj_kernel<<<1, 1, 0, st>>>(d_obj, fl->fs.p, dss ? 1 : 0, (double)nf, d_obj);
   GPS_LAUNCH_CHECK();
   ctx->launches += 2;
   f.pass2_done = true;
@@ -1094,6 +1131,41 @@ int block_pass2(gps_ctx* ctx, double* acc2, bool want_grad) {
   fl->ready = true;
   fl->block_seeds = want_grad;
   if (!want_grad) return GPS_OK;
+  if (!dss) {
+    // ---- C
+    for (int fo = 0; fo < 4; ++fo) {
+      double *E = A5 + fo * AF, *hbar = E + MM;
+      GPS_CHECK(fold_rowdot(ctx, fl, fr[fo], mbar, hbar));                     // W_f mbar
+      negate_kernel<<<nbv, 256, 0, st>>>(hbar, Mp);                            // hbar = -W_f mbar
+      GPS_LAUNCH_CHECK();
+      GPS_CHECK(fold_splitk(ctx, fl, fo, fr[fo], cbar, E));                    // E = W_f diag(cbar) W_f'
+      ctx->launches++;
+    }
+    if (allreduce) GPS_CHECK(allreduce(ctx, A5, 4 * AF));
+    // ---- D
+    for (int fo = 0; fo < 4; ++fo) {
+      const FoldRange r = fr[fo];
+      const unsigned nbf = blocks_for(std::max<int64_t>(1, r.hi - r.lo));
+      double *Pf = A4 + fo * AF, *g = Pf + MM, *Hinv = HI + fo * MM, *h = HV + fo * (size_t)Mp;
+      double *E = A5 + fo * AF, *hbar = E + MM, *gbar = GB + fo * (size_t)Mp;
+      matvec_t_kernel<<<nbv, 256, 0, st>>>(Hinv, Mp, hbar, gbar);              // gbar = H^-1 hbar
+      GPS_LAUNCH_CHECK();
+      GPS_CHECK(mm_gemm(ctx, fl, GEMM_KC_MC, Hinv, E, Y, 1.0));                // Y = H^-1 E
+      GPS_CHECK(mm_gemm(ctx, fl, GEMM_KC_MC, Y, Hinv, Z, 1.0));                // Z = H^-1 E H^-1
+      hbar_kernel<<<nbm, 256, 0, st>>>(Z, h, gbar, Mp, M, HX);
+      GPS_LAUNCH_CHECK();
+      if (r.hi > r.lo) {
+        GPS_CHECK(fold_apply(ctx, fl, r, HX));                                 // T1 = Hbar W_f
+        col_kcb_kernel<<<nbf, 256, 0, st>>>(fl->W.p, fl->T1.p, fl->T2.p, Npp, M, r.lo, r.hi, gbar, lam, alpha, mbar, cbar,
+                                            abar, lbar);
+        GPS_LAUNCH_CHECK();
+      }
+      GPS_CHECK(mm_gemm(ctx, fl, GEMM_KC_MC, HX, Pf, X2, -2.0));               // -2 Hbar P_f
+      gw_kc_kernel<<<nbm, 256, 0, st>>>(X2, Y, Pf, h, hbar, g, gbar, Mp, GW, bbar);
+      GPS_LAUNCH_CHECK();
+      ctx->launches += 4;
+    }
+  }
   block_seed_kernel<<<blocks_for(Npp), 256, 0, st>>>(N, Npp, il, alpha, abar, lbar, rv + RV_RBAR * Npp, rv + RV_TBAR * Npp);
   GPS_LAUNCH_CHECK();
   ctx->launches++;
@@ -1105,7 +1177,7 @@ int block_pass2(gps_ctx* ctx, double* acc2, bool want_grad) {
 void gps_fitc_large_free(gps_ctx* ctx) {
   gps_fitc_large* fl = ctx->fl;
   if (!fl) return;
-  for (DevBuf* b : {&fl->Kuf, &fl->V, &fl->W, &fl->T1, &fl->T2, &fl->sm, &fl->rv, &fl->mv, &fl->part, &fl->out, &fl->U, &fl->dotp, &fl->acc, &fl->fs})
+  for (DevBuf* b : {&fl->Kuf, &fl->V, &fl->W, &fl->T1, &fl->T2, &fl->sm, &fl->rv, &fl->mv, &fl->part, &fl->out, &fl->U, &fl->dotp, &fl->acc, &fl->fs, &fl->fb})
     if (b->p) cudaFree(b->p);
   if (fl->tasks) cudaFree(fl->tasks);
   if (fl->ftasks) cudaFree(fl->ftasks);
@@ -1135,8 +1207,8 @@ int gps_fitc_large_begin(gps_ctx* ctx, const double* theta, const double* U, int
                          int64_t world_n) {
   if (score < GPS_CRPS || score > GPS_KC) return gps_fail(ctx, GPS_EINVAL, "fitc: unknown score %d", score);
   const bool block = score == GPS_DSS || score == GPS_KC;
-  if (block && (ctx->N % 4 != 0 || (world_n > 0 && world_n != ctx->N)))
-    return gps_fail(ctx, GPS_EINVAL, "fitc dss/kc: needs N %% 4 == 0 (K20:541-543) and runs on one GPU in this version");
+  if (block && (world_n > 0 ? world_n : ctx->N) % 4 != 0)
+    return gps_fail(ctx, GPS_EINVAL, "fitc dss/kc: the four folds need N %% 4 == 0 (K20:541-543)");
   if (ctx->D > DMAX) return gps_fail(ctx, GPS_EINVAL, "fitc: D=%d > %d not supported", ctx->D, DMAX);
   if (M > 4096) return gps_fail(ctx, GPS_EINVAL, "fitc: M=%d > 4096 not supported", M);
   GPS_CUDA(cudaSetDevice(ctx->device));
@@ -1147,6 +1219,8 @@ int gps_fitc_large_begin(gps_ctx* ctx, const double* theta, const double* U, int
   GPS_CHECK(setup(ctx, M, block));
   gps_fitc_large* fl = ctx->fl;
   fl->ready = false;
+  fl->allreduce = nullptr;
+  fl->row_off = 0;
   gps_ctx* ch = fl->ch;
   const int D = ctx->D, Mp = fl->Mp;
   const size_t MM = (size_t)Mp * Mp;
@@ -1335,26 +1409,35 @@ int gps_fitc_large_eval(gps_ctx* ctx, const double* theta, const double* U, int 
   return gps_fitc_large_finish(ctx, a2, a3, obj, grad_theta, grad_U);
 }
 
-// row-sharded evaluation: the same chain with the packed accumulators summed over the ranks between the passes
+// row-sharded evaluation: the same chain with the packed accumulators summed over the ranks between the passes.
+// row_offset = first global row of this context's block (only the block objectives' fold geometry needs it)
 int gps_fitc_large_eval_sharded(gps_ctx* ctx, const double* theta, const double* U, int M, double jitter, int score,
-                                int64_t world_n, gps_allreduce_fn allreduce, double* obj, double* grad_theta,
-                                double* grad_U) {
+                                int64_t world_n, int64_t row_offset, gps_allreduce_fn allreduce, double* obj,
+                                double* grad_theta, double* grad_U) {
   if (M < 1 || M > 4096) return gps_fail(ctx, GPS_EINVAL, "fitc_eval_sharded: M=%d outside 1..4096", M);
+  const bool block = score == GPS_DSS || score == GPS_KC;
+  if (row_offset < 0 || row_offset + ctx->N > world_n)
+    return gps_fail(ctx, GPS_EINVAL, "fitc_eval_sharded: rows [%lld, %lld) outside the %lld global rows", (long long)row_offset,
+                    (long long)(row_offset + ctx->N), (long long)world_n);
   GPS_CHECK(gps_fitc_large_begin(ctx, theta, U, M, jitter, score, world_n));
   gps_fitc_large* fl = ctx->fl;
+  fl->allreduce = allreduce;
+  fl->row_off = row_offset;
   int64_t l1, l2, l3;
   gps_fitc_large_acc_len(M, ctx->D, &l1, &l2, &l3);
   GPS_CHECK(gps_ensure(ctx, fl->acc, (size_t)(l1 + l2 + l3)));
   double *a1 = fl->acc.p, *a2 = a1 + l1, *a3 = a2 + l2;
   const bool want_grad = grad_theta || grad_U;
-  GPS_CHECK(gps_fitc_large_pass1(ctx, a1));
-  GPS_CHECK(allreduce(ctx, a1, (size_t)l1));
-  GPS_CHECK(gps_fitc_large_pass2(ctx, a1, a2, want_grad));
-  GPS_CHECK(allreduce(ctx, a2, (size_t)l2));
-  if (want_grad) {
-    GPS_CHECK(gps_fitc_large_pass3(ctx, a2, a3));
-    GPS_CHECK(allreduce(ctx, a3, (size_t)l3));
+  int rc = gps_fitc_large_pass1(ctx, a1);
+  if (rc == GPS_OK) rc = allreduce(ctx, a1, (size_t)l1);
+  if (rc == GPS_OK) rc = gps_fitc_large_pass2(ctx, a1, a2, want_grad);   // block objectives: all-reduces inside, acc2 replicated
+  if (rc == GPS_OK && !block) rc = allreduce(ctx, a2, (size_t)l2);
+  if (rc == GPS_OK && want_grad) {
+    rc = gps_fitc_large_pass3(ctx, a2, a3);
+    if (rc == GPS_OK) rc = allreduce(ctx, a3, (size_t)l3);
   }
+  fl->allreduce = nullptr;
+  if (rc != GPS_OK) return rc;
   return gps_fitc_large_finish(ctx, a2, a3, obj, grad_theta, grad_U);
 }
 

@@ -74,6 +74,25 @@ def main():
                 ov, og, ogu = W.fitc_obj_grad(X, y, U, theta, O.SCORES[score])[:3]
                 check("M=%d %s library-NCCL sharded vs oracle (objective)" % (m_ind, score), abs(sv - ov) / abs(ov), 1e-8)
                 check("M=%d %s library-NCCL sharded vs oracle (gradient)" % (m_ind, score), max(rel(sg, og), rel(sgu, ogu)), 1e-6)
+    # block objectives (4-fold DSS, kc): folds are ranges of the GLOBAL row order and straddle the ranks' uneven blocks
+    n4 = 20012
+    X4, y4 = synth.kin40k_like(n4, seed=5)
+    cuts = [0] + [gd.row_block(n4, r, world)[1] + 37 for r in range(world - 1)] + [n4]
+    part.set_data(torch.from_numpy(X4[cuts[rank]:cuts[rank + 1]]).cuda(), torch.from_numpy(y4[cuts[rank]:cuts[rank + 1]]).cuda())
+    whole.set_data(torch.from_numpy(X4).cuda(), torch.from_numpy(y4).cuda())
+    for m_ind in (20, 64):
+        U = X4[rng.choice(n4, m_ind, replace=False)] + 0.05 * rng.standard_normal((m_ind, 8))
+        for kind in ("dss", "kc"):
+            sv, sg, sgu = part.fitc_eval_sharded(theta, U, kind, n4)
+            v1, g1, gu1 = whole.fitc_eval(theta, U, kind)
+            check("M=%d %s block objective row-sharded vs single GPU" % (m_ind, kind),
+                  max(abs(sv - v1) / abs(v1), rel(sg, g1), rel(sgu, gu1)), 1e-9)
+            if m_ind == 20:
+                ov, og, ogu = W.fitc_block_obj_grad(X4, y4, U, theta, kind)
+                check("M=%d %s block objective row-sharded vs oracle" % (m_ind, kind),
+                      max(abs(sv - ov) / abs(ov) * 100, rel(sg, og), rel(sgu, ogu)), 1e-6)
+    part.set_data(torch.from_numpy(X[lo:hi]).cuda(), torch.from_numpy(y[lo:hi]).cuda())
+    whole.set_data(torch.from_numpy(X).cuda(), torch.from_numpy(y).cuda())
     part.comm_transport(True)
     # every rank got the same numbers
     U = synth.inducing_init(20)

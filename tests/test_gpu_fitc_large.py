@@ -284,3 +284,57 @@ def test_large_m_block_objective_after_loo_score_and_back(ctx):
             oval, og, ogU = Wd.fitc_obj_grad(X, y, U, theta, O.SCORES[kind])[:3]
         assert abs(val - oval) <= OBJ_TOL * abs(oval), kind
         assert relerr(grad, og) <= GRAD_TOL and relerr(gU, ogU) <= GRAD_TOL, kind
+
+
+@pytest.mark.parametrize("m_ind", [20, 48])
+def test_block_objectives_through_sharded_entry_single_rank(m_ind):
+    """gps_fitc_eval_sharded with a one-rank communicator: the row-offset exchange, the per-fold all-reduces and the
+    replicated M x M chain of the block objectives, against gps_fitc_eval (row kernels at M = 20, matrix form at 48).
+    The multi-rank case (folds straddling ranks) runs under torchrun in tests/mgpu_check.py."""
+    import ctypes as C
+    from gpscore_b200 import api, lib as L
+    rng = np.random.default_rng(50 + m_ind)
+    n = 1500                                        # 4 | n; fold size 375
+    X = rng.uniform(-1, 1, (n, 8))
+    y = np.sin(X @ rng.standard_normal(8)) + 0.1 * rng.standard_normal(n)
+    U = rng.uniform(-1, 1, (m_ind, 8))
+    theta = np.concatenate([[0.2], np.log(rng.uniform(0.8, 2.0, 8)), [-2.0]])
+    c = api.Context(0)
+    try:
+        uid = (C.c_char * 128)()
+        code = c._lib.gps_comm_unique_id(uid)
+        if code != L.GPS_OK:
+            pytest.skip("libnccl.so.2 not loadable")
+        c._check(c._lib.gps_comm_init(c._h, C.c_char_p(uid.raw), 0, 1))
+        c.set_data(_dev(X), _dev(y))
+        for kind in ("dss", "kc"):
+            a = c.fitc_eval(theta, U, kind)
+            b = c.fitc_eval_sharded(theta, U, kind, n)
+            assert abs(a[0] - b[0]) <= 1e-10 * abs(a[0]), kind
+            assert relerr(b[1], a[1]) <= 1e-8 and relerr(b[2], a[2]) <= 1e-8, kind
+        with pytest.raises(L.GpsError):             # the ranks' rows must add up to world_n
+            c.fitc_eval_sharded(theta, U, "dss", n + 4)
+    finally:
+        c.close()
+
+
+def test_large_m_rows_grow_inside_one_padded_shape(ctx):
+    """N changes without changing the padded shape (1000 -> 1020 rows, both padded to 1024): the per-row scalar
+    block is laid out with stride N and has to follow (it once kept the first N's size)."""
+    from oracle import woodbury as Wd
+    from oracle import gp_oracle as O
+    rng = np.random.default_rng(77)
+    X = rng.uniform(-1, 1, (1020, 8))
+    y = np.sin(X @ rng.standard_normal(8)) + 0.1 * rng.standard_normal(1020)
+    U = rng.uniform(-1, 1, (48, 8))
+    theta = np.concatenate([[0.2], np.log(rng.uniform(0.8, 2.0, 8)), [-2.0]])
+    for n in (1000, 1020):
+        ctx.set_data(_dev(X[:n]), _dev(y[:n]))
+        for kind in ("crps", "kc"):
+            val, grad, gU = ctx.fitc_eval(theta, U, kind)
+            if kind == "kc":
+                oval, og, ogU = Wd.fitc_block_obj_grad(X[:n], y[:n], U, theta, kind)
+            else:
+                oval, og, ogU = Wd.fitc_obj_grad(X[:n], y[:n], U, theta, O.SCORES[kind])[:3]
+            assert abs(val - oval) <= OBJ_TOL * abs(oval)
+            assert relerr(grad, og) <= GRAD_TOL and relerr(gU, ogU) <= GRAD_TOL
