@@ -486,6 +486,25 @@ def run_ours(args):
         ov, og, ogu = WB.fitc_obj_grad(X, y, U, theta, O.SCORE_CRPS)[:3]
         gates.check("fitc20_N10000_obj_vs_oracle", abs(fv - ov) / abs(ov), OBJ_TOL)
         gates.check("fitc20_N10000_grad_vs_oracle", max(relmax(fg, og), relmax(fgu, ogu)), GRAD_TOL)
+    # ---- the FITC block objectives (4-fold DSS K20:538-587, block CRPS "kc" K20:669-720) at the same shape ----
+    rng_k = np.random.default_rng(5)
+    U64 = X[rng_k.choice(N_FULL, 64, replace=False)] + 0.01 * rng_k.standard_normal((64, D))
+    blk = {"workload": "KIN40K-FITC N=10000 D=8: 4-fold block objectives, objective + gradient incl. inducing inputs; "
+                       "M=20 runs the row kernels of gps_fitc.cu, M=64 the matrix form (gps_fitc_large.cu)"}
+    blk_res = {}
+    for m_b, U_b in ((20, U), (64, U64)):           # all timings first: the oracle's BLAS threads disturb host-bound calls
+        for kind in ("dss", "kc"):
+            ms_k, blk_res[m_b, kind] = timed(lambda: ctx.fitc_eval(theta, U_b, kind), 10, warm=2)
+            blk["M%d_%s_ms_per_eval" % (m_b, kind)] = ms_k
+    if rank == 0:
+        from oracle import woodbury as WB
+        for m_b, U_b in ((20, U), (64, U64)):
+            for kind in ("dss", "kc"):
+                kv, kg, kgu = blk_res[m_b, kind]
+                ov, og, ogu = WB.fitc_block_obj_grad(X, y, U_b, theta, kind)
+                gates.check("fitc%d_N10000_%s_vs_oracle" % (m_b, kind),
+                            max(abs(kv - ov) / abs(ov) * (GRAD_TOL / OBJ_TOL), relmax(kg, og), relmax(kgu, ogu)), GRAD_TOL)
+    fitc["block_objectives"] = blk
     if world > 1:
         # row-sharded evaluation of ONE problem: each rank holds N/world rows, the three all-reduces run inside
         # the library on the context's stream (NCCL)
@@ -510,6 +529,13 @@ def run_ours(args):
         v1, g1, gu1 = ctx.fitc_eval(th0, U, "crps")
         gates.check("fitc20_N10000_sharded_vs_single", max(abs(sv - v1) / abs(v1), relmax(sg, g1), relmax(sgu, gu1)), SHARD_TOL,
                     world=world)
+        # the block objectives row-sharded: folds are quarters of the global row order and straddle the ranks' blocks
+        for kind in ("dss", "kc"):
+            ms_ks, (sv, sg, sgu) = timed(lambda: cs.fitc_eval_sharded(th0, U64, kind, N_FULL), 5, warm=2)
+            v1, g1, gu1 = ctx.fitc_eval(th0, U64, kind)
+            blk["M64_%s_row_sharded_ms_per_eval" % kind] = ms_ks
+            gates.check("fitc64_N10000_%s_sharded_vs_single" % kind,
+                        max(abs(sv - v1) / abs(v1), relmax(sg, g1), relmax(sgu, gu1)), SHARD_TOL, world=world)
         cs.close()
 
     # ---- FITC scaling-sweep point: N = 1e6 rows, M = 20 (BASELINE configs[4]) -----------------------------
