@@ -494,8 +494,10 @@ def run_ours(args):
     blk_res = {}
     for m_b, U_b in ((20, U), (64, U64)):           # all timings first: the oracle's BLAS threads disturb host-bound calls
         for kind in ("dss", "kc"):
-            ms_k, blk_res[m_b, kind] = timed(lambda: ctx.fitc_eval(theta, U_b, kind), 10, warm=2)
-            blk["M%d_%s_ms_per_eval" % (m_b, kind)] = ms_k
+            runs_k = [timed(lambda: ctx.fitc_eval(theta, U_b, kind), 10, warm=2) for _ in range(3)]
+            blk_res[m_b, kind] = runs_k[0][1]
+            blk["M%d_%s_ms_per_eval" % (m_b, kind)] = min(r[0] for r in runs_k)   # best of 3 batches of 10: these calls
+            # are host-latency-bound (several stream synchronisations each) and a 2 ms batch is easily disturbed
     if rank == 0:
         from oracle import woodbury as WB
         for m_b, U_b in ((20, U), (64, U64)):

@@ -146,14 +146,23 @@ rowdot_reduce_kernel(const double* __restrict__ part, int rows, int chunks, doub
   out[r] = s;
 }
 
-// out[c] = sum_k Mat[k][c] x[k]
+// out[c] = sum_k Mat[k][c] x[k]: 16 columns x 16 k-slices per block, fixed-order combine (grid = Mp / 16)
 __global__ void __launch_bounds__(256)
 matvec_t_kernel(const double* __restrict__ Mat, int Mp, const double* __restrict__ x, double* __restrict__ out) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= Mp) return;
+  __shared__ double sh[16][17];
+  const int cl = threadIdx.x & 15, ks = threadIdx.x >> 4;
+  const int c = blockIdx.x * 16 + cl;
   double s = 0.0;
-  for (int k = 0; k < Mp; ++k) s = fma(Mat[(int64_t)k * Mp + c], x[k], s);
-  out[c] = s;
+#pragma unroll 4
+  for (int k = ks; k < Mp; k += 16) s = fma(Mat[(int64_t)k * Mp + c], x[k], s);
+  sh[ks][cl] = s;
+  __syncthreads();
+  if (ks == 0) {
+    double t = 0.0;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) t += sh[q][cl];
+    out[c] = t;
+  }
 }
 
 // out = sum_s part[s] (+ I); lower tiles only are valid when `lower`: the upper triangle is mirrored
@@ -642,21 +651,8 @@ kgrad_reduce_kernel(const double* __restrict__ part, int gx, int gy, int M, int 
                     double* __restrict__ out) {
   constexpr int NV = MT * (1 + DMX) + DMX;
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t == 0) {
-    double s = 0.0;
-    for (int bx = 0; bx < gx; ++bx)
-      for (int by = 0; by < gy; ++by)
-        for (int mm = 0; mm < MT; ++mm) s += part[((int64_t)by * gx + bx) * NV + mm * (1 + DMX)];
-    out[0] = s;
-  } else if (t <= D) {
-    const int d = t - 1;
-    double s = 0.0;
-    for (int bx = 0; bx < gx; ++bx)
-      for (int by = 0; by < gy; ++by) s += part[((int64_t)by * gx + bx) * NV + MT * (1 + DMX) + d];
-    out[1 + d] = s;
-  } else if (t < 1 + DMAX) {
-    return;
-  } else {
+  if (t < 1 + DMAX) return;                        // the D + 1 global sums: kgrad_globals_kernel
+  {
     const int e = t - (1 + DMAX);
     if (e >= M * D) return;
     const int m = e / D, d = e - m * D;
@@ -665,6 +661,25 @@ kgrad_reduce_kernel(const double* __restrict__ part, int gx, int gy, int M, int 
     for (int by = 0; by < gy; ++by) s += part[((int64_t)by * gx + bx) * NV + mm * (1 + DMX) + 1 + d];
     out[1 + DMAX + e] = -s * par[2 + d];
   }
+}
+
+// the D + 1 sums over ALL partial blocks (block 0: sum G -> out[0]; block 1 + d: g_b partial -> out[1 + d]): every
+// thread takes a fixed strided share, then a fixed-order block sum (was one thread per sum: 0.18 ms of latency)
+template <int MT, int DMX>
+__global__ void __launch_bounds__(256)
+kgrad_globals_kernel(const double* __restrict__ part, int gx, int gy, double* __restrict__ out) {
+  constexpr int NV = MT * (1 + DMX) + DMX;
+  __shared__ double sh[32];
+  const int64_t nb = (int64_t)gx * gy;
+  double s = 0.0;
+  if (blockIdx.x == 0) {
+    for (int64_t e = threadIdx.x; e < nb * MT; e += blockDim.x) s += part[(e / MT) * NV + (e % MT) * (1 + DMX)];
+  } else {
+    const int d = blockIdx.x - 1;
+    for (int64_t e = threadIdx.x; e < nb; e += blockDim.x) s += part[e * NV + MT * (1 + DMX) + d];
+  }
+  s = block_sum(s, sh);
+  if (threadIdx.x == 0) out[blockIdx.x] = s;
 }
 
 // prediction columns: mean = Ws_:t . beta, var = sn2 + e^a - |Vs_:t|^2 + |Ws_:t|^2   (K20:76-83)
@@ -925,7 +940,9 @@ int kgrad(gps_ctx* ctx, gps_fitc_large* fl, const double* Kbar, const double* Km
   const int nthreads = 1 + DMAX + M * D;
   kgrad_reduce_kernel<MT, DMX><<<blocks_for(nthreads), 256, 0, ctx->stream>>>(fl->part.p, gx, (int)gy, M, D, ctx->params.p, out);
   GPS_LAUNCH_CHECK();
-  ctx->launches += 2;
+  kgrad_globals_kernel<MT, DMX><<<1 + D, 256, 0, ctx->stream>>>(fl->part.p, gx, (int)gy, out);
+  GPS_LAUNCH_CHECK();
+  ctx->launches += 3;
   return GPS_OK;
 }
 
@@ -1088,7 +1105,7 @@ int block_pass2(gps_ctx* ctx, double* acc2, bool want_grad) {
     GPS_LAUNCH_CHECK();
     GPS_CHECK(factor(ctx, fl, LH, LHi, "I - W_f Lambda_f^-1 W_f' (fold)"));
     GPS_CHECK(mm_gemm(ctx, fl, GEMM_MC_MC, LHi, LHi, Hinv, 1.0));              // H^-1 = L_H^-T L_H^-1
-    matvec_t_kernel<<<nbv, 256, 0, st>>>(Hinv, Mp, g, h);                      // h = H^-1 g (H^-1 symmetric)
+    matvec_t_kernel<<<Mp / 16, 256, 0, st>>>(Hinv, Mp, g, h);                      // h = H^-1 g (H^-1 symmetric)
     GPS_LAUNCH_CHECK();
     fold_scalar_kernel<<<1, 256, 0, st>>>(LH, Mp, M, g, h, fl->fs.p + 2 * fo);
     GPS_LAUNCH_CHECK();
@@ -1148,7 +1165,7 @@ int block_pass2(gps_ctx* ctx, double* acc2, bool want_grad) {
       const unsigned nbf = blocks_for(std::max<int64_t>(1, r.hi - r.lo));
       double *Pf = A4 + fo * AF, *g = Pf + MM, *Hinv = HI + fo * MM, *h = HV + fo * (size_t)Mp;
       double *E = A5 + fo * AF, *hbar = E + MM, *gbar = GB + fo * (size_t)Mp;
-      matvec_t_kernel<<<nbv, 256, 0, st>>>(Hinv, Mp, hbar, gbar);              // gbar = H^-1 hbar
+      matvec_t_kernel<<<Mp / 16, 256, 0, st>>>(Hinv, Mp, hbar, gbar);              // gbar = H^-1 hbar
       GPS_LAUNCH_CHECK();
       GPS_CHECK(mm_gemm(ctx, fl, GEMM_KC_MC, Hinv, E, Y, 1.0));                // Y = H^-1 E
       GPS_CHECK(mm_gemm(ctx, fl, GEMM_KC_MC, Y, Hinv, Z, 1.0));                // Z = H^-1 E H^-1
@@ -1332,7 +1349,7 @@ int gps_fitc_large_pass3(gps_ctx* ctx, const double* acc2, double* acc3) {
   sw_kernel<<<blocks_for((int64_t)MM), 256, 0, st>>>(mv + MV_BETA * Mp, bbar, acc2, Mp, block ? 1.0 : 2.0, sm + SM_SW * MM);
   GPS_LAUNCH_CHECK();
   GPS_CHECK(chol_adjoint(ctx, fl, sm + SM_LC * MM, sm + SM_LCI * MM, sm + SM_SW * MM, nlml ? 1 : 0, sm + SM_CBAR * MM));
-  matvec_t_kernel<<<blocks_for(Mp), 256, 0, st>>>(sm + SM_LCI * MM, Mp, bbar, mv + MV_VYBAR * Mp);
+  matvec_t_kernel<<<Mp / 16, 256, 0, st>>>(sm + SM_LCI * MM, Mp, bbar, mv + MV_VYBAR * Mp);
   GPS_LAUNCH_CHECK();
   ctx->launches += 2;
   GPS_CHECK(big_gemm(ctx, fl, GEMM_KC_MC, fl->t_full, sm + SM_CBAR * MM, fl->V.p, fl->T1.p));     // CV
