@@ -619,8 +619,9 @@ def run_ours(args):
         "workload": "kin40k-FULL prediction + test scoring (KF:267-292): N=%d train, T=%d test rows split over %d GPU(s); "
                     "every rank factors K (replicated), predicts its rows, six metric sums all-reduced" % (N_FULL, T_TEST, world),
         "ms": ms_p, "test_rows_per_s": T_TEST / (ms_p * 1e-3), "metrics": met,
-        "bound": "tensor: T x N x N cross-Gram product (2 T N^2 = %.1e flop over the ranks) after the replicated 2/3 N^3 "
-                 "factor+invert" % (2.0 * T_TEST * N_FULL * N_FULL)}
+        "bound": "tensor: cross-Gram block times the triangular factor inverse, k-ranges stop at the diagonal (T N^2 = %.1e "
+                 "flop over the ranks), after the replicated 2/3 N^3 factor + factor inverse (no K^-1: alpha by two "
+                 "triangular sweeps)" % (1.0 * T_TEST * N_FULL * N_FULL)}
     ms_pf, metf = timed(lambda: gdist.sharded_predict_metrics(ctx, th0, Xsd, ysd, inducing_x=U), 5, warm=1)
     sharded["fitc20_predict_metrics"] = {
         "workload": "KIN40K-FITC-20 prediction + test scoring (K20:270-304): T=%d test rows split over %d GPU(s)" % (T_TEST, world),

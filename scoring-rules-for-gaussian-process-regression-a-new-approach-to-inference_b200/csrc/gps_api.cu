@@ -118,7 +118,7 @@ static int stage_mark(gps_ctx* ctx, int which) {
 }
 
 // K = ARD(X, X) + sn2 I  ->  L, L^-1, K^-1 (in Kb), alpha.  logdiag optionally.
-int gps_factor_and_invert(gps_ctx* ctx, bool want_logdet) {
+int gps_factor_and_invert(gps_ctx* ctx, bool want_logdet, bool want_kinv) {
   const int64_t N = ctx->N, Np = ctx->Np;
   double* v = ctx->vecs.p;
   GPS_CHECK(stage_mark(ctx, gps_ctx::ST_BEGIN));
@@ -136,6 +136,7 @@ int gps_factor_and_invert(gps_ctx* ctx, bool want_logdet) {
     GPS_CHECK(gps_trtri(ctx, ctx->Kb.p, ctx->Xb.p, ctx->Sb.p, Np));
   }
   GPS_CHECK(stage_mark(ctx, gps_ctx::ST_TRTRI));
+  if (!want_kinv) return GPS_OK;            // prediction: L^-1 (Xb) is all it needs
   GPS_CHECK(gps_lauum(ctx, ctx->Xb.p, ctx->Kb.p, Np));
   GPS_CHECK(stage_mark(ctx, gps_ctx::ST_LAUUM));
   GPS_CHECK(gps_symv(ctx, ctx->Kb.p, Np, ctx->y.p, v + V_ALPHA * Np));

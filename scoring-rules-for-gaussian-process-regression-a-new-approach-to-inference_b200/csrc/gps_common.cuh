@@ -161,7 +161,7 @@ int gps_stage_in(gps_ctx* ctx, const double* p, size_t n, DevBuf& tmp, const dou
 int gps_ensure_ws(gps_ctx* ctx, int64_t Np);
 int gps_upload_params(gps_ctx* ctx, const double* theta, int D, double* ea_out, double* sn2_out);
 int gps_upload_tasks2(gps_ctx* ctx, const std::vector<GemmTask>& h);
-int gps_factor_and_invert(gps_ctx* ctx, bool want_logdet);
+int gps_factor_and_invert(gps_ctx* ctx, bool want_logdet, bool want_kinv = true);
 int gps_full_dss(gps_ctx* ctx, double* par_obj, double* par_gsum, bool want_grad);
 void gps_ctx_release(gps_ctx* child);
 // gps_fitc_large.cu

@@ -3,14 +3,16 @@
 //
 // The reference forms the full T x T predictive covariance (cal_mean_and_cov, KF:121-126) and
 // keeps its diagonal (KF:273); at T = 30 000 that matrix alone is 7.2 GB.  Here
-//   mean_t = k_t' alpha,      var_t = sn2 + e^a - k_t' K^-1 k_t
-// are produced per block of test rows: cross-Gram tile -> DMMA product with K^-1 -> fused row
-// reduction.  Rows of the test set are independent, which is what multi-GPU runs shard.
+//   mean_t = k_t' alpha,      var_t = sn2 + e^a - k_t' K^-1 k_t = sn2 + e^a - |L^-1 k_t|^2
+// are produced per block of test rows: cross-Gram tile -> DMMA product with the TRIANGULAR factor inverse
+// (block k-ranges stop at the diagonal: T N^2 flops, half of a product with the full K^-1) -> fused row
+// reduction (dot with alpha, sum of squares).  Rows of the test set are independent, which is what
+// multi-GPU runs shard.
 #include "gps_common.cuh"
 
 namespace {
 
-// one warp per test row: mean = Ks[t,:] . alpha ; q = Ks[t,:] . V[t,:] ; var = sn2 + ea - q
+// one warp per test row: mean = Ks[t,:] . alpha ; q = |V[t,:]|^2 with V = Ks L^-T ; var = sn2 + ea - q
 __global__ void __launch_bounds__(256)
 predict_rows_kernel(const double* __restrict__ Ks, const double* __restrict__ V, int64_t ld, int64_t rows,
                     const double* __restrict__ alpha, const double* __restrict__ par,
@@ -26,14 +28,59 @@ predict_rows_kernel(const double* __restrict__ Ks, const double* __restrict__ V,
     const double2 kk = k[j], vv = v[j], aa = a[j];
     m = fma(kk.x, aa.x, m);
     m = fma(kk.y, aa.y, m);
-    q = fma(kk.x, vv.x, q);
-    q = fma(kk.y, vv.y, q);
+    q = fma(vv.x, vv.x, q);
+    q = fma(vv.y, vv.y, q);
   }
   m = warp_sum(m);
   q = warp_sum(q);
   if (lane == 0) {
     mean[t] = m;
     var[t] = par[1] + par[0] - q;
+  }
+}
+
+// u = L^-1 y on the block-lower-triangular Xinv (row i reads the columns below (i / 128 + 1) * 128; the diagonal blocks
+// hold explicit zeros above the diagonal, the strict upper block triangle is undefined): one warp per row
+__global__ void __launch_bounds__(256)
+trmv_lower_kernel(const double* __restrict__ A, int64_t Np, const double* __restrict__ x, double* __restrict__ out) {
+  const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= Np) return;
+  const int64_t jmax = (row / GPS_TILE + 1) * GPS_TILE;
+  const double2* a = reinterpret_cast<const double2*>(A + row * Np);
+  const double2* xv = reinterpret_cast<const double2*>(x);
+  double s0 = 0.0, s1 = 0.0;
+  for (int64_t j = lane; j < jmax / 2; j += 32) {
+    const double2 aa = a[j], xx = xv[j];
+    s0 = fma(aa.x, xx.x, s0);
+    s1 = fma(aa.y, xx.y, s1);
+  }
+  const double s = warp_sum(s0 + s1);
+  if (lane == 0) out[row] = s;
+}
+
+// alpha = L^-T u: out[j] = sum over i >= (j / 128) * 128 of Xinv[i][j] u[i].  A block owns 32 columns; its 8 warps take
+// the rows i = i0 + w, i0 + w + 8, ...; fixed-order combine in shared memory (grid = Np / 32)
+__global__ void __launch_bounds__(256)
+trmv_lower_t_kernel(const double* __restrict__ A, int64_t Np, const double* __restrict__ u, double* __restrict__ out) {
+  __shared__ double sh[8][33];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t j = (int64_t)blockIdx.x * 32 + lane;
+  const int64_t i0 = (j / GPS_TILE) * GPS_TILE;
+  double s0 = 0.0, s1 = 0.0;
+  int64_t i = i0 + w;
+  for (; i + 8 < Np; i += 16) {
+    s0 = fma(A[i * Np + j], u[i], s0);
+    s1 = fma(A[(i + 8) * Np + j], u[i + 8], s1);
+  }
+  if (i < Np) s0 = fma(A[i * Np + j], u[i], s0);
+  sh[w][lane] = s0 + s1;
+  __syncthreads();
+  if (w == 0) {
+    double t = 0.0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) t += sh[q][lane];
+    out[j] = t;
   }
 }
 
@@ -58,9 +105,18 @@ int gps_full_predict(gps_ctx* ctx, const double* theta, const double* Xs, int64_
   GPS_CHECK(gps_ensure_ws(ctx, Np));
   GPS_CHECK(gps_upload_params(ctx, theta, D, nullptr, nullptr));
   ctx->gemm_events_used = 0;
-  GPS_CHECK(gps_factor_and_invert(ctx, false));
+  // factor and invert the factor only: alpha = L^-T (L^-1 y) by two triangular sweeps, no K^-1 (saves the LAUUM stage)
+  GPS_CHECK(gps_factor_and_invert(ctx, false, false));
   GPS_CHECK(gps_check_info(ctx));
   ctx->loo_valid = false;
+  {
+    double* v = ctx->vecs.p;
+    trmv_lower_kernel<<<(unsigned)((Np + 7) / 8), 256, 0, ctx->stream>>>(ctx->Xb.p, Np, ctx->y.p, v + V_U * Np);
+    GPS_LAUNCH_CHECK();
+    trmv_lower_t_kernel<<<(unsigned)(Np / 32), 256, 0, ctx->stream>>>(ctx->Xb.p, Np, v + V_U * Np, v + V_ALPHA * Np);
+    GPS_LAUNCH_CHECK();
+    ctx->launches += 2;
+  }
   const double* dXs;
   GPS_CHECK(gps_stage_in(ctx, Xs, (size_t)T * D, ctx->stage[0], &dXs));
   const bool dev_out = gps_is_device_ptr(mean) && gps_is_device_ptr(var);
@@ -71,28 +127,29 @@ int gps_full_predict(gps_ctx* ctx, const double* theta, const double* Xs, int64_
     dmean = ctx->stage[1].p;
     dvar = ctx->stage[2].p;
   }
-  // after the inversion L^-1 (Xb) and the scratch (Sb) are free: reuse them as the
-  // cross-Gram block and its product with K^-1, Np rows at a time.
+  // alpha = K^-1 y is in the vectors; from here on only L^-1 (Xb, lower block triangle, diagonal blocks with explicit
+  // zeros above the diagonal) is needed: the scratch (Sb) takes the cross-Gram block, K^-1's buffer (Kb) its product
+  // with L^-T, Np test rows at a time.  Task (ti, tj) contracts over k < (tj + 1) * 128 only; longest tasks first.
   const int64_t chunk = Np;
   std::vector<GemmTask> tasks;
   for (int64_t t0 = 0; t0 < T; t0 += chunk) {
     const int64_t rows = (T - t0 < chunk) ? (T - t0) : chunk;
     const int64_t rows_p = gps_pad(rows);
-    GPS_CUDA(cudaMemsetAsync(ctx->Xb.p, 0, (size_t)rows_p * Np * sizeof(double), ctx->stream));
-    GPS_CHECK(gps_gram_rect(ctx, dXs + t0 * D, rows, ctx->X.p, N, D, ctx->params.p, ctx->Xb.p, Np));
+    GPS_CUDA(cudaMemsetAsync(ctx->Sb.p, 0, (size_t)rows_p * Np * sizeof(double), ctx->stream));
+    GPS_CHECK(gps_gram_rect(ctx, dXs + t0 * D, rows, ctx->X.p, N, D, ctx->params.p, ctx->Sb.p, Np));
     tasks.clear();
-    for (int ti = 0; ti < rows_p / GPS_TILE; ++ti)
-      for (int tj = 0; tj < Np / GPS_TILE; ++tj) {
+    for (int tj = (int)(Np / GPS_TILE) - 1; tj >= 0; --tj)
+      for (int ti = 0; ti < rows_p / GPS_TILE; ++ti) {
         GemmTask t;
-        t.a_row = ti * GPS_TILE; t.b_row = tj * GPS_TILE; t.k0 = 0; t.k1 = (int)Np;
+        t.a_row = ti * GPS_TILE; t.b_row = tj * GPS_TILE; t.k0 = 0; t.k1 = (tj + 1) * GPS_TILE;
         t.c_row = ti * GPS_TILE; t.c_col = tj * GPS_TILE; t.flags = 0; t.pad = 0;
         tasks.push_back(t);
       }
     GPS_CHECK(gps_upload_tasks2(ctx, tasks));
-    GPS_CHECK(gps_gemm_tasks(ctx, GEMM_KC_KC, ctx->Xb.p, Np, ctx->Kb.p, Np, ctx->Sb.p, Np, 1.0, 0.0, nullptr,
+    GPS_CHECK(gps_gemm_tasks(ctx, GEMM_KC_KC, ctx->Sb.p, Np, ctx->Xb.p, Np, ctx->Kb.p, Np, 1.0, 0.0, nullptr,
                              false, ctx->d_tasks2, tasks.size()));
     predict_rows_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, ctx->stream>>>(
-        ctx->Xb.p, ctx->Sb.p, Np, rows, ctx->vecs.p + V_ALPHA * Np, ctx->params.p, dmean + t0, dvar + t0);
+        ctx->Sb.p, ctx->Kb.p, Np, rows, ctx->vecs.p + V_ALPHA * Np, ctx->params.p, dmean + t0, dvar + t0);
     GPS_LAUNCH_CHECK();
     ctx->launches++;
   }
