@@ -162,6 +162,8 @@ int gps_ensure_ws(gps_ctx* ctx, int64_t Np);
 int gps_upload_params(gps_ctx* ctx, const double* theta, int D, double* ea_out, double* sn2_out);
 int gps_upload_tasks2(gps_ctx* ctx, const std::vector<GemmTask>& h);
 int gps_factor_and_invert(gps_ctx* ctx, bool want_logdet, bool want_kinv = true);
+// gps_predict.cu
+int gps_alpha_from_linv(gps_ctx* ctx, const double* Xinv, int64_t Np, const double* y, double* u, double* alpha, double* d);
 int gps_full_dss(gps_ctx* ctx, double* par_obj, double* par_gsum, bool want_grad);
 void gps_ctx_release(gps_ctx* child);
 // gps_fitc_large.cu

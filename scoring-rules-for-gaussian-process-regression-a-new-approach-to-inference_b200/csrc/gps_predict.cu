@@ -84,12 +84,56 @@ trmv_lower_t_kernel(const double* __restrict__ A, int64_t Np, const double* __re
   }
 }
 
+// d[j] = (K^-1)_jj = sum over i >= j of Xinv[i][j]^2, same decomposition as trmv_lower_t_kernel
+__global__ void __launch_bounds__(256)
+colsq_lower_kernel(const double* __restrict__ A, int64_t Np, double* __restrict__ out) {
+  __shared__ double sh[8][33];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int64_t j = (int64_t)blockIdx.x * 32 + lane;
+  const int64_t i0 = (j / GPS_TILE) * GPS_TILE;
+  double s0 = 0.0, s1 = 0.0;
+  int64_t i = i0 + w;
+  for (; i + 8 < Np; i += 16) {
+    const double a = A[i * Np + j], b = A[(i + 8) * Np + j];
+    s0 = fma(a, a, s0);
+    s1 = fma(b, b, s1);
+  }
+  if (i < Np) {
+    const double a = A[i * Np + j];
+    s0 = fma(a, a, s0);
+  }
+  sh[w][lane] = s0 + s1;
+  __syncthreads();
+  if (w == 0) {
+    double t = 0.0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) t += sh[q][lane];
+    out[j] = t;
+  }
+}
+
 __global__ void pad_identity_kernel(double* __restrict__ K, int64_t n, int64_t Np) {
   const int64_t i = n + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < Np) K[i * Np + i] = 1.0;
 }
 
 }  // namespace
+
+// alpha = K^-1 y = L^-T (L^-1 y) and (optionally) d = diag K^-1 from the factor inverse alone (no LAUUM):
+// what prediction and the objective-only grid sweep need
+int gps_alpha_from_linv(gps_ctx* ctx, const double* Xinv, int64_t Np, const double* y, double* u, double* alpha, double* d) {
+  trmv_lower_kernel<<<(unsigned)((Np + 7) / 8), 256, 0, ctx->stream>>>(Xinv, Np, y, u);
+  GPS_LAUNCH_CHECK();
+  trmv_lower_t_kernel<<<(unsigned)(Np / 32), 256, 0, ctx->stream>>>(Xinv, Np, u, alpha);
+  GPS_LAUNCH_CHECK();
+  ctx->launches += 2;
+  if (d) {
+    colsq_lower_kernel<<<(unsigned)(Np / 32), 256, 0, ctx->stream>>>(Xinv, Np, d);
+    GPS_LAUNCH_CHECK();
+    ctx->launches++;
+  }
+  return GPS_OK;
+}
 
 extern "C" {
 
@@ -109,14 +153,7 @@ int gps_full_predict(gps_ctx* ctx, const double* theta, const double* Xs, int64_
   GPS_CHECK(gps_factor_and_invert(ctx, false, false));
   GPS_CHECK(gps_check_info(ctx));
   ctx->loo_valid = false;
-  {
-    double* v = ctx->vecs.p;
-    trmv_lower_kernel<<<(unsigned)((Np + 7) / 8), 256, 0, ctx->stream>>>(ctx->Xb.p, Np, ctx->y.p, v + V_U * Np);
-    GPS_LAUNCH_CHECK();
-    trmv_lower_t_kernel<<<(unsigned)(Np / 32), 256, 0, ctx->stream>>>(ctx->Xb.p, Np, v + V_U * Np, v + V_ALPHA * Np);
-    GPS_LAUNCH_CHECK();
-    ctx->launches += 2;
-  }
+  GPS_CHECK(gps_alpha_from_linv(ctx, ctx->Xb.p, Np, ctx->y.p, ctx->vecs.p + V_U * Np, ctx->vecs.p + V_ALPHA * Np, nullptr));
   const double* dXs;
   GPS_CHECK(gps_stage_in(ctx, Xs, (size_t)T * D, ctx->stage[0], &dXs));
   const bool dev_out = gps_is_device_ptr(mean) && gps_is_device_ptr(var);
