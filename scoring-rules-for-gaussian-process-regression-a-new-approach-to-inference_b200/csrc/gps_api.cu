@@ -299,16 +299,21 @@ int gps_set_data(gps_ctx* ctx, const double* X, const double* y, int64_t N, int 
 static int full_eval_enqueue(gps_ctx* ctx, int score, bool want_grad, bool* stages_full) {
   const int64_t N = ctx->N, Np = ctx->Np;
   const int D = ctx->D;
-  GPS_CHECK(gps_factor_and_invert(ctx, score == GPS_NLML));
+  // objective only (crps / logs / nlml): alpha and diag K^-1 follow from L^-1 alone, the K^-1 = L^-T L^-1 stage is skipped
+  const bool want_kinv = want_grad || score == GPS_DSS;
+  GPS_CHECK(gps_factor_and_invert(ctx, score == GPS_NLML, want_kinv));
   double* v = ctx->vecs.p;
   double* par = ctx->params.p;
   *stages_full = false;
   ctx->stage_valid = false;
+  if (!want_kinv)
+    GPS_CHECK(gps_alpha_from_linv(ctx, ctx->Xb.p, Np, ctx->y.p, v + V_U * Np, v + V_ALPHA * Np,
+                                  score == GPS_NLML ? nullptr : v + V_D * Np));
   if (score == GPS_DSS) {
     ctx->loo_valid = false;
     GPS_CHECK(gps_full_dss(ctx, par + PAR_OBJ, par + PAR_GSUM, want_grad));
   } else if (score != GPS_NLML) {
-    GPS_CHECK(gps_diag_extract(ctx, ctx->Kb.p, Np, v + V_D * Np, 0));
+    if (want_kinv) GPS_CHECK(gps_diag_extract(ctx, ctx->Kb.p, Np, v + V_D * Np, 0));
     GPS_CHECK(gps_loo_score(ctx, score, N, Np, N, v + V_ALPHA * Np, v + V_D * Np, ctx->y.p, v + V_ABAR * Np,
                             v + V_DBAR * Np, v + V_LOOM * Np, v + V_LOOV * Np, par + PAR_OBJ));
     ctx->loo_valid = true;
