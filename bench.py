@@ -319,17 +319,23 @@ def run_ours(args):
     ctx.set_data(Xd, yd)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
-    def timed(fn, reps, warm=1):
-        """device time per call of fn (ms), events on the library's stream, max over ranks"""
+    def timed(fn, reps, warm=1, batches=1):
+        """device time per call of fn (ms), events on the library's stream, max over ranks; batches > 1: the best of
+        that many back-to-back batches of `reps` calls (the sub-millisecond calls are host-latency-bound and a batch of
+        a few milliseconds is easily disturbed by the host)"""
         for _ in range(warm):
             fn()
-        barrier()
-        e0.record(stream)
-        for _ in range(reps):
-            out = fn()
-        e1.record(stream)
-        barrier()
-        return max_over_ranks(e0.elapsed_time(e1)) / reps, out
+        best = None
+        for _ in range(batches):
+            barrier()
+            e0.record(stream)
+            for _ in range(reps):
+                out = fn()
+            e1.record(stream)
+            barrier()
+            t = max_over_ranks(e0.elapsed_time(e1)) / reps
+            best = t if best is None else min(best, t)
+        return best, out
 
     # ---- device-resident timing ------------------------------------------------------------------
     clocks = ClockSampler(local)
@@ -450,7 +456,7 @@ def run_ours(args):
     U = synth.inducing_init(M_FITC)
     steps_f = max(args.steps * 20, 100)
     lf0 = ctx.launch_count()
-    ms_f, (fv, fg, fgu) = timed(lambda: ctx.fitc_eval(theta, U, "crps"), steps_f, warm=5)
+    ms_f, (fv, fg, fgu) = timed(lambda: ctx.fitc_eval(theta, U, "crps"), steps_f, warm=5, batches=3)
     lf1 = ctx.launch_count()
     # the scripts' optimiser loop (K20:219-251) with theta and U resident on the device: `iters` evaluations +
     # updates inside one call, no host round trip in between
@@ -469,7 +475,8 @@ def run_ours(args):
     barrier()
     fitc = {"workload": "KIN40K-FITC-20 N=10000 D=8 M=20 LOO-CRPS obj+grad incl. inducing inputs (K20:222-251)",
             "replicas_evals_per_s": world * steps_f / (ms_f * steps_f * 1e-3), "ms_per_eval": ms_f,
-            "launches_per_eval": (lf1 - lf0) / (steps_f + 5),
+            "timing": "best of 3 back-to-back batches of %d calls (CUDA events on the library stream around each batch)" % steps_f,
+            "launches_per_eval": (lf1 - lf0) / (3 * steps_f + 5),
             "descend": {"iters": iters_d, "ms_per_iter": ms_desc / iters_d, "evals_per_s": 1e3 * iters_d / ms_desc,
                         "what": "gps_fitc_descend: evaluation + update of theta and the inducing inputs, device-resident "
                                 "(K20:243-251 with the two learning rates of K20:326-327), per iteration"},
@@ -494,10 +501,8 @@ def run_ours(args):
     blk_res = {}
     for m_b, U_b in ((20, U), (64, U64)):           # all timings first: the oracle's BLAS threads disturb host-bound calls
         for kind in ("dss", "kc"):
-            runs_k = [timed(lambda: ctx.fitc_eval(theta, U_b, kind), 10, warm=2) for _ in range(3)]
-            blk_res[m_b, kind] = runs_k[0][1]
-            blk["M%d_%s_ms_per_eval" % (m_b, kind)] = min(r[0] for r in runs_k)   # best of 3 batches of 10: these calls
-            # are host-latency-bound (several stream synchronisations each) and a 2 ms batch is easily disturbed
+            ms_k, blk_res[m_b, kind] = timed(lambda: ctx.fitc_eval(theta, U_b, kind), 10, warm=2, batches=3)
+            blk["M%d_%s_ms_per_eval" % (m_b, kind)] = ms_k
     if rank == 0:
         from oracle import woodbury as WB
         for m_b, U_b in ((20, U), (64, U64)):
@@ -515,7 +520,7 @@ def run_ours(args):
         cs.set_stream(stream)
         cs.comm_init()
         cs.set_data(Xd[lo:hi].contiguous(), yd[lo:hi].contiguous())
-        ms_s, (sv, sg, sgu) = timed(lambda: cs.fitc_eval_sharded(th0, U, "crps", N_FULL), steps_f, warm=5)
+        ms_s, (sv, sg, sgu) = timed(lambda: cs.fitc_eval_sharded(th0, U, "crps", N_FULL), steps_f, warm=5, batches=3)
         p2p = cs.comm_transport(True)
         ms_sd, _ = timed(lambda: cs.fitc_descend_sharded(th0, U, "crps", N_FULL, 1e-3, 1e-3, iters_d), 3, warm=1)
         fitc["row_sharded_evals_per_s"] = 1e3 / ms_s
@@ -533,7 +538,7 @@ def run_ours(args):
                     world=world)
         # the block objectives row-sharded: folds are quarters of the global row order and straddle the ranks' blocks
         for kind in ("dss", "kc"):
-            ms_ks, (sv, sg, sgu) = timed(lambda: cs.fitc_eval_sharded(th0, U64, kind, N_FULL), 5, warm=2)
+            ms_ks, (sv, sg, sgu) = timed(lambda: cs.fitc_eval_sharded(th0, U64, kind, N_FULL), 5, warm=2, batches=3)
             v1, g1, gu1 = ctx.fitc_eval(th0, U64, kind)
             blk["M64_%s_row_sharded_ms_per_eval" % kind] = ms_ks
             gates.check("fitc64_N10000_%s_sharded_vs_single" % kind,
@@ -554,7 +559,7 @@ def run_ours(args):
         cb.comm_init()
         run_big = lambda Uq: cb.fitc_eval_sharded(th0, Uq, "crps", N_BIG)
     steps_b = max(args.steps * 4, 20)
-    ms_b, (bv, bg, bgu) = timed(lambda: run_big(U), steps_b, warm=3)
+    ms_b, (bv, bg, bgu) = timed(lambda: run_big(U), steps_b, warm=3, batches=3)
     if world == 1:
         ms_bd, _ = timed(lambda: cb.fitc_descend(th0, U, "crps", 1e-4, 1e-4, 100), 2, warm=1)
     else:
