@@ -1786,12 +1786,12 @@ static int fitc_begin_impl(gps_ctx* ctx, const double* theta, const double* U, i
   if (ctx->N == 0) return gps_fail(ctx, GPS_ESTATE, "fitc: call gps_set_data first");
   if (!theta || !U || score < GPS_CRPS || score > GPS_KC) return gps_fail(ctx, GPS_EINVAL, "fitc: bad arguments");
   if (staged && (score == GPS_DSS || score == GPS_KC))
-    return gps_fail(ctx, GPS_EINVAL, "fitc: the staged (row-sharded) protocol implements crps / logs / nlml only; "
-                                     "dss and kc run through gps_fitc_eval on one GPU");
+    return gps_fail(ctx, GPS_EINVAL, "fitc: the staged (caller-side all-reduce) protocol implements crps / logs / nlml only; "
+                                     "dss and kc run through gps_fitc_eval on one GPU and gps_fitc_eval_sharded on several");
   if (M > 32) return gps_fitc_large_begin(ctx, theta, U, M, jitter, score, world_n);   // matrix form, same protocol
   const bool block_obj = score == GPS_DSS || score == GPS_KC;
   if (block_obj && ((world_n > 0 ? world_n : ctx->N) % 4 || world_n > ctx->N))
-    return gps_fail(ctx, GPS_EINVAL, "fitc dss/kc: needs N %% 4 == 0 (K20:541-543) and runs on one GPU in this version");
+    return gps_fail(ctx, GPS_EINVAL, "fitc dss/kc: needs N %% 4 == 0 (K20:541-543); the row kernels run on one GPU (gps_fitc_eval_sharded shards them)");
   if (block_obj && ctx->fitc_variant == 0)
     return gps_fail(ctx, GPS_EINVAL, "fitc dss/kc: only the tile formulation of the row passes implements them");
   if (M <= 0 || M > 32)
