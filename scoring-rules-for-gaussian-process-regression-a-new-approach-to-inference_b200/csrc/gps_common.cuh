@@ -17,9 +17,14 @@ struct GemmTask {  // one 128 x 128 output tile of a tile-GEMM launch
   int32_t b_row;   // same for B
   int32_t k0, k1;  // contraction range in elements, multiples of 16
   int32_t c_row, c_col;
-  int32_t flags;
+  int32_t flags;   // GEMM_TRI_END / GEMM_TRI_BEGIN: the k-range ends / begins with a diagonal 128-block of a triangular A
   int32_t pad;
 };
+// A strip of rows [h, h + TM) of the tile then only needs k < k1 - 128 + h + TM (lower-triangular block last: the rest
+// of the strip's rows in that block are explicit zeros) resp. k >= k0 + h (block of a transposed lower factor first).
+// The skipped products are exact zeros, so results are bit-identical; it matters where a task has few k-tiles
+// (matrix-form FITC with 1-8 tile rows).
+enum { GEMM_TRI_END = 1, GEMM_TRI_BEGIN = 2 };
 
 struct DevBuf {
   double* p = nullptr;

@@ -704,10 +704,10 @@ col_predict_kernel(const double* __restrict__ Vs, const double* __restrict__ Ws,
 
 inline unsigned blocks_for(int64_t n, int t = 256) { return (unsigned)((n + t - 1) / t); }
 
-GemmTask make_task(int a_row, int b_row, int k0, int k1, int c_row, int c_col) {
+GemmTask make_task(int a_row, int b_row, int k0, int k1, int c_row, int c_col, int flags = 0) {
   GemmTask t;
   t.a_row = a_row; t.b_row = b_row; t.k0 = k0; t.k1 = k1; t.c_row = c_row; t.c_col = c_col;
-  t.flags = 0; t.pad = 0;
+  t.flags = flags; t.pad = 0;
   return t;
 }
 
@@ -723,12 +723,14 @@ int build_tasks(gps_ctx* ctx, gps_fitc_large* fl) {
   begin(fl->t_low);
   for (int64_t j = 0; j < nt; ++j)
     for (int i = 0; i < mt; ++i)
-      h.push_back(make_task(i * GPS_TILE, (int)(j * GPS_TILE), 0, (i + 1) * GPS_TILE, i * GPS_TILE, (int)(j * GPS_TILE)));
+      h.push_back(make_task(i * GPS_TILE, (int)(j * GPS_TILE), 0, (i + 1) * GPS_TILE, i * GPS_TILE, (int)(j * GPS_TILE),
+                            GEMM_TRI_END));     // A = a lower-triangular factor inverse: row strips stop at their diagonal
   end(fl->t_low);
   begin(fl->t_up);
   for (int64_t j = 0; j < nt; ++j)
     for (int i = 0; i < mt; ++i)
-      h.push_back(make_task(i * GPS_TILE, (int)(j * GPS_TILE), i * GPS_TILE, Mp, i * GPS_TILE, (int)(j * GPS_TILE)));
+      h.push_back(make_task(i * GPS_TILE, (int)(j * GPS_TILE), i * GPS_TILE, Mp, i * GPS_TILE, (int)(j * GPS_TILE),
+                            GEMM_TRI_BEGIN));   // A' with A lower-triangular: row strips start at their diagonal
   end(fl->t_up);
   begin(fl->t_full);
   for (int64_t j = 0; j < nt; ++j)
@@ -1474,7 +1476,8 @@ int gps_fitc_large_predict(gps_ctx* ctx, const double* dXs, int64_t T, double* d
     std::vector<GemmTask> tasks;
     for (int64_t j = 0; j < tp / GPS_TILE; ++j)
       for (int i = 0; i < mt; ++i)
-        tasks.push_back(make_task(i * GPS_TILE, (int)(j * GPS_TILE), 0, (i + 1) * GPS_TILE, i * GPS_TILE, (int)(j * GPS_TILE)));
+        tasks.push_back(make_task(i * GPS_TILE, (int)(j * GPS_TILE), 0, (i + 1) * GPS_TILE, i * GPS_TILE, (int)(j * GPS_TILE),
+                                  GEMM_TRI_END));
     GPS_CHECK(gps_upload_tasks2(ctx, tasks));
     GPS_CUDA(cudaMemsetAsync(fl->T1.p, 0, (size_t)Mp * tp * sizeof(double), ctx->stream));
     GPS_CHECK(gps_gram_rect(ctx, fl->U.p, M, dXs + t0 * D, tc, D, par, fl->T1.p, tp));

@@ -107,6 +107,8 @@ gemm_tile_kernel(const double* __restrict__ A, int64_t lda, const double* __rest
   const int half = (int)(blockIdx.x % Cfg::SPLIT) * TM;
   t.a_row += half;
   t.c_row += half;
+  if (t.flags & GEMM_TRI_END) t.k1 -= 128 - half - TM;
+  if (t.flags & GEMM_TRI_BEGIN) t.k0 += half;
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
   const int wm = warp / Cfg::WN, wn = warp % Cfg::WN;
@@ -299,6 +301,8 @@ gemm_tma_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   const int half = (int)(blockIdx.x & 1) * TM;
   t.a_row += half;
   t.c_row += half;
+  if (t.flags & GEMM_TRI_END) t.k1 -= 128 - half - TM;
+  if (t.flags & GEMM_TRI_BEGIN) t.k0 += half;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int wm = warp >> 1, wn = warp & 1, g = lane >> 2, tq = lane & 3;
   const int nk = (t.k1 - t.k0) / BK;
