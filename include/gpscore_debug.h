@@ -39,7 +39,8 @@ int gps_dbg_fp64_peak(gps_ctx* ctx, int iters, double* dmma_tflops, double* dfma
  * stream, one at a time (used to time launches alone); what = 6 arms the lane timeline (gps_dbg_trace);
  * what = 7 sets the row-strip height of the few-tile launches on POTRF's serial chain (16 = default, 32, 0 = the
  * normal policy); what = 8 switches the automatic strip policies for under-filled launches off (0) or on (1); what = 9 sets the share (per cent)
- * of a large TRTRI node's tiles that goes to its left child (50 = halving). */
+ * of a large TRTRI node's tiles that goes to its left child (50 = halving); what = 10 sets the row-strip height of the TRTRI
+ * merges issued behind POTRF (0 = the normal policy, default; 32 / 16 measured slower). */
 int gps_dbg_set_variant(gps_ctx* ctx, int what, int value);
 
 /* Timeline of the factorisation lanes of the last full-GP evaluation (arm with gps_dbg_set_variant(ctx, 6, 1)):

@@ -734,6 +734,7 @@ int potrf_lanes(gps_ctx* ctx, double* K, double* Xinv, double* scratch, int64_t 
     ctx->stream = s_tri;
     GPS_CUDA(cudaStreamWaitEvent(s_tri, ctx->potrf_events[2 * o + 1], 0));
     GPS_CUDA(cudaStreamWaitEvent(s_tri, ctx->below_events[o], 0));
+    ctx->gemm_strip_policy = ctx->tri_strip;
     while (next_tri < ctx->trtri_sched.size() && ctx->trtri_sched[next_tri].step == o && rc == GPS_OK) {
       const auto& tl = ctx->trtri_sched[next_tri++];
       if (tl.phase == 0)   // P = L21 * X11
@@ -743,6 +744,7 @@ int potrf_lanes(gps_ctx* ctx, double* K, double* Xinv, double* scratch, int64_t 
         rc = gps_gemm_tasks(ctx, GEMM_KC_MC, Xinv, Np, scratch, Np, Xinv, Np, -1.0, 0.0, nullptr, false,
                             ctx->d_tasks + tl.r.off, tl.r.cnt);
     }
+    ctx->gemm_strip_policy = 0;
     if (rc == GPS_OK) rc = trace_mark(ctx, 4000 + o, s_tri);
   }
   return rc;
