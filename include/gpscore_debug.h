@@ -40,7 +40,8 @@ int gps_dbg_fp64_peak(gps_ctx* ctx, int iters, double* dmma_tflops, double* dfma
  * what = 7 sets the row-strip height of the few-tile launches on POTRF's serial chain (16 = default, 32, 0 = the
  * normal policy); what = 8 switches the automatic strip policies for under-filled launches off (0) or on (1); what = 9 sets the share (per cent)
  * of a large TRTRI node's tiles that goes to its left child (50 = halving); what = 10 sets the row-strip height of the TRTRI
- * merges issued behind POTRF (0 = the normal policy, default; 32 / 16 measured slower). */
+ * merges issued behind POTRF (0 = the normal policy, default; 32 / 16 measured slower); what = 11 / 12 run the overlapped TRTRI
+ * merges / the POTRF trailing updates as persistent launches with that many CTAs (0 = off, default; measured slower). */
 int gps_dbg_set_variant(gps_ctx* ctx, int what, int value);
 
 /* Timeline of the factorisation lanes of the last full-GP evaluation (arm with gps_dbg_set_variant(ctx, 6, 1)):

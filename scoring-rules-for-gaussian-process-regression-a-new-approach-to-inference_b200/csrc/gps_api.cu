@@ -70,6 +70,7 @@ int gps_ensure_ws(gps_ctx* ctx, int64_t Np) {
 int gps_upload_tasks2(gps_ctx* ctx, const std::vector<GemmTask>& h) {
   if (h.size() > ctx->tasks2_cap) {
     if (ctx->d_tasks2) cudaFree(ctx->d_tasks2);
+  if (ctx->d_tickets) cudaFree(ctx->d_tickets);
     ctx->d_tasks2 = nullptr;
     GPS_CUDA(cudaMalloc(&ctx->d_tasks2, h.size() * sizeof(GemmTask)));
     ctx->tasks2_cap = h.size();
@@ -152,6 +153,7 @@ void gps_ctx_release(gps_ctx* ch) {
     if (b->p) cudaFree(b->p);
   if (ch->d_info) cudaFree(ch->d_info);
   if (ch->d_tasks) cudaFree(ch->d_tasks);
+  if (ch->d_tickets) cudaFree(ch->d_tickets);
   for (auto* v : {&ch->potrf_events, &ch->tile_events, &ch->below_events, &ch->trailA1_events})
     for (auto e : *v) cudaEventDestroy(e);
   for (cudaStream_t s : {ch->panel_stream, ch->panel2_stream, ch->trail_stream, ch->tri_stream})
@@ -220,6 +222,7 @@ void gps_destroy(gps_ctx* ctx) {
   if (ctx->d_info) cudaFree(ctx->d_info);
   if (ctx->d_tasks) cudaFree(ctx->d_tasks);
   if (ctx->d_tasks2) cudaFree(ctx->d_tasks2);
+  if (ctx->d_tickets) cudaFree(ctx->d_tickets);
   for (auto& pr : ctx->trace) cudaEventDestroy(pr.second);
   for (auto& pr : ctx->gemm_events) {
     cudaEventDestroy(pr.first);

@@ -653,7 +653,7 @@ struct LaneGuard {
   cudaStream_t s;
   int policy;
   explicit LaneGuard(gps_ctx* ctx) : c(ctx), s(ctx->stream), policy(ctx->gemm_strip_policy) {}
-  ~LaneGuard() { c->stream = s; c->gemm_strip_policy = policy; }
+  ~LaneGuard() { c->stream = s; c->gemm_strip_policy = policy; c->gemm_grid_cap = 0; }
 };
 
 int potrf_lanes(gps_ctx* ctx, double* K, double* Xinv, double* scratch, int64_t Np, bool with_trtri) {
@@ -724,10 +724,12 @@ int potrf_lanes(gps_ctx* ctx, double* K, double* Xinv, double* scratch, int64_t 
     if (rc != GPS_OK) break;
     GPS_CUDA(cudaEventRecord(ctx->potrf_events[2 * o + 2], s_trail));
     GPS_CHECK(trace_mark(ctx, 7000 + o, s_trail));
+    ctx->gemm_grid_cap = ctx->cap_trail;
     rc = gemm_nt(K, -1.0, 1.0, ctx->potrf_trailA1[o], 0, ctx->potrf_trailA1[o].cnt);
-    if (rc != GPS_OK) break;
+    if (rc != GPS_OK) { ctx->gemm_grid_cap = 0; break; }
     GPS_CUDA(cudaEventRecord(ctx->trailA1_events[o], s_trail));
-    rc = gemm_nt(K, -1.0, 1.0, ctx->potrf_trailB[o], 0, ctx->potrf_trailB[o].cnt);   // (gemm_equal_tasks here: no gain, the other lanes fill the tail)
+    rc = gemm_nt(K, -1.0, 1.0, ctx->potrf_trailB[o], 0, ctx->potrf_trailB[o].cnt);
+    ctx->gemm_grid_cap = 0;   // (gemm_equal_tasks here: no gain, the other lanes fill the tail)
     if (rc == GPS_OK) rc = trace_mark(ctx, 3000 + o, s_trail);
     if (rc != GPS_OK || !with_trtri) continue;
     // inversion merges whose operands are final after this step
@@ -735,6 +737,7 @@ int potrf_lanes(gps_ctx* ctx, double* K, double* Xinv, double* scratch, int64_t 
     GPS_CUDA(cudaStreamWaitEvent(s_tri, ctx->potrf_events[2 * o + 1], 0));
     GPS_CUDA(cudaStreamWaitEvent(s_tri, ctx->below_events[o], 0));
     ctx->gemm_strip_policy = ctx->tri_strip;
+    ctx->gemm_grid_cap = ctx->cap_trtri;
     while (next_tri < ctx->trtri_sched.size() && ctx->trtri_sched[next_tri].step == o && rc == GPS_OK) {
       const auto& tl = ctx->trtri_sched[next_tri++];
       if (tl.phase == 0)   // P = L21 * X11
@@ -745,6 +748,7 @@ int potrf_lanes(gps_ctx* ctx, double* K, double* Xinv, double* scratch, int64_t 
                             ctx->d_tasks + tl.r.off, tl.r.cnt);
     }
     ctx->gemm_strip_policy = 0;
+    ctx->gemm_grid_cap = 0;
     if (rc == GPS_OK) rc = trace_mark(ctx, 4000 + o, s_tri);
   }
   return rc;

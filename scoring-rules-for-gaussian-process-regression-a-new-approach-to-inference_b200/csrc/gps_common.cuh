@@ -106,6 +106,10 @@ struct gps_ctx {
   cudaStream_t tri_stream = nullptr;            // overlapped TRTRI (lowest priority)
   cudaEvent_t fork_ev = nullptr, join_trail_ev = nullptr, join_tri_ev = nullptr;
   int overlap_trtri = 1;                        // 0: POTRF then TRTRI back to back (A/B knob)
+  int gemm_grid_cap = 0;                        // > 0: TMA tile GEMMs larger than this many CTAs run persistent with that grid (slots left free for the chain)
+  int cap_trtri = 0, cap_trail = 0;             // A/B knobs 11 / 12: grid caps of the overlapped TRTRI merges / the POTRF trailing updates
+  int* d_tickets = nullptr;                     // dynamic-scheduling counters of the persistent launches (ring of 256)
+  unsigned ticket_seq = 0;
   int tri_strip = 0;                            // strip policy of the TRTRI merges issued behind POTRF (A/B knob 10; 0 = the normal policy)
   int trtri_split_pct = 50;                     // share of a large TRTRI node's tiles that goes to its left child (A/B knob 9)
   // debug timeline of the factorisation lanes (knob 6): (code, event) pairs, code = lane * 1000 + outer step

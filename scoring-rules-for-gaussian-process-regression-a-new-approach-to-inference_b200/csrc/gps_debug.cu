@@ -153,6 +153,8 @@ int gps_dbg_set_variant(gps_ctx* ctx, int what, int value) {
   else if (what == 7) ctx->chain_strip = value;
   else if (what == 8) ctx->gemm_auto_strip = value;
   else if (what == 10) ctx->tri_strip = value;
+  else if (what == 11) ctx->cap_trtri = value;
+  else if (what == 12) ctx->cap_trail = value;
   else if (what == 9) {
     if (value < 30 || value > 90) return gps_fail(ctx, GPS_EINVAL, "dbg_set_variant: split percentage outside 30..90");
     ctx->trtri_split_pct = value;

@@ -446,6 +446,122 @@ int tma_map(gps_ctx* ctx, const double* base, int64_t ld, int panel_rows, bool m
   return GPS_OK;
 }
 
+// Persistent variant of gemm_tma_kernel for launches that share the GPU with a latency-critical lane (the diagonal-block
+// chain of POTRF): the grid is capped below the number of resident CTA slots, every CTA takes 64 x 128 slices from a
+// ticket counter until the list is drained, so slots stay free for the chain's kernels at all times (a CTA of a deep
+// merge holds its slot for up to 0.7 ms; without free slots a chain launch of a few dozen CTAs waits for that many
+// to retire).  Same tile, same k-order per output element: bit-identical results.
+template <bool A_MC, bool B_MC>
+__global__ void __launch_bounds__(128, 2)
+gemm_tma_persist_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, double* __restrict__ C,
+                        int64_t ldc, double alpha, double beta, const GemmTask* __restrict__ tasks, int nslices,
+                        int* __restrict__ ticket) {
+  extern __shared__ unsigned char smem_raw[];
+  __shared__ unsigned long long full[TMA_STAGES];
+  __shared__ int next_slice;
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  constexpr int TM = 64, MF = 4, NF = 8, WROWS = 32, WCOLS = 64, BK = 16, S = TMA_STAGES;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int wm = warp >> 1, wn = warp & 1, g = lane >> 2, tq = lane & 3;
+  if (tid == 0) {
+#pragma unroll
+    for (int s = 0; s < S; ++s) mbar_init(&full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+  unsigned base = 0;                       // k-blocks this CTA has consumed so far: position and phase of the ring
+  int slice = blockIdx.x;
+  while (slice < nslices) {
+    GemmTask t = tasks[slice >> 1];
+    const int half = (slice & 1) * TM;
+    t.a_row += half;
+    t.c_row += half;
+    if (t.flags & GEMM_TRI_END) t.k1 -= 128 - half - TM;
+    if (t.flags & GEMM_TRI_BEGIN) t.k0 += half;
+    const int nk = (t.k1 - t.k0) / BK;
+    auto issue = [&](int kb) {
+      const unsigned q = base + kb;
+      unsigned char* sl = smem + (size_t)(q % S) * TMA_STAGE_BYTES;
+      const int k = t.k0 + kb * BK;
+      mbar_expect_tx(&full[q % S], TMA_STAGE_BYTES);
+      if (A_MC) tma_load_2d(sl, &tmA, &full[q % S], t.a_row, k);
+      else tma_load_2d(sl, &tmA, &full[q % S], k, t.a_row);
+      if (B_MC) tma_load_2d(sl + TMA_A_BYTES, &tmB, &full[q % S], t.b_row, k);
+      else tma_load_2d(sl + TMA_A_BYTES, &tmB, &full[q % S], k, t.b_row);
+    };
+    if (tid == 0)
+      for (int s = 0; s < S - 1 && s < nk; ++s) issue(s);
+    double acc[MF][NF][2];
+#pragma unroll
+    for (int i = 0; i < MF; ++i)
+#pragma unroll
+      for (int j = 0; j < NF; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int kb = 0; kb < nk; ++kb) {
+      const unsigned q = base + kb;
+      mbar_wait(&full[q % S], (q / S) & 1);
+      __syncthreads();                     // everyone is done with the slot the next load overwrites
+      if (tid == 0 && kb + S - 1 < nk) issue(kb + S - 1);
+      const unsigned char* As = smem + (size_t)(q % S) * TMA_STAGE_BYTES;
+      const unsigned char* Bs = As + TMA_A_BYTES;
+#pragma unroll
+      for (int kk = 0; kk < BK / 4; ++kk) {
+        const int k = kk * 4 + tq;
+        double a[MF], b[NF];
+#pragma unroll
+        for (int i = 0; i < MF; ++i) a[i] = tma_frag<TM, A_MC>(As, wm * WROWS + i * 8 + g, k);
+#pragma unroll
+        for (int j = 0; j < NF; ++j) b[j] = tma_frag<128, B_MC>(Bs, wn * WCOLS + j * 8 + g, k);
+#pragma unroll
+        for (int i = 0; i < MF; ++i)
+#pragma unroll
+          for (int j = 0; j < NF; ++j) dmma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < MF; ++i) {
+      const int row = t.c_row + wm * WROWS + i * 8 + g;
+#pragma unroll
+      for (int j = 0; j < NF; ++j) {
+        const int col = t.c_col + wn * WCOLS + j * 8 + 2 * tq;
+        double2* p = reinterpret_cast<double2*>(C + (int64_t)row * ldc + col);
+        double2 v;
+        v.x = alpha * acc[i][j][0];
+        v.y = alpha * acc[i][j][1];
+        if (beta != 0.0) {
+          const double2 o = *p;
+          v.x += beta * o.x;
+          v.y += beta * o.y;
+        }
+        *p = v;
+      }
+    }
+    base += (unsigned)nk;
+    if (tid == 0) next_slice = (int)gridDim.x + atomicAdd(ticket, 1);
+    __syncthreads();                       // the ring is free for the next slice's first loads; next_slice is visible
+    slice = next_slice;
+  }
+}
+
+template <bool A_MC, bool B_MC>
+int launch_tma_persist(gps_ctx* ctx, const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc,
+                       double alpha, double beta, const GemmTask* tasks, size_t ntasks) {
+  CUtensorMap ma, mb;
+  GPS_CHECK(tma_map(ctx, A, lda, 64, A_MC, &ma));
+  GPS_CHECK(tma_map(ctx, B, ldb, 128, B_MC, &mb));
+  auto kern = gemm_tma_persist_kernel<A_MC, B_MC>;
+  GPS_ONCE_PER_DEVICE(ctx);
+  if (!configured) {
+    GPS_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TMA_SMEM));
+    configured = true;
+  }
+  if (!ctx->d_tickets) GPS_CUDA(cudaMalloc(&ctx->d_tickets, 256 * sizeof(int)));
+  int* ticket = ctx->d_tickets + (ctx->ticket_seq++ & 255u);
+  GPS_CUDA(cudaMemsetAsync(ticket, 0, sizeof(int), ctx->stream));
+  kern<<<(unsigned)ctx->gemm_grid_cap, 128, TMA_SMEM, ctx->stream>>>(ma, mb, C, ldc, alpha, beta, tasks, (int)(ntasks * 2), ticket);
+  GPS_LAUNCH_CHECK();
+  return GPS_OK;
+}
+
 template <bool A_MC, bool B_MC, bool MIRROR>
 int launch_tma_k(gps_ctx* ctx, const double* A, int64_t lda, const double* B, int64_t ldb, double* C, int64_t ldc, double alpha,
                  double beta, const GemmTask* tasks, size_t ntasks) {
@@ -465,6 +581,10 @@ int launch_tma_k(gps_ctx* ctx, const double* A, int64_t lda, const double* B, in
 
 int launch_tma(gps_ctx* ctx, int kind, bool mirror, const double* A, int64_t lda, const double* B, int64_t ldb, double* C,
                int64_t ldc, double alpha, double beta, const GemmTask* tasks, size_t ntasks) {
+  if (ctx->gemm_grid_cap > 0 && ntasks * 2 > (size_t)ctx->gemm_grid_cap && ctx->gemm_variant == 9) {
+    if (kind == GEMM_KC_KC) return launch_tma_persist<false, false>(ctx, A, lda, B, ldb, C, ldc, alpha, beta, tasks, ntasks);
+    if (kind == GEMM_KC_MC) return launch_tma_persist<false, true>(ctx, A, lda, B, ldb, C, ldc, alpha, beta, tasks, ntasks);
+  }
   if (kind == GEMM_KC_KC) return launch_tma_k<false, false, false>(ctx, A, lda, B, ldb, C, ldc, alpha, beta, tasks, ntasks);
   if (kind == GEMM_KC_MC) return launch_tma_k<false, true, false>(ctx, A, lda, B, ldb, C, ldc, alpha, beta, tasks, ntasks);
   if (mirror) return launch_tma_k<true, true, true>(ctx, A, lda, B, ldb, C, ldc, alpha, beta, tasks, ntasks);
