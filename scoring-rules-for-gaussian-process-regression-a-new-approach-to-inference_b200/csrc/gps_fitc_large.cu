@@ -50,6 +50,7 @@ struct gps_fitc_large {
   gps_ctx::Range t_fold[4];
   int fold_S[4] = {0, 0, 0, 0};
   int64_t fold_key[10] = {-1, -1, -1, -1, -1, -1, -1, -1, -1, -1};
+  int* latch = nullptr;       // device: [which matrix, pivot] of the first failed factorisation of the evaluation
   DevBuf fb;                  // block objectives: per-fold accumulators and replicated M x M matrices
   int64_t row_off = 0;        // first global row of this context's block (row-sharded block objectives)
   gps_allreduce_fn allreduce = nullptr;   // set for the duration of a row-sharded evaluation
@@ -876,25 +877,35 @@ int splitk(gps_ctx* ctx, gps_fitc_large* fl, const double* A, const double* B, c
   return GPS_OK;
 }
 
-// factor the matrix in ch->Kb: L -> Lout, L^-1 -> Linv (both with an explicit zero upper triangle)
-int factor(gps_ctx* ctx, gps_fitc_large* fl, double* Lout, double* Linv, const char* what) {
+// first failed factorisation of an evaluation: latch[0] = which matrix (1 K_uu + jitter I, 2 I + V Lambda^-1 V',
+// 3 + f = H_f of fold f), latch[1] = the failing pivot
+__global__ void latch_info_kernel(const int* __restrict__ info, int* __restrict__ latch, int code) {
+  if (*info != 0 && latch[0] == 0) {
+    latch[0] = code;
+    latch[1] = *info;
+  }
+}
+
+// factor the matrix in ch->Kb: L -> Lout, L^-1 -> Linv (both with an explicit zero upper triangle).  Nothing is read
+// back here: a failed pivot (the diagonal kernel substitutes 1 and carries on, so everything downstream stays finite
+// or NaN but never hangs) is latched on the device and reported by gps_fitc_large_finish with the result read-back —
+// no host synchronisation inside an evaluation, and in row-sharded runs every rank reaches every all-reduce.
+int factor(gps_ctx* ctx, gps_fitc_large* fl, double* Lout, double* Linv, int code) {
   gps_ctx* ch = fl->ch;
   const int Mp = fl->Mp;
   GPS_CUDA(cudaMemsetAsync(ch->d_info, 0, sizeof(int), ctx->stream));
   int r = gps_potrf(ch, ch->Kb.p, ch->Xb.p, Mp);
   if (r == GPS_OK) r = gps_trtri(ch, ch->Kb.p, ch->Xb.p, ch->Sb.p, Mp);
-  if (r != GPS_OK) return gps_fail(ctx, r, "fitc %s: %s", what, ch->err.c_str());
+  if (r != GPS_OK) return gps_fail(ctx, r, "fitc factorisation %d: %s", code, ch->err.c_str());
   const unsigned nb = blocks_for((int64_t)Mp * Mp);
   tri_copy_kernel<<<nb, 256, 0, ctx->stream>>>(ch->Kb.p, Lout, Mp);
   GPS_LAUNCH_CHECK();
   tri_copy_kernel<<<nb, 256, 0, ctx->stream>>>(ch->Xb.p, Linv, Mp);
   GPS_LAUNCH_CHECK();
-  ctx->launches += 2 + ch->launches;
+  latch_info_kernel<<<1, 1, 0, ctx->stream>>>(ch->d_info, fl->latch, code);
+  GPS_LAUNCH_CHECK();
+  ctx->launches += 3 + ch->launches;
   ch->launches = 0;
-  int info = 0;
-  GPS_CUDA(cudaMemcpyAsync(&info, ch->d_info, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
-  GPS_CUDA(cudaStreamSynchronize(ctx->stream));
-  if (info != 0) return gps_fail(ctx, GPS_ENOTPD, "fitc: %s not positive definite at pivot %d", what, info);
   return GPS_OK;
 }
 
@@ -1105,7 +1116,7 @@ int block_pass2(gps_ctx* ctx, double* acc2, bool want_grad) {
     double *Pf = A4 + fo * AF, *g = Pf + MM, *Hinv = HI + fo * MM, *h = HV + fo * (size_t)Mp;
     h_from_p_kernel<<<nbm, 256, 0, st>>>(Pf, Mp, ch->Kb.p);
     GPS_LAUNCH_CHECK();
-    GPS_CHECK(factor(ctx, fl, LH, LHi, "I - W_f Lambda_f^-1 W_f' (fold)"));
+    GPS_CHECK(factor(ctx, fl, LH, LHi, 3 + fo));
     GPS_CHECK(mm_gemm(ctx, fl, GEMM_MC_MC, LHi, LHi, Hinv, 1.0));              // H^-1 = L_H^-T L_H^-1
     matvec_t_kernel<<<Mp / 16, 256, 0, st>>>(Hinv, Mp, g, h);                      // h = H^-1 g (H^-1 symmetric)
     GPS_LAUNCH_CHECK();
@@ -1200,6 +1211,7 @@ void gps_fitc_large_free(gps_ctx* ctx) {
     if (b->p) cudaFree(b->p);
   if (fl->tasks) cudaFree(fl->tasks);
   if (fl->ftasks) cudaFree(fl->ftasks);
+  if (fl->latch) cudaFree(fl->latch);
   if (fl->ch) gps_ctx_release(fl->ch);
   delete fl;
   ctx->fl = nullptr;
@@ -1240,6 +1252,8 @@ int gps_fitc_large_begin(gps_ctx* ctx, const double* theta, const double* U, int
   fl->ready = false;
   fl->allreduce = nullptr;
   fl->row_off = 0;
+  if (!fl->latch) GPS_CUDA(cudaMalloc(&fl->latch, 2 * sizeof(int)));
+  GPS_CUDA(cudaMemsetAsync(fl->latch, 0, 2 * sizeof(int), ctx->stream));
   gps_ctx* ch = fl->ch;
   const int D = ctx->D, Mp = fl->Mp;
   const size_t MM = (size_t)Mp * Mp;
@@ -1257,7 +1271,7 @@ int gps_fitc_large_begin(gps_ctx* ctx, const double* theta, const double* U, int
   kuu_fix_kernel<<<blocks_for((int64_t)MM), 256, 0, st>>>(ch->Kb.p, Mp, M, jitter, sm + SM_KUU * MM);
   GPS_LAUNCH_CHECK();
   ctx->launches++;
-  GPS_CHECK(factor(ctx, fl, sm + SM_LA * MM, sm + SM_LAI * MM, "K_uu + jitter I"));
+  GPS_CHECK(factor(ctx, fl, sm + SM_LA * MM, sm + SM_LAI * MM, 1));
   f.begun = true;
   return GPS_OK;
 }
@@ -1299,7 +1313,7 @@ int gps_fitc_large_pass2(gps_ctx* ctx, const double* acc1, double* acc2, bool wa
   add_identity_kernel<<<blocks_for((int64_t)MM), 256, 0, st>>>(acc1, Mp, ch->Kb.p);
   GPS_LAUNCH_CHECK();
   ctx->launches++;
-  GPS_CHECK(factor(ctx, fl, sm + SM_LC * MM, sm + SM_LCI * MM, "I + V Lambda^-1 V'"));
+  GPS_CHECK(factor(ctx, fl, sm + SM_LC * MM, sm + SM_LCI * MM, 2));
   GPS_CHECK(rowdot(ctx, fl, sm + SM_LCI * MM, Mp, Mp, Mp, acc1 + MM, mv + MV_BETA * Mp));
   GPS_CHECK(big_gemm(ctx, fl, GEMM_KC_MC, fl->t_low, sm + SM_LCI * MM, fl->V.p, fl->W.p));
   col_w_kernel<<<nbn, 256, 0, st>>>(fl->W.p, Npp, M, N, Npp, mv + MV_BETA * Mp, ctx->y.p, rv + RV_IL * Npp,
@@ -1395,7 +1409,15 @@ int gps_fitc_large_finish(gps_ctx* ctx, const double* acc2, const double* acc3, 
     GPS_CUDA(cudaMemcpyAsync(&h[OUT_G1], acc3 + MM, (glen + 1) * sizeof(double), cudaMemcpyDeviceToHost, st));
     GPS_CUDA(cudaMemcpyAsync(&h[OUT_G1 + glen + 1], d_out + OUT_G1 + glen, glen * sizeof(double), cudaMemcpyDeviceToHost, st));
   }
+  int latch[2] = {0, 0};
+  GPS_CUDA(cudaMemcpyAsync(latch, fl->latch, sizeof latch, cudaMemcpyDeviceToHost, st));
   GPS_CUDA(cudaStreamSynchronize(st));
+  if (latch[0] != 0) {
+    fl->ready = false;                      // no prediction / LOO read-back from a failed evaluation
+    f.loo_ok = false;
+    static const char* const what[3] = {"K_uu + jitter I", "I + V Lambda^-1 V'", "I - W_f Lambda_f^-1 W_f' (a fold of the block objective)"};
+    return gps_fail(ctx, GPS_ENOTPD, "fitc: %s not positive definite at pivot %d", what[latch[0] > 3 ? 2 : latch[0] - 1], latch[1]);
+  }
   double value = h[OUT_OBJ];
   if (f.score == GPS_NLML) value += (double)f.world_n * HALF_LOG_2PI + h[OUT_LOGDET];   // replicated terms, added once
   if (obj) *obj = value;

@@ -66,7 +66,7 @@ def test_argument_errors_are_reported(ctx):
     ctx.set_data(_dev(X), _dev(y))
     with pytest.raises(L.GpsError):                       # no accumulator layout beyond the matrix form
         ctx.fitc_acc_len(4097)
-    with pytest.raises(L.GpsError):                       # block objectives stop at M = 32 too
+    with pytest.raises(L.GpsError):                       # the block objectives' four folds need 4 | N (here N = 50)
         ctx.fitc_eval(np.zeros(4), np.random.default_rng(1).standard_normal((33, 2)), "kc")
     with pytest.raises(L.GpsError):                       # M beyond the matrix form
         ctx.fitc_eval(np.zeros(4), np.zeros((4097, 2)), "crps")

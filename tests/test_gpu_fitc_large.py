@@ -338,3 +338,31 @@ def test_large_m_rows_grow_inside_one_padded_shape(ctx):
                 oval, og, ogU = Wd.fitc_obj_grad(X[:n], y[:n], U, theta, O.SCORES[kind])[:3]
             assert abs(val - oval) <= OBJ_TOL * abs(oval)
             assert relerr(grad, og) <= GRAD_TOL and relerr(gU, ogU) <= GRAD_TOL
+
+
+@pytest.mark.parametrize("kind", ["crps", "dss"])
+def test_large_m_failed_factorisation_is_reported_and_recoverable(ctx, kind):
+    """No host synchronisation inside a matrix-form evaluation: a failed pivot is latched on the device and raised with
+    the result read-back; the context is usable afterwards and refuses to predict from the failed evaluation."""
+    from gpscore_b200 import lib as L
+    from oracle import woodbury as Wd
+    from oracle import gp_oracle as O
+    rng = np.random.default_rng(91)
+    X = rng.uniform(-1, 1, (800, 4))
+    y = np.sin(X @ rng.standard_normal(4)) + 0.1 * rng.standard_normal(800)
+    U = rng.uniform(-1, 1, (40, 4))
+    theta = np.concatenate([[0.1], np.zeros(4), [-2.0]])
+    ctx.set_data(_dev(X), _dev(y))
+    with pytest.raises(L.GpsError) as ei:
+        ctx.fitc_eval(theta, U, kind, jitter=-2.0)          # K_uu - 2 I is indefinite
+    assert ei.value.code == L.GPS_ENOTPD and "K_uu" in str(ei.value)
+    xs, mo, vo = _dev(X[:4]), _dev(np.zeros(4)), _dev(np.zeros(4))
+    with pytest.raises(L.GpsError):
+        ctx._check(ctx._lib.gps_fitc_predict(ctx._h, xs.data_ptr(), 4, mo.data_ptr(), vo.data_ptr()))
+    val, grad, gU = ctx.fitc_eval(theta, U, kind)
+    if kind == "dss":
+        oval, og, ogU = Wd.fitc_block_obj_grad(X, y, U, theta, kind)
+    else:
+        oval, og, ogU = Wd.fitc_obj_grad(X, y, U, theta, O.SCORES[kind])[:3]
+    assert abs(val - oval) <= OBJ_TOL * abs(oval)
+    assert relerr(grad, og) <= GRAD_TOL and relerr(gU, ogU) <= GRAD_TOL
