@@ -278,7 +278,9 @@ class Context:
         library over its NCCL communicator (`comm_init`), nothing synchronises the host between the
         passes.  A callable (`allreduce(tensor)` sums a 1-D float64 device tensor in place across
         ranks) selects the staged protocol of include/gpscore.h instead, for callers that bring their
-        own collective."""
+        own collective.  The block objectives "dss" / "kc" (world_n % 4 == 0) shard through
+        the library communicator only (allreduce=None); the ranks must hold consecutive row blocks in rank
+        order (`dist.row_block`), because the four folds are quarters of the global row order."""
         self._enter()
         th = self._theta(theta)
         Uh = _host_vec(U)
