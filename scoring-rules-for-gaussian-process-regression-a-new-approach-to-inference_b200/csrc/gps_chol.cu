@@ -378,23 +378,23 @@ struct Node { int lo, mid, hi, depth; };
 // Large nodes are therefore split off-centre (pct % of the tiles to the left, rounded to the POTRF outer block so the
 // early P phase is released at an outer-step boundary): the late X phase shrinks with the square of the right part,
 // the work moves into the P phase, which runs while POTRF still leaves SMs idle.
-int split_point(int lo, int hi, int pct) {
+int split_point(int lo, int hi, int pct, int ob) {
   const int n = hi - lo;
   if (n < 16 || pct == 50) return lo + n / 2;
   int mid = lo + (n * pct + 50) / 100;
-  const int al = (mid + GPS_POTRF_OB / 2) / GPS_POTRF_OB * GPS_POTRF_OB;
+  const int al = (mid + ob / 2) / ob * ob;
   if (al > lo && al < hi) mid = al;
   if (mid <= lo) mid = lo + 1;
   if (mid >= hi) mid = hi - 1;
   return mid;
 }
 
-void collect(int lo, int hi, int depth, int pct, std::vector<Node>& out) {
+void collect(int lo, int hi, int depth, int pct, int ob, std::vector<Node>& out) {
   if (hi - lo <= 1) return;
-  const int mid = split_point(lo, hi, pct);
+  const int mid = split_point(lo, hi, pct, ob);
   out.push_back({lo, mid, hi, depth});
-  collect(lo, mid, depth + 1, pct, out);
-  collect(mid, hi, depth + 1, pct, out);
+  collect(lo, mid, depth + 1, pct, ob, out);
+  collect(mid, hi, depth + 1, pct, ob, out);
 }
 
 }  // namespace
@@ -415,11 +415,12 @@ int gps_build_tasks(gps_ctx* ctx, int64_t Np) {
   // block column; the rest of the matrix receives ONE update per outer step with k = OB*128,
   // split into the part the next block column needs (A) and the remainder (B) so that the next
   // block column can be factored on a second stream while B runs (look-ahead).
-  const int OB = GPS_POTRF_OB;
+  const int OB = ctx->potrf_ob;
   const int no = (nb + OB - 1) / OB;
   ctx->potrf_panel.assign(nb, {});
   ctx->potrf_inner.assign(nb, {});
   ctx->potrf_innerB.assign(nb, {});
+  ctx->potrf_innerL.assign(nb, {});
   ctx->potrf_trailA.assign(no, {});
   ctx->potrf_trailA1.assign(no, {});
   ctx->potrf_trailB.assign(no, {});
@@ -438,6 +439,12 @@ int gps_build_tasks(gps_ctx* ctx, int64_t Np) {
       for (int j = k + 1; j < c1; ++j)
         for (int i = c1; i < nb; ++i) push(i * T, j * T, k * T, (k + 1) * T, i, j);
       ctx->potrf_innerB[k].cnt = h.size() - ctx->potrf_innerB[k].off;
+      // the same update of the rows below, left-looking: tile column k receives its block-internal updates in one
+      // launch with k-range [c0, k) tiles right before its panel solve (A/B knob 13)
+      ctx->potrf_innerL[k].off = h.size();
+      if (k > c0)
+        for (int i = c1; i < nb; ++i) push(i * T, k * T, c0 * T, k * T, i, k);
+      ctx->potrf_innerL[k].cnt = h.size() - ctx->potrf_innerL[k].off;
     }
     const int n1 = std::min(nb, c1 + OB);
     // part A of the trailing update = the next block column, its diagonal 512 x 512 block (what the next chain
@@ -460,7 +467,7 @@ int gps_build_tasks(gps_ctx* ctx, int64_t Np) {
   }
   // TRTRI: nodes by depth, deepest first
   std::vector<Node> nodes;
-  collect(0, nb, 0, ctx->trtri_split_pct, nodes);
+  collect(0, nb, 0, ctx->trtri_split_pct, OB, nodes);
   int maxd = -1;
   for (auto& n : nodes) maxd = std::max(maxd, n.depth);
   ctx->trtri_p.clear();
@@ -520,7 +527,7 @@ int gps_build_tasks(gps_ctx* ctx, int64_t Np) {
     std::vector<Node> spine;
     int lo = 0, hi = nb;
     while (hi - lo > 1) {
-      const int mid = split_point(lo, hi, ctx->trtri_split_pct);
+      const int mid = split_point(lo, hi, ctx->trtri_split_pct, OB);
       Node n{lo, mid, hi, 0};
       const int step = (mid - 1) / OB;
       subtree(lo, mid, step);
@@ -658,7 +665,7 @@ struct LaneGuard {
 
 int potrf_lanes(gps_ctx* ctx, double* K, double* Xinv, double* scratch, int64_t Np, bool with_trtri) {
   const int nb = (int)(Np / T);
-  const int OB = GPS_POTRF_OB;
+  const int OB = ctx->potrf_ob;
   const int no = (nb + OB - 1) / OB;
   GPS_CHECK(ensure_potrf_streams(ctx, nb, no));
   // overlap_trtri == 2 (debug): every lane on the caller's stream, so that launches run one at a time and
@@ -706,9 +713,11 @@ int potrf_lanes(gps_ctx* ctx, double* K, double* Xinv, double* scratch, int64_t 
       GPS_CUDA(cudaEventRecord(ctx->tile_events[k], s_pan));
       GPS_CHECK(trace_mark(ctx, 5000 + k, s_pan));
       ctx->stream = s_pan2;
+      if (ctx->potrf_left && ctx->potrf_innerL[k].cnt)    // needs only rows / columns that were final one tile step ago
+        rc = gemm_nt(K, -1.0, 1.0, ctx->potrf_innerL[k], 0, ctx->potrf_innerL[k].cnt);
       GPS_CUDA(cudaStreamWaitEvent(s_pan2, ctx->tile_events[k], 0));
-      rc = gemm_nt(Xinv, 1.0, 0.0, ctx->potrf_panel[k], n_in, ctx->potrf_panel[k].cnt - n_in);
-      if (rc == GPS_OK) rc = gemm_nt(K, -1.0, 1.0, ctx->potrf_innerB[k], 0, ctx->potrf_innerB[k].cnt);
+      if (rc == GPS_OK) rc = gemm_nt(Xinv, 1.0, 0.0, ctx->potrf_panel[k], n_in, ctx->potrf_panel[k].cnt - n_in);
+      if (rc == GPS_OK && !ctx->potrf_left) rc = gemm_nt(K, -1.0, 1.0, ctx->potrf_innerB[k], 0, ctx->potrf_innerB[k].cnt);
       if (rc == GPS_OK) rc = trace_mark(ctx, 6000 + k, s_pan2);
     }
     if (rc != GPS_OK) break;
@@ -786,7 +795,7 @@ int gps_potrf(gps_ctx* ctx, double* K, double* Xinv, int64_t Np) {
 // finalises their operands: the tail of POTRF (serial chain of diagonal blocks, trailing updates too
 // small to fill the GPU) is filled with inversion work that would otherwise start after it.
 int gps_potrf_trtri(gps_ctx* ctx, double* K, double* Xinv, double* scratch, int64_t Np) {
-  const int no = (int)((Np / T + GPS_POTRF_OB - 1) / GPS_POTRF_OB);
+  const int no = (int)((Np / T + ctx->potrf_ob - 1) / ctx->potrf_ob);
   if (ctx->overlap_trtri != 1 || no < 3) {
     GPS_CHECK(gps_potrf(ctx, K, Xinv, Np));
     return gps_trtri(ctx, K, Xinv, scratch, Np);

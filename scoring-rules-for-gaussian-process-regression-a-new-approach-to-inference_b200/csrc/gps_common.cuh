@@ -93,7 +93,7 @@ struct gps_ctx {
   bool loo_valid = false;
   // cached task-list layout for ws_Np (offsets into d_tasks)
   struct Range { size_t off = 0, cnt = 0; };
-  std::vector<Range> potrf_panel, potrf_inner, potrf_innerB, potrf_trailA, potrf_trailA1, potrf_trailB;
+  std::vector<Range> potrf_panel, potrf_inner, potrf_innerB, potrf_innerL, potrf_trailA, potrf_trailA1, potrf_trailB;
   cudaStream_t panel_stream = nullptr;          // high-priority stream for the POTRF look-ahead
   std::vector<cudaEvent_t> potrf_events, tile_events, below_events, trailA1_events;
   cudaStream_t panel2_stream = nullptr;         // POTRF panel work below the diagonal block (high priority)
@@ -110,6 +110,8 @@ struct gps_ctx {
   int cap_trtri = 0, cap_trail = 0;             // A/B knobs 11 / 12: grid caps of the overlapped TRTRI merges / the POTRF trailing updates
   int* d_tickets = nullptr;                     // dynamic-scheduling counters of the persistent launches (ring of 256)
   unsigned ticket_seq = 0;
+  int potrf_ob = GPS_POTRF_OB;                  // POTRF outer block column in tiles (A/B knob 14)
+  int potrf_left = 1;                           // A/B knob 13: rows below the diagonal block updated left-looking (one k <= 896 update per tile column instead of up to seven k = 128 updates; default since round 2: 66.2 -> 65.6 ms)
   int tri_strip = 0;                            // strip policy of the TRTRI merges issued behind POTRF (A/B knob 10; 0 = the normal policy)
   int trtri_split_pct = 50;                     // share of a large TRTRI node's tiles that goes to its left child (A/B knob 9)
   // debug timeline of the factorisation lanes (knob 6): (code, event) pairs, code = lane * 1000 + outer step

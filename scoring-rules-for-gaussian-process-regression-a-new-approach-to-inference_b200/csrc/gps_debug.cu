@@ -155,6 +155,12 @@ int gps_dbg_set_variant(gps_ctx* ctx, int what, int value) {
   else if (what == 10) ctx->tri_strip = value;
   else if (what == 11) ctx->cap_trtri = value;
   else if (what == 12) ctx->cap_trail = value;
+  else if (what == 13) ctx->potrf_left = value;
+  else if (what == 14) {
+    if (value < 2 || value > 32) return gps_fail(ctx, GPS_EINVAL, "dbg_set_variant: outer block outside 2..32 tiles");
+    ctx->potrf_ob = value;
+    ctx->ws_Np = 0;   // task lists and events are rebuilt on the next evaluation
+  }
   else if (what == 9) {
     if (value < 30 || value > 90) return gps_fail(ctx, GPS_EINVAL, "dbg_set_variant: split percentage outside 30..90");
     ctx->trtri_split_pct = value;
