@@ -43,7 +43,8 @@ int gps_dbg_fp64_peak(gps_ctx* ctx, int iters, double* dmma_tflops, double* dfma
  * merges issued behind POTRF (0 = the normal policy, default; 32 / 16 measured slower); what = 11 / 12 run the overlapped TRTRI
  * merges / the POTRF trailing updates as persistent launches with that many CTAs (0 = off, default; measured slower);
  * what = 13: rows below POTRF's diagonal blocks updated left-looking inside a block column (1 = default) or by a rank-128
- * update per tile step (0, the round-1 order); what = 14 sets the POTRF outer block width in tiles (default 8). */
+ * update per tile step (0, the round-1 order); what = 14 sets the POTRF outer block width in tiles (default 8); what = 15
+ * releases the X phases of the inversion tree's right spine row group by row group (0 = default; 1 measured slower). */
 int gps_dbg_set_variant(gps_ctx* ctx, int what, int value);
 
 /* Timeline of the factorisation lanes of the last full-GP evaluation (arm with gps_dbg_set_variant(ctx, 6, 1)):

@@ -501,10 +501,11 @@ int gps_build_tasks(gps_ctx* ctx, int64_t Np) {
       for (int j = n.lo; j < n.mid; ++j)
         for (int i = n.mid; i < n.hi; ++i) push(i * T, j * T, j * T, n.mid * T, i, j);
     };
-    auto x_tasks = [&](const Node& n) {
-      for (int i = n.hi - 1; i >= n.mid; --i)
+    auto x_rows = [&](const Node& n, int r0, int r1) {       // rows [r0, r1) of the node's X21 = -X22 * P
+      for (int i = r1 - 1; i >= r0; --i)
         for (int j = n.lo; j < n.mid; ++j) push(i * T, j * T, n.mid * T, (i + 1) * T, i, j);
     };
+    auto x_tasks = [&](const Node& n) { x_rows(n, n.mid, n.hi); };
     auto emit = [&](int step, int phase, size_t off) {
       gps_ctx::TriLaunch tl{step, phase, {}};
       tl.r.off = off;
@@ -526,6 +527,12 @@ int gps_build_tasks(gps_ctx* ctx, int64_t Np) {
     // walk down the right spine of the tree
     std::vector<Node> spine;
     int lo = 0, hi = nb;
+    // Row-wise release of the spine's X phases (knob 15): rows [lo, mid) of EVERY ancestor's X21 need only the
+    // ancestor's P (released long ago), the inverse of the diagonal block [lo, mid) (the sub-tree just emitted) and
+    // the same rows of the deeper ancestors' X21 — so they go out here, deepest ancestor first, instead of after
+    // the whole right half is inverted.  The late work after POTRF's last step shrinks from the top node's full X
+    // phase (39 % of all inversion flops) to the last row group's share.
+    const bool rowwise = ctx->trtri_rowwise != 0;
     while (hi - lo > 1) {
       const int mid = split_point(lo, hi, ctx->trtri_split_pct, OB);
       Node n{lo, mid, hi, 0};
@@ -534,12 +541,19 @@ int gps_build_tasks(gps_ctx* ctx, int64_t Np) {
       size_t off = h.size();
       p_tasks(n);
       emit(step, 0, off);
+      if (rowwise)
+        for (int s = (int)spine.size() - 1; s >= 0; --s) {
+          off = h.size();
+          x_rows(spine[s], lo, mid);
+          emit(step, 1, off);
+        }
       spine.push_back(n);
       lo = mid;
     }
     for (int s = (int)spine.size() - 1; s >= 0; --s) {
       size_t off = h.size();
-      x_tasks(spine[s]);
+      if (rowwise) x_rows(spine[s], lo, hi);          // the last leaf's rows
+      else x_tasks(spine[s]);
       emit((spine[s].hi - 1) / OB, 1, off);
     }
   }

@@ -110,6 +110,7 @@ struct gps_ctx {
   int cap_trtri = 0, cap_trail = 0;             // A/B knobs 11 / 12: grid caps of the overlapped TRTRI merges / the POTRF trailing updates
   int* d_tickets = nullptr;                     // dynamic-scheduling counters of the persistent launches (ring of 256)
   unsigned ticket_seq = 0;
+  int trtri_rowwise = 0;                        // A/B knob 15: X phases of the inversion tree's right spine released row group by row group
   int potrf_ob = GPS_POTRF_OB;                  // POTRF outer block column in tiles (A/B knob 14)
   int potrf_left = 1;                           // A/B knob 13: rows below the diagonal block updated left-looking (one k <= 896 update per tile column instead of up to seven k = 128 updates; default since round 2: 66.2 -> 65.6 ms)
   int tri_strip = 0;                            // strip policy of the TRTRI merges issued behind POTRF (A/B knob 10; 0 = the normal policy)

@@ -156,6 +156,10 @@ int gps_dbg_set_variant(gps_ctx* ctx, int what, int value) {
   else if (what == 11) ctx->cap_trtri = value;
   else if (what == 12) ctx->cap_trail = value;
   else if (what == 13) ctx->potrf_left = value;
+  else if (what == 15) {
+    ctx->trtri_rowwise = value;
+    ctx->ws_Np = 0;
+  }
   else if (what == 14) {
     if (value < 2 || value > 32) return gps_fail(ctx, GPS_EINVAL, "dbg_set_variant: outer block outside 2..32 tiles");
     ctx->potrf_ob = value;
