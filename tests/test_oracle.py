@@ -177,3 +177,21 @@ def test_kspace_prototype_matches_goldens(name, score):
         grad = np.concatenate([[grad[0]], [grad[1:-1].sum()], [grad[-1]]])
     assert relerr(grad, ref) <= GRAD_TOL
     assert relerr(gU, g["grad_u_" + score]) <= GRAD_TOL
+
+
+@pytest.mark.parametrize("kind", ["dss", "kc"])
+@pytest.mark.parametrize("m_ind,n,d", [(40, 240, 3), (70, 316, 8)])
+def test_woodbury_block_objectives_match_dense_oracle_beyond_m32(m_ind, n, d, kind):
+    """The goldens pin the block objectives at the scripts' M = 20; the GPU parity tests of the matrix form
+    (tests/test_gpu_fitc_large.py) use the O(N M^2) Woodbury restatement at M = 33 ... 200 as their checker, so it is
+    pinned here against the dense big_Q restatement (oracle/gp_oracle.py, K20:538-587 / 669-720 line by line) at
+    M > 32, fold sizes 60 and 79."""
+    rng = np.random.default_rng(500 + m_ind)
+    X = rng.uniform(-1, 1, (n, d))
+    y = (np.sin(X @ rng.standard_normal(d)) + 0.1 * rng.standard_normal(n)).reshape(-1, 1)
+    U = rng.uniform(-1, 1, (m_ind, d))
+    theta = np.concatenate([[0.3], np.log(rng.uniform(0.8, 2.0, d)), [-2.0]])
+    dv, dg, dgu = O.fitc_obj_grad(X, y, U, theta, kind)[:3]
+    wv, wg, wgu = WB.fitc_block_obj_grad(X, y, U, theta, kind)
+    assert abs(wv - dv) <= 1e-10 * abs(dv)
+    assert relerr(wg, dg) <= 1e-7 and relerr(wgu, dgu) <= 1e-7
