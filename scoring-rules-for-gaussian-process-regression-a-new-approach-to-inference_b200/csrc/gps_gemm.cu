@@ -34,11 +34,11 @@ namespace {
 // MINB = CTAs per SM the register budget is sized for.
 template <int TM_, int BK_, int STAGES_, int WM_, int WN_, bool PIPE_, int MINB_>
 struct GemmCfg {
-  static constexpr int TM = TM_, TN = 128;
+  static constexpr int TM = TM_;                                 // x 128 columns
   static constexpr int BK = BK_;
   static constexpr int STAGES = STAGES_;
   static constexpr bool PIPE = PIPE_;
-  static constexpr int WM = WM_, WN = WN_, MINB = MINB_;
+  static constexpr int WN = WN_, MINB = MINB_;
   static constexpr int THREADS = 32 * WM_ * WN_;
   static constexpr int MF = TM_ / WM_ / 8, NF = 128 / WN_ / 8;   // m8n8k4 fragments per warp tile
   static constexpr int SPLIT = 128 / TM_;
